@@ -1,0 +1,117 @@
+"""Track XML ("discrete" format) -> per-node constants for the collocation kernels.
+
+Host-side mirror of `create_track_from_xml` (src/main/c/fastestlapc.cpp:176-203):
+  Circuit_preprocessor(Xml_document&) loader      src/core/applications/circuit_preprocessor.hpp:64-258
+  Track_by_polynomial(const Circuit_preprocessor&) src/core/vehicles/track_by_polynomial.hpp:78-153
+The reference builds order-1 (piecewise linear) polynomials of the arclength for the centreline, yaw, yaw',
+pitch, roll, pitch', roll', nl and nr; closed tracks get one closing sample (L, value[0]) appended, the yaw included
+(no 2 pi unwrap, track_by_polynomial.hpp:115).  pitch'/roll' are fed from the XML arrays dpitch_dot/droll_dot
+(track_by_polynomial.hpp:87-88), which is what the reference's golden files were produced with.
+The track is evaluated in plain doubles and never differentiated (road_curvilinear.hpp:104-135): everything the
+kernels need is a per-node constant, computed here once per mesh.
+"""
+import xml.etree.ElementTree as ET
+import numpy as np
+
+
+def _vec(node):
+    return np.array([float(t) for t in node.text.replace("\n", " ").split(",") if t.strip()], dtype=np.float64)
+
+
+class Track:
+    def __init__(self, s, x, y, z, yaw, pitch, roll, yaw_dot, dpitch, droll, nl, nr, track_length, closed, with_elevation, name=""):
+        self.name = name
+        self.closed = bool(closed)
+        self.with_elevation = bool(with_elevation)
+        self.track_length = float(track_length)
+        self.s_data = np.asarray(s, dtype=np.float64)
+        arrays = dict(x=x, y=y, z=z, yaw=yaw, pitch=pitch, roll=roll, yaw_dot=yaw_dot, dpitch=dpitch, droll=droll, nl=nl, nr=nr)
+        sk = self.s_data
+        if self.closed:
+            sk = np.append(sk, self.track_length)
+        self._s = sk
+        self._a = {}
+        for k, v in arrays.items():
+            v = np.asarray(v, dtype=np.float64)
+            if self.closed:
+                v = np.append(v, v[0])
+            self._a[k] = v
+
+    @property
+    def n_points(self):
+        return len(self.s_data)
+
+    def has_elevation(self):
+        # track_by_polynomial.hpp:156-160
+        a = self._a
+        return bool(np.any(a["pitch"] != 0.0) or np.any(a["roll"] != 0.0) or np.any(np.abs(a["z"]) >= 1.0e-12)
+                    or np.any(a["dpitch"] != 0.0) or np.any(a["droll"] != 0.0))
+
+    def __call__(self, key, s):
+        """Piecewise-linear evaluation (lion sPolynomial of order 1)."""
+        return np.interp(np.asarray(s, dtype=np.float64), self._s, self._a[key])
+
+    def left_track_limit(self, s):
+        return self("nl", s)
+
+    def right_track_limit(self, s):
+        return self("nr", s)
+
+    def node_data(self, s):
+        """[n][6] array: theta, mu, phi, dtheta/ds, dmu/ds, dphi/ds at the mesh nodes `s`."""
+        s = np.asarray(s, dtype=np.float64)
+        out = np.empty((len(s), 6))
+        for c, k in enumerate(("yaw", "pitch", "roll", "yaw_dot", "dpitch", "droll")):
+            out[:, c] = self(k, s)
+        return out
+
+    def position(self, s):
+        return np.stack([self("x", s), self("y", s), self("z", s)], axis=-1)
+
+
+def track_from_xml(source, name=""):
+    text = source if source.lstrip().startswith("<") else open(source).read()
+    root = ET.fromstring(text)
+    if root.attrib.get("format") != "discrete":
+        raise ValueError('Track should be of type "discrete"')
+    ttype = root.attrib.get("type")
+    if ttype not in ("open", "closed"):
+        raise ValueError('Incorrect track type, should be "open" or "closed"')
+    dims = root.attrib.get("dimensions")
+    if dims not in ("2", "3"):
+        raise ValueError("Track XML file must have a dimensions attribute equal to 2 or 3")
+    elev = dims == "3"
+    data = root.find("data")
+    n = int(data.attrib["number_of_points"])
+    s = _vec(data.find("arclength"))
+    x = _vec(data.find("centerline/x"))
+    y = _vec(data.find("centerline/y"))
+    z = _vec(data.find("centerline/z")) if elev else np.zeros(n)
+    yaw = _vec(data.find("yaw"))
+    yaw_dot = _vec(data.find("yaw_dot"))
+    nl = _vec(data.find("nl"))
+    nr = _vec(data.find("nr"))
+    if elev:
+        pitch, roll = _vec(data.find("pitch")), _vec(data.find("roll"))
+        dpitch, droll = _vec(data.find("dpitch_dot")), _vec(data.find("droll_dot"))
+    else:
+        pitch = roll = dpitch = droll = np.zeros(n)
+    for a in (s, x, y, z, yaw, yaw_dot, nl, nr, pitch, roll, dpitch, droll):
+        if len(a) != n:
+            raise ValueError("track arrays must have number_of_points entries")
+    length = float(root.find("header/track_length").text)
+    # kerbs (track_by_polynomial.hpp:93-108) widen nl / nr where a used kerb covers the sample
+    kerbs = root.find("kerbs")
+    if kerbs is not None:
+        for side, arr in (("left", nl), ("right", nr)):
+            node = kerbs.find(side)
+            if node is None:
+                continue
+            for kerb in node.findall("kerb"):
+                used = (kerb.findtext("used") or "true").strip().lower() == "true"
+                if not used:
+                    continue
+                s0, s1, wd = float(kerb.findtext("arclength_start")), float(kerb.findtext("arclength_finish")), float(kerb.findtext("width"))
+                mask = (s > s0 - 1.0e-12) & (s < s1 + 1.0e-12)
+                arr[mask] += wd
+    return Track(s, x, y, z, yaw, pitch, roll, yaw_dot, dpitch, droll, nl, nr, length, ttype == "closed", elev, name)

@@ -1,0 +1,102 @@
+"""Vehicle XML -> flat parameter vector.
+
+Host-side mirror of the reference's `create_vehicle_from_xml` (src/main/c/fastestlapc.cpp:103-142): the root
+attribute `type` selects the model ("f1-3dof" | "kart-6dof"), every parameter is addressed by its XML path exactly as
+the reference's DECLARE_PARAMS tables do (src/core/chassis/chassis.h:255-270, chassis_car_3dof.h, axle_car_3dof.h,
+tire_pacejka.h:329-342, chassis_car_6dof.h, axle_car_6dof.h).  The order of the vector is the ABI shared with the CUDA
+kernels (include/fastestlap_b200.h: FL_F1_* / FL_KART_* enums).
+"""
+import xml.etree.ElementTree as ET
+import numpy as np
+
+MODEL_F1 = 0
+MODEL_KART = 1
+
+_F1_TIRE = ["radius", "reference-load-1", "reference-load-2", "mu-x-max-1", "mu-x-max-2", "kappa-max-1", "kappa-max-2",
+            "mu-y-max-1", "mu-y-max-2", "lambda-max-1", "lambda-max-2", "Qx", "Qy"]
+
+F1_PARAM_PATHS = (
+    ["chassis/mass", "chassis/inertia/Ixx", "chassis/inertia/Iyy", "chassis/inertia/Izz",
+     "chassis/aerodynamics/rho", "chassis/aerodynamics/area", "chassis/aerodynamics/cd", "chassis/aerodynamics/cl",
+     "chassis/com/x", "chassis/com/y", "chassis/com/z",
+     "chassis/front_axle/x", "chassis/front_axle/z", "chassis/rear_axle/x", "chassis/rear_axle/z",
+     "chassis/pressure_center/x", "chassis/pressure_center/y", "chassis/pressure_center/z",
+     "chassis/brake_bias", "chassis/roll_balance_coefficient", "chassis/Fz_max_ref2",
+     "front-axle/track", "front-axle/inertia", "front-axle/smooth_throttle_coeff", "front-axle/brakes/max_torque",
+     "rear-axle/track", "rear-axle/inertia", "rear-axle/smooth_throttle_coeff", "rear-axle/differential_stiffness",
+     "rear-axle/brakes/max_torque", "rear-axle/engine/maximum-power", "rear-axle/boost/maximum-power"]
+    + ["front-tire/" + p for p in _F1_TIRE] + ["rear-tire/" + p for p in _F1_TIRE])
+
+_KART_TIRE = ["radius", "radial-stiffness", "radial-damping", "nominal-vertical-load", "lambdaFz0", "Fz-max-ref2",
+              "longitudinal/pure/pCx1", "longitudinal/pure/pDx1", "longitudinal/pure/pEx1", "longitudinal/pure/pKx1",
+              "longitudinal/pure/pKx2", "longitudinal/pure/pKx3", "longitudinal/combined/rBx1", "longitudinal/combined/rCx1",
+              "lateral/pure/pCy1", "lateral/pure/pDy1", "lateral/pure/pEy1", "lateral/pure/pKy1", "lateral/pure/pKy2",
+              "lateral/pure/pKy4", "lateral/combined/rBy1", "lateral/combined/rCy1"]
+
+KART_PARAM_PATHS = (
+    ["chassis/mass", "chassis/inertia/Ixx", "chassis/inertia/Iyy", "chassis/inertia/Izz", "chassis/inertia/Ixz",
+     "chassis/aerodynamics/rho", "chassis/aerodynamics/cd", "chassis/aerodynamics/cl", "chassis/aerodynamics/area",
+     "chassis/com/x", "chassis/com/y", "chassis/com/z",
+     "chassis/front_axle/x", "chassis/front_axle/z", "chassis/rear_axle/x", "chassis/rear_axle/z",
+     "front-axle/track", "front-axle/stiffness/chassis", "front-axle/stiffness/antiroll",
+     "front-axle/beta-steering/left", "front-axle/beta-steering/right",
+     "rear-axle/track", "rear-axle/stiffness/chassis", "rear-axle/stiffness/antiroll", "rear-axle/inertia",
+     "rear-axle/smooth_throttle_coeff", "rear-axle/brakes/max_torque", "rear-axle/engine/maximum-power"]
+    + ["front-tire/" + p for p in _KART_TIRE] + ["rear-tire/" + p for p in _KART_TIRE])
+
+_VEC3 = {"x": 0, "y": 1, "z": 2}
+
+
+def _lookup(root, path):
+    """Value of `path` below the <vehicle> root.  Three-vectors may be written either as <x>,<y>,<z> children
+    (F1 database files) or as one whitespace separated text node (kart database files)."""
+    node = root.find(path)
+    if node is not None and node.text is not None and node.text.strip():
+        return float(node.text.split()[0]) if len(node.text.split()) == 1 else None
+    parent_path, _, leaf = path.rpartition("/")
+    parent = root.find(parent_path)
+    if parent is not None and leaf in _VEC3 and parent.text and len(parent.text.split()) == 3:
+        return float(parent.text.split()[_VEC3[leaf]])
+    return None
+
+
+class Vehicle:
+    def __init__(self, model, params, name=""):
+        self.model = model
+        self.params = np.ascontiguousarray(params, dtype=np.float64)
+        self.name = name
+        self.paths = F1_PARAM_PATHS if model == MODEL_F1 else KART_PARAM_PATHS
+
+    def copy(self):
+        return Vehicle(self.model, self.params.copy(), self.name)
+
+    def set_parameter(self, path, value):
+        """Mirror of vehicle_set_parameter (fastestlapc.cpp): `path` is "vehicle/..." as in the reference."""
+        key = path[len("vehicle/"):] if path.startswith("vehicle/") else path
+        if key not in self.paths:
+            raise KeyError('Parameter "%s" was not found' % path)
+        self.params[self.paths.index(key)] = float(value)
+
+    def get_parameter(self, path):
+        key = path[len("vehicle/"):] if path.startswith("vehicle/") else path
+        return float(self.params[self.paths.index(key)])
+
+
+def vehicle_from_xml(source, name=""):
+    """`source` is a file name or an XML string."""
+    text = source if source.lstrip().startswith("<") else open(source).read()
+    root = ET.fromstring(text)
+    vtype = root.attrib.get("type")
+    if vtype == "f1-3dof":
+        model, paths = MODEL_F1, F1_PARAM_PATHS
+    elif vtype == "kart-6dof":
+        model, paths = MODEL_KART, KART_PARAM_PATHS
+    else:
+        raise ValueError('vehicle type "%s" not recognized' % vtype)
+    values = []
+    for p in paths:
+        v = _lookup(root, p)
+        if v is None:
+            raise ValueError('vehicle parameter "%s" is missing' % p)
+        values.append(v)
+    return Vehicle(model, values, name)

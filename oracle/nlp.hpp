@@ -1,0 +1,386 @@
+// TEST INFRASTRUCTURE ONLY -- part of the CPU oracle (see oracle/README.md).
+//
+// CPU restatement of the collocation NLP the reference hands to Ipopt:
+//   Optimal_laptime::FG_direct<closed>::compute      /root/reference/src/core/applications/optimal_laptime.hpp:1226-1420
+//   Optimal_laptime::FG_derivative<closed>::compute  /root/reference/src/core/applications/optimal_laptime.hpp:1426-1657
+// together with the derivative objects CppAD would produce from its tape (eval_grad_f, eval_jac_g, eval_h of
+// lion::ipopt_cppad_solve, call site optimal_laptime.hpp:546-551).  Entries are emitted as (row, col, value)
+// triplets; parity is always checked by (row, col), never by position.
+#ifndef ORACLE_NLP_HPP
+#define ORACLE_NLP_HPP
+
+#include <vector>
+#include <cstring>
+#include "jet.hpp"
+#include "f1_model.hpp"
+#include "kart_model.hpp"
+
+namespace oracle {
+
+enum { MODEL_F1 = 0, MODEL_KART = 1 };
+enum { FORM_DIRECT = 0, FORM_DERIVATIVE = 1 };
+
+struct Desc
+{
+    int model, form, closed, elevation, n_points, kart_direct_torque;
+    const double* s;            // [n_points]
+    double track_length;
+    const double* track;        // [n_points][6]: theta, mu, phi, dtheta/ds, dmu/ds, dphi/ds
+    const double* params;       // model parameter vector
+    double sigma;
+    double dissipation[2];      // of the two full-mesh controls (F1: delta, throttle; kart: delta, throttle/torque)
+    const double* q0;           // open problems: inputs of node 0   [NIN]
+    const double* u0;           // open problems: controls of node 0 [NCTRL]
+    const double* du0;          // open problems, derivative form: dcontrols_dt of the full-mesh controls at node 0 [2]
+    const double* ctrl_default; // default value of every control [NCTRL] (used for the not-optimised ones)
+};
+
+constexpr int MAX_ROWS = 14;
+
+// What one node contributes: everything is a function of the node's own variables only.
+template <int NV>
+struct NodeRows
+{
+    Jet2<NV> q[MAX_ROWS];      // states of the time-derivative equations
+    Jet2<NV> qd[MAX_ROWS];     // dstates_dt * dt/ds of the time-derivative equations
+    Jet2<NV> alg[4];           // algebraic rows: dstates_dt[eq] / (dt/ds)
+    Jet2<NV> ext[6];           // extra constraints
+    Jet2<NV> dtds;
+    Jet2<NV> cdot[2];          // derivative form: dcontrol_dt * dt/ds of the full-mesh controls
+    Jet2<NV> ctrl[2];          // the full-mesh controls themselves
+    Jet2<NV> dctrl[2];         // derivative form: dcontrols_dt variables
+};
+
+struct Layout
+{
+    int nv;          // variables per node
+    int n_td, n_alg, n_ext, n_fm, n_ctrl_rows;
+    int ncpe;        // constraints per element
+    int td_ids[MAX_ROWS], alg_ids[4];
+    int ctrl_pos[2]; // position of the full-mesh controls within the node variables
+    int dctrl_pos[2];
+    int n_nodes_var; // nodes that carry variables
+    int n_elements;
+    int n, m;
+};
+
+inline Layout make_layout(const Desc& d)
+{
+    Layout L;
+    std::memset(&L, 0, sizeof(L));
+    const bool deriv = d.form == FORM_DERIVATIVE;
+    if (d.model == MODEL_F1)
+    {
+        // limebeer2014f1.h:185-225 ; test/vehicles/limebeer2014f1_test.cpp:176-198
+        if (d.elevation)
+        {
+            const int ids[13] = {0,1,2,3,4,5,6,7,8,9,10,12,13};
+            L.n_td = 13; for (int i = 0; i < 13; ++i) L.td_ids[i] = ids[i];
+            L.n_alg = 0;
+        }
+        else
+        {
+            const int ids[9] = {0,1,2,3,4,5,6,12,13};
+            L.n_td = 9; for (int i = 0; i < 9; ++i) L.td_ids[i] = ids[i];
+            L.n_alg = 4; for (int i = 0; i < 4; ++i) L.alg_ids[i] = 7 + i;
+        }
+        L.n_ext = F1_NEXTRA;
+        L.n_fm = 2;
+        L.nv = (F1_NIN - 1) + 2 + (deriv ? 2 : 0);
+        L.ctrl_pos[0] = 13; L.ctrl_pos[1] = 14;
+        L.dctrl_pos[0] = 15; L.dctrl_pos[1] = 16;
+    }
+    else
+    {
+        // dynamic_model_car.h:170-188: all kart equations are time derivatives except time itself
+        const int ids[12] = {0,1,2,3,4,5,6,7,8,9,11,12};
+        L.n_td = 12; for (int i = 0; i < 12; ++i) L.td_ids[i] = ids[i];
+        L.n_alg = 0;
+        L.n_ext = KART_NEXTRA;
+        L.n_fm = 2;
+        L.nv = (KART_NIN - 1) + 2 + (deriv ? 2 : 0);
+        L.ctrl_pos[0] = 12; L.ctrl_pos[1] = 13;
+        L.dctrl_pos[0] = 14; L.dctrl_pos[1] = 15;
+    }
+    L.n_ctrl_rows = deriv ? L.n_fm : 0;
+    L.ncpe = L.n_td + L.n_alg + L.n_ext + L.n_ctrl_rows;
+    L.n_nodes_var = d.closed ? d.n_points : d.n_points - 1;
+    L.n_elements = d.closed ? d.n_points : d.n_points - 1;      // optimal_laptime.hpp:73-74
+    L.n = L.n_nodes_var * L.nv;
+    L.m = L.n_elements * L.ncpe;
+    return L;
+}
+
+// Evaluate one node.  xn = the node's NV variables (or nullptr for the fixed first node of an open problem).
+template <int NV>
+inline void eval_node(const Desc& d, const Layout& L, int i, const double* xn, NodeRows<NV>& R)
+{
+    typedef Jet2<NV> J;
+    const bool deriv = d.form == FORM_DERIVATIVE;
+    TrackNode tk;
+    const double* t = d.track + 6 * i;
+    tk.theta = t[0]; tk.mu = t[1]; tk.phi = t[2]; tk.dtheta = t[3]; tk.dmu = t[4]; tk.dphi = t[5];
+
+    if (d.model == MODEL_F1)
+    {
+        J q[F1_NIN], u[F1_NCTRL];
+        for (int c = 0; c < F1_NCTRL; ++c) u[c] = J(d.ctrl_default[c]);
+        if (xn)
+        {
+            // optimal_laptime.hpp:1269-1285: inputs before time, inputs after time, full-mesh controls
+            int k = 0;
+            for (int j = 0; j < F1_ITIME; ++j, ++k) q[j] = J::variable(xn[k], k);
+            q[F1_ITIME] = J(0.0);
+            for (int j = F1_ITIME + 1; j < F1_NIN; ++j, ++k) q[j] = J::variable(xn[k], k);
+            u[F1_CDELTA] = J::variable(xn[k], k); ++k;
+            u[F1_CTHROTTLE] = J::variable(xn[k], k); ++k;
+            if (deriv) { R.dctrl[0] = J::variable(xn[k], k); ++k; R.dctrl[1] = J::variable(xn[k], k); ++k; }
+        }
+        else
+        {
+            for (int j = 0; j < F1_NIN; ++j) q[j] = J(d.q0[j]);
+            for (int c = 0; c < F1_NCTRL; ++c) u[c] = J(d.u0[c]);
+            if (deriv) { R.dctrl[0] = J(d.du0[0]); R.dctrl[1] = J(d.du0[1]); }
+        }
+        F1Out<J> o;
+        f1_car(q, u, d.params, tk, o);
+        for (int r = 0; r < L.n_td; ++r) { R.q[r] = o.states[L.td_ids[r]]; R.qd[r] = o.dstates[L.td_ids[r]]; }
+        for (int r = 0; r < L.n_alg; ++r) R.alg[r] = o.dstates[L.alg_ids[r]] / o.dtds;      // optimal_laptime.hpp:1341
+        for (int r = 0; r < L.n_ext; ++r) R.ext[r] = o.extra[r];
+        R.dtds = o.dstates[F1_ITIME];
+        R.ctrl[0] = u[F1_CDELTA]; R.ctrl[1] = u[F1_CTHROTTLE];
+    }
+    else
+    {
+        J q[KART_NIN], u[KART_NCTRL];
+        for (int c = 0; c < KART_NCTRL; ++c) u[c] = J(d.ctrl_default[c]);
+        if (xn)
+        {
+            int k = 0;
+            for (int j = 0; j < KART_ITIME; ++j, ++k) q[j] = J::variable(xn[k], k);
+            q[KART_ITIME] = J(0.0);
+            for (int j = KART_ITIME + 1; j < KART_NIN; ++j, ++k) q[j] = J::variable(xn[k], k);
+            u[0] = J::variable(xn[k], k); ++k;
+            u[1] = J::variable(xn[k], k); ++k;
+            if (deriv) { R.dctrl[0] = J::variable(xn[k], k); ++k; R.dctrl[1] = J::variable(xn[k], k); ++k; }
+        }
+        else
+        {
+            for (int j = 0; j < KART_NIN; ++j) q[j] = J(d.q0[j]);
+            for (int c = 0; c < KART_NCTRL; ++c) u[c] = J(d.u0[c]);
+            if (deriv) { R.dctrl[0] = J(d.du0[0]); R.dctrl[1] = J(d.du0[1]); }
+        }
+        KartOut<J> o;
+        kart_car(q, u, d.params, tk, d.kart_direct_torque != 0, true, o);
+        for (int r = 0; r < L.n_td; ++r) { R.q[r] = o.states[L.td_ids[r]]; R.qd[r] = o.dstates[L.td_ids[r]]; }
+        for (int r = 0; r < L.n_ext; ++r) R.ext[r] = o.extra[r];
+        R.dtds = o.dstates[KART_ITIME];
+        R.ctrl[0] = u[0]; R.ctrl[1] = u[1];
+    }
+    if (deriv)
+        for (int c = 0; c < L.n_fm; ++c) R.cdot[c] = R.dctrl[c] * R.dtds;     // optimal_laptime.hpp:1580-1581
+}
+
+struct Triplets
+{
+    std::vector<int> row, col;
+    std::vector<double> val;
+    void add(int r, int c, double v) { row.push_back(r); col.push_back(c); val.push_back(v); }
+};
+
+struct EvalOut
+{
+    double f;
+    std::vector<double> grad, g;
+    Triplets jac, hess;     // hess: lower triangle (row >= col), duplicates must be summed
+};
+
+template <int NV>
+void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj_factor, bool want_derivs, EvalOut& out)
+{
+    typedef Jet2<NV> J;
+    const Layout L = make_layout(d);
+    const int np = d.n_points;
+    const bool deriv = d.form == FORM_DERIVATIVE;
+    const double sigma = d.sigma;
+    std::vector<NodeRows<NV>> R(np);
+
+    auto var0 = [&](int node) { return d.closed ? node * NV : (node - 1) * NV; };     // -NV for the fixed node of open problems
+    #pragma omp parallel for schedule(static)
+    for (int i = 0; i < np; ++i)
+    {
+        const double* xn = (d.closed || i > 0) ? x + var0(i) : nullptr;
+        eval_node<NV>(d, L, i, xn, R[i]);
+    }
+
+    out.f = 0.0;
+    out.g.assign(L.m, 0.0);
+    out.grad.assign(L.n, 0.0);
+    out.jac = Triplets();
+    out.hess = Triplets();
+    // per-node Hessian accumulators (lower triangle)
+    std::vector<double> H;
+    if (want_derivs) H.assign((size_t)np * NV * NV, 0.0);
+
+    auto add_grad = [&](int node, const J& a, double c) {
+        if (!want_derivs) return;
+        if (!d.closed && node == 0) return;
+        double* gr = out.grad.data() + var0(node);
+        for (int k = 0; k < NV; ++k) gr[k] += c * a.g[k];
+    };
+    auto add_hess = [&](int node, const J& a, double c) {
+        if (!want_derivs) return;
+        if (!d.closed && node == 0) return;
+        double* Hn = H.data() + (size_t)node * NV * NV;
+        for (int r = 0; r < NV; ++r) for (int cc = 0; cc <= r; ++cc) Hn[r * NV + cc] += c * a.h[r][cc];
+    };
+    auto add_jac = [&](int row, int node, const J& a, double c) {
+        if (!want_derivs) return;
+        if (!d.closed && node == 0) return;
+        const int c0 = var0(node);
+        for (int k = 0; k < NV; ++k) out.jac.add(row, c0 + k, c * a.g[k]);
+    };
+
+    for (int e = 0; e < L.n_elements; ++e)
+    {
+        // element e joins node i -> j ; the closing element of a closed lap joins n-1 -> 0 with h = L - s.back()
+        const bool closing = d.closed && e == np - 1;
+        const int i = closing ? np - 1 : e;
+        const int j = closing ? 0 : e + 1;
+        const double h = closing ? d.track_length - d.s[np - 1] : d.s[j] - d.s[i];
+        const NodeRows<NV>& A = R[i];
+        const NodeRows<NV>& B = R[j];
+        int row = e * L.ncpe;
+
+        // objective: integral of time (optimal_laptime.hpp:1333, 1378)
+        out.f += h * ((1.0 - sigma) * A.dtds.v + sigma * B.dtds.v);
+        add_grad(i, A.dtds, h * (1.0 - sigma));
+        add_grad(j, B.dtds, h * sigma);
+        add_hess(i, A.dtds, obj_factor * h * (1.0 - sigma));
+        add_hess(j, B.dtds, obj_factor * h * sigma);
+
+        // control penalisation
+        for (int c = 0; c < L.n_fm; ++c)
+        {
+            const double diss = d.dissipation[c];
+            if (!deriv)
+            {
+                // optimal_laptime.hpp:1362-1366, 1401-1402
+                const double du = B.ctrl[c].v - A.ctrl[c].v;
+                const double derivative = du / h;
+                out.f += diss * (derivative * derivative) * h;
+                if (want_derivs)
+                {
+                    const int pi = var0(i) + L.ctrl_pos[c], pj = var0(j) + L.ctrl_pos[c];
+                    const bool vi = d.closed || i > 0;
+                    if (vi) out.grad[pi] += -2.0 * diss * du / h;
+                    out.grad[pj] += 2.0 * diss * du / h;
+                    const double hv = obj_factor * 2.0 * diss / h;
+                    if (vi) out.hess.add(pi, pi, hv);
+                    out.hess.add(pj, pj, hv);
+                    if (vi) out.hess.add(pi > pj ? pi : pj, pi > pj ? pj : pi, -hv);
+                }
+            }
+            else
+            {
+                // optimal_laptime.hpp:1553 (note the reference's dcontrols_dt[i-i] = dcontrols_dt[0]) and :1611
+                const int il = closing ? np - 1 : 0;
+                const J& dl = R[il].dctrl[c];
+                const J& dr = B.dctrl[c];
+                out.f += 0.5 * diss * (dl.v * dl.v + dr.v * dr.v) * h;
+                if (want_derivs)
+                {
+                    const int pl = var0(il) + L.dctrl_pos[c], pr = var0(j) + L.dctrl_pos[c];
+                    const bool vl = d.closed || il > 0;
+                    if (vl) { out.grad[pl] += diss * dl.v * h; out.hess.add(pl, pl, obj_factor * diss * h); }
+                    out.grad[pr] += diss * dr.v * h;
+                    out.hess.add(pr, pr, obj_factor * diss * h);
+                }
+            }
+        }
+
+        // trapezoidal rows (optimal_laptime.hpp:1337-1338, 1383-1384)
+        for (int r = 0; r < L.n_td; ++r, ++row)
+        {
+            out.g[row] = B.q[r].v - A.q[r].v - h * ((1.0 - sigma) * A.qd[r].v + sigma * B.qd[r].v);
+            const double lam = lambda ? lambda[row] : 0.0;
+            add_jac(row, i, A.q[r], -1.0);  add_jac(row, i, A.qd[r], -h * (1.0 - sigma));
+            add_jac(row, j, B.q[r], 1.0);   add_jac(row, j, B.qd[r], -h * sigma);
+            add_hess(i, A.q[r], -lam);      add_hess(i, A.qd[r], -lam * h * (1.0 - sigma));
+            add_hess(j, B.q[r], lam);       add_hess(j, B.qd[r], -lam * h * sigma);
+        }
+        // algebraic rows (optimal_laptime.hpp:1340-1341, 1386-1387)
+        for (int r = 0; r < L.n_alg; ++r, ++row)
+        {
+            out.g[row] = B.alg[r].v;
+            const double lam = lambda ? lambda[row] : 0.0;
+            add_jac(row, j, B.alg[r], 1.0);
+            add_hess(j, B.alg[r], lam);
+        }
+        // extra constraints (optimal_laptime.hpp:1344-1347, 1390-1394)
+        for (int r = 0; r < L.n_ext; ++r, ++row)
+        {
+            out.g[row] = B.ext[r].v;
+            const double lam = lambda ? lambda[row] : 0.0;
+            add_jac(row, j, B.ext[r], 1.0);
+            add_hess(j, B.ext[r], lam);
+        }
+        // derivative form: control rate rows (optimal_laptime.hpp:1573-1583, 1632-1641)
+        for (int c = 0; c < L.n_ctrl_rows; ++c, ++row)
+        {
+            out.g[row] = B.ctrl[c].v - A.ctrl[c].v - h * ((1.0 - sigma) * A.cdot[c].v + sigma * B.cdot[c].v);
+            const double lam = lambda ? lambda[row] : 0.0;
+            add_jac(row, i, A.ctrl[c], -1.0); add_jac(row, i, A.cdot[c], -h * (1.0 - sigma));
+            add_jac(row, j, B.ctrl[c], 1.0);  add_jac(row, j, B.cdot[c], -h * sigma);
+            add_hess(i, A.cdot[c], -lam * h * (1.0 - sigma));
+            add_hess(j, B.cdot[c], -lam * h * sigma);
+        }
+    }
+
+    if (want_derivs)
+    {
+        // merge the duplicate jacobian triplets (q and qd contributions of the same (row, col))
+        Triplets merged;
+        const size_t nt = out.jac.val.size();
+        size_t k = 0;
+        while (k < nt)
+        {
+            // contributions of one (row, node) come in runs of NV, possibly two consecutive runs for the same node
+            if (k + 2 * NV <= nt && out.jac.row[k] == out.jac.row[k + NV] && out.jac.col[k] == out.jac.col[k + NV])
+            {
+                for (int q = 0; q < NV; ++q) merged.add(out.jac.row[k + q], out.jac.col[k + q], out.jac.val[k + q] + out.jac.val[k + NV + q]);
+                k += 2 * NV;
+            }
+            else
+            {
+                for (int q = 0; q < NV; ++q) merged.add(out.jac.row[k + q], out.jac.col[k + q], out.jac.val[k + q]);
+                k += NV;
+            }
+        }
+        out.jac = merged;
+
+        for (int node = 0; node < np; ++node)
+        {
+            if (!d.closed && node == 0) continue;
+            const double* Hn = H.data() + (size_t)node * NV * NV;
+            const int c0 = var0(node);
+            for (int r = 0; r < NV; ++r) for (int c = 0; c <= r; ++c) out.hess.add(c0 + r, c0 + c, Hn[r * NV + c]);
+        }
+    }
+}
+
+inline void eval_nlp(const Desc& d, const double* x, const double* lambda, double obj_factor, bool want_derivs, EvalOut& out)
+{
+    const Layout L = make_layout(d);
+    switch (L.nv)
+    {
+    case 14: eval_nlp_t<14>(d, x, lambda, obj_factor, want_derivs, out); break;
+    case 15: eval_nlp_t<15>(d, x, lambda, obj_factor, want_derivs, out); break;
+    case 16: eval_nlp_t<16>(d, x, lambda, obj_factor, want_derivs, out); break;
+    case 17: eval_nlp_t<17>(d, x, lambda, obj_factor, want_derivs, out); break;
+    default: break;
+    }
+}
+
+} // namespace oracle
+#endif

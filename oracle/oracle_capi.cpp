@@ -1,0 +1,127 @@
+// TEST INFRASTRUCTURE ONLY -- C entry points of the CPU oracle, loaded with ctypes by tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline leg.  The product (fastest_lap_b200/) never links or loads this file.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <omp.h>
+#include "nlp.hpp"
+
+using namespace oracle;
+
+extern "C" {
+
+struct orc_desc
+{
+    int model, form, closed, elevation, n_points, kart_direct_torque;
+    const double* s;
+    double track_length;
+    const double* track;
+    const double* params;
+    double sigma;
+    double dissipation[2];
+    const double* q0;
+    const double* u0;
+    const double* du0;
+    const double* ctrl_default;
+};
+
+static Desc to_desc(const orc_desc* c)
+{
+    Desc d;
+    d.model = c->model; d.form = c->form; d.closed = c->closed; d.elevation = c->elevation; d.n_points = c->n_points;
+    d.kart_direct_torque = c->kart_direct_torque;
+    d.s = c->s; d.track_length = c->track_length; d.track = c->track; d.params = c->params; d.sigma = c->sigma;
+    d.dissipation[0] = c->dissipation[0]; d.dissipation[1] = c->dissipation[1];
+    d.q0 = c->q0; d.u0 = c->u0; d.du0 = c->du0; d.ctrl_default = c->ctrl_default;
+    return d;
+}
+
+int orc_nparams(int model) { return model == MODEL_F1 ? (int)F1_NPARAMS : (int)K_NPARAMS; }
+
+void orc_sizes(const orc_desc* c, int* n, int* m, int* nv, int* ncpe, long* max_jac, long* max_hess)
+{
+    const Desc d = to_desc(c);
+    const Layout L = make_layout(d);
+    *n = L.n; *m = L.m; *nv = L.nv; *ncpe = L.ncpe;
+    *max_jac = (long)L.m * 2 * L.nv;
+    *max_hess = (long)d.n_points * (L.nv * (L.nv + 1) / 2) + (long)L.n_elements * 3 * L.n_fm;
+}
+
+// Full evaluation: f, grad f, g, Jacobian triplets, Hessian-of-the-Lagrangian triplets (lower triangle, duplicates summed by the caller)
+int orc_eval(const orc_desc* c, const double* x, const double* lambda, double obj_factor, int want_derivs, int n_threads,
+             double* f, double* grad, double* g,
+             int* jrow, int* jcol, double* jval, long* njac,
+             int* hrow, int* hcol, double* hval, long* nhess)
+{
+    const Desc d = to_desc(c);
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+    EvalOut out;
+    eval_nlp(d, x, lambda, obj_factor, want_derivs != 0, out);
+    *f = out.f;
+    std::memcpy(g, out.g.data(), out.g.size() * sizeof(double));
+    if (want_derivs)
+    {
+        std::memcpy(grad, out.grad.data(), out.grad.size() * sizeof(double));
+        *njac = (long)out.jac.val.size();
+        std::memcpy(jrow, out.jac.row.data(), out.jac.row.size() * sizeof(int));
+        std::memcpy(jcol, out.jac.col.data(), out.jac.col.size() * sizeof(int));
+        std::memcpy(jval, out.jac.val.data(), out.jac.val.size() * sizeof(double));
+        *nhess = (long)out.hess.val.size();
+        std::memcpy(hrow, out.hess.row.data(), out.hess.row.size() * sizeof(int));
+        std::memcpy(hcol, out.hess.col.data(), out.hess.col.size() * sizeof(int));
+        std::memcpy(hval, out.hess.val.data(), out.hess.val.size() * sizeof(double));
+    }
+    return 0;
+}
+
+// Timing leg for bench.py's cpu_baseline: `reps` full callback rounds (f, grad, g, Jacobian, Hessian) over the lap,
+// returns seconds per round.
+double orc_time_eval(const orc_desc* c, const double* x, const double* lambda, double obj_factor, int reps, int n_threads)
+{
+    const Desc d = to_desc(c);
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+    EvalOut out;
+    const double t0 = omp_get_wtime();
+    for (int r = 0; r < reps; ++r) eval_nlp(d, x, lambda, obj_factor, true, out);
+    const double t1 = omp_get_wtime();
+    return (t1 - t0) / reps;
+}
+
+int orc_max_threads() { return omp_get_max_threads(); }
+
+// One node of the F1, values only (unit-level checks against the reference's closed-form tests)
+void orc_f1_car(const double* q, const double* u, const double* P, const double* track6,
+                double* states, double* dstates, double* dtds, double* extra, double* diag /* kappa[4], lambda[4], omega_w[4], Fx[4], Fy[4], N[4] */)
+{
+    TrackNode tk; tk.theta = track6[0]; tk.mu = track6[1]; tk.phi = track6[2]; tk.dtheta = track6[3]; tk.dmu = track6[4]; tk.dphi = track6[5];
+    F1Out<double> o;
+    f1_car<double>(q, u, P, tk, o);
+    for (int i = 0; i < F1_NIN; ++i) { states[i] = o.states[i]; dstates[i] = o.dstates[i]; }
+    *dtds = o.dtds;
+    for (int i = 0; i < F1_NEXTRA; ++i) extra[i] = o.extra[i];
+    for (int i = 0; i < 4; ++i)
+    {
+        diag[i] = o.kappa[i]; diag[4 + i] = o.lambda[i]; diag[8 + i] = o.omega_w[i];
+        diag[12 + i] = o.Fx_t[i]; diag[16 + i] = o.Fy_t[i]; diag[20 + i] = o.N[i];
+    }
+}
+
+// One node of the kart, values only
+void orc_kart_car(const double* q, const double* u, const double* P, const double* track6, int direct_torque, int curvilinear,
+                  double* states, double* dstates, double* dtds, double* extra, double* diag /* kappa[4], lambda[4], N[4], Fx[4], Fy[4], w[4], force[3], torque[3] */)
+{
+    TrackNode tk; tk.theta = track6[0]; tk.mu = track6[1]; tk.phi = track6[2]; tk.dtheta = track6[3]; tk.dmu = track6[4]; tk.dphi = track6[5];
+    KartOut<double> o;
+    kart_car<double>(q, u, P, tk, direct_torque != 0, curvilinear != 0, o);
+    for (int i = 0; i < KART_NIN; ++i) { states[i] = o.states[i]; dstates[i] = o.dstates[i]; }
+    *dtds = o.dtds;
+    for (int i = 0; i < KART_NEXTRA; ++i) extra[i] = o.extra[i];
+    for (int i = 0; i < 4; ++i)
+    {
+        diag[i] = o.kappa[i]; diag[4 + i] = o.lambda[i]; diag[8 + i] = o.N[i];
+        diag[12 + i] = o.Fx_t[i]; diag[16 + i] = o.Fy_t[i]; diag[20 + i] = o.w[i];
+    }
+    for (int i = 0; i < 3; ++i) { diag[24 + i] = o.force[i]; diag[27 + i] = o.torque[i]; }
+}
+
+} // extern "C"
