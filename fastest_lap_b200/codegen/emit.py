@@ -1,0 +1,183 @@
+"""Straight-line fp64 CUDA / C emission of expression DAGs (see expr.py)."""
+from .expr import CONST, SYM, ADD, SUB, MUL, NEG, RCP, SQRT, SIN, COS, ATAN, TANH, EXP
+
+_FN = {SQRT: "sqrt", SIN: "sin", COS: "cos", ATAN: "atan", TANH: "tanh", EXP: "exp"}
+
+
+def lit(v):
+    s = repr(float(v))
+    if "e" not in s and "." not in s and "inf" not in s and "nan" not in s:
+        s += ".0"
+    return s
+
+
+class ParamTable:
+    """Raw parameters followed by host-derived ones (sub-expressions that depend on parameters only)."""
+
+    def __init__(self, graph, raw_names):
+        self.g = graph
+        self.raw_names = list(raw_names)
+        self.index = {}          # node id -> slot in D
+        for k, n in enumerate(self.raw_names):
+            self.index[graph.sym("p_" + n, "p")] = k
+        self.derived = []        # node ids, in slot order after the raw ones
+        self._ponly = {}
+
+    def param_only(self, i):
+        g = self.g
+        r = self._ponly.get(i)
+        if r is None:
+            k = g.kind[i]
+            if k == CONST:
+                r = True
+            elif k == SYM:
+                r = g.sym_class[g.a[i]] == "p"
+            else:
+                r = all(self.param_only(o) for o in g.operands(i))
+            self._ponly[i] = r
+        return r
+
+    def slot(self, i):
+        s = self.index.get(i)
+        if s is None:
+            s = len(self.raw_names) + len(self.derived)
+            self.derived.append(i)
+            self.index[i] = s
+        return s
+
+    @property
+    def size(self):
+        return len(self.raw_names) + len(self.derived)
+
+
+class Emitter:
+    """Emits one function body: `inputs` maps symbol name -> C expression; outputs are (expr id, "lhs") pairs."""
+
+    def __init__(self, graph, ptable, inputs, dname="D"):
+        self.g, self.pt, self.inputs, self.dname = graph, ptable, inputs, dname
+
+    def body(self, outputs, indent="    "):
+        g, pt = self.g, self.pt
+        lines = []
+        name = {}
+        K, A, B = g.kind, g.a, g.b
+
+        # which sin/cos share an argument (-> sincos)
+        needed = g.topo([e for e, _ in outputs])
+        sin_of, cos_of = {}, {}
+        for i in needed:
+            if pt.param_only(i):
+                continue
+            if K[i] == SIN:
+                sin_of[A[i]] = i
+            elif K[i] == COS:
+                cos_of[A[i]] = i
+        pair = {a: (sin_of[a], cos_of[a]) for a in sin_of if a in cos_of}
+
+        def ref(i):
+            """C expression for an already emitted node (negations and literals are folded into the consumer)."""
+            k = K[i]
+            if k == CONST:
+                v = A[i]
+                return lit(v) if v >= 0 else "(" + lit(v) + ")"
+            if k == NEG and not pt.param_only(i):
+                return "(-" + ref(A[i]) + ")"
+            return name[i]
+
+        def emit(i):
+            # iterative post-order DFS
+            stack = [(i, False)]
+            while stack:
+                n, done = stack.pop()
+                if n in name or K[n] == CONST:
+                    continue
+                if K[n] != SYM and pt.param_only(n):
+                    s = pt.slot(n)
+                    name[n] = "d%d" % s
+                    lines.append("%sconst double d%d = %s[%d];" % (indent, s, self.dname, s))
+                    continue
+                if K[n] == SYM:
+                    cls = g.sym_class[A[n]]
+                    if cls == "p":
+                        s = pt.slot(n)
+                        name[n] = "d%d" % s
+                        lines.append("%sconst double d%d = %s[%d];" % (indent, s, self.dname, s))
+                    else:
+                        name[n] = self.inputs[A[n]]
+                    continue
+                if not done:
+                    stack.append((n, True))
+                    for o in reversed(g.operands(n)):
+                        if o not in name and K[o] != CONST:
+                            stack.append((o, False))
+                    continue
+                k = K[n]
+                if k == NEG:
+                    name[n] = None     # folded by ref()
+                    continue
+                t = "t%d" % n
+                if k == ADD:
+                    rhs = "%s + %s" % (ref(A[n]), ref(B[n]))
+                elif k == SUB:
+                    rhs = "%s - %s" % (ref(A[n]), ref(B[n]))
+                elif k == MUL:
+                    rhs = "%s * %s" % (ref(A[n]), ref(B[n]))
+                elif k == RCP:
+                    rhs = "1.0 / %s" % ref(A[n])
+                elif k in (SIN, COS) and A[n] in pair:
+                    s_id, c_id = pair[A[n]]
+                    if s_id not in name and c_id not in name:
+                        lines.append("%sdouble t%d, t%d; sincos(%s, &t%d, &t%d);" % (indent, s_id, c_id, ref(A[n]), s_id, c_id))
+                        name[s_id], name[c_id] = "t%d" % s_id, "t%d" % c_id
+                    continue
+                else:
+                    rhs = "%s(%s)" % (_FN[k], ref(A[n]))
+                lines.append("%sconst double %s = %s;" % (indent, t, rhs))
+                name[n] = t
+
+        for e, lhs in outputs:
+            emit(e)
+            lines.append("%s%s = %s;" % (indent, lhs, ref(e)))
+        return "\n".join(lines)
+
+
+def emit_host_derive(graph, ptable, fname):
+    """C function computing the derived-parameter slots from the raw ones (run once per vehicle on the host)."""
+    g = graph
+    K, A, B = g.kind, g.a, g.b
+    lines = ["void %s(double* D)" % fname, "{"]
+    name = {}
+    raw = {i: s for i, s in ptable.index.items() if s < len(ptable.raw_names)}
+
+    def ref(i):
+        if K[i] == CONST:
+            v = A[i]
+            return lit(v) if v >= 0 else "(" + lit(v) + ")"
+        return name[i]
+
+    for i in g.topo(list(ptable.derived)):
+        k = K[i]
+        if k == CONST:
+            continue
+        if k == SYM:
+            name[i] = "D[%d]" % raw[i]
+            continue
+        t = "h%d" % i
+        if k == ADD:
+            rhs = "%s + %s" % (ref(A[i]), ref(B[i]))
+        elif k == SUB:
+            rhs = "%s - %s" % (ref(A[i]), ref(B[i]))
+        elif k == MUL:
+            rhs = "%s * %s" % (ref(A[i]), ref(B[i]))
+        elif k == NEG:
+            rhs = "-%s" % ref(A[i])
+        elif k == RCP:
+            rhs = "1.0 / %s" % ref(A[i])
+        else:
+            rhs = "%s(%s)" % (_FN[k], ref(A[i]))
+        lines.append("    const double %s = %s;" % (t, rhs))
+        name[i] = t
+    for i in ptable.derived:
+        lines.append("    D[%d] = %s;" % (ptable.index[i], ref(i)))
+    lines.append("}")
+    return "\n".join(lines)

@@ -1,0 +1,180 @@
+"""Symbolic statement of what ONE collocation node contributes to the NLP callbacks.
+
+Restates Optimal_laptime::FG_direct / FG_derivative (src/core/applications/optimal_laptime.hpp:1226-1657) node-wise:
+every term of f, g and the Lagrangian that involves node j depends on x_j only (plus, linearly, on the neighbours'
+controls through the control-rate penalty), so eval_grad_f / eval_jac_g / eval_h split into independent per-node pieces:
+
+  A-block  rows of the element that ENDS at node j   (j is the "right" node: states, sigma-weighted rates, algebraic rows, extras)
+  B-block  rows of the element that STARTS at node j (j is the "left" node: trapezoid rows only)
+  H-block  lower triangle of the Hessian of phi_j(x_j) = obj*f_j + sum(lambda * rows touching x_j)
+  C-slots  control-control couplings (u_j, u_{j-1}) of the direct form's control-rate penalty.
+
+The variable order inside a node is the reference's (optimal_laptime.hpp:1269-1285): inputs without `time`, then the
+full-mesh controls, then (derivative form) their rates.
+"""
+from .expr import Graph, E
+from . import models
+
+
+class Variant:
+    def __init__(self, model, form, elevation=False, direct_torque=False):
+        assert model in ("f1", "kart") and form in ("direct", "derivative")
+        self.model, self.form, self.elevation, self.direct_torque = model, form, bool(elevation), bool(direct_torque)
+        if model == "kart":
+            assert not elevation, "lot2016kart rejects tracks with elevation (lot2016kart.h:63-68)"
+
+    @property
+    def name(self):
+        n = "%s_%s" % (self.model, self.form)
+        if self.elevation:
+            n += "_3d"
+        if self.direct_torque:
+            n += "_torque"
+        return n
+
+
+class NodeProgram:
+    """All symbols and output expressions of one variant."""
+
+    def __init__(self, variant):
+        v = self.variant = variant
+        g = self.g = Graph()
+        S = lambda name, cls: E(g, g.sym(name, cls))
+        deriv = v.form == "derivative"
+
+        if v.model == "f1":
+            self.param_names = models.F1_PARAMS + models.F1_HOST_PARAMS
+            n_in, time_idx = 14, 11
+            self.n_fm = 2
+            td_ids = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13] if v.elevation else [0, 1, 2, 3, 4, 5, 6, 12, 13]
+            alg_ids = [] if v.elevation else [7, 8, 9, 10]       # limebeer2014f1.h:185-225
+        else:
+            self.param_names = models.KART_PARAMS + models.KART_HOST_PARAMS
+            n_in, time_idx = 13, 10
+            self.n_fm = 2
+            td_ids = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 12]
+            alg_ids = []
+        self.param_names = self.param_names + ["diss0", "diss1"]
+        self.td_ids, self.alg_ids = td_ids, alg_ids
+        self.n_td, self.n_alg, self.n_ext = len(td_ids), len(alg_ids), 6
+        self.n_ctrl_rows = self.n_fm if deriv else 0
+        self.ncpe = self.n_td + self.n_alg + self.n_ext + self.n_ctrl_rows
+        self.nv = (n_in - 1) + self.n_fm + (self.n_fm if deriv else 0)
+        self.ctrl_pos = [n_in - 1, n_in]
+        self.dctrl_pos = [n_in + 1, n_in + 2] if deriv else []
+
+        # ---- symbols
+        self.x = [S("x%d" % k, "x") for k in range(self.nv)]
+        P = self.P = {n: S("p_" + n, "p") for n in self.param_names}
+        if v.elevation:
+            self.track_names = ["kx", "ky", "kz", "smu", "cmu", "sph", "cph"]
+            trk = {n: S("t_" + n, "t") for n in self.track_names}
+        else:
+            self.track_names = ["kz"]
+            trk = dict(kx=0.0, ky=0.0, kz=S("t_kz", "t"), smu=0.0, cmu=1.0, sph=0.0, cph=1.0)
+        self.geom_names = ["hin", "hout"] + (["penw"] if deriv else [])
+        hin, hout = S("t_hin", "t"), S("t_hout", "t")
+        penw = S("t_penw", "t") if deriv else None
+        self.lam_in = [S("lin%d" % r, "w") for r in range(self.ncpe)]
+        self.lam_out = [S("lout%d" % r, "w") for r in range(self.n_td)] + [None] * (self.n_alg + self.n_ext) + \
+                       [S("lout%d" % (self.n_td + self.n_alg + self.n_ext + c), "w") for c in range(self.n_ctrl_rows)]
+        obj = S("obj", "w")
+        self.uprev = [S("uprev%d" % c, "n") for c in range(self.n_fm)] if not deriv else []
+        self.unext = [S("unext%d" % c, "n") for c in range(self.n_fm)] if not deriv else []
+        sigma = P["sigma"]
+        diss = [P["diss0"], P["diss1"]]
+
+        # ---- the vehicle at this node
+        q = list(self.x[:time_idx]) + [E(g, g.const(0.0))] + list(self.x[time_idx:n_in - 1])
+        ctrl = [self.x[p] for p in self.ctrl_pos]
+        if v.model == "f1":
+            # controls: delta, boost, throttle, brake-bias; boost and brake-bias keep their default values
+            # (Control_variables::control_array_at_s, detail/optimal_laptime_control_variables.h:190-222)
+            u = [ctrl[0], E(g, g.const(0.0)), ctrl[1], P["brake_bias"]]
+            out = models.f1_model(q, u, P, trk)
+        else:
+            out = models.kart_model(q, ctrl, P, trk, direct_torque=v.direct_torque, curvilinear=True)
+        states, dstates, dtds, extra = out["states"], out["dstates"], out["dtds"], out["extra"]
+
+        Q = [states[i] for i in td_ids]
+        QD = [dstates[i] for i in td_ids]
+        ALG = [dstates[i] / dtds for i in alg_ids]              # optimal_laptime.hpp:1341 (= the un-scaled equation)
+        EXT = list(extra)
+        CDOT = [self.x[p] * dtds for p in self.dctrl_pos]       # optimal_laptime.hpp:1580-1581
+        self.Q, self.QD, self.ALG, self.EXT, self.CDOT, self.DTDS = Q, QD, ALG, EXT, CDOT, dtds
+
+        # ---- node values handed to the element assembly (g, f)
+        self.values = Q + QD + ALG + EXT + [dtds] + CDOT
+        self.value_names = (["Q%d" % r for r in range(self.n_td)] + ["QD%d" % r for r in range(self.n_td)] +
+                            ["ALG%d" % r for r in range(self.n_alg)] + ["EXT%d" % r for r in range(self.n_ext)] + ["DTDS"] +
+                            ["CDOT%d" % c for c in range(self.n_ctrl_rows)])
+
+        # ---- rows as functions of x_j: A (j is the right node of its element), B (j is the left node)
+        one_m_sigma = 1.0 - sigma
+        rowsA, rowsB = [], []
+        for r in range(self.n_td):
+            rowsA.append(Q[r] - hin * sigma * QD[r])
+            rowsB.append(-Q[r] - hout * one_m_sigma * QD[r])
+        for r in range(self.n_alg):
+            rowsA.append(ALG[r]); rowsB.append(None)
+        for r in range(self.n_ext):
+            rowsA.append(EXT[r]); rowsB.append(None)
+        for c in range(self.n_ctrl_rows):
+            rowsA.append(ctrl[c] - hin * sigma * CDOT[c])
+            rowsB.append(-ctrl[c] - hout * one_m_sigma * CDOT[c])
+        self.rowsA, self.rowsB = rowsA, rowsB
+
+        # ---- local objective: every term of f that involves x_j (its x_j-gradient is d f / d x_j)
+        fobj = (hin * sigma + hout * one_m_sigma) * dtds
+        if deriv:
+            for c in range(self.n_fm):
+                du = self.x[self.dctrl_pos[c]]
+                fobj = fobj + 0.5 * diss[c] * penw * du * du                   # optimal_laptime.hpp:1553, 1611
+        else:
+            for c in range(self.n_fm):
+                d_in, d_out = ctrl[c] - self.uprev[c], self.unext[c] - ctrl[c]
+                fobj = fobj + diss[c] * (d_in * d_in / hin + d_out * d_out / hout)   # optimal_laptime.hpp:1362-1366, 1401-1402
+        self.fobj = fobj
+
+        # ---- Lagrangian restricted to x_j
+        phi = obj * fobj
+        for r in range(self.ncpe):
+            phi = phi + self.lam_in[r] * rowsA[r]
+            if rowsB[r] is not None:
+                phi = phi + self.lam_out[r] * rowsB[r]
+        self.phi = phi
+
+        xs = [xx.i for xx in self.x]
+        # Jacobian blocks (forward sweeps), gradient of f
+        fw = []
+        roots = [e.i for e in rowsA] + [e.i for e in rowsB if e is not None] + [fobj.i]
+        for k in range(self.nv):
+            fw.append(g.forward(roots, xs[k]))
+        nA = len(rowsA)
+        idxB = [r for r in range(self.ncpe) if rowsB[r] is not None]
+        zero = g.const(0.0)
+        self.jacA = {}      # (row, var) -> expr id
+        self.jacB = {}
+        self.gradf = []
+        for k in range(self.nv):
+            for r in range(nA):
+                if fw[k][r] != zero:
+                    self.jacA[(r, k)] = fw[k][r]
+            for q_, r in enumerate(idxB):
+                if fw[k][nA + q_] != zero:
+                    self.jacB[(r, k)] = fw[k][nA + q_]
+            self.gradf.append(fw[k][nA + len(idxB)])
+
+        # Hessian of phi: reverse sweep for the gradient, forward sweeps over it for the columns (forward-over-reverse)
+        grad_phi = g.reverse(phi.i, xs)
+        self.hess = {}      # (row >= col) -> expr id
+        for c in range(self.nv):
+            col = g.forward(grad_phi, xs[c])
+            for r in range(c, self.nv):
+                if col[r] != zero:
+                    self.hess[(r, c)] = col[r]
+        # coupling slots of the direct-form control-rate penalty: d2 f / d u_j d u_{j-1} = -2 diss / h_in
+        self.coupling = []
+        if not deriv:
+            for c in range(self.n_fm):
+                self.coupling.append((obj * (-2.0) * diss[c] / hin).i)
