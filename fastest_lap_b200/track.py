@@ -115,3 +115,19 @@ def track_from_xml(source, name=""):
                 mask = (s > s0 - 1.0e-12) & (s < s1 + 1.0e-12)
                 arr[mask] += wd
     return Track(s, x, y, z, yaw, pitch, roll, yaw_dot, dpitch, droll, nl, nr, length, ttype == "closed", elev, name)
+
+
+_NPZ_KEYS = ("x", "y", "z", "yaw", "pitch", "roll", "yaw_dot", "dpitch", "droll", "nl", "nr")
+
+
+def track_to_npz(track, path):
+    """Compact binary form of a loaded track (the arrays of the XML, before the closing sample is appended)."""
+    n = track.n_points
+    arrays = {k: track._a[k][:n] for k in _NPZ_KEYS}
+    np.savez_compressed(path, s=track.s_data, track_length=track.track_length, closed=int(track.closed),
+                        with_elevation=int(track.with_elevation), **arrays)
+
+
+def track_from_npz(path, name=""):
+    d = np.load(path)
+    return Track(d["s"], *[d[k] for k in _NPZ_KEYS], float(d["track_length"]), bool(int(d["closed"])), bool(int(d["with_elevation"])), name)

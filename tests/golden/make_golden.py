@@ -1,0 +1,87 @@
+"""Generates the committed fixtures of tests/golden/ from the reference's own data files (run in the dev container only).
+
+    python tests/golden/make_golden.py
+
+Reads, with this repository's XML loaders, the vehicle / track databases and the golden solution files that the
+reference's GoogleTest suites compare against (src/test/applications/f1_optimal_laptime_test.cpp,
+optimal_laptime_test.cpp) and stores, per case, one compressed .npz holding the LapProblem arrays plus the golden NLP
+point (x, lambda, zl, zu, lap time, iteration count).  /root/reference is not available on the GPU box, these files are.
+"""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from fastest_lap_b200 import vehicle_from_xml, track_from_xml, MODEL_F1, MODEL_KART      # noqa: E402
+from fastest_lap_b200.problem import LapProblem, FORM_DIRECT, FORM_DERIVATIVE            # noqa: E402
+from fastest_lap_b200.solution import solution_from_xml                                  # noqa: E402
+from fastest_lap_b200.track import track_to_npz                                          # noqa: E402
+
+REF = "/root/reference/"
+DATA = REF + "src/test/applications/data/"
+
+
+def golden_case(name, vehicle, track, sol, dissipation, **kw):
+    form = FORM_DIRECT if sol.is_direct else FORM_DERIVATIVE
+    q0 = u0 = du0 = None
+    if not sol.is_closed:
+        q0 = sol.inputs[0]
+        u0 = np.array(LapProblem(vehicle.model, form, True, sol.s, track.track_length, track.node_data(sol.s), track.left_track_limit(sol.s),
+                                 track.right_track_limit(sol.s), vehicle.params).ctrl_default)
+        fm = sol.full_mesh_controls()
+        for c in fm:
+            u0[c] = sol.controls[c].values[0]
+        if not sol.is_direct:
+            du0 = np.array([sol.controls[c].derivatives[0] for c in fm])
+    p = LapProblem.from_vehicle_track(vehicle, track, sol.s, form=form, closed=sol.is_closed, dissipation=dissipation, q0=q0, u0=u0, du0=du0, **kw)
+    x = sol.pack_x()
+    assert x.size == p.n and sol.lam.size == p.m, (x.size, p.n, sol.lam.size, p.m)
+    # The flat-track F1 goldens predate a sign change of the roll-moment equation (second algebraic row, offset 10 of 19/21):
+    # with the stored multiplier of that row negated, grad f + J^T lambda - zl + zu vanishes to 1.5e-10 on every variable
+    # (1.3 otherwise).  The tests of the reference never compare multipliers.  `lam` is the sign-corrected vector, `lam_raw` the file's.
+    lam = sol.lam.copy()
+    if vehicle.model == MODEL_F1 and not p.elevation:
+        lam.reshape(p.n_elements, p.ncpe)[:, 10] *= -1.0
+    p.save_npz(os.path.join(HERE, name + ".npz"), x=x, lam=lam, lam_raw=sol.lam, zl=sol.zl, zu=sol.zu, laptime=sol.laptime, iter_count=sol.iter_count,
+               time=sol.inputs[:, sol.inputs.shape[1] - 3])
+    print(name, "n =", p.n, "m =", p.m, "laptime", sol.laptime)
+
+
+def main():
+    f1 = vehicle_from_xml(REF + "database/vehicles/f1/limebeer-2014-f1.xml")
+    kart = vehicle_from_xml(REF + "database/vehicles/kart/roberto-lot-kart-2016.xml")
+    rental = vehicle_from_xml(REF + "database/vehicles/kart/rental-kart.xml")
+    catalunya = track_from_xml(REF + "database/tracks/catalunya/catalunya.xml")
+    catalunya_3d = track_from_xml(REF + "database/tracks/catalunya/catalunya_3d.xml")
+    catalunya_adapted = track_from_xml(REF + "database/tracks/catalunya/catalunya_adapted.xml")
+    vendrell = track_from_xml(REF + "database/tracks/vendrell/vendrell.xml")
+
+    # f1_optimal_laptime_test.cpp:168-213 (Ixx = Iyy = 0)
+    v = f1.copy()
+    v.set_parameter("vehicle/chassis/inertia/Ixx", 0.0)
+    v.set_parameter("vehicle/chassis/inertia/Iyy", 0.0)
+    golden_case("f1_catalunya_discrete", v, catalunya, solution_from_xml(DATA + "f1_optimal_laptime_catalunya_discrete.xml", MODEL_F1), (50.0, 20.0 * 8.0e-4))
+    # f1_optimal_laptime_test.cpp:1296-1340
+    golden_case("f1_catalunya_3d", f1, catalunya_3d, solution_from_xml(DATA + "f1_optimal_laptime_catalunya_3d.xml", MODEL_F1), (50.0, 50.0 * 8.0e-4))
+    # f1_optimal_laptime_test.cpp:318-395 and :782-852 (open sections, wheel inertia 1.00 / 1.55)
+    v = f1.copy()
+    v.set_parameter("vehicle/front-axle/inertia", 1.00)
+    v.set_parameter("vehicle/rear-axle/inertia", 1.55)
+    golden_case("f1_catalunya_chicane", v, catalunya_adapted, solution_from_xml(DATA + "f1_optimal_laptime_catalunya_chicane.xml", MODEL_F1), (50.0, 20.0 * 8.0e-4))
+    golden_case("f1_catalunya_chicane_derivative", v, catalunya_adapted,
+                solution_from_xml(DATA + "f1_optimal_laptime_catalunya_chicane_derivative.xml", MODEL_F1), (2.0e-1, 2.0e-5))
+    # optimal_laptime_test.cpp:516-572
+    golden_case("kart_vendrell", rental, vendrell, solution_from_xml(DATA + "vendrell_optimal.xml", MODEL_KART), (1.0e-2, 200 * 200.0 * 1.0e-10))
+
+    # input data of the benchmark configurations: tracks and vehicle parameter vectors
+    data_dir = os.path.join(HERE, "..", "..", "fastest_lap_b200", "data")
+    os.makedirs(data_dir, exist_ok=True)
+    track_to_npz(catalunya, os.path.join(data_dir, "catalunya.npz"))
+    track_to_npz(vendrell, os.path.join(data_dir, "vendrell.npz"))
+    np.savez(os.path.join(data_dir, "vehicles.npz"), limebeer_2014_f1=f1.params, roberto_lot_kart_2016=kart.params, rental_kart=rental.params)
+
+
+if __name__ == "__main__":
+    main()

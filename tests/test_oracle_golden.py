@@ -1,0 +1,87 @@
+"""Pins the CPU oracle against the reference's golden solution files.
+
+Every golden optimal-laptime XML of the reference is a known-answer test of the NLP callbacks:
+  * eval_g: all equality rows vanish at the stored point (the reference solves to constr_viol_tol = 1e-10),
+  * eval_f: the time integral equals the stored lap time (written with 6 decimals),
+  * eval_grad_f + eval_jac_g: grad f + J^T lambda - zl + zu = 0 with the stored multipliers (tol = 1e-10 scaled).
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import load_golden, oracle_nlp, equality_rows
+
+CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell"]
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    p, ex = load_golden(request.param)
+    r = oracle_nlp(p).eval(ex["x"], ex["lam"], 1.0)
+    return p, ex, r
+
+
+def test_equality_rows_vanish(case):
+    p, ex, r = case
+    g = r["g"].reshape(p.n_elements, p.ncpe)
+    assert np.abs(g[:, equality_rows(p)]).max() < 5.0e-11
+
+
+def test_laptime(case):
+    p, ex, r = case
+    # objective = lap time + control-rate penalty; lap time = sum h (0.5 dtds_i + 0.5 dtds_j) (optimal_laptime.hpp:616-634)
+    o = oracle_nlp(p)
+    p0 = type(p)(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.wl, p.wr, p.params, [0.0, 0.0], p.sigma, p.elevation,
+                 p.q0, p.u0, p.du0, p.ctrl_default, p.kart_direct_torque)
+    t = oracle_nlp(p0).eval(ex["x"], None, 1.0, derivs=False)["f"]
+    t0 = 0.0 if p.closed else float(ex["time"][0])      # open sections keep integrating the time input of their first node
+    assert abs(t0 + t - float(ex["laptime"])) < 1.0e-6
+    assert r["f"] >= t
+
+
+def test_kkt_stationarity(case):
+    p, ex, r = case
+    jr, jc, jv = r["jac"]
+    JTl = np.zeros(p.n)
+    np.add.at(JTl, jc, jv * ex["lam"][jr])
+    kkt = r["grad"] + JTl - ex["zl"] + ex["zu"]
+    assert np.abs(kkt).max() < 5.0e-10
+
+
+def test_inequality_rows_within_bounds(case):
+    p, ex, r = case
+    g = r["g"].reshape(p.n_elements, p.ncpe)
+    n_eq = p.ncpe - 6 - (0 if p.form == 0 else 2)
+    ext = g[:, n_eq:n_eq + 6]
+    if p.model == 0:
+        # track limits: n +- t/2 cos(alpha) in [-wl, wr] at the element's right node (limebeer2014f1.h:266-281)
+        j = (np.arange(p.n_elements) + 1) % p.n_points
+        assert np.all(ext[:, 4] <= p.wr[j] + 1e-6) and np.all(ext[:, 5] >= -p.wl[j] - 1e-6)
+    else:
+        assert np.abs(ext).max() <= 0.11 + 1e-8          # lot2016kart.h:194-211
+
+
+def test_hessian_matches_finite_differences_of_gradient():
+    """Second derivatives are not pinned by any reference fixture: cross-check the oracle's jets against
+    central differences of its own first derivatives on a short open section."""
+    p, ex = load_golden("f1_catalunya_chicane")
+    o = oracle_nlp(p)
+    rng = np.random.default_rng(0)
+    lam = rng.standard_normal(p.m)
+    x = ex["x"]
+    r = o.eval(x, lam, 0.7)
+    hr, hc, hv = r["hess"]
+    H = np.zeros((p.n, p.n))
+    np.add.at(H, (hr, hc), hv)
+    H = H + np.tril(H, -1).T
+
+    def grad_lagr(xx):
+        rr = o.eval(xx, lam, 0.7)
+        jr, jc, jv = rr["jac"]
+        gl = 0.7 * rr["grad"]
+        np.add.at(gl, jc, jv * lam[jr])
+        return gl
+    for k in rng.choice(p.n, 12, replace=False):
+        h = 1.0e-6 * max(1.0, abs(x[k]))
+        e = np.zeros(p.n); e[k] = h
+        col = (grad_lagr(x + e) - grad_lagr(x - e)) / (2 * h)
+        assert np.abs(col - H[:, k]).max() <= 2.0e-6 * max(1.0, np.abs(H[:, k]).max())
