@@ -51,10 +51,10 @@ class ParamTable:
 
 
 class Emitter:
-    """Emits one function body: `inputs` maps symbol name -> C expression; outputs are (expr id, "lhs") pairs."""
+    """Emits one function body: `inputs` maps symbol name -> C expression; outputs are (expr id, "statement with one %s") pairs."""
 
-    def __init__(self, graph, ptable, inputs, dname="D"):
-        self.g, self.pt, self.inputs, self.dname = graph, ptable, inputs, dname
+    def __init__(self, graph, ptable, inputs, dfmt="D[%d]"):
+        self.g, self.pt, self.inputs, self.dfmt = graph, ptable, inputs, dfmt
 
     def body(self, outputs, indent="    "):
         g, pt = self.g, self.pt
@@ -94,14 +94,14 @@ class Emitter:
                 if K[n] != SYM and pt.param_only(n):
                     s = pt.slot(n)
                     name[n] = "d%d" % s
-                    lines.append("%sconst double d%d = %s[%d];" % (indent, s, self.dname, s))
+                    lines.append("%sconst double d%d = %s;" % (indent, s, self.dfmt % s))
                     continue
                 if K[n] == SYM:
                     cls = g.sym_class[A[n]]
                     if cls == "p":
                         s = pt.slot(n)
                         name[n] = "d%d" % s
-                        lines.append("%sconst double d%d = %s[%d];" % (indent, s, self.dname, s))
+                        lines.append("%sconst double d%d = %s;" % (indent, s, self.dfmt % s))
                     else:
                         name[n] = self.inputs[A[n]]
                     continue
@@ -135,9 +135,9 @@ class Emitter:
                 lines.append("%sconst double %s = %s;" % (indent, t, rhs))
                 name[n] = t
 
-        for e, lhs in outputs:
+        for e, fmt in outputs:
             emit(e)
-            lines.append("%s%s = %s;" % (indent, lhs, ref(e)))
+            lines.append(indent + (fmt % ref(e)))
         return "\n".join(lines)
 
 

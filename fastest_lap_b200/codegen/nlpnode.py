@@ -72,9 +72,13 @@ class NodeProgram:
         else:
             self.track_names = ["kz"]
             trk = dict(kx=0.0, ky=0.0, kz=S("t_kz", "t"), smu=0.0, cmu=1.0, sph=0.0, cph=1.0)
-        self.geom_names = ["hin", "hout"] + (["penw"] if deriv else [])
+        # per-node mesh constants: lengths of the element that ends / starts at the node; direct form: their inverses
+        # (0 where the element does not exist); derivative form: total length weighting the node's control-rate penalty
+        self.geom_names = ["hin", "hout"] + (["penw"] if deriv else ["ihin", "ihout"])
         hin, hout = S("t_hin", "t"), S("t_hout", "t")
         penw = S("t_penw", "t") if deriv else None
+        ihin = None if deriv else S("t_ihin", "t")
+        ihout = None if deriv else S("t_ihout", "t")
         self.lam_in = [S("lin%d" % r, "w") for r in range(self.ncpe)]
         self.lam_out = [S("lout%d" % r, "w") for r in range(self.n_td)] + [None] * (self.n_alg + self.n_ext) + \
                        [S("lout%d" % (self.n_td + self.n_alg + self.n_ext + c), "w") for c in range(self.n_ctrl_rows)]
@@ -133,7 +137,7 @@ class NodeProgram:
         else:
             for c in range(self.n_fm):
                 d_in, d_out = ctrl[c] - self.uprev[c], self.unext[c] - ctrl[c]
-                fobj = fobj + diss[c] * (d_in * d_in / hin + d_out * d_out / hout)   # optimal_laptime.hpp:1362-1366, 1401-1402
+                fobj = fobj + diss[c] * (d_in * d_in * ihin + d_out * d_out * ihout)   # optimal_laptime.hpp:1362-1366, 1401-1402
         self.fobj = fobj
 
         # ---- Lagrangian restricted to x_j
@@ -177,4 +181,4 @@ class NodeProgram:
         self.coupling = []
         if not deriv:
             for c in range(self.n_fm):
-                self.coupling.append((obj * (-2.0) * diss[c] / hin).i)
+                self.coupling.append((obj * (-2.0) * diss[c] * ihin).i)

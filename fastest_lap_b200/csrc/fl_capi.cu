@@ -1,0 +1,595 @@
+// C-ABI of the collocation-NLP callbacks (include/fastestlap_b200.h).  Host side: problem set-up (per-node track and mesh
+// constants, parameter vectors, fixed sparsity, bounds) and kernel launches; no model arithmetic happens on the host.
+// Reference counterparts: Optimal_laptime::compute_direct / compute_derivative (variable and constraint vectors, bounds:
+// src/core/applications/optimal_laptime.hpp:326-483, 780-960) and lion::ipopt_cppad_solve's TNLP callbacks (:546-551).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/fastestlap_b200.h"
+#include "nlp_kernels.cuh"
+
+#define FL_DECLARE_VARIANT(name) extern "C" const fl_variant* fl_variant_##name();
+FL_DECLARE_VARIANT(f1_direct)
+FL_DECLARE_VARIANT(f1_derivative)
+FL_DECLARE_VARIANT(f1_direct_3d)
+FL_DECLARE_VARIANT(f1_derivative_3d)
+FL_DECLARE_VARIANT(kart_direct)
+FL_DECLARE_VARIANT(kart_derivative)
+FL_DECLARE_VARIANT(kart_direct_torque)
+FL_DECLARE_VARIANT(kart_derivative_torque)
+
+namespace {
+
+thread_local std::string g_error;
+
+bool fail(const std::string& msg) { g_error = msg; return false; }
+
+#define FL_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    g_error = std::string(#call) + ": " + cudaGetErrorString(e_); return 0; } } while (0)
+
+constexpr double DEG = 3.14159265358979323846 / 180.0;
+constexpr double KMH = 1.0 / 3.6;
+constexpr double G0 = 9.81;
+constexpr int F1_NPARAMS = 58, KART_NPARAMS = 72;
+constexpr int F1_NIN = 14, KART_NIN = 13, F1_NCTRL = 4, KART_NCTRL = 2;
+
+const fl_variant* pick_variant(int model, int form, int elevation, int torque)
+{
+    if (model == FL_MODEL_F1_3DOF)
+    {
+        if (form == FL_FORM_DIRECT) return elevation ? fl_variant_f1_direct_3d() : fl_variant_f1_direct();
+        return elevation ? fl_variant_f1_derivative_3d() : fl_variant_f1_derivative();
+    }
+    if (model == FL_MODEL_KART_6DOF && !elevation)
+    {
+        if (form == FL_FORM_DIRECT) return torque ? fl_variant_kart_direct_torque() : fl_variant_kart_direct();
+        return torque ? fl_variant_kart_derivative_torque() : fl_variant_kart_derivative();
+    }
+    return nullptr;
+}
+
+template <class T> T* dev_alloc(size_t count)
+{
+    void* p = nullptr;
+    if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, (count ? count : 1) * sizeof(T));
+    return static_cast<T*>(p);
+}
+
+} // namespace
+
+struct fl_nlp
+{
+    const fl_variant* v = nullptr;
+    fl_problem_desc desc{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    fl_dev P{};
+    // owned device buffers
+    double *d_xfull = nullptr, *d_xuser = nullptr, *d_tc = nullptr, *d_D = nullptr, *d_lambda = nullptr, *d_zeros = nullptr;
+    double *d_V = nullptr, *d_g = nullptr, *d_f = nullptr, *d_fpart = nullptr, *d_grad = nullptr, *d_jac = nullptr, *d_hess = nullptr;
+    unsigned int* d_fcount = nullptr;
+    std::vector<double> s, wl, wr, params;
+    std::vector<int> jac_row, jac_col, hess_row, hess_col;
+    bool values_valid = false, derivs_jac_valid = false;
+    long launches = 0;
+    int n_in = 0, n_ctrl = 0;
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+};
+
+namespace {
+
+// x of the user ([batch][n], free nodes only) -> xfull ([batch][n_points*NV]); a strided device copy when the first node is fixed
+int scatter_x(fl_nlp* h)
+{
+    const fl_dev& P = h->P;
+    const int NV = h->v->NV;
+    if (P.node0 == 0) return 1;     // xfull aliases the user vector
+    FL_CUDA(cudaMemcpy2DAsync(h->d_xfull + (size_t)P.node0 * NV, (size_t)P.n_points * NV * sizeof(double), h->d_xuser, (size_t)P.n * sizeof(double),
+                              (size_t)P.n * sizeof(double), P.batch, cudaMemcpyDeviceToDevice, h->stream));
+    return 1;
+}
+
+void build_structure(fl_nlp* h)
+{
+    const fl_variant* v = h->v;
+    const fl_dev& P = h->P;
+    const int np = P.n_points, NV = v->NV, NCPE = v->NCPE;
+    h->jac_row.resize(P.nnz_jac); h->jac_col.resize(P.nnz_jac);
+    h->hess_row.resize(P.nnz_hess); h->hess_col.resize(P.nnz_hess);
+    size_t k = 0;
+    for (int a = 0; a < v->NJA; ++a)
+        for (int e = 0; e < P.n_elements; ++e, ++k)
+        {
+            const int j = (e + 1 == np) ? 0 : e + 1;
+            h->jac_row[k] = e * NCPE + v->JA_ROW[a];
+            h->jac_col[k] = (j - P.node0) * NV + v->JA_COL[a];
+        }
+    for (int b = 0; b < v->NJB; ++b)
+        for (int eb = 0; eb < P.nB; ++eb, ++k)
+        {
+            const int e = eb + P.node0;
+            h->jac_row[k] = e * NCPE + v->JB_ROW[b];
+            h->jac_col[k] = (e - P.node0) * NV + v->JB_COL[b];
+        }
+    k = 0;
+    for (int a = 0; a < v->NH; ++a)
+        for (int vn = 0; vn < P.n_var_nodes; ++vn, ++k)
+        {
+            h->hess_row[k] = vn * NV + v->H_ROW[a];
+            h->hess_col[k] = vn * NV + v->H_COL[a];
+        }
+    for (int c = 0; c < v->NCPL; ++c)
+        for (int ec = 0; ec < P.nC; ++ec, ++k)
+        {
+            const int e = ec + P.node0;                       // element e joins node e -> (e+1) % np, both free
+            const int j = (e + 1 == np) ? 0 : e + 1;
+            const int r = (j - P.node0) * NV + v->CTRL_POS[c], q = (e - P.node0) * NV + v->CTRL_POS[c];
+            h->hess_row[k] = r > q ? r : q;
+            h->hess_col[k] = r > q ? q : r;
+        }
+}
+
+} // namespace
+
+extern "C" {
+
+const char* fl_last_error(void) { return g_error.c_str(); }
+
+int fl_n_vehicle_params(int model) { return model == FL_MODEL_F1_3DOF ? F1_NPARAMS : (model == FL_MODEL_KART_6DOF ? KART_NPARAMS : -1); }
+
+void fl_nlp_destroy(fl_nlp* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    double* bufs[] = { h->d_xfull, h->P.node0 ? h->d_xuser : nullptr, h->d_tc, h->d_D, h->d_lambda, h->d_zeros, h->d_V, h->d_g, h->d_f, h->d_fpart,
+                       h->d_grad, h->d_jac, h->d_hess };
+    for (double* b : bufs) if (b) cudaFree(b);
+    if (h->d_fcount) cudaFree(h->d_fcount);
+    if (h->d_flush) cudaFree(h->d_flush);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+fl_nlp* fl_nlp_create(const fl_problem_desc* d)
+{
+    if (!d) { fail("null problem description"); return nullptr; }
+    const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque);
+    if (!v) { fail(d->model == FL_MODEL_KART_6DOF && d->elevation ? "lot2016kart does not support tracks with elevation" : "unknown model / form"); return nullptr; }
+    if (d->n_points < 2) { fail("provide at least two values of arclength"); return nullptr; }
+    if (d->batch < 1) { fail("batch must be >= 1"); return nullptr; }
+    if (!d->s || !d->track_nodes || !d->wl || !d->wr || !d->vehicle_params) { fail("null array in problem description"); return nullptr; }
+    for (int i = 1; i < d->n_points; ++i)
+        if (!(d->s[i] > d->s[i - 1])) { fail("arclength must be strictly increasing"); return nullptr; }
+    if (d->closed && !(d->track_length > d->s[d->n_points - 1])) { fail("closed meshes must end before the track length"); return nullptr; }
+    if (!d->closed && (!d->q0 || !d->u0 || (d->form == FL_FORM_DERIVATIVE && !d->du0))) { fail("open problems need the inputs and controls of the first node"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { fail("no CUDA device: this library has no CPU path"); return nullptr; }
+    if (d->device < 0 || d->device >= ndev) { fail("invalid CUDA device ordinal"); return nullptr; }
+    if (cudaSetDevice(d->device) != cudaSuccess) { fail("cudaSetDevice failed"); return nullptr; }
+
+    fl_nlp* h = new fl_nlp();
+    h->v = v; h->desc = *d; h->device = d->device;
+    h->n_in = d->model == FL_MODEL_F1_3DOF ? F1_NIN : KART_NIN;
+    h->n_ctrl = d->model == FL_MODEL_F1_3DOF ? F1_NCTRL : KART_NCTRL;
+    const int np = d->n_points, NV = v->NV, batch = d->batch;
+    const int nvp = fl_n_vehicle_params(d->model);
+    h->s.assign(d->s, d->s + np); h->wl.assign(d->wl, d->wl + np); h->wr.assign(d->wr, d->wr + np);
+    h->params.assign(d->vehicle_params, d->vehicle_params + (size_t)batch * nvp);
+    h->desc.s = h->s.data(); h->desc.wl = h->wl.data(); h->desc.wr = h->wr.data(); h->desc.vehicle_params = h->params.data();
+    h->desc.track_nodes = nullptr; h->desc.q0 = h->desc.u0 = h->desc.du0 = h->desc.ctrl_default = nullptr;
+
+    fl_dev& P = h->P;
+    P.n_points = np; P.closed = d->closed ? 1 : 0; P.batch = batch;
+    P.node0 = d->closed ? 0 : 1;
+    P.n_elements = d->closed ? np : np - 1;
+    P.n_var_nodes = np - P.node0;
+    P.nB = P.n_elements - P.node0;
+    P.nC = v->NCPL ? P.n_elements - P.node0 : 0;
+    P.n = P.n_var_nodes * NV;
+    P.m = P.n_elements * v->NCPE;
+    P.nnz_jac = (long)v->NJA * P.n_elements + (long)v->NJB * P.nB;
+    P.nnz_hess = (long)v->NH * P.n_var_nodes + (long)v->NCPL * P.nC;
+    P.obj_factor = 1.0;
+
+    // ---- per-node constants [NTC][np]: track (kz | kx ky kz sin/cos pitch, sin/cos roll), then hin, hout, (ihin, ihout | penw)
+    std::vector<double> tc((size_t)v->NTC * np, 0.0);
+    const double L = d->track_length;
+    for (int i = 0; i < np; ++i)
+    {
+        const double* t = d->track_nodes + 6 * i;
+        const double mu = t[1], phi = t[2], dth = t[3], dmu = t[4], dph = t[5];
+        // Road_curvilinear::curvature (src/core/vehicles/road_curvilinear.h:49-60)
+        const double kx = dph - std::sin(mu) * dth;
+        const double ky = std::cos(phi) * dmu + std::cos(mu) * std::sin(phi) * dth;
+        const double kz = -std::sin(phi) * dmu + std::cos(mu) * std::cos(phi) * dth;
+        int k = 0;
+        if (v->IS_3D)
+        {
+            tc[(size_t)(k++) * np + i] = kx; tc[(size_t)(k++) * np + i] = ky; tc[(size_t)(k++) * np + i] = kz;
+            tc[(size_t)(k++) * np + i] = std::sin(mu); tc[(size_t)(k++) * np + i] = std::cos(mu);
+            tc[(size_t)(k++) * np + i] = std::sin(phi); tc[(size_t)(k++) * np + i] = std::cos(phi);
+        }
+        else
+            tc[(size_t)(k++) * np + i] = kz;
+        const double hin = i > 0 ? d->s[i] - d->s[i - 1] : (d->closed ? L - d->s[np - 1] : 0.0);
+        const double hout = i + 1 < np ? d->s[i + 1] - d->s[i] : (d->closed ? L - d->s[np - 1] : 0.0);
+        tc[(size_t)(k++) * np + i] = hin;
+        tc[(size_t)(k++) * np + i] = hout;
+        if (!v->IS_DERIVATIVE)
+        {
+            tc[(size_t)(k++) * np + i] = hin > 0.0 ? 1.0 / hin : 0.0;
+            tc[(size_t)(k++) * np + i] = hout > 0.0 ? 1.0 / hout : 0.0;
+        }
+        else
+            ++k;    // penw, below
+    }
+    if (v->IS_DERIVATIVE)
+    {
+        // total element length weighting 0.5 diss du_j^2: right node of its element, plus the reference's left-rate quirk
+        // (dcontrols_dt[i-i], optimal_laptime.hpp:1553): node 0 for every non-closing element, node n-1 for the closing one
+        double* penw = tc.data() + (size_t)(v->NTC - 1) * np;
+        for (int e = 0; e < P.n_elements; ++e)
+        {
+            const bool closing = e + 1 == np;
+            const int j = closing ? 0 : e + 1;
+            const double he = closing ? L - d->s[np - 1] : d->s[e + 1] - d->s[e];
+            penw[j] += he;
+            penw[closing ? np - 1 : 0] += he;
+        }
+    }
+
+    // ---- parameter vectors [batch][ND]: vehicle parameters, host-side slots, parameter-only sub-expressions
+    std::vector<double> D((size_t)batch * v->ND, 0.0);
+    for (int b = 0; b < batch; ++b)
+    {
+        double* Db = D.data() + (size_t)b * v->ND;
+        std::memcpy(Db, d->vehicle_params + (size_t)b * nvp, nvp * sizeof(double));
+        if (v->P_F_WHEEL_SCALE >= 0)
+        {
+            // axle_car_3dof.hpp:294: wheel equations are scaled by 1/m when the wheels have no inertia
+            const double m = Db[0], If = Db[22], Ir = Db[26];
+            Db[v->P_F_WHEEL_SCALE] = If < 1.0e-10 ? 1.0 / m : 1.0;
+            Db[v->P_R_WHEEL_SCALE] = Ir < 1.0e-10 ? 1.0 / m : 1.0;
+        }
+        Db[v->P_SIGMA] = d->sigma;
+        Db[v->P_DISS0] = d->dissipation[0];
+        Db[v->P_DISS1] = d->dissipation[1];
+        v->derive(Db);
+    }
+
+    // ---- x with the fixed first node of open problems
+    std::vector<double> xfull((size_t)batch * np * NV, 0.0);
+    if (!d->closed)
+    {
+        const int time_idx = h->n_in - 3;
+        std::vector<double> x0(NV, 0.0);
+        int k = 0;
+        for (int j = 0; j < h->n_in; ++j) if (j != time_idx) x0[k++] = d->q0[j];
+        for (int c = 0; c < v->NFM; ++c) x0[v->CTRL_POS[c]] = d->u0[d->model == FL_MODEL_F1_3DOF ? 2 * c : c];
+        if (v->IS_DERIVATIVE) for (int c = 0; c < v->NFM; ++c) x0[v->DCTRL_POS[c]] = d->du0[c];
+        for (int b = 0; b < batch; ++b) std::memcpy(xfull.data() + (size_t)b * np * NV, x0.data(), NV * sizeof(double));
+    }
+
+    const int nblk = v->assemble_blocks(P);
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
+           && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+    h->d_xfull = dev_alloc<double>((size_t)batch * np * NV);
+    h->d_xuser = P.node0 ? dev_alloc<double>((size_t)batch * P.n) : h->d_xfull;
+    h->d_tc = dev_alloc<double>(tc.size());
+    h->d_D = dev_alloc<double>(D.size());
+    h->d_lambda = dev_alloc<double>((size_t)batch * P.m);
+    h->d_zeros = dev_alloc<double>(64);
+    h->d_V = dev_alloc<double>((size_t)batch * v->NVAL * np);
+    h->d_g = dev_alloc<double>((size_t)batch * P.m);
+    h->d_f = dev_alloc<double>(batch);
+    h->d_fpart = dev_alloc<double>((size_t)batch * nblk);
+    h->d_fcount = dev_alloc<unsigned int>(batch);
+    h->d_grad = dev_alloc<double>((size_t)batch * P.n);
+    h->d_jac = dev_alloc<double>((size_t)batch * P.nnz_jac);
+    h->d_hess = dev_alloc<double>((size_t)batch * P.nnz_hess);
+    ok = ok && h->d_xfull && h->d_xuser && h->d_tc && h->d_D && h->d_lambda && h->d_zeros && h->d_V && h->d_g && h->d_f && h->d_fpart
+            && h->d_fcount && h->d_grad && h->d_jac && h->d_hess;
+    ok = ok && cudaMemcpy(h->d_tc, tc.data(), tc.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess
+            && cudaMemcpy(h->d_D, D.data(), D.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess
+            && cudaMemcpy(h->d_xfull, xfull.data(), xfull.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok)
+    {
+        const std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        fl_nlp_destroy(h);
+        fail(msg);
+        return nullptr;
+    }
+    P.x = h->d_xfull; P.tc = h->d_tc; P.D = h->d_D; P.lambda = h->d_lambda; P.zeros = h->d_zeros;
+    P.V = h->d_V; P.g = h->d_g; P.f = h->d_f; P.f_partial = h->d_fpart; P.f_counter = h->d_fcount;
+    P.grad = h->d_grad; P.jac = h->d_jac; P.hess = h->d_hess;
+    build_structure(h);
+    return h;
+}
+
+void fl_nlp_sizes(const fl_nlp* h, int* n, int* m, int* nnz_jac, int* nnz_hess)
+{
+    if (n) *n = h->P.n;
+    if (m) *m = h->P.m;
+    if (nnz_jac) *nnz_jac = (int)h->P.nnz_jac;
+    if (nnz_hess) *nnz_hess = (int)h->P.nnz_hess;
+}
+
+int fl_nlp_batch(const fl_nlp* h) { return h->P.batch; }
+const char* fl_nlp_variant(const fl_nlp* h) { return h->v->name; }
+void fl_nlp_ops_per_node(const fl_nlp* h, int ops[4]) { ops[0] = h->v->OPS_VALUES; ops[1] = h->v->OPS_JAC; ops[2] = h->v->OPS_HESS; ops[3] = h->v->OPS_ALL; }
+long fl_kernel_launches(const fl_nlp* h) { return h->launches; }
+
+int fl_nlp_structure(const fl_nlp* h, int* jac_row, int* jac_col, int* hess_row, int* hess_col)
+{
+    if (jac_row) std::memcpy(jac_row, h->jac_row.data(), h->jac_row.size() * sizeof(int));
+    if (jac_col) std::memcpy(jac_col, h->jac_col.data(), h->jac_col.size() * sizeof(int));
+    if (hess_row) std::memcpy(hess_row, h->hess_row.data(), h->hess_row.size() * sizeof(int));
+    if (hess_col) std::memcpy(hess_col, h->hess_col.data(), h->hess_col.size() * sizeof(int));
+    return 1;
+}
+
+int fl_nlp_bounds(const fl_nlp* h, double* x_l, double* x_u, double* g_l, double* g_u)
+{
+    const fl_variant* v = h->v;
+    const fl_dev& P = h->P;
+    const int NV = v->NV, n_in = h->n_in;
+    const double big = std::numeric_limits<double>::max();
+    std::vector<double> lb(NV), ub(NV);
+    const double* par = h->params.data();        // bounds that depend on parameters use problem 0
+    if (h->desc.model == FL_MODEL_F1_3DOF)
+    {
+        // axle_car_3dof.hpp:366-397, chassis.hpp:400-425 (50..380 km/h, |v| <= 50 km/h, |omega| <= 10), chassis_car_3dof.hpp:306-352,
+        // road_curvilinear.hpp:63-82
+        const double l[13] = { -1, -1, -1, -1, 50.0 * KMH, -50.0 * KMH, -10.0, -3.0, -3.0, -3.0, -3.0, 0.0, -45.0 * DEG };
+        const double u[13] = { 1, 1, 1, 1, 380.0 * KMH, 50.0 * KMH, 10.0, -0.01, -0.01, -0.01, -0.01, 0.0, 45.0 * DEG };
+        for (int k = 0; k < 13; ++k) { lb[k] = l[k]; ub[k] = u[k]; }
+        lb[13] = -20.0 * DEG; ub[13] = 20.0 * DEG;      // steering
+        lb[14] = -1.0; ub[14] = 1.0;                    // throttle
+        if (v->IS_DERIVATIVE) { lb[15] = -20.0 * DEG; ub[15] = 20.0 * DEG; lb[16] = -10.0; ub[16] = 10.0; }   // limebeer2014f1.h:227-230, by control id
+    }
+    else
+    {
+        // axle_car_6dof.hpp:311-335, chassis.hpp:400-425 (10..200 km/h), chassis_car_6dof.hpp:320-365, road_curvilinear.hpp:63-82
+        const double l[12] = { 10.0 * KMH / 0.139, 10.0 * KMH, -10.0 * KMH, -10.0, 1.0e-5, -30.0 * DEG, -30.0 * DEG, -10.0, -10.0, -10.0, 0.0, -45.0 * DEG };
+        const double u[12] = { 200.0 * KMH / 0.139, 200.0 * KMH, 10.0 * KMH, 10.0, 0.139, 30.0 * DEG, 30.0 * DEG, 10.0, 10.0, 10.0, 0.0, 45.0 * DEG };
+        for (int k = 0; k < 12; ++k) { lb[k] = l[k]; ub[k] = u[k]; }
+        lb[12] = -20.0 * DEG; ub[12] = 20.0 * DEG;
+        lb[13] = -1.0; ub[13] = 1.0;
+        if (v->IS_DERIVATIVE)
+        {
+            const double r = h->desc.kart_direct_torque ? 4000.0 : 10.0;      // lot2016kart.h:186-192
+            lb[14] = -20.0 * DEG; ub[14] = 20.0 * DEG; lb[15] = -r; ub[15] = r;
+        }
+    }
+    const int n_pos = n_in - 3;      // position of the lateral displacement within the node variables
+    for (int vn = 0; vn < P.n_var_nodes; ++vn)
+    {
+        const int node = vn + P.node0;
+        for (int k = 0; k < NV; ++k)
+        {
+            if (x_l) x_l[(size_t)vn * NV + k] = (k == n_pos) ? -h->wl[node] : lb[k];
+            if (x_u) x_u[(size_t)vn * NV + k] = (k == n_pos) ? h->wr[node] : ub[k];
+        }
+    }
+    (void)big;
+    // constraints: equalities, then the 6 extra rows at the element's right node, then (derivative form) the control-rate rows
+    const int n_eq = v->NTD + v->NALG;
+    double el[6], eu[6];
+    for (int e = 0; e < P.n_elements; ++e)
+    {
+        const int j = (e + 1 == P.n_points) ? 0 : e + 1;
+        if (h->desc.model == FL_MODEL_F1_3DOF)
+        {
+            // limebeer2014f1.h:232-262: +-max(lambda_max(0), lambda_max(m g0)) per tyre, track limits for n +- t/2 cos(alpha)
+            const double m = par[0];
+            for (int t = 0; t < 4; ++t)
+            {
+                const double* tp = par + (t < 2 ? 32 : 45);
+                const double l1 = tp[9] * DEG, l2 = tp[10] * DEG, Fz1 = tp[1], Fz2 = tp[2];
+                const double a = (0.0 - Fz1) * (l2 - l1) / (Fz2 - Fz1) + l1, b = (m * G0 - Fz1) * (l2 - l1) / (Fz2 - Fz1) + l1;
+                eu[t] = a > b ? a : b; el[t] = -eu[t];
+            }
+            el[4] = el[5] = -h->wl[j]; eu[4] = eu[5] = h->wr[j];
+        }
+        else
+            for (int t = 0; t < 6; ++t) { el[t] = -0.11; eu[t] = 0.11; }      // lot2016kart.h:194-198
+        for (int r = 0; r < v->NCPE; ++r)
+        {
+            const bool ext = r >= n_eq && r < n_eq + 6;
+            if (g_l) g_l[(size_t)e * v->NCPE + r] = ext ? el[r - n_eq] : 0.0;
+            if (g_u) g_u[(size_t)e * v->NCPE + r] = ext ? eu[r - n_eq] : 0.0;
+        }
+    }
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+double* fl_dev_x(fl_nlp* h) { return h->d_xuser; }
+double* fl_dev_lambda(fl_nlp* h) { return h->d_lambda; }
+const double* fl_dev_f(fl_nlp* h) { return h->d_f; }
+const double* fl_dev_g(fl_nlp* h) { return h->d_g; }
+const double* fl_dev_grad(fl_nlp* h) { return h->d_grad; }
+const double* fl_dev_jac(fl_nlp* h) { return h->d_jac; }
+const double* fl_dev_hess(fl_nlp* h) { return h->d_hess; }
+void* fl_nlp_stream(fl_nlp* h) { return (void*)h->stream; }
+
+int fl_nlp_sync(fl_nlp* h)
+{
+    FL_CUDA(cudaSetDevice(h->device));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    return 1;
+}
+
+int fl_eval_device(fl_nlp* h, int what, double obj_factor)
+{
+    FL_CUDA(cudaSetDevice(h->device));
+    if (!scatter_x(h)) return 0;
+    fl_dev P = h->P;
+    P.obj_factor = obj_factor;
+    if (what & FL_EVAL_FG)
+    {
+        h->v->launch_values(P, h->stream);
+        h->v->launch_assemble(P, h->stream);
+        h->launches += 2;
+    }
+    const int dw = ((what & FL_EVAL_JAC) ? FL_DERIV_JAC : 0) | ((what & FL_EVAL_HESS) ? FL_DERIV_HESS : 0);
+    if (dw) { h->v->launch_derivs(P, dw, h->stream); h->launches += 1; }
+    FL_CUDA(cudaGetLastError());
+    return 1;
+}
+
+double fl_time_device(fl_nlp* h, int what, double obj_factor, int reps)
+{
+    if (cudaSetDevice(h->device) != cudaSuccess || reps < 1) return -1.0;
+    if (cudaEventRecord(h->ev0, h->stream) != cudaSuccess) return -1.0;
+    for (int r = 0; r < reps; ++r) if (!fl_eval_device(h, what, obj_factor)) return -1.0;
+    if (cudaEventRecord(h->ev1, h->stream) != cudaSuccess) return -1.0;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) { g_error = cudaGetErrorString(cudaGetLastError()); return -1.0; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    return (double)ms / reps;
+}
+
+int fl_flush_l2(fl_nlp* h)
+{
+    FL_CUDA(cudaSetDevice(h->device));
+    if (!h->d_flush)
+    {
+        int l2 = 0;
+        FL_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
+        h->flush_bytes = 2 * (size_t)(l2 > 0 ? l2 : (128 << 20));
+        FL_CUDA(cudaMalloc(&h->d_flush, h->flush_bytes));
+    }
+    FL_CUDA(cudaMemsetAsync(h->d_flush, 0, h->flush_bytes, h->stream));
+    return 1;
+}
+
+void* fl_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_error = cudaGetErrorString(cudaGetLastError()); return nullptr; }
+    return p;
+}
+
+void fl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int fl_eval_all(fl_nlp* h, const double* x, const double* lambda, double obj_factor,
+                double* f, double* g, double* grad_f, double* jac_values, double* hess_values)
+{
+    FL_CUDA(cudaSetDevice(h->device));
+    const fl_dev& P = h->P;
+    const size_t B = P.batch;
+    if (!x) return fail("x is null") ? 1 : 0;
+    FL_CUDA(cudaMemcpyAsync(h->d_xuser, x, B * P.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (hess_values)
+    {
+        if (!lambda) return fail("lambda is null") ? 1 : 0;
+        FL_CUDA(cudaMemcpyAsync(h->d_lambda, lambda, B * P.m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    const int what = ((f || g) ? FL_EVAL_FG : 0) | ((grad_f || jac_values) ? FL_EVAL_JAC : 0) | (hess_values ? FL_EVAL_HESS : 0);
+    if (!fl_eval_device(h, what, obj_factor)) return 0;
+    if (f) FL_CUDA(cudaMemcpyAsync(f, h->d_f, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (g) FL_CUDA(cudaMemcpyAsync(g, h->d_g, B * P.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (grad_f) FL_CUDA(cudaMemcpyAsync(grad_f, h->d_grad, B * P.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (jac_values) FL_CUDA(cudaMemcpyAsync(jac_values, h->d_jac, B * P.nnz_jac * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (hess_values) FL_CUDA(cudaMemcpyAsync(hess_values, h->d_hess, B * P.nnz_hess * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    h->values_valid = (what & FL_EVAL_FG) != 0;
+    h->derivs_jac_valid = (what & FL_EVAL_JAC) != 0;
+    return 1;
+}
+
+// ---- Ipopt C-interface callbacks: problem 0 of the batch ----------------------------------------------------------------
+static int upload_x(fl_nlp* h, int n, const double* x, int new_x)
+{
+    if (n != h->P.n) return fail("eval: wrong number of variables") ? 1 : 0;
+    if (new_x)
+    {
+        FL_CUDA(cudaSetDevice(h->device));
+        FL_CUDA(cudaMemcpyAsync(h->d_xuser, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->values_valid = h->derivs_jac_valid = false;
+    }
+    return 1;
+}
+
+static int ensure_values(fl_nlp* h)
+{
+    if (h->values_valid) return 1;
+    if (!fl_eval_device(h, FL_EVAL_FG, 1.0)) return 0;
+    h->values_valid = true;
+    return 1;
+}
+
+int fl_eval_f(int n, const double* x, int new_x, double* obj_value, void* ud)
+{
+    fl_nlp* h = (fl_nlp*)ud;
+    if (!upload_x(h, n, x, new_x) || !ensure_values(h)) return 0;
+    FL_CUDA(cudaMemcpyAsync(obj_value, h->d_f, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    return 1;
+}
+
+int fl_eval_g(int n, const double* x, int new_x, int m, double* g, void* ud)
+{
+    fl_nlp* h = (fl_nlp*)ud;
+    if (m != h->P.m) return fail("eval_g: wrong number of constraints") ? 1 : 0;
+    if (!upload_x(h, n, x, new_x) || !ensure_values(h)) return 0;
+    FL_CUDA(cudaMemcpyAsync(g, h->d_g, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    return 1;
+}
+
+static int ensure_jac(fl_nlp* h)
+{
+    if (h->derivs_jac_valid) return 1;
+    if (!fl_eval_device(h, FL_EVAL_JAC, 1.0)) return 0;
+    h->derivs_jac_valid = true;
+    return 1;
+}
+
+int fl_eval_grad_f(int n, const double* x, int new_x, double* grad_f, void* ud)
+{
+    fl_nlp* h = (fl_nlp*)ud;
+    if (!upload_x(h, n, x, new_x) || !ensure_jac(h)) return 0;
+    FL_CUDA(cudaMemcpyAsync(grad_f, h->d_grad, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    return 1;
+}
+
+int fl_eval_jac_g(int n, const double* x, int new_x, int m, int nele_jac, int* iRow, int* jCol, double* values, void* ud)
+{
+    fl_nlp* h = (fl_nlp*)ud;
+    if (nele_jac != (int)h->P.nnz_jac || m != h->P.m) return fail("eval_jac_g: wrong sizes") ? 1 : 0;
+    if (!values) return fl_nlp_structure(h, iRow, jCol, nullptr, nullptr);
+    if (!upload_x(h, n, x, new_x) || !ensure_jac(h)) return 0;
+    FL_CUDA(cudaMemcpyAsync(values, h->d_jac, (size_t)nele_jac * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    return 1;
+}
+
+int fl_eval_h(int n, const double* x, int new_x, double obj_factor, int m, const double* lambda, int new_lambda,
+              int nele_hess, int* iRow, int* jCol, double* values, void* ud)
+{
+    fl_nlp* h = (fl_nlp*)ud;
+    (void)new_lambda;
+    if (nele_hess != (int)h->P.nnz_hess || m != h->P.m) return fail("eval_h: wrong sizes") ? 1 : 0;
+    if (!values) return fl_nlp_structure(h, nullptr, nullptr, iRow, jCol);
+    if (!upload_x(h, n, x, new_x)) return 0;
+    FL_CUDA(cudaMemcpyAsync(h->d_lambda, lambda, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (!fl_eval_device(h, FL_EVAL_HESS, obj_factor)) return 0;
+    FL_CUDA(cudaMemcpyAsync(values, h->d_hess, (size_t)nele_hess * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FL_CUDA(cudaStreamSynchronize(h->stream));
+    return 1;
+}
+
+} // extern "C"

@@ -1,0 +1,283 @@
+// Collocation NLP callbacks on sm_100a: kernel templates over a generated node program (csrc/generated/gen_*.cuh).
+//
+// What the reference computes by sweeping one CppAD tape over all mesh nodes on one CPU thread
+// (Optimal_laptime::FG_direct / FG_derivative::compute, src/core/applications/optimal_laptime.hpp:1226-1657, evaluated
+// through lion::ipopt_cppad_solve, :546-551) is split here into three data-parallel passes, one thread per collocation
+// node (or element), fp64 throughout:
+//
+//   k_node_values   x_j -> node values V (states, s-derivatives, algebraic rows, extra constraints, dt/ds)
+//   k_assemble      elements: trapezoidal / algebraic / extra / control-rate rows g, and the objective f
+//   k_node_derivs   x_j, lambda, obj_factor -> grad f, the node's two Jacobian blocks, its Lagrangian-Hessian block
+//
+// Layout in HBM (all fp64):
+//   xfull  [problem][node][NV]      node-major, the reference's variable order (optimal_laptime.hpp:1269-1303); the fixed
+//                                   first node of open problems occupies slot 0 and is filled by the host
+//   tc     [NTC][node]              per-node track / mesh constants, structure-of-arrays, shared by the whole batch
+//   D      [problem][ND]            vehicle parameters followed by their parameter-only sub-expressions
+//   V      [problem][NVAL][node]    structure-of-arrays
+//   g, lambda [problem][element][NCPE]   element-major, the reference's constraint order (optimal_laptime.hpp:413-483)
+//   grad   [problem][var node][NV]
+//   jac    [problem]{ A[NJA][element] , B[NJB][element with a free left node] }   slot-major: consecutive threads write
+//   hess   [problem]{ H[NH][var node] , C[NCPL][coupled element] }               consecutive addresses (coalesced)
+// The triplet (row, col) of every slot is fixed at problem creation (fl_nlp_structure); Ipopt's triplet format accepts
+// any fixed order, so the order is chosen for the GPU, not for the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+struct fl_dev
+{
+    int n_points, n_elements, n_var_nodes, node0, closed, batch;
+    int nB, nC;                  // number of elements that carry a B block / a control coupling
+    int n, m;                    // variables / constraints per problem (user-visible sizes)
+    long nnz_jac, nnz_hess;      // per problem
+    const double* x;             // [batch][n_points*NV]
+    const double* tc;            // [NTC][n_points]
+    const double* D;             // [batch][ND]
+    const double* lambda;        // [batch][m]
+    const double* zeros;         // >= NCPE zeros
+    double obj_factor;
+    double* V;                   // [batch][NVAL][n_points]
+    double* g;                   // [batch][m]
+    double* f;                   // [batch]
+    double* f_partial;           // [batch][n_blocks_assemble]
+    unsigned int* f_counter;     // [batch]
+    double* grad;                // [batch][n]
+    double* jac;                 // [batch][nnz_jac]
+    double* hess;                // [batch][nnz_hess]
+};
+
+constexpr int FL_BLOCK = 128;
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class G>
+struct ValuesIO
+{
+    const double* xn; const double* tcn; const double* Dp; double* Vn; int np;
+    __device__ __forceinline__ double x(int k) const { return xn[k]; }
+    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + (size_t)k * np); }
+    __device__ __forceinline__ double d(int k) const { return __ldg(Dp + k); }
+    __device__ __forceinline__ void val(int k, double v) const { Vn[(size_t)k * np] = v; }
+};
+
+template <class G>
+__global__ void __launch_bounds__(FL_BLOCK) k_node_values(fl_dev P)
+{
+    const int node = blockIdx.x * FL_BLOCK + threadIdx.x;
+    const int prob = blockIdx.y;
+    if (node >= P.n_points) return;
+    ValuesIO<G> io;
+    io.xn = P.x + ((size_t)prob * P.n_points + node) * G::NV;
+    io.tcn = P.tc + node;
+    io.Dp = P.D + (size_t)prob * G::ND;
+    io.Vn = P.V + (size_t)prob * G::NVAL * P.n_points + node;
+    io.np = P.n_points;
+    G::values(io);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Element assembly.  V offsets: Q [0,NTD) QD [NTD,2NTD) ALG EXT DTDS CDOT.
+template <class G>
+__global__ void __launch_bounds__(FL_BLOCK) k_assemble(fl_dev P)
+{
+    constexpr int oQ = 0, oQD = G::NTD, oALG = 2 * G::NTD, oEXT = oALG + G::NALG, oDT = oEXT + G::NEXT, oCD = oDT + 1;
+    const int e = blockIdx.x * FL_BLOCK + threadIdx.x;
+    const int prob = blockIdx.y;
+    const int np = P.n_points;
+    double fe = 0.0;
+    if (e < P.n_elements)
+    {
+        const int i = e;
+        const int j = (e + 1 == np) ? 0 : e + 1;
+        const bool closing = (e + 1 == np);
+        const double* D = P.D + (size_t)prob * G::ND;
+        const double sigma = __ldg(D + G::P_SIGMA), oms = 1.0 - sigma;
+        const double h = __ldg(P.tc + (size_t)(G::NTRACK + 1) * np + i);           // hout of the left node
+        const double* V = P.V + (size_t)prob * G::NVAL * np;
+        const double* xi = P.x + ((size_t)prob * np + i) * G::NV;
+        const double* xj = P.x + ((size_t)prob * np + j) * G::NV;
+        double* g = P.g + (size_t)prob * P.m + (size_t)e * G::NCPE;
+        int row = 0;
+#pragma unroll
+        for (int r = 0; r < G::NTD; ++r, ++row)
+            g[row] = V[(size_t)(oQ + r) * np + j] - V[(size_t)(oQ + r) * np + i]
+                   - h * (oms * V[(size_t)(oQD + r) * np + i] + sigma * V[(size_t)(oQD + r) * np + j]);
+#pragma unroll
+        for (int r = 0; r < G::NALG; ++r, ++row) g[row] = V[(size_t)(oALG + r) * np + j];
+#pragma unroll
+        for (int r = 0; r < G::NEXT; ++r, ++row) g[row] = V[(size_t)(oEXT + r) * np + j];
+        fe = h * (oms * V[(size_t)oDT * np + i] + sigma * V[(size_t)oDT * np + j]);
+        if (G::IS_DERIVATIVE)
+        {
+            // control-rate rows (optimal_laptime.hpp:1573-1583, 1632-1641) and penalty (:1553, :1611; the left rate is
+            // taken at node 0 for every non-closing element, as the reference's dcontrols_dt[i-i] does)
+            const double* xl = P.x + ((size_t)prob * np + (closing ? np - 1 : 0)) * G::NV;
+#pragma unroll
+            for (int c = 0; c < G::NCR; ++c, ++row)
+            {
+                g[row] = xj[G::ctrl_pos(c)] - xi[G::ctrl_pos(c)]
+                       - h * (oms * V[(size_t)(oCD + c) * np + i] + sigma * V[(size_t)(oCD + c) * np + j]);
+                const double dl = xl[G::dctrl_pos(c)], dr = xj[G::dctrl_pos(c)];
+                fe += 0.5 * __ldg(D + G::P_DISS0 + c) * (dl * dl + dr * dr) * h;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int c = 0; c < G::NFM; ++c)
+            {
+                const double derivative = (xj[G::ctrl_pos(c)] - xi[G::ctrl_pos(c)]) / h;     // optimal_laptime.hpp:1362-1366
+                fe += __ldg(D + G::P_DISS0 + c) * (derivative * derivative) * h;
+            }
+        }
+    }
+    // objective: fixed-order block tree, then the last block to finish adds the block partials in index order
+    __shared__ double red[FL_BLOCK];
+    __shared__ bool last;
+    red[threadIdx.x] = fe;
+    __syncthreads();
+#pragma unroll
+    for (int s = FL_BLOCK / 2; s > 0; s >>= 1)
+    {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    double* part = P.f_partial + (size_t)prob * gridDim.x;
+    if (threadIdx.x == 0)
+    {
+        part[blockIdx.x] = red[0];
+        __threadfence();
+        const unsigned int t = atomicInc(P.f_counter + prob, gridDim.x - 1);      // wraps back to 0 for the next launch
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0)
+    {
+        __threadfence();
+        double acc = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) acc += ((volatile double*)part)[b];
+        P.f[prob] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class G>
+struct DerivIO
+{
+    const double* xn; const double* xp; const double* xq;     // this node, previous node, next node
+    const double* tcn; const double* Dp; const double* lin_; const double* lout_;
+    double obj_; int np;
+    double* gradn; double* ja_; double* jb_; double* h_; double* c_;
+    size_t sA, sB, sH, sC;
+    bool hasB, hasC;
+    __device__ __forceinline__ double x(int k) const { return xn[k]; }
+    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + (size_t)k * np); }
+    __device__ __forceinline__ double d(int k) const { return __ldg(Dp + k); }
+    __device__ __forceinline__ double lin(int r) const { return lin_[r]; }
+    __device__ __forceinline__ double lout(int r) const { return lout_[r]; }
+    __device__ __forceinline__ double obj() const { return obj_; }
+    __device__ __forceinline__ double uprev(int c) const { return xp[G::ctrl_pos(c)]; }
+    __device__ __forceinline__ double unext(int c) const { return xq[G::ctrl_pos(c)]; }
+    __device__ __forceinline__ void val(int, double) const {}
+    __device__ __forceinline__ void grad(int k, double v) const { gradn[k] = v; }
+    __device__ __forceinline__ void ja(int k, double v) const { ja_[k * sA] = v; }
+    __device__ __forceinline__ void jb(int k, double v) const { if (hasB) jb_[k * sB] = v; }
+    __device__ __forceinline__ void h(int k, double v) const { h_[k * sH] = v; }
+    __device__ __forceinline__ void cpl(int k, double v) const { if (hasC) c_[k * sC] = v; }
+};
+
+enum { FL_DERIV_JAC = 1, FL_DERIV_HESS = 2, FL_DERIV_ALL = 3 };
+
+template <class G, int WHAT>
+__global__ void __launch_bounds__(FL_BLOCK) k_node_derivs(fl_dev P)
+{
+    const int vn = blockIdx.x * FL_BLOCK + threadIdx.x;       // variable-node index
+    const int prob = blockIdx.y;
+    if (vn >= P.n_var_nodes) return;
+    const int np = P.n_points;
+    const int node = vn + P.node0;
+    const int prev = (node == 0) ? np - 1 : node - 1;
+    const int next = (node + 1 == np) ? 0 : node + 1;
+    const int e_in = prev;                                     // element e starts at node e
+    const int e_out = node;
+    const bool has_out = P.closed || (node + 1 < np);
+    const double* xb = P.x + (size_t)prob * np * G::NV;
+    const double* lam = P.lambda + (size_t)prob * P.m;
+    DerivIO<G> io;
+    io.xn = xb + (size_t)node * G::NV;
+    io.xp = xb + (size_t)prev * G::NV;
+    io.xq = xb + (size_t)next * G::NV;
+    io.tcn = P.tc + node;
+    io.Dp = P.D + (size_t)prob * G::ND;
+    io.lin_ = lam + (size_t)e_in * G::NCPE;
+    io.lout_ = has_out ? lam + (size_t)e_out * G::NCPE : P.zeros;
+    io.obj_ = P.obj_factor;
+    io.np = np;
+    io.gradn = P.grad + (size_t)prob * P.n + (size_t)vn * G::NV;
+    double* jac = P.jac + (size_t)prob * P.nnz_jac;
+    double* hes = P.hess + (size_t)prob * P.nnz_hess;
+    io.sA = P.n_elements; io.sB = P.nB; io.sH = P.n_var_nodes; io.sC = P.nC;
+    io.ja_ = jac + e_in;
+    // B blocks / couplings exist for elements whose left node is free: all of them on closed laps, e >= 1 on open ones
+    io.hasB = has_out && (e_out >= P.node0);
+    io.jb_ = jac + (size_t)G::NJA * P.n_elements + (e_out - P.node0);
+    io.h_ = hes + vn;
+    io.hasC = (e_in >= P.node0);
+    io.c_ = hes + (size_t)G::NH * P.n_var_nodes + (e_in - P.node0);
+    if (WHAT == FL_DERIV_JAC) G::jac(io);
+    else if (WHAT == FL_DERIV_HESS) G::hess(io);
+    else G::all(io);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// What the C-ABI layer sees of a variant (one translation unit per variant fills this in).
+struct fl_variant
+{
+    const char* name;
+    int NV, NCPE, NTD, NALG, NEXT, NCR, NFM, NVAL, NTC, NTRACK, NRAW, ND, NJA, NJB, NH, NCPL, IS_DERIVATIVE, IS_3D;
+    int OPS_VALUES, OPS_JAC, OPS_HESS, OPS_ALL;
+    const int *CTRL_POS, *DCTRL_POS, *JA_ROW, *JA_COL, *JB_ROW, *JB_COL, *H_ROW, *H_COL;
+    int P_SIGMA, P_DISS0, P_DISS1, P_F_WHEEL_SCALE, P_R_WHEEL_SCALE;     // -1 when the model has no such slot
+    void (*derive)(double* D);
+    void (*launch_values)(const fl_dev&, cudaStream_t);
+    void (*launch_assemble)(const fl_dev&, cudaStream_t);
+    void (*launch_derivs)(const fl_dev&, int what, cudaStream_t);
+    int (*assemble_blocks)(const fl_dev&);
+};
+
+template <class G> struct has_wheel_scale { template <class T> static auto test(int) -> decltype(T::P_F_WHEEL_SCALE, char()); template <class T> static long test(...);
+                                            static constexpr bool value = sizeof(test<G>(0)) == 1; };
+template <class G, bool = has_wheel_scale<G>::value> struct wheel_slots { static constexpr int f = -1, r = -1; };
+template <class G> struct wheel_slots<G, true> { static constexpr int f = G::P_F_WHEEL_SCALE, r = G::P_R_WHEEL_SCALE; };
+
+template <class G>
+struct variant_ops
+{
+    static dim3 grid(int items, int batch) { return dim3((items + FL_BLOCK - 1) / FL_BLOCK, batch, 1); }
+    static void values(const fl_dev& P, cudaStream_t s) { k_node_values<G><<<grid(P.n_points, P.batch), FL_BLOCK, 0, s>>>(P); }
+    static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<grid(P.n_elements, P.batch), FL_BLOCK, 0, s>>>(P); }
+    static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_BLOCK - 1) / FL_BLOCK; }
+    static void derivs(const fl_dev& P, int what, cudaStream_t s)
+    {
+        const dim3 g = grid(P.n_var_nodes, P.batch);
+        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC><<<g, FL_BLOCK, 0, s>>>(P);
+        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS><<<g, FL_BLOCK, 0, s>>>(P);
+        else k_node_derivs<G, FL_DERIV_ALL><<<g, FL_BLOCK, 0, s>>>(P);
+    }
+    static fl_variant make()
+    {
+        fl_variant v;
+        v.name = G::name;
+        v.NV = G::NV; v.NCPE = G::NCPE; v.NTD = G::NTD; v.NALG = G::NALG; v.NEXT = G::NEXT; v.NCR = G::NCR; v.NFM = G::NFM;
+        v.NVAL = G::NVAL; v.NTC = G::NTC; v.NTRACK = G::NTRACK; v.NRAW = G::NRAW; v.ND = G::ND;
+        v.NJA = G::NJA; v.NJB = G::NJB; v.NH = G::NH; v.NCPL = G::NCPL; v.IS_DERIVATIVE = G::IS_DERIVATIVE; v.IS_3D = G::IS_3D;
+        v.OPS_VALUES = G::OPS_VALUES; v.OPS_JAC = G::OPS_JAC; v.OPS_HESS = G::OPS_HESS; v.OPS_ALL = G::OPS_ALL;
+        v.CTRL_POS = G::CTRL_POS; v.DCTRL_POS = G::DCTRL_POS;
+        v.JA_ROW = G::JA_ROW; v.JA_COL = G::JA_COL; v.JB_ROW = G::JB_ROW; v.JB_COL = G::JB_COL; v.H_ROW = G::H_ROW; v.H_COL = G::H_COL;
+        v.P_SIGMA = G::P_SIGMA; v.P_DISS0 = G::P_DISS0; v.P_DISS1 = G::P_DISS1;
+        v.P_F_WHEEL_SCALE = wheel_slots<G>::f; v.P_R_WHEEL_SCALE = wheel_slots<G>::r;
+        v.derive = &G::derive;
+        v.launch_values = &values; v.launch_assemble = &assemble; v.launch_derivs = &derivs; v.assemble_blocks = &assemble_blocks;
+        return v;
+    }
+};

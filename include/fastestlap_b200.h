@@ -1,0 +1,114 @@
+/* fastestlap_b200.h -- C ABI of the B200-native collocation-NLP callbacks of fastest-lap.
+ *
+ * Drop-in boundary.  In the reference the collocation NLP reaches Ipopt through a C++ functor
+ *     FG::operator()(ADvector& fg, const ADvector& x)        src/core/applications/optimal_laptime.h:281-287, 329-335
+ * handed to lion::ipopt_cppad_solve                           src/core/applications/optimal_laptime.hpp:546-551
+ * which implements Ipopt::TNLP (eval_f, eval_grad_f, eval_g, eval_jac_g, eval_h) by sweeping a CppAD tape.
+ * This library replaces tape + sweeps: the functions below have the signatures of Ipopt's C interface
+ * (IpStdCInterface.h: Eval_F_CB, Eval_Grad_F_CB, Eval_G_CB, Eval_Jac_G_CB, Eval_H_CB; `user_data` = fl_nlp*), so the
+ * handle can be given to CreateIpoptProblem as it is, or driven by any other interior-point loop.
+ *
+ * Conventions (Ipopt's): indices are 0-based (C style); eval_jac_g / eval_h called with values == NULL return the
+ * sparsity structure in iRow/jCol; the Hessian is the lower triangle of obj_factor * d2f + sum_i lambda_i d2g_i;
+ * duplicated (row, col) pairs are to be summed.  Callbacks return 1 on success and 0 on failure (fl_last_error()).
+ * No C++ exception crosses this boundary.  Host pointers everywhere unless a function says "device".
+ * A handle is not re-entrant (as the reference's functor, optimal_laptime.h:222-243); different handles are independent.
+ * There is no CPU fallback: every entry point fails if no CUDA device is usable.
+ */
+#ifndef FASTESTLAP_B200_H
+#define FASTESTLAP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fl_nlp fl_nlp;
+
+enum { FL_MODEL_F1_3DOF = 0, FL_MODEL_KART_6DOF = 1 };   /* limebeer2014f1 (vehicles/limebeer2014f1.h), lot2016kart (vehicles/lot2016kart.h) */
+enum { FL_FORM_DIRECT = 0, FL_FORM_DERIVATIVE = 1 };     /* Optimal_laptime::compute_direct / compute_derivative */
+
+/* Number of entries of the vehicle parameter vector of a model (order: fastest_lap_b200/vehicle.py F1_PARAM_PATHS /
+ * KART_PARAM_PATHS, the XML paths of the reference's DECLARE_PARAMS tables). */
+int fl_n_vehicle_params(int model);
+
+/* Problem description; replaces the constructor arguments of Optimal_laptime<Dynamic_model_t>
+ * (src/core/applications/optimal_laptime.h:98-120) once vehicle and track have been evaluated at the mesh. */
+typedef struct fl_problem_desc
+{
+    int model;                  /* FL_MODEL_*                                                                          */
+    int form;                   /* FL_FORM_*                                                                           */
+    int closed;                 /* 1: closed circuit (n_elements = n_points), 0: open section (first node fixed)       */
+    int elevation;              /* 1: track with pitch/roll/z (F1 only; all 13 equations become differential)          */
+    int kart_direct_torque;     /* kart: rear-axle control is a torque (enable_direct_torque) instead of throttle      */
+    int n_points;
+    const double* s;            /* [n_points] arclength mesh, strictly increasing                                      */
+    double track_length;
+    const double* track_nodes;  /* [n_points][6]: yaw, pitch, roll, yaw', pitch', roll' at the mesh nodes              */
+    const double* wl;           /* [n_points] left track limit  (road.lateral-displacement >= -wl)                    */
+    const double* wr;           /* [n_points] right track limit                                                        */
+    int batch;                  /* >= 1 independent problems sharing mesh and layout                                   */
+    const double* vehicle_params; /* [batch][fl_n_vehicle_params(model)]                                               */
+    double sigma;               /* trapezoidal weight, 0.5 in the reference (optimal_laptime.h:33-58)                 */
+    double dissipation[2];      /* of the two full-mesh controls: steering, throttle|torque                            */
+    const double* q0;           /* open problems: inputs of node 0   [n_inputs]  (14 F1, 13 kart)                      */
+    const double* u0;           /* open problems: controls of node 0 [n_controls] (4 F1, 2 kart)                       */
+    const double* du0;          /* open problems, derivative form: control rates of node 0 [2]                         */
+    const double* ctrl_default; /* value of every control [n_controls]; used for the ones that are not optimised       */
+    int device;                 /* CUDA device ordinal                                                                 */
+} fl_problem_desc;
+
+fl_nlp* fl_nlp_create(const fl_problem_desc* desc);       /* NULL on failure */
+void    fl_nlp_destroy(fl_nlp* nlp);
+const char* fl_last_error(void);
+
+/* get_nlp_info: sizes of ONE problem of the batch */
+void fl_nlp_sizes(const fl_nlp* nlp, int* n, int* m, int* nnz_jac, int* nnz_hess);
+int  fl_nlp_batch(const fl_nlp* nlp);
+const char* fl_nlp_variant(const fl_nlp* nlp);
+/* get_bounds_info (optimal_laptime.hpp:326-483): model default bounds, track limits on the lateral displacement */
+int fl_nlp_bounds(const fl_nlp* nlp, double* x_l, double* x_u, double* g_l, double* g_u);
+/* fixed sparsity (triplets), same for every problem of the batch */
+int fl_nlp_structure(const fl_nlp* nlp, int* jac_row, int* jac_col, int* hess_row, int* hess_col);
+/* fp64 operations per node of each pass (values, jac, hess, all): the algorithmic work the roofline is quoted on */
+void fl_nlp_ops_per_node(const fl_nlp* nlp, int ops[4]);
+
+/* Ipopt C-interface callbacks (problem 0 of the batch); user_data = fl_nlp*. */
+int fl_eval_f     (int n, const double* x, int new_x, double* obj_value, void* user_data);
+int fl_eval_grad_f(int n, const double* x, int new_x, double* grad_f, void* user_data);
+int fl_eval_g     (int n, const double* x, int new_x, int m, double* g, void* user_data);
+int fl_eval_jac_g (int n, const double* x, int new_x, int m, int nele_jac, int* iRow, int* jCol, double* values, void* user_data);
+int fl_eval_h     (int n, const double* x, int new_x, double obj_factor, int m, const double* lambda, int new_lambda,
+                   int nele_hess, int* iRow, int* jCol, double* values, void* user_data);
+
+/* Whole batch, one call: every output may be NULL.  Arrays are [batch][...] contiguous. */
+int fl_eval_all(fl_nlp* nlp, const double* x, const double* lambda, double obj_factor,
+                double* f, double* g, double* grad_f, double* jac_values, double* hess_values);
+
+/* Device-resident path (what an on-device interior-point loop uses): pointers are device pointers on the handle's
+ * device and stay owned by the handle; inputs are read from fl_dev_x / fl_dev_lambda.  `what` is a bit mask. */
+enum { FL_EVAL_FG = 1, FL_EVAL_JAC = 2, FL_EVAL_HESS = 4 };
+double* fl_dev_x(fl_nlp* nlp);          /* [batch][n] */
+double* fl_dev_lambda(fl_nlp* nlp);     /* [batch][m] */
+const double* fl_dev_f(fl_nlp* nlp);    /* [batch]    */
+const double* fl_dev_g(fl_nlp* nlp);    /* [batch][m] */
+const double* fl_dev_grad(fl_nlp* nlp); /* [batch][n] */
+const double* fl_dev_jac(fl_nlp* nlp);  /* [batch][nnz_jac]  */
+const double* fl_dev_hess(fl_nlp* nlp); /* [batch][nnz_hess] */
+int  fl_eval_device(fl_nlp* nlp, int what, double obj_factor);   /* enqueue on the handle's stream, no synchronisation */
+int  fl_nlp_sync(fl_nlp* nlp);
+void* fl_nlp_stream(fl_nlp* nlp);                                /* cudaStream_t */
+/* Times `reps` back-to-back enqueues of `what` with CUDA events on the handle's stream; returns ms per enqueue (< 0 on error). */
+double fl_time_device(fl_nlp* nlp, int what, double obj_factor, int reps);
+long fl_kernel_launches(const fl_nlp* nlp);                      /* kernels launched by this handle so far */
+/* Writes a scratch buffer larger than the L2 cache on the handle's stream (benchmark hygiene between timed iterations). */
+int  fl_flush_l2(fl_nlp* nlp);
+/* Page-locked host memory for the host-buffer entry points (pageable memory works too, at lower PCIe throughput). */
+void* fl_host_alloc(size_t bytes);
+void  fl_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,134 @@
+"""Parity of the CUDA callbacks (through the C-ABI, host buffers) with the CPU oracle.
+
+Tolerance (BASELINE.json north_star): callback values and derivative entries within 1e-10 relative, fp64.  "Relative" is
+taken against max(|reference entry|, 1) for f, g and grad f, and against max(|reference entry|, largest entry of the same
+row block / 1e3, 1e-3) for matrix entries: entries that are the difference of O(1e3) terms cannot carry more digits.
+Entries are compared by (row, col) with duplicates summed -- never by position.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests.helpers import load_golden, oracle_nlp
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell"]
+RTOL = 1.0e-10
+
+
+def _csr(rows, cols, vals, shape):
+    return sp.coo_matrix((vals, (rows, cols)), shape=shape).tocsr()
+
+
+def _matrix_close(A, B, what):
+    """A: candidate, B: reference; both CSR with duplicates already summed."""
+    D = (A - B).tocoo()
+    if D.nnz == 0:
+        return
+    Babs = abs(B)
+    rowmax = np.asarray(Babs.max(axis=1).todense()).ravel()
+    ref = np.asarray(Babs[D.row, D.col]).ravel()
+    scale = np.maximum(np.maximum(ref, rowmax[D.row] * 1.0e-3), 1.0e-3)
+    err = np.abs(D.data) / scale
+    k = int(np.argmax(err))
+    assert err[k] <= RTOL, "%s: entry (%d, %d) differs by %.3e relative (ref %.6e)" % (what, D.row[k], D.col[k], err[k], ref[k])
+
+
+def _points(p, ex, count=3, seed=0):
+    """The golden point plus seeded perturbations of it (x (1 + 0.01 N) + 1e-3 N)."""
+    rng = np.random.default_rng(seed)
+    pts = [(ex["x"], ex["lam"], 1.0)]
+    for _ in range(count - 1):
+        x = ex["x"] * (1.0 + 0.01 * rng.standard_normal(p.n)) + 1.0e-3 * rng.standard_normal(p.n)
+        pts.append((x, rng.standard_normal(p.m), float(rng.uniform(0.1, 1.0))))
+    return pts
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    from fastest_lap_b200.nlp import CollocationNLP
+    p, ex = load_golden(request.param)
+    nlp = CollocationNLP(p)
+    yield p, ex, nlp, oracle_nlp(p)
+    nlp.close()
+
+
+def test_sizes_match_reference_layout(case):
+    p, ex, nlp, o = case
+    assert (nlp.n, nlp.m) == (p.n, p.m) == (o.n, o.m)
+    jr, jc, hr, hc = nlp.structure()
+    assert jr.min() >= 0 and jr.max() < p.m and jc.min() >= 0 and jc.max() < p.n
+    assert np.all(hr >= hc) and hr.max() < p.n            # lower triangle
+
+
+def test_callbacks_match_oracle(case):
+    p, ex, nlp, o = case
+    jr, jc, hr, hc = nlp.structure()
+    for x, lam, obj in _points(p, ex):
+        ref = o.eval(x, lam, obj)
+        out = nlp.eval_all(x, lam, obj)
+        assert abs(out["f"][0] - ref["f"]) <= RTOL * max(1.0, abs(ref["f"]))
+        assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
+        assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
+        _matrix_close(_csr(jr, jc, out["jac"][0], (p.m, p.n)), _csr(*ref["jac"], (p.m, p.n)), "jacobian")
+        _matrix_close(_csr(hr, hc, out["hess"][0], (p.n, p.n)), _csr(*ref["hess"], (p.n, p.n)), "hessian")
+
+
+def test_ipopt_style_callbacks_agree_with_fused_call(case):
+    p, ex, nlp, o = case
+    x, lam, obj = _points(p, ex, 2, seed=3)[1]
+    out = nlp.eval_all(x, lam, obj)
+    assert nlp.eval_f(x, True) == out["f"][0]
+    assert np.array_equal(nlp.eval_g(x, False), out["g"][0])
+    assert np.array_equal(nlp.eval_grad_f(x, False), out["grad"][0])
+    assert np.array_equal(nlp.eval_jac_g(x, False), out["jac"][0])
+    h = nlp.eval_h(x, lam, obj, False)
+    np.testing.assert_allclose(h, out["hess"][0], rtol=1e-13, atol=1e-13)
+
+
+def test_golden_point_is_a_kkt_point_on_the_gpu(case):
+    p, ex, nlp, o = case
+    out = nlp.eval_all(ex["x"], ex["lam"], 1.0)
+    jr, jc, hr, hc = nlp.structure()
+    JTl = np.zeros(p.n)
+    np.add.at(JTl, jc, out["jac"][0] * ex["lam"][jr])
+    assert np.abs(out["grad"][0] + JTl - ex["zl"] + ex["zu"]).max() < 5.0e-10
+
+
+def test_batch_of_parameter_sets_matches_single_problems():
+    from fastest_lap_b200.nlp import CollocationNLP
+    p, ex = load_golden("f1_catalunya_chicane")
+    rng = np.random.default_rng(2)
+    B = 5
+    params = np.tile(p.params, (B, 1))
+    params[:, 0] = rng.uniform(620, 760, B)        # mass
+    params[:, 6] = rng.uniform(0.8, 1.1, B)        # cd
+    params[:, 7] = rng.uniform(2.6, 3.4, B)        # cl
+    params[:, 30] = rng.uniform(650, 800, B)       # engine power
+    xs = np.stack([ex["x"] * (1 + 0.01 * rng.standard_normal(p.n)) for _ in range(B)])
+    lams = rng.standard_normal((B, p.m))
+    nlp = CollocationNLP(p, params)
+    out = nlp.eval_all(xs, lams, 0.5)
+    for b in (0, B - 1):
+        pb = type(p)(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.wl, p.wr, params[b], p.dissipation, p.sigma, p.elevation,
+                     p.q0, p.u0, p.du0, None, p.kart_direct_torque)
+        single = CollocationNLP(pb)
+        ob = single.eval_all(xs[b], lams[b], 0.5)
+        for k in ("f", "g", "grad", "jac", "hess"):
+            assert np.array_equal(ob[k][0], out[k][b]), k
+        single.close()
+    nlp.close()
+
+
+def test_empty_and_invalid_inputs_are_rejected():
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.problem import LapProblem
+    p, ex = load_golden("f1_catalunya_chicane")
+    with pytest.raises(ValueError):
+        LapProblem(p.model, p.form, True, p.s[:1], p.track_length, p.track_nodes[:1], p.wl[:1], p.wr[:1], p.params)
+    bad = type(p)(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.wl, p.wr, p.params, p.dissipation, p.sigma, p.elevation, p.q0, p.u0, p.du0)
+    nlp = CollocationNLP(bad)
+    with pytest.raises(AssertionError):
+        nlp.eval_all(ex["x"][:-1], ex["lam"])
+    nlp.close()
