@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: collocation node-evals/s (g + Jacobian + Hessian) on the F1 3DOF Catalunya lap refined to
+8000 nodes (BASELINE.json configs[2], the configuration the north_star target is quoted on).
+
+A step = one full callback round (f, g, grad f, Jacobian values, Lagrangian-Hessian values) over every node of the lap.
+  value   node-evals/s with x and lambda resident in HBM (CUDA events on the library's stream, L2 flushed between steps)
+  e2e     the same through the C-ABI call with HOST buffers: x, lambda host->device and f, g, grad, jac, hess device->host
+          inside the timed region (pinned memory)
+  --impl reference   the CPU oracle port (oracle/, OpenMP over nodes, all host cores) on the same workload
+Under torchrun every rank evaluates its own lap on its own GPU (weak scaling, no data-path collective; one NCCL
+all_gather of the objective values at the end); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "collocation node-evals/s (g+Jac+Hess), F1 3DOF Catalunya 8000 nodes"
+UNIT = "node-evals/s"
+N_NODES = 8000
+
+
+def workload(n_nodes=N_NODES):
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.problem import LapProblem
+    p = workloads.f1_catalunya(n_nodes)
+    gp, ex = LapProblem.load_npz(os.path.join(ROOT, "tests", "golden", "f1_catalunya_discrete.npz"))
+    x = workloads.resample_point(p, gp.s, ex["x"], p.nv)
+    lam = np.random.default_rng(1).standard_normal(p.m)
+    return p, x, lam
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_baseline(p, x, lam, budget_s=12.0, threads=0):
+    """Times the CPU oracle port on a bounded sample: whole callback rounds of the same lap, about `budget_s` seconds."""
+    from tests.helpers import oracle_nlp
+    from oracle import oracle as orc
+    o = oracle_nlp(p)
+    cores = int(orc.lib().orc_max_threads()) if threads == 0 else threads
+    t1 = o.time_eval(x, lam, 1.0, reps=1, threads=cores)
+    reps = max(1, min(200, int(budget_s / max(t1, 1e-6))))
+    t = o.time_eval(x, lam, 1.0, reps=reps, threads=cores)
+    return {"value": p.n_points / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d full callback rounds (f, g, grad, Jacobian, Hessian) of the %d-node lap, C++ second-order jets, OpenMP over nodes" % (reps, p.n_points)}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p, x, lam = workload()
+    from tests.helpers import oracle_nlp
+    from oracle import oracle as orc
+    o = oracle_nlp(p)
+    cores = int(orc.lib().orc_max_threads())
+    for _ in range(min(args.warmup, 2)):
+        o.time_eval(x, lam, 1.0, reps=1, threads=cores)
+    steps = min(args.steps, 50)
+    t = o.time_eval(x, lam, 1.0, reps=steps, threads=cores)
+    v = p.n_points / t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "limebeer-2014-f1 3DOF, Catalunya, closed, direct form, 8000 trapezoidal nodes, one full callback round per step",
+                       "nodes": p.n_points, "n": p.n, "m": p.m},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d full callback rounds of the %d-node lap on the CPU oracle port (the reference itself cannot be built offline)" % (steps, p.n_points)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nodes", type=int, default=N_NODES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, pinned_empty
+    p, x, lam = workload(args.nodes)
+    nlp = CollocationNLP(p, device=local)
+    B = nlp.batch
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    # pinned host buffers for the end-to-end leg
+    hx, _ = pinned_empty(B * nlp.n); hl, _ = pinned_empty(B * nlp.m)
+    hx[:] = x; hl[:] = lam
+    out = {}
+    for k, cnt in (("f", B), ("g", B * nlp.m), ("grad", B * nlp.n), ("jac", B * nlp.nnz_jac), ("hess", B * nlp.nnz_hess)):
+        out[k], _ = pinned_empty(cnt)
+    nlp.eval_all(hx, hl, 1.0, out=out)             # also leaves x, lambda resident on the device
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        nlp.sync()
+
+    # ---- device-resident leg
+    for _ in range(W):
+        nlp.flush_l2(); nlp.time_device(EVAL_ALL, 1.0, 1)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    launches0 = nlp.kernel_launches
+    dev_ms = 0.0
+    for _ in range(K):
+        nlp.flush_l2()
+        dev_ms += nlp.time_device(EVAL_ALL, 1.0, 1)
+    barrier()
+    launches = nlp.kernel_launches - launches0
+    # dominant kernel alone (grad f + Jacobian + Hessian of every node), same hygiene
+    ker_ms = 0.0
+    for _ in range(K):
+        nlp.flush_l2()
+        ker_ms += nlp.time_device(EVAL_JAC | EVAL_HESS, 1.0, 1)
+    fg_ms = 0.0
+    for _ in range(K):
+        nlp.flush_l2()
+        fg_ms += nlp.time_device(EVAL_FG, 1.0, 1)
+    # ---- end-to-end leg: host buffers in, host buffers out
+    for _ in range(3):
+        nlp.eval_all(hx, hl, 1.0, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        nlp.eval_all(hx, hl, 1.0, out=out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s, ker_ms, fg_ms], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fs = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(fs, torch.tensor([float(out["f"][0])], dtype=torch.float64, device="cuda"))     # the final gather of results
+    dev_ms, e2e_s, ker_ms, fg_ms = [float(v) for v in t.tolist()]
+
+    if rank == 0:
+        nodes = p.n_points * B * world
+        ms_per_step = dev_ms / K
+        v = nlp.variant
+        # algorithmic bytes of the dominant kernel per node-eval: read x, lambda, per-node constants; write grad, Jacobian, Hessian slots
+        nv, ncpe = p.nv, p.ncpe
+        per_node_read = (nv + ncpe + 5) * 8
+        per_node_write = nv * 8 + (nlp.nnz_jac + nlp.nnz_hess) * 8 / p.n_points
+        ker_bytes = (per_node_read + per_node_write) * p.n_points * B
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = ker_bytes / (ker_ms / K * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": nodes / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "limebeer-2014-f1 3DOF, Catalunya, closed, direct form, %d trapezoidal nodes, one full callback round per step" % p.n_points,
+                           "nodes": p.n_points, "laps_per_gpu": B, "n": nlp.n, "m": nlp.m, "nnz_jac": nlp.nnz_jac, "nnz_hess": nlp.nnz_hess, "variant": v,
+                           "point": "golden 500-node solution interpolated to the mesh, lambda ~ N(0,1) seed 1, obj_factor 1",
+                           "l2": "flushed between steps (memset of 2x L2 size, untimed)", "parallelism": "1 lap per GPU, replicas"},
+                "e2e": {"value": nodes / (e2e_s / K), "unit": UNIT, "h2d_bytes_per_step": int(B * (nlp.n + nlp.m) * 8),
+                        "d2h_bytes_per_step": int(B * (1 + nlp.m + nlp.n + nlp.nnz_jac + nlp.nnz_hess) * 8), "ms_per_step": e2e_s / K * 1e3},
+                "gpu_launches": int(launches),
+                "kernels_ms": {"values+assemble": fg_ms / K, "node_derivs": ker_ms / K},
+                "roofline": {"bound": "hbm", "kernel": "k_node_derivs<%s, all>" % v, "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                             "bytes_per_node_eval": per_node_read + per_node_write, "fp64_ops_per_node_eval": nlp.ops_per_node["all"]},
+                "clocks": clocks}
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_baseline(p, x, lam)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    nlp.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

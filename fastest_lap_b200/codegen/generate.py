@@ -6,9 +6,11 @@ Each header defines `struct gen_<variant>` with the sizes and sparsity tables of
 function templates over an accessor object `io`:
 
     values(io)   node values handed to the element assembly (eval_f, eval_g)
-    jac(io)      gradient of f and the two Jacobian blocks of the node (eval_grad_f, eval_jac_g)
-    hess(io)     lower triangle of the node's Lagrangian-Hessian block + control-rate couplings (eval_h)
-    all(io)      the three above in one pass (shared sub-expressions computed once)
+    jac_part(w, io)   gradient of f and the two Jacobian blocks of the node (eval_grad_f, eval_jac_g), w-th code partition
+    hess_part(w, io)  lower triangle of the node's Lagrangian-Hessian block + control-rate couplings (eval_h)
+    all_part(w, io)   both in one pass
+The derivative outputs of a node are split into NP_* partitions of balanced operation count (shared sub-expressions are
+recomputed per partition); partition w is executed by warp w of a block, the 32 lanes of a warp being 32 nodes.
 
 plus the host function `derive(D)` that fills the parameter-only sub-expressions after the raw vehicle parameters.
 The code is what the CppAD tape sweeps of the reference compute (lion::ipopt_cppad_solve, call site
@@ -23,6 +25,9 @@ from .emit import Emitter, ParamTable, emit_host_derive
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "..", "csrc", "generated")
 
+# warps (= straight-line code partitions) per group of 32 nodes in each derivative kernel
+NPARTS = {"jac": 4, "hess": 8, "all": 8}
+
 VARIANTS = {
     "f1_direct": Variant("f1", "direct"),
     "f1_derivative": Variant("f1", "derivative"),
@@ -33,6 +38,26 @@ VARIANTS = {
     "kart_direct_torque": Variant("kart", "direct", direct_torque=True),
     "kart_derivative_torque": Variant("kart", "derivative", direct_torque=True),
 }
+
+
+def _cone(g, outs):
+    from .expr import CONST, SYM, NEG
+    return set(n for n in g.topo(outs) if g.kind[n] not in (CONST, SYM, NEG))
+
+
+def partition(g, groups, n_parts):
+    """Splits output groups (lists of (expr, statement) pairs) into `n_parts` lists so that the largest part's operation
+    count -- the union of the expression cones of its outputs, shared sub-expressions counted once -- is small: groups are
+    taken by decreasing cone size and each goes to the part whose cone grows to the smallest size.  One part = one warp
+    of the derivative kernel: every warp runs different straight-line code over the same 32 nodes."""
+    cones = sorted(((_cone(g, [e for e, _ in grp]), grp) for grp in groups if grp), key=lambda c: -len(c[0]))
+    bins = [set() for _ in range(n_parts)]
+    outs = [[] for _ in range(n_parts)]
+    for c, grp in cones:
+        b = min(range(n_parts), key=lambda i: (len(bins[i] | c), len(bins[i])))
+        bins[b] |= c
+        outs[b] += grp
+    return outs, [len(b) for b in bins]
 
 
 def _int_table(name, vals):
@@ -88,11 +113,26 @@ def generate(name, variant):
         head = "\n".join("        " + l for l in sum(pres, []))
         return ("    template <class IO> static __device__ __forceinline__ void %s(IO& io)\n    {\n%s\n%s\n    }\n" % (fname, head, body))
 
+    # output groups that share most of their expression cone: per variable k the k-th Jacobian column (+ df/dx_k) and the
+    # k-th column of the Hessian's lower triangle
+    grp_j, grp_h = [], []
+    for k in range(p.nv):
+        grp_j.append([out_grad[k]] + [o for o, key in zip(out_ja, ja) if key[1] == k] + [o for o, key in zip(out_jb, jb) if key[1] == k])
+        grp_h.append([o for o, key in zip(out_h, hs) if key[1] == k])
+    grp_h.append(out_c)
     parts = []
     parts.append(fn("values", out_values, [pre]))
-    parts.append(fn("jac", out_grad + out_ja + out_jb, [pre, pre_n]))
-    parts.append(fn("hess", out_h + out_c, [pre, pre_w]))
-    parts.append(fn("all", out_values + out_grad + out_ja + out_jb + out_h + out_c, [pre, pre_w, pre_n]))
+    part_sizes = {}
+    for mode, groups, pres in (("jac", grp_j, [pre, pre_n]), ("hess", grp_h, [pre, pre_w]), ("all", grp_j + grp_h, [pre, pre_w, pre_n])):
+        outs, sizes = partition(g, groups, NPARTS[mode])
+        part_sizes[mode] = sizes
+        for w, o in enumerate(outs):
+            parts.append(fn("%s_p%d" % (mode, w), o, pres))
+        disp = ["    template <class IO> static __device__ __forceinline__ void %s_part(int w, IO& io)" % mode, "    {", "        switch (w)", "        {"]
+        for w in range(len(outs)):
+            disp.append("        case %d: %s_p%d(io); break;" % (w, mode, w))
+        disp += ["        default: break;", "        }", "    }", ""]
+        parts.append("\n".join(disp))
     host = emit_host_derive(g, pt, "derive")
     host = "    static inline " + host.replace("\n", "\n    ")
 
@@ -117,6 +157,9 @@ def generate(name, variant):
     L.append("    static constexpr int NVAL = %d, NTC = %d, NTRACK = %d, NRAW = %d, ND = %d;" % (len(p.values), len(tnames), len(p.track_names), len(raw_names), pt.size))
     L.append("    static constexpr int NJA = %d, NJB = %d, NH = %d, NCPL = %d;" % (len(ja), len(jb), len(hs), len(p.coupling)))
     L.append("    static constexpr int IS_DERIVATIVE = %d, IS_3D = %d;" % (int(variant.form == "derivative"), int(variant.elevation)))
+    L.append("    static constexpr int NP_JAC = %d, NP_HESS = %d, NP_ALL = %d;   // code partitions (warps per 32 nodes)" % (NPARTS["jac"], NPARTS["hess"], NPARTS["all"]))
+    for mode in ("jac", "hess", "all"):
+        L.append("    // %s partition operation counts: %s (sum %d)" % (mode, part_sizes[mode], sum(part_sizes[mode])))
     L.append("    static constexpr int OPS_VALUES = %d, OPS_JAC = %d, OPS_HESS = %d, OPS_ALL = %d;" %
              (sum(counts_val.values()), sum(counts_jac.values()), sum(counts_hes.values()), sum(counts_all.values())))
     L.append(_int_table("CTRL_POS", p.ctrl_pos))

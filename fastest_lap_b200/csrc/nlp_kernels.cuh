@@ -8,6 +8,7 @@
 //   k_node_values   x_j -> node values V (states, s-derivatives, algebraic rows, extra constraints, dt/ds)
 //   k_assemble      elements: trapezoidal / algebraic / extra / control-rate rows g, and the objective f
 //   k_node_derivs   x_j, lambda, obj_factor -> grad f, the node's two Jacobian blocks, its Lagrangian-Hessian block
+//                   (lane = node, warp = one of N balanced partitions of the node's derivative outputs)
 //
 // Layout in HBM (all fp64):
 //   xfull  [problem][node][NV]      node-major, the reference's variable order (optimal_laptime.hpp:1269-1303); the fixed
@@ -188,10 +189,18 @@ struct DerivIO
 
 enum { FL_DERIV_JAC = 1, FL_DERIV_HESS = 2, FL_DERIV_ALL = 3 };
 
+template <class G, int WHAT> struct deriv_parts { };
+template <class G> struct deriv_parts<G, FL_DERIV_JAC>  { static constexpr int N = G::NP_JAC;  template <class IO> static __device__ __forceinline__ void run(int w, IO& io) { G::jac_part(w, io); } };
+template <class G> struct deriv_parts<G, FL_DERIV_HESS> { static constexpr int N = G::NP_HESS; template <class IO> static __device__ __forceinline__ void run(int w, IO& io) { G::hess_part(w, io); } };
+template <class G> struct deriv_parts<G, FL_DERIV_ALL>  { static constexpr int N = G::NP_ALL;  template <class IO> static __device__ __forceinline__ void run(int w, IO& io) { G::all_part(w, io); } };
+
+// One block = 32 nodes x N code partitions: lane = node, warp = partition.  Every warp runs its own straight-line code
+// (no divergence inside a warp), so a lap of 8000 nodes spreads over 250 blocks x N warps instead of 63 blocks x 4 warps.
 template <class G, int WHAT>
-__global__ void __launch_bounds__(FL_BLOCK) k_node_derivs(fl_dev P)
+__global__ void __launch_bounds__(32 * deriv_parts<G, WHAT>::N) k_node_derivs(fl_dev P)
 {
-    const int vn = blockIdx.x * FL_BLOCK + threadIdx.x;       // variable-node index
+    const int vn = blockIdx.x * 32 + (threadIdx.x & 31);     // variable-node index
+    const int part = threadIdx.x >> 5;
     const int prob = blockIdx.y;
     if (vn >= P.n_var_nodes) return;
     const int np = P.n_points;
@@ -224,9 +233,7 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_derivs(fl_dev P)
     io.h_ = hes + vn;
     io.hasC = (e_in >= P.node0);
     io.c_ = hes + (size_t)G::NH * P.n_var_nodes + (e_in - P.node0);
-    if (WHAT == FL_DERIV_JAC) G::jac(io);
-    else if (WHAT == FL_DERIV_HESS) G::hess(io);
-    else G::all(io);
+    deriv_parts<G, WHAT>::run(part, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -259,10 +266,10 @@ struct variant_ops
     static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_BLOCK - 1) / FL_BLOCK; }
     static void derivs(const fl_dev& P, int what, cudaStream_t s)
     {
-        const dim3 g = grid(P.n_var_nodes, P.batch);
-        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC><<<g, FL_BLOCK, 0, s>>>(P);
-        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS><<<g, FL_BLOCK, 0, s>>>(P);
-        else k_node_derivs<G, FL_DERIV_ALL><<<g, FL_BLOCK, 0, s>>>(P);
+        const dim3 g((P.n_var_nodes + 31) / 32, P.batch, 1);
+        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC><<<g, 32 * G::NP_JAC, 0, s>>>(P);
+        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS><<<g, 32 * G::NP_HESS, 0, s>>>(P);
+        else k_node_derivs<G, FL_DERIV_ALL><<<g, 32 * G::NP_ALL, 0, s>>>(P);
     }
     static fl_variant make()
     {

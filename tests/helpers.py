@@ -29,3 +29,82 @@ def equality_rows(p):
 def rel_err(a, b, floor=1.0):
     a, b = np.asarray(a), np.asarray(b)
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)) if a.size else 0.0
+
+
+# ---- 40-digit evaluation of the symbolic node program (the ground truth where fp64 conditioning limits entry-wise parity)
+def truth_node(p, x, lam, obj, node, digits=40):
+    """Exact (mpmath) gradient / Jacobian blocks / Hessian block of one collocation node, from the same expression DAG the
+    CUDA code is generated from, evaluated with `digits` significant digits.  Returns dict of {(row, col): float}."""
+    import mpmath as mp
+    from fastest_lap_b200.codegen.nlpnode import Variant, NodeProgram
+    from fastest_lap_b200.codegen import expr as X
+    mp.mp.dps = digits
+    key = (p.model, p.form, p.elevation, p.kart_direct_torque)
+    prog = _PROGRAMS.get(key)
+    if prog is None:
+        prog = _PROGRAMS[key] = NodeProgram(Variant("f1" if p.model == 0 else "kart", "direct" if p.form == 0 else "derivative", p.elevation,
+                                                    p.kart_direct_torque))
+    g = prog.g
+    NV, NCPE, n = prog.nv, prog.ncpe, p.n_points
+    node0 = 0 if p.closed else 1
+    xfull = np.zeros((n, NV))
+    xfull[node0:] = np.asarray(x).reshape(-1, NV)
+    if not p.closed:
+        time_idx = (14 if p.model == 0 else 13) - 3
+        q = [p.q0[j] for j in range(len(p.q0)) if j != time_idx]
+        u = [p.u0[0], p.u0[2]] if p.model == 0 else [p.u0[0], p.u0[1]]
+        xfull[0, :len(q) + 2] = q + u
+        if p.form != 0:
+            xfull[0, len(q) + 2:] = p.du0
+    lam = np.asarray(lam).reshape(-1, NCPE)
+    s, L = p.s, p.track_length
+    hin = s[node] - s[node - 1] if node > 0 else (L - s[-1] if p.closed else 0.0)
+    hout = s[node + 1] - s[node] if node + 1 < n else (L - s[-1] if p.closed else 0.0)
+    prev, nxt = (node - 1) % n, (node + 1) % n
+    env = {"x%d" % k: xfull[node, k] for k in range(NV)}
+    th, mu, ph, dth, dmu, dph = p.track_nodes[node]
+    trk = dict(kx=dph - np.sin(mu) * dth, ky=np.cos(ph) * dmu + np.cos(mu) * np.sin(ph) * dth, kz=-np.sin(ph) * dmu + np.cos(mu) * np.cos(ph) * dth,
+               smu=np.sin(mu), cmu=np.cos(mu), sph=np.sin(ph), cph=np.cos(ph), hin=hin, hout=hout,
+               ihin=1.0 / hin if hin > 0 else 0.0, ihout=1.0 / hout if hout > 0 else 0.0)
+    if p.form != 0:
+        penw = 0.0
+        for e in range(p.n_elements):
+            closing = e + 1 == n
+            he = L - s[-1] if closing else s[e + 1] - s[e]
+            penw += he * ((1 if (0 if closing else e + 1) == node else 0) + (1 if (n - 1 if closing else 0) == node else 0))
+        trk["penw"] = penw
+    for nm in prog.track_names + prog.geom_names:
+        env["t_" + nm] = trk[nm]
+    m = p.params[0]
+    host = dict(sigma=p.sigma, diss0=p.dissipation[0], diss1=p.dissipation[1])
+    if p.model == 0:
+        host.update(f_wheel_scale=1.0 / m if p.params[22] < 1e-10 else 1.0, r_wheel_scale=1.0 / m if p.params[26] < 1e-10 else 1.0)
+    for k, nm in enumerate(prog.param_names):
+        env["p_" + nm] = p.params[k] if k < len(p.params) else host[nm]
+    e_in = prev
+    has_out = p.closed or node + 1 < n
+    for r in range(NCPE):
+        env["lin%d" % r] = lam[e_in, r]
+        env["lout%d" % r] = lam[node, r] if has_out else 0.0
+    env["obj"] = obj
+    for c in range(len(prog.uprev)):
+        env["uprev%d" % c] = xfull[prev, prog.ctrl_pos[c]]
+        env["unext%d" % c] = xfull[nxt, prog.ctrl_pos[c]]
+    fn = {X.SQRT: mp.sqrt, X.SIN: mp.sin, X.COS: mp.cos, X.ATAN: mp.atan, X.TANH: mp.tanh, X.EXP: mp.exp}
+    groups = dict(hess=prog.hess, jacA=prog.jacA, jacB=prog.jacB, grad={(k, 0): e for k, e in enumerate(prog.gradf)})
+    roots = [e for d in groups.values() for e in d.values()]
+    val = {}
+    for i in g.topo(roots):
+        k, a, b = g.kind[i], g.a[i], g.b[i]
+        if k == X.CONST: val[i] = mp.mpf(a)
+        elif k == X.SYM: val[i] = mp.mpf(float(env[a]))
+        elif k == X.ADD: val[i] = val[a] + val[b]
+        elif k == X.SUB: val[i] = val[a] - val[b]
+        elif k == X.MUL: val[i] = val[a] * val[b]
+        elif k == X.NEG: val[i] = -val[a]
+        elif k == X.RCP: val[i] = 1 / val[a]
+        else: val[i] = fn[k](val[a])
+    return {name: {key_: float(val[e]) for key_, e in d.items()} for name, d in groups.items()}
+
+
+_PROGRAMS = {}
