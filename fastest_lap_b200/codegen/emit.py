@@ -53,8 +53,10 @@ class ParamTable:
 class Emitter:
     """Emits one function body: `inputs` maps symbol name -> C expression; outputs are (expr id, "statement with one %s") pairs."""
 
-    def __init__(self, graph, ptable, inputs, dfmt="D[%d]"):
-        self.g, self.pt, self.inputs, self.dfmt = graph, ptable, inputs, dfmt
+    def __init__(self, graph, ptable, inputs, dfmt="D[%d]", cut=None):
+        # cut: node id -> C expression that LOADS the node's value (a checkpoint written by an earlier pass) instead of
+        # recomputing it; the load is emitted lazily, right before the first use
+        self.g, self.pt, self.inputs, self.dfmt, self.cut = graph, ptable, inputs, dfmt, (cut or {})
 
     def body(self, outputs, indent="    "):
         g, pt = self.g, self.pt
@@ -66,7 +68,7 @@ class Emitter:
         needed = g.topo([e for e, _ in outputs])
         sin_of, cos_of = {}, {}
         for i in needed:
-            if pt.param_only(i):
+            if pt.param_only(i) or i in self.cut:
                 continue
             if K[i] == SIN:
                 sin_of[A[i]] = i
@@ -90,6 +92,10 @@ class Emitter:
             while stack:
                 n, done = stack.pop()
                 if n in name or K[n] == CONST:
+                    continue
+                if n in self.cut:
+                    name[n] = "t%d" % n
+                    lines.append("%sconst double t%d = %s;" % (indent, n, self.cut[n]))
                     continue
                 if K[n] != SYM and pt.param_only(n):
                     s = pt.slot(n)

@@ -5,7 +5,7 @@
 Each header defines `struct gen_<variant>` with the sizes and sparsity tables of the variant and four static device
 function templates over an accessor object `io`:
 
-    values(io)   node values handed to the element assembly (eval_f, eval_g)
+    values(io)   node values handed to the element assembly (eval_f, eval_g) + the node's checkpoints (see checkpoints())
     jac_part(w, io)   gradient of f and the two Jacobian blocks of the node (eval_grad_f, eval_jac_g), w-th code partition
     hess_part(w, io)  lower triangle of the node's Lagrangian-Hessian block + control-rate couplings (eval_h)
     all_part(w, io)   both in one pass
@@ -40,17 +40,40 @@ VARIANTS = {
 }
 
 
-def _cone(g, outs):
+def _cone(g, outs, stop=()):
+    """Operation nodes needed for `outs`, not descending below the nodes in `stop` (checkpoints are loaded, not recomputed)."""
     from .expr import CONST, SYM, NEG
-    return set(n for n in g.topo(outs) if g.kind[n] not in (CONST, SYM, NEG))
+    seen, res, stack = set(), set(), list(outs)
+    while stack:
+        n = stack.pop()
+        if n in seen:
+            continue
+        seen.add(n)
+        k = g.kind[n]
+        if k in (CONST, SYM) or n in stop:
+            continue
+        if k != NEG:
+            res.add(n)
+        stack.extend(g.operands(n))
+    return res
 
 
-def partition(g, groups, n_parts):
+def checkpoints(g, pt, outs):
+    """The expensive primal intermediates below the derivative outputs: every sin/cos/atan/tanh/exp/reciprocal/sqrt whose
+    argument depends on the node variables.  Each expands to 10-80 SASS instructions; the values pass computes them once per
+    node and stores them, the derivative partitions load them (one coalesced 8-byte load each) and are left with plain
+    multiply-add arithmetic."""
+    from .expr import SIN, COS, ATAN, TANH, EXP, RCP, SQRT
+    heavy = (SIN, COS, ATAN, TANH, EXP, RCP, SQRT)
+    return [n for n in g.topo(outs) if g.kind[n] in heavy and not pt.param_only(n)]
+
+
+def partition(g, groups, n_parts, stop=()):
     """Splits output groups (lists of (expr, statement) pairs) into `n_parts` lists so that the largest part's operation
     count -- the union of the expression cones of its outputs, shared sub-expressions counted once -- is small: groups are
     taken by decreasing cone size and each goes to the part whose cone grows to the smallest size.  One part = one warp
     of the derivative kernel: every warp runs different straight-line code over the same 32 nodes."""
-    cones = sorted(((_cone(g, [e for e, _ in grp]), grp) for grp in groups if grp), key=lambda c: -len(c[0]))
+    cones = sorted(((_cone(g, [e for e, _ in grp], stop), grp) for grp in groups if grp), key=lambda c: -len(c[0]))
     bins = [set() for _ in range(n_parts)]
     outs = [[] for _ in range(n_parts)]
     for c, grp in cones:
@@ -107,8 +130,13 @@ def generate(name, variant):
     out_h = [(p.hess[key], "io.h(%d, %%s);" % k) for k, key in enumerate(hs)]
     out_c = [(e, "io.cpl(%d, %%s);" % k) for k, e in enumerate(p.coupling)]
 
-    def fn(fname, outputs, pres):
-        em = Emitter(g, pt, inputs, dfmt="io.d(%d)")
+    # checkpoints: slot k of the per-node checkpoint buffer holds node ck[k]
+    ck = checkpoints(g, pt, [e for e, _ in out_grad + out_ja + out_jb + out_h + out_c])
+    cut = {n: "io.c(%d)" % k for k, n in enumerate(ck)}
+    out_ck = [(n, "io.cs(%d, %%s);" % k) for k, n in enumerate(ck)]
+
+    def fn(fname, outputs, pres, use_cut=True):
+        em = Emitter(g, pt, inputs, dfmt="io.d(%d)", cut=cut if use_cut else None)
         body = em.body(outputs, indent="        ")
         head = "\n".join("        " + l for l in sum(pres, []))
         return ("    template <class IO> static __device__ __forceinline__ void %s(IO& io)\n    {\n%s\n%s\n    }\n" % (fname, head, body))
@@ -121,10 +149,10 @@ def generate(name, variant):
         grp_h.append([o for o, key in zip(out_h, hs) if key[1] == k])
     grp_h.append(out_c)
     parts = []
-    parts.append(fn("values", out_values, [pre]))
+    parts.append(fn("values", out_values + out_ck, [pre], use_cut=False))
     part_sizes = {}
     for mode, groups, pres in (("jac", grp_j, [pre, pre_n]), ("hess", grp_h, [pre, pre_w]), ("all", grp_j + grp_h, [pre, pre_w, pre_n])):
-        outs, sizes = partition(g, groups, NPARTS[mode])
+        outs, sizes = partition(g, groups, NPARTS[mode], stop=set(ck))
         part_sizes[mode] = sizes
         for w, o in enumerate(outs):
             parts.append(fn("%s_p%d" % (mode, w), o, pres))
@@ -154,7 +182,7 @@ def generate(name, variant):
     L.append("    static constexpr const char* name = \"%s\";" % name)
     L.append("    static constexpr int NV = %d, NCPE = %d, NTD = %d, NALG = %d, NEXT = %d, NCR = %d, NFM = %d;" %
              (p.nv, p.ncpe, p.n_td, p.n_alg, p.n_ext, p.n_ctrl_rows, p.n_fm))
-    L.append("    static constexpr int NVAL = %d, NTC = %d, NTRACK = %d, NRAW = %d, ND = %d;" % (len(p.values), len(tnames), len(p.track_names), len(raw_names), pt.size))
+    L.append("    static constexpr int NVAL = %d, NTC = %d, NTRACK = %d, NRAW = %d, ND = %d, NCK = %d;" % (len(p.values), len(tnames), len(p.track_names), len(raw_names), pt.size, len(ck)))
     L.append("    static constexpr int NJA = %d, NJB = %d, NH = %d, NCPL = %d;" % (len(ja), len(jb), len(hs), len(p.coupling)))
     L.append("    static constexpr int IS_DERIVATIVE = %d, IS_3D = %d;" % (int(variant.form == "derivative"), int(variant.elevation)))
     L.append("    static constexpr int NP_JAC = %d, NP_HESS = %d, NP_ALL = %d;   // code partitions (warps per 32 nodes)" % (NPARTS["jac"], NPARTS["hess"], NPARTS["all"]))

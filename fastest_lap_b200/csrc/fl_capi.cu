@@ -72,7 +72,7 @@ struct fl_nlp
     fl_dev P{};
     // owned device buffers
     double *d_xfull = nullptr, *d_xuser = nullptr, *d_tc = nullptr, *d_D = nullptr, *d_lambda = nullptr, *d_zeros = nullptr;
-    double *d_V = nullptr, *d_g = nullptr, *d_f = nullptr, *d_fpart = nullptr, *d_grad = nullptr, *d_jac = nullptr, *d_hess = nullptr;
+    double *d_C = nullptr, *d_V = nullptr, *d_g = nullptr, *d_f = nullptr, *d_fpart = nullptr, *d_grad = nullptr, *d_jac = nullptr, *d_hess = nullptr;
     unsigned int* d_fcount = nullptr;
     std::vector<double> s, wl, wr, params;
     std::vector<int> jac_row, jac_col, hess_row, hess_col;
@@ -149,7 +149,7 @@ void fl_nlp_destroy(fl_nlp* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    double* bufs[] = { h->d_xfull, h->P.node0 ? h->d_xuser : nullptr, h->d_tc, h->d_D, h->d_lambda, h->d_zeros, h->d_V, h->d_g, h->d_f, h->d_fpart,
+    double* bufs[] = { h->d_xfull, h->P.node0 ? h->d_xuser : nullptr, h->d_tc, h->d_D, h->d_lambda, h->d_zeros, h->d_V, h->d_C, h->d_g, h->d_f, h->d_fpart,
                        h->d_grad, h->d_jac, h->d_hess };
     for (double* b : bufs) if (b) cudaFree(b);
     if (h->d_fcount) cudaFree(h->d_fcount);
@@ -290,6 +290,7 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
     h->d_lambda = dev_alloc<double>((size_t)batch * P.m);
     h->d_zeros = dev_alloc<double>(64);
     h->d_V = dev_alloc<double>((size_t)batch * v->NVAL * np);
+    h->d_C = dev_alloc<double>((size_t)batch * v->NCK * np);
     h->d_g = dev_alloc<double>((size_t)batch * P.m);
     h->d_f = dev_alloc<double>(batch);
     h->d_fpart = dev_alloc<double>((size_t)batch * nblk);
@@ -297,7 +298,7 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
     h->d_grad = dev_alloc<double>((size_t)batch * P.n);
     h->d_jac = dev_alloc<double>((size_t)batch * P.nnz_jac);
     h->d_hess = dev_alloc<double>((size_t)batch * P.nnz_hess);
-    ok = ok && h->d_xfull && h->d_xuser && h->d_tc && h->d_D && h->d_lambda && h->d_zeros && h->d_V && h->d_g && h->d_f && h->d_fpart
+    ok = ok && h->d_xfull && h->d_xuser && h->d_tc && h->d_D && h->d_lambda && h->d_zeros && h->d_V && h->d_C && h->d_g && h->d_f && h->d_fpart
             && h->d_fcount && h->d_grad && h->d_jac && h->d_hess;
     ok = ok && cudaMemcpy(h->d_tc, tc.data(), tc.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess
             && cudaMemcpy(h->d_D, D.data(), D.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess
@@ -310,7 +311,7 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
         return nullptr;
     }
     P.x = h->d_xfull; P.tc = h->d_tc; P.D = h->d_D; P.lambda = h->d_lambda; P.zeros = h->d_zeros;
-    P.V = h->d_V; P.g = h->d_g; P.f = h->d_f; P.f_partial = h->d_fpart; P.f_counter = h->d_fcount;
+    P.V = h->d_V; P.C = h->d_C; P.g = h->d_g; P.f = h->d_f; P.f_partial = h->d_fpart; P.f_counter = h->d_fcount;
     P.grad = h->d_grad; P.jac = h->d_jac; P.hess = h->d_hess;
     build_structure(h);
     return h;
@@ -436,11 +437,14 @@ int fl_eval_device(fl_nlp* h, int what, double obj_factor)
     if (!scatter_x(h)) return 0;
     fl_dev P = h->P;
     P.obj_factor = obj_factor;
+    // the values pass also writes the checkpoints every derivative pass loads: it always runs (x may have been rewritten
+    // on the device since the last call)
+    h->v->launch_values(P, h->stream);
+    h->launches += 1;
     if (what & FL_EVAL_FG)
     {
-        h->v->launch_values(P, h->stream);
         h->v->launch_assemble(P, h->stream);
-        h->launches += 2;
+        h->launches += 1;
     }
     const int dw = ((what & FL_EVAL_JAC) ? FL_DERIV_JAC : 0) | ((what & FL_EVAL_HESS) ? FL_DERIV_HESS : 0);
     if (dw) { h->v->launch_derivs(P, dw, h->stream); h->launches += 1; }

@@ -5,17 +5,18 @@
 // through lion::ipopt_cppad_solve, :546-551) is split here into three data-parallel passes, one thread per collocation
 // node (or element), fp64 throughout:
 //
-//   k_node_values   x_j -> node values V (states, s-derivatives, algebraic rows, extra constraints, dt/ds)
+//   k_node_values   x_j -> node values V (states, s-derivatives, algebraic rows, extra constraints, dt/ds) and the node's
+//                   checkpoints C (every sin/cos/atan/tanh/exp/reciprocal/sqrt the derivative code needs)
 //   k_assemble      elements: trapezoidal / algebraic / extra / control-rate rows g, and the objective f
 //   k_node_derivs   x_j, lambda, obj_factor -> grad f, the node's two Jacobian blocks, its Lagrangian-Hessian block
-//                   (lane = node, warp = one of N balanced partitions of the node's derivative outputs)
+//                   (thread = node, blockIdx.y = one of N balanced partitions of the node's derivative outputs)
 //
 // Layout in HBM (all fp64):
 //   xfull  [problem][node][NV]      node-major, the reference's variable order (optimal_laptime.hpp:1269-1303); the fixed
 //                                   first node of open problems occupies slot 0 and is filled by the host
 //   tc     [NTC][node]              per-node track / mesh constants, structure-of-arrays, shared by the whole batch
 //   D      [problem][ND]            vehicle parameters followed by their parameter-only sub-expressions
-//   V      [problem][NVAL][node]    structure-of-arrays
+//   V, C   [problem][NVAL|NCK][node] structure-of-arrays
 //   g, lambda [problem][element][NCPE]   element-major, the reference's constraint order (optimal_laptime.hpp:413-483)
 //   grad   [problem][var node][NV]
 //   jac    [problem]{ A[NJA][element] , B[NJB][element with a free left node] }   slot-major: consecutive threads write
@@ -39,6 +40,7 @@ struct fl_dev
     const double* zeros;         // >= NCPE zeros
     double obj_factor;
     double* V;                   // [batch][NVAL][n_points]
+    double* C;                   // [batch][NCK][n_points]  checkpoints: transcendental / reciprocal / sqrt intermediates of each node
     double* g;                   // [batch][m]
     double* f;                   // [batch]
     double* f_partial;           // [batch][n_blocks_assemble]
@@ -54,11 +56,12 @@ constexpr int FL_BLOCK = 128;
 template <class G>
 struct ValuesIO
 {
-    const double* xn; const double* tcn; const double* Dp; double* Vn; int np;
+    const double* xn; const double* tcn; const double* Dp; double* Vn; double* Cn; int np;
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
     __device__ __forceinline__ double t(int k) const { return __ldg(tcn + (size_t)k * np); }
     __device__ __forceinline__ double d(int k) const { return __ldg(Dp + k); }
     __device__ __forceinline__ void val(int k, double v) const { Vn[(size_t)k * np] = v; }
+    __device__ __forceinline__ void cs(int k, double v) const { Cn[(size_t)k * np] = v; }
 };
 
 template <class G>
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(fl_dev P)
     io.tcn = P.tc + node;
     io.Dp = P.D + (size_t)prob * G::ND;
     io.Vn = P.V + (size_t)prob * G::NVAL * P.n_points + node;
+    io.Cn = P.C + (size_t)prob * G::NCK * P.n_points + node;
     io.np = P.n_points;
     G::values(io);
 }
@@ -166,7 +170,7 @@ template <class G>
 struct DerivIO
 {
     const double* xn; const double* xp; const double* xq;     // this node, previous node, next node
-    const double* tcn; const double* Dp; const double* lin_; const double* lout_;
+    const double* tcn; const double* Dp; const double* lin_; const double* lout_; const double* Cn;
     double obj_; int np;
     double* gradn; double* ja_; double* jb_; double* h_; double* c_;
     size_t sA, sB, sH, sC;
@@ -174,6 +178,7 @@ struct DerivIO
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
     __device__ __forceinline__ double t(int k) const { return __ldg(tcn + (size_t)k * np); }
     __device__ __forceinline__ double d(int k) const { return __ldg(Dp + k); }
+    __device__ __forceinline__ double c(int k) const { return Cn[(size_t)k * np]; }
     __device__ __forceinline__ double lin(int r) const { return lin_[r]; }
     __device__ __forceinline__ double lout(int r) const { return lout_[r]; }
     __device__ __forceinline__ double obj() const { return obj_; }
@@ -194,14 +199,19 @@ template <class G> struct deriv_parts<G, FL_DERIV_JAC>  { static constexpr int N
 template <class G> struct deriv_parts<G, FL_DERIV_HESS> { static constexpr int N = G::NP_HESS; template <class IO> static __device__ __forceinline__ void run(int w, IO& io) { G::hess_part(w, io); } };
 template <class G> struct deriv_parts<G, FL_DERIV_ALL>  { static constexpr int N = G::NP_ALL;  template <class IO> static __device__ __forceinline__ void run(int w, IO& io) { G::all_part(w, io); } };
 
-// One block = 32 nodes x N code partitions: lane = node, warp = partition.  Every warp runs its own straight-line code
-// (no divergence inside a warp), so a lap of 8000 nodes spreads over 250 blocks x N warps instead of 63 blocks x 4 warps.
+// The derivative outputs of a node are split into N balanced code partitions (straight-line code, ~2 k fp64 operations
+// each).  One block = FL_DBLOCK consecutive nodes x ONE partition (blockIdx.y): all warps of a block run the same
+// instruction stream, so each instruction-cache line is fetched once per block and shared by its warps -- the code is
+// executed exactly once per thread, which makes instruction fetch, not data, the first bottleneck (profiles/).
+// A lap of 8000 nodes spreads over 32 x N blocks instead of 63 blocks of one thread per node.
+constexpr int FL_DBLOCK = 256;
+
 template <class G, int WHAT>
-__global__ void __launch_bounds__(32 * deriv_parts<G, WHAT>::N) k_node_derivs(fl_dev P)
+__global__ void __launch_bounds__(FL_DBLOCK) k_node_derivs(fl_dev P)
 {
-    const int vn = blockIdx.x * 32 + (threadIdx.x & 31);     // variable-node index
-    const int part = threadIdx.x >> 5;
-    const int prob = blockIdx.y;
+    const int vn = blockIdx.x * FL_DBLOCK + threadIdx.x;     // variable-node index
+    const int part = blockIdx.y;
+    const int prob = blockIdx.z;
     if (vn >= P.n_var_nodes) return;
     const int np = P.n_points;
     const int node = vn + P.node0;
@@ -222,6 +232,7 @@ __global__ void __launch_bounds__(32 * deriv_parts<G, WHAT>::N) k_node_derivs(fl
     io.lout_ = has_out ? lam + (size_t)e_out * G::NCPE : P.zeros;
     io.obj_ = P.obj_factor;
     io.np = np;
+    io.Cn = P.C + (size_t)prob * G::NCK * np + node;
     io.gradn = P.grad + (size_t)prob * P.n + (size_t)vn * G::NV;
     double* jac = P.jac + (size_t)prob * P.nnz_jac;
     double* hes = P.hess + (size_t)prob * P.nnz_hess;
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(32 * deriv_parts<G, WHAT>::N) k_node_derivs(fl
 struct fl_variant
 {
     const char* name;
-    int NV, NCPE, NTD, NALG, NEXT, NCR, NFM, NVAL, NTC, NTRACK, NRAW, ND, NJA, NJB, NH, NCPL, IS_DERIVATIVE, IS_3D;
+    int NV, NCPE, NTD, NALG, NEXT, NCR, NFM, NVAL, NCK, NTC, NTRACK, NRAW, ND, NJA, NJB, NH, NCPL, IS_DERIVATIVE, IS_3D;
     int OPS_VALUES, OPS_JAC, OPS_HESS, OPS_ALL;
     const int *CTRL_POS, *DCTRL_POS, *JA_ROW, *JA_COL, *JB_ROW, *JB_COL, *H_ROW, *H_COL;
     int P_SIGMA, P_DISS0, P_DISS1, P_F_WHEEL_SCALE, P_R_WHEEL_SCALE;     // -1 when the model has no such slot
@@ -266,17 +277,17 @@ struct variant_ops
     static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_BLOCK - 1) / FL_BLOCK; }
     static void derivs(const fl_dev& P, int what, cudaStream_t s)
     {
-        const dim3 g((P.n_var_nodes + 31) / 32, P.batch, 1);
-        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC><<<g, 32 * G::NP_JAC, 0, s>>>(P);
-        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS><<<g, 32 * G::NP_HESS, 0, s>>>(P);
-        else k_node_derivs<G, FL_DERIV_ALL><<<g, 32 * G::NP_ALL, 0, s>>>(P);
+        const unsigned nb = (P.n_var_nodes + FL_DBLOCK - 1) / FL_DBLOCK;
+        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC><<<dim3(nb, G::NP_JAC, P.batch), FL_DBLOCK, 0, s>>>(P);
+        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS><<<dim3(nb, G::NP_HESS, P.batch), FL_DBLOCK, 0, s>>>(P);
+        else k_node_derivs<G, FL_DERIV_ALL><<<dim3(nb, G::NP_ALL, P.batch), FL_DBLOCK, 0, s>>>(P);
     }
     static fl_variant make()
     {
         fl_variant v;
         v.name = G::name;
         v.NV = G::NV; v.NCPE = G::NCPE; v.NTD = G::NTD; v.NALG = G::NALG; v.NEXT = G::NEXT; v.NCR = G::NCR; v.NFM = G::NFM;
-        v.NVAL = G::NVAL; v.NTC = G::NTC; v.NTRACK = G::NTRACK; v.NRAW = G::NRAW; v.ND = G::ND;
+        v.NVAL = G::NVAL; v.NCK = G::NCK; v.NTC = G::NTC; v.NTRACK = G::NTRACK; v.NRAW = G::NRAW; v.ND = G::ND;
         v.NJA = G::NJA; v.NJB = G::NJB; v.NH = G::NH; v.NCPL = G::NCPL; v.IS_DERIVATIVE = G::IS_DERIVATIVE; v.IS_3D = G::IS_3D;
         v.OPS_VALUES = G::OPS_VALUES; v.OPS_JAC = G::OPS_JAC; v.OPS_HESS = G::OPS_HESS; v.OPS_ALL = G::OPS_ALL;
         v.CTRL_POS = G::CTRL_POS; v.DCTRL_POS = G::DCTRL_POS;
