@@ -10,11 +10,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libfastestlap_b200.so")
+OBJ = os.environ.get("FL_OBJ", os.path.join(CSRC, "build"))
+LIB = os.environ.get("FL_OUT", os.path.join(HERE, "libfastestlap_b200.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("FL_EXTRA_FLAGS", "").split()
 
 
 def _newer(target, sources):

@@ -26,7 +26,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "..", "csrc", "generated")
 
 # warps (= straight-line code partitions) per group of 32 nodes in each derivative kernel
-NPARTS = {"jac": 4, "hess": 8, "all": 8}
+NPARTS = {"jac": int(os.environ.get("FL_NP_JAC", 4)), "hess": int(os.environ.get("FL_NP_HESS", 8)), "all": int(os.environ.get("FL_NP_ALL", 8)),
+          "values": int(os.environ.get("FL_NP_VALUES", 1))}
 
 VARIANTS = {
     "f1_direct": Variant("f1", "direct"),
@@ -149,8 +150,18 @@ def generate(name, variant):
         grp_h.append([o for o, key in zip(out_h, hs) if key[1] == k])
     grp_h.append(out_c)
     parts = []
-    parts.append(fn("values", out_values + out_ck, [pre], use_cut=False))
     part_sizes = {}
+    # values pass: the node values and checkpoints, split the same way (every output is its own group; the pass is one
+    # long dependent chain per node, so shorter partitions on more warps cut its latency)
+    outs, sizes = partition(g, [[o] for o in out_values + out_ck], NPARTS["values"])
+    part_sizes["values"] = sizes
+    for w, o in enumerate(outs):
+        parts.append(fn("values_p%d" % w, o, [pre], use_cut=False))
+    disp = ["    template <class IO> static __device__ __forceinline__ void values_part(int w, IO& io)", "    {", "        switch (w)", "        {"]
+    for w in range(len(outs)):
+        disp.append("        case %d: values_p%d(io); break;" % (w, w))
+    disp += ["        default: break;", "        }", "    }", ""]
+    parts.append("\n".join(disp))
     for mode, groups, pres in (("jac", grp_j, [pre, pre_n]), ("hess", grp_h, [pre, pre_w]), ("all", grp_j + grp_h, [pre, pre_w, pre_n])):
         outs, sizes = partition(g, groups, NPARTS[mode], stop=set(ck))
         part_sizes[mode] = sizes
@@ -185,8 +196,8 @@ def generate(name, variant):
     L.append("    static constexpr int NVAL = %d, NTC = %d, NTRACK = %d, NRAW = %d, ND = %d, NCK = %d;" % (len(p.values), len(tnames), len(p.track_names), len(raw_names), pt.size, len(ck)))
     L.append("    static constexpr int NJA = %d, NJB = %d, NH = %d, NCPL = %d;" % (len(ja), len(jb), len(hs), len(p.coupling)))
     L.append("    static constexpr int IS_DERIVATIVE = %d, IS_3D = %d;" % (int(variant.form == "derivative"), int(variant.elevation)))
-    L.append("    static constexpr int NP_JAC = %d, NP_HESS = %d, NP_ALL = %d;   // code partitions (warps per 32 nodes)" % (NPARTS["jac"], NPARTS["hess"], NPARTS["all"]))
-    for mode in ("jac", "hess", "all"):
+    L.append("    static constexpr int NP_VALUES = %d, NP_JAC = %d, NP_HESS = %d, NP_ALL = %d;   // code partitions of each pass" % (NPARTS["values"], NPARTS["jac"], NPARTS["hess"], NPARTS["all"]))
+    for mode in ("values", "jac", "hess", "all"):
         L.append("    // %s partition operation counts: %s (sum %d)" % (mode, part_sizes[mode], sum(part_sizes[mode])))
     L.append("    static constexpr int OPS_VALUES = %d, OPS_JAC = %d, OPS_HESS = %d, OPS_ALL = %d;" %
              (sum(counts_val.values()), sum(counts_jac.values()), sum(counts_hes.values()), sum(counts_all.values())))

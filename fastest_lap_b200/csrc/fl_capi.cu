@@ -74,7 +74,8 @@ struct fl_nlp
     double *d_xfull = nullptr, *d_xuser = nullptr, *d_tc = nullptr, *d_D = nullptr, *d_lambda = nullptr, *d_zeros = nullptr;
     double *d_C = nullptr, *d_V = nullptr, *d_g = nullptr, *d_f = nullptr, *d_fpart = nullptr, *d_grad = nullptr, *d_jac = nullptr, *d_hess = nullptr;
     unsigned int* d_fcount = nullptr;
-    std::vector<double> s, wl, wr, params;
+    std::vector<double> s, wl, wr, params, D0;      // D0: parameter vector (with derived slots) of problem 0
+    int shared_d = 1;                               // every problem of the batch has the parameter vector D0
     std::vector<int> jac_row, jac_col, hess_row, hess_col;
     bool values_valid = false, derivs_jac_valid = false;
     long launches = 0;
@@ -191,6 +192,7 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
     fl_dev& P = h->P;
     P.n_points = np; P.closed = d->closed ? 1 : 0; P.batch = batch;
     P.node0 = d->closed ? 0 : 1;
+    P.n_pad = (np + 31) / 32 * 32;
     P.n_elements = d->closed ? np : np - 1;
     P.n_var_nodes = np - P.node0;
     P.nB = P.n_elements - P.node0;
@@ -202,7 +204,8 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
     P.obj_factor = 1.0;
 
     // ---- per-node constants [NTC][np]: track (kz | kx ky kz sin/cos pitch, sin/cos roll), then hin, hout, (ihin, ihout | penw)
-    std::vector<double> tc((size_t)v->NTC * np, 0.0);
+    std::vector<double> tc((size_t)v->NTC * P.n_pad, 0.0);
+    auto TC = [&](int slot, int node) -> double& { return tc[fl_chunk_base(node, v->NTC) + (size_t)slot * 32]; };
     const double L = d->track_length;
     for (int i = 0; i < np; ++i)
     {
@@ -215,20 +218,20 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
         int k = 0;
         if (v->IS_3D)
         {
-            tc[(size_t)(k++) * np + i] = kx; tc[(size_t)(k++) * np + i] = ky; tc[(size_t)(k++) * np + i] = kz;
-            tc[(size_t)(k++) * np + i] = std::sin(mu); tc[(size_t)(k++) * np + i] = std::cos(mu);
-            tc[(size_t)(k++) * np + i] = std::sin(phi); tc[(size_t)(k++) * np + i] = std::cos(phi);
+            TC(k++, i) = kx; TC(k++, i) = ky; TC(k++, i) = kz;
+            TC(k++, i) = std::sin(mu); TC(k++, i) = std::cos(mu);
+            TC(k++, i) = std::sin(phi); TC(k++, i) = std::cos(phi);
         }
         else
-            tc[(size_t)(k++) * np + i] = kz;
+            TC(k++, i) = kz;
         const double hin = i > 0 ? d->s[i] - d->s[i - 1] : (d->closed ? L - d->s[np - 1] : 0.0);
         const double hout = i + 1 < np ? d->s[i + 1] - d->s[i] : (d->closed ? L - d->s[np - 1] : 0.0);
-        tc[(size_t)(k++) * np + i] = hin;
-        tc[(size_t)(k++) * np + i] = hout;
+        TC(k++, i) = hin;
+        TC(k++, i) = hout;
         if (!v->IS_DERIVATIVE)
         {
-            tc[(size_t)(k++) * np + i] = hin > 0.0 ? 1.0 / hin : 0.0;
-            tc[(size_t)(k++) * np + i] = hout > 0.0 ? 1.0 / hout : 0.0;
+            TC(k++, i) = hin > 0.0 ? 1.0 / hin : 0.0;
+            TC(k++, i) = hout > 0.0 ? 1.0 / hout : 0.0;
         }
         else
             ++k;    // penw, below
@@ -237,14 +240,14 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
     {
         // total element length weighting 0.5 diss du_j^2: right node of its element, plus the reference's left-rate quirk
         // (dcontrols_dt[i-i], optimal_laptime.hpp:1553): node 0 for every non-closing element, node n-1 for the closing one
-        double* penw = tc.data() + (size_t)(v->NTC - 1) * np;
+        const int penw = v->NTC - 1;
         for (int e = 0; e < P.n_elements; ++e)
         {
             const bool closing = e + 1 == np;
             const int j = closing ? 0 : e + 1;
             const double he = closing ? L - d->s[np - 1] : d->s[e + 1] - d->s[e];
-            penw[j] += he;
-            penw[closing ? np - 1 : 0] += he;
+            TC(penw, j) += he;
+            TC(penw, closing ? np - 1 : 0) += he;
         }
     }
 
@@ -266,6 +269,10 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
         Db[v->P_DISS1] = d->dissipation[1];
         v->derive(Db);
     }
+
+    h->D0.assign(D.begin(), D.begin() + v->ND);
+    for (int b = 1; b < batch && h->shared_d; ++b)
+        if (std::memcmp(D.data() + (size_t)b * v->ND, D.data(), v->ND * sizeof(double)) != 0) h->shared_d = 0;
 
     // ---- x with the fixed first node of open problems
     std::vector<double> xfull((size_t)batch * np * NV, 0.0);
@@ -289,8 +296,8 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
     h->d_D = dev_alloc<double>(D.size());
     h->d_lambda = dev_alloc<double>((size_t)batch * P.m);
     h->d_zeros = dev_alloc<double>(64);
-    h->d_V = dev_alloc<double>((size_t)batch * v->NVAL * np);
-    h->d_C = dev_alloc<double>((size_t)batch * v->NCK * np);
+    h->d_V = dev_alloc<double>((size_t)batch * v->NVAL * P.n_pad);
+    h->d_C = dev_alloc<double>((size_t)batch * v->NCK * P.n_pad);
     h->d_g = dev_alloc<double>((size_t)batch * P.m);
     h->d_f = dev_alloc<double>(batch);
     h->d_fpart = dev_alloc<double>((size_t)batch * nblk);
@@ -329,6 +336,11 @@ int fl_nlp_batch(const fl_nlp* h) { return h->P.batch; }
 const char* fl_nlp_variant(const fl_nlp* h) { return h->v->name; }
 void fl_nlp_ops_per_node(const fl_nlp* h, int ops[4]) { ops[0] = h->v->OPS_VALUES; ops[1] = h->v->OPS_JAC; ops[2] = h->v->OPS_HESS; ops[3] = h->v->OPS_ALL; }
 long fl_kernel_launches(const fl_nlp* h) { return h->launches; }
+void fl_nlp_workspace_slots(const fl_nlp* h, int* n_values, int* n_checkpoints)
+{
+    if (n_values) *n_values = h->v->NVAL;
+    if (n_checkpoints) *n_checkpoints = h->v->NCK;
+}
 
 int fl_nlp_structure(const fl_nlp* h, int* jac_row, int* jac_col, int* hess_row, int* hess_col)
 {
@@ -439,15 +451,17 @@ int fl_eval_device(fl_nlp* h, int what, double obj_factor)
     P.obj_factor = obj_factor;
     // the values pass also writes the checkpoints every derivative pass loads: it always runs (x may have been rewritten
     // on the device since the last call)
-    h->v->launch_values(P, h->stream);
+    h->v->launch_values(P, h->D0.data(), h->shared_d, h->stream);
     h->launches += 1;
-    if (what & FL_EVAL_FG)
+    const int dw = ((what & FL_EVAL_JAC) ? FL_DERIV_JAC : 0) | ((what & FL_EVAL_HESS) ? FL_DERIV_HESS : 0);
+    // a full round (f, g, grad f, Jacobian, Hessian) assembles the rows inside the derivative launch
+    const int fold = (what & FL_EVAL_FG) && dw == FL_DERIV_ALL;
+    if ((what & FL_EVAL_FG) && !fold)
     {
         h->v->launch_assemble(P, h->stream);
         h->launches += 1;
     }
-    const int dw = ((what & FL_EVAL_JAC) ? FL_DERIV_JAC : 0) | ((what & FL_EVAL_HESS) ? FL_DERIV_HESS : 0);
-    if (dw) { h->v->launch_derivs(P, dw, h->stream); h->launches += 1; }
+    if (dw) { h->v->launch_derivs(P, h->D0.data(), h->shared_d, dw, fold, h->stream); h->launches += 1; }
     FL_CUDA(cudaGetLastError());
     return 1;
 }

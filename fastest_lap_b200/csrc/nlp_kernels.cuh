@@ -14,9 +14,11 @@
 // Layout in HBM (all fp64):
 //   xfull  [problem][node][NV]      node-major, the reference's variable order (optimal_laptime.hpp:1269-1303); the fixed
 //                                   first node of open problems occupies slot 0 and is filled by the host
-//   tc     [NTC][node]              per-node track / mesh constants, structure-of-arrays, shared by the whole batch
+//   tc     [chunk][NTC][32]         per-node track / mesh constants, shared by the whole batch
 //   D      [problem][ND]            vehicle parameters followed by their parameter-only sub-expressions
-//   V, C   [problem][NVAL|NCK][node] structure-of-arrays
+//   V, C   [problem][chunk][NVAL|NCK][32]  structure-of-arrays in chunks of 32 nodes (one warp): slot k of a node sits at a
+//                                   fixed byte offset k*256 from the node's base, so every access is base + immediate and a
+//                                   warp's access to a slot is one contiguous 256-byte segment
 //   g, lambda [problem][element][NCPE]   element-major, the reference's constraint order (optimal_laptime.hpp:413-483)
 //   grad   [problem][var node][NV]
 //   jac    [problem]{ A[NJA][element] , B[NJB][element with a free left node] }   slot-major: consecutive threads write
@@ -26,21 +28,23 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
 
 struct fl_dev
 {
     int n_points, n_elements, n_var_nodes, node0, closed, batch;
+    int n_pad;                   // n_points rounded up to a multiple of 32 (chunked workspace layout)
     int nB, nC;                  // number of elements that carry a B block / a control coupling
     int n, m;                    // variables / constraints per problem (user-visible sizes)
     long nnz_jac, nnz_hess;      // per problem
     const double* x;             // [batch][n_points*NV]
-    const double* tc;            // [NTC][n_points]
+    const double* tc;            // [n_pad/32][NTC][32]
     const double* D;             // [batch][ND]
     const double* lambda;        // [batch][m]
     const double* zeros;         // >= NCPE zeros
     double obj_factor;
-    double* V;                   // [batch][NVAL][n_points]
-    double* C;                   // [batch][NCK][n_points]  checkpoints: transcendental / reciprocal / sqrt intermediates of each node
+    double* V;                   // [batch][n_pad/32][NVAL][32]
+    double* C;                   // [batch][n_pad/32][NCK][32]  checkpoints: transcendental / reciprocal / sqrt intermediates of each node
     double* g;                   // [batch][m]
     double* f;                   // [batch]
     double* f_partial;           // [batch][n_blocks_assemble]
@@ -50,44 +54,66 @@ struct fl_dev
     double* hess;                // [batch][nnz_hess]
 };
 
-constexpr int FL_BLOCK = 128;
+// offset of slot 0 of `node` inside a chunked [chunk][nslot][32] array
+__host__ __device__ __forceinline__ size_t fl_chunk_base(int node, int nslot) { return ((size_t)(node >> 5) * nslot << 5) + (node & 31); }
+
+#ifndef FL_VBLOCK_N
+#define FL_VBLOCK_N 128
+#endif
+constexpr int FL_BLOCK = FL_VBLOCK_N;        // values pass: nodes per block (x one code partition)
+// derivative pass: nodes per block (x one code partition), and the element-assembly block size
+#ifndef FL_DBLOCK_N
+#define FL_DBLOCK_N 256
+#endif
+#ifndef FL_DMINB
+#define FL_DMINB 1
+#endif
+constexpr int FL_DBLOCK = FL_DBLOCK_N;
+constexpr int FL_ABLOCK = FL_DBLOCK;
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <class G>
+// Parameter vector of a problem handed over as a kernel argument: when every problem of the batch drives the same vehicle
+// (a single lap, replicas, G-G sweeps) the generated code reads D[k] as a constant-bank operand of the arithmetic
+// instruction itself -- no load, no register (CD = true).  Batches with per-problem vehicles read D from global memory.
+template <class G> struct DVec { double d[G::ND]; };
+
+template <class G, bool CD>
 struct ValuesIO
 {
-    const double* xn; const double* tcn; const double* Dp; double* Vn; double* Cn; int np;
+    const double* xn; const double* tcn; const double* Dp; const DVec<G>* Dk; double* Vn; double* Cn;
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
-    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + (size_t)k * np); }
-    __device__ __forceinline__ double d(int k) const { return __ldg(Dp + k); }
-    __device__ __forceinline__ void val(int k, double v) const { Vn[(size_t)k * np] = v; }
-    __device__ __forceinline__ void cs(int k, double v) const { Cn[(size_t)k * np] = v; }
+    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
+    __device__ __forceinline__ double d(int k) const { if constexpr (CD) return Dk->d[k]; else return __ldg(Dp + k); }
+    __device__ __forceinline__ void val(int k, double v) const { Vn[k * 32] = v; }
+    __device__ __forceinline__ void cs(int k, double v) const { Cn[k * 32] = v; }
 };
 
-template <class G>
-__global__ void __launch_bounds__(FL_BLOCK) k_node_values(fl_dev P)
+template <class G, bool CD>
+__global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
 {
     const int node = blockIdx.x * FL_BLOCK + threadIdx.x;
-    const int prob = blockIdx.y;
+    const int part = blockIdx.y;
+    const int prob = blockIdx.z;
     if (node >= P.n_points) return;
-    ValuesIO<G> io;
+    ValuesIO<G, CD> io;
     io.xn = P.x + ((size_t)prob * P.n_points + node) * G::NV;
-    io.tcn = P.tc + node;
+    io.tcn = P.tc + fl_chunk_base(node, G::NTC);
     io.Dp = P.D + (size_t)prob * G::ND;
-    io.Vn = P.V + (size_t)prob * G::NVAL * P.n_points + node;
-    io.Cn = P.C + (size_t)prob * G::NCK * P.n_points + node;
-    io.np = P.n_points;
-    G::values(io);
+    io.Dk = &Dk;
+    io.Vn = P.V + (size_t)prob * G::NVAL * P.n_pad + fl_chunk_base(node, G::NVAL);
+    io.Cn = P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node, G::NCK);
+    G::values_part(part, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Element assembly.  V offsets: Q [0,NTD) QD [NTD,2NTD) ALG EXT DTDS CDOT.
-template <class G>
-__global__ void __launch_bounds__(FL_BLOCK) k_assemble(fl_dev P)
+// Runs as its own kernel (eval_f / eval_g alone) or as one extra blockIdx.y slice of the derivative kernel (a full
+// callback round: one launch less, and the rows are written while the derivative partitions compute).
+template <class G, int BS>
+__device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, const int nbx, const int prob)
 {
     constexpr int oQ = 0, oQD = G::NTD, oALG = 2 * G::NTD, oEXT = oALG + G::NALG, oDT = oEXT + G::NEXT, oCD = oDT + 1;
-    const int e = blockIdx.x * FL_BLOCK + threadIdx.x;
-    const int prob = blockIdx.y;
+    const int e = bx * BS + threadIdx.x;
     const int np = P.n_points;
     double fe = 0.0;
     if (e < P.n_elements)
@@ -97,21 +123,21 @@ __global__ void __launch_bounds__(FL_BLOCK) k_assemble(fl_dev P)
         const bool closing = (e + 1 == np);
         const double* D = P.D + (size_t)prob * G::ND;
         const double sigma = __ldg(D + G::P_SIGMA), oms = 1.0 - sigma;
-        const double h = __ldg(P.tc + (size_t)(G::NTRACK + 1) * np + i);           // hout of the left node
-        const double* V = P.V + (size_t)prob * G::NVAL * np;
+        const double h = __ldg(P.tc + fl_chunk_base(i, G::NTC) + (G::NTRACK + 1) * 32);           // hout of the left node
+        const double* Vi = P.V + (size_t)prob * G::NVAL * P.n_pad + fl_chunk_base(i, G::NVAL);
+        const double* Vj = P.V + (size_t)prob * G::NVAL * P.n_pad + fl_chunk_base(j, G::NVAL);
         const double* xi = P.x + ((size_t)prob * np + i) * G::NV;
         const double* xj = P.x + ((size_t)prob * np + j) * G::NV;
         double* g = P.g + (size_t)prob * P.m + (size_t)e * G::NCPE;
         int row = 0;
 #pragma unroll
         for (int r = 0; r < G::NTD; ++r, ++row)
-            g[row] = V[(size_t)(oQ + r) * np + j] - V[(size_t)(oQ + r) * np + i]
-                   - h * (oms * V[(size_t)(oQD + r) * np + i] + sigma * V[(size_t)(oQD + r) * np + j]);
+            g[row] = Vj[(oQ + r) * 32] - Vi[(oQ + r) * 32] - h * (oms * Vi[(oQD + r) * 32] + sigma * Vj[(oQD + r) * 32]);
 #pragma unroll
-        for (int r = 0; r < G::NALG; ++r, ++row) g[row] = V[(size_t)(oALG + r) * np + j];
+        for (int r = 0; r < G::NALG; ++r, ++row) g[row] = Vj[(oALG + r) * 32];
 #pragma unroll
-        for (int r = 0; r < G::NEXT; ++r, ++row) g[row] = V[(size_t)(oEXT + r) * np + j];
-        fe = h * (oms * V[(size_t)oDT * np + i] + sigma * V[(size_t)oDT * np + j]);
+        for (int r = 0; r < G::NEXT; ++r, ++row) g[row] = Vj[(oEXT + r) * 32];
+        fe = h * (oms * Vi[oDT * 32] + sigma * Vj[oDT * 32]);
         if (G::IS_DERIVATIVE)
         {
             // control-rate rows (optimal_laptime.hpp:1573-1583, 1632-1641) and penalty (:1553, :1611; the left rate is
@@ -121,7 +147,7 @@ __global__ void __launch_bounds__(FL_BLOCK) k_assemble(fl_dev P)
             for (int c = 0; c < G::NCR; ++c, ++row)
             {
                 g[row] = xj[G::ctrl_pos(c)] - xi[G::ctrl_pos(c)]
-                       - h * (oms * V[(size_t)(oCD + c) * np + i] + sigma * V[(size_t)(oCD + c) * np + j]);
+                       - h * (oms * Vi[(oCD + c) * 32] + sigma * Vj[(oCD + c) * 32]);
                 const double dl = xl[G::dctrl_pos(c)], dr = xj[G::dctrl_pos(c)];
                 fe += 0.5 * __ldg(D + G::P_DISS0 + c) * (dl * dl + dr * dr) * h;
             }
@@ -136,49 +162,65 @@ __global__ void __launch_bounds__(FL_BLOCK) k_assemble(fl_dev P)
             }
         }
     }
-    // objective: fixed-order block tree, then the last block to finish adds the block partials in index order
-    __shared__ double red[FL_BLOCK];
+    // objective: fixed-order tree inside the block; the last block to finish sums the block partials, again in a fixed
+    // order (thread t takes partials t, t + BS, ...; then the same tree) -- the result does not depend on block timing
+    __shared__ double red[BS];
     __shared__ bool last;
     red[threadIdx.x] = fe;
     __syncthreads();
 #pragma unroll
-    for (int s = FL_BLOCK / 2; s > 0; s >>= 1)
+    for (int s = BS / 2; s > 0; s >>= 1)
     {
         if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    double* part = P.f_partial + (size_t)prob * gridDim.x;
+    double* part = P.f_partial + (size_t)prob * nbx;
     if (threadIdx.x == 0)
     {
-        part[blockIdx.x] = red[0];
+        part[bx] = red[0];
         __threadfence();
-        const unsigned int t = atomicInc(P.f_counter + prob, gridDim.x - 1);      // wraps back to 0 for the next launch
-        last = (t == gridDim.x - 1);
+        const unsigned int t = atomicInc(P.f_counter + prob, nbx - 1);      // wraps back to 0 for the next launch
+        last = (t == (unsigned)nbx - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x == 0)
+    if (last)
     {
         __threadfence();
         double acc = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) acc += ((volatile double*)part)[b];
-        P.f[prob] = acc;
+        for (int b = threadIdx.x; b < nbx; b += BS) acc += __ldcg(part + b);
+        red[threadIdx.x] = acc;
+        __syncthreads();
+#pragma unroll
+        for (int s = BS / 2; s > 0; s >>= 1)
+        {
+            if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) P.f[prob] = red[0];
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
+// (same block size as the slice inside the derivative launch: both paths give the same bits for f)
 template <class G>
+__global__ void __launch_bounds__(FL_ABLOCK) k_assemble(const __grid_constant__ fl_dev P)
+{
+    assemble_block<G, FL_ABLOCK>(P, blockIdx.x, gridDim.x, blockIdx.y);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class G, bool CD>
 struct DerivIO
 {
     const double* xn; const double* xp; const double* xq;     // this node, previous node, next node
-    const double* tcn; const double* Dp; const double* lin_; const double* lout_; const double* Cn;
-    double obj_; int np;
+    const double* tcn; const double* Dp; const DVec<G>* Dk; const double* lin_; const double* lout_; const double* Cn;
+    double obj_;
     double* gradn; double* ja_; double* jb_; double* h_; double* c_;
     size_t sA, sB, sH, sC;
     bool hasB, hasC;
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
-    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + (size_t)k * np); }
-    __device__ __forceinline__ double d(int k) const { return __ldg(Dp + k); }
-    __device__ __forceinline__ double c(int k) const { return Cn[(size_t)k * np]; }
+    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
+    __device__ __forceinline__ double d(int k) const { if constexpr (CD) return Dk->d[k]; else return __ldg(Dp + k); }
+    __device__ __forceinline__ double c(int k) const { return Cn[k * 32]; }
     __device__ __forceinline__ double lin(int r) const { return lin_[r]; }
     __device__ __forceinline__ double lout(int r) const { return lout_[r]; }
     __device__ __forceinline__ double obj() const { return obj_; }
@@ -204,14 +246,19 @@ template <class G> struct deriv_parts<G, FL_DERIV_ALL>  { static constexpr int N
 // instruction stream, so each instruction-cache line is fetched once per block and shared by its warps -- the code is
 // executed exactly once per thread, which makes instruction fetch, not data, the first bottleneck (profiles/).
 // A lap of 8000 nodes spreads over 32 x N blocks instead of 63 blocks of one thread per node.
-constexpr int FL_DBLOCK = 256;
 
-template <class G, int WHAT>
-__global__ void __launch_bounds__(FL_DBLOCK) k_node_derivs(fl_dev P)
+template <class G, int WHAT, bool ASSEMBLE, bool CD>
+__global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
 {
     const int vn = blockIdx.x * FL_DBLOCK + threadIdx.x;     // variable-node index
     const int part = blockIdx.y;
     const int prob = blockIdx.z;
+    if (ASSEMBLE && part == deriv_parts<G, WHAT>::N)         // the slice that assembles g and f (block-uniform branch)
+    {
+        const int nbx = (P.n_elements + FL_DBLOCK - 1) / FL_DBLOCK;
+        if ((int)blockIdx.x < nbx) assemble_block<G, FL_DBLOCK>(P, blockIdx.x, nbx, prob);
+        return;
+    }
     if (vn >= P.n_var_nodes) return;
     const int np = P.n_points;
     const int node = vn + P.node0;
@@ -222,17 +269,17 @@ __global__ void __launch_bounds__(FL_DBLOCK) k_node_derivs(fl_dev P)
     const bool has_out = P.closed || (node + 1 < np);
     const double* xb = P.x + (size_t)prob * np * G::NV;
     const double* lam = P.lambda + (size_t)prob * P.m;
-    DerivIO<G> io;
+    DerivIO<G, CD> io;
+    io.Dk = &Dk;
     io.xn = xb + (size_t)node * G::NV;
     io.xp = xb + (size_t)prev * G::NV;
     io.xq = xb + (size_t)next * G::NV;
-    io.tcn = P.tc + node;
+    io.tcn = P.tc + fl_chunk_base(node, G::NTC);
     io.Dp = P.D + (size_t)prob * G::ND;
     io.lin_ = lam + (size_t)e_in * G::NCPE;
     io.lout_ = has_out ? lam + (size_t)e_out * G::NCPE : P.zeros;
     io.obj_ = P.obj_factor;
-    io.np = np;
-    io.Cn = P.C + (size_t)prob * G::NCK * np + node;
+    io.Cn = P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node, G::NCK);
     io.gradn = P.grad + (size_t)prob * P.n + (size_t)vn * G::NV;
     double* jac = P.jac + (size_t)prob * P.nnz_jac;
     double* hes = P.hess + (size_t)prob * P.nnz_hess;
@@ -257,9 +304,10 @@ struct fl_variant
     const int *CTRL_POS, *DCTRL_POS, *JA_ROW, *JA_COL, *JB_ROW, *JB_COL, *H_ROW, *H_COL;
     int P_SIGMA, P_DISS0, P_DISS1, P_F_WHEEL_SCALE, P_R_WHEEL_SCALE;     // -1 when the model has no such slot
     void (*derive)(double* D);
-    void (*launch_values)(const fl_dev&, cudaStream_t);
+    // `D0` = host copy of the parameter vector of problem 0; `shared_d` = every problem of the batch has that same vector
+    void (*launch_values)(const fl_dev&, const double* D0, int shared_d, cudaStream_t);
     void (*launch_assemble)(const fl_dev&, cudaStream_t);
-    void (*launch_derivs)(const fl_dev&, int what, cudaStream_t);
+    void (*launch_derivs)(const fl_dev&, const double* D0, int shared_d, int what, int with_assemble, cudaStream_t);
     int (*assemble_blocks)(const fl_dev&);
 };
 
@@ -272,15 +320,32 @@ template <class G>
 struct variant_ops
 {
     static dim3 grid(int items, int batch) { return dim3((items + FL_BLOCK - 1) / FL_BLOCK, batch, 1); }
-    static void values(const fl_dev& P, cudaStream_t s) { k_node_values<G><<<grid(P.n_points, P.batch), FL_BLOCK, 0, s>>>(P); }
-    static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<grid(P.n_elements, P.batch), FL_BLOCK, 0, s>>>(P); }
-    static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_BLOCK - 1) / FL_BLOCK; }
-    static void derivs(const fl_dev& P, int what, cudaStream_t s)
+    static void values(const fl_dev& P, const double* D0, int shared_d, cudaStream_t s)
     {
-        const unsigned nb = (P.n_var_nodes + FL_DBLOCK - 1) / FL_DBLOCK;
-        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC><<<dim3(nb, G::NP_JAC, P.batch), FL_DBLOCK, 0, s>>>(P);
-        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS><<<dim3(nb, G::NP_HESS, P.batch), FL_DBLOCK, 0, s>>>(P);
-        else k_node_derivs<G, FL_DERIV_ALL><<<dim3(nb, G::NP_ALL, P.batch), FL_DBLOCK, 0, s>>>(P);
+        DVec<G> Dk;
+        memcpy(Dk.d, D0, sizeof(Dk.d));
+        const dim3 grid((P.n_points + FL_BLOCK - 1) / FL_BLOCK, G::NP_VALUES, P.batch);
+        if (shared_d) k_node_values<G, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        else k_node_values<G, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+    }
+    static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<dim3((P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK, P.batch, 1), FL_ABLOCK, 0, s>>>(P); }
+    static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK; }
+    template <bool CD>
+    static void derivs_cd(const fl_dev& P, const DVec<G>& Dk, int what, int with_assemble, cudaStream_t s)
+    {
+        // n_elements <= n_var_nodes + 1: one more block column covers the assembly slice of an open problem
+        const unsigned nb = ((with_assemble ? P.n_points : P.n_var_nodes) + FL_DBLOCK - 1) / FL_DBLOCK;
+        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC, false, CD><<<dim3(nb, G::NP_JAC, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
+        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS, false, CD><<<dim3(nb, G::NP_HESS, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
+        else if (!with_assemble) k_node_derivs<G, FL_DERIV_ALL, false, CD><<<dim3(nb, G::NP_ALL, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
+        else k_node_derivs<G, FL_DERIV_ALL, true, CD><<<dim3(nb, G::NP_ALL + 1, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
+    }
+    static void derivs(const fl_dev& P, const double* D0, int shared_d, int what, int with_assemble, cudaStream_t s)
+    {
+        DVec<G> Dk;
+        memcpy(Dk.d, D0, sizeof(Dk.d));
+        if (shared_d) derivs_cd<true>(P, Dk, what, with_assemble, s);
+        else derivs_cd<false>(P, Dk, what, with_assemble, s);
     }
     static fl_variant make()
     {

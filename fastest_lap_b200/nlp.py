@@ -12,7 +12,7 @@ import numpy as np
 from .problem import LapProblem
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfastestlap_b200.so")
+LIB_PATH = os.environ.get("FL_LIB", os.path.join(_HERE, "libfastestlap_b200.so"))
 _lib = None
 
 EVAL_FG, EVAL_JAC, EVAL_HESS = 1, 2, 4
@@ -48,6 +48,7 @@ def load_library():
     lib.fl_nlp_bounds.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     lib.fl_nlp_structure.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
     lib.fl_nlp_ops_per_node.argtypes = [C.c_void_p, _ip]
+    lib.fl_nlp_workspace_slots.argtypes = [C.c_void_p, _ip, _ip]
     lib.fl_eval_all.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp]
     lib.fl_eval_f.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_void_p]
     lib.fl_eval_grad_f.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_void_p]
@@ -117,6 +118,9 @@ class CollocationNLP:
         ops = (C.c_int * 4)()
         lib.fl_nlp_ops_per_node(self._h, ops)
         self.ops_per_node = dict(values=ops[0], jac=ops[1], hess=ops[2], all=ops[3])
+        nval, nck = C.c_int(), C.c_int()
+        lib.fl_nlp_workspace_slots(self._h, C.byref(nval), C.byref(nck))
+        self.n_values, self.n_checkpoints = nval.value, nck.value
 
     def close(self):
         if getattr(self, "_h", None):

@@ -71,6 +71,9 @@ const char* fl_nlp_variant(const fl_nlp* nlp);
 int fl_nlp_bounds(const fl_nlp* nlp, double* x_l, double* x_u, double* g_l, double* g_u);
 /* fixed sparsity (triplets), same for every problem of the batch */
 int fl_nlp_structure(const fl_nlp* nlp, int* jac_row, int* jac_col, int* hess_row, int* hess_col);
+/* per-node slots of the device workspace written by the values pass: node values handed to the element assembly, and
+ * checkpointed intermediates (sin/cos/atan/tanh/exp/reciprocal/sqrt) the derivative pass loads */
+void fl_nlp_workspace_slots(const fl_nlp* nlp, int* n_values, int* n_checkpoints);
 /* fp64 operations per node of each pass (values, jac, hess, all): the algorithmic work the roofline is quoted on */
 void fl_nlp_ops_per_node(const fl_nlp* nlp, int ops[4]);
 
