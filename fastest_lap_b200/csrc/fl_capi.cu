@@ -351,15 +351,18 @@ int fl_nlp_structure(const fl_nlp* h, int* jac_row, int* jac_col, int* hess_row,
     return 1;
 }
 
-int fl_nlp_bounds(const fl_nlp* h, double* x_l, double* x_u, double* g_l, double* g_u)
+int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double* g_l, double* g_u)
 {
-    const fl_variant* v = h->v;
-    const fl_dev& P = h->P;
-    const int NV = v->NV, n_in = h->n_in;
+    if (!d || !d->wl || !d->wr || !d->vehicle_params) return fail("null problem description") ? 1 : 0;
+    const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque);
+    if (!v) return fail("unknown model / form") ? 1 : 0;
+    const int node0 = d->closed ? 0 : 1, n_points = d->n_points;
+    const int n_var_nodes = n_points - node0, n_elements = d->closed ? n_points : n_points - 1;
+    const int NV = v->NV, n_in = d->model == FL_MODEL_F1_3DOF ? F1_NIN : KART_NIN;
     const double big = std::numeric_limits<double>::max();
     std::vector<double> lb(NV), ub(NV);
-    const double* par = h->params.data();        // bounds that depend on parameters use problem 0
-    if (h->desc.model == FL_MODEL_F1_3DOF)
+    const double* par = d->vehicle_params;        // bounds that depend on parameters use problem 0
+    if (d->model == FL_MODEL_F1_3DOF)
     {
         // axle_car_3dof.hpp:366-397, chassis.hpp:400-425 (50..380 km/h, |v| <= 50 km/h, |omega| <= 10), chassis_car_3dof.hpp:306-352,
         // road_curvilinear.hpp:63-82
@@ -380,28 +383,28 @@ int fl_nlp_bounds(const fl_nlp* h, double* x_l, double* x_u, double* g_l, double
         lb[13] = -1.0; ub[13] = 1.0;
         if (v->IS_DERIVATIVE)
         {
-            const double r = h->desc.kart_direct_torque ? 4000.0 : 10.0;      // lot2016kart.h:186-192
+            const double r = d->kart_direct_torque ? 4000.0 : 10.0;      // lot2016kart.h:186-192
             lb[14] = -20.0 * DEG; ub[14] = 20.0 * DEG; lb[15] = -r; ub[15] = r;
         }
     }
     const int n_pos = n_in - 3;      // position of the lateral displacement within the node variables
-    for (int vn = 0; vn < P.n_var_nodes; ++vn)
+    for (int vn = 0; vn < n_var_nodes; ++vn)
     {
-        const int node = vn + P.node0;
+        const int node = vn + node0;
         for (int k = 0; k < NV; ++k)
         {
-            if (x_l) x_l[(size_t)vn * NV + k] = (k == n_pos) ? -h->wl[node] : lb[k];
-            if (x_u) x_u[(size_t)vn * NV + k] = (k == n_pos) ? h->wr[node] : ub[k];
+            if (x_l) x_l[(size_t)vn * NV + k] = (k == n_pos) ? -d->wl[node] : lb[k];
+            if (x_u) x_u[(size_t)vn * NV + k] = (k == n_pos) ? d->wr[node] : ub[k];
         }
     }
     (void)big;
     // constraints: equalities, then the 6 extra rows at the element's right node, then (derivative form) the control-rate rows
     const int n_eq = v->NTD + v->NALG;
     double el[6], eu[6];
-    for (int e = 0; e < P.n_elements; ++e)
+    for (int e = 0; e < n_elements; ++e)
     {
-        const int j = (e + 1 == P.n_points) ? 0 : e + 1;
-        if (h->desc.model == FL_MODEL_F1_3DOF)
+        const int j = (e + 1 == n_points) ? 0 : e + 1;
+        if (d->model == FL_MODEL_F1_3DOF)
         {
             // limebeer2014f1.h:232-262: +-max(lambda_max(0), lambda_max(m g0)) per tyre, track limits for n +- t/2 cos(alpha)
             const double m = par[0];
@@ -412,7 +415,7 @@ int fl_nlp_bounds(const fl_nlp* h, double* x_l, double* x_u, double* g_l, double
                 const double a = (0.0 - Fz1) * (l2 - l1) / (Fz2 - Fz1) + l1, b = (m * G0 - Fz1) * (l2 - l1) / (Fz2 - Fz1) + l1;
                 eu[t] = a > b ? a : b; el[t] = -eu[t];
             }
-            el[4] = el[5] = -h->wl[j]; eu[4] = eu[5] = h->wr[j];
+            el[4] = el[5] = -d->wl[j]; eu[4] = eu[5] = d->wr[j];
         }
         else
             for (int t = 0; t < 6; ++t) { el[t] = -0.11; eu[t] = 0.11; }      // lot2016kart.h:194-198
@@ -424,6 +427,11 @@ int fl_nlp_bounds(const fl_nlp* h, double* x_l, double* x_u, double* g_l, double
         }
     }
     return 1;
+}
+
+int fl_nlp_bounds(const fl_nlp* h, double* x_l, double* x_u, double* g_l, double* g_u)
+{
+    return fl_problem_bounds(&h->desc, x_l, x_u, g_l, g_u);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

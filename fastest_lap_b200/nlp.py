@@ -46,6 +46,7 @@ def load_library():
     lib.fl_nlp_sizes.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
     lib.fl_nlp_batch.argtypes = [C.c_void_p]
     lib.fl_nlp_bounds.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    lib.fl_problem_bounds.argtypes = [C.POINTER(_Desc), _dp, _dp, _dp, _dp]
     lib.fl_nlp_structure.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
     lib.fl_nlp_ops_per_node.argtypes = [C.c_void_p, _ip]
     lib.fl_nlp_workspace_slots.argtypes = [C.c_void_p, _ip, _ip]
@@ -87,6 +88,35 @@ def pinned_empty(count):
     return arr, p
 
 
+def _describe(lib, p, vehicle_params=None, device=0):
+    """fl_problem_desc of a LapProblem; returns (desc, arrays to keep alive, batch)."""
+    params = p.params if vehicle_params is None else vehicle_params
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    if params.ndim == 1:
+        params = params[None, :]
+    nvp = lib.fl_n_vehicle_params(p.model)
+    if params.shape[1] != nvp:
+        raise ValueError("vehicle parameter vectors must have %d entries" % nvp)
+    keep = [params, p.s, p.track_nodes, p.wl, p.wr, p.q0, p.u0, p.du0, p.ctrl_default]
+    d = _Desc()
+    d.model, d.form, d.closed, d.elevation, d.kart_direct_torque = p.model, p.form, int(p.closed), int(p.elevation), int(p.kart_direct_torque)
+    d.n_points, d.s, d.track_length, d.track_nodes, d.wl, d.wr = p.n_points, _ptr(p.s), p.track_length, _ptr(p.track_nodes), _ptr(p.wl), _ptr(p.wr)
+    d.batch, d.vehicle_params, d.sigma = params.shape[0], _ptr(params), p.sigma
+    d.dissipation[0], d.dissipation[1] = float(p.dissipation[0]), float(p.dissipation[1])
+    d.q0, d.u0, d.du0, d.ctrl_default, d.device = _ptr(p.q0), _ptr(p.u0), _ptr(p.du0), _ptr(p.ctrl_default), int(device)
+    return d, keep, params.shape[0]
+
+
+def problem_bounds(problem):
+    """Variable and constraint bounds of a lap (get_bounds_info; optimal_laptime.hpp:326-483): host-only, no device needed."""
+    lib = load_library()
+    d, keep, _ = _describe(lib, problem)
+    xl, xu, gl, gu = np.zeros(problem.n), np.zeros(problem.n), np.zeros(problem.m), np.zeros(problem.m)
+    if not lib.fl_problem_bounds(C.byref(d), _ptr(xl), _ptr(xu), _ptr(gl), _ptr(gu)):
+        raise RuntimeError("fl_problem_bounds: " + lib.fl_last_error().decode())
+    return xl, xu, gl, gu
+
+
 class CollocationNLP:
     """One batch of collocation NLPs sharing mesh and layout, resident on one GPU."""
 
@@ -94,20 +124,8 @@ class CollocationNLP:
         assert isinstance(problem, LapProblem)
         lib = self._lib = load_library()
         p = self.problem = problem
-        params = p.params if vehicle_params is None else vehicle_params
-        params = np.ascontiguousarray(params, dtype=np.float64)
-        if params.ndim == 1:
-            params = params[None, :]
-        nvp = lib.fl_n_vehicle_params(p.model)
-        if params.shape[1] != nvp:
-            raise ValueError("vehicle parameter vectors must have %d entries" % nvp)
-        self._keep = [params, p.s, p.track_nodes, p.wl, p.wr, p.q0, p.u0, p.du0, p.ctrl_default]
-        d = _Desc()
-        d.model, d.form, d.closed, d.elevation, d.kart_direct_torque = p.model, p.form, int(p.closed), int(p.elevation), int(p.kart_direct_torque)
-        d.n_points, d.s, d.track_length, d.track_nodes, d.wl, d.wr = p.n_points, _ptr(p.s), p.track_length, _ptr(p.track_nodes), _ptr(p.wl), _ptr(p.wr)
-        d.batch, d.vehicle_params, d.sigma = params.shape[0], _ptr(params), p.sigma
-        d.dissipation[0], d.dissipation[1] = float(p.dissipation[0]), float(p.dissipation[1])
-        d.q0, d.u0, d.du0, d.ctrl_default, d.device = _ptr(p.q0), _ptr(p.u0), _ptr(p.du0), _ptr(p.ctrl_default), int(device)
+        d, self._keep, batch = _describe(lib, p, vehicle_params, device)
+        params = self._keep[0]
         self._h = lib.fl_nlp_create(C.byref(d))
         if not self._h:
             raise RuntimeError("fl_nlp_create: " + lib.fl_last_error().decode())

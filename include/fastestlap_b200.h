@@ -69,6 +69,9 @@ int  fl_nlp_batch(const fl_nlp* nlp);
 const char* fl_nlp_variant(const fl_nlp* nlp);
 /* get_bounds_info (optimal_laptime.hpp:326-483): model default bounds, track limits on the lateral displacement */
 int fl_nlp_bounds(const fl_nlp* nlp, double* x_l, double* x_u, double* g_l, double* g_u);
+/* the same from the description alone (host-only: no device is touched); only model, form, closed, elevation,
+ * kart_direct_torque, n_points, wl, wr and vehicle_params (problem 0) are read */
+int fl_problem_bounds(const fl_problem_desc* desc, double* x_l, double* x_u, double* g_l, double* g_u);
 /* fixed sparsity (triplets), same for every problem of the batch */
 int fl_nlp_structure(const fl_nlp* nlp, int* jac_row, int* jac_col, int* hess_row, int* hess_col);
 /* per-node slots of the device workspace written by the values pass: node values handed to the element assembly, and

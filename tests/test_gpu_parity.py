@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from tests.helpers import load_golden, oracle_nlp
+from tests.helpers import load_golden, oracle_nlp, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -182,7 +182,9 @@ def test_batch_of_parameter_sets_matches_single_problems():
         single = CollocationNLP(pb)
         ob = single.eval_all(xs[b], lams[b], 0.5)
         for k in ("f", "g", "grad", "jac", "hess"):
-            assert np.array_equal(ob[k][0], out[k][b]), k
+            # the batch reads its per-problem parameters from global memory, the single problem from the constant bank:
+            # two compilations of the same straight-line code, equal up to the rounding of fused multiply-adds
+            assert rel_err(out[k][b], ob[k][0]) <= 1e-12, k
         single.close()
     nlp.close()
 
