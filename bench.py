@@ -116,6 +116,83 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+N_LAPS = 4096
+
+
+def batched_leg(args, torch, dist, world, rank, local, peak):
+    """BASELINE.json configs[4]: 4096 independent F1 laps of 500 nodes with perturbed vehicle parameters, sharded
+    contiguously over the ranks (no data-path collective; one gather of the objective values at the end).  A step = one
+    full callback round of every lap.  The batch's buffers (GBs) exceed the L2 many times over: no flush needed."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, pinned_empty
+    from fastest_lap_b200.problem import LapProblem
+    from fastest_lap_b200.sharding import shard_range, gather_results
+    from fastest_lap_b200.vehicle import MODEL_F1
+    p, ex = LapProblem.load_npz(os.path.join(ROOT, "tests", "golden", "f1_catalunya_discrete.npz"))
+    lo, hi = shard_range(args.laps, world, rank)
+    B = hi - lo
+    params = workloads.sweep_parameters(MODEL_F1, args.laps)[lo:hi]
+    nlp = CollocationNLP(p, vehicle_params=params, device=local)
+    rng = np.random.default_rng(1000 + lo)
+    hx, _ = pinned_empty(B * nlp.n); hl, _ = pinned_empty(B * nlp.m)
+    X = hx.reshape(B, nlp.n); Lm = hl.reshape(B, nlp.m)
+    X[:] = ex["x"][None, :] * (1.0 + 1.0e-3 * rng.standard_normal((B, 1)))
+    Lm[:] = np.random.default_rng(1).standard_normal(nlp.m)[None, :]
+    out = {}
+    for k, cnt in (("f", B), ("g", B * nlp.m), ("grad", B * nlp.n), ("jac", B * nlp.nnz_jac), ("hess", B * nlp.nnz_hess)):
+        out[k], _ = pinned_empty(cnt)
+    nlp.eval_all(hx, hl, 1.0, out=out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        nlp.sync()
+
+    K = max(1, min(args.steps, 20))
+    for _ in range(3):
+        nlp.time_device(EVAL_ALL, 1.0, 1)
+    barrier()
+    l0 = nlp.kernel_launches
+    dev_ms = sum(nlp.time_device(EVAL_ALL, 1.0, 1) for _ in range(K))
+    barrier()
+    launches = nlp.kernel_launches - l0
+    ker_ms = sum(nlp.time_device(EVAL_JAC | EVAL_HESS, 1.0, 1) for _ in range(K))
+    val_ms = sum(nlp.time_device(0, 1.0, 1) for _ in range(K))
+    ker_ms -= val_ms
+    Ke = 2
+    nlp.eval_all(hx, hl, 1.0, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        nlp.eval_all(hx, hl, 1.0, out=out)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / Ke
+    t = torch.tensor([dev_ms / K, e2e_s, ker_ms / K, val_ms / K], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    f_all = gather_results(out["f"].reshape(B, 1).copy(), args.laps)          # the final gather of per-lap results
+    dev_ms, e2e_s, ker_ms, val_ms = [float(v) for v in t.tolist()]
+    nodes = p.n_points * args.laps
+    per_node = (p.nv + p.ncpe + 5) * 8 + p.nv * 8 + (nlp.nnz_jac + nlp.nnz_hess) * 8 / p.n_points
+    # per-rank kernel: the slowest rank's launch over the largest shard
+    shard_nodes = p.n_points * (-(-args.laps // world))
+    achieved = per_node * shard_nodes / (ker_ms * 1e-3) / 1e9
+    res = {"workload": "%d independent limebeer-2014-f1 laps, Catalunya, 500 nodes, closed, direct form; mass, cd, cl, power drawn per lap (rng 2); "
+                       "contiguous shards over %d GPU(s), no data-path collective, one final all_gather of the %d objective values" % (args.laps, world, args.laps),
+           "laps": args.laps, "laps_per_gpu": B, "scaling": "strong", "value": nodes / (dev_ms * 1e-3), "unit": UNIT, "steps": K, "ms_per_step": dev_ms,
+           "rounds_per_s": args.laps / (dev_ms * 1e-3), "gpu_launches": int(launches),
+           "e2e": {"value": nodes / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "steps": Ke, "h2d_bytes_per_step": int(B * (nlp.n + nlp.m) * 8),
+                   "d2h_bytes_per_step": int(B * (1 + nlp.m + nlp.n + nlp.nnz_jac + nlp.nnz_hess) * 8)},
+           "kernels_ms": {"node_values": val_ms, "node_derivs+assemble": ker_ms},
+           "roofline": {"bound": "hbm", "kernel": "k_node_derivs<%s, all> (per-lap parameters from global memory)" % nlp.variant, "achieved": achieved,
+                        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "bytes_per_node_eval": per_node,
+                        "fp64_ops_per_node_eval": nlp.ops_per_node["all"]},
+           "objective_checksum": float(np.sum(f_all))}
+    nlp.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -124,6 +201,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nodes", type=int, default=N_NODES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--laps", type=int, default=N_LAPS, help="laps of the batched leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -239,9 +317,17 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(p, x, lam)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
     for h in ring:
         h.close()
+    ring = None
+    if args.laps > 0:
+        peak_ = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        b = batched_leg(args, torch, dist, world, rank, local, peak_)
+        if rank == 0:
+            line["batched"] = b
+            line["gpu_launches"] += b["gpu_launches"]
+    if rank == 0:
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
