@@ -53,14 +53,19 @@ class ParamTable:
 class Emitter:
     """Emits one function body: `inputs` maps symbol name -> C expression; outputs are (expr id, "statement with one %s") pairs."""
 
-    def __init__(self, graph, ptable, inputs, dfmt="D[%d]", cut=None):
+    def __init__(self, graph, ptable, inputs, dfmt="D[%d]", cut=None, lazy_inputs=None, segment=0):
         # cut: node id -> C expression that LOADS the node's value (a checkpoint written by an earlier pass) instead of
         # recomputing it; the load is emitted lazily, right before the first use
+        # lazy_inputs: symbol name -> (local name, C expression that loads it), emitted at first use instead of up front
+        # segment: > 0 splits the body into segments of that many arithmetic statements separated by `io.fence(t)`; the
+        #          loads a segment needs are issued at the start of the PREVIOUS segment (software prefetch into registers)
         self.g, self.pt, self.inputs, self.dfmt, self.cut = graph, ptable, inputs, dfmt, (cut or {})
+        self.lazy_inputs, self.segment = (lazy_inputs or {}), int(segment)
 
     def body(self, outputs, indent="    "):
         g, pt = self.g, self.pt
         lines = []
+        is_load = set()     # indices into `lines` of statements that only load a value
         name = {}
         K, A, B = g.kind, g.a, g.b
 
@@ -95,11 +100,13 @@ class Emitter:
                     continue
                 if n in self.cut:
                     name[n] = "t%d" % n
+                    is_load.add(len(lines))
                     lines.append("%sconst double t%d = %s;" % (indent, n, self.cut[n]))
                     continue
                 if K[n] != SYM and pt.param_only(n):
                     s = pt.slot(n)
                     name[n] = "d%d" % s
+                    is_load.add(len(lines))
                     lines.append("%sconst double d%d = %s;" % (indent, s, self.dfmt % s))
                     continue
                 if K[n] == SYM:
@@ -107,7 +114,13 @@ class Emitter:
                     if cls == "p":
                         s = pt.slot(n)
                         name[n] = "d%d" % s
+                        is_load.add(len(lines))
                         lines.append("%sconst double d%d = %s;" % (indent, s, self.dfmt % s))
+                    elif A[n] in self.lazy_inputs:
+                        local, load = self.lazy_inputs[A[n]]
+                        name[n] = local
+                        is_load.add(len(lines))
+                        lines.append("%sconst double %s = %s;" % (indent, local, load))
                     else:
                         name[n] = self.inputs[A[n]]
                     continue
@@ -144,7 +157,38 @@ class Emitter:
         for e, fmt in outputs:
             emit(e)
             lines.append(indent + (fmt % ref(e)))
+        if self.segment > 0:
+            lines = self._pipeline(lines, is_load, indent)
         return "\n".join(lines)
+
+    def _pipeline(self, lines, is_load, indent):
+        """Segments of `self.segment` arithmetic statements; segment k's loads move to the start of segment k-1, and every
+        boundary stores the value computed last through `io.fence` (a store the compiler must assume may alias the inputs,
+        so it cannot hoist the following loads above it -- it otherwise moves every load to the top and spills)."""
+        import re
+        segs, cur, nops, last_tmp = [[]], [], 0, None
+        loads = [[]]
+        for idx, ln in enumerate(lines):
+            if idx in is_load:
+                loads[-1].append(ln)
+                continue
+            segs[-1].append(ln)
+            m = re.match(r"\s*const double (t\d+) = ", ln)
+            if m:
+                nops += 1
+                last_tmp = m.group(1)
+                if nops % self.segment == 0:
+                    segs[-1].append("%sio.fence(%s);" % (indent, last_tmp))
+                    segs.append([])
+                    loads.append([])
+        out = []
+        for k in range(len(segs)):
+            if k == 0:
+                out += loads[0]
+            if k + 1 < len(segs):
+                out += loads[k + 1]
+            out += segs[k]
+        return out
 
 
 def emit_host_derive(graph, ptable, fname):

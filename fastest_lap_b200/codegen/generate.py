@@ -17,6 +17,7 @@ The code is what the CppAD tape sweeps of the reference compute (lion::ipopt_cpp
 src/core/applications/optimal_laptime.hpp:546-551), differentiated at build time instead of interpreted at run time.
 """
 import os
+import re
 import sys
 
 from .nlpnode import Variant, NodeProgram
@@ -28,6 +29,9 @@ OUT_DIR = os.path.join(HERE, "..", "csrc", "generated")
 # warps (= straight-line code partitions) per group of 32 nodes in each derivative kernel
 NPARTS = {"jac": int(os.environ.get("FL_NP_JAC", 4)), "hess": int(os.environ.get("FL_NP_HESS", 8)), "all": int(os.environ.get("FL_NP_ALL", 8)),
           "values": int(os.environ.get("FL_NP_VALUES", 1))}
+
+# arithmetic statements per fenced segment of a derivative partition (0 = no fences, all loads where the compiler puts them)
+SEGMENT = int(os.environ.get("FL_SEGMENT", 0))
 
 VARIANTS = {
     "f1_direct": Variant("f1", "direct"),
@@ -137,7 +141,14 @@ def generate(name, variant):
     out_ck = [(n, "io.cs(%d, %%s);" % k) for k, n in enumerate(ck)]
 
     def fn(fname, outputs, pres, use_cut=True):
-        em = Emitter(g, pt, inputs, dfmt="io.d(%d)", cut=cut if use_cut else None)
+        lazy = {}
+        if use_cut and SEGMENT > 0:
+            # derivative partitions: every input is loaded at first use and software-prefetched one segment ahead
+            for l in sum(pres, []):
+                m = re.match(r"const double (\w+) = (io\.\w+\(\d*\));", l)
+                lazy[m.group(1)] = (m.group(1), m.group(2))
+            pres = []
+        em = Emitter(g, pt, inputs, dfmt="io.d(%d)", cut=cut if use_cut else None, lazy_inputs=lazy, segment=SEGMENT if use_cut else 0)
         body = em.body(outputs, indent="        ")
         head = "\n".join("        " + l for l in sum(pres, []))
         return ("    template <class IO> static __device__ __forceinline__ void %s(IO& io)\n    {\n%s\n%s\n    }\n" % (fname, head, body))

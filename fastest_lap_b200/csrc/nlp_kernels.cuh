@@ -86,6 +86,7 @@ struct ValuesIO
     __device__ __forceinline__ double d(int k) const { if constexpr (CD) return Dk->d[k]; else return __ldg(Dp + k); }
     __device__ __forceinline__ void val(int k, double v) const { Vn[k * 32] = v; }
     __device__ __forceinline__ void cs(int k, double v) const { Cn[k * 32] = v; }
+    __device__ __forceinline__ void fence(double) const {}
 };
 
 template <class G, bool CD>
@@ -227,6 +228,9 @@ struct DerivIO
     __device__ __forceinline__ double uprev(int c) const { return xp[G::ctrl_pos(c)]; }
     __device__ __forceinline__ double unext(int c) const { return xq[G::ctrl_pos(c)]; }
     __device__ __forceinline__ void val(int, double) const {}
+    // codegen FL_SEGMENT > 0 separates code segments with fence(); measured on B200 (profiles/README.md) the fenced,
+    // software-prefetched schedule is slower than ptxas' own (the spills are the reverse sweep's tape, not hoisted loads)
+    __device__ __forceinline__ void fence(double) const {}
     __device__ __forceinline__ void grad(int k, double v) const { gradn[k] = v; }
     __device__ __forceinline__ void ja(int k, double v) const { ja_[k * sA] = v; }
     __device__ __forceinline__ void jb(int k, double v) const { if (hasB) jb_[k * sB] = v; }

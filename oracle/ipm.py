@@ -18,6 +18,8 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
+from . import kkt
+
 
 class Options:
     tol = 1.0e-10
@@ -64,7 +66,7 @@ class Result:
     pass
 
 
-def solve(evaluate, x0, xl, xu, gl, gu, opts=None, y0=None, log=None, kkt_solver=None):
+def solve(evaluate, x0, xl, xu, gl, gu, opts=None, y0=None, log=None, kkt_solver=None, layout=None):
     """evaluate(x, y, obj_factor, derivs) -> dict(f, g[, grad, J (csr m x n), H (csr n x n symmetric)])."""
     o = opts or Options()
     n, m = len(x0), len(gl)
@@ -105,11 +107,21 @@ def solve(evaluate, x0, xl, xu, gl, gu, opts=None, y0=None, log=None, kkt_solver
         return sol[:n], sol[n:]
 
     if y0 is None:
-        # least-squares multipliers (Ipopt's default initialisation): [I J^T; J 0][w; y] = -[grad f - zl + zu; 0]
-        _, yls = kkt_solve(sp.csr_matrix((n, n)), ev["J"], np.ones(n), np.ones(ni) * 1e300, 0.0, 0.0, -(ev["grad"] - zl + zu), np.zeros(m))
-        # the slack rows: y_i = vl - vu = 0 at the start
-        yls[ineq] = 0.0
-        y = yls if np.max(np.abs(yls)) <= o.y_init_max else np.zeros(m)
+        # least-squares multipliers (Ipopt's default initialisation): min |grad f + J^T y - zl + zu|^2 + |-y_ineq - vl + vu|^2,
+        # i.e. [I J^T; J -D][w; y] = -[grad f - zl + zu; 0] with D = 1 on the inequality rows (their slack columns)
+        try:
+            if layout is not None:
+                Dv = np.full(m, o.delta_c_bar * mu ** o.kappa_c)
+                Dv[ineq] = 1.0
+                Dg, Lo = kkt.assemble_blocks(layout, sp.csr_matrix((n, n)), ev["J"], np.ones(n), Dv)
+                F = kkt.BlockCyclicLDL(Dg, Lo, layout.closed)
+                r1_, r2_ = -(ev["grad"] - zl + zu), np.zeros(m)
+                _, yls = kkt.expand_solution(layout, ev["J"], Dv, r2_, F.solve(kkt.condense_rhs(layout, ev["J"], Dv, r1_, r2_)))
+            else:
+                _, yls = kkt_solve(sp.csr_matrix((n, n)), ev["J"], np.ones(n), np.ones(ni), 0.0, 0.0, -(ev["grad"] - zl + zu), np.zeros(m))
+            y = yls if np.all(np.isfinite(yls)) and np.max(np.abs(yls)) <= o.y_init_max else np.zeros(m)
+        except RuntimeError:
+            y = np.zeros(m)
 
     def resid(x, s, g):
         c = g.copy()
@@ -136,7 +148,7 @@ def solve(evaluate, x0, xl, xu, gl, gu, opts=None, y0=None, log=None, kkt_solver
     theta_max = theta_min = None
     dw_last = 0.0
     res = Result()
-    res.status, res.iters, res.n_reg, res.history = "max_iter", 0, 0, []
+    res.status, res.iters, res.n_reg, res.n_fact, res.history = "max_iter", 0, 0, 0, []
     acceptable_count = 0
 
     for it in range(o.max_iter + 1):
@@ -183,25 +195,72 @@ def solve(evaluate, x0, xl, xu, gl, gu, opts=None, y0=None, log=None, kkt_solver
             ds = (dy[ineq] - rs_bar) / (sig_s + dw)
             return dx, ds, dy
 
-        # regularisation: inertia-free curvature test along the computed direction
-        dc = o.delta_c_bar * mu ** o.kappa_c
-        dw = 0.0
-        while True:
+        # regularisation
+        if layout is not None:
+            # Algorithm IC of the paper with the exact inertia of the block factorisation
+            def factor(dw_, dc_):
+                Dv = np.full(m, dc_)
+                Dv[ineq] += 1.0 / (sig_s + dw_)
+                Dg, Lo = kkt.assemble_blocks(layout, H, J, sig_x + dw_, Dv)
+                F = kkt.BlockCyclicLDL(Dg, Lo, layout.closed)
+                return F, Dv
+            n_pos, n_neg = layout.n, layout.n_stages * layout.neq
+            # closed laps with an even number of nodes and massless wheels have structurally dependent rows (the wheel rows
+            # of consecutive elements read f_i + f_j = 0: their alternating sum vanishes), so the Jacobian regularisation
+            # of IC-2 is always on -- what Ipopt's degeneracy heuristic arrives at after its first iterations
+            dw, dc = 0.0, o.delta_c_bar * mu ** o.kappa_c
+            F, Dv = factor(dw, dc)
+            res.n_fact += 1
+            while not (F.ok and F.inertia == (n_pos, n_neg, 0)):
+                res.n_reg += 1
+                if dw == 0.0:
+                    dw = o.delta_w_0 if dw_last == 0.0 else max(o.delta_w_min, o.kappa_w_minus * dw_last)
+                else:
+                    dw *= o.kappa_w_plus_bar if dw_last == 0.0 else o.kappa_w_plus
+                if dw > o.delta_w_max:
+                    res.status = "regularisation_failed"
+                    break
+                F, Dv = factor(dw, dc)
+                res.n_fact += 1
+            if res.status == "regularisation_failed":
+                break
+
+            def direction(dw_, dc_, cvec):
+                r2 = -cvec.copy()
+                r2[ineq] -= rs_bar / (sig_s + dw_)
+                b = kkt.condense_rhs(layout, J, Dv, r1, r2)
+                z = F.solve(b)
+                dx_, dy_ = kkt.expand_solution(layout, J, Dv, r2, z)
+                for _ in range(o.refine_steps):
+                    # iterative refinement on the full augmented system
+                    e1 = r1 - (H @ dx_ + (sig_x + dw_) * dx_ + J.T @ dy_)
+                    e2 = r2 - (J @ dx_ - Dv * dy_)
+                    z = F.solve(kkt.condense_rhs(layout, J, Dv, e1, e2))
+                    ddx, ddy = kkt.expand_solution(layout, J, Dv, e2, z)
+                    dx_, dy_ = dx_ + ddx, dy_ + ddy
+                ds_ = (dy_[ineq] - rs_bar) / (sig_s + dw_)
+                return dx_, ds_, dy_
             dx, ds, dy = direction(dw, dc, c)
-            Hd = H @ dx
-            curv = dx @ Hd + dx @ ((sig_x + dw) * dx) + ds @ ((sig_s + dw) * ds)
-            if np.all(np.isfinite(dx)) and curv >= o.curv_tol * (dx @ dx + ds @ ds):
+        else:
+            # inertia-free curvature test along the computed direction (Chiang & Zavala)
+            dc = o.delta_c_bar * mu ** o.kappa_c
+            dw = 0.0
+            while True:
+                dx, ds, dy = direction(dw, dc, c)
+                Hd = H @ dx
+                curv = dx @ Hd + dx @ ((sig_x + dw) * dx) + ds @ ((sig_s + dw) * ds)
+                if np.all(np.isfinite(dx)) and curv >= o.curv_tol * (dx @ dx + ds @ ds):
+                    break
+                res.n_reg += 1
+                if dw == 0.0:
+                    dw = o.delta_w_0 if dw_last == 0.0 else max(o.delta_w_min, o.kappa_w_minus * dw_last)
+                else:
+                    dw *= o.kappa_w_plus_bar if dw_last == 0.0 else o.kappa_w_plus
+                if dw > o.delta_w_max:
+                    res.status = "regularisation_failed"
+                    break
+            if res.status == "regularisation_failed":
                 break
-            res.n_reg += 1
-            if dw == 0.0:
-                dw = o.delta_w_0 if dw_last == 0.0 else max(o.delta_w_min, o.kappa_w_minus * dw_last)
-            else:
-                dw *= o.kappa_w_plus_bar if dw_last == 0.0 else o.kappa_w_plus
-            if dw > o.delta_w_max:
-                res.status = "regularisation_failed"
-                break
-        if res.status == "regularisation_failed":
-            break
         if dw > 0.0:
             dw_last = dw
 

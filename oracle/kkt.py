@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy statement of the block-cyclic-tridiagonal KKT factorisation the device solver runs
+(fastest_lap_b200/csrc/kkt_kernels.cuh).
+
+The reference leaves the linear algebra of every interior-point iteration to Ipopt + MUMPS (third-party, absent from the
+reference tree; call site /root/reference/src/core/applications/optimal_laptime.hpp:546-551).  The augmented system of the
+collocation NLP,
+
+        [ W + Sigma_x + dw I      J^T ] [dx]   [r1]
+        [ J                       -D  ] [dy] = [r2],        D = dc (equality rows),  1/(Sigma_s + dw) + dc (inequality rows),
+
+has a chain structure: W is block diagonal per node plus control-control couplings between neighbouring
+nodes, and the rows of element e (node e -> node e+1) touch only those two nodes.  With the inequality rows (which touch
+the element's right node only) condensed into that node's diagonal block, and the unknowns grouped per stage
+z_j = (dx_j, dy of the equality rows of the element that ENDS at node j), the matrix is symmetric block tridiagonal --
+cyclic for closed laps -- with blocks of NV + n_eq (28 for the F1 direct form).  Stages are eliminated from the last one
+backwards (the order of a Riccati recursion: the Schur complement handed to stage j-1 is the cost-to-go Hessian of node
+j-1), stage 0 last; the closing element of a closed lap makes every stage couple with stage 0 through a fill block F_j.
+
+Inertia: by Haynsworth additivity the inertia of the whole matrix is the sum of the inertias of the pivot blocks, so the
+factorisation reports exactly what Ipopt asks of MUMPS (n positive, m negative eigenvalues, none zero).
+"""
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+
+class StageLayout:
+    """Index bookkeeping of one lap: which (variable / equality-row / inequality-row) belongs to which stage."""
+
+    def __init__(self, n_points, n_elements, nv, ncpe, eq_rows, closed):
+        self.n_points, self.n_elements, self.nv, self.ncpe, self.closed = n_points, n_elements, nv, ncpe, bool(closed)
+        self.eq_rows = np.asarray(eq_rows)
+        self.ineq_rows = np.array([r for r in range(ncpe) if r not in set(self.eq_rows.tolist())])
+        self.neq = len(self.eq_rows)
+        self.nb = nv + self.neq
+        self.n_stages = n_elements                      # closed: one per node; open: one per free node (node 0 is fixed)
+        self.n, self.m = n_elements * nv, n_elements * ncpe
+        # element e ends at free node index: closed -> (e + 1) % N ; open -> e (free nodes are 1..N-1, numbered 0..N-2)
+        st_of_el = (np.arange(n_elements) + 1) % n_points if closed else np.arange(n_elements)
+        self.stage_of_element = st_of_el
+        xs = np.arange(self.n).reshape(n_elements, nv)
+        rows = np.arange(self.m).reshape(n_elements, ncpe)
+        self.x_index = xs                                # [stage][nv]  (variable node == stage)
+        el_of_stage = np.empty(n_elements, int)
+        el_of_stage[st_of_el] = np.arange(n_elements)
+        self.element_of_stage = el_of_stage
+        self.eq_index = rows[el_of_stage][:, self.eq_rows]        # [stage][neq]  global constraint rows
+        self.ineq_index = rows[el_of_stage][:, self.ineq_rows]    # [stage][nineq]
+        self.all_eq = self.eq_index.ravel()
+        self.all_ineq = self.ineq_index.ravel()
+        # permutation of the reduced unknown vector (dx, dy_eq) into stage order
+        self.perm = np.concatenate([np.concatenate([xs[j], self.n + np.arange(j * self.neq, (j + 1) * self.neq)]) for j in range(n_elements)])
+
+
+def assemble_blocks(lay, H, J, sig_x, D):
+    """Diagonal blocks Dg[stage] and sub-diagonal blocks Lo[stage] = K[stage, stage-1] (Lo[0] = corner K[0, last] of closed
+    laps, zero otherwise) of the condensed KKT matrix.  H: n x n symmetric sparse; J: m x n sparse; sig_x: [n] diagonal
+    added to H; D: [m] (see module docstring).  Also returns the operator that condenses a right-hand side."""
+    n, neq, nb, S = lay.n, lay.neq, lay.nb, lay.n_stages
+    Jc = sp.csr_matrix(J)
+    Ji = Jc[lay.all_ineq]
+    Je = Jc[lay.all_eq]
+    Dinv_i = 1.0 / D[lay.all_ineq]
+    W = sp.csr_matrix(H) + sp.diags(sig_x) + Ji.T @ sp.diags(Dinv_i) @ Ji
+    K = sp.bmat([[W, Je.T], [Je, -sp.diags(D[lay.all_eq])]], format="csr")
+    Kp = K[lay.perm][:, lay.perm].tobsr(blocksize=(nb, nb))
+    Kp.sort_indices()
+    Dg = np.zeros((S, nb, nb))
+    Lo = np.zeros((S, nb, nb))
+    indptr, indices, data = Kp.indptr, Kp.indices, Kp.data
+    for j in range(S):
+        for p in range(indptr[j], indptr[j + 1]):
+            c = indices[p]
+            if c == j:
+                Dg[j] = data[p]
+            elif c == j - 1:
+                Lo[j] = data[p]
+            elif j == 0 and c == S - 1 and S > 2:
+                Lo[0] = data[p]
+            elif c == j + 1 or (j == S - 1 and c == 0):
+                pass                                        # upper part, by symmetry
+            else:
+                raise AssertionError("entry outside the block-cyclic-tridiagonal pattern: stage %d, %d" % (j, c))
+    if S == 2 and lay.closed:
+        raise NotImplementedError("closed laps need at least three nodes")
+    return Dg, Lo
+
+
+def condense_rhs(lay, J, D, r1, r2):
+    """Right-hand side of the condensed system in stage order."""
+    Jc = sp.csr_matrix(J)
+    Ji = Jc[lay.all_ineq]
+    b1 = r1 + Ji.T @ (r2[lay.all_ineq] / D[lay.all_ineq])
+    return np.concatenate([b1, r2[lay.all_eq]])[lay.perm].reshape(lay.n_stages, lay.nb)
+
+
+def expand_solution(lay, J, D, r2, z):
+    """(dx, dy) of the full augmented system from the stage-ordered solution z."""
+    full = np.empty(lay.n + lay.n_stages * lay.neq)
+    full[lay.perm] = z.ravel()
+    dx = full[:lay.n]
+    dy = np.empty(lay.m)
+    dy[lay.all_eq] = full[lay.n:]
+    Ji = sp.csr_matrix(J)[lay.all_ineq]
+    dy[lay.all_ineq] = (Ji @ dx - r2[lay.all_ineq]) / D[lay.all_ineq]
+    return dx, dy
+
+
+def _inertia(ldl_d):
+    """(#positive, #negative, #zero) of the block-diagonal factor of scipy.linalg.ldl."""
+    w = np.linalg.eigvalsh(ldl_d)
+    tol = 1e-300
+    return int(np.sum(w > tol)), int(np.sum(w < -tol)), int(np.sum(np.abs(w) <= tol))
+
+
+class BlockCyclicLDL:
+    """Backward block elimination (see module docstring).  Dg, Lo are consumed."""
+
+    def __init__(self, Dg, Lo, cyclic):
+        S, nb, _ = Dg.shape
+        self.S, self.nb, self.cyclic = S, nb, bool(cyclic) and S > 1
+        self.Lo = Lo
+        self.F = np.zeros((S, nb, nb)) if self.cyclic else None      # F[j] = K[0, j] after fill, j >= 1
+        self.lu = [None] * S
+        self.XL = np.zeros((S, nb, nb))                               # D_j^{-1} L_j
+        self.XF = np.zeros((S, nb, nb)) if self.cyclic else None      # D_j^{-1} F_j^T
+        pos = neg = zero = 0
+        self.ok = True
+        if self.cyclic:
+            self.F[S - 1] = Lo[0]
+            self.F[1] = self.F[1] + Lo[1].T
+        for j in range(S - 1, -1, -1):
+            Dj = 0.5 * (Dg[j] + Dg[j].T)
+            try:
+                _, d, _ = sla.ldl(Dj, lower=True)
+                p, q, z = _inertia(d)
+            except Exception:
+                p, q, z = 0, 0, nb
+            pos, neg, zero = pos + p, neg + q, zero + z
+            self.lu[j] = sla.lu_factor(Dj)
+            if not np.all(np.isfinite(self.lu[j][0])):
+                self.ok = False
+            if j == 0:
+                break
+            if self.cyclic:
+                XF = sla.lu_solve(self.lu[j], self.F[j].T)
+                self.XF[j] = XF
+                Dg[0] -= self.F[j] @ XF
+            if j >= 2 or not self.cyclic:
+                XL = sla.lu_solve(self.lu[j], Lo[j])
+                self.XL[j] = XL
+                Dg[j - 1] -= Lo[j].T @ XL
+                if self.cyclic:
+                    self.F[j - 1] -= self.F[j] @ XL
+        self.inertia = (pos, neg, zero)
+
+    def solve(self, b):
+        """b: [S][nb] -> z with K z = b."""
+        S, cyc = self.S, self.cyclic
+        b = np.array(b, dtype=float)
+        y = np.zeros_like(b)
+        for j in range(S - 1, 0, -1):
+            y[j] = sla.lu_solve(self.lu[j], b[j])
+            if j >= 2 or not cyc:
+                b[j - 1] -= self.Lo[j].T @ y[j]
+            if cyc:
+                b[0] -= self.F[j] @ y[j]
+        z = np.zeros_like(b)
+        z[0] = sla.lu_solve(self.lu[0], b[0])
+        for j in range(1, S):
+            z[j] = y[j]
+            if j >= 2 or not cyc:
+                z[j] -= self.XL[j] @ z[j - 1]
+            if cyc:
+                z[j] -= self.XF[j] @ z[0]
+        return z

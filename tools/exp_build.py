@@ -1,5 +1,6 @@
 """Experiment builds of one variant's derivative kernel: python tools/exp_build.py NAME NP_ALL DBLOCK MINB [extra nvcc flags]
-Writes exp/NAME/lib.so = the experimental f1_direct unit linked with the standard objects of the other variants."""
+Environment: FL_SEGMENT (fenced segment length), EXP_VARIANT.  Writes exp/NAME/lib.so = the experimental unit linked with
+stubs for the other variants."""
 import os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,13 +19,13 @@ for f in ("variant.cu", "nlp_kernels.cuh"):
     shutil.copy(os.path.join(csrc, f), d)
 obj = os.path.join(d, "variant.o")
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-       "-DFL_VARIANT=" + variant, "-DFL_DBLOCK_N=%d" % dblock, "-DFL_DMINB=%d" % minb, "-DFL_VBLOCK_N=%s" % os.environ.get("FL_VBLOCK", "64")] + extra + ["-c", os.path.join(d, "variant.cu"), "-o", obj]
+       "-DFL_VARIANT=" + variant, "-DFL_DBLOCK_N=%d" % dblock, "-DFL_DMINB=%d" % minb, "-DFL_VBLOCK_N=%s" % os.environ.get("FL_VBLOCK", "128")] + extra + ["-c", os.path.join(d, "variant.cu"), "-o", obj]
 r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
 open(os.path.join(d, "build.log"), "w").write(r.stdout)
 assert r.returncode == 0, r.stdout[-3000:]
 import re
-for m in re.finditer(r"k_node_derivsI\w+Li(\d)E.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", r.stdout):
-    print("derivs<%s>: stack %s spill st %s ld %s regs %s" % m.groups())
+for m in re.finditer(r"k_node_derivsI\w+Li(\d)ELb(\d)ELb(\d)E.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", r.stdout):
+    print("derivs<what %s, assemble %s, const-bank %s>: stack %s spill st %s ld %s regs %s" % m.groups())
 std = os.path.join(csrc, "build")
 stub = os.path.join(d, "stubs.cu")
 with open(stub, "w") as fh:
