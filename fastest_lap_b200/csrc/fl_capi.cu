@@ -9,8 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/fastestlap_b200.h"
-#include "nlp_kernels.cuh"
+#include "fl_internal.h"
 
 #define FL_DECLARE_VARIANT(name) extern "C" const fl_variant* fl_variant_##name();
 FL_DECLARE_VARIANT(f1_direct)
@@ -62,27 +61,6 @@ template <class T> T* dev_alloc(size_t count)
 
 } // namespace
 
-struct fl_nlp
-{
-    const fl_variant* v = nullptr;
-    fl_problem_desc desc{};
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    fl_dev P{};
-    // owned device buffers
-    double *d_xfull = nullptr, *d_xuser = nullptr, *d_tc = nullptr, *d_D = nullptr, *d_lambda = nullptr, *d_zeros = nullptr;
-    double *d_C = nullptr, *d_V = nullptr, *d_g = nullptr, *d_f = nullptr, *d_fpart = nullptr, *d_grad = nullptr, *d_jac = nullptr, *d_hess = nullptr;
-    unsigned int* d_fcount = nullptr;
-    std::vector<double> s, wl, wr, params, D0;      // D0: parameter vector (with derived slots) of problem 0
-    int shared_d = 1;                               // every problem of the batch has the parameter vector D0
-    std::vector<int> jac_row, jac_col, hess_row, hess_col;
-    bool values_valid = false, derivs_jac_valid = false;
-    long launches = 0;
-    int n_in = 0, n_ctrl = 0;
-    void* d_flush = nullptr;
-    size_t flush_bytes = 0;
-};
 
 namespace {
 
@@ -138,6 +116,8 @@ void build_structure(fl_nlp* h)
 }
 
 } // namespace
+
+void fl_set_error(const std::string& msg) { g_error = msg; }
 
 extern "C" {
 

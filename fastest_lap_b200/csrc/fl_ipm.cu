@@ -1,0 +1,405 @@
+// Host driver and C-ABI of the device-resident interior-point solver for batches of laps (include/fastestlap_b200.h,
+// section "interior-point solver").  Replaces, for the collocation NLP, what Ipopt + MUMPS do behind
+// lion::ipopt_cppad_solve in the reference (src/core/applications/optimal_laptime.hpp:528-556).  The host sequences
+// phases and reads a few counters per phase; every vector, matrix and per-lap decision lives on the device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fl_internal.h"
+#include "ipm_kernels.cuh"
+
+namespace {
+
+#define FLI_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fl_set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return 0; } } while (0)
+
+template <class T> T* dalloc(size_t count, std::vector<void*>& owned)
+{
+    void* p = nullptr;
+    if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, (count ? count : 1) * sizeof(T));
+    owned.push_back(p);
+    return static_cast<T*>(p);
+}
+
+template <class T> T* dupload(const std::vector<T>& v, std::vector<void*>& owned)
+{
+    T* p = dalloc<T>(v.size(), owned);
+    if (p && !v.empty()) cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return p;
+}
+
+} // namespace
+
+struct fl_ipm
+{
+    fl_nlp* nlp = nullptr;
+    int B = 0, NV = 0, NEQ = 0, NB = 0;
+    fl_ipm_dev I{};
+    fl_kkt_dev K{};
+    std::vector<void*> owned;
+    double *wx = nullptr, *wy = nullptr;          // solution of one solve
+    int* d_neg = nullptr; int* d_zero = nullptr;
+    long launches = 0;
+    long n_factor_launches = 0, n_solve_launches = 0, n_eval_full = 0, n_eval_fg = 0, n_rounds = 0;
+    double ms_factor = 0.0, ms_solve = 0.0, ms_eval = 0.0, ms_total = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+template <int NV, int NEQ> void launch_factor(fl_ipm* s, const fl_kkt_dev& K)
+{
+    k_kkt_factor<NV, NEQ><<<s->B, 32, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K);
+}
+template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, const double* r1, const double* r2, double* dx, double* dy)
+{
+    k_kkt_solve<NV, NEQ><<<s->B, 32, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K, r1, r2, dx, dy);
+}
+
+#define FLI_DISPATCH(fn, ...) \
+    do { \
+        if (s->NV == 15 && s->NEQ == 13) fn<15, 13>(s, __VA_ARGS__); \
+        else if (s->NV == 17 && s->NEQ == 15) fn<17, 15>(s, __VA_ARGS__); \
+        else if (s->NV == 14 && s->NEQ == 12) fn<14, 12>(s, __VA_ARGS__); \
+        else if (s->NV == 16 && s->NEQ == 14) fn<16, 14>(s, __VA_ARGS__); \
+        else { fl_set_error("no KKT kernel for this stage size"); return 0; } \
+    } while (0)
+
+int kkt_factor(fl_ipm* s, const int* active, int ls_mode)
+{
+    fl_kkt_dev K = s->K;
+    K.active = active; K.ls_mode = ls_mode;
+    FLI_DISPATCH(launch_factor, K);
+    s->launches += 1; s->n_factor_launches += 1;
+    FLI_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int kkt_solve(fl_ipm* s, const int* active, int ls_mode, const double* r1, const double* r2, double* dx, double* dy)
+{
+    fl_kkt_dev K = s->K;
+    K.active = active; K.ls_mode = ls_mode;
+    FLI_DISPATCH(launch_solve, K, r1, r2, dx, dy);
+    s->launches += 1; s->n_solve_launches += 1;
+    FLI_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// solve K (tx, ty) = (I.r1, I.r2) with iterative refinement on the full augmented system; result into (ox, oy)
+int solve_refined(fl_ipm* s, const int* active, int ls_mode, double* ox, double* oy)
+{
+    const fl_ipm_dev& I = s->I;
+    cudaStream_t st = s->nlp->stream;
+    if (!kkt_solve(s, active, ls_mode, I.r1, I.r2, s->wx, s->wy)) return 0;
+    k_ipm_axpy_sol<<<s->B, IPM_BLOCK, 0, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 1);
+    for (int k = 0; k < I.o.refine_steps; ++k)
+    {
+        k_ipm_residual<<<s->B, IPM_BLOCK, 0, st>>>(I, active, ls_mode);
+        if (!kkt_solve(s, active, ls_mode, I.e1, I.e2, s->wx, s->wy)) return 0;
+        k_ipm_axpy_sol<<<s->B, IPM_BLOCK, 0, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 0);
+        s->launches += 2;
+    }
+    k_ipm_axpy_sol<<<s->B, IPM_BLOCK, 0, st>>>(I, active, I.tx, I.ty, ox, oy, 1);
+    s->launches += 2;
+    FLI_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int read_counters(fl_ipm* s, int* host4)
+{
+    FLI_CUDA(cudaMemcpyAsync(host4, s->I.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->nlp->stream));
+    FLI_CUDA(cudaStreamSynchronize(s->nlp->stream));
+    return 1;
+}
+
+int zero_counters(fl_ipm* s)
+{
+    FLI_CUDA(cudaMemsetAsync(s->I.counters, 0, 8 * sizeof(int), s->nlp->stream));
+    return 1;
+}
+
+} // namespace
+
+extern "C" {
+
+void fl_ipm_default_options(fl_ipm_opts* o)
+{
+    // Ipopt defaults, with the tolerances the reference sets (optimal_laptime.hpp:528-541)
+    o->tol = 1.0e-10; o->constr_viol_tol = 1.0e-10; o->acceptable_tol = 1.0e-8; o->acceptable_iter = 15; o->max_iter = 3000;
+    o->mu_init = 0.1; o->bound_push = 1.0e-2; o->bound_frac = 1.0e-2; o->bound_relax_factor = 1.0e-8;
+    o->kappa_eps = 10.0; o->kappa_mu = 0.2; o->theta_mu = 1.5; o->tau_min = 0.99; o->kappa_sigma = 1.0e10; o->s_max = 100.0;
+    o->gamma_theta = 1.0e-5; o->gamma_phi = 1.0e-8; o->delta = 1.0; o->s_theta = 1.1; o->s_phi = 2.3; o->eta_phi = 1.0e-8;
+    o->kappa_soc = 0.99; o->alpha_red = 0.5; o->max_soc = 4; o->max_backtracks = 40;
+    o->delta_w_min = 1.0e-20; o->delta_w_0 = 1.0e-4; o->delta_w_max = 1.0e40; o->kappa_w_minus = 1.0 / 3.0; o->kappa_w_plus = 8.0;
+    o->kappa_w_plus_bar = 100.0; o->delta_c_bar = 1.0e-8; o->kappa_c = 0.25; o->y_init_max = 1.0e3; o->refine_steps = 2;
+}
+
+void fl_ipm_destroy(fl_ipm* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->nlp->device);
+    cudaStreamSynchronize(s->nlp->stream);
+    for (void* p : s->owned) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, const double* x_u, const double* g_l, const double* g_u)
+{
+    if (!nlp) { fl_set_error("null nlp"); return nullptr; }
+    if (cudaSetDevice(nlp->device) != cudaSuccess) { fl_set_error("cudaSetDevice failed"); return nullptr; }
+    static_assert(sizeof(fl_ipm_opts) == sizeof(fl_ipm_options), "public and device option structs must match");
+    const fl_variant* v = nlp->v;
+    const fl_dev& P = nlp->P;
+    if (v->NV > IPM_NVMAX || v->NCPE > IPM_NCPEMAX) { fl_set_error("variant too large for the interior-point kernels"); return nullptr; }
+    fl_ipm* s = new fl_ipm;
+    s->nlp = nlp;
+    s->B = P.batch;
+    fl_ipm_opts o;
+    if (opts) o = *opts; else fl_ipm_default_options(&o);
+    const int NV = v->NV, NCPE = v->NCPE, NINEQ = v->NEXT, NEQ = NCPE - NINEQ;
+    s->NV = NV; s->NEQ = NEQ; s->NB = NV + NEQ;
+    const int n = P.n, m = P.m, S = P.n_var_nodes, n_el = P.n_elements, ni = n_el * NINEQ, B = P.batch;
+    // bounds: the caller's, or the model defaults; relaxed by bound_relax_factor as Ipopt does
+    std::vector<double> xl(n), xu(n), gl(m), gu(m);
+    if (x_l && x_u && g_l && g_u) { xl.assign(x_l, x_l + n); xu.assign(x_u, x_u + n); gl.assign(g_l, g_l + m); gu.assign(g_u, g_u + m); }
+    else if (!fl_nlp_bounds(nlp, xl.data(), xu.data(), gl.data(), gu.data())) { delete s; return nullptr; }
+    auto rel = [&](double b) { return o.bound_relax_factor * std::fmax(1.0, std::fabs(b)); };
+    // row classification: the NEXT "extra" rows of every element are the inequalities (optimal_laptime.hpp:447-476)
+    std::vector<int> eq_of(NCPE, -1), ineq_of(NCPE, -1), eq_rows, ineq_rows;
+    for (int r = 0; r < NCPE; ++r)
+    {
+        const bool ineq = r >= v->NTD + v->NALG && r < v->NTD + v->NALG + v->NEXT;
+        if (ineq) { ineq_of[r] = (int)ineq_rows.size(); ineq_rows.push_back(r); }
+        else { eq_of[r] = (int)eq_rows.size(); eq_rows.push_back(r); }
+    }
+    for (int i = 0; i < m; ++i)
+    {
+        const bool ineq = ineq_of[i % NCPE] >= 0;
+        if (ineq != (gu[i] > gl[i])) { fl_set_error("constraint bounds do not match the row classification of the variant"); delete s; return nullptr; }
+    }
+    std::vector<double> sl(ni), su(ni);
+    for (int e = 0; e < n_el; ++e)
+        for (int t = 0; t < NINEQ; ++t)
+        {
+            const int row = e * NCPE + ineq_rows[t];
+            sl[e * NINEQ + t] = gl[row] - rel(gl[row]);
+            su[e * NINEQ + t] = gu[row] + rel(gu[row]);
+        }
+    for (int i = 0; i < n; ++i)
+    {
+        if (!(xu[i] > xl[i])) { fl_set_error("every variable needs lower < upper bound"); delete s; return nullptr; }
+        xl[i] -= rel(xl[i]); xu[i] += rel(xu[i]);
+    }
+    auto& own = s->owned;
+    fl_ipm_dev& I = s->I;
+    I.n = n; I.m = m; I.ni = ni; I.S = S; I.NV = NV; I.NCPE = NCPE; I.NINEQ = NINEQ; I.NEQ = NEQ; I.n_el = n_el; I.node0 = P.node0; I.n_points = P.n_points;
+    I.NJA = v->NJA; I.NJB = v->NJB; I.NH = v->NH; I.NCPL = v->NCPL; I.nB = P.nB; I.nC = P.nC; I.closed = P.closed;
+    I.nnz_jac = P.nnz_jac; I.nnz_hess = P.nnz_hess;
+    auto ivec = [&](const int* p, int cnt) { return dupload(std::vector<int>(p, p + cnt), own); };
+    I.t.ja_row = ivec(v->JA_ROW, v->NJA); I.t.ja_col = ivec(v->JA_COL, v->NJA);
+    I.t.jb_row = ivec(v->JB_ROW, v->NJB); I.t.jb_col = ivec(v->JB_COL, v->NJB);
+    I.t.h_row = ivec(v->H_ROW, v->NH); I.t.h_col = ivec(v->H_COL, v->NH);
+    I.t.ctrl_pos = ivec(v->CTRL_POS, 2);
+    I.t.eq_of_row = dupload(eq_of, own); I.t.ineq_of_row = dupload(ineq_of, own);
+    I.t.eq_rows = dupload(eq_rows, own); I.t.ineq_rows = dupload(ineq_rows, own);
+    std::memcpy(&I.o, &o, sizeof(o));
+    I.nx = nlp->d_xuser; I.nlam = nlp->d_lambda; I.nf = nlp->d_f; I.ng = nlp->d_g; I.ngrad = nlp->d_grad; I.njac = nlp->d_jac; I.nhess = nlp->d_hess;
+    I.xl = dupload(xl, own); I.xu = dupload(xu, own); I.gl = dupload(gl, own); I.sl = dupload(sl, own); I.su = dupload(su, own);
+    const size_t Bn = (size_t)B * n, Bm = (size_t)B * m, Bi = (size_t)B * ni;
+    I.x = dalloc<double>(Bn, own); I.s = dalloc<double>(Bi, own); I.y = dalloc<double>(Bm, own);
+    I.zl = dalloc<double>(Bn, own); I.zu = dalloc<double>(Bn, own); I.vl = dalloc<double>(Bi, own); I.vu = dalloc<double>(Bi, own);
+    I.dx = dalloc<double>(Bn, own); I.ds = dalloc<double>(Bi, own); I.dy = dalloc<double>(Bm, own);
+    I.dxs = dalloc<double>(Bn, own); I.dss = dalloc<double>(Bi, own); I.dys = dalloc<double>(Bm, own); I.st = dalloc<double>(Bi, own);
+    I.sigx = dalloc<double>(Bn, own); I.sigs = dalloc<double>(Bi, own); I.r1 = dalloc<double>(Bn, own); I.r2 = dalloc<double>(Bm, own);
+    I.c = dalloc<double>(Bm, own); I.csoc = dalloc<double>(Bm, own); I.rsbar = dalloc<double>(Bi, own); I.gx = dalloc<double>(Bn, own);
+    I.e1 = dalloc<double>(Bn, own); I.e2 = dalloc<double>(Bm, own); I.tx = dalloc<double>(Bn, own); I.ty = dalloc<double>(Bm, own);
+    s->wx = dalloc<double>(Bn, own); s->wy = dalloc<double>(Bm, own);
+    I.dw = dalloc<double>(B, own); I.dc = dalloc<double>(B, own);
+    I.act_factor = dalloc<int>(B, own); I.act_soc = dalloc<int>(B, own); I.act_run = dalloc<int>(B, own);
+    I.counters = dalloc<int>(8, own);
+    s->d_neg = dalloc<int>(B, own); s->d_zero = dalloc<int>(B, own);
+    I.n_neg = s->d_neg; I.n_zero = s->d_zero;
+    I.lap = dalloc<fl_ipm_lap>(B, own);
+    fl_kkt_dev& K = s->K;
+    K.S = S; K.n_el = n_el; K.node0 = P.node0; K.closed = P.closed; K.nB = P.nB; K.nC = P.nC; K.n_points = P.n_points;
+    K.NJA = v->NJA; K.NJB = v->NJB; K.NH = v->NH; K.NCPL = v->NCPL; K.NCPE = NCPE; K.NINEQ = NINEQ; K.n = n; K.m = m;
+    K.nnz_jac = P.nnz_jac; K.nnz_hess = P.nnz_hess; K.t = I.t;
+    K.jac = nlp->d_jac; K.hess = nlp->d_hess; K.sigx = I.sigx; K.sigs = I.sigs; K.dw = I.dw; K.dc = I.dc; K.active = nullptr;
+    const size_t NB2 = (size_t)s->NB * s->NB;
+    K.Dinv = dalloc<double>((size_t)B * S * NB2, own);
+    K.F = (P.closed && S > 2) ? dalloc<double>((size_t)B * S * NB2, own) : nullptr;
+    K.Aq = dalloc<double>((size_t)B * S * NINEQ * (NV + 1), own);
+    K.ywork = dalloc<double>((size_t)B * S * s->NB, own);
+    K.n_neg = s->d_neg; K.n_zero = s->d_zero; K.ls_mode = 0;
+    if (!I.lap || !K.Dinv || !K.ywork || !s->wy || (P.closed && S > 2 && !K.F))
+    {
+        fl_set_error("out of device memory for the interior-point workspace");
+        fl_ipm_destroy(s);
+        return nullptr;
+    }
+    cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+    if (P.closed && S <= 2) { fl_set_error("closed laps need at least three nodes"); fl_ipm_destroy(s); return nullptr; }
+    return s;
+}
+
+// Test / building-block entry: one factorisation and solve of the augmented system at the callbacks' current output.
+// Host arrays: sigx [batch][n], sigs [batch][n_el*NINEQ] (element-major), dw, dc [batch], r1 [batch][n], r2 [batch][m].
+int fl_kkt_factor_solve(fl_ipm* s, const double* x, const double* lambda, const double* sigx, const double* sigs, const double* dw, const double* dc,
+                        const double* r1, const double* r2, int refine_steps, int ls_mode, double* dx, double* dy, int* n_neg, int* n_zero)
+{
+    fl_nlp* nlp = s->nlp;
+    FLI_CUDA(cudaSetDevice(nlp->device));
+    const fl_ipm_dev& I = s->I;
+    const size_t B = s->B;
+    cudaStream_t st = nlp->stream;
+    FLI_CUDA(cudaMemcpyAsync(nlp->d_xuser, x, B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
+    FLI_CUDA(cudaMemcpyAsync(nlp->d_lambda, lambda, B * I.m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!fl_eval_device(nlp, FL_EVAL_FG | FL_EVAL_JAC | FL_EVAL_HESS, 1.0)) return 0;
+    FLI_CUDA(cudaMemcpyAsync(I.sigx, sigx, B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
+    FLI_CUDA(cudaMemcpyAsync(I.sigs, sigs, B * I.ni * sizeof(double), cudaMemcpyHostToDevice, st));
+    FLI_CUDA(cudaMemcpyAsync(I.dw, dw, B * sizeof(double), cudaMemcpyHostToDevice, st));
+    FLI_CUDA(cudaMemcpyAsync(I.dc, dc, B * sizeof(double), cudaMemcpyHostToDevice, st));
+    FLI_CUDA(cudaMemcpyAsync(I.r1, r1, B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
+    FLI_CUDA(cudaMemcpyAsync(I.r2, r2, B * I.m * sizeof(double), cudaMemcpyHostToDevice, st));
+    // the refinement kernel reads dw, dc from the lap records
+    std::vector<fl_ipm_lap> laps(B);
+    for (size_t b = 0; b < B; ++b) { std::memset(&laps[b], 0, sizeof(fl_ipm_lap)); laps[b].dw = dw[b]; laps[b].dc = dc[b]; }
+    FLI_CUDA(cudaMemcpyAsync(I.lap, laps.data(), B * sizeof(fl_ipm_lap), cudaMemcpyHostToDevice, st));
+    if (!kkt_factor(s, nullptr, ls_mode)) return 0;
+    fl_ipm_options keep = s->I.o;
+    s->I.o.refine_steps = refine_steps;
+    const int ok = solve_refined(s, nullptr, ls_mode, I.dx, I.dy);
+    s->I.o = keep;
+    if (!ok) return 0;
+    FLI_CUDA(cudaMemcpyAsync(dx, I.dx, B * I.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FLI_CUDA(cudaMemcpyAsync(dy, I.dy, B * I.m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (n_neg) FLI_CUDA(cudaMemcpyAsync(n_neg, s->d_neg, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n_zero) FLI_CUDA(cudaMemcpyAsync(n_zero, s->d_zero, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FLI_CUDA(cudaStreamSynchronize(st));
+    return 1;
+}
+
+int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
+{
+    fl_nlp* nlp = s->nlp;
+    FLI_CUDA(cudaSetDevice(nlp->device));
+    const fl_ipm_dev& I = s->I;
+    const int B = s->B;
+    cudaStream_t st = nlp->stream;
+    const int ALL = FL_EVAL_FG | FL_EVAL_JAC | FL_EVAL_HESS;
+    int cnt[4];
+    cudaEventRecord(s->ev0, st);
+    FLI_CUDA(cudaMemcpyAsync(nlp->d_xuser, x0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_ipm_init<<<B, IPM_BLOCK, 0, st>>>(I);
+    if (!fl_eval_device(nlp, ALL, 1.0)) return 0;
+    k_ipm_init_slacks<<<B, IPM_BLOCK, 0, st>>>(I);
+    s->launches += 2; s->n_eval_full += 1;
+    // least-squares multipliers (Ipopt's default start): [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
+    if (!kkt_factor(s, nullptr, 1)) return 0;
+    if (!solve_refined(s, nullptr, 1, I.dx, I.dy)) return 0;
+    k_ipm_take_multipliers<<<B, IPM_BLOCK, 0, st>>>(I);
+    s->launches += 1;
+    const int blocks_b = (B + 127) / 128;
+    for (long round = 0;; ++round)
+    {
+        s->n_rounds = round;
+        // callbacks at (x, y), state of the iterate
+        if (!fl_eval_device(nlp, ALL, 1.0)) return 0;
+        s->n_eval_full += 1;
+        if (!zero_counters(s)) return 0;
+        k_ipm_state<<<B, IPM_BLOCK, 0, st>>>(I);
+        k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B);
+        s->launches += 2;
+        if (!read_counters(s, cnt)) return 0;
+        if (verbose)
+        {
+            fl_ipm_lap l0;
+            cudaMemcpy(&l0, I.lap, sizeof(fl_ipm_lap), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "%4ld  running %d  lap0: it %d f %.10f inf_pr %.2e inf_du %.2e mu %.1e dw %.1e alpha %.2e status %d\n", round, cnt[0], l0.iter, l0.f,
+                         l0.cviol, l0.dual_inf, l0.mu, l0.dw_last, l0.alpha, l0.status);
+        }
+        if (cnt[0] == 0) break;
+        // factorisation with inertia correction
+        for (int attempt = 0; attempt < 200; ++attempt)
+        {
+            if (!kkt_factor(s, I.act_factor, 0)) return 0;
+            if (!zero_counters(s)) return 0;
+            k_ipm_inertia<<<blocks_b, 128, 0, st>>>(I, B);
+            s->launches += 1;
+            if (!read_counters(s, cnt)) return 0;
+            if (cnt[1] == 0) break;
+        }
+        // search direction
+        k_ipm_rhs<<<B, IPM_BLOCK, 0, st>>>(I, 0);
+        s->launches += 1;
+        if (!solve_refined(s, I.act_run, 0, I.dx, I.dy)) return 0;
+        if (!zero_counters(s)) return 0;
+        k_ipm_direction<<<B, IPM_BLOCK, 0, st>>>(I);
+        s->launches += 1;
+        if (!read_counters(s, cnt)) return 0;
+        // filter line search, all laps in lock step
+        int guard = 0;
+        while (cnt[2] > 0 && guard++ < 400)
+        {
+            if (cnt[3] > 0)
+            {
+                k_ipm_rhs<<<B, IPM_BLOCK, 0, st>>>(I, 1);
+                if (!solve_refined(s, I.act_soc, 0, I.dxs, I.dys)) return 0;
+                k_ipm_soc_direction<<<B, IPM_BLOCK, 0, st>>>(I);
+                s->launches += 2;
+            }
+            if (!fl_eval_device(nlp, FL_EVAL_FG, 1.0)) return 0;
+            s->n_eval_fg += 1;
+            if (!zero_counters(s)) return 0;
+            k_ipm_line_search<<<B, IPM_BLOCK, 0, st>>>(I);
+            s->launches += 1;
+            if (!read_counters(s, cnt)) return 0;
+        }
+    }
+    cudaEventRecord(s->ev1, st);
+    FLI_CUDA(cudaEventSynchronize(s->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    s->ms_total = ms;
+    FLI_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int fl_ipm_results(fl_ipm* s, double* x, double* y, double* zl, double* zu, double* obj, int* status, int* iters, double* errors)
+{
+    fl_nlp* nlp = s->nlp;
+    FLI_CUDA(cudaSetDevice(nlp->device));
+    const fl_ipm_dev& I = s->I;
+    const size_t B = s->B;
+    if (x) FLI_CUDA(cudaMemcpy(x, I.x, B * I.n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (y) FLI_CUDA(cudaMemcpy(y, I.y, B * I.m * sizeof(double), cudaMemcpyDeviceToHost));
+    if (zl) FLI_CUDA(cudaMemcpy(zl, I.zl, B * I.n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (zu) FLI_CUDA(cudaMemcpy(zu, I.zu, B * I.n * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<fl_ipm_lap> laps(B);
+    FLI_CUDA(cudaMemcpy(laps.data(), I.lap, B * sizeof(fl_ipm_lap), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b)
+    {
+        if (obj) obj[b] = laps[b].f;
+        if (status) status[b] = laps[b].status;
+        if (iters) iters[b] = laps[b].iter;
+        if (errors) { errors[4 * b] = laps[b].err0; errors[4 * b + 1] = laps[b].cviol; errors[4 * b + 2] = laps[b].dual_inf; errors[4 * b + 3] = laps[b].mu; }
+    }
+    return 1;
+}
+
+// counters of the last solve: [0] kernel launches of the solver (callbacks excluded), [1] factorisation launches, [2] solve launches,
+// [3] full callback rounds, [4] f/g-only callback rounds, [5] outer rounds; ms = device time of the whole solve
+void fl_ipm_stats(const fl_ipm* s, long stats[6], double* ms)
+{
+    stats[0] = s->launches; stats[1] = s->n_factor_launches; stats[2] = s->n_solve_launches; stats[3] = s->n_eval_full; stats[4] = s->n_eval_fg;
+    stats[5] = s->n_rounds;
+    if (ms) *ms = s->ms_total;
+}
+
+} // extern "C"

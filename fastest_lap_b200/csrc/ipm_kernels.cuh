@@ -1,0 +1,657 @@
+// Interior-point iteration for batches of independent collocation NLPs, device resident, sm_100a fp64.
+//
+// The reference hands its NLP to Ipopt (lion::ipopt_cppad_solve, src/core/applications/optimal_laptime.hpp:546-551, with
+// the options of :528-541: tol 1e-10, constr_viol_tol 1e-10, acceptable_tol 1e-8, max_iter 3000, Ipopt defaults
+// otherwise).  Ipopt is a third-party dependency outside the reference tree; these kernels implement its published
+// algorithm (Waechter & Biegler, Math. Program. 106 (2006); equation numbers below are the paper's): slack
+// reformulation of the inequality rows, monotone barrier update (7), fraction to the boundary (15), filter line search
+// (18)-(20) with second-order correction, multiplier reset (16), inertia-correcting regularisation (Algorithm IC) on the
+// exact inertia reported by the block factorisation of kkt_kernels.cuh.  oracle/ipm.py is the numpy statement of the
+// same iteration.  Deviations from Ipopt: no NLP scaling, no restoration phase (a lap whose line search fails stops with
+// that status), Jacobian regularisation dc always on (closed laps with an even node count have dependent rows).
+//
+// One block per lap; every reduction is a fixed-order tree (results do not depend on scheduling).  The host only
+// sequences phases and reads a few counters per phase: all laps advance in lock step, each with its own state.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cmath>
+#include "kkt_kernels.cuh"
+
+constexpr int IPM_BLOCK = 128;
+constexpr int IPM_NVMAX = 17, IPM_NCPEMAX = 21, IPM_FILTER_MAX = 256;
+
+enum { IPM_RUNNING = 0, IPM_SUCCESS = 1, IPM_ACCEPTABLE = 2, IPM_MAX_ITER = -1, IPM_LINE_SEARCH_FAILED = -2, IPM_REGULARISATION_FAILED = -3,
+       IPM_NOT_FINITE = -4 };
+enum { LS_IDLE = 0, LS_TRIAL = 1, LS_SOC_SOLVE = 2, LS_SOC_TRIAL = 3, LS_DONE = 4 };
+
+struct fl_ipm_options
+{
+    double tol, constr_viol_tol, acceptable_tol;
+    int acceptable_iter, max_iter;
+    double mu_init, bound_push, bound_frac, bound_relax_factor, kappa_eps, kappa_mu, theta_mu, tau_min, kappa_sigma, s_max;
+    double gamma_theta, gamma_phi, delta, s_theta, s_phi, eta_phi, kappa_soc, alpha_red;
+    int max_soc, max_backtracks;
+    double delta_w_min, delta_w_0, delta_w_max, kappa_w_minus, kappa_w_plus, kappa_w_plus_bar, delta_c_bar, kappa_c, y_init_max;
+    int refine_steps;
+};
+
+struct fl_ipm_lap
+{
+    double mu, tau, theta, phi, dphi, alpha, alpha_max, alpha_dual, dw, dw_last, dc, theta_max, theta_min;
+    double f, cviol, dual_inf, compl_inf, err0, theta_soc_old, alpha_soc;
+    int status, ls, iter, acc_count, n_filter, n_backtrack, n_soc, n_reg, n_fact, switching, soc_step;
+    double filter[2 * IPM_FILTER_MAX];
+};
+
+struct fl_ipm_dev
+{
+    int n, m, ni, S, NV, NCPE, NINEQ, NEQ, n_el, node0, n_points, NJA, NJB, NH, NCPL, nB, nC, closed;
+    long nnz_jac, nnz_hess;
+    fl_kkt_tables t;
+    fl_ipm_options o;
+    // the NLP's buffers (fl_nlp): inputs x, lambda; outputs f, g, grad, jac, hess
+    double* nx; double* nlam; const double* nf; const double* ng; const double* ngrad; const double* njac; const double* nhess;
+    // bounds (relaxed), shared by the batch
+    const double *xl, *xu, *gl, *sl, *su;          // [n], [n], [m], [ni], [ni]
+    // iterate and work vectors, [batch][...]
+    double *x, *s, *y, *zl, *zu, *vl, *vu;
+    double *dx, *ds, *dy, *dxs, *dss, *dys, *st;   // step, second-order-corrected step, trial slacks
+    double *sigx, *sigs, *r1, *r2, *c, *csoc, *rsbar, *gx, *e1, *e2, *tx, *ty;
+    double *dw, *dc;                               // [batch] mirrors of lap.dw / lap.dc for the factorisation
+    int *act_factor, *act_soc, *act_run;           // [batch] masks
+    int* counters;                                 // [8]: 0 running laps, 1 pending factorisations, 2 laps in line search, 3 pending SOC solves
+    const int* n_neg; const int* n_zero;
+    fl_ipm_lap* lap;
+};
+
+// ---- block reductions (fixed order) -----------------------------------------------------------------------------------
+__device__ __forceinline__ double ipm_block_sum(double v, double* red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < IPM_BLOCK / 32; ++w) r += red[w];
+    return r;
+}
+__device__ __forceinline__ double ipm_block_max(double v, double* red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+    for (int w = 1; w < IPM_BLOCK / 32; ++w) r = fmax(r, red[w]);
+    return r;
+}
+__device__ __forceinline__ double ipm_block_min(double v, double* red) { return -ipm_block_max(-v, red); }
+
+__device__ __forceinline__ int ipm_row_of_ineq(const fl_ipm_dev& I, int k) { return (k / I.NINEQ) * I.NCPE + I.t.ineq_rows[k % I.NINEQ]; }
+
+// ---- sparse products with the slot-major Jacobian / Hessian of one lap ------------------------------------------------
+// out[n] (+)= J^T w : thread per variable node, accumulators in shared memory (acc[NVMAX][IPM_BLOCK])
+__device__ void ipm_JT_mul(const fl_ipm_dev& I, const double* jac, const double* w, double* out, bool accumulate, double* acc)
+{
+    const int NV = I.NV;
+    for (int base = 0; base < I.S; base += IPM_BLOCK)
+    {
+        const int j = base + threadIdx.x;
+        if (j < I.S)
+        {
+            for (int c = 0; c < NV; ++c) acc[c * IPM_BLOCK + threadIdx.x] = accumulate ? out[(size_t)j * NV + c] : 0.0;
+            const int node = j + I.node0;
+            const int e_in = node == 0 ? I.n_points - 1 : node - 1;
+            for (int k = 0; k < I.NJA; ++k)
+                acc[I.t.ja_col[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)k * I.n_el + e_in] * w[(size_t)e_in * I.NCPE + I.t.ja_row[k]];
+            const bool has_out = I.closed || node + 1 < I.n_points;
+            if (has_out)
+            {
+                const int e_out = node, eb = e_out - I.node0;
+                for (int k = 0; k < I.NJB; ++k)
+                    acc[I.t.jb_col[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * w[(size_t)e_out * I.NCPE + I.t.jb_row[k]];
+            }
+            for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * IPM_BLOCK + threadIdx.x];
+        }
+    }
+}
+
+// out[m] = J v : thread per element
+__device__ void ipm_J_mul(const fl_ipm_dev& I, const double* jac, const double* v, double* out, double* acc)
+{
+    const int NV = I.NV, NCPE = I.NCPE;
+    for (int base = 0; base < I.n_el; base += IPM_BLOCK)
+    {
+        const int e = base + threadIdx.x;
+        if (e < I.n_el)
+        {
+            for (int r = 0; r < NCPE; ++r) acc[r * IPM_BLOCK + threadIdx.x] = 0.0;
+            const int nj = (e + 1 == I.n_points) ? 0 : e + 1;          // right node
+            const int sj = nj - I.node0;
+            for (int k = 0; k < I.NJA; ++k)
+                acc[I.t.ja_row[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)k * I.n_el + e] * v[(size_t)sj * NV + I.t.ja_col[k]];
+            const int eb = e - I.node0;
+            if (eb >= 0)
+                for (int k = 0; k < I.NJB; ++k)
+                    acc[I.t.jb_row[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * v[(size_t)eb * NV + I.t.jb_col[k]];
+            for (int r = 0; r < NCPE; ++r) out[(size_t)e * NCPE + r] = acc[r * IPM_BLOCK + threadIdx.x];
+        }
+    }
+}
+
+// out[n] += H v (symmetric, lower-triangle slots + control couplings); out must be initialised
+__device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const double* v, double* out, double* acc)
+{
+    const int NV = I.NV;
+    for (int base = 0; base < I.S; base += IPM_BLOCK)
+    {
+        const int j = base + threadIdx.x;
+        if (j < I.S)
+        {
+            for (int c = 0; c < NV; ++c) acc[c * IPM_BLOCK + threadIdx.x] = out[(size_t)j * NV + c];
+            for (int k = 0; k < I.NH; ++k)
+            {
+                const int r = I.t.h_row[k], c = I.t.h_col[k];
+                const double h = hes[(size_t)k * I.S + j];
+                acc[r * IPM_BLOCK + threadIdx.x] += h * v[(size_t)j * NV + c];
+                if (r != c) acc[c * IPM_BLOCK + threadIdx.x] += h * v[(size_t)j * NV + r];
+            }
+            // couplings with the previous node (element e_in) and with the next node (element e_out)
+            const int node = j + I.node0;
+            const int e_in = node == 0 ? I.n_points - 1 : node - 1;
+            const int eb_in = e_in - I.node0;
+            if (eb_in >= 0 && (I.closed || node > 0))
+            {
+                const int jp = (j == 0) ? I.S - 1 : j - 1;
+                for (int q = 0; q < I.NCPL; ++q)
+                {
+                    const int cp = I.t.ctrl_pos[q];
+                    acc[cp * IPM_BLOCK + threadIdx.x] += hes[(size_t)I.NH * I.S + (size_t)q * I.nC + eb_in] * v[(size_t)jp * NV + cp];
+                }
+            }
+            const bool has_out = I.closed || node + 1 < I.n_points;
+            if (has_out)
+            {
+                const int eb_out = node - I.node0;
+                const int jn = (j + 1 == I.S) ? 0 : j + 1;
+                for (int q = 0; q < I.NCPL; ++q)
+                {
+                    const int cp = I.t.ctrl_pos[q];
+                    acc[cp * IPM_BLOCK + threadIdx.x] += hes[(size_t)I.NH * I.S + (size_t)q * I.nC + eb_out] * v[(size_t)jn * NV + cp];
+                }
+            }
+            for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * IPM_BLOCK + threadIdx.x];
+        }
+    }
+}
+
+#define IPM_LAP_PROLOGUE \
+    const int lap = blockIdx.x; \
+    fl_ipm_lap& L = I.lap[lap]; \
+    const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni; \
+    __shared__ double red[IPM_BLOCK / 32]; \
+    (void)on; (void)om; (void)oi; (void)red;
+
+__device__ __forceinline__ double ipm_push(double v, double lo, double hi, const fl_ipm_options& o)
+{
+    const double pl = fmin(o.bound_push * fmax(1.0, fabs(lo)), o.bound_frac * (hi - lo));
+    const double pu = fmin(o.bound_push * fmax(1.0, fabs(hi)), o.bound_frac * (hi - lo));
+    return fmin(fmax(v, lo + pl), hi - pu);
+}
+
+// ---- start ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_init(const fl_ipm_dev I)
+{
+    IPM_LAP_PROLOGUE
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    {
+        const double v = ipm_push(I.nx[on + i], I.xl[i], I.xu[i], I.o);
+        I.x[on + i] = v; I.nx[on + i] = v;
+        I.zl[on + i] = 1.0; I.zu[on + i] = 1.0;
+    }
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
+    if (threadIdx.x == 0)
+    {
+        L.mu = I.o.mu_init; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
+        L.theta_max = -1.0; L.theta_min = -1.0; L.status = IPM_RUNNING; L.ls = LS_IDLE; L.iter = 0; L.acc_count = 0; L.n_filter = 0;
+        L.n_backtrack = 0; L.n_soc = 0; L.n_reg = 0; L.n_fact = 0; L.switching = 0; L.soc_step = 0;
+        I.dw[lap] = 0.0; I.dc[lap] = L.dc; I.act_run[lap] = 1; I.act_factor[lap] = 1; I.act_soc[lap] = 0;
+    }
+}
+
+// after the first evaluation: slacks pushed inside their bounds, multipliers 1; right-hand side of the least-squares
+// multiplier system  [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_init_slacks(const fl_ipm_dev I)
+{
+    IPM_LAP_PROLOGUE
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    {
+        I.s[oi + k] = ipm_push(I.ng[om + ipm_row_of_ineq(I, k)], I.sl[k], I.su[k], I.o);
+        I.vl[oi + k] = 1.0; I.vu[oi + k] = 1.0;
+    }
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.r1[on + i] = -(I.ngrad[on + i] - I.zl[on + i] + I.zu[on + i]);
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) I.r2[om + i] = 0.0;
+}
+
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_take_multipliers(const fl_ipm_dev I)
+{
+    IPM_LAP_PROLOGUE
+    double mx = 0.0;
+    bool bad = false;
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { const double v = I.dy[om + i]; if (!isfinite(v)) bad = true; mx = fmax(mx, fabs(v)); }
+    mx = ipm_block_max(bad ? 1.0e300 : mx, red);
+    const bool take = mx <= I.o.y_init_max;
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { const double v = take ? I.dy[om + i] : 0.0; I.y[om + i] = v; I.nlam[om + i] = v; }
+}
+
+// ---- state of the current iterate: optimality error, barrier update, right-hand sides ----------------------------------
+// Needs the callbacks evaluated at (x, y): f, g, grad f, Jacobian.
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
+{
+    IPM_LAP_PROLOGUE
+    __shared__ double acc[IPM_NCPEMAX * IPM_BLOCK];
+    __shared__ double sh_mu;
+    if (L.status != IPM_RUNNING) return;
+    const fl_ipm_options& o = I.o;
+    const double* jac = I.njac + (size_t)lap * I.nnz_jac;
+    // gx = grad f + J^T y
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.gx[on + i] = I.ngrad[on + i];
+    __syncthreads();
+    ipm_JT_mul(I, jac, I.y + om, I.gx + on, true, acc);
+    __syncthreads();
+    // constraint residual c = g - gl (equality rows), g - s (inequality rows)
+    double th = 0.0, cmax = 0.0, ysum = 0.0;
+    bool bad = false;
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    {
+        const int r = i % I.NCPE;
+        const int q = I.t.ineq_of_row[r];
+        const double g = I.ng[om + i];
+        const double c = (q < 0) ? g - I.gl[i] : g - I.s[oi + (size_t)(i / I.NCPE) * I.NINEQ + q];
+        I.c[om + i] = c;
+        th += fabs(c); cmax = fmax(cmax, fabs(c)); ysum += fabs(I.y[om + i]);
+        if (!isfinite(g)) bad = true;
+    }
+    th = ipm_block_sum(th, red); cmax = ipm_block_max(cmax, red); ysum = ipm_block_sum(ysum, red);
+    // dual infeasibility, complementarity products, multiplier sums
+    double dmax = 0.0, zsum = 0.0, pmin = 1.0e300, pmax = -1.0e300;
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    {
+        const double zl = I.zl[on + i], zu = I.zu[on + i], x = I.x[on + i];
+        const double rx = I.gx[on + i] - zl + zu;
+        dmax = fmax(dmax, fabs(rx)); zsum += zl + zu;
+        const double p1 = (x - I.xl[i]) * zl, p2 = (I.xu[i] - x) * zu;
+        pmin = fmin(pmin, fmin(p1, p2)); pmax = fmax(pmax, fmax(p1, p2));
+        if (!isfinite(rx)) bad = true;
+    }
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    {
+        const double vl = I.vl[oi + k], vu = I.vu[oi + k], s = I.s[oi + k];
+        const double rs = -I.y[om + ipm_row_of_ineq(I, k)] - vl + vu;
+        dmax = fmax(dmax, fabs(rs)); zsum += vl + vu;
+        const double p1 = (s - I.sl[k]) * vl, p2 = (I.su[k] - s) * vu;
+        pmin = fmin(pmin, fmin(p1, p2)); pmax = fmax(pmax, fmax(p1, p2));
+    }
+    dmax = ipm_block_max(dmax, red); zsum = ipm_block_sum(zsum, red);
+    pmin = ipm_block_min(pmin, red); pmax = ipm_block_max(pmax, red);
+    const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
+    if (threadIdx.x == 0)
+    {
+        const double nz = 2.0 * I.n + 2.0 * I.ni;
+        const double sd = fmax(o.s_max, (ysum + zsum) / (I.m + nz)) / o.s_max;
+        const double sc = fmax(o.s_max, zsum / nz) / o.s_max;
+        auto err = [&](double mu) { return fmax(fmax(dmax / sd, cmax), fmax(fabs(pmax - mu), fabs(pmin - mu)) / sc); };
+        const double f = I.nf[lap];
+        L.f = f; L.cviol = cmax; L.dual_inf = dmax; L.compl_inf = fmax(fabs(pmax), fabs(pmin)); L.err0 = err(0.0); L.theta = th;
+        if (badf > 0.0 || !isfinite(f)) L.status = IPM_NOT_FINITE;
+        else if (L.err0 <= o.tol && cmax <= o.constr_viol_tol) L.status = IPM_SUCCESS;
+        else
+        {
+            L.acc_count = (L.err0 <= o.acceptable_tol) ? L.acc_count + 1 : 0;
+            if (L.acc_count >= o.acceptable_iter) L.status = IPM_ACCEPTABLE;
+            else if (L.iter >= o.max_iter) L.status = IPM_MAX_ITER;
+        }
+        if (L.status == IPM_RUNNING)
+        {
+            // barrier parameter update (7); several reductions may follow each other; the filter is reset
+            bool changed = false;
+            double mu = L.mu;
+            while (mu > o.tol / 10.0 && err(mu) <= o.kappa_eps * mu) { mu = fmax(o.tol / 10.0, fmin(o.kappa_mu * mu, pow(mu, o.theta_mu))); changed = true; }
+            if (changed) L.n_filter = 0;
+            L.mu = mu; L.tau = fmax(o.tau_min, 1.0 - mu);
+            if (L.theta_max < 0.0) { L.theta_max = 1.0e4 * fmax(1.0, th); L.theta_min = 1.0e-4 * fmax(1.0, th); }
+            L.dw = 0.0; L.dc = o.delta_c_bar * pow(mu, o.kappa_c);
+            I.dw[lap] = 0.0; I.dc[lap] = L.dc; I.act_factor[lap] = 1;
+            L.ls = LS_IDLE;
+        }
+        else { I.act_run[lap] = 0; I.act_factor[lap] = 0; }
+        sh_mu = L.mu;
+    }
+    __syncthreads();
+    if (L.status != IPM_RUNNING) return;
+    const double mu = sh_mu;
+    // Sigma, barrier function, gradient of the barrier Lagrangian
+    double lg = 0.0;
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    {
+        const double x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x;
+        const double zl = I.zl[on + i], zu = I.zu[on + i];
+        I.sigx[on + i] = zl / dl + zu / du;
+        lg += log(dl) + log(du);
+        // r1 = -(grad phi_x + J^T y) = -(gx - mu/dl + mu/du)
+        I.r1[on + i] = -(I.gx[on + i] - mu / dl + mu / du);
+    }
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    {
+        const double s = I.s[oi + k], dl = s - I.sl[k], du = I.su[k] - s;
+        I.sigs[oi + k] = I.vl[oi + k] / dl + I.vu[oi + k] / du;
+        lg += log(dl) + log(du);
+        I.rsbar[oi + k] = -mu / dl + mu / du - I.y[om + ipm_row_of_ineq(I, k)];
+    }
+    lg = ipm_block_sum(lg, red);
+    if (threadIdx.x == 0) L.phi = L.f - mu * lg;
+}
+
+// ---- inertia check and regularisation update (Algorithm IC) -------------------------------------------------------------
+__global__ void k_ipm_inertia(const fl_ipm_dev I, int batch)
+{
+    const int lap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lap >= batch || !I.act_factor[lap]) return;
+    fl_ipm_lap& L = I.lap[lap];
+    const fl_ipm_options& o = I.o;
+    L.n_fact += 1;
+    const int want_neg = I.S * I.NEQ;
+    if (I.n_neg[lap] == want_neg && I.n_zero[lap] == 0)
+    {
+        I.act_factor[lap] = 0;
+        if (L.dw > 0.0) L.dw_last = L.dw;
+        return;
+    }
+    L.n_reg += 1;
+    if (L.dw == 0.0) L.dw = (L.dw_last == 0.0) ? o.delta_w_0 : fmax(o.delta_w_min, o.kappa_w_minus * L.dw_last);
+    else L.dw *= (L.dw_last == 0.0) ? o.kappa_w_plus_bar : o.kappa_w_plus;
+    if (L.dw > o.delta_w_max) { L.status = IPM_REGULARISATION_FAILED; I.act_factor[lap] = 0; I.act_run[lap] = 0; return; }
+    I.dw[lap] = L.dw;
+    atomicAdd(I.counters + 1, 1);
+}
+
+// ---- right-hand side of the augmented system: r2 = -c, inequality rows -= rs_bar / (Sigma_s + dw) ------------------------
+// which = 0: c of the iterate, for every running lap; which = 1: the second-order-correction residual, for laps in LS_SOC_SOLVE
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_rhs(const fl_ipm_dev I, int which)
+{
+    IPM_LAP_PROLOGUE
+    if (L.status != IPM_RUNNING) return;
+    if (which == 1 && L.ls != LS_SOC_SOLVE) return;
+    const double* cv = (which == 0 ? I.c : I.csoc) + om;
+    const double dw = L.dw;
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    {
+        const int q = I.t.ineq_of_row[i % I.NCPE];
+        double v = -cv[i];
+        if (q >= 0)
+        {
+            const size_t k = oi + (size_t)(i / I.NCPE) * I.NINEQ + q;
+            v -= I.rsbar[k] / (I.sigs[k] + dw);
+        }
+        I.r2[om + i] = v;
+    }
+}
+
+// ---- residual of the full augmented system for iterative refinement: e = (r1, r2) - K (tx, ty) -----------------------------
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_residual(const fl_ipm_dev I, const int* active, int ls_mode)
+{
+    IPM_LAP_PROLOGUE
+    __shared__ double acc[IPM_NCPEMAX * IPM_BLOCK];
+    if (active && !active[lap]) return;
+    const double* jac = I.njac + (size_t)lap * I.nnz_jac;
+    const double* hes = I.nhess + (size_t)lap * I.nnz_hess;
+    const double dw = ls_mode ? 0.0 : L.dw, dc = L.dc;
+    double* e1 = I.e1 + on; double* e2 = I.e2 + om;
+    const double* tx = I.tx + on; const double* ty = I.ty + om;
+    // e2 = r2 - (J tx - D ty)
+    ipm_J_mul(I, jac, tx, e2, acc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    {
+        const int q = I.t.ineq_of_row[i % I.NCPE];
+        double D = dc;
+        if (q >= 0)
+        {
+            const size_t k = oi + (size_t)(i / I.NCPE) * I.NINEQ + q;
+            D = ls_mode ? 1.0 : 1.0 / (I.sigs[k] + dw) + dc;
+        }
+        e2[i] = I.r2[om + i] - (e2[i] - D * ty[i]);
+    }
+    // e1 = r1 - (H tx + (sigx + dw) tx + J^T ty)
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) e1[i] = ls_mode ? tx[i] : (I.sigx[on + i] + dw) * tx[i];
+    __syncthreads();
+    if (!ls_mode) ipm_H_mul_add(I, hes, tx, e1, acc);
+    __syncthreads();
+    ipm_JT_mul(I, jac, ty, e1, true, acc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) e1[i] = I.r1[on + i] - e1[i];
+}
+
+// (tx, ty) += (dx, dy) of the refinement solve;  or initialise
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_axpy_sol(const fl_ipm_dev I, const int* active, const double* sx, const double* sy, double* tx, double* ty, int init)
+{
+    IPM_LAP_PROLOGUE
+    if (active && !active[lap]) return;
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) tx[on + i] = (init ? 0.0 : tx[on + i]) + sx[on + i];
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) ty[om + i] = (init ? 0.0 : ty[om + i]) + sy[om + i];
+}
+
+// fraction to the boundary (15): largest alpha in (0, 1] with v + alpha dv >= lo + (1 - tau)(v - lo) and the same at the upper bound
+__device__ __forceinline__ double ipm_ftb(double v, double dv, double lo, double hi, double tau)
+{
+    if (dv < 0.0) return -tau * (v - lo) / dv;
+    if (dv > 0.0) return tau * (hi - v) / dv;
+    return 1.0;
+}
+
+__device__ __forceinline__ void ipm_write_trial(const fl_ipm_dev& I, int lap, const double* dx, const double* ds, double alpha)
+{
+    const size_t on = (size_t)lap * I.n, oi = (size_t)lap * I.ni;
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.nx[on + i] = I.x[on + i] + alpha * dx[on + i];
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK) I.st[oi + k] = I.s[oi + k] + alpha * ds[oi + k];
+}
+
+// ---- search direction: slacks, step lengths, directional derivative, first trial point --------------------------------
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_direction(const fl_ipm_dev I)
+{
+    IPM_LAP_PROLOGUE
+    if (L.status != IPM_RUNNING) return;
+    const double mu = L.mu, tau = L.tau, dw = L.dw;
+    double amax = 1.0, adual = 1.0, dphi = 0.0;
+    bool bad = false;
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    {
+        const double ds = (I.dy[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
+        I.ds[oi + k] = ds;
+        const double s = I.s[oi + k], dl = s - I.sl[k], du = I.su[k] - s, vl = I.vl[oi + k], vu = I.vu[oi + k];
+        amax = fmin(amax, ipm_ftb(s, ds, I.sl[k], I.su[k], tau));
+        const double dvl = mu / dl - vl - vl / dl * ds, dvu = mu / du - vu + vu / du * ds;
+        if (dvl < 0.0) adual = fmin(adual, -tau * vl / dvl);
+        if (dvu < 0.0) adual = fmin(adual, -tau * vu / dvu);
+        dphi += (-mu / dl + mu / du) * ds;
+        if (!isfinite(ds)) bad = true;
+    }
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    {
+        const double dx = I.dx[on + i], x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x, zl = I.zl[on + i], zu = I.zu[on + i];
+        amax = fmin(amax, ipm_ftb(x, dx, I.xl[i], I.xu[i], tau));
+        const double dzl = mu / dl - zl - zl / dl * dx, dzu = mu / du - zu + zu / du * dx;
+        if (dzl < 0.0) adual = fmin(adual, -tau * zl / dzl);
+        if (dzu < 0.0) adual = fmin(adual, -tau * zu / dzu);
+        dphi += (I.ngrad[on + i] - mu / dl + mu / du) * dx;
+        if (!isfinite(dx)) bad = true;
+    }
+    amax = ipm_block_min(amax, red); adual = ipm_block_min(adual, red); dphi = ipm_block_sum(dphi, red);
+    const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
+    if (threadIdx.x == 0)
+    {
+        L.alpha_max = amax; L.alpha = amax; L.alpha_dual = adual; L.dphi = dphi; L.n_backtrack = 0; L.n_soc = 0; L.soc_step = 0;
+        if (badf > 0.0) { L.status = IPM_NOT_FINITE; I.act_run[lap] = 0; L.ls = LS_IDLE; }
+        else { L.ls = LS_TRIAL; atomicAdd(I.counters + 2, 1); }
+    }
+    __syncthreads();
+    if (L.status != IPM_RUNNING) return;
+    ipm_write_trial(I, lap, I.dx, I.ds, amax);
+}
+
+// step length of a second-order-corrected step and its trial point (laps in LS_SOC_SOLVE, after the solve)
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_soc_direction(const fl_ipm_dev I)
+{
+    IPM_LAP_PROLOGUE
+    if (L.status != IPM_RUNNING || L.ls != LS_SOC_SOLVE) return;
+    const double tau = L.tau, dw = L.dw;
+    double amax = 1.0;
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    {
+        const double ds = (I.dys[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
+        I.dss[oi + k] = ds;
+        amax = fmin(amax, ipm_ftb(I.s[oi + k], ds, I.sl[k], I.su[k], tau));
+    }
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) amax = fmin(amax, ipm_ftb(I.x[on + i], I.dxs[on + i], I.xl[i], I.xu[i], tau));
+    amax = ipm_block_min(amax, red);
+    if (threadIdx.x == 0) { L.alpha_soc = amax; L.ls = LS_SOC_TRIAL; }
+    __syncthreads();
+    ipm_write_trial(I, lap, I.dxs, I.dss, amax);
+}
+
+// ---- filter line search: judge the trial point (f, g evaluated at it) --------------------------------------------------
+__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev I)
+{
+    IPM_LAP_PROLOGUE
+    __shared__ int sh_decision;      // 0 backtrack, 1 accept, 2 start / continue SOC, 3 fail
+    __shared__ double sh_alpha;
+    if (L.status != IPM_RUNNING || (L.ls != LS_TRIAL && L.ls != LS_SOC_TRIAL)) return;
+    const fl_ipm_options& o = I.o;
+    const bool soc = L.ls == LS_SOC_TRIAL;
+    const double mu = L.mu;
+    // theta and barrier function at the trial point; c_trial into e2 (scratch)
+    double th = 0.0, lg = 0.0;
+    bool bad = false;
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    {
+        const int q = I.t.ineq_of_row[i % I.NCPE];
+        const double g = I.ng[om + i];
+        const double c = (q < 0) ? g - I.gl[i] : g - I.st[oi + (size_t)(i / I.NCPE) * I.NINEQ + q];
+        I.e2[om + i] = c;
+        th += fabs(c);
+        if (!isfinite(g)) bad = true;
+    }
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) { const double x = I.nx[on + i]; lg += log(x - I.xl[i]) + log(I.xu[i] - x); }
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK) { const double s = I.st[oi + k]; lg += log(s - I.sl[k]) + log(I.su[k] - s); }
+    th = ipm_block_sum(th, red); lg = ipm_block_sum(lg, red);
+    const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
+    if (threadIdx.x == 0)
+    {
+        const double ft = I.nf[lap];
+        const double phi_t = ft - mu * lg;
+        const double theta = L.theta, phi = L.phi, dphi = L.dphi;
+        const double alpha = soc ? L.alpha_soc : L.alpha;
+        bool okf = badf == 0.0 && isfinite(phi_t) && th <= L.theta_max;
+        for (int k = 0; okf && k < L.n_filter; ++k)
+            okf = th < (1.0 - o.gamma_theta) * L.filter[2 * k] || phi_t < L.filter[2 * k + 1] - o.gamma_phi * L.filter[2 * k];
+        // switching condition (19) at the step length of the ordinary step
+        const double a_sw = L.alpha;
+        const bool switching = dphi < 0.0 && a_sw * pow(-dphi, o.s_phi) > o.delta * pow(theta, o.s_theta) && theta <= L.theta_min;
+        const double a_arm = soc ? L.alpha_max : L.alpha;
+        const bool armijo = phi_t <= phi + o.eta_phi * a_arm * dphi;
+        bool accepted = false;
+        if (okf) accepted = switching ? armijo : (th <= (1.0 - o.gamma_theta) * theta || phi_t <= phi - o.gamma_phi * theta);
+        int decision = 0;
+        if (accepted)
+        {
+            decision = 1;
+            if (!switching || !armijo)
+            {
+                if (L.n_filter < IPM_FILTER_MAX) { L.filter[2 * L.n_filter] = theta; L.filter[2 * L.n_filter + 1] = phi; L.n_filter += 1; }
+            }
+            L.switching = switching;
+        }
+        else if (!soc)
+        {
+            if (L.n_backtrack == 0 && th >= theta && o.max_soc > 0) { decision = 2; L.theta_soc_old = th; L.n_soc = 0; }
+        }
+        else
+        {
+            L.n_soc += 1;
+            if (th <= o.kappa_soc * L.theta_soc_old && L.n_soc < o.max_soc) { decision = 2; L.theta_soc_old = th; }
+        }
+        if (decision == 0)
+        {
+            // shorter ordinary step
+            L.alpha = (soc ? L.alpha_max : L.alpha) * o.alpha_red;
+            if (soc) L.alpha = L.alpha_max * o.alpha_red;
+            L.n_backtrack += 1;
+            if (L.alpha < 1.0e-13 || L.n_backtrack >= o.max_backtracks) decision = 3;
+        }
+        sh_decision = decision;
+        sh_alpha = alpha;
+    }
+    __syncthreads();
+    const int decision = sh_decision;
+    if (decision == 1)
+    {
+        // accept: new iterate, multiplier steps, reset (16)
+        const double alpha = sh_alpha, ad = L.alpha_dual, ks = o.kappa_sigma;
+        const double* dxa = soc ? I.dxs : I.dx; const double* dsa = soc ? I.dss : I.ds; const double* dya = soc ? I.dys : I.dy;
+        for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+        {
+            const double x0 = I.x[on + i], dl0 = x0 - I.xl[i], du0 = I.xu[i] - x0, dx = I.dx[on + i];
+            double zl = I.zl[on + i], zu = I.zu[on + i];
+            zl += ad * (mu / dl0 - zl - zl / dl0 * dx);
+            zu += ad * (mu / du0 - zu + zu / du0 * dx);
+            const double x = x0 + alpha * dxa[on + i];
+            const double dl = x - I.xl[i], du = I.xu[i] - x;
+            I.x[on + i] = x; I.nx[on + i] = x;
+            I.zl[on + i] = fmax(fmin(zl, ks * mu / dl), mu / (ks * dl));
+            I.zu[on + i] = fmax(fmin(zu, ks * mu / du), mu / (ks * du));
+        }
+        for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+        {
+            const double s0 = I.s[oi + k], dl0 = s0 - I.sl[k], du0 = I.su[k] - s0, ds = I.ds[oi + k];
+            double vl = I.vl[oi + k], vu = I.vu[oi + k];
+            vl += ad * (mu / dl0 - vl - vl / dl0 * ds);
+            vu += ad * (mu / du0 - vu + vu / du0 * ds);
+            const double s = s0 + alpha * dsa[oi + k];
+            const double dl = s - I.sl[k], du = I.su[k] - s;
+            I.s[oi + k] = s;
+            I.vl[oi + k] = fmax(fmin(vl, ks * mu / dl), mu / (ks * dl));
+            I.vu[oi + k] = fmax(fmin(vu, ks * mu / du), mu / (ks * du));
+        }
+        for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { const double y = I.y[om + i] + alpha * dya[om + i]; I.y[om + i] = y; I.nlam[om + i] = y; }
+        if (threadIdx.x == 0) { L.ls = LS_DONE; L.iter += 1; I.act_soc[lap] = 0; }
+    }
+    else if (decision == 2)
+    {
+        // second-order correction: c_soc = alpha c_prev + c(trial), a solve with that residual follows
+        const double alpha = sh_alpha;
+        const double* prev = soc ? I.csoc : I.c;
+        for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) I.csoc[om + i] = alpha * prev[om + i] + I.e2[om + i];
+        if (threadIdx.x == 0) { L.ls = LS_SOC_SOLVE; I.act_soc[lap] = 1; atomicAdd(I.counters + 2, 1); atomicAdd(I.counters + 3, 1); }
+    }
+    else if (decision == 0)
+    {
+        __syncthreads();
+        ipm_write_trial(I, lap, I.dx, I.ds, L.alpha);
+        if (threadIdx.x == 0) { L.ls = LS_TRIAL; I.act_soc[lap] = 0; atomicAdd(I.counters + 2, 1); }
+    }
+    else
+    {
+        // failure: restore the iterate in the NLP's buffers
+        for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.nx[on + i] = I.x[on + i];
+        if (threadIdx.x == 0) { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; I.act_soc[lap] = 0; }
+    }
+}
+
+__global__ void k_ipm_count_running(const fl_ipm_dev I, int batch)
+{
+    const int lap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lap < batch && I.lap[lap].status == IPM_RUNNING) atomicAdd(I.counters + 0, 1);
+}

@@ -1,0 +1,130 @@
+"""Host front-end of the device-resident interior-point solver (include/fastestlap_b200.h, "interior-point solver").
+
+Mirror of the reference's hand-off `ipopt_cppad_solve(options, x0, xl, xu, gl, gu, fg, result)` and of the fields it reads
+back from `ipopt_cppad_result` (src/core/applications/optimal_laptime.hpp:546-556, 590-647): status, x, zl, zu, lambda,
+objective, iteration count -- for every lap of a batch at once.  No CPU path: everything runs in libfastestlap_b200.so.
+"""
+import ctypes as C
+import numpy as np
+
+from .nlp import CollocationNLP, load_library, _ptr, _dp
+
+STATUS = {0: "running", 1: "success", 2: "acceptable", -1: "max_iter", -2: "line_search_failed", -3: "regularisation_failed", -4: "not_finite"}
+
+
+class IpmOptions(C.Structure):
+    _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double), ("acceptable_tol", C.c_double), ("acceptable_iter", C.c_int), ("max_iter", C.c_int),
+                ("mu_init", C.c_double), ("bound_push", C.c_double), ("bound_frac", C.c_double), ("bound_relax_factor", C.c_double),
+                ("kappa_eps", C.c_double), ("kappa_mu", C.c_double), ("theta_mu", C.c_double), ("tau_min", C.c_double), ("kappa_sigma", C.c_double),
+                ("s_max", C.c_double), ("gamma_theta", C.c_double), ("gamma_phi", C.c_double), ("delta", C.c_double), ("s_theta", C.c_double),
+                ("s_phi", C.c_double), ("eta_phi", C.c_double), ("kappa_soc", C.c_double), ("alpha_red", C.c_double), ("max_soc", C.c_int),
+                ("max_backtracks", C.c_int), ("delta_w_min", C.c_double), ("delta_w_0", C.c_double), ("delta_w_max", C.c_double),
+                ("kappa_w_minus", C.c_double), ("kappa_w_plus", C.c_double), ("kappa_w_plus_bar", C.c_double), ("delta_c_bar", C.c_double),
+                ("kappa_c", C.c_double), ("y_init_max", C.c_double), ("refine_steps", C.c_int)]
+
+
+_ip = C.POINTER(C.c_int)
+
+
+def _bind(lib):
+    if getattr(lib, "_ipm_bound", False):
+        return
+    lib.fl_ipm_default_options.argtypes = [C.POINTER(IpmOptions)]
+    lib.fl_ipm_create.restype = C.c_void_p
+    lib.fl_ipm_create.argtypes = [C.c_void_p, C.POINTER(IpmOptions), _dp, _dp, _dp, _dp]
+    lib.fl_ipm_destroy.argtypes = [C.c_void_p]
+    lib.fl_ipm_solve.argtypes = [C.c_void_p, _dp, C.c_int]
+    lib.fl_ipm_results.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
+    lib.fl_ipm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_long), _dp]
+    lib.fl_kkt_factor_solve.argtypes = [C.c_void_p] + [_dp] * 8 + [C.c_int, C.c_int, _dp, _dp, _ip, _ip]
+    lib._ipm_bound = True
+
+
+def default_options():
+    lib = load_library()
+    _bind(lib)
+    o = IpmOptions()
+    lib.fl_ipm_default_options(C.byref(o))
+    return o
+
+
+class LapSolver:
+    """Interior-point solver bound to one CollocationNLP (one batch of laps on one GPU)."""
+
+    def __init__(self, nlp, options=None, bounds=None):
+        assert isinstance(nlp, CollocationNLP)
+        self.nlp, self._lib = nlp, load_library()
+        _bind(self._lib)
+        self.options = options
+        args = [None] * 4
+        if bounds is not None:
+            self._bounds = [np.ascontiguousarray(b, dtype=np.float64) for b in bounds]
+            args = [_ptr(b) for b in self._bounds]
+        self._h = self._lib.fl_ipm_create(nlp._h, C.byref(options) if options is not None else None, *args)
+        if not self._h:
+            raise RuntimeError("fl_ipm_create: " + self._lib.fl_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fl_ipm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, x0, verbose=False):
+        """x0: [batch][n] (or [n], replicated).  Returns a dict of per-lap results."""
+        nlp, B = self.nlp, self.nlp.batch
+        x0 = np.asarray(x0, dtype=np.float64)
+        if x0.size == nlp.n:
+            x0 = np.tile(x0.reshape(1, -1), (B, 1))
+        x0 = np.ascontiguousarray(x0.reshape(B, nlp.n))
+        if not self._lib.fl_ipm_solve(self._h, _ptr(x0), int(verbose)):
+            raise RuntimeError("fl_ipm_solve: " + self._lib.fl_last_error().decode())
+        x, y = np.empty((B, nlp.n)), np.empty((B, nlp.m))
+        zl, zu = np.empty((B, nlp.n)), np.empty((B, nlp.n))
+        obj, err = np.empty(B), np.empty((B, 4))
+        status, iters = np.empty(B, np.int32), np.empty(B, np.int32)
+        ip = lambda a: a.ctypes.data_as(_ip)
+        if not self._lib.fl_ipm_results(self._h, _ptr(x), _ptr(y), _ptr(zl), _ptr(zu), _ptr(obj), ip(status), ip(iters), _ptr(err)):
+            raise RuntimeError("fl_ipm_results: " + self._lib.fl_last_error().decode())
+        stats = (C.c_long * 6)()
+        ms = C.c_double()
+        self._lib.fl_ipm_stats(self._h, stats, C.byref(ms))
+        return dict(x=x, y=y, zl=zl, zu=zu, obj=obj, status=status, iters=iters, error=err[:, 0], constr_viol=err[:, 1], dual_inf=err[:, 2], mu=err[:, 3],
+                    device_ms=ms.value, stats=dict(zip(("solver_launches", "factor_launches", "solve_launches", "full_rounds", "fg_rounds", "outer_rounds"), list(stats))))
+
+    def kkt_factor_solve(self, x, lam, sigx, sigs, dw, dc, r1, r2, refine_steps=0, ls_mode=False):
+        """One factorisation + solve of the augmented system for every lap (building block / test entry)."""
+        nlp, B = self.nlp, self.nlp.batch
+        f64 = lambda a, shape: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(shape if np.size(a) == np.prod(shape) else (1,) + shape[1:]), shape))
+        x, lam = f64(x, (B, nlp.n)), f64(lam, (B, nlp.m))
+        sigx, r1, r2 = f64(sigx, (B, nlp.n)), f64(r1, (B, nlp.n)), f64(r2, (B, nlp.m))
+        sigs = f64(sigs, (B, np.size(sigs) // (B if np.ndim(sigs) > 1 else 1)))
+        dw = np.ascontiguousarray(np.broadcast_to(np.asarray(dw, dtype=np.float64), (B,)))
+        dc = np.ascontiguousarray(np.broadcast_to(np.asarray(dc, dtype=np.float64), (B,)))
+        dx, dy = np.empty((B, nlp.n)), np.empty((B, nlp.m))
+        neg, zero = np.empty(B, np.int32), np.empty(B, np.int32)
+        ip = lambda a: a.ctypes.data_as(_ip)
+        if not self._lib.fl_kkt_factor_solve(self._h, _ptr(x), _ptr(lam), _ptr(sigx), _ptr(sigs), _ptr(dw), _ptr(dc), _ptr(r1), _ptr(r2), int(refine_steps),
+                                             int(ls_mode), _ptr(dx), _ptr(dy), ip(neg), ip(zero)):
+            raise RuntimeError("fl_kkt_factor_solve: " + self._lib.fl_last_error().decode())
+        return dx, dy, neg, zero
+
+
+def lap_time(problem, x, obj):
+    """Lap time of a solution: the objective minus the control-rate penalty (direct form, optimal_laptime.hpp:1358-1368)."""
+    from .problem import FORM_DIRECT
+    X = np.asarray(x).reshape(-1, problem.nv)
+    if problem.form != FORM_DIRECT or not problem.closed:
+        raise NotImplementedError("lap time from the objective: closed laps in direct form")
+    h = np.diff(np.append(problem.s, problem.track_length))
+    n_in = problem.nv - 2
+    pen = 0.0
+    for c in range(2):
+        du = np.roll(X[:, n_in + c], -1) - X[:, n_in + c]
+        pen += problem.dissipation[c] * np.sum(du * du / h)
+    return float(obj) - pen

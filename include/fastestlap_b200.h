@@ -114,6 +114,46 @@ int  fl_flush_l2(fl_nlp* nlp);
 void* fl_host_alloc(size_t bytes);
 void  fl_host_free(void* p);
 
+/* ---- interior-point solver -------------------------------------------------------------------------------------------
+ * Device-resident replacement of what Ipopt + MUMPS do behind lion::ipopt_cppad_solve for this NLP
+ * (src/core/applications/optimal_laptime.hpp:528-556: options, solve, result): a primal-dual interior-point method with
+ * filter line search (Waechter & Biegler 2006, the algorithm Ipopt implements) whose augmented system is factorised as a
+ * batched block-(cyclic-)tridiagonal LDL^T, one warp per lap.  Every lap of the handle's batch is solved independently
+ * and concurrently.  Defaults = Ipopt's defaults with the reference's tolerances (tol, constr_viol_tol 1e-10,
+ * acceptable_tol 1e-8, max_iter 3000). */
+typedef struct fl_ipm fl_ipm;
+typedef struct fl_ipm_opts
+{
+    double tol, constr_viol_tol, acceptable_tol;
+    int acceptable_iter, max_iter;
+    double mu_init, bound_push, bound_frac, bound_relax_factor, kappa_eps, kappa_mu, theta_mu, tau_min, kappa_sigma, s_max;
+    double gamma_theta, gamma_phi, delta, s_theta, s_phi, eta_phi, kappa_soc, alpha_red;
+    int max_soc, max_backtracks;
+    double delta_w_min, delta_w_0, delta_w_max, kappa_w_minus, kappa_w_plus, kappa_w_plus_bar, delta_c_bar, kappa_c, y_init_max;
+    int refine_steps;
+} fl_ipm_opts;
+void fl_ipm_default_options(fl_ipm_opts* opts);
+/* status of a lap (ipopt_cppad_result::status analogue) */
+enum { FL_IPM_RUNNING = 0, FL_IPM_SUCCESS = 1, FL_IPM_ACCEPTABLE = 2, FL_IPM_MAX_ITER = -1, FL_IPM_LINE_SEARCH_FAILED = -2,
+       FL_IPM_REGULARISATION_FAILED = -3, FL_IPM_NOT_FINITE = -4 };
+/* opts == NULL: defaults.  Bounds x_l, x_u [n], g_l, g_u [m] (shared by the batch) == NULL: fl_nlp_bounds.  The nlp handle must
+ * outlive the solver and must not be used concurrently. */
+fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, const double* x_u, const double* g_l, const double* g_u);
+void    fl_ipm_destroy(fl_ipm* ipm);
+/* x0: [batch][n] starting points (host).  Returns 1 when the iteration ran (per-lap outcomes are in fl_ipm_results). */
+int fl_ipm_solve(fl_ipm* ipm, const double* x0, int verbose);
+/* any output may be NULL: x [batch][n], y [batch][m], zl, zu [batch][n], obj [batch], status [batch], iters [batch],
+ * errors [batch][4] = (scaled NLP error, constraint violation, dual infeasibility, barrier parameter) */
+int fl_ipm_results(fl_ipm* ipm, double* x, double* y, double* zl, double* zu, double* obj, int* status, int* iters, double* errors);
+/* [0] solver kernel launches, [1] factorisation launches, [2] solve launches, [3] full callback rounds, [4] f/g-only rounds, [5] outer rounds */
+void fl_ipm_stats(const fl_ipm* ipm, long stats[6], double* device_ms);
+/* One factorisation + solve of  [W + diag(sigx) + dw, J^T; J, -D][dx; dy] = [r1; r2]  at (x, lambda) for every lap of the batch
+ * (D = dc on equality rows, 1/(sigs + dw) + dc on inequality rows; sigs is [batch][n_elements * 6], element-major);
+ * ls_mode = 1 solves the least-squares multiplier system instead (W = 0, sigx = 1, D = 1 on inequality rows).
+ * n_neg / n_zero: negative and vanishing pivots of the condensed matrix (expected: n_stages * n_equality_rows, 0). */
+int fl_kkt_factor_solve(fl_ipm* ipm, const double* x, const double* lambda, const double* sigx, const double* sigs, const double* dw, const double* dc,
+                        const double* r1, const double* r2, int refine_steps, int ls_mode, double* dx, double* dy, int* n_neg, int* n_zero);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,107 @@
+"""Device interior-point solver and its batched block-tridiagonal KKT factorisation against the CPU statements
+(oracle/kkt.py, scipy) and against the reference's converged laps (tests/golden/*.npz)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from tests.helpers import load_golden, oracle_nlp, equality_rows
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["f1_catalunya_discrete", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell", "f1_catalunya_3d"]
+
+
+def _ineq_rows(p):
+    eq = set(equality_rows(p).tolist())
+    return np.array([r for r in range(p.ncpe) if r not in eq])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_kkt_factor_solve_matches_sparse_lu(case):
+    """[W + Sigma + dw, J^T; J, -D] solved by the device block factorisation == scipy's sparse LU of the same matrix built
+    from the oracle's derivatives; the pivot signs give the inertia (n, m_eq) of the condensed matrix."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver
+    from oracle import ipm as oipm
+    p, ex = load_golden(case)
+    rng = np.random.default_rng(3)
+    x = ex["x"] * (1 + 1e-3 * rng.standard_normal(p.n))
+    lam = ex["lam"]
+    r = oipm.oracle_evaluator(oracle_nlp(p))(x, lam, 1.0, True)
+    H, J = r["H"], r["J"]
+    ineq = _ineq_rows(p)
+    rows = np.arange(p.m).reshape(p.n_elements, p.ncpe)
+    all_ineq = rows[:, ineq].ravel()
+    sigx = rng.uniform(0.01, 10.0, p.n)
+    sigs = rng.uniform(0.1, 10.0, all_ineq.size)
+    dw, dc = 1.0e-3, 1.0e-9
+    D = np.full(p.m, dc)
+    D[all_ineq] = 1.0 / (sigs + dw) + dc
+    r1, r2 = rng.standard_normal(p.n), rng.standard_normal(p.m)
+    K = sp.bmat([[H + sp.diags(sigx + dw), J.T], [J, -sp.diags(D)]], format="csc")
+    sol = spla.splu(K).solve(np.concatenate([r1, r2]))
+    nlp = CollocationNLP(p)
+    solver = LapSolver(nlp)
+    dx, dy, neg, zero = solver.kkt_factor_solve(x, lam, sigx, sigs, dw, dc, r1, r2, refine_steps=2)
+    n_eq = p.n_elements * (p.ncpe - len(ineq))
+    assert neg[0] == n_eq and zero[0] == 0
+    got = np.concatenate([dx[0], dy[0]])
+    scale = np.max(np.abs(sol))
+    assert np.max(np.abs(got - sol)) <= 1e-8 * scale
+    res = K @ got - np.concatenate([r1, r2])
+    assert np.max(np.abs(res)) <= 1e-7 * max(1.0, scale)
+    solver.close(); nlp.close()
+
+
+def test_wrong_inertia_is_reported():
+    """With a strongly negative shift of the Hessian the condensed matrix has too many negative pivots."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver
+    p, ex = load_golden("f1_catalunya_chicane")
+    nlp = CollocationNLP(p)
+    solver = LapSolver(nlp)
+    ni = p.n_elements * 6
+    _, _, neg, _ = solver.kkt_factor_solve(ex["x"], ex["lam"], np.full(p.n, -1.0e4), np.ones(ni), 0.0, 1e-9, np.zeros(p.n), np.zeros(p.m))
+    assert neg[0] > p.n_elements * (p.ncpe - 6)
+    solver.close(); nlp.close()
+
+
+def test_warm_started_lap_converges_to_the_reference_solution():
+    """F1, Catalunya, 500 nodes: from the golden solution perturbed by 1 % the solver returns to the reference's converged
+    lap (f1_optimal_laptime_catalunya_discrete.xml): lap time within 1e-6 relative, controls and states within 1e-5."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    p, ex = load_golden("f1_catalunya_discrete")
+    rng = np.random.default_rng(0)
+    x0 = ex["x"] * (1 + 0.01 * rng.standard_normal(p.n))
+    nlp = CollocationNLP(p)
+    solver = LapSolver(nlp)
+    out = solver.solve(x0)
+    assert out["status"][0] == 1, out["status"]
+    t = lap_time(p, out["x"][0], out["obj"][0])
+    assert abs(t - float(ex["laptime"])) <= 1e-6 * float(ex["laptime"])
+    assert np.max(np.abs(out["x"][0] - ex["x"])) <= 1e-5
+    assert out["constr_viol"][0] <= 1e-10
+    solver.close(); nlp.close()
+
+
+def test_cold_start_batch_of_laps():
+    """Four laps with different vehicles from the same straight-line start converge; the one with the reference vehicle
+    reaches the reference lap time to 1e-5 (its local minimum is 0.3 ms faster than the stored one)."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.vehicle import MODEL_F1
+    p, ex = load_golden("f1_catalunya_discrete")
+    params = workloads.sweep_parameters(MODEL_F1, 4)
+    params[0] = p.params
+    nlp = CollocationNLP(p, vehicle_params=params)
+    solver = LapSolver(nlp)
+    out = solver.solve(workloads.f1_start_point(p, 50.0))
+    assert np.all(out["status"] == 1), out["status"]
+    t0 = lap_time(p, out["x"][0], out["obj"][0])
+    assert abs(t0 - float(ex["laptime"])) <= 1e-5 * float(ex["laptime"])
+    times = [lap_time(p, out["x"][b], out["obj"][b]) for b in range(4)]
+    assert all(60.0 < t < 100.0 for t in times)
+    solver.close(); nlp.close()
