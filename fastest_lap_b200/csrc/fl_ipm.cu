@@ -4,6 +4,7 @@
 // phases and reads a few counters per phase; every vector, matrix and per-lap decision lives on the device.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,11 +54,11 @@ namespace {
 
 template <int NV, int NEQ> void launch_factor(fl_ipm* s, const fl_kkt_dev& K)
 {
-    k_kkt_factor<NV, NEQ><<<s->B, 32, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K);
+    k_kkt_factor<NV, NEQ><<<s->B, KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K);
 }
 template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, const double* r1, const double* r2, double* dx, double* dy)
 {
-    k_kkt_solve<NV, NEQ><<<s->B, 32, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K, r1, r2, dx, dy);
+    k_kkt_solve<NV, NEQ><<<s->B, KT, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
 }
 
 #define FLI_DISPATCH(fn, ...) \
@@ -69,10 +70,22 @@ template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, con
         else { fl_set_error("no KKT kernel for this stage size"); return 0; } \
     } while (0)
 
-int kkt_factor(fl_ipm* s, const int* active, int ls_mode)
+// FL_IPM_PROFILE=1: synchronise around the phases and accumulate their device time (diagnosis only)
+bool profiling() { static const bool on = std::getenv("FL_IPM_PROFILE") != nullptr; return on; }
+struct phase_timer
 {
+    fl_ipm* s; double* acc; cudaEvent_t a, b;
+    phase_timer(fl_ipm* s_, double* acc_) : s(s_), acc(acc_) { if (profiling()) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s->nlp->stream); } }
+    ~phase_timer() { if (profiling()) { cudaEventRecord(b, s->nlp->stream); cudaEventSynchronize(b); float ms = 0.f; cudaEventElapsedTime(&ms, a, b); *acc += ms; cudaEventDestroy(a); cudaEventDestroy(b); } }
+};
+
+// with_ic: the inertia-correcting loop runs inside the kernel on the lap records (the interior-point iteration);
+// otherwise one pass with the dw / dc arrays, pivot counts reported
+int kkt_factor(fl_ipm* s, const int* active, int ls_mode, bool with_ic)
+{
+    phase_timer pt(s, &s->ms_factor);
     fl_kkt_dev K = s->K;
-    K.active = active; K.ls_mode = ls_mode;
+    K.active = active; K.ls_mode = ls_mode; K.laps = with_ic ? s->I.lap : nullptr; K.o = s->I.o;
     FLI_DISPATCH(launch_factor, K);
     s->launches += 1; s->n_factor_launches += 1;
     FLI_CUDA(cudaGetLastError());
@@ -81,8 +94,9 @@ int kkt_factor(fl_ipm* s, const int* active, int ls_mode)
 
 int kkt_solve(fl_ipm* s, const int* active, int ls_mode, const double* r1, const double* r2, double* dx, double* dy)
 {
+    phase_timer pt(s, &s->ms_solve);
     fl_kkt_dev K = s->K;
-    K.active = active; K.ls_mode = ls_mode;
+    K.active = active; K.ls_mode = ls_mode; K.laps = nullptr;
     FLI_DISPATCH(launch_solve, K, r1, r2, dx, dy);
     s->launches += 1; s->n_solve_launches += 1;
     FLI_CUDA(cudaGetLastError());
@@ -236,8 +250,10 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     K.F = (P.closed && S > 2) ? dalloc<double>((size_t)B * S * NB2, own) : nullptr;
     K.Aq = dalloc<double>((size_t)B * S * NINEQ * (NV + 1), own);
     K.ywork = dalloc<double>((size_t)B * S * s->NB, own);
+    K.Lst = dalloc<double>((size_t)B * S * s->NB * NV, own);
+    K.laps = nullptr;
     K.n_neg = s->d_neg; K.n_zero = s->d_zero; K.ls_mode = 0;
-    if (!I.lap || !K.Dinv || !K.ywork || !s->wy || (P.closed && S > 2 && !K.F))
+    if (!I.lap || !K.Dinv || !K.ywork || !K.Lst || !s->wy || (P.closed && S > 2 && !K.F))
     {
         fl_set_error("out of device memory for the interior-point workspace");
         fl_ipm_destroy(s);
@@ -271,7 +287,7 @@ int fl_kkt_factor_solve(fl_ipm* s, const double* x, const double* lambda, const 
     std::vector<fl_ipm_lap> laps(B);
     for (size_t b = 0; b < B; ++b) { std::memset(&laps[b], 0, sizeof(fl_ipm_lap)); laps[b].dw = dw[b]; laps[b].dc = dc[b]; }
     FLI_CUDA(cudaMemcpyAsync(I.lap, laps.data(), B * sizeof(fl_ipm_lap), cudaMemcpyHostToDevice, st));
-    if (!kkt_factor(s, nullptr, ls_mode)) return 0;
+    if (!kkt_factor(s, nullptr, ls_mode, false)) return 0;
     fl_ipm_options keep = s->I.o;
     s->I.o.refine_steps = refine_steps;
     const int ok = solve_refined(s, nullptr, ls_mode, I.dx, I.dy);
@@ -301,7 +317,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     k_ipm_init_slacks<<<B, IPM_BLOCK, 0, st>>>(I);
     s->launches += 2; s->n_eval_full += 1;
     // least-squares multipliers (Ipopt's default start): [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
-    if (!kkt_factor(s, nullptr, 1)) return 0;
+    if (!kkt_factor(s, nullptr, 1, false)) return 0;
     if (!solve_refined(s, nullptr, 1, I.dx, I.dy)) return 0;
     k_ipm_take_multipliers<<<B, IPM_BLOCK, 0, st>>>(I);
     s->launches += 1;
@@ -310,7 +326,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     {
         s->n_rounds = round;
         // callbacks at (x, y), state of the iterate
-        if (!fl_eval_device(nlp, ALL, 1.0)) return 0;
+        { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device(nlp, ALL, 1.0)) return 0; }
         s->n_eval_full += 1;
         if (!zero_counters(s)) return 0;
         k_ipm_state<<<B, IPM_BLOCK, 0, st>>>(I);
@@ -325,16 +341,8 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
                          l0.cviol, l0.dual_inf, l0.mu, l0.dw_last, l0.alpha, l0.status);
         }
         if (cnt[0] == 0) break;
-        // factorisation with inertia correction
-        for (int attempt = 0; attempt < 200; ++attempt)
-        {
-            if (!kkt_factor(s, I.act_factor, 0)) return 0;
-            if (!zero_counters(s)) return 0;
-            k_ipm_inertia<<<blocks_b, 128, 0, st>>>(I, B);
-            s->launches += 1;
-            if (!read_counters(s, cnt)) return 0;
-            if (cnt[1] == 0) break;
-        }
+        // factorisation; the inertia correction (Algorithm IC) runs inside the kernel, lap by lap
+        if (!kkt_factor(s, I.act_run, 0, true)) return 0;
         // search direction
         k_ipm_rhs<<<B, IPM_BLOCK, 0, st>>>(I, 0);
         s->launches += 1;
@@ -354,7 +362,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
                 k_ipm_soc_direction<<<B, IPM_BLOCK, 0, st>>>(I);
                 s->launches += 2;
             }
-            if (!fl_eval_device(nlp, FL_EVAL_FG, 1.0)) return 0;
+            { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device(nlp, FL_EVAL_FG, 1.0)) return 0; }
             s->n_eval_fg += 1;
             if (!zero_counters(s)) return 0;
             k_ipm_line_search<<<B, IPM_BLOCK, 0, st>>>(I);
@@ -367,6 +375,8 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->ms_total = ms;
+    if (profiling()) std::fprintf(stderr, "ipm profile: total %.1f ms, factor %.1f ms (%ld launches), solve %.1f ms (%ld), callbacks %.1f ms (%ld + %ld)\n", s->ms_total,
+                                  s->ms_factor, s->n_factor_launches, s->ms_solve, s->n_solve_launches, s->ms_eval, s->n_eval_full, s->n_eval_fg);
     FLI_CUDA(cudaGetLastError());
     return 1;
 }

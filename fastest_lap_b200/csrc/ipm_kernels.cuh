@@ -19,30 +19,7 @@
 #include "kkt_kernels.cuh"
 
 constexpr int IPM_BLOCK = 128;
-constexpr int IPM_NVMAX = 17, IPM_NCPEMAX = 21, IPM_FILTER_MAX = 256;
-
-enum { IPM_RUNNING = 0, IPM_SUCCESS = 1, IPM_ACCEPTABLE = 2, IPM_MAX_ITER = -1, IPM_LINE_SEARCH_FAILED = -2, IPM_REGULARISATION_FAILED = -3,
-       IPM_NOT_FINITE = -4 };
-enum { LS_IDLE = 0, LS_TRIAL = 1, LS_SOC_SOLVE = 2, LS_SOC_TRIAL = 3, LS_DONE = 4 };
-
-struct fl_ipm_options
-{
-    double tol, constr_viol_tol, acceptable_tol;
-    int acceptable_iter, max_iter;
-    double mu_init, bound_push, bound_frac, bound_relax_factor, kappa_eps, kappa_mu, theta_mu, tau_min, kappa_sigma, s_max;
-    double gamma_theta, gamma_phi, delta, s_theta, s_phi, eta_phi, kappa_soc, alpha_red;
-    int max_soc, max_backtracks;
-    double delta_w_min, delta_w_0, delta_w_max, kappa_w_minus, kappa_w_plus, kappa_w_plus_bar, delta_c_bar, kappa_c, y_init_max;
-    int refine_steps;
-};
-
-struct fl_ipm_lap
-{
-    double mu, tau, theta, phi, dphi, alpha, alpha_max, alpha_dual, dw, dw_last, dc, theta_max, theta_min;
-    double f, cviol, dual_inf, compl_inf, err0, theta_soc_old, alpha_soc;
-    int status, ls, iter, acc_count, n_filter, n_backtrack, n_soc, n_reg, n_fact, switching, soc_step;
-    double filter[2 * IPM_FILTER_MAX];
-};
+constexpr int IPM_NVMAX = 17, IPM_NCPEMAX = 21;
 
 struct fl_ipm_dev
 {
@@ -353,29 +330,6 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
     }
     lg = ipm_block_sum(lg, red);
     if (threadIdx.x == 0) L.phi = L.f - mu * lg;
-}
-
-// ---- inertia check and regularisation update (Algorithm IC) -------------------------------------------------------------
-__global__ void k_ipm_inertia(const fl_ipm_dev I, int batch)
-{
-    const int lap = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lap >= batch || !I.act_factor[lap]) return;
-    fl_ipm_lap& L = I.lap[lap];
-    const fl_ipm_options& o = I.o;
-    L.n_fact += 1;
-    const int want_neg = I.S * I.NEQ;
-    if (I.n_neg[lap] == want_neg && I.n_zero[lap] == 0)
-    {
-        I.act_factor[lap] = 0;
-        if (L.dw > 0.0) L.dw_last = L.dw;
-        return;
-    }
-    L.n_reg += 1;
-    if (L.dw == 0.0) L.dw = (L.dw_last == 0.0) ? o.delta_w_0 : fmax(o.delta_w_min, o.kappa_w_minus * L.dw_last);
-    else L.dw *= (L.dw_last == 0.0) ? o.kappa_w_plus_bar : o.kappa_w_plus;
-    if (L.dw > o.delta_w_max) { L.status = IPM_REGULARISATION_FAILED; I.act_factor[lap] = 0; I.act_run[lap] = 0; return; }
-    I.dw[lap] = L.dw;
-    atomicAdd(I.counters + 1, 1);
 }
 
 // ---- right-hand side of the augmented system: r2 = -c, inequality rows -= rs_bar / (Sigma_s + dw) ------------------------

@@ -18,13 +18,17 @@
 //     largest diagonal, 2x2 pivots when the diagonal is weak), which also counts the negative pivots: by Haynsworth
 //     additivity their sum is the inertia Ipopt asks of its linear solver (n positive, m negative, none zero).
 //
-// One warp per lap: lane r owns row r of every stage matrix (shared memory, column-major with leading dimension 32 so a
-// warp's access to a column is one conflict-free 256-byte row of banks; operands shared by all lanes are broadcast reads),
-// products are accumulated in registers, reductions are warp shuffles.  Laps are independent: a batch fills the machine
-// with one warp per lap, several laps per SM.  oracle/kkt.py is the numpy statement of the same algorithm.
+// One block of four warps per lap: thread (lane r, warp w) owns row r and the columns c = w, w+4, w+8, ... of every stage
+// matrix (shared memory, column-major with leading dimension 32, so a warp's access to a column is one conflict-free
+// 256-byte row of banks and operands shared by the lanes are broadcast reads); products are accumulated in registers,
+// pivot searches are warp shuffles.  The inertia-correcting regularisation (Algorithm IC of Waechter & Biegler) runs
+// inside the kernel: a stage whose pivot block has the wrong inertia stops the elimination at once, dw is raised and the
+// lap starts over, while the other laps of the batch go on.  Laps are independent: a batch fills the machine with
+// several laps per SM.  oracle/kkt.py is the numpy statement of the same algorithm.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "ipm_types.cuh"
 
 struct fl_kkt_tables          // device pointers, per variant
 {
@@ -53,13 +57,19 @@ struct fl_kkt_dev
     double* Dinv;             // [batch][S][NB*NB]  inverse pivot blocks (column-major, ld NB)
     double* F;                // [batch][S][NB*NB]  closed laps: fill blocks K[0, j] (rows: stage 0, columns: stage j)
     double* Aq;               // [batch][S][NINEQ*(NV+1)]  inequality rows of the stage's element w.r.t. its right node, and 1/D
+    double* Lst;              // [batch][S][NB*NV]   coupling blocks K[j, j-1] as gathered (dense, column-major, ld NB)
     double* ywork;            // [batch][S][NB]      forward-substitution intermediates
     int* n_neg;               // [batch] negative pivots
     int* n_zero;              // [batch] vanishing pivots
     int ls_mode;              // 1: least-squares multiplier system (W = 0, Sigma_x = 1, D_ineq = 1)
+    fl_ipm_lap* laps;         // [batch] or null.  Not null: dw is read from / written to the lap records and the inertia
+                              // correction loop runs in the kernel; null: one pass with dw[], the pivot counts are reported
+    fl_ipm_options o;
 };
 
 constexpr int KLD = 32;                                   // leading dimension of the stage matrices in shared memory
+constexpr int KT = 128;                                   // threads per lap
+constexpr int KW = KT / 32;                               // warps per lap: columns are dealt round-robin to the warps
 #define KM(M, r, c) (M)[(r) + KLD * (c)]
 
 __device__ __forceinline__ double kkt_warp_max(double v)
@@ -69,7 +79,7 @@ __device__ __forceinline__ double kkt_warp_max(double v)
     return v;
 }
 
-// arg max over the warp, ties to the lowest lane (deterministic)
+// arg max over the warp, ties to the lowest index (deterministic)
 __device__ __forceinline__ void kkt_warp_argmax(double& v, int& idx)
 {
 #pragma unroll
@@ -81,98 +91,132 @@ __device__ __forceinline__ void kkt_warp_argmax(double& v, int& idx)
     }
 }
 
-// In-place inverse of the symmetric NB x NB matrix M (shared memory, both triangles stored) by Gauss-Jordan sweeps with
-// Bunch-Parlett pivoting.  rowbuf: 2 * KLD doubles of shared memory.  Returns the number of negative pivots through
-// n_neg and of vanishing ones through n_zero (accumulated).
-template <int NB>
-__device__ __forceinline__ void kkt_invert(double* M, double* rowbuf, int& n_neg, int& n_zero)
+struct kkt_pivot            // decision of one Gauss-Jordan step, written by warp 0, read by the whole block
 {
-    const int lane = threadIdx.x & 31;
+    int two, p, q, done;
+    double pv, i00, i01, i10, i11;
+};
+
+// In-place inverse of the symmetric NB x NB matrix M (shared memory, both triangles stored) by Gauss-Jordan sweeps with
+// Bunch-Parlett pivoting; the whole block takes part.  rowbuf / colbuf: 2 * KLD doubles each.  Thread 0 accumulates the
+// number of negative and vanishing pivots.
+template <int NB>
+__device__ __forceinline__ void kkt_invert(double* M, double* rowbuf, double* colbuf, kkt_pivot* pv_s, int& n_neg, int& n_zero)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const double ALPHA = 0.6403882032022076;              // (1 + sqrt(17)) / 8
     unsigned swept = 0u;
     const unsigned all = (NB == 32) ? 0xffffffffu : ((1u << NB) - 1u);
     while (swept != all)
     {
-        const bool mine = lane < NB && !((swept >> lane) & 1u);
-        double dmax = mine ? fabs(KM(M, lane, lane)) : -1.0;
-        int k = lane;
-        kkt_warp_argmax(dmax, k);
-        const double lam = kkt_warp_max((mine && lane != k) ? fabs(KM(M, lane, k)) : 0.0);
-        bool two = false;
-        int p = k, q = k;
-        if (!(dmax >= ALPHA * lam && dmax > 0.0))
+        if (w == 0)
         {
-            // largest off-diagonal entry of the unswept part
-            double best = -1.0;
-            int bc = 0;
-            if (mine)
-                for (int c = 0; c < NB; ++c)
-                    if (c != lane && !((swept >> c) & 1u))
+            const bool mine = lane < NB && !((swept >> lane) & 1u);
+            double dmax = mine ? fabs(KM(M, lane, lane)) : -1.0;
+            int k = lane;
+            kkt_warp_argmax(dmax, k);
+            const double lam = kkt_warp_max((mine && lane != k) ? fabs(KM(M, lane, k)) : 0.0);
+            bool two = false;
+            int p = k, q = k;
+            if (!(dmax >= ALPHA * lam && dmax > 0.0))
+            {
+                // largest off-diagonal entry of the unswept part
+                double best = -1.0;
+                int bc = 0;
+                if (mine)
+                    for (int c = 0; c < NB; ++c)
+                        if (c != lane && !((swept >> c) & 1u))
+                        {
+                            const double a = fabs(KM(M, lane, c));
+                            if (a > best) { best = a; bc = c; }
+                        }
+                int br = lane;
+                double mu0 = best;
+                kkt_warp_argmax(mu0, br);
+                bc = __shfl_sync(0xffffffffu, bc, br);
+                if (mu0 > 0.0 && !(dmax >= ALPHA * mu0)) { two = true; p = br; q = bc; }
+            }
+            if (!two)
+            {
+                double d = KM(M, k, k);
+                if (d == 0.0) { d = 1.0e-300; if (lane == 0) ++n_zero; }
+                if (lane == 0 && d < 0.0) ++n_neg;
+                const double pv = 1.0 / d;
+                if (lane < NB) { rowbuf[lane] = KM(M, k, lane) * pv; colbuf[lane] = KM(M, lane, k); }
+                if (lane == 0) { pv_s->two = 0; pv_s->p = k; pv_s->q = k; pv_s->pv = pv; }
+            }
+            else
+            {
+                const double a = KM(M, p, p), b = KM(M, p, q), b2 = KM(M, q, p), c2 = KM(M, q, q);
+                const double det = a * c2 - b * b2;
+                if (lane == 0) n_neg += (det < 0.0) ? 1 : ((a < 0.0) ? 2 : 0);
+                const double i00 = c2 / det, i01 = -b / det, i10 = -b2 / det, i11 = a / det;
+                if (lane < NB)
+                {
+                    const double mp = KM(M, p, lane), mq = KM(M, q, lane);
+                    rowbuf[lane] = i00 * mp + i01 * mq;
+                    rowbuf[KLD + lane] = i10 * mp + i11 * mq;
+                    colbuf[lane] = KM(M, lane, p);
+                    colbuf[KLD + lane] = KM(M, lane, q);
+                }
+                if (lane == 0) { pv_s->two = 1; pv_s->p = p; pv_s->q = q; pv_s->i00 = i00; pv_s->i01 = i01; pv_s->i10 = i10; pv_s->i11 = i11; }
+            }
+        }
+        __syncthreads();
+        const int two = pv_s->two, p = pv_s->p, q = pv_s->q;
+        if (lane < NB)
+        {
+            if (!two)
+            {
+                const double pv = pv_s->pv, f = colbuf[lane];
+                if (lane != p)
+                {
+#pragma unroll
+                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
                     {
-                        const double a = fabs(KM(M, lane, c));
-                        if (a > best) { best = a; bc = c; }
+                        const int c = w + KW * i;
+                        if (c < NB) KM(M, lane, c) = (c == p) ? -f * pv : KM(M, lane, c) - f * rowbuf[c];
                     }
-            int br = lane;
-            double mu0 = best;
-            kkt_warp_argmax(mu0, br);
-            bc = __shfl_sync(0xffffffffu, bc, br);
-            if (mu0 > 0.0 && !(dmax >= ALPHA * mu0)) { two = true; p = br; q = bc; }
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
+                    {
+                        const int c = w + KW * i;
+                        if (c < NB) KM(M, lane, c) = (c == p) ? pv : rowbuf[c];
+                    }
+                }
+            }
+            else
+            {
+                const double i00 = pv_s->i00, i01 = pv_s->i01, i10 = pv_s->i10, i11 = pv_s->i11;
+                const double fp = colbuf[lane], fq = colbuf[KLD + lane];
+                if (lane != p && lane != q)
+                {
+#pragma unroll
+                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
+                    {
+                        const int c = w + KW * i;
+                        if (c < NB)
+                            KM(M, lane, c) = (c == p) ? -(fp * i00 + fq * i10) : (c == q) ? -(fp * i01 + fq * i11)
+                                                      : KM(M, lane, c) - fp * rowbuf[c] - fq * rowbuf[KLD + c];
+                    }
+                }
+                else
+                {
+                    const double* rb = rowbuf + (lane == p ? 0 : KLD);
+#pragma unroll
+                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
+                    {
+                        const int c = w + KW * i;
+                        if (c < NB) KM(M, lane, c) = (c == p) ? ((lane == p) ? i00 : i10) : (c == q) ? ((lane == p) ? i01 : i11) : rb[c];
+                    }
+                }
+            }
         }
-        if (!two)
-        {
-            double d = KM(M, k, k);
-            if (d == 0.0) { d = 1.0e-300; if (lane == 0) ++n_zero; }
-            if (lane == 0 && d < 0.0) ++n_neg;
-            const double pv = 1.0 / d;
-            if (lane < NB) rowbuf[lane] = KM(M, k, lane) * pv;
-            __syncwarp();
-            if (lane < NB && lane != k)
-            {
-                const double f = KM(M, lane, k);
-#pragma unroll 4
-                for (int c = 0; c < NB; ++c) KM(M, lane, c) -= f * rowbuf[c];
-                KM(M, lane, k) = -f * pv;
-            }
-            else if (lane == k)
-            {
-#pragma unroll 4
-                for (int c = 0; c < NB; ++c) KM(M, k, c) = rowbuf[c];
-                KM(M, k, k) = pv;
-            }
-            swept |= 1u << k;
-        }
-        else
-        {
-            const double a = KM(M, p, p), b = KM(M, p, q), b2 = KM(M, q, p), c2 = KM(M, q, q);
-            const double det = a * c2 - b * b2;
-            if (lane == 0) n_neg += (det < 0.0) ? 1 : ((a < 0.0) ? 2 : 0);
-            const double i00 = c2 / det, i01 = -b / det, i10 = -b2 / det, i11 = a / det;
-            if (lane < NB)
-            {
-                const double mp = KM(M, p, lane), mq = KM(M, q, lane);
-                rowbuf[lane] = i00 * mp + i01 * mq;
-                rowbuf[KLD + lane] = i10 * mp + i11 * mq;
-            }
-            __syncwarp();
-            if (lane < NB && lane != p && lane != q)
-            {
-                const double fp = KM(M, lane, p), fq = KM(M, lane, q);
-#pragma unroll 4
-                for (int c = 0; c < NB; ++c) KM(M, lane, c) -= fp * rowbuf[c] + fq * rowbuf[KLD + c];
-                KM(M, lane, p) = -(fp * i00 + fq * i10);
-                KM(M, lane, q) = -(fp * i01 + fq * i11);
-            }
-            else if (lane == p || lane == q)
-            {
-                const double* rb = rowbuf + (lane == p ? 0 : KLD);
-#pragma unroll 4
-                for (int c = 0; c < NB; ++c) KM(M, lane, c) = rb[c];
-                KM(M, lane, p) = (lane == p) ? i00 : i10;
-                KM(M, lane, q) = (lane == p) ? i01 : i11;
-            }
-            swept |= (1u << p) | (1u << q);
-        }
-        __syncwarp();
+        swept |= two ? ((1u << p) | (1u << q)) : (1u << p);
+        __syncthreads();
     }
 }
 
@@ -181,38 +225,32 @@ template <int NV, int NEQ>
 struct kkt_stage
 {
     static constexpr int NB = NV + NEQ;
-    static_assert(NB <= 32, "a stage must fit one warp");
+    static constexpr int CB = (NB + KW - 1) / KW, CV = (NV + KW - 1) / KW;      // columns per thread
+    static_assert(NB <= 32, "a stage must fit one warp of rows");
 
-    // element that ends at stage j's node, and whether its left node is a variable node (coupling to stage j-1 exists)
+    // element that ends at stage j's node
     static __device__ __forceinline__ int e_in(const fl_kkt_dev& K, int j) { const int node = j + K.node0; return node == 0 ? K.n_points - 1 : node - 1; }
 
-    // Diagonal block of stage j into M (zeroed here), inequality rows into Aq (global, per stage) -- without Schur terms.
-    static __device__ void gather_diag(const fl_kkt_dev& K, int lap, int j, double* M, double* aq_s /* shared [NINEQ][KLD] + [KLD] */)
+    // Diagonal block of stage j into M, inequality rows and 1/D into aq_s ([NINEQ][KLD] + [KLD]) -- without Schur terms.
+    static __device__ void gather_diag(const fl_kkt_dev& K, int lap, int j, double dw, double dc, double* M, double* aq_s)
     {
-        const int lane = threadIdx.x & 31;
+        const int t = threadIdx.x, lane = t & 31, w = t >> 5;
         const int e = e_in(K, j);
         const double* jac = K.jac + (size_t)lap * K.nnz_jac;
         const double* hes = K.hess + (size_t)lap * K.nnz_hess;
-        for (int c = 0; c < NB; ++c) KM(M, lane, c) = 0.0;
-        for (int t = 0; t < K.NINEQ; ++t) aq_s[t * KLD + lane] = 0.0;
-        __syncwarp();
-        const double dw = K.dw[lap], dc = K.dc[lap];
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) KM(M, lane, c) = 0.0; }
+        for (int k = t; k < (K.NINEQ + 1) * KLD; k += KT) aq_s[k] = 0.0;
+        __syncthreads();
         if (!K.ls_mode)
-        {
-            for (int k = lane; k < K.NH; k += 32)
+            for (int k = t; k < K.NH; k += KT)
             {
                 const int r = K.t.h_row[k], c = K.t.h_col[k];
                 const double v = hes[(size_t)k * K.S + j];
                 KM(M, r, c) = v;
                 KM(M, c, r) = v;
             }
-            __syncwarp();
-            if (lane < NV) KM(M, lane, lane) += K.sigx[(size_t)lap * K.n + (size_t)j * NV + lane] + dw;
-        }
-        else if (lane < NV) KM(M, lane, lane) = 1.0;
-        if (lane >= NV && lane < NB) KM(M, lane, lane) = -dc;
-        __syncwarp();
-        for (int k = lane; k < K.NJA; k += 32)
+        for (int k = t; k < K.NJA; k += KT)
         {
             const int r = K.t.ja_row[k], c = K.t.ja_col[k];
             const double v = jac[(size_t)k * K.n_el + e];
@@ -220,307 +258,471 @@ struct kkt_stage
             if (q >= 0) { KM(M, NV + q, c) = v; KM(M, c, NV + q) = v; }
             else aq_s[K.t.ineq_of_row[r] * KLD + c] = v;
         }
-        __syncwarp();
-        // 1 / D of the inequality rows
-        if (lane < K.NINEQ)
+        if (t < K.NINEQ)
         {
-            const double ss = K.ls_mode ? 1.0 : K.sigs[(size_t)lap * K.n_el * K.NINEQ + (size_t)e * K.NINEQ + lane] + dw;
-            aq_s[K.NINEQ * KLD + lane] = 1.0 / (1.0 / ss + (K.ls_mode ? 0.0 : dc));
+            const double ss = K.ls_mode ? 1.0 : K.sigs[(size_t)lap * K.n_el * K.NINEQ + (size_t)e * K.NINEQ + t] + dw;
+            aq_s[K.NINEQ * KLD + t] = 1.0 / (1.0 / ss + (K.ls_mode ? 0.0 : dc));
         }
-        __syncwarp();
+        __syncthreads();
+        if (t < NV) KM(M, t, t) = K.ls_mode ? 1.0 : KM(M, t, t) + K.sigx[(size_t)lap * K.n + (size_t)j * NV + t] + dw;
+        else if (t < NB) KM(M, t, t) = -dc;
+        __syncthreads();
         if (lane < NV)
-            for (int t = 0; t < K.NINEQ; ++t)
+        {
+            double acc[CV];
+#pragma unroll
+            for (int i = 0; i < CV; ++i) acc[i] = 0.0;
+            for (int q = 0; q < K.NINEQ; ++q)
             {
-                const double w = aq_s[K.NINEQ * KLD + t] * aq_s[t * KLD + lane];
-                if (w != 0.0)
-                    for (int c = 0; c < NV; ++c) KM(M, lane, c) += w * aq_s[t * KLD + c];
+                const double wq = aq_s[K.NINEQ * KLD + q] * aq_s[q * KLD + lane];
+#pragma unroll
+                for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += wq * aq_s[q * KLD + c]; }
             }
-        __syncwarp();
+#pragma unroll
+            for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(M, lane, c) += acc[i]; }
+        }
+        __syncthreads();
     }
 
-    // Coupling block K[stage j, stage j-1] (or, for j == 0 of a closed lap, K[0, S-1]) into L (NB x NV, zeroed here).
+    // Coupling block K[stage j, stage j-1] (or, for j == 0 of a closed lap, K[0, S-1]) into L (NB x NV).
     static __device__ void gather_coupling(const fl_kkt_dev& K, int lap, int j, double* L)
     {
-        const int lane = threadIdx.x & 31;
+        const int t = threadIdx.x, lane = t & 31, w = t >> 5;
         const int e = e_in(K, j);
         const double* jac = K.jac + (size_t)lap * K.nnz_jac;
         const double* hes = K.hess + (size_t)lap * K.nnz_hess;
-        for (int c = 0; c < NV; ++c) KM(L, lane, c) = 0.0;
-        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(L, lane, c) = 0.0; }
+        __syncthreads();
         const int eb = e - K.node0;              // index among the elements with a free left node
-        if (eb < 0) return;
-        for (int k = lane; k < K.NJB; k += 32)
+        if (eb >= 0)
         {
-            const int q = K.t.eq_of_row[K.t.jb_row[k]];
-            KM(L, NV + q, K.t.jb_col[k]) = jac[(size_t)K.NJA * K.n_el + (size_t)k * K.nB + eb];
+            for (int k = t; k < K.NJB; k += KT)
+            {
+                const int q = K.t.eq_of_row[K.t.jb_row[k]];
+                KM(L, NV + q, K.t.jb_col[k]) = jac[(size_t)K.NJA * K.n_el + (size_t)k * K.nB + eb];
+            }
+            if (!K.ls_mode && t < K.NCPL)
+            {
+                const int cp = K.t.ctrl_pos[t];
+                KM(L, cp, cp) = hes[(size_t)K.NH * K.S + (size_t)t * K.nC + eb];
+            }
         }
-        if (!K.ls_mode && lane < K.NCPL)
-        {
-            const int cp = K.t.ctrl_pos[lane];
-            KM(L, cp, cp) = hes[(size_t)K.NH * K.S + (size_t)lane * K.nC + eb];
-        }
-        __syncwarp();
+        __syncthreads();
     }
 };
 
-// shared memory of one warp: M, F, XF (NB x NB each, ld 32 -> 32 x NB), L, XL, P (32 x NV), aq, rowbuf, vectors
+// shared memory of one lap: M, F, XF (32 x NB each), L, XL, P (32 x NV), inequality rows, pivot buffers
 template <int NV, int NEQ>
 struct kkt_smem
 {
     static constexpr int NB = NV + NEQ;
     double M[KLD * NB], F[KLD * NB], XF[KLD * NB], L[KLD * NV], XL[KLD * NV], P[KLD * NV];
-    double aq[8 * KLD], rowbuf[2 * KLD];
+    double aq[8 * KLD], rowbuf[2 * KLD], colbuf[2 * KLD];
+    kkt_pivot piv;
+    int flag;
 };
 
 template <int NV, int NEQ>
-__global__ void __launch_bounds__(32) k_kkt_factor(const fl_kkt_dev K)
+__global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
 {
     using St = kkt_stage<NV, NEQ>;
-    constexpr int NB = St::NB;
+    constexpr int NB = St::NB, CB = St::CB, CV = St::CV;
     extern __shared__ __align__(16) unsigned char kkt_raw[];
     kkt_smem<NV, NEQ>& sm = *reinterpret_cast<kkt_smem<NV, NEQ>*>(kkt_raw);
-    const int lap = blockIdx.x, lane = threadIdx.x;
+    const int lap = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
+    fl_ipm_lap* Lp = K.laps ? K.laps + lap : nullptr;
+    if (Lp && Lp->status != IPM_RUNNING) return;
     const int S = K.S;
     const bool cyc = K.closed && S > 2;
     double* gD = K.Dinv + (size_t)lap * S * NB * NB;
     double* gF = K.F ? K.F + (size_t)lap * S * NB * NB : nullptr;
+    double* gL = K.Lst + (size_t)lap * S * NB * NV;
     double* gA = K.Aq + (size_t)lap * S * (K.NINEQ * (NV + 1));
-    int n_neg = 0, n_zero = 0;
-    double d0acc[NB];                          // row `lane` of the Schur terms handed to stage 0 through the fill blocks
-#pragma unroll
-    for (int c = 0; c < NB; ++c) d0acc[c] = 0.0;
-    for (int c = 0; c < NV; ++c) KM(sm.P, lane, c) = 0.0;
-    for (int c = 0; c < NB; ++c) KM(sm.F, lane, c) = 0.0;
-    __syncwarp();
-    if (cyc)
+    const int AQ = K.NINEQ * (NV + 1);
+    const double dc = Lp ? Lp->dc : K.dc[lap];
+    double dw = Lp ? Lp->dw : K.dw[lap];
+
+    for (int attempt = 0;; ++attempt)
     {
-        // F_{S-1} = K[0, S-1]: coupling of stage 0 with its left neighbour (the closing element)
-        St::gather_coupling(K, lap, 0, sm.L);
-        for (int c = 0; c < NV; ++c) KM(sm.F, lane, c) = KM(sm.L, lane, c);
-        __syncwarp();
-    }
-    for (int j = S - 1; j >= 0; --j)
-    {
-        St::gather_diag(K, lap, j, sm.M, sm.aq);
-        // keep the inequality rows and 1/D for the solves
-        for (int t = 0; t < K.NINEQ; ++t)
-            if (lane < NV) gA[(size_t)j * (K.NINEQ * (NV + 1)) + t * NV + lane] = sm.aq[t * KLD + lane];
-        if (lane < K.NINEQ) gA[(size_t)j * (K.NINEQ * (NV + 1)) + K.NINEQ * NV + lane] = sm.aq[K.NINEQ * KLD + lane];
-        // Schur complement of the later stages
-        if (lane < NV)
-            for (int c = 0; c < NV; ++c) KM(sm.M, lane, c) -= KM(sm.P, lane, c);
-        if (j == 0 && cyc && lane < NB)
+        int n_neg = 0, n_zero = 0;
+        bool ok = true;
+        double d0acc[CB];                          // (row lane, own columns) of the Schur terms handed to stage 0 through the fill blocks
 #pragma unroll
-            for (int c = 0; c < NB; ++c) KM(sm.M, lane, c) -= d0acc[c];
-        __syncwarp();
-        const bool chain = j >= 1 && (j >= 2 || !cyc);          // stage j hands a Schur term to stage j-1 through L_j
-        if (j >= 1) St::gather_coupling(K, lap, j, sm.L);
-        if (cyc && j == 1)
+        for (int i = 0; i < CB; ++i) d0acc[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.P, lane, c) = 0.0; }
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) KM(sm.F, lane, c) = 0.0; }
+        __syncthreads();
+        if (cyc)
         {
-            // K[0, 1] = L_1^T joins the fill block
-            if (lane < NB)
-                for (int c = 0; c < NV; ++c) KM(sm.F, c, lane) += KM(sm.L, lane, c);
-            __syncwarp();
+            // F_{S-1} = K[0, S-1]: coupling of stage 0 with its left neighbour (the closing element)
+            St::gather_coupling(K, lap, 0, sm.L);
+#pragma unroll
+            for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.F, lane, c) = KM(sm.L, lane, c); }
+            __syncthreads();
         }
-        kkt_invert<NB>(sm.M, sm.rowbuf, n_neg, n_zero);
-        if (lane < NB)
-            for (int c = 0; c < NB; ++c) gD[(size_t)j * NB * NB + lane + NB * c] = KM(sm.M, lane, c);
-        if (cyc && j >= 1 && lane < NB)
-            for (int c = 0; c < NB; ++c) gF[(size_t)j * NB * NB + lane + NB * c] = KM(sm.F, lane, c);
-        if (j == 0) break;
-        // XL = Dinv L (NB x NV), XF = Dinv F^T (NB x NB)
-        if (chain && lane < NB)
+        for (int j = S - 1; j >= 0; --j)
         {
-            double acc[NV];
-#pragma unroll
-            for (int c = 0; c < NV; ++c) acc[c] = 0.0;
-            for (int k = 0; k < NB; ++k)
+            St::gather_diag(K, lap, j, dw, dc, sm.M, sm.aq);
+            // keep the inequality rows and 1/D for the solves
+            for (int k = t; k < K.NINEQ * NV; k += KT) gA[(size_t)j * AQ + k] = sm.aq[(k / NV) * KLD + (k % NV)];
+            if (t < K.NINEQ) gA[(size_t)j * AQ + K.NINEQ * NV + t] = sm.aq[K.NINEQ * KLD + t];
+            // Schur complement of the later stages
+            if (lane < NV)
             {
-                const double a = KM(sm.M, lane, k);
 #pragma unroll
-                for (int c = 0; c < NV; ++c) acc[c] += a * KM(sm.L, k, c);
+                for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.M, lane, c) -= KM(sm.P, lane, c); }
             }
-#pragma unroll
-            for (int c = 0; c < NV; ++c) KM(sm.XL, lane, c) = acc[c];
-        }
-        if (cyc && lane < NB)
-        {
-            double acc[NB];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) acc[c] = 0.0;
-            for (int k = 0; k < NB; ++k)
+            if (j == 0 && cyc && lane < NB)
             {
-                const double a = KM(sm.M, lane, k);
 #pragma unroll
-                for (int c = 0; c < NB; ++c) acc[c] += a * KM(sm.F, c, k);
+                for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) KM(sm.M, lane, c) -= d0acc[i]; }
             }
-#pragma unroll
-            for (int c = 0; c < NB; ++c) KM(sm.XF, lane, c) = acc[c];
-        }
-        __syncwarp();
-        // P = L^T XL (what stage j-1 subtracts from its x-x block)
-        if (lane < NV)
-        {
-            double acc[NV];
-#pragma unroll
-            for (int c = 0; c < NV; ++c) acc[c] = 0.0;
-            if (chain)
-                for (int k = 0; k < NB; ++k)
+            __syncthreads();
+            const bool chain = j >= 1 && (j >= 2 || !cyc);          // stage j hands a Schur term to stage j-1 through L_j
+            if (j >= 1)
+            {
+                St::gather_coupling(K, lap, j, sm.L);
+                if (lane < NB)
                 {
-                    const double a = KM(sm.L, k, lane);
 #pragma unroll
-                    for (int c = 0; c < NV; ++c) acc[c] += a * KM(sm.XL, k, c);
+                    for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) gL[(size_t)j * NB * NV + lane + NB * c] = KM(sm.L, lane, c); }
+                }
+            }
+            if (cyc && j == 1)
+            {
+                // K[0, 1] = L_1^T joins the fill block: F[c][r] += L[r][c]
+                if (lane < NB)
+                {
+#pragma unroll
+                    for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.F, c, lane) += KM(sm.L, lane, c); }
+                }
+                __syncthreads();
+            }
+            const int neg_before = n_neg, zero_before = n_zero;
+            kkt_invert<NB>(sm.M, sm.rowbuf, sm.colbuf, &sm.piv, n_neg, n_zero);
+            if (Lp)
+            {
+                // every pivot block carries exactly NEQ negative pivots when the reduced Hessian is positive definite
+                if (t == 0) sm.flag = (n_neg - neg_before == NEQ && n_zero == zero_before) ? 1 : 0;
+                __syncthreads();
+                ok = sm.flag != 0;
+                __syncthreads();
+                if (!ok) break;
+            }
+            if (lane < NB)
+            {
+#pragma unroll
+                for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) gD[(size_t)j * NB * NB + lane + NB * c] = KM(sm.M, lane, c); }
+                if (cyc && j >= 1)
+                {
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) gF[(size_t)j * NB * NB + lane + NB * c] = KM(sm.F, lane, c); }
+                }
+            }
+            if (j == 0) break;
+            // XL = Dinv L (NB x NV), XF = Dinv F^T (NB x NB)
+            if (lane < NB)
+            {
+                if (chain)
+                {
+                    double acc[CV];
+#pragma unroll
+                    for (int i = 0; i < CV; ++i) acc[i] = 0.0;
+#pragma unroll 4
+                    for (int k = 0; k < NB; ++k)
+                    {
+                        const double a = KM(sm.M, lane, k);
+#pragma unroll
+                        for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.L, k, c); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.XL, lane, c) = acc[i]; }
+                }
+                if (cyc)
+                {
+                    double acc[CB];
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) acc[i] = 0.0;
+#pragma unroll 4
+                    for (int k = 0; k < NB; ++k)
+                    {
+                        const double a = KM(sm.M, lane, k);
+#pragma unroll
+                        for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) acc[i] += a * KM(sm.F, c, k); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) KM(sm.XF, lane, c) = acc[i]; }
+                }
+            }
+            __syncthreads();
+            // P = L^T XL (what stage j-1 subtracts from its x-x block)
+            if (lane < NV)
+            {
+                double acc[CV];
+#pragma unroll
+                for (int i = 0; i < CV; ++i) acc[i] = 0.0;
+                if (chain)
+                {
+#pragma unroll 4
+                    for (int k = 0; k < NB; ++k)
+                    {
+                        const double a = KM(sm.L, k, lane);
+#pragma unroll
+                        for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.XL, k, c); }
+                    }
                 }
 #pragma unroll
-            for (int c = 0; c < NV; ++c) KM(sm.P, lane, c) = acc[c];
-        }
-        double fn[NV];
-#pragma unroll
-        for (int c = 0; c < NV; ++c) fn[c] = 0.0;
-        if (cyc && lane < NB)
-        {
-            // stage 0: d0acc += F XF ; new fill F_{j-1} = -F XL (columns: x of stage j-1)
-#pragma unroll
-            for (int c = 0; c < NB; ++c)
-            {
-                double a = 0.0;
-                for (int k = 0; k < NB; ++k) a += KM(sm.F, lane, k) * KM(sm.XF, k, c);
-                d0acc[c] += a;
+                for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.P, lane, c) = acc[i]; }
             }
-            if (chain)
+            double fn[CV];
+#pragma unroll
+            for (int i = 0; i < CV; ++i) fn[i] = 0.0;
+            if (cyc && lane < NB)
+            {
+                // stage 0: d0acc += F XF ; new fill F_{j-1} = -F XL (columns: x of stage j-1)
+#pragma unroll 4
                 for (int k = 0; k < NB; ++k)
                 {
                     const double a = KM(sm.F, lane, k);
 #pragma unroll
-                    for (int c = 0; c < NV; ++c) fn[c] -= a * KM(sm.XL, k, c);
-                }
-        }
-        __syncwarp();
-        if (cyc)
-        {
+                    for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) d0acc[i] += a * KM(sm.XF, k, c); }
+                    if (chain)
+                    {
 #pragma unroll
-            for (int c = 0; c < NV; ++c) KM(sm.F, lane, c) = fn[c];
-            for (int c = NV; c < NB; ++c) KM(sm.F, lane, c) = 0.0;
+                        for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) fn[i] -= a * KM(sm.XL, k, c); }
+                    }
+                }
+            }
+            __syncthreads();
+            if (cyc)
+            {
+#pragma unroll
+                for (int i = 0; i < CB; ++i)
+                {
+                    const int c = w + KW * i;
+                    if (c < NB) KM(sm.F, lane, c) = (c < NV && i < CV) ? fn[i < CV ? i : 0] : 0.0;
+                }
+            }
+            __syncthreads();
         }
-        __syncwarp();
+        if (!Lp)
+        {
+            if (t == 0) { K.n_neg[lap] = n_neg; K.n_zero[lap] = n_zero; }
+            return;
+        }
+        // Algorithm IC (Waechter & Biegler, section 3.1)
+        if (t == 0)
+        {
+            const fl_ipm_options& o = K.o;
+            Lp->n_fact += 1;
+            if (ok)
+            {
+                if (dw > 0.0) Lp->dw_last = dw;
+                Lp->dw = dw;
+                sm.flag = 1;
+            }
+            else
+            {
+                Lp->n_reg += 1;
+                if (dw == 0.0) dw = (Lp->dw_last == 0.0) ? o.delta_w_0 : fmax(o.delta_w_min, o.kappa_w_minus * Lp->dw_last);
+                else dw *= (Lp->dw_last == 0.0) ? o.kappa_w_plus_bar : o.kappa_w_plus;
+                if (dw > o.delta_w_max) { Lp->status = IPM_REGULARISATION_FAILED; sm.flag = 2; }
+                else sm.flag = 0;
+                sm.rowbuf[0] = dw;
+            }
+        }
+        __syncthreads();
+        const int fl = sm.flag;
+        if (fl != 0) return;
+        dw = sm.rowbuf[0];
+        __syncthreads();
     }
-    if (lane == 0) { K.n_neg[lap] = n_neg; K.n_zero[lap] = n_zero; }
 }
 
 // Solves K z = (r1, r2) for every active lap with the factorisation above; dx [n], dy [m] in the NLP's own orders.
+// Thread (lane r, warp w) multiplies row r of the stage's matrices with the entries k = w, w+4, ... of the vector; the
+// operands of the next stage are loaded into registers while the current stage is reduced.
 template <int NV, int NEQ>
-__global__ void __launch_bounds__(32) k_kkt_solve(const fl_kkt_dev K, const double* __restrict__ r1, const double* __restrict__ r2,
+__global__ void __launch_bounds__(KT) k_kkt_solve(const fl_kkt_dev K, const double* __restrict__ r1, const double* __restrict__ r2,
                                                    double* __restrict__ dx, double* __restrict__ dy)
 {
     using St = kkt_stage<NV, NEQ>;
-    constexpr int NB = St::NB;
-    extern __shared__ __align__(16) unsigned char kkt_raw[];
-    kkt_smem<NV, NEQ>& sm = *reinterpret_cast<kkt_smem<NV, NEQ>*>(kkt_raw);
-    const int lap = blockIdx.x, lane = threadIdx.x;
+    constexpr int NB = St::NB, CB = St::CB, CV = St::CV;
+    __shared__ double vb[KLD], vy[KLD], z0[KLD], part[3][KW][KLD];
+    const int lap = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
+    if (K.laps && K.laps[lap].status != IPM_RUNNING) return;
     const int S = K.S;
     const bool cyc = K.closed && S > 2;
     const double* gD = K.Dinv + (size_t)lap * S * NB * NB;
     const double* gF = K.F ? K.F + (size_t)lap * S * NB * NB : nullptr;
+    const double* gL = K.Lst + (size_t)lap * S * NB * NV;
     const double* gA = K.Aq + (size_t)lap * S * (K.NINEQ * (NV + 1));
     double* yw = K.ywork + (size_t)lap * S * NB;
     r1 += (size_t)lap * K.n; r2 += (size_t)lap * K.m; dx += (size_t)lap * K.n; dy += (size_t)lap * K.m;
-    double* vb = sm.rowbuf;            // b_j / w (NB)
-    double* vy = sm.rowbuf + KLD;      // y_j / z_{j-1}
-    double* z0 = sm.aq;                // z_0 (NB)
     const int AQ = K.NINEQ * (NV + 1);
 
-    // condensed right-hand side of stage j (before the updates from later stages)
+    // condensed right-hand side of stage j (before the updates from later stages); threads t < NB
     auto rhs = [&](int j) -> double {
         const int e = St::e_in(K, j);
         double b = 0.0;
-        if (lane < NV)
+        if (t < NV)
         {
-            b = r1[(size_t)j * NV + lane];
-            for (int t = 0; t < K.NINEQ; ++t)
-                b += gA[(size_t)j * AQ + t * NV + lane] * gA[(size_t)j * AQ + K.NINEQ * NV + t] * r2[(size_t)e * K.NCPE + K.t.ineq_rows[t]];
+            b = r1[(size_t)j * NV + t];
+            for (int q = 0; q < K.NINEQ; ++q)
+                b += gA[(size_t)j * AQ + q * NV + t] * gA[(size_t)j * AQ + K.NINEQ * NV + q] * r2[(size_t)e * K.NCPE + K.t.ineq_rows[q]];
         }
-        else if (lane < NB) b = r2[(size_t)e * K.NCPE + K.t.eq_rows[lane - NV]];
+        else if (t < NB) b = r2[(size_t)e * K.NCPE + K.t.eq_rows[t - NV]];
         return b;
     };
+    double dreg[CB], freg[CB], lreg[CB];
+    auto load_rows = [&](const double* g, int j, double* reg) {            // reg[i] = G_j[lane][w + KW i]
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int c = w + KW * i; reg[i] = (lane < NB && c < NB) ? g[(size_t)j * NB * NB + lane + NB * c] : 0.0; }
+    };
+    auto load_LT = [&](int j, double* reg) {                               // reg[i] = L_j[w + KW i][lane]  (lane < NV)
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int k = w + KW * i; reg[i] = (lane < NV && k < NB) ? gL[(size_t)j * NB * NV + k + NB * lane] : 0.0; }
+    };
 
-    double carry = 0.0;                // update of stage j-1's x rows from stage j
-    double b0 = 0.0;                   // updates of stage 0 through the fill blocks
+    // ---- forward: y_j = Dinv_j b_j,  b_{j-1} -= L_j^T y_j,  b_0 -= F_j y_j
+    double carry = 0.0, b0 = 0.0;            // held by threads t < NV / t < NB
+    if (S > 1) { load_rows(gD, S - 1, dreg); if (cyc) load_rows(gF, S - 1, freg); load_LT(S - 1, lreg); }
     for (int j = S - 1; j >= 1; --j)
     {
         const bool chain = j >= 2 || !cyc;
-        const double b = rhs(j) + carry;
-        if (lane < NB) vb[lane] = b;
-        __syncwarp();
-        double y = 0.0;
-        if (lane < NB)
-            for (int k = 0; k < NB; ++k) y += gD[(size_t)j * NB * NB + lane + NB * k] * vb[k];
-        if (lane < NB) { vy[lane] = y; yw[(size_t)j * NB + lane] = y; }
-        __syncwarp();
-        carry = 0.0;
-        if (chain)
+        if (t < NB) vb[t] = rhs(j) + carry;
+        __syncthreads();
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int k = w + KW * i; if (k < NB) a += dreg[i] * vb[k]; }
+        part[0][w][lane] = a;
+        double dn[CB], fnx[CB], ln[CB];
+        if (j >= 2) { load_rows(gD, j - 1, dn); if (cyc) load_rows(gF, j - 1, fnx); load_LT(j - 1, ln); }
+        __syncthreads();
+        if (t < NB)
         {
-            St::gather_coupling(K, lap, j, sm.L);
-            if (lane < NV)
-                for (int k = 0; k < NB; ++k) carry -= KM(sm.L, k, lane) * vy[k];
+            double y = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < KW; ++ww) y += part[0][ww][t];
+            vy[t] = y; yw[(size_t)j * NB + t] = y;
         }
-        if (cyc && lane < NB)
-            for (int k = 0; k < NB; ++k) b0 -= gF[(size_t)j * NB * NB + lane + NB * k] * vy[k];
-        __syncwarp();
+        __syncthreads();
+        double c1 = 0.0, c2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < CB; ++i)
+        {
+            const int k = w + KW * i;
+            if (k < NB) { if (chain) c1 += lreg[i] * vy[k]; if (cyc) c2 += freg[i] * vy[k]; }
+        }
+        part[1][w][lane] = c1; part[2][w][lane] = c2;
+        __syncthreads();
+        if (t < NB)
+        {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < KW; ++ww) { s1 += part[1][ww][t]; s2 += part[2][ww][t]; }
+            carry = (t < NV) ? -s1 : 0.0;
+            b0 -= s2;
+        }
+        if (j >= 2)
+        {
+#pragma unroll
+            for (int i = 0; i < CB; ++i) { dreg[i] = dn[i]; freg[i] = fnx[i]; lreg[i] = ln[i]; }
+        }
+        __syncthreads();
     }
     {
-        const double b = rhs(0) + carry + b0;
-        if (lane < NB) vb[lane] = b;
-        __syncwarp();
-        double z = 0.0;
-        if (lane < NB)
-            for (int k = 0; k < NB; ++k) z += gD[lane + NB * k] * vb[k];
-        if (lane < NB) { z0[lane] = z; vy[lane] = z; yw[lane] = z; }
-        __syncwarp();
+        load_rows(gD, 0, dreg);
+        if (t < NB) vb[t] = rhs(0) + carry + b0;
+        __syncthreads();
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int k = w + KW * i; if (k < NB) a += dreg[i] * vb[k]; }
+        part[0][w][lane] = a;
+        __syncthreads();
+        if (t < NB)
+        {
+            double z = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < KW; ++ww) z += part[0][ww][t];
+            z0[t] = z; vy[t] = z; yw[t] = z;
+        }
+        __syncthreads();
     }
+    // ---- backward: z_j = y_j - Dinv_j (L_j z_{j-1} + F_j^T z_0)
+    auto load_L = [&](int j, double* reg) {                                // reg[i] = L_j[lane][w + KW i]
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int c = w + KW * i; reg[i] = (lane < NB && c < NV) ? gL[(size_t)j * NB * NV + lane + NB * c] : 0.0; }
+    };
+    auto load_FT = [&](int j, double* reg) {                               // reg[i] = F_j[w + KW i][lane]
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int k = w + KW * i; reg[i] = (lane < NB && k < NB) ? gF[(size_t)j * NB * NB + k + NB * lane] : 0.0; }
+    };
+    if (S > 1) { load_rows(gD, 1, dreg); load_L(1, lreg); if (cyc) load_FT(1, freg); }
     for (int j = 1; j < S; ++j)
     {
         const bool chain = j >= 2 || !cyc;
-        // w = L_j z_{j-1} + F_j^T z_0
-        double w = 0.0;
-        if (chain)
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < CB; ++i)
         {
-            St::gather_coupling(K, lap, j, sm.L);
-            if (lane < NB)
-                for (int c = 0; c < NV; ++c) w += KM(sm.L, lane, c) * vy[c];
+            const int c = w + KW * i;
+            if (chain && c < NV) a += lreg[i] * vy[c];
+            if (cyc && c < NB) a += freg[i] * z0[c];
         }
-        if (cyc && lane < NB)
-            for (int k = 0; k < NB; ++k) w += gF[(size_t)j * NB * NB + k + NB * lane] * z0[k];
-        __syncwarp();
-        if (lane < NB) vb[lane] = w;
-        __syncwarp();
-        double z = 0.0;
-        if (lane < NB)
+        part[0][w][lane] = a;
+        double dn[CB], fnx[CB], ln[CB];
+        if (j + 1 < S) { load_rows(gD, j + 1, dn); load_L(j + 1, ln); if (cyc) load_FT(j + 1, fnx); }
+        const double yj = (t < NB) ? yw[(size_t)j * NB + t] : 0.0;
+        __syncthreads();
+        if (t < NB)
         {
-            z = yw[(size_t)j * NB + lane];
-            for (int k = 0; k < NB; ++k) z -= gD[(size_t)j * NB * NB + lane + NB * k] * vb[k];
+            double s1 = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < KW; ++ww) s1 += part[0][ww][t];
+            vb[t] = s1;
         }
-        __syncwarp();
-        if (lane < NB) { vy[lane] = z; yw[(size_t)j * NB + lane] = z; }
-        __syncwarp();
+        __syncthreads();
+        double b = 0.0;
+#pragma unroll
+        for (int i = 0; i < CB; ++i) { const int k = w + KW * i; if (k < NB) b += dreg[i] * vb[k]; }
+        part[1][w][lane] = b;
+        __syncthreads();
+        if (t < NB)
+        {
+            double z = yj;
+#pragma unroll
+            for (int ww = 0; ww < KW; ++ww) z -= part[1][ww][t];
+            vy[t] = z; yw[(size_t)j * NB + t] = z;
+        }
+        if (j + 1 < S)
+        {
+#pragma unroll
+            for (int i = 0; i < CB; ++i) { dreg[i] = dn[i]; freg[i] = fnx[i]; lreg[i] = ln[i]; }
+        }
+        __syncthreads();
     }
-    // scatter: dx, equality multipliers, then the condensed inequality multipliers dy_t = (a_t . dx_j - r2_t) / D_t
-    for (int j = 0; j < S; ++j)
+    // ---- scatter: dx, equality multipliers, then the condensed inequality multipliers dy_q = (a_q . dx_j - r2_q) / D_q
+    for (int j = w; j < S; j += KW)
     {
         const int e = St::e_in(K, j);
         const double z = (lane < NB) ? yw[(size_t)j * NB + lane] : 0.0;
         if (lane < NV) dx[(size_t)j * NV + lane] = z;
         else if (lane < NB) dy[(size_t)e * K.NCPE + K.t.eq_rows[lane - NV]] = z;
-        for (int t = 0; t < K.NINEQ; ++t)
+        for (int q = 0; q < K.NINEQ; ++q)
         {
-            double a = (lane < NV) ? gA[(size_t)j * AQ + t * NV + lane] * z : 0.0;
+            double a = (lane < NV) ? gA[(size_t)j * AQ + q * NV + lane] * z : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
             if (lane == 0)
             {
-                const int row = e * K.NCPE + K.t.ineq_rows[t];
-                dy[row] = (a - r2[row]) * gA[(size_t)j * AQ + K.NINEQ * NV + t];
+                const int row = e * K.NCPE + K.t.ineq_rows[q];
+                dy[row] = (a - r2[row]) * gA[(size_t)j * AQ + K.NINEQ * NV + q];
             }
         }
     }
