@@ -193,6 +193,55 @@ def batched_leg(args, torch, dist, world, rank, local, peak):
     return res
 
 
+N_SOLVE = 256
+
+
+def solve_leg(args, torch, dist, world, rank, local):
+    """Batched laps/s: `--solve-laps` independent F1 laps (Catalunya, 500 nodes, perturbed vehicles, configs[4] scaled to a
+    default bench run) solved to Ipopt's tolerances by the device interior-point solver from the reference's starting point
+    (steady state at 50 km/h replicated).  Sharded contiguously over the ranks; one final all_gather of (lap time, status,
+    iterations).  Timed end to end through the public API: host start point in, host solution out."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    from fastest_lap_b200.sharding import shard_range, gather_results
+    from fastest_lap_b200.vehicle import MODEL_F1
+    p = workloads.f1_catalunya(500)
+    lo, hi = shard_range(args.solve_laps, world, rank)
+    B = hi - lo
+    params = workloads.sweep_parameters(MODEL_F1, args.solve_laps)
+    params[0] = p.params                                     # lap 0 drives the reference vehicle (known answer)
+    nlp = CollocationNLP(p, vehicle_params=params[lo:hi], device=local)
+    solver = LapSolver(nlp)
+    x0 = workloads.f1_start_point(p, 50.0)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = solver.solve(x0)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall, out["device_ms"]], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, dev_ms = [float(v) for v in t.tolist()]
+    times = np.array([lap_time(p, out["x"][b], out["obj"][b]) for b in range(B)])
+    local_res = np.stack([times, out["status"].astype(np.float64), out["iters"].astype(np.float64)], axis=1)
+    res = gather_results(local_res, args.solve_laps)          # the final gather of per-lap results
+    ok = res[:, 1] == 1
+    st = out["stats"]
+    golden = 77.791438
+    r = {"workload": "%d independent limebeer-2014-f1 laps, Catalunya, 500 nodes, closed, direct form, vehicles drawn per lap (rng 2), start = steady state at 50 km/h; "
+                     "tol 1e-10 (the reference's Ipopt options); contiguous shards over %d GPU(s)" % (args.solve_laps, world),
+         "laps": args.solve_laps, "laps_per_gpu": B, "scaling": "strong", "value": args.solve_laps / wall, "unit": "laps/s", "seconds": wall, "device_ms": dev_ms,
+         "converged": int(ok.sum()), "not_converged": int((~ok).sum()), "iterations_median": float(np.median(res[:, 2])), "iterations_max": float(res[:, 2].max()),
+         "lap0_time_s": float(res[0, 0]), "lap0_reference_s": golden, "lap0_rel_err": abs(float(res[0, 0]) - golden) / golden,
+         "lap_time_range_s": [float(res[ok, 0].min()), float(res[ok, 0].max())] if ok.any() else None,
+         "rank0_launches": st, "reference_cpu": "Ipopt+MUMPS in the reference: 82.7 s for a 697-node lap (docs quickstart.rst:134), about 1 lap/minute/core"}
+    solver.close(); nlp.close()
+    return r
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,7 +250,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--nodes", type=int, default=N_NODES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--laps", type=int, default=N_LAPS, help="laps of the batched leg (0 = skip)")
+    ap.add_argument("--laps", type=int, default=N_LAPS, help="laps of the batched callback leg (0 = skip)")
+    ap.add_argument("--solve-laps", type=int, default=N_SOLVE, help="laps solved to convergence in the laps/s leg (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -326,6 +376,11 @@ def main():
         if rank == 0:
             line["batched"] = b
             line["gpu_launches"] += b["gpu_launches"]
+    if args.solve_laps > 0:
+        sl = solve_leg(args, torch, dist, world, rank, local)
+        if rank == 0:
+            line["batched_solve"] = sl
+            line["gpu_launches"] += int(sl["rank0_launches"]["solver_launches"]) + 3 * int(sl["rank0_launches"]["full_rounds"]) + 2 * int(sl["rank0_launches"]["fg_rounds"])
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

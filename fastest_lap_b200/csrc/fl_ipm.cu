@@ -104,13 +104,14 @@ int kkt_solve(fl_ipm* s, const int* active, int ls_mode, const double* r1, const
 }
 
 // solve K (tx, ty) = (I.r1, I.r2) with iterative refinement on the full augmented system; result into (ox, oy)
-int solve_refined(fl_ipm* s, const int* active, int ls_mode, double* ox, double* oy)
+int solve_refined(fl_ipm* s, const int* active, int ls_mode, double* ox, double* oy, int refine_steps = -1)
 {
     const fl_ipm_dev& I = s->I;
     cudaStream_t st = s->nlp->stream;
     if (!kkt_solve(s, active, ls_mode, I.r1, I.r2, s->wx, s->wy)) return 0;
     k_ipm_axpy_sol<<<s->B, IPM_BLOCK, 0, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 1);
-    for (int k = 0; k < I.o.refine_steps; ++k)
+    if (refine_steps < 0) refine_steps = I.o.refine_steps;
+    for (int k = 0; k < refine_steps; ++k)
     {
         k_ipm_residual<<<s->B, IPM_BLOCK, 0, st>>>(I, active, ls_mode);
         if (!kkt_solve(s, active, ls_mode, I.e1, I.e2, s->wx, s->wy)) return 0;
@@ -149,7 +150,7 @@ void fl_ipm_default_options(fl_ipm_opts* o)
     o->gamma_theta = 1.0e-5; o->gamma_phi = 1.0e-8; o->delta = 1.0; o->s_theta = 1.1; o->s_phi = 2.3; o->eta_phi = 1.0e-8;
     o->kappa_soc = 0.99; o->alpha_red = 0.5; o->max_soc = 4; o->max_backtracks = 40;
     o->delta_w_min = 1.0e-20; o->delta_w_0 = 1.0e-4; o->delta_w_max = 1.0e40; o->kappa_w_minus = 1.0 / 3.0; o->kappa_w_plus = 8.0;
-    o->kappa_w_plus_bar = 100.0; o->delta_c_bar = 1.0e-8; o->kappa_c = 0.25; o->y_init_max = 1.0e3; o->refine_steps = 2;
+    o->kappa_w_plus_bar = 100.0; o->delta_c_bar = 1.0e-8; o->kappa_c = 0.25; o->y_init_max = 1.0e3; o->refine_steps = 1;
 }
 
 void fl_ipm_destroy(fl_ipm* s)
@@ -358,7 +359,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
             if (cnt[3] > 0)
             {
                 k_ipm_rhs<<<B, IPM_BLOCK, 0, st>>>(I, 1);
-                if (!solve_refined(s, I.act_soc, 0, I.dxs, I.dys)) return 0;
+                if (!solve_refined(s, I.act_soc, 0, I.dxs, I.dys, 0)) return 0;
                 k_ipm_soc_direction<<<B, IPM_BLOCK, 0, st>>>(I);
                 s->launches += 2;
             }

@@ -19,7 +19,7 @@
 #include "kkt_kernels.cuh"
 
 constexpr int IPM_BLOCK = 128;
-constexpr int IPM_NVMAX = 17, IPM_NCPEMAX = 21;
+constexpr int IPM_NVMAX = 17, IPM_NCPEMAX = 21, IPM_MAX_RESTARTS = 3;
 
 struct fl_ipm_dev
 {
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_direction(const fl_ipm_dev I)
     const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
     if (threadIdx.x == 0)
     {
-        L.alpha_max = amax; L.alpha = amax; L.alpha_dual = adual; L.dphi = dphi; L.n_backtrack = 0; L.n_soc = 0; L.soc_step = 0;
+        L.alpha_max = amax; L.alpha = amax; L.alpha_dual = adual; L.dphi = dphi; L.n_backtrack = 0; L.n_soc = 0;
         if (badf > 0.0) { L.status = IPM_NOT_FINITE; I.act_run[lap] = 0; L.ls = LS_IDLE; }
         else { L.ls = LS_TRIAL; atomicAdd(I.counters + 2, 1); }
     }
@@ -598,9 +598,25 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
     }
     else
     {
-        // failure: restore the iterate in the NLP's buffers
+        // The line search found no acceptable step.  Ipopt would enter its restoration phase here; this solver restores
+        // the iterate in the NLP's buffers and restarts the barrier problem from a larger mu with an empty filter (at
+        // most IPM_MAX_RESTARTS times per lap), which moves the iterate back towards the central path.
         for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.nx[on + i] = I.x[on + i];
-        if (threadIdx.x == 0) { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; I.act_soc[lap] = 0; }
+        if (threadIdx.x == 0)
+        {
+            I.act_soc[lap] = 0;
+            if (L.soc_step < IPM_MAX_RESTARTS)
+            {
+                L.soc_step += 1;                       // restarts so far
+                L.mu = fmin(I.o.mu_init, fmax(10.0 * L.mu, 1.0e-6));
+                L.tau = fmax(I.o.tau_min, 1.0 - L.mu);
+                L.n_filter = 0;
+                L.theta_max = 1.0e4 * fmax(1.0, L.theta); L.theta_min = 1.0e-4 * fmax(1.0, L.theta);
+                L.acc_count = 0;
+                L.ls = LS_DONE; L.iter += 1;
+            }
+            else { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; }
+        }
     }
 }
 

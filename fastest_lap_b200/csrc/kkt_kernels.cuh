@@ -91,133 +91,114 @@ __device__ __forceinline__ void kkt_warp_argmax(double& v, int& idx)
     }
 }
 
-struct kkt_pivot            // decision of one Gauss-Jordan step, written by warp 0, read by the whole block
-{
-    int two, p, q, done;
-    double pv, i00, i01, i10, i11;
-};
+// magnitude of v as an order-preserving 27-bit key with the lane in the low bits: one REDUX gives arg max |v| over a warp
+// (ties and magnitudes closer than 2^-15 relative go to the lowest lane; pivoting decisions do not need more)
+__device__ __forceinline__ unsigned kkt_key(double v, int lane) { return ((unsigned)__double2hiint(fabs(v)) & ~31u) | (unsigned)(31 - lane); }
+__device__ __forceinline__ double kkt_key_value(unsigned key) { return __hiloint2double((int)(key & ~31u), 0); }
 
-// In-place inverse of the symmetric NB x NB matrix M (shared memory, both triangles stored) by Gauss-Jordan sweeps with
-// Bunch-Parlett pivoting; the whole block takes part.  rowbuf / colbuf: 2 * KLD doubles each.  Thread 0 accumulates the
-// number of negative and vanishing pivots.
+// Inverse of the symmetric NB x NB matrix in A (shared memory, both triangles stored) by Gauss-Jordan sweeps with
+// Bunch-Parlett pivoting.  Every sweep rewrites the whole matrix, so the sweeps ping-pong between A and B (one barrier
+// per sweep); every warp takes the same pivoting decision from the same data.  Thread (lane r, warp w) owns row r and
+// the columns w, w + KW, ...  Returns the buffer holding the inverse; thread 0 accumulates the pivot counts.
 template <int NB>
-__device__ __forceinline__ void kkt_invert(double* M, double* rowbuf, double* colbuf, kkt_pivot* pv_s, int& n_neg, int& n_zero)
+__device__ __forceinline__ double* kkt_invert(double* A, double* B, int& n_neg, int& n_zero)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int CB = (NB + KW - 1) / KW;
     const double ALPHA = 0.6403882032022076;              // (1 + sqrt(17)) / 8
     unsigned swept = 0u;
     const unsigned all = (NB == 32) ? 0xffffffffu : ((1u << NB) - 1u);
+    double* M = A;
+    double* N = B;
     while (swept != all)
     {
-        if (w == 0)
+        const bool mine = lane < NB && !((swept >> lane) & 1u);
+        const unsigned kd = __reduce_max_sync(0xffffffffu, mine ? kkt_key(KM(M, lane, lane), lane) : 0u);
+        int p = 31 - (int)(kd & 31u), q = p;
+        const double dmax = kkt_key_value(kd);
+        const unsigned kl = __reduce_max_sync(0xffffffffu, (mine && lane != p) ? kkt_key(KM(M, lane, p), lane) : 0u);
+        const double lam = kkt_key_value(kl);
+        bool two = false;
+        if (!(dmax >= ALPHA * lam && dmax > 0.0))
         {
-            const bool mine = lane < NB && !((swept >> lane) & 1u);
-            double dmax = mine ? fabs(KM(M, lane, lane)) : -1.0;
-            int k = lane;
-            kkt_warp_argmax(dmax, k);
-            const double lam = kkt_warp_max((mine && lane != k) ? fabs(KM(M, lane, k)) : 0.0);
-            bool two = false;
-            int p = k, q = k;
-            if (!(dmax >= ALPHA * lam && dmax > 0.0))
-            {
-                // largest off-diagonal entry of the unswept part
-                double best = -1.0;
-                int bc = 0;
-                if (mine)
-                    for (int c = 0; c < NB; ++c)
-                        if (c != lane && !((swept >> c) & 1u))
-                        {
-                            const double a = fabs(KM(M, lane, c));
-                            if (a > best) { best = a; bc = c; }
-                        }
-                int br = lane;
-                double mu0 = best;
-                kkt_warp_argmax(mu0, br);
-                bc = __shfl_sync(0xffffffffu, bc, br);
-                if (mu0 > 0.0 && !(dmax >= ALPHA * mu0)) { two = true; p = br; q = bc; }
-            }
-            if (!two)
-            {
-                double d = KM(M, k, k);
-                if (d == 0.0) { d = 1.0e-300; if (lane == 0) ++n_zero; }
-                if (lane == 0 && d < 0.0) ++n_neg;
-                const double pv = 1.0 / d;
-                if (lane < NB) { rowbuf[lane] = KM(M, k, lane) * pv; colbuf[lane] = KM(M, lane, k); }
-                if (lane == 0) { pv_s->two = 0; pv_s->p = k; pv_s->q = k; pv_s->pv = pv; }
-            }
-            else
-            {
-                const double a = KM(M, p, p), b = KM(M, p, q), b2 = KM(M, q, p), c2 = KM(M, q, q);
-                const double det = a * c2 - b * b2;
-                if (lane == 0) n_neg += (det < 0.0) ? 1 : ((a < 0.0) ? 2 : 0);
-                const double i00 = c2 / det, i01 = -b / det, i10 = -b2 / det, i11 = a / det;
-                if (lane < NB)
-                {
-                    const double mp = KM(M, p, lane), mq = KM(M, q, lane);
-                    rowbuf[lane] = i00 * mp + i01 * mq;
-                    rowbuf[KLD + lane] = i10 * mp + i11 * mq;
-                    colbuf[lane] = KM(M, lane, p);
-                    colbuf[KLD + lane] = KM(M, lane, q);
-                }
-                if (lane == 0) { pv_s->two = 1; pv_s->p = p; pv_s->q = q; pv_s->i00 = i00; pv_s->i01 = i01; pv_s->i10 = i10; pv_s->i11 = i11; }
-            }
+            // largest off-diagonal entry of the unswept part
+            double best = 0.0;
+            int bc = 0;
+            if (mine)
+                for (int c = 0; c < NB; ++c)
+                    if (c != lane && !((swept >> c) & 1u))
+                    {
+                        const double a = fabs(KM(M, lane, c));
+                        if (a > best) { best = a; bc = c; }
+                    }
+            const unsigned km = __reduce_max_sync(0xffffffffu, mine ? kkt_key(best, lane) : 0u);
+            const int br = 31 - (int)(km & 31u);
+            const double mu0 = kkt_key_value(km);
+            bc = __shfl_sync(0xffffffffu, bc, br);
+            if (mu0 > 0.0 && !(dmax >= ALPHA * mu0)) { two = true; p = br; q = bc; }
         }
-        __syncthreads();
-        const int two = pv_s->two, p = pv_s->p, q = pv_s->q;
-        if (lane < NB)
+        if (!two)
         {
-            if (!two)
+            double d = KM(M, p, p);
+            if (d == 0.0) { d = 1.0e-300; if (threadIdx.x == 0) ++n_zero; }
+            if (threadIdx.x == 0 && d < 0.0) ++n_neg;
+            const double pv = 1.0 / d;
+            if (lane < NB)
             {
-                const double pv = pv_s->pv, f = colbuf[lane];
+                const double f = KM(M, lane, p);
                 if (lane != p)
                 {
 #pragma unroll
-                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
+                    for (int i = 0; i < CB; ++i)
                     {
                         const int c = w + KW * i;
-                        if (c < NB) KM(M, lane, c) = (c == p) ? -f * pv : KM(M, lane, c) - f * rowbuf[c];
+                        if (NB % KW == 0 || c < NB) KM(N, lane, c) = KM(M, lane, c) - f * (KM(M, p, c) * pv);
                     }
+                    if ((p & (KW - 1)) == w) KM(N, lane, p) = -f * pv;
                 }
                 else
                 {
 #pragma unroll
-                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
+                    for (int i = 0; i < CB; ++i)
                     {
                         const int c = w + KW * i;
-                        if (c < NB) KM(M, lane, c) = (c == p) ? pv : rowbuf[c];
+                        if (NB % KW == 0 || c < NB) KM(N, p, c) = KM(M, p, c) * pv;
                     }
+                    if ((p & (KW - 1)) == w) KM(N, p, p) = pv;
                 }
             }
-            else
-            {
-                const double i00 = pv_s->i00, i01 = pv_s->i01, i10 = pv_s->i10, i11 = pv_s->i11;
-                const double fp = colbuf[lane], fq = colbuf[KLD + lane];
-                if (lane != p && lane != q)
-                {
-#pragma unroll
-                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
-                    {
-                        const int c = w + KW * i;
-                        if (c < NB)
-                            KM(M, lane, c) = (c == p) ? -(fp * i00 + fq * i10) : (c == q) ? -(fp * i01 + fq * i11)
-                                                      : KM(M, lane, c) - fp * rowbuf[c] - fq * rowbuf[KLD + c];
-                    }
-                }
-                else
-                {
-                    const double* rb = rowbuf + (lane == p ? 0 : KLD);
-#pragma unroll
-                    for (int i = 0; i < (NB + KW - 1) / KW; ++i)
-                    {
-                        const int c = w + KW * i;
-                        if (c < NB) KM(M, lane, c) = (c == p) ? ((lane == p) ? i00 : i10) : (c == q) ? ((lane == p) ? i01 : i11) : rb[c];
-                    }
-                }
-            }
+            swept |= 1u << p;
         }
-        swept |= two ? ((1u << p) | (1u << q)) : (1u << p);
+        else
+        {
+            const double a = KM(M, p, p), b = KM(M, p, q), b2 = KM(M, q, p), c2 = KM(M, q, q);
+            const double det = a * c2 - b * b2;
+            if (threadIdx.x == 0) n_neg += (det < 0.0) ? 1 : ((a < 0.0) ? 2 : 0);
+            const double i00 = c2 / det, i01 = -b / det, i10 = -b2 / det, i11 = a / det;
+            if (lane < NB)
+            {
+                const double fp = KM(M, lane, p), fq = KM(M, lane, q);
+                const bool piv_row = lane == p || lane == q;
+#pragma unroll
+                for (int i = 0; i < CB; ++i)
+                {
+                    const int c = w + KW * i;
+                    if (NB % KW == 0 || c < NB)
+                    {
+                        const double mp = KM(M, p, c), mq = KM(M, q, c);
+                        const double rp = i00 * mp + i01 * mq, rq = i10 * mp + i11 * mq;
+                        KM(N, lane, c) = piv_row ? (lane == p ? rp : rq) : KM(M, lane, c) - fp * rp - fq * rq;
+                    }
+                }
+                if ((p & (KW - 1)) == w) KM(N, lane, p) = piv_row ? (lane == p ? i00 : i10) : -(fp * i00 + fq * i10);
+                if ((q & (KW - 1)) == w) KM(N, lane, q) = piv_row ? (lane == p ? i01 : i11) : -(fp * i01 + fq * i11);
+            }
+            swept |= (1u << p) | (1u << q);
+        }
         __syncthreads();
+        double* tmp = M; M = N; N = tmp;
     }
+    return M;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -317,9 +298,9 @@ template <int NV, int NEQ>
 struct kkt_smem
 {
     static constexpr int NB = NV + NEQ;
-    double M[KLD * NB], F[KLD * NB], XF[KLD * NB], L[KLD * NV], XL[KLD * NV], P[KLD * NV];
-    double aq[8 * KLD], rowbuf[2 * KLD], colbuf[2 * KLD];
-    kkt_pivot piv;
+    double M[KLD * NB], M2[KLD * NB], F[KLD * NB], XF[KLD * NB], L[KLD * NV], XL[KLD * NV], P[KLD * NV];
+    double aq[8 * KLD];
+    double dw_next;
     int flag;
 };
 
@@ -403,7 +384,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                 __syncthreads();
             }
             const int neg_before = n_neg, zero_before = n_zero;
-            kkt_invert<NB>(sm.M, sm.rowbuf, sm.colbuf, &sm.piv, n_neg, n_zero);
+            const double* Mi = kkt_invert<NB>(sm.M, sm.M2, n_neg, n_zero);
             if (Lp)
             {
                 // every pivot block carries exactly NEQ negative pivots when the reduced Hessian is positive definite
@@ -416,7 +397,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
             if (lane < NB)
             {
 #pragma unroll
-                for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) gD[(size_t)j * NB * NB + lane + NB * c] = KM(sm.M, lane, c); }
+                for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) gD[(size_t)j * NB * NB + lane + NB * c] = KM(Mi, lane, c); }
                 if (cyc && j >= 1)
                 {
 #pragma unroll
@@ -435,7 +416,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
 #pragma unroll 4
                     for (int k = 0; k < NB; ++k)
                     {
-                        const double a = KM(sm.M, lane, k);
+                        const double a = KM(Mi, lane, k);
 #pragma unroll
                         for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.L, k, c); }
                     }
@@ -450,7 +431,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
 #pragma unroll 4
                     for (int k = 0; k < NB; ++k)
                     {
-                        const double a = KM(sm.M, lane, k);
+                        const double a = KM(Mi, lane, k);
 #pragma unroll
                         for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) acc[i] += a * KM(sm.F, c, k); }
                     }
@@ -532,13 +513,13 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                 else dw *= (Lp->dw_last == 0.0) ? o.kappa_w_plus_bar : o.kappa_w_plus;
                 if (dw > o.delta_w_max) { Lp->status = IPM_REGULARISATION_FAILED; sm.flag = 2; }
                 else sm.flag = 0;
-                sm.rowbuf[0] = dw;
+                sm.dw_next = dw;
             }
         }
         __syncthreads();
         const int fl = sm.flag;
         if (fl != 0) return;
-        dw = sm.rowbuf[0];
+        dw = sm.dw_next;
         __syncthreads();
     }
 }

@@ -16,11 +16,11 @@ cyclic for closed laps -- with blocks of NV + n_eq (28 for the F1 direct form). 
 backwards (the order of a Riccati recursion: the Schur complement handed to stage j-1 is the cost-to-go Hessian of node
 j-1), stage 0 last; the closing element of a closed lap makes every stage couple with stage 0 through a fill block F_j.
 
+Every pivot block is inverted by Gauss-Jordan sweeps with Bunch-Parlett pivoting, which also counts negative pivots.
 Inertia: by Haynsworth additivity the inertia of the whole matrix is the sum of the inertias of the pivot blocks, so the
 factorisation reports exactly what Ipopt asks of MUMPS (n positive, m negative eigenvalues, none zero).
 """
 import numpy as np
-import scipy.linalg as sla
 import scipy.sparse as sp
 
 
@@ -106,11 +106,63 @@ def expand_solution(lay, J, D, r2, z):
     return dx, dy
 
 
-def _inertia(ldl_d):
-    """(#positive, #negative, #zero) of the block-diagonal factor of scipy.linalg.ldl."""
-    w = np.linalg.eigvalsh(ldl_d)
-    tol = 1e-300
-    return int(np.sum(w > tol)), int(np.sum(w < -tol)), int(np.sum(np.abs(w) <= tol))
+ALPHA = (1.0 + 17.0 ** 0.5) / 8.0
+
+
+def pivoted_gauss_jordan(A):
+    """In-place style inverse of a symmetric matrix by Gauss-Jordan sweeps with Bunch-Parlett pivoting (1x1 pivots on the
+    largest diagonal entry of the unswept part, 2x2 pivots when the diagonal is weak).  Returns (inverse, number of
+    negative pivots, number of vanishing pivots): the statement of kkt_invert in csrc/kkt_kernels.cuh."""
+    M = np.array(A, dtype=float)
+    n = len(M)
+    swept = np.zeros(n, bool)
+    neg = zero = 0
+    while not swept.all():
+        un = np.where(~swept)[0]
+        dv = np.abs(M[un, un])
+        k = un[np.argmax(dv)]
+        dmax = dv.max()
+        others = un[un != k]
+        lam = np.max(np.abs(M[others, k])) if len(others) else 0.0
+        two = False
+        if not (dmax >= ALPHA * lam and dmax > 0.0):
+            sub = np.abs(M[np.ix_(un, un)])
+            np.fill_diagonal(sub, -1.0)
+            mu0 = sub.max() if len(un) > 1 else -1.0
+            if mu0 > 0.0 and not (dmax >= ALPHA * mu0):
+                ip, iq = np.unravel_index(np.argmax(sub), sub.shape)       # first maximum in row-major order
+                p, q = un[ip], un[iq]
+                two = True
+        if not two:
+            d = M[k, k]
+            if d == 0.0:
+                zero += 1
+                d = 1.0e-300
+            neg += d < 0.0
+            pv = 1.0 / d
+            rowk = M[k, :] * pv
+            col = M[:, k].copy()
+            M -= np.outer(col, rowk)
+            M[:, k] = -col * pv
+            M[k, :] = rowk
+            M[k, k] = pv
+            swept[k] = True
+        else:
+            a, b, b2, c = M[p, p], M[p, q], M[q, p], M[q, q]
+            det = a * c - b * b2
+            neg += 1 if det < 0.0 else (2 if a < 0.0 else 0)
+            Bi = np.array([[c, -b], [-b2, a]]) / det
+            rp = Bi[0, 0] * M[p, :] + Bi[0, 1] * M[q, :]
+            rq = Bi[1, 0] * M[p, :] + Bi[1, 1] * M[q, :]
+            fp, fq = M[:, p].copy(), M[:, q].copy()
+            M -= np.outer(fp, rp) + np.outer(fq, rq)
+            M[:, p] = -(fp * Bi[0, 0] + fq * Bi[1, 0])
+            M[:, q] = -(fp * Bi[0, 1] + fq * Bi[1, 1])
+            M[p, :] = rp
+            M[q, :] = rq
+            M[p, p], M[p, q], M[q, p], M[q, q] = Bi[0, 0], Bi[0, 1], Bi[1, 0], Bi[1, 1]
+            swept[p] = swept[q] = True
+    return M, int(neg), int(zero)
 
 
 class BlockCyclicLDL:
@@ -121,7 +173,7 @@ class BlockCyclicLDL:
         self.S, self.nb, self.cyclic = S, nb, bool(cyclic) and S > 1
         self.Lo = Lo
         self.F = np.zeros((S, nb, nb)) if self.cyclic else None      # F[j] = K[0, j] after fill, j >= 1
-        self.lu = [None] * S
+        self.Dinv = np.zeros((S, nb, nb))                             # explicit inverses of the pivot blocks
         self.XL = np.zeros((S, nb, nb))                               # D_j^{-1} L_j
         self.XF = np.zeros((S, nb, nb)) if self.cyclic else None      # D_j^{-1} F_j^T
         pos = neg = zero = 0
@@ -131,23 +183,19 @@ class BlockCyclicLDL:
             self.F[1] = self.F[1] + Lo[1].T
         for j in range(S - 1, -1, -1):
             Dj = 0.5 * (Dg[j] + Dg[j].T)
-            try:
-                _, d, _ = sla.ldl(Dj, lower=True)
-                p, q, z = _inertia(d)
-            except Exception:
-                p, q, z = 0, 0, nb
-            pos, neg, zero = pos + p, neg + q, zero + z
-            self.lu[j] = sla.lu_factor(Dj)
-            if not np.all(np.isfinite(self.lu[j][0])):
+            Di, q, z = pivoted_gauss_jordan(Dj)
+            pos, neg, zero = pos + nb - q - z, neg + q, zero + z
+            self.Dinv[j] = Di
+            if not np.all(np.isfinite(Di)):
                 self.ok = False
             if j == 0:
                 break
             if self.cyclic:
-                XF = sla.lu_solve(self.lu[j], self.F[j].T)
+                XF = Di @ self.F[j].T
                 self.XF[j] = XF
                 Dg[0] -= self.F[j] @ XF
             if j >= 2 or not self.cyclic:
-                XL = sla.lu_solve(self.lu[j], Lo[j])
+                XL = Di @ Lo[j]
                 self.XL[j] = XL
                 Dg[j - 1] -= Lo[j].T @ XL
                 if self.cyclic:
@@ -160,13 +208,13 @@ class BlockCyclicLDL:
         b = np.array(b, dtype=float)
         y = np.zeros_like(b)
         for j in range(S - 1, 0, -1):
-            y[j] = sla.lu_solve(self.lu[j], b[j])
+            y[j] = self.Dinv[j] @ b[j]
             if j >= 2 or not cyc:
                 b[j - 1] -= self.Lo[j].T @ y[j]
             if cyc:
                 b[0] -= self.F[j] @ y[j]
         z = np.zeros_like(b)
-        z[0] = sla.lu_solve(self.lu[0], b[0])
+        z[0] = self.Dinv[0] @ b[0]
         for j in range(1, S):
             z[j] = y[j]
             if j >= 2 or not cyc:

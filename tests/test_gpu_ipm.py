@@ -105,3 +105,38 @@ def test_cold_start_batch_of_laps():
     times = [lap_time(p, out["x"][b], out["obj"][b]) for b in range(4)]
     assert all(60.0 < t < 100.0 for t in times)
     solver.close(); nlp.close()
+
+
+def test_kart_lap_returns_to_the_reference_solution():
+    """Kart, Vendrell, 500 nodes, derivative form (vendrell_optimal.xml): warm start 0.01 % off the golden point (the kart lap has many local minima within 3e-4 of each other); the
+    objective of the converged lap equals the golden point's to 1e-6 relative and the states agree to 1e-4."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver
+    p, ex = load_golden("kart_vendrell")
+    rng = np.random.default_rng(0)
+    x0 = ex["x"] * (1 + 1.0e-4 * rng.standard_normal(p.n))
+    nlp = CollocationNLP(p)
+    f_gold = nlp.eval_all(ex["x"], want=("f",))["f"][0]
+    solver = LapSolver(nlp)
+    out = solver.solve(x0)
+    assert out["status"][0] == 1, out["status"]
+    assert abs(out["obj"][0] - f_gold) <= 1e-6 * abs(f_gold)
+    assert np.max(np.abs(out["x"][0] - ex["x"])) <= 1e-4 * max(1.0, np.max(np.abs(ex["x"])))
+    solver.close(); nlp.close()
+
+
+def test_open_section_returns_to_the_reference_solution():
+    """F1 chicane (open section, first node fixed; f1_optimal_laptime_catalunya_chicane.xml)."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver
+    p, ex = load_golden("f1_catalunya_chicane")
+    rng = np.random.default_rng(0)
+    x0 = ex["x"] * (1 + 0.01 * rng.standard_normal(p.n))
+    nlp = CollocationNLP(p)
+    f_gold = nlp.eval_all(ex["x"], want=("f",))["f"][0]
+    solver = LapSolver(nlp)
+    out = solver.solve(x0)
+    assert out["status"][0] == 1, out["status"]
+    assert abs(out["obj"][0] - f_gold) <= 1e-8 * abs(f_gold)
+    assert np.max(np.abs(out["x"][0] - ex["x"])) <= 1e-5
+    solver.close(); nlp.close()
