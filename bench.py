@@ -242,6 +242,38 @@ def solve_leg(args, torch, dist, world, rank, local):
     return r
 
 
+
+def gg_leg(args, torch, dist, world, rank, local):
+    """BASELINE.json configs[1]: roberto-lot-2016-kart G-G diagram sweep, 32 speeds x 64 lateral accelerations, maximum and
+    minimum longitudinal acceleration at each (plus the 0 g and maximum-lateral NLPs per speed), solved as batches of
+    one-node NLPs by the device interior-point solver.  Speeds are sharded over the ranks."""
+    from fastest_lap_b200 import gg, workloads
+    from fastest_lap_b200.sharding import shard_range, gather_results
+    params = workloads._vehicles()["roberto_lot_kart_2016"]
+    speeds = np.linspace(50.0, 120.0, args.gg_speeds) / 3.6
+    lo, hi = shard_range(args.gg_speeds, world, rank)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = gg.gg_diagram(params, speeds[lo:hi], n_lat=args.gg_lat, device=local)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    local_res = np.concatenate([r["ax_max"], r["ax_min"], r["ax_max_solved"].astype(float), r["ax_min_solved"].astype(float), r["ay_max"][:, None]], axis=1)
+    res = gather_results(local_res, args.gg_speeds)
+    L = args.gg_lat
+    n_nlp = args.gg_speeds * (2 * L + 2)
+    return {"workload": "roberto-lot-kart-2016 G-G diagram: %d speeds (50..120 km/h) x %d lateral accelerations x {max, min} longitudinal acceleration "
+                        "+ 0 g and maximum-lateral NLPs per speed; 8 variables, 6 equations, 6 tyre-slip rows each; speeds sharded over %d GPU(s)" % (args.gg_speeds, L, world),
+            "nlps": n_nlp, "value": n_nlp / wall, "unit": "NLPs/s", "seconds": wall, "solved_fraction_max": float(res[:, 2 * L:3 * L].mean()),
+            "solved_fraction_min": float(res[:, 3 * L:4 * L].mean()), "ay_max_range": [float(res[:, -1].min()), float(res[:, -1].max())],
+            "reference_cpu": "the reference solves these NLPs one after the other with Ipopt (steady_state.hpp:594-880), ~130 solves per speed"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,6 +284,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--laps", type=int, default=N_LAPS, help="laps of the batched callback leg (0 = skip)")
     ap.add_argument("--solve-laps", type=int, default=N_SOLVE, help="laps solved to convergence in the laps/s leg (0 = skip)")
+    ap.add_argument("--gg-speeds", type=int, default=32, help="speeds of the G-G sweep leg (0 = skip)")
+    ap.add_argument("--gg-lat", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -381,6 +415,10 @@ def main():
         if rank == 0:
             line["batched_solve"] = sl
             line["gpu_launches"] += int(sl["rank0_launches"]["solver_launches"]) + 3 * int(sl["rank0_launches"]["full_rounds"]) + 2 * int(sl["rank0_launches"]["fg_rounds"])
+    if args.gg_speeds > 0:
+        gl = gg_leg(args, torch, dist, world, rank, local)
+        if rank == 0:
+            line["gg_sweep"] = gl
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

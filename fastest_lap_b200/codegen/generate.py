@@ -42,6 +42,7 @@ VARIANTS = {
     "kart_derivative": Variant("kart", "derivative"),
     "kart_direct_torque": Variant("kart", "direct", direct_torque=True),
     "kart_derivative_torque": Variant("kart", "derivative", direct_torque=True),
+    "kart_steady": Variant("kart", "steady"),
 }
 
 

@@ -18,13 +18,16 @@ from . import models
 
 class Variant:
     def __init__(self, model, form, elevation=False, direct_torque=False):
-        assert model in ("f1", "kart") and form in ("direct", "derivative")
+        assert model in ("f1", "kart") and form in ("direct", "derivative", "steady")
+        assert form != "steady" or model == "kart"
         self.model, self.form, self.elevation, self.direct_torque = model, form, bool(elevation), bool(direct_torque)
         if model == "kart":
             assert not elevation, "lot2016kart rejects tracks with elevation (lot2016kart.h:63-68)"
 
     @property
     def name(self):
+        if self.form == "steady":
+            return "%s_steady" % self.model
         n = "%s_%s" % (self.model, self.form)
         if self.elevation:
             n += "_3d"
@@ -40,6 +43,9 @@ class NodeProgram:
         v = self.variant = variant
         g = self.g = Graph()
         S = lambda name, cls: E(g, g.sym(name, cls))
+        if v.form == "steady":
+            self._init_steady(S)
+            return
         deriv = v.form == "derivative"
 
         if v.model == "f1":
@@ -148,6 +154,59 @@ class NodeProgram:
                 phi = phi + self.lam_out[r] * rowsB[r]
         self.phi = phi
 
+        self._differentiate(rowsA, rowsB, fobj, phi, obj, diss if not deriv else None, ihin if not deriv else None)
+
+    def _init_steady(self, S):
+        """Steady-state (G-G diagram) NLP of the kart as a one-node "lap": lot2016kart::steady_state_equations
+        (src/core/vehicles/lot2016kart.h:124-182) behind the functors Solve / Max_lat_acc / Max_lon_acc / Min_lon_acc of
+        src/core/applications/steady_state.h:99-284, in the 8-variable layout of Max_lat_acc (steady_state.hpp:899):
+        x = [w_axle, z, phi, mu, psi, delta, ax, ay].  Per-problem data travel as extra parameters: speed, given ax / ay,
+        switches that make ax / ay a variable or a given value, and the objective weights (f = cax ax + cay ay).
+        The 6 equations are the node's "algebraic" rows, the 6 tyre-slip rows its inequality rows; there are no trapezoid
+        rows and no controls, and the element assembly's objective h * dt/ds carries f (h = 1)."""
+        g = self.g
+        self.param_names = models.KART_PARAMS + models.KART_HOST_PARAMS + ["diss0", "diss1"] + \
+            ["ss_v", "ss_ax", "ss_ay", "ss_free_ax", "ss_free_ay", "ss_cax", "ss_cay"]
+        self.n_fm, self.td_ids, self.alg_ids = 0, [], list(range(6))
+        self.n_td, self.n_alg, self.n_ext, self.n_ctrl_rows = 0, 6, 6, 0
+        self.ncpe, self.nv = 12, 8
+        self.ctrl_pos, self.dctrl_pos = [0, 0], []
+        self.x = [S("x%d" % k, "x") for k in range(self.nv)]
+        P = self.P = {n: S("p_" + n, "p") for n in self.param_names}
+        self.track_names = ["kz"]
+        self.geom_names = ["hin", "hout", "ihin", "ihout"]
+        self.lam_in = [S("lin%d" % r, "w") for r in range(self.ncpe)]
+        self.lam_out = [None] * self.ncpe
+        obj = S("obj", "w")
+        self.uprev, self.unext = [], []
+        x, v = self.x, P["ss_v"]
+        ax = x[6] * P["ss_free_ax"] + (1.0 - P["ss_free_ax"]) * P["ss_ax"]
+        ay = x[7] * P["ss_free_ay"] + (1.0 - P["ss_free_ay"]) * P["ss_ay"]
+        psi = x[4]
+        cps, sps = models.cos(psi), models.sin(psi)
+        zero = E(g, g.const(0.0))
+        q = [(x[0] + 1.0) * (v / 0.139), v * cps, -(v * sps), ay / v, x[1], x[2], x[3], zero, zero, zero, zero, zero, psi]
+        out = models.kart_model(q, [x[5], zero], P, None, direct_torque=True, curvilinear=False)
+        d = out["dstates"]
+        du, dv = d[1], d[2]
+        eqs = [d[7], d[3], d[8], d[9], du * sps + dv * cps, ax - du * cps + dv * sps]
+        kap, lam = out["kappa"], out["lam"]
+        ext = [kap[2], kap[3], lam[2], lam[3], lam[0], lam[1]]
+        fobj = x[6] * P["ss_cax"] + x[7] * P["ss_cay"]
+        self.Q, self.QD, self.ALG, self.EXT, self.CDOT, self.DTDS = [], [], eqs, ext, [], fobj
+        self.values = eqs + ext + [fobj]
+        self.value_names = ["ALG%d" % r for r in range(6)] + ["EXT%d" % r for r in range(6)] + ["DTDS"]
+        rowsA, rowsB = eqs + ext, [None] * 12
+        self.rowsA, self.rowsB, self.fobj = rowsA, rowsB, fobj
+        phi = obj * fobj
+        for r in range(self.ncpe):
+            phi = phi + self.lam_in[r] * rowsA[r]
+        self.phi = phi
+        self._differentiate(rowsA, rowsB, fobj, phi, obj, None, None)
+
+    def _differentiate(self, rowsA, rowsB, fobj, phi, obj, diss, ihin):
+        g = self.g
+        deriv = diss is None
         xs = [xx.i for xx in self.x]
         # Jacobian blocks (forward sweeps), gradient of f
         fw = []

@@ -20,6 +20,7 @@ FL_DECLARE_VARIANT(kart_direct)
 FL_DECLARE_VARIANT(kart_derivative)
 FL_DECLARE_VARIANT(kart_direct_torque)
 FL_DECLARE_VARIANT(kart_derivative_torque)
+FL_DECLARE_VARIANT(kart_steady)
 
 namespace {
 
@@ -45,6 +46,7 @@ const fl_variant* pick_variant(int model, int form, int elevation, int torque)
     }
     if (model == FL_MODEL_KART_6DOF && !elevation)
     {
+        if (form == FL_FORM_STEADY) return fl_variant_kart_steady();
         if (form == FL_FORM_DIRECT) return torque ? fl_variant_kart_direct_torque() : fl_variant_kart_direct();
         return torque ? fl_variant_kart_derivative_torque() : fl_variant_kart_derivative();
     }
@@ -141,12 +143,34 @@ void fl_nlp_destroy(fl_nlp* h)
     delete h;
 }
 
+static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec);
+
 fl_nlp* fl_nlp_create(const fl_problem_desc* d)
+{
+    if (d && d->form == FL_FORM_STEADY) { fail("steady-state problems are created with fl_steady_create"); return nullptr; }
+    return create_impl(d, nullptr);
+}
+
+// Steady-state (G-G diagram) NLPs: a batch of one-node problems (see fl_steady_desc in the header).
+fl_nlp* fl_steady_create(const fl_steady_desc* sd)
+{
+    if (!sd || !sd->vehicle_params || !sd->spec) { fail("null steady-state description"); return nullptr; }
+    if (sd->model != FL_MODEL_KART_6DOF) { fail("steady-state problems: lot2016kart only"); return nullptr; }
+    const double s0 = 0.0, zeros6[6] = {0, 0, 0, 0, 0, 0}, w0 = 0.0;
+    fl_problem_desc d{};
+    d.model = sd->model; d.form = FL_FORM_STEADY; d.closed = 1; d.elevation = 0; d.kart_direct_torque = 1;
+    d.n_points = 1; d.s = &s0; d.track_length = 1.0; d.track_nodes = zeros6; d.wl = &w0; d.wr = &w0;
+    d.batch = sd->batch; d.vehicle_params = sd->vehicle_params; d.sigma = 0.5; d.dissipation[0] = d.dissipation[1] = 0.0;
+    d.device = sd->device;
+    return create_impl(&d, sd->spec);
+}
+
+static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
 {
     if (!d) { fail("null problem description"); return nullptr; }
     const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque);
     if (!v) { fail(d->model == FL_MODEL_KART_6DOF && d->elevation ? "lot2016kart does not support tracks with elevation" : "unknown model / form"); return nullptr; }
-    if (d->n_points < 2) { fail("provide at least two values of arclength"); return nullptr; }
+    if (d->n_points < 2 && !steady_spec) { fail("provide at least two values of arclength"); return nullptr; }
     if (d->batch < 1) { fail("batch must be >= 1"); return nullptr; }
     if (!d->s || !d->track_nodes || !d->wl || !d->wr || !d->vehicle_params) { fail("null array in problem description"); return nullptr; }
     for (int i = 1; i < d->n_points; ++i)
@@ -247,6 +271,7 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
         Db[v->P_SIGMA] = d->sigma;
         Db[v->P_DISS0] = d->dissipation[0];
         Db[v->P_DISS1] = d->dissipation[1];
+        if (steady_spec) std::memcpy(Db + v->P_DISS1 + 1, steady_spec + (size_t)b * 7, 7 * sizeof(double));    // ss_v ... ss_cay follow diss1
         v->derive(Db);
     }
 
@@ -342,6 +367,21 @@ int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double
     const double big = std::numeric_limits<double>::max();
     std::vector<double> lb(NV), ub(NV);
     const double* par = d->vehicle_params;        // bounds that depend on parameters use problem 0
+    if (d->form == FL_FORM_STEADY)
+    {
+        // lot2016kart.h:81-121: steady_state_variable_bounds, then ax, ay (solve_max_lat_acc uses +-2 / +-20, steady_state.hpp:146-147;
+        // the G-G loop narrows ax per speed, callers may pass their own); constraints: 6 equations, kappa +-0.11, lambda +-0.09
+        const double l[8] = { -0.5, 1.0e-4, -10.0 * DEG, -10.0 * DEG, -10.0 * DEG, -10.0 * DEG, -20.0, -20.0 };
+        const double u[8] = { 0.5, 0.04, 10.0 * DEG, 10.0 * DEG, 10.0 * DEG, 10.0 * DEG, 20.0, 20.0 };
+        for (int k = 0; k < 8; ++k) { if (x_l) x_l[k] = l[k]; if (x_u) x_u[k] = u[k]; }
+        for (int r = 0; r < 12; ++r)
+        {
+            const double b = r < 6 ? 0.0 : (r < 8 ? 0.11 : 0.09);
+            if (g_l) g_l[r] = -b;
+            if (g_u) g_u[r] = b;
+        }
+        return 1;
+    }
     if (d->model == FL_MODEL_F1_3DOF)
     {
         // axle_car_3dof.hpp:366-397, chassis.hpp:400-425 (50..380 km/h, |v| <= 50 km/h, |omega| <= 10), chassis_car_3dof.hpp:306-352,

@@ -67,6 +67,7 @@ template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, con
         else if (s->NV == 17 && s->NEQ == 15) fn<17, 15>(s, __VA_ARGS__); \
         else if (s->NV == 14 && s->NEQ == 12) fn<14, 12>(s, __VA_ARGS__); \
         else if (s->NV == 16 && s->NEQ == 14) fn<16, 14>(s, __VA_ARGS__); \
+        else if (s->NV == 8 && s->NEQ == 6) fn<8, 6>(s, __VA_ARGS__); \
         else { fl_set_error("no KKT kernel for this stage size"); return 0; } \
     } while (0)
 
@@ -261,7 +262,7 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
         return nullptr;
     }
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
-    if (P.closed && S <= 2) { fl_set_error("closed laps need at least three nodes"); fl_ipm_destroy(s); return nullptr; }
+    if (P.closed && S == 2) { fl_set_error("closed laps need at least three nodes"); fl_ipm_destroy(s); return nullptr; }
     return s;
 }
 

@@ -238,3 +238,42 @@ class CollocationNLP:
     @property
     def kernel_launches(self):
         return int(self._lib.fl_kernel_launches(self._h))
+
+
+class _SteadyDesc(C.Structure):
+    _fields_ = [("model", C.c_int), ("batch", C.c_int), ("vehicle_params", _dp), ("spec", _dp), ("device", C.c_int)]
+
+
+class SteadyStateNLP(CollocationNLP):
+    """A batch of steady-state (G-G diagram) NLPs, x = [w_axle, z, phi, mu, psi, delta, ax, ay]: the reference's
+    Steady_state functors Solve / Max_lat_acc / Max_lon_acc / Min_lon_acc (src/core/applications/steady_state.h:99-284) over
+    lot2016kart::steady_state_equations (src/core/vehicles/lot2016kart.h:124-182).  spec rows: (v, ax, ay, free_ax, free_ay,
+    cax, cay).  Everything a CollocationNLP offers (callbacks, eval_all, LapSolver) works on it."""
+
+    def __init__(self, model, vehicle_params, spec, device=0):
+        lib = self._lib = load_library()
+        lib.fl_steady_create.restype = C.c_void_p
+        lib.fl_steady_create.argtypes = [C.POINTER(_SteadyDesc)]
+        spec = np.ascontiguousarray(spec, dtype=np.float64).reshape(-1, 7)
+        B = spec.shape[0]
+        params = np.ascontiguousarray(vehicle_params, dtype=np.float64)
+        if params.ndim == 1:
+            params = np.ascontiguousarray(np.tile(params[None, :], (B, 1)))
+        if params.shape != (B, lib.fl_n_vehicle_params(model)):
+            raise ValueError("vehicle parameters must be [batch][%d]" % lib.fl_n_vehicle_params(model))
+        self.problem = None
+        self._keep = [params, spec]
+        d = _SteadyDesc(int(model), B, _ptr(params), _ptr(spec), int(device))
+        self._h = lib.fl_steady_create(C.byref(d))
+        if not self._h:
+            raise RuntimeError("fl_steady_create: " + lib.fl_last_error().decode())
+        n, m, nj, nh = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        lib.fl_nlp_sizes(self._h, C.byref(n), C.byref(m), C.byref(nj), C.byref(nh))
+        self.n, self.m, self.nnz_jac, self.nnz_hess, self.batch = n.value, m.value, nj.value, nh.value, B
+        self.variant = lib.fl_nlp_variant(self._h).decode()
+        ops = (C.c_int * 4)()
+        lib.fl_nlp_ops_per_node(self._h, ops)
+        self.ops_per_node = dict(values=ops[0], jac=ops[1], hess=ops[2], all=ops[3])
+        nval, nck = C.c_int(), C.c_int()
+        lib.fl_nlp_workspace_slots(self._h, C.byref(nval), C.byref(nck))
+        self.n_values, self.n_checkpoints = nval.value, nck.value

@@ -27,7 +27,8 @@ extern "C" {
 typedef struct fl_nlp fl_nlp;
 
 enum { FL_MODEL_F1_3DOF = 0, FL_MODEL_KART_6DOF = 1 };   /* limebeer2014f1 (vehicles/limebeer2014f1.h), lot2016kart (vehicles/lot2016kart.h) */
-enum { FL_FORM_DIRECT = 0, FL_FORM_DERIVATIVE = 1 };     /* Optimal_laptime::compute_direct / compute_derivative */
+enum { FL_FORM_DIRECT = 0, FL_FORM_DERIVATIVE = 1,      /* Optimal_laptime::compute_direct / compute_derivative */
+       FL_FORM_STEADY = 2 };                             /* steady-state NLPs (fl_steady_create) */
 
 /* Number of entries of the vehicle parameter vector of a model (order: fastest_lap_b200/vehicle.py F1_PARAM_PATHS /
  * KART_PARAM_PATHS, the XML paths of the reference's DECLARE_PARAMS tables). */
@@ -60,6 +61,25 @@ typedef struct fl_problem_desc
 } fl_problem_desc;
 
 fl_nlp* fl_nlp_create(const fl_problem_desc* desc);       /* NULL on failure */
+
+/* Steady-state (G-G diagram) NLPs: a batch of independent 8-variable problems
+ *     x = [w_axle, z, phi, mu, psi, delta, ax, ay]           (layout of Max_lat_acc, src/core/applications/steady_state.hpp:899)
+ *     g = lot2016kart::steady_state_equations(x, ax, ay, v)   (src/core/vehicles/lot2016kart.h:124-182): 6 equations + 6 tyre-slip rows
+ *     f = cax * ax + cay * ay
+ * replacing the functors Solve / Max_lat_acc / Max_lon_acc / Min_lon_acc of src/core/applications/steady_state.h:99-284.
+ * spec [batch][7] = (v, ax, ay, free_ax, free_ay, cax, cay): with free_ax == 0 the equations use the given ax and the
+ * variable x[6] is inert (likewise ay); Solve: free 0/0, c 0/0; Max_lat_acc: free 1/1, cay -1; Max_lon_acc: free 1/0,
+ * cax -1; Min_lon_acc: free 1/0, cax +1.  The handle is an fl_nlp with n = 8, m = 12: every callback, fl_eval_all and the
+ * interior-point solver work on it as on a lap (it is a one-node lap to them). */
+typedef struct fl_steady_desc
+{
+    int model;                    /* FL_MODEL_KART_6DOF                                  */
+    int batch;
+    const double* vehicle_params; /* [batch][fl_n_vehicle_params(model)]                 */
+    const double* spec;           /* [batch][7]                                          */
+    int device;
+} fl_steady_desc;
+fl_nlp* fl_steady_create(const fl_steady_desc* desc);
 void    fl_nlp_destroy(fl_nlp* nlp);
 const char* fl_last_error(void);
 

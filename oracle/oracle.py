@@ -129,3 +129,14 @@ def kart_car(q, u, params, track6=None, direct_torque=False, curvilinear=True):
     lib().orc_kart_car(_dp(q), _dp(u), _dp(params), _dp(track6), int(direct_torque), int(curvilinear), _dp(st), _dp(dst), C.byref(dtds), _dp(ext), _dp(diag))
     return dict(states=st, dstates=dst, dtds=dtds.value, extra=ext, kappa=diag[0:4], lam=diag[4:8], N=diag[8:12], Fx=diag[12:16],
                 Fy=diag[16:20], w=diag[20:24], force=diag[24:27], torque=diag[27:30])
+
+
+def kart_steady(x, params, v, ax=0.0, ay=0.0, free_ax=False, free_ay=False, cax=0.0, cay=0.0, lam=None, obj_factor=1.0):
+    """Steady-state NLP of the kart at x = [w_axle, z, phi, mu, psi, delta, ax, ay] (oracle/steady.hpp)."""
+    x, params = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, params))
+    spec = np.array([v, ax, ay, float(free_ax), float(free_ay), cax, cay])
+    lam = np.zeros(12) if lam is None else np.ascontiguousarray(lam, dtype=np.float64)
+    f = C.c_double()
+    c, grad, jac, hess = np.zeros(12), np.zeros(8), np.zeros((12, 8)), np.zeros((8, 8))
+    lib().orc_kart_steady(_dp(x), _dp(params), _dp(spec), _dp(lam), C.c_double(obj_factor), C.byref(f), _dp(c), _dp(grad), _dp(jac), _dp(hess))
+    return dict(f=f.value, c=c, grad=grad, jac=jac, hess=hess)

@@ -5,6 +5,7 @@
 #include <vector>
 #include <omp.h>
 #include "nlp.hpp"
+#include "steady.hpp"
 
 using namespace oracle;
 
@@ -122,6 +123,30 @@ void orc_kart_car(const double* q, const double* u, const double* P, const doubl
         diag[12 + i] = o.Fx_t[i]; diag[16 + i] = o.Fy_t[i]; diag[20 + i] = o.w[i];
     }
     for (int i = 0; i < 3; ++i) { diag[24 + i] = o.force[i]; diag[27 + i] = o.torque[i]; }
+}
+
+// Steady-state NLP of the kart at one point: f, c[12], grad f [8], dense Jacobian [12][8], dense Hessian of the Lagrangian [8][8]
+// spec = {v, ax, ay, free_ax, free_ay, cax, cay}
+void orc_kart_steady(const double* x, const double* P, const double* spec, const double* lambda, double obj_factor,
+                     double* f, double* c, double* grad, double* jac, double* hess)
+{
+    SteadySpec sp{spec[0], spec[1], spec[2], spec[3], spec[4], spec[5], spec[6]};
+    using J = Jet2<KSS_NX>;
+    J xj[KSS_NX], cj[KSS_NC], fj;
+    for (int k = 0; k < KSS_NX; ++k) xj[k] = J::variable(x[k], k);
+    kart_steady<J>(xj, P, sp, cj, fj);
+    *f = fj.v;
+    for (int r = 0; r < KSS_NC; ++r) c[r] = cj[r].v;
+    if (!grad) return;
+    for (int k = 0; k < KSS_NX; ++k) grad[k] = fj.g[k];
+    for (int r = 0; r < KSS_NC; ++r) for (int k = 0; k < KSS_NX; ++k) jac[r * KSS_NX + k] = cj[r].g[k];
+    for (int i = 0; i < KSS_NX; ++i)
+        for (int k = 0; k <= i; ++k)
+        {
+            double h = obj_factor * fj.h[i][k];
+            for (int r = 0; r < KSS_NC; ++r) h += lambda[r] * cj[r].h[i][k];
+            hess[i * KSS_NX + k] = h; hess[k * KSS_NX + i] = h;
+        }
 }
 
 } // extern "C"

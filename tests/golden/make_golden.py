@@ -83,5 +83,29 @@ def main():
     np.savez(os.path.join(data_dir, "vehicles.npz"), limebeer_2014_f1=f1.params, roberto_lot_kart_2016=kart.params, rental_kart=rental.params)
 
 
+
+
+def steady_state_golden():
+    """src/test/applications/data/steady_state.xml (steady_state_ad_test.cpp / steady_state_test.cpp): converged kart steady
+    states -- 0 g, maximum lateral acceleration, maximum / minimum longitudinal acceleration at given lateral ones -- as
+    x = [w_axle, z, phi, mu, psi, delta, ax, ay] of the 8-variable steady-state NLP (steady_state.hpp:899)."""
+    import xml.etree.ElementTree as ET
+    root = ET.fromstring(open(DATA + "steady_state.xml").read())
+    names, rows = [], []
+    for vel in root:
+        v = float(vel.tag.split("_")[1]) / 3.6
+        for case in vel:
+            q = np.array([float(t) for t in case.find("q").text.split(",")])
+            u = np.array([float(t) for t in case.find("u").text.split(",")])
+            ax = float(case.find("ax").text) if case.find("ax") is not None else 0.0
+            ay = q[3] * v
+            names.append(vel.tag + "/" + case.tag)
+            rows.append([v, (q[0] * 0.139 - v) / v, q[4], q[5], q[6], q[12], u[0], ax, ay])
+    kart = vehicle_from_xml(REF + "database/vehicles/kart/roberto-lot-kart-2016.xml")
+    np.savez_compressed(os.path.join(HERE, "kart_steady_state.npz"), names=np.array(names), v=np.array(rows)[:, 0], x=np.array(rows)[:, 1:], params=kart.params)
+    print("kart_steady_state", len(names), "points")
+
+
 if __name__ == "__main__":
     main()
+    steady_state_golden()

@@ -1,0 +1,89 @@
+"""Steady-state (G-G diagram) NLPs on the GPU: callbacks against the oracle, and converged solutions against the
+reference's stored steady states (src/test/applications/data/steady_state.xml -> tests/golden/kart_steady_state.npz)."""
+import os
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kart_steady_state.npz"))
+
+
+def _dense(nlp, out, b):
+    jr, jc, hr, hc = nlp.structure()
+    J = np.zeros((12, 8)); np.add.at(J, (jr, jc), out["jac"][b])
+    H = np.zeros((8, 8)); np.add.at(H, (hr, hc), out["hess"][b])
+    H = H + np.tril(H, -1).T
+    return J, H
+
+
+def test_callbacks_match_oracle():
+    from fastest_lap_b200.nlp import SteadyStateNLP
+    from fastest_lap_b200.vehicle import MODEL_KART
+    rng = np.random.default_rng(0)
+    B = len(GOLD["v"])
+    x = GOLD["x"] * (1 + 1e-3 * rng.standard_normal(GOLD["x"].shape))
+    lam = rng.standard_normal((B, 12))
+    spec = np.stack([GOLD["v"], GOLD["x"][:, 6], GOLD["x"][:, 7], rng.integers(0, 2, B), rng.integers(0, 2, B), rng.standard_normal(B), rng.standard_normal(B)], axis=1)
+    nlp = SteadyStateNLP(MODEL_KART, GOLD["params"], spec)
+    assert (nlp.n, nlp.m) == (8, 12)
+    out = nlp.eval_all(x, lam, 0.7)
+    rel = lambda a, b: np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))
+    for b in range(B):
+        r = orc.kart_steady(x[b], GOLD["params"], *spec[b, :3], free_ax=spec[b, 3], free_ay=spec[b, 4], cax=spec[b, 5], cay=spec[b, 6], lam=lam[b], obj_factor=0.7)
+        J, H = _dense(nlp, out, b)
+        assert abs(out["f"][b] - r["f"]) <= 1e-12 * max(1.0, abs(r["f"]))
+        assert rel(out["g"][b], r["c"]) <= 1e-10
+        assert rel(out["grad"][b], r["grad"]) <= 1e-10
+        assert rel(J, r["jac"]) <= 1e-10
+        assert rel(H, r["hess"]) <= 1e-9
+    nlp.close()
+
+
+def test_converged_steady_states_match_the_reference():
+    """max / min longitudinal acceleration at given lateral acceleration, and the maximum lateral acceleration, for every
+    stored case: ax (ay) within 1e-6 relative of steady_state.xml."""
+    from fastest_lap_b200 import gg
+    names, v, xg = GOLD["names"], GOLD["v"], GOLD["x"]
+    spec, ref, col, group, order = [], [], [], [], []
+    for nm, vv, x in zip(names, v, xg):
+        case = nm.split("/")[1]
+        kind = 0 if case.startswith("max_lon") else 1 if case.startswith("min_lon") else 2 if case == "max_lat_acc" else -1
+        if kind < 0:
+            continue
+        spec.append([[vv, 0, x[7], 1, 0, -1, 0], [vv, 0, x[7], 1, 0, 1, 0], [vv, 0, 0, 1, 1, 0, -1]][kind])
+        ref.append(x[7] if kind == 2 else x[6]); col.append(7 if kind == 2 else 6)
+        group.append(3 * int(round(vv * 3.6)) + kind); order.append(x[7])
+    spec, ref, col, group, order = np.array(spec, dtype=float), np.array(ref), np.array(col), np.array(group), np.array(order)
+    B = len(spec)
+    # start: the 0 g state of each speed, as the reference does (steady_state.hpp:605-615)
+    sp0 = np.zeros((B, 7)); sp0[:, 0] = spec[:, 0]
+    out0 = gg.solve_batch(GOLD["params"], sp0, np.tile(gg.X0, (B, 1)))
+    assert np.all(out0["status"] >= 1)
+    # cold start from 0 g; the points at the tip of the diagram need the reference's continuation in lateral acceleration
+    out = gg.solve_with_continuation(GOLD["params"], spec, out0["x"], group, order)
+    ok = out["status"] >= 1
+    # the stored lateral accelerations are 3 m/s2 apart: a few minimum-ax points at the very tip of the diagram (ay = 14 of a
+    # 14.3 maximum) are out of reach of a continuation that coarse; the reference gets there in steps of ~0.1 m/s2
+    assert ok.mean() >= 0.95, (ok.sum(), B)
+    got = out["x"][np.arange(B), col]
+    err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+    assert np.max(err[ok]) <= 1e-6, np.max(err[ok])
+
+
+def test_gg_diagram_sweep_is_consistent():
+    """A small G-G sweep (4 speeds x 16 lateral accelerations): every point solved, max >= min longitudinal acceleration,
+    the envelope closes at the maximum lateral acceleration, and the stored 0 g / maximum-lateral states are reproduced."""
+    from fastest_lap_b200 import gg
+    speeds = np.array([50.0, 70.0, 90.0, 110.0]) / 3.6
+    r = gg.gg_diagram(GOLD["params"], speeds, n_lat=16)
+    assert r["zero_g_solved"].all() and r["ay_max_solved"].all()
+    assert r["ax_max_solved"].mean() >= 0.9 and r["ax_min_solved"].mean() >= 0.9, (r["ax_max_solved"].mean(), r["ax_min_solved"].mean())
+    ok = r["ax_max_solved"] & r["ax_min_solved"]
+    assert np.all(r["ax_max"][ok] >= r["ax_min"][ok] - 1e-6)
+    for k, vk in enumerate((50, 70, 90, 110)):
+        i = list(GOLD["names"]).index("velocity_%d/max_lat_acc" % vk)
+        assert abs(r["ay_max"][k] - GOLD["x"][i, 7]) <= 1e-6 * GOLD["x"][i, 7]
+        j = list(GOLD["names"]).index("velocity_%d/zero_g" % vk)
+        assert np.max(np.abs(r["zero_g"][k, :6] - GOLD["x"][j, :6])) <= 1e-6
