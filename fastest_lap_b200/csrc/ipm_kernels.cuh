@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_init(const fl_ipm_dev I)
     {
         L.mu = I.o.mu_init; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
         L.theta_max = -1.0; L.theta_min = -1.0; L.status = IPM_RUNNING; L.ls = LS_IDLE; L.iter = 0; L.acc_count = 0; L.n_filter = 0;
-        L.n_backtrack = 0; L.n_soc = 0; L.n_reg = 0; L.n_fact = 0; L.switching = 0; L.soc_step = 0;
+        L.n_backtrack = 0; L.n_soc = 0; L.n_reg = 0; L.n_fact = 0; L.switching = 0; L.n_restart = 0; L.n_small = 0;
         I.dw[lap] = 0.0; I.dc[lap] = L.dc; I.act_run[lap] = 1; I.act_factor[lap] = 1; I.act_soc[lap] = 0;
     }
 }
@@ -476,6 +476,39 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_soc_direction(const fl_ipm_de
     ipm_write_trial(I, lap, I.dxs, I.dss, amax);
 }
 
+// Restart of the barrier problem at the current primal point (stands in for Ipopt's restoration phase, which this solver
+// does not have): larger mu, empty filter, equality multipliers forgotten, bound multipliers on the central path.
+// Used when the line search finds no acceptable step, or when the iteration has crawled with tiny steps for a while
+// (the multipliers then typically blow up).  At most IPM_MAX_RESTARTS times per lap.
+__device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L)
+{
+    const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni;
+    __shared__ double sh_mu;
+    if (threadIdx.x == 0)
+    {
+        L.n_restart += 1;
+        L.mu = fmin(I.o.mu_init, fmax(100.0 * L.mu, 1.0e-4));
+        L.tau = fmax(I.o.tau_min, 1.0 - L.mu);
+        L.n_filter = 0; L.acc_count = 0; L.n_small = 0; L.dw_last = 0.0;
+        L.theta_max = 1.0e4 * fmax(1.0, L.theta); L.theta_min = 1.0e-4 * fmax(1.0, L.theta);
+        sh_mu = L.mu;
+    }
+    __syncthreads();
+    const double mu = sh_mu;
+    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    {
+        const double x = I.x[on + i];
+        I.nx[on + i] = x;
+        I.zl[on + i] = mu / (x - I.xl[i]); I.zu[on + i] = mu / (I.xu[i] - x);
+    }
+    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    {
+        const double s = I.s[oi + k];
+        I.vl[oi + k] = mu / (s - I.sl[k]); I.vu[oi + k] = mu / (I.su[k] - s);
+    }
+    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
+}
+
 // ---- filter line search: judge the trial point (f, g evaluated at it) --------------------------------------------------
 __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev I)
 {
@@ -580,7 +613,15 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
             I.vu[oi + k] = fmax(fmin(vu, ks * mu / du), mu / (ks * du));
         }
         for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { const double y = I.y[om + i] + alpha * dya[om + i]; I.y[om + i] = y; I.nlam[om + i] = y; }
-        if (threadIdx.x == 0) { L.ls = LS_DONE; L.iter += 1; I.act_soc[lap] = 0; }
+        __shared__ int sh_restart;
+        if (threadIdx.x == 0)
+        {
+            L.ls = LS_DONE; L.iter += 1; I.act_soc[lap] = 0;
+            L.n_small = (alpha < 0.05) ? L.n_small + 1 : 0;
+            sh_restart = (L.n_small >= 8 && L.n_restart < IPM_MAX_RESTARTS) ? 1 : 0;
+        }
+        __syncthreads();
+        if (sh_restart) ipm_restart(I, lap, L);
     }
     else if (decision == 2)
     {
@@ -598,24 +639,19 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
     }
     else
     {
-        // The line search found no acceptable step.  Ipopt would enter its restoration phase here; this solver restores
-        // the iterate in the NLP's buffers and restarts the barrier problem from a larger mu with an empty filter (at
-        // most IPM_MAX_RESTARTS times per lap), which moves the iterate back towards the central path.
-        for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.nx[on + i] = I.x[on + i];
-        if (threadIdx.x == 0)
+        // The line search found no acceptable step: restart the barrier problem from the current iterate, or give up.
+        __shared__ int sh_can;
+        if (threadIdx.x == 0) { I.act_soc[lap] = 0; sh_can = L.n_restart < IPM_MAX_RESTARTS ? 1 : 0; }
+        __syncthreads();
+        if (sh_can)
         {
-            I.act_soc[lap] = 0;
-            if (L.soc_step < IPM_MAX_RESTARTS)
-            {
-                L.soc_step += 1;                       // restarts so far
-                L.mu = fmin(I.o.mu_init, fmax(10.0 * L.mu, 1.0e-6));
-                L.tau = fmax(I.o.tau_min, 1.0 - L.mu);
-                L.n_filter = 0;
-                L.theta_max = 1.0e4 * fmax(1.0, L.theta); L.theta_min = 1.0e-4 * fmax(1.0, L.theta);
-                L.acc_count = 0;
-                L.ls = LS_DONE; L.iter += 1;
-            }
-            else { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; }
+            ipm_restart(I, lap, L);
+            if (threadIdx.x == 0) { L.ls = LS_DONE; L.iter += 1; }
+        }
+        else
+        {
+            for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.nx[on + i] = I.x[on + i];
+            if (threadIdx.x == 0) { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; }
         }
     }
 }
