@@ -193,7 +193,7 @@ def batched_leg(args, torch, dist, world, rank, local, peak):
     return res
 
 
-N_SOLVE = 256
+N_SOLVE = 1024
 
 
 def solve_leg(args, torch, dist, world, rank, local):
@@ -212,7 +212,10 @@ def solve_leg(args, torch, dist, world, rank, local):
     params = workloads.sweep_parameters(MODEL_F1, args.solve_laps)
     params[0] = p.params                                     # lap 0 drives the reference vehicle (known answer)
     nlp = CollocationNLP(p, vehicle_params=params[lo:hi], device=local)
-    solver = LapSolver(nlp)
+    from fastest_lap_b200.ipm import default_options
+    opts = default_options()
+    opts.max_iter = args.solve_max_iter       # laps that need more count as not converged (reported below); Ipopt's default is 3000
+    solver = LapSolver(nlp, options=opts)
     x0 = workloads.f1_start_point(p, 50.0)
     if dist is not None:
         dist.barrier()
@@ -232,7 +235,7 @@ def solve_leg(args, torch, dist, world, rank, local):
     st = out["stats"]
     golden = 77.791438
     r = {"workload": "%d independent limebeer-2014-f1 laps, Catalunya, 500 nodes, closed, direct form, vehicles drawn per lap (rng 2), start = steady state at 50 km/h; "
-                     "tol 1e-10 (the reference's Ipopt options); contiguous shards over %d GPU(s)" % (args.solve_laps, world),
+                     "tol 1e-10 (the reference's Ipopt options), at most %d iterations per lap; contiguous shards over %d GPU(s)" % (args.solve_laps, args.solve_max_iter, world),
          "laps": args.solve_laps, "laps_per_gpu": B, "scaling": "strong", "value": args.solve_laps / wall, "unit": "laps/s", "seconds": wall, "device_ms": dev_ms,
          "converged": int(ok.sum()), "not_converged": int((~ok).sum()), "iterations_median": float(np.median(res[:, 2])), "iterations_max": float(res[:, 2].max()),
          "lap0_time_s": float(res[0, 0]), "lap0_reference_s": golden, "lap0_rel_err": abs(float(res[0, 0]) - golden) / golden,
@@ -284,6 +287,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--laps", type=int, default=N_LAPS, help="laps of the batched callback leg (0 = skip)")
     ap.add_argument("--solve-laps", type=int, default=N_SOLVE, help="laps solved to convergence in the laps/s leg (0 = skip)")
+    ap.add_argument("--solve-max-iter", type=int, default=250)
     ap.add_argument("--gg-speeds", type=int, default=32, help="speeds of the G-G sweep leg (0 = skip)")
     ap.add_argument("--gg-lat", type=int, default=64)
     args = ap.parse_args()

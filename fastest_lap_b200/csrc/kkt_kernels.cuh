@@ -14,7 +14,7 @@
 //   * stages are eliminated from the last one backwards (the order of a Riccati recursion: what stage j hands to stage
 //     j-1 is the cost-to-go Hessian of node j-1), stage 0 last; on closed laps every stage also carries its fill block
 //     F_j = K[0, j] towards stage 0;
-//   * every pivot block is inverted in place by a Gauss-Jordan sweep with Bunch-Parlett pivoting (1x1 pivots on the
+//   * every pivot block is inverted in place by a Gauss-Jordan sweep with Bunch-Kaufman pivoting (1x1 pivots on the
 //     largest diagonal, 2x2 pivots when the diagonal is weak), which also counts the negative pivots: by Haynsworth
 //     additivity their sum is the inertia Ipopt asks of its linear solver (n positive, m negative, none zero).
 //
@@ -97,7 +97,7 @@ __device__ __forceinline__ unsigned kkt_key(double v, int lane) { return ((unsig
 __device__ __forceinline__ double kkt_key_value(unsigned key) { return __hiloint2double((int)(key & ~31u), 0); }
 
 // Inverse of the symmetric NB x NB matrix in A (shared memory, both triangles stored) by Gauss-Jordan sweeps with
-// Bunch-Parlett pivoting.  Every sweep rewrites the whole matrix, so the sweeps ping-pong between A and B (one barrier
+// Bunch-Kaufman pivoting (candidate: the largest diagonal entry).  Every sweep rewrites the whole matrix, so the sweeps ping-pong between A and B (one barrier
 // per sweep); every warp takes the same pivoting decision from the same data.  Thread (lane r, warp w) owns row r and
 // the columns w, w + KW, ...  Returns the buffer holding the inverse; thread 0 accumulates the pivot counts.
 template <int NB>
@@ -119,23 +119,16 @@ __device__ __forceinline__ double* kkt_invert(double* A, double* B, int& n_neg, 
         const unsigned kl = __reduce_max_sync(0xffffffffu, (mine && lane != p) ? kkt_key(KM(M, lane, p), lane) : 0u);
         const double lam = kkt_key_value(kl);
         bool two = false;
-        if (!(dmax >= ALPHA * lam && dmax > 0.0))
+        if (!(dmax >= ALPHA * lam && dmax > 0.0) && lam > 0.0)
         {
-            // largest off-diagonal entry of the unswept part
-            double best = 0.0;
-            int bc = 0;
-            if (mine)
-                for (int c = 0; c < NB; ++c)
-                    if (c != lane && !((swept >> c) & 1u))
-                    {
-                        const double a = fabs(KM(M, lane, c));
-                        if (a > best) { best = a; bc = c; }
-                    }
-            const unsigned km = __reduce_max_sync(0xffffffffu, mine ? kkt_key(best, lane) : 0u);
-            const int br = 31 - (int)(km & 31u);
-            const double mu0 = kkt_key_value(km);
-            bc = __shfl_sync(0xffffffffu, bc, br);
-            if (mu0 > 0.0 && !(dmax >= ALPHA * mu0)) { two = true; p = br; q = bc; }
+            // Bunch-Kaufman: r = row of the largest entry of column p, sigma = largest off-diagonal entry of column r
+            const int r = 31 - (int)(kl & 31u);
+            const unsigned ks = __reduce_max_sync(0xffffffffu, (mine && lane != r) ? kkt_key(KM(M, lane, r), lane) : 0u);
+            const double sigma = kkt_key_value(ks);
+            const double arr = fabs(KM(M, r, r));
+            if (dmax * sigma >= ALPHA * lam * lam) { }                       // 1x1 pivot on p
+            else if (arr >= ALPHA * sigma) { p = r; q = r; }                  // 1x1 pivot on r
+            else { two = true; q = r; }                                       // 2x2 pivot on (p, r)
         }
         if (!two)
         {
@@ -413,7 +406,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                     double acc[CV];
 #pragma unroll
                     for (int i = 0; i < CV; ++i) acc[i] = 0.0;
-#pragma unroll 4
+#pragma unroll 7
                     for (int k = 0; k < NB; ++k)
                     {
                         const double a = KM(Mi, lane, k);
@@ -428,7 +421,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                     double acc[CB];
 #pragma unroll
                     for (int i = 0; i < CB; ++i) acc[i] = 0.0;
-#pragma unroll 4
+#pragma unroll 7
                     for (int k = 0; k < NB; ++k)
                     {
                         const double a = KM(Mi, lane, k);
@@ -448,7 +441,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                 for (int i = 0; i < CV; ++i) acc[i] = 0.0;
                 if (chain)
                 {
-#pragma unroll 4
+#pragma unroll 7
                     for (int k = 0; k < NB; ++k)
                     {
                         const double a = KM(sm.L, k, lane);
@@ -465,7 +458,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
             if (cyc && lane < NB)
             {
                 // stage 0: d0acc += F XF ; new fill F_{j-1} = -F XL (columns: x of stage j-1)
-#pragma unroll 4
+#pragma unroll 7
                 for (int k = 0; k < NB; ++k)
                 {
                     const double a = KM(sm.F, lane, k);

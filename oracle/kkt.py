@@ -16,7 +16,7 @@ cyclic for closed laps -- with blocks of NV + n_eq (28 for the F1 direct form). 
 backwards (the order of a Riccati recursion: the Schur complement handed to stage j-1 is the cost-to-go Hessian of node
 j-1), stage 0 last; the closing element of a closed lap makes every stage couple with stage 0 through a fill block F_j.
 
-Every pivot block is inverted by Gauss-Jordan sweeps with Bunch-Parlett pivoting, which also counts negative pivots.
+Every pivot block is inverted by Gauss-Jordan sweeps with Bunch-Kaufman pivoting, which also counts negative pivots.
 Inertia: by Haynsworth additivity the inertia of the whole matrix is the sum of the inertias of the pivot blocks, so the
 factorisation reports exactly what Ipopt asks of MUMPS (n positive, m negative eigenvalues, none zero).
 """
@@ -110,8 +110,8 @@ ALPHA = (1.0 + 17.0 ** 0.5) / 8.0
 
 
 def pivoted_gauss_jordan(A):
-    """In-place style inverse of a symmetric matrix by Gauss-Jordan sweeps with Bunch-Parlett pivoting (1x1 pivots on the
-    largest diagonal entry of the unswept part, 2x2 pivots when the diagonal is weak).  Returns (inverse, number of
+    """In-place style inverse of a symmetric matrix by Gauss-Jordan sweeps with Bunch-Kaufman pivoting (candidate: the
+    largest diagonal entry of the unswept part; 2x2 pivots when the diagonal is weak).  Returns (inverse, number of
     negative pivots, number of vanishing pivots): the statement of kkt_invert in csrc/kkt_kernels.cuh."""
     M = np.array(A, dtype=float)
     n = len(M)
@@ -125,14 +125,17 @@ def pivoted_gauss_jordan(A):
         others = un[un != k]
         lam = np.max(np.abs(M[others, k])) if len(others) else 0.0
         two = False
-        if not (dmax >= ALPHA * lam and dmax > 0.0):
-            sub = np.abs(M[np.ix_(un, un)])
-            np.fill_diagonal(sub, -1.0)
-            mu0 = sub.max() if len(un) > 1 else -1.0
-            if mu0 > 0.0 and not (dmax >= ALPHA * mu0):
-                ip, iq = np.unravel_index(np.argmax(sub), sub.shape)       # first maximum in row-major order
-                p, q = un[ip], un[iq]
-                two = True
+        if not (dmax >= ALPHA * lam and dmax > 0.0) and lam > 0.0:
+            # Bunch-Kaufman: r = row of the largest entry of column k, sigma = largest off-diagonal entry of column r
+            r = others[np.argmax(np.abs(M[others, k]))]
+            rest = un[un != r]
+            sigma = np.max(np.abs(M[rest, r]))
+            if dmax * sigma >= ALPHA * lam * lam:
+                pass
+            elif abs(M[r, r]) >= ALPHA * sigma:
+                k = r
+            else:
+                two, p, q = True, k, r
         if not two:
             d = M[k, k]
             if d == 0.0:

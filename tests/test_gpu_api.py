@@ -1,0 +1,66 @@
+"""The reference's Python surface (src/main/python/fastest_lap.py) on the GPU path: the README example of the reference --
+limebeer-2014-f1 on Catalunya, 500 points -- and the kart G-G diagram."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _write_xml_fixtures(tmp_path):
+    """Vehicle / track XML files rebuilt from the packaged data (the reference's database is not on the GPU box)."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.vehicle import F1_PARAM_PATHS, KART_PARAM_PATHS
+    from fastest_lap_b200.track import track_from_npz
+    import xml.etree.ElementTree as ET
+    veh = workloads._vehicles()
+    paths = {}
+    for name, typ, plist, key in (("f1", "f1-3dof", F1_PARAM_PATHS, "limebeer_2014_f1"), ("kart", "kart-6dof", KART_PARAM_PATHS, "roberto_lot_kart_2016")):
+        root = ET.Element("vehicle", type=typ)
+        for pth, val in zip(plist, veh[key]):
+            node = root
+            for part in pth.split("/"):
+                nxt = node.find(part)
+                node = ET.SubElement(node, part) if nxt is None else nxt
+            node.text = repr(float(val))
+        paths[name] = str(tmp_path / (name + ".xml"))
+        ET.ElementTree(root).write(paths[name])
+    return paths
+
+
+def test_optimal_laptime_readme_example(tmp_path):
+    from fastest_lap_b200 import api, workloads
+    from fastest_lap_b200.track import track_from_npz
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api.create_vehicle_from_xml("car", paths["f1"])
+    api._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    L = api.track_download_length("catalunya")
+    s = np.linspace(0.0, L, 501)[:-1]
+    prefix, names = api.optimal_laptime("car", "catalunya", s, "<options><output_variables><prefix>run/</prefix></output_variables></options>")
+    assert prefix == "run/" and "chassis.velocity.x" in names and "laptime" in names
+    gold = np.load(os.path.join(HERE, "golden", "f1_catalunya_discrete.npz"))
+    assert abs(api.download_scalar("run/laptime") - float(gold["laptime"])) <= 1e-6 * float(gold["laptime"])
+    u = api.download_vector("run/chassis.velocity.x")
+    assert u.shape == (500,) and np.max(np.abs(u - gold["x"].reshape(500, 15)[:, 4])) <= 1e-4
+    t = api.download_vector("run/time")
+    assert np.max(np.abs(t - gold["time"])) <= 1e-5
+    with pytest.raises(api.FastestLapError):
+        api.create_vehicle_from_xml("car", paths["f1"])          # name already taken
+    api.delete_variable("run/*")
+    with pytest.raises(api.FastestLapError):
+        api.download_scalar("run/laptime")
+
+
+def test_gg_diagram_of_the_kart(tmp_path):
+    from fastest_lap_b200 import api
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api.create_vehicle_from_xml("kart", paths["kart"])
+    ay, ay_minus, ax_max, ax_min = api.gg_diagram("kart", 50.0 / 3.6, 12)
+    g = np.load(os.path.join(HERE, "golden", "kart_steady_state.npz"))
+    i = list(g["names"]).index("velocity_50/max_lat_acc")
+    assert abs(ay[-1] * 9.81 - g["x"][i, 7]) <= 1e-6 * g["x"][i, 7]
+    assert len(ay) == 12 and ay[0] == 0.0 and all(a >= b - 1e-9 for a, b in zip(ax_max, ax_min))
+    assert ay_minus[3] == -ay[3]
