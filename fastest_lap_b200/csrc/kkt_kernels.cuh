@@ -286,12 +286,12 @@ struct kkt_stage
     }
 };
 
-// shared memory of one lap: M, F, XF (32 x NB each), L, XL, P (32 x NV), inequality rows, pivot buffers
+// shared memory of one lap: M, M2 (sweep buffers), F (32 x NB each), L, XL, P (32 x NV), inequality rows
 template <int NV, int NEQ>
 struct kkt_smem
 {
     static constexpr int NB = NV + NEQ;
-    double M[KLD * NB], M2[KLD * NB], F[KLD * NB], XF[KLD * NB], L[KLD * NV], XL[KLD * NV], P[KLD * NV];
+    double M[KLD * NB], M2[KLD * NB], F[KLD * NB], L[KLD * NV], XL[KLD * NV], P[KLD * NV];     // D^-1 F^T reuses the idle half of (M, M2)
     double aq[8 * KLD];
     double dw_next;
     int flag;
@@ -357,6 +357,9 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
             }
             __syncthreads();
             const bool chain = j >= 1 && (j >= 2 || !cyc);          // stage j hands a Schur term to stage j-1 through L_j
+            // non-zero columns of the fill block: x of stage j, except at stage 1 where K[0, 1] = L_1^T brings the multiplier columns
+            const int KF = (cyc && j == 1) ? NB : NV;
+            const int ncpl = K.ls_mode ? 0 : K.NCPL;
             if (j >= 1)
             {
                 St::gather_coupling(K, lap, j, sm.L);
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
             }
             const int neg_before = n_neg, zero_before = n_zero;
             const double* Mi = kkt_invert<NB>(sm.M, sm.M2, n_neg, n_zero);
+            double* XF = (Mi == sm.M) ? sm.M2 : sm.M;           // the sweep buffer that does not hold the inverse
             if (Lp)
             {
                 // every pivot block carries exactly NEQ negative pivots when the reduced Hessian is positive definite
@@ -406,12 +410,19 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                     double acc[CV];
 #pragma unroll
                     for (int i = 0; i < CV; ++i) acc[i] = 0.0;
-#pragma unroll 7
-                    for (int k = 0; k < NB; ++k)
+                    // rows of L that can be non-zero: the NEQ multiplier rows, and the diagonal coupling entries (cp, cp)
+#pragma unroll
+                    for (int k = NV; k < NB; ++k)
                     {
                         const double a = KM(Mi, lane, k);
 #pragma unroll
                         for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.L, k, c); }
+                    }
+                    for (int q = 0; q < ncpl; ++q)
+                    {
+                        const int cp = K.t.ctrl_pos[q];
+#pragma unroll
+                        for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c == cp) acc[i] += KM(Mi, lane, cp) * KM(sm.L, cp, cp); }
                     }
 #pragma unroll
                     for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.XL, lane, c) = acc[i]; }
@@ -421,15 +432,15 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                     double acc[CB];
 #pragma unroll
                     for (int i = 0; i < CB; ++i) acc[i] = 0.0;
-#pragma unroll 7
-                    for (int k = 0; k < NB; ++k)
+#pragma unroll 5
+                    for (int k = 0; k < KF; ++k)
                     {
                         const double a = KM(Mi, lane, k);
 #pragma unroll
                         for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) acc[i] += a * KM(sm.F, c, k); }
                     }
 #pragma unroll
-                    for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) KM(sm.XF, lane, c) = acc[i]; }
+                    for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) KM(XF, lane, c) = acc[i]; }
                 }
             }
             __syncthreads();
@@ -441,12 +452,22 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                 for (int i = 0; i < CV; ++i) acc[i] = 0.0;
                 if (chain)
                 {
-#pragma unroll 7
-                    for (int k = 0; k < NB; ++k)
+#pragma unroll
+                    for (int k = NV; k < NB; ++k)
                     {
                         const double a = KM(sm.L, k, lane);
 #pragma unroll
                         for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.XL, k, c); }
+                    }
+                    for (int q = 0; q < ncpl; ++q)
+                    {
+                        const int cp = K.t.ctrl_pos[q];
+                        if (lane == cp)
+                        {
+                            const double a = KM(sm.L, cp, cp);
+#pragma unroll
+                            for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.XL, cp, c); }
+                        }
                     }
                 }
 #pragma unroll
@@ -458,12 +479,12 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
             if (cyc && lane < NB)
             {
                 // stage 0: d0acc += F XF ; new fill F_{j-1} = -F XL (columns: x of stage j-1)
-#pragma unroll 7
-                for (int k = 0; k < NB; ++k)
+#pragma unroll 5
+                for (int k = 0; k < KF; ++k)
                 {
                     const double a = KM(sm.F, lane, k);
 #pragma unroll
-                    for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) d0acc[i] += a * KM(sm.XF, k, c); }
+                    for (int i = 0; i < CB; ++i) { const int c = w + KW * i; if (c < NB) d0acc[i] += a * KM(XF, k, c); }
                     if (chain)
                     {
 #pragma unroll
