@@ -200,3 +200,70 @@ def test_empty_and_invalid_inputs_are_rejected():
     with pytest.raises(AssertionError):
         nlp.eval_all(ex["x"][:-1], ex["lam"])
     nlp.close()
+
+
+# ---- BASELINE.json's full sizes --------------------------------------------------------------------------------------
+def test_full_size_f1_8000_nodes_against_oracle():
+    """configs[2]: F1, Catalunya, 8000 nodes (n = 120 000, m = 152 000): every callback against the oracle at the golden
+    solution interpolated to the mesh, and a size-independent property: refining the mesh leaves the lap time (the
+    objective without the control penalty) of the interpolated solution within the trapezoid error of the 500-node one."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    p = workloads.f1_catalunya(8000)
+    gp, ex = load_golden("f1_catalunya_discrete")
+    x = workloads.resample_point(p, gp.s, ex["x"], p.nv)
+    lam = np.random.default_rng(1).standard_normal(p.m)
+    nlp = CollocationNLP(p)
+    assert (nlp.n, nlp.m) == (120000, 152000)
+    out = nlp.eval_all(x, lam, 1.0)
+    ref = oracle_nlp(p).eval(x, lam, 1.0)
+    jr, jc, hr, hc = nlp.structure()
+    assert abs(out["f"][0] - ref["f"]) <= RTOL * abs(ref["f"])
+    assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
+    assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
+    _matrix_close(_csr(jr, jc, out["jac"][0], (p.m, p.n)), _csr(*ref["jac"], (p.m, p.n)), "jacobian", p.ncpe)
+    _matrix_close(_csr(hr, hc, out["hess"][0], (p.n, p.n)), _csr(*ref["hess"], (p.n, p.n)), "hessian", p.nv, rtol=1.0e-8)
+    from fastest_lap_b200.ipm import lap_time
+    assert abs(lap_time(p, x, out["f"][0]) - float(ex["laptime"])) <= 5.0e-2       # 77.82 s vs 77.79 s: interpolation of a 500-node solution
+    nlp.close()
+
+
+def test_full_size_kart_2000_nodes_against_oracle():
+    """configs[3]: kart, Vendrell, 2000 nodes, derivative form (n = 32 000, m = 40 000)."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    p = workloads.kart_vendrell(2000)
+    gp, ex = load_golden("kart_vendrell")
+    x = workloads.resample_point(p, gp.s, ex["x"], p.nv)
+    lam = 0.1 * np.random.default_rng(1).standard_normal(p.m)
+    nlp = CollocationNLP(p)
+    assert (nlp.n, nlp.m) == (32000, 40000)
+    out = nlp.eval_all(x, lam, 1.0)
+    ref = oracle_nlp(p).eval(x, lam, 1.0)
+    jr, jc, hr, hc = nlp.structure()
+    assert abs(out["f"][0] - ref["f"]) <= RTOL * abs(ref["f"])
+    assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
+    assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
+    _matrix_close(_csr(jr, jc, out["jac"][0], (p.m, p.n)), _csr(*ref["jac"], (p.m, p.n)), "jacobian", p.ncpe)
+    _matrix_close(_csr(hr, hc, out["hess"][0], (p.n, p.n)), _csr(*ref["hess"], (p.n, p.n)), "hessian", p.nv, rtol=1.0e-8)
+    nlp.close()
+
+
+def test_batch_linearity_in_the_multipliers():
+    """configs[4]-style batch (64 laps with perturbed vehicles): the Lagrangian Hessian is linear in (obj_factor, lambda):
+    H(a, lam1 + lam2) = H(a, lam1) + H(0, lam2), lap by lap -- a size-independent check of the batched derivative kernel."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.vehicle import MODEL_F1
+    p, ex = load_golden("f1_catalunya_discrete")
+    B = 64
+    rng = np.random.default_rng(5)
+    nlp = CollocationNLP(p, vehicle_params=workloads.sweep_parameters(MODEL_F1, B))
+    x = ex["x"][None, :] * (1 + 1e-3 * rng.standard_normal((B, 1)))
+    l1, l2 = rng.standard_normal((B, p.m)), rng.standard_normal((B, p.m))
+    h12 = nlp.eval_all(x, l1 + l2, 0.7, want=("hess",))["hess"].copy()
+    h1 = nlp.eval_all(x, l1, 0.7, want=("hess",))["hess"].copy()
+    h2 = nlp.eval_all(x, l2, 0.0, want=("hess",))["hess"].copy()
+    scale = np.maximum(np.abs(h1) + np.abs(h2), 1.0)
+    assert np.max(np.abs(h12 - h1 - h2) / scale) <= 1e-9       # entries are sums of ~40 products of mixed sign: fp64 cancellation
+    nlp.close()
