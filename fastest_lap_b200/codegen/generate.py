@@ -43,6 +43,7 @@ VARIANTS = {
     "kart_direct_torque": Variant("kart", "direct", direct_torque=True),
     "kart_derivative_torque": Variant("kart", "derivative", direct_torque=True),
     "kart_steady": Variant("kart", "steady"),
+    "f1_steady": Variant("f1", "steady"),
 }
 
 

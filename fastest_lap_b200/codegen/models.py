@@ -209,7 +209,10 @@ def f1_model(q, u, P, trk):
     dstates = [d * dtds for d in dstates]                                # dynamic_model_car.hpp:104-105
     half_track = 0.5 * P["f_track"]
     extra = [lam[0], lam[1], lam[2], lam[3], n + half_track * ca, n - half_track * ca]     # limebeer2014f1.h:266-281
-    return dict(states=states, dstates=dstates, dtds=dtds, extra=extra)
+    # un-scaled time derivatives and wheel balances (the steady-state equations use them, limebeer2014f1.h:148-169)
+    rates = dict(du=du, dv=dv, domega=domega, dw_g=dw * (1.0 / G0), dLroll_mg=dLroll * inv_mg, dLpitch_mg=dLpitch * inv_mg,
+                 roll_balance_mg=roll_balance * inv_mg, dL=dL, lam=lam)
+    return dict(states=states, dstates=dstates, dtds=dtds, extra=extra, rates=rates)
 
 
 def kart_tire(P, pre, kappa, lam, N, only_lateral):

@@ -19,7 +19,6 @@ from . import models
 class Variant:
     def __init__(self, model, form, elevation=False, direct_torque=False):
         assert model in ("f1", "kart") and form in ("direct", "derivative", "steady")
-        assert form != "steady" or model == "kart"
         self.model, self.form, self.elevation, self.direct_torque = model, form, bool(elevation), bool(direct_torque)
         if model == "kart":
             assert not elevation, "lot2016kart rejects tracks with elevation (lot2016kart.h:63-68)"
@@ -44,7 +43,7 @@ class NodeProgram:
         g = self.g = Graph()
         S = lambda name, cls: E(g, g.sym(name, cls))
         if v.form == "steady":
-            self._init_steady(S)
+            (self._init_steady if v.model == "kart" else self._init_steady_f1)(S)
             return
         deriv = v.form == "derivative"
 
@@ -201,6 +200,63 @@ class NodeProgram:
         phi = obj * fobj
         for r in range(self.ncpe):
             phi = phi + self.lam_in[r] * rowsA[r]
+        self.phi = phi
+        self._differentiate(rowsA, rowsB, fobj, phi, obj, None, None)
+
+    def _init_steady_f1(self, S):
+        """Steady-state NLP of the F1: limebeer2014f1::steady_state_equations (src/core/vehicles/limebeer2014f1.h:103-178)
+        behind the same Steady_state functors; x = [kappa x4, psi / 10 deg, Fz x4 (in m g), delta / 10 deg, throttle, ax, ay]
+        with ax, ay in g (acceleration_units = g0, limebeer2014f1.h:51): 11 equations, then lambda_i / lambda_max_i in [-1, 1.2]."""
+        import math
+        g = self.g
+        self.param_names = models.F1_PARAMS + models.F1_HOST_PARAMS + ["diss0", "diss1"] + \
+            ["ss_v", "ss_ax", "ss_ay", "ss_free_ax", "ss_free_ay", "ss_cax", "ss_cay"]
+        self.n_fm, self.td_ids, self.alg_ids = 0, [], list(range(11))
+        self.n_td, self.n_alg, self.n_ext, self.n_ctrl_rows = 0, 11, 4, 0
+        self.ncpe, self.nv = 15, 13
+        self.ctrl_pos, self.dctrl_pos = [0, 0], []
+        self.x = [S("x%d" % k, "x") for k in range(self.nv)]
+        P = self.P = {n: S("p_" + n, "p") for n in self.param_names}
+        self.track_names = ["kz"]
+        self.geom_names = ["hin", "hout", "ihin", "ihout"]
+        self.lam_in = [S("lin%d" % r, "w") for r in range(self.ncpe)]
+        self.lam_out = [None] * self.ncpe
+        obj = S("obj", "w")
+        self.uprev, self.unext = [], []
+        x, v = self.x, P["ss_v"]
+        G0 = models.G0
+        ax = x[11] * P["ss_free_ax"] + (1.0 - P["ss_free_ax"]) * P["ss_ax"]
+        ay = x[12] * P["ss_free_ay"] + (1.0 - P["ss_free_ay"]) * P["ss_ay"]
+        max_angle = 10.0 * math.pi / 180.0
+        psi = x[4] * max_angle
+        cps, sps = models.cos(psi), models.sin(psi)
+        zero = E(g, g.const(0.0))
+        q = [x[0], x[1], x[2], x[3], v * cps, -(v * sps), ay * (G0 / v), x[5], x[6], x[7], x[8], zero, zero, zero]
+        u = [x[9] * max_angle, zero, x[10], P["brake_bias"]]
+        trk = dict(kx=0.0, ky=0.0, kz=0.0, smu=0.0, cmu=1.0, sph=0.0, cph=1.0)
+        out = models.f1_model(q, u, P, trk)
+        r = out["rates"]
+        m = P["mass"]
+        inv_g, inv_mg = 1.0 / G0, 1.0 / (m * G0)
+        eqs = [r["dw_g"], r["dLroll_mg"], r["dLpitch_mg"], r["roll_balance_mg"],
+               (r["du"] * sps + r["dv"] * cps) * inv_g, ax + (r["dv"] * sps - r["du"] * cps) * inv_g, r["domega"] * inv_g] + \
+              [r["dL"][i] * inv_mg for i in range(4)]
+        ext = []
+        for i in range(4):
+            pre = "ft_" if i < 2 else "rt_"
+            Fz = -(x[5 + i] * (m * G0))                       # maximum_lambda of the load fed to the model (limebeer2014f1.h:123-126)
+            lmax = (Fz - P[pre + "Fz1"]) * ((P[pre + "lmax2_deg"] * models.DEG - P[pre + "lmax1_deg"] * models.DEG) * (1.0 / (P[pre + "Fz2"] - P[pre + "Fz1"]))) \
+                + P[pre + "lmax1_deg"] * models.DEG
+            ext.append(r["lam"][i] / lmax)
+        fobj = x[11] * P["ss_cax"] + x[12] * P["ss_cay"]
+        self.Q, self.QD, self.ALG, self.EXT, self.CDOT, self.DTDS = [], [], eqs, ext, [], fobj
+        self.values = eqs + ext + [fobj]
+        self.value_names = ["ALG%d" % k for k in range(11)] + ["EXT%d" % k for k in range(4)] + ["DTDS"]
+        rowsA, rowsB = eqs + ext, [None] * 15
+        self.rowsA, self.rowsB, self.fobj = rowsA, rowsB, fobj
+        phi = obj * fobj
+        for k in range(self.ncpe):
+            phi = phi + self.lam_in[k] * rowsA[k]
         self.phi = phi
         self._differentiate(rowsA, rowsB, fobj, phi, obj, None, None)
 

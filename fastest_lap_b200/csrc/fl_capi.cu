@@ -21,6 +21,7 @@ FL_DECLARE_VARIANT(kart_derivative)
 FL_DECLARE_VARIANT(kart_direct_torque)
 FL_DECLARE_VARIANT(kart_derivative_torque)
 FL_DECLARE_VARIANT(kart_steady)
+FL_DECLARE_VARIANT(f1_steady)
 
 namespace {
 
@@ -41,6 +42,7 @@ const fl_variant* pick_variant(int model, int form, int elevation, int torque)
 {
     if (model == FL_MODEL_F1_3DOF)
     {
+        if (form == FL_FORM_STEADY) return elevation ? nullptr : fl_variant_f1_steady();
         if (form == FL_FORM_DIRECT) return elevation ? fl_variant_f1_direct_3d() : fl_variant_f1_direct();
         return elevation ? fl_variant_f1_derivative_3d() : fl_variant_f1_derivative();
     }
@@ -155,10 +157,10 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* d)
 fl_nlp* fl_steady_create(const fl_steady_desc* sd)
 {
     if (!sd || !sd->vehicle_params || !sd->spec) { fail("null steady-state description"); return nullptr; }
-    if (sd->model != FL_MODEL_KART_6DOF) { fail("steady-state problems: lot2016kart only"); return nullptr; }
+    if (sd->model != FL_MODEL_KART_6DOF && sd->model != FL_MODEL_F1_3DOF) { fail("unknown model"); return nullptr; }
     const double s0 = 0.0, zeros6[6] = {0, 0, 0, 0, 0, 0}, w0 = 0.0;
     fl_problem_desc d{};
-    d.model = sd->model; d.form = FL_FORM_STEADY; d.closed = 1; d.elevation = 0; d.kart_direct_torque = 1;
+    d.model = sd->model; d.form = FL_FORM_STEADY; d.closed = 1; d.elevation = 0; d.kart_direct_torque = sd->model == FL_MODEL_KART_6DOF;
     d.n_points = 1; d.s = &s0; d.track_length = 1.0; d.track_nodes = zeros6; d.wl = &w0; d.wr = &w0;
     d.batch = sd->batch; d.vehicle_params = sd->vehicle_params; d.sigma = 0.5; d.dissipation[0] = d.dissipation[1] = 0.0;
     d.device = sd->device;
@@ -367,6 +369,16 @@ int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double
     const double big = std::numeric_limits<double>::max();
     std::vector<double> lb(NV), ub(NV);
     const double* par = d->vehicle_params;        // bounds that depend on parameters use problem 0
+    if (d->form == FL_FORM_STEADY && d->model == FL_MODEL_F1_3DOF)
+    {
+        // limebeer2014f1.h:57-86: steady_state_variable_bounds, then ax, ay in g (the reference widens them until they are
+        // inactive, steady_state.hpp:200-226); constraints: 11 equations, lambda / lambda_max in [-1, 1.2]
+        const double l[13] = { -1.15, -1.15, -1.15, -1.15, 0.0, -2.0, -2.0, -2.0, -2.0, 0.0, -1.0, -8.0, -8.0 };
+        const double u[13] = { 0.25, 0.25, 1.0, 1.0, 1.5, 0.1, 0.1, 0.1, 0.1, 1.5, 1.0, 8.0, 8.0 };
+        for (int k = 0; k < 13; ++k) { if (x_l) x_l[k] = l[k]; if (x_u) x_u[k] = u[k]; }
+        for (int r = 0; r < 15; ++r) { if (g_l) g_l[r] = r < 11 ? 0.0 : -1.0; if (g_u) g_u[r] = r < 11 ? 0.0 : 1.2; }
+        return 1;
+    }
     if (d->form == FL_FORM_STEADY)
     {
         // lot2016kart.h:81-121: steady_state_variable_bounds, then ax, ay (solve_max_lat_acc uses +-2 / +-20, steady_state.hpp:146-147;

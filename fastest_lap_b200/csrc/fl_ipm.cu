@@ -68,6 +68,7 @@ template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, con
         else if (s->NV == 14 && s->NEQ == 12) fn<14, 12>(s, __VA_ARGS__); \
         else if (s->NV == 16 && s->NEQ == 14) fn<16, 14>(s, __VA_ARGS__); \
         else if (s->NV == 8 && s->NEQ == 6) fn<8, 6>(s, __VA_ARGS__); \
+        else if (s->NV == 13 && s->NEQ == 11) fn<13, 11>(s, __VA_ARGS__); \
         else { fl_set_error("no KKT kernel for this stage size"); return 0; } \
     } while (0)
 

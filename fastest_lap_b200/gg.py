@@ -10,9 +10,14 @@ import numpy as np
 
 from .nlp import SteadyStateNLP
 from .ipm import LapSolver, default_options
-from .vehicle import MODEL_KART
+from .vehicle import MODEL_KART, MODEL_F1
 
 X0 = np.array([0.0, 0.02, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0])          # lot2016kart::steady_state_initial_guess (lot2016kart.h:83-86)
+X0_F1 = np.array([0.0, 0.0, 0.0, 0.0, 0.0, -0.25, -0.25, -0.25, -0.25, 0.0, 0.0, 0.0, 0.0])   # limebeer2014f1.h:57-60 (+ ax, ay)
+
+
+def _model_of(params):
+    return MODEL_F1 if np.shape(params)[-1] == 58 else MODEL_KART
 
 
 def _options(tol=1.0e-8):
@@ -23,19 +28,30 @@ def _options(tol=1.0e-8):
 
 def solve_batch(params, spec, x0, device=0, bounds=None):
     """Solves one batch of steady-state NLPs; returns the LapSolver result dict."""
-    nlp = SteadyStateNLP(MODEL_KART, params, spec, device=device)
+    nlp = SteadyStateNLP(_model_of(params), params, spec, device=device)
     solver = LapSolver(nlp, options=_options(), bounds=bounds)
     out = solver.solve(x0)
     solver.close(); nlp.close()
     return out
 
 
-def solve_with_continuation(params, spec, x0, group, order, device=0, max_sweeps=8):
+def f1_bounds(brake=False):
+    """limebeer2014f1::steady_state_variable_bounds[_brake] (limebeer2014f1.h:62-80) + ax, ay in g, and the constraint bounds."""
+    if brake:
+        xl = [-1.15, -1.15, -1.30, -1.30, 0.0, -2.0, -2.0, -2.0, -2.0, 0.0, -1.0, -8.0, -8.0]
+        xu = [0.25, 0.25, 0.25, 0.25, 1.0, 0.1, 0.1, 0.1, 0.1, 1.0, 0.5, 8.0, 8.0]
+    else:
+        xl = [-1.15, -1.15, -1.15, -1.15, 0.0, -2.0, -2.0, -2.0, -2.0, 0.0, -1.0, -8.0, -8.0]
+        xu = [0.25, 0.25, 1.00, 1.00, 1.5, 0.1, 0.1, 0.1, 0.1, 1.5, 1.0, 8.0, 8.0]
+    return np.array(xl), np.array(xu), np.array([0.0] * 11 + [-1.0] * 4), np.array([0.0] * 11 + [1.2] * 4)
+
+
+def solve_with_continuation(params, spec, x0, group, order, device=0, max_sweeps=8, bounds=None, polish=0, objective=None):
     """Solves a batch; problems that fail are solved again from the converged solution of their nearest predecessor in
     `order` within the same `group` (the reference warm-starts every G-G point from the previous lateral acceleration,
     steady_state.hpp:615-633: this is the same continuation, applied only where the cold start fails)."""
     spec, x0 = np.asarray(spec, dtype=np.float64), np.array(x0, dtype=np.float64)
-    out = solve_batch(params, spec, x0, device)
+    out = solve_batch(params, spec, x0, device, bounds)
     x, status, iters = out["x"].copy(), out["status"].copy(), out["iters"].copy()
     for _ in range(max_sweeps):
         bad = np.where(status < 1)[0]
@@ -51,37 +67,60 @@ def solve_with_continuation(params, spec, x0, group, order, device=0, max_sweeps
             break
         todo = np.array(todo)
         p_b = params if np.ndim(params) == 1 else np.asarray(params)[todo]
-        o2 = solve_batch(p_b, spec[todo], np.array(starts), device)
+        o2 = solve_batch(p_b, spec[todo], np.array(starts), device, bounds)
         good = o2["status"] >= 1
         if not good.any():
             break
         x[todo[good]] = o2["x"][good]; status[todo[good]] = o2["status"][good]; iters[todo[good]] += o2["iters"][good]
+    # polish: these NLPs have several local optima; the reference follows one branch by warm-starting every point from
+    # the previous lateral acceleration.  Every point is solved again from its predecessor's solution and the better
+    # optimum is kept.
+    for _ in range(polish):
+        idx, starts = [], []
+        for b in range(len(spec)):
+            cand = np.where((group == group[b]) & (order < order[b]) & (status >= 1))[0]
+            if cand.size:
+                idx.append(b); starts.append(x[cand[np.argmax(order[cand])]])
+        if not idx:
+            break
+        idx = np.array(idx)
+        p_b = params if np.ndim(params) == 1 else np.asarray(params)[idx]
+        o2 = solve_batch(p_b, spec[idx], np.array(starts), device, bounds)
+        better = (o2["status"] >= 1) & ((status[idx] < 1) | (objective(o2["x"], spec[idx]) < objective(x[idx], spec[idx]) - 1.0e-9))
+        x[idx[better]] = o2["x"][better]; status[idx[better]] = o2["status"][better]
+        if not better.any():
+            break
     return dict(x=x, status=status, iters=iters)
 
 
-def gg_diagram(params, speeds, n_lat=64, device=0):
-    """speeds [m/s].  Returns dict(ay [S][n_lat], ax_max, ax_min [S][n_lat], ay_max [S], solved masks)."""
+def gg_diagram(params, speeds, n_lat=64, device=0, polish=3):
+    """speeds [m/s].  Returns dict(ay [S][n_lat], ax_max, ax_min [S][n_lat], ay_max [S], solved masks); accelerations in the
+    model's units (m/s2 for the kart, g for the F1: acceleration_units of lot2016kart.h:79 / limebeer2014f1.h:51)."""
     speeds = np.asarray(speeds, dtype=np.float64)
     S = len(speeds)
     z = np.zeros(S)
+    f1 = _model_of(params) == MODEL_F1
+    ia, iy = (11, 12) if f1 else (6, 7)
     # (1) 0 g
-    out0 = solve_batch(params, np.stack([speeds, z, z, z, z, z, z], axis=1), np.tile(X0, (S, 1)), device)
+    out0 = solve_batch(params, np.stack([speeds, z, z, z, z, z, z], axis=1), np.tile(X0_F1 if f1 else X0, (S, 1)), device)
     x_0g = out0["x"].copy()
     # (2) maximum lateral acceleration: ax and ay free, f = -ay
     one = np.ones(S)
     out_lat = solve_batch(params, np.stack([speeds, z, z, one, one, z, -one], axis=1), x_0g, device)
-    ay_max, ax_at_max = out_lat["x"][:, 7], out_lat["x"][:, 6]
+    ay_max, ax_at_max = out_lat["x"][:, iy], out_lat["x"][:, ia]
     # (3) fan of lateral accelerations: max / min longitudinal acceleration (f = -+ax), ay given
     ay = np.linspace(0.0, 1.0, n_lat)[None, :] * ay_max[:, None]
     v_b = np.repeat(speeds, n_lat)
     zb, ob = np.zeros(S * n_lat), np.ones(S * n_lat)
     x0 = np.repeat(x_0g, n_lat, axis=0)
-    x0[:, 7] = 0.0
+    x0[:, iy] = 0.0
     res = {}
     grp, order = np.repeat(np.arange(S), n_lat), np.tile(np.arange(n_lat), S)
     for name, sign in (("ax_max", -1.0), ("ax_min", 1.0)):
-        out = solve_with_continuation(params, np.stack([v_b, zb, ay.ravel(), ob, zb, sign * ob, zb], axis=1), x0, grp, order, device)
-        res[name] = out["x"][:, 6].reshape(S, n_lat)
+        bnd = f1_bounds(brake=sign > 0) if f1 else None         # the F1 brakes within its own variable bounds (steady_state.hpp:803-806)
+        out = solve_with_continuation(params, np.stack([v_b, zb, ay.ravel(), ob, zb, sign * ob, zb], axis=1), x0, grp, order, device, bounds=bnd,
+                                      polish=polish, objective=lambda xx, sp: sp[:, 5] * xx[:, ia])
+        res[name] = out["x"][:, ia].reshape(S, n_lat)
         res[name + "_solved"] = (out["status"] == 1).reshape(S, n_lat) | (out["status"] == 2).reshape(S, n_lat)
         res[name + "_iters"] = out["iters"].reshape(S, n_lat)
         # the last point is the maximum-lateral-acceleration solution itself (steady_state.hpp:715, 857-870: the loop stops at

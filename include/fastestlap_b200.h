@@ -73,7 +73,9 @@ fl_nlp* fl_nlp_create(const fl_problem_desc* desc);       /* NULL on failure */
  * interior-point solver work on it as on a lap (it is a one-node lap to them). */
 typedef struct fl_steady_desc
 {
-    int model;                    /* FL_MODEL_KART_6DOF                                  */
+    int model;                    /* FL_MODEL_KART_6DOF, or FL_MODEL_F1_3DOF: 13 variables [kappa x4, psi/10deg, Fz x4, delta/10deg,
+                                     throttle, ax, ay] (ax, ay in g), 15 rows: limebeer2014f1::steady_state_equations,
+                                     src/core/vehicles/limebeer2014f1.h:103-178 */
     int batch;
     const double* vehicle_params; /* [batch][fl_n_vehicle_params(model)]                 */
     const double* spec;           /* [batch][7]                                          */

@@ -64,6 +64,7 @@ struct F1Out
     T extra[F1_NEXTRA];    // vehicles/limebeer2014f1.h:266-281
     // diagnostics used by the unit-level tests
     T kappa[4], lambda[4], omega_w[4], Fx_t[4], Fy_t[4], N[4];
+    T dL[4];               // wheel angular-momentum balance, unscaled (axle_car_3dof.hpp:263-268)
 };
 
 // Pacejka_simple_model, tire/tire_pacejka.hpp:196-226 and tire/tire_pacejka.h:291-294
@@ -271,6 +272,7 @@ inline void f1_car(const T q[F1_NIN], const T u[F1_NCTRL], const double* P, cons
     {
         out.states[i] = out.omega_w[i] * Iw[i] * sc[i];
         out.dstates[i] = dL[i] * sc[i];
+        out.dL[i] = dL[i];
     }
     out.states[4] = vx - h * omega_y;           out.dstates[4] = du;
     out.states[5] = vy + h * omega_x;           out.dstates[5] = dv;

@@ -140,3 +140,14 @@ def kart_steady(x, params, v, ax=0.0, ay=0.0, free_ax=False, free_ay=False, cax=
     c, grad, jac, hess = np.zeros(12), np.zeros(8), np.zeros((12, 8)), np.zeros((8, 8))
     lib().orc_kart_steady(_dp(x), _dp(params), _dp(spec), _dp(lam), C.c_double(obj_factor), C.byref(f), _dp(c), _dp(grad), _dp(jac), _dp(hess))
     return dict(f=f.value, c=c, grad=grad, jac=jac, hess=hess)
+
+
+def f1_steady(x, params, v, ax=0.0, ay=0.0, free_ax=False, free_ay=False, cax=0.0, cay=0.0, lam=None, obj_factor=1.0):
+    """Steady-state NLP of the F1 at x = [kappa x4, psi/10deg, Fz x4, delta/10deg, throttle, ax, ay] (ax, ay in g; oracle/steady.hpp)."""
+    x, params = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, params))
+    spec = np.array([v, ax, ay, float(free_ax), float(free_ay), cax, cay])
+    lam = np.zeros(15) if lam is None else np.ascontiguousarray(lam, dtype=np.float64)
+    f = C.c_double()
+    c, grad, jac, hess = np.zeros(15), np.zeros(13), np.zeros((15, 13)), np.zeros((13, 13))
+    lib().orc_f1_steady(_dp(x), _dp(params), _dp(spec), _dp(lam), C.c_double(obj_factor), C.byref(f), _dp(c), _dp(grad), _dp(jac), _dp(hess))
+    return dict(f=f.value, c=c, grad=grad, jac=jac, hess=hess)

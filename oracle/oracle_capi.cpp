@@ -149,4 +149,27 @@ void orc_kart_steady(const double* x, const double* P, const double* spec, const
         }
 }
 
+// The same for the F1 (13 variables, 15 rows)
+void orc_f1_steady(const double* x, const double* P, const double* spec, const double* lambda, double obj_factor,
+                   double* f, double* c, double* grad, double* jac, double* hess)
+{
+    SteadySpec sp{spec[0], spec[1], spec[2], spec[3], spec[4], spec[5], spec[6]};
+    using J = Jet2<FSS_NX>;
+    J xj[FSS_NX], cj[FSS_NC], fj;
+    for (int k = 0; k < FSS_NX; ++k) xj[k] = J::variable(x[k], k);
+    f1_steady<J>(xj, P, sp, cj, fj);
+    *f = fj.v;
+    for (int r = 0; r < FSS_NC; ++r) c[r] = cj[r].v;
+    if (!grad) return;
+    for (int k = 0; k < FSS_NX; ++k) grad[k] = fj.g[k];
+    for (int r = 0; r < FSS_NC; ++r) for (int k = 0; k < FSS_NX; ++k) jac[r * FSS_NX + k] = cj[r].g[k];
+    for (int i = 0; i < FSS_NX; ++i)
+        for (int k = 0; k <= i; ++k)
+        {
+            double h = obj_factor * fj.h[i][k];
+            for (int r = 0; r < FSS_NC; ++r) h += lambda[r] * cj[r].h[i][k];
+            hess[i * FSS_NX + k] = h; hess[k * FSS_NX + i] = h;
+        }
+}
+
 } // extern "C"

@@ -13,6 +13,7 @@
 
 #include "jet.hpp"
 #include "kart_model.hpp"
+#include "f1_model.hpp"
 
 namespace oracle {
 
@@ -52,6 +53,51 @@ inline void kart_steady(const T x[KSS_NX], const double* P, const SteadySpec& sp
     c[6] = o.kappa[2]; c[7] = o.kappa[3];
     c[8] = o.lambda[2]; c[9] = o.lambda[3]; c[10] = o.lambda[0]; c[11] = o.lambda[1];
     f = x[6] * sp.cax + x[7] * sp.cay;
+}
+
+// ---- F1: limebeer2014f1::steady_state_equations (/root/reference/src/core/vehicles/limebeer2014f1.h:103-178)
+// x = [kappa_fl, kappa_fr, kappa_rl, kappa_rr, psi / 10 deg, Fz_fl, Fz_fr, Fz_rl, Fz_rr (in m g), delta / 10 deg, throttle, ax, ay]
+// with ax, ay in g (acceleration_units = g0, limebeer2014f1.h:51); 11 equations + 4 rows lambda_i / lambda_max_i in [-1, 1.2]
+constexpr int FSS_NX = 13, FSS_NC = 15;
+
+template <class T>
+inline void f1_steady(const T x[FSS_NX], const double* P, const SteadySpec& sp, T c[FSS_NC], T& f)
+{
+    const double g0 = 9.81, v = sp.v, m = P[F1_MASS];
+    const double max_yaw = 10.0 * DEG, max_steering = 10.0 * DEG;
+    const T ax = x[11] * sp.free_ax + (1.0 - sp.free_ax) * sp.ax;
+    const T ay = x[12] * sp.free_ay + (1.0 - sp.free_ay) * sp.ay;
+    const T psi = x[4] * max_yaw;
+    const T cps = cos(psi), sps = sin(psi);
+    T q[F1_NIN];
+    for (int i = 0; i < 4; ++i) { q[F1_IKFL + i] = x[i]; q[F1_IFZFL + i] = x[5 + i]; }
+    q[F1_IU] = cps * v;
+    q[F1_IV] = -(sps * v);
+    q[F1_IOMEGA] = ay * (g0 / v);
+    q[F1_ITIME] = T(0.0); q[F1_IN] = T(0.0); q[F1_IALPHA] = T(0.0);        // flat cartesian road: the car does not see psi
+    T u[F1_NCTRL] = { x[9] * max_steering, T(0.0), x[10], T(P[F1_BRAKE_BIAS]) };
+    TrackNode tk{};
+    F1Out<T> o;
+    f1_car<T>(q, u, P, tk, o);
+    // time derivatives: the curvilinear wrapper multiplied by dt/ds = 1 / u on a straight road
+    const T inv = 1.0 / o.dtds;
+    const T du = o.dstates[F1_IU] * inv, dv = o.dstates[F1_IV] * inv;
+    c[0] = o.dstates[7] * inv;
+    c[1] = o.dstates[8] * inv;
+    c[2] = o.dstates[9] * inv;
+    c[3] = o.dstates[10] * inv;
+    c[4] = (du * sps + dv * cps) / g0;
+    c[5] = ax + (dv * sps - du * cps) / g0;
+    c[6] = o.dstates[F1_IOMEGA] * inv / g0;
+    for (int i = 0; i < 4; ++i) c[7 + i] = o.dL[i] / (g0 * m);
+    const SimpleTire tf = load_tire(P + F1_FT_R0), tr = load_tire(P + F1_RT_R0);
+    for (int i = 0; i < 4; ++i)
+    {
+        // maximum_lambda of the load the model is fed with, -Fz m g (limebeer2014f1.h:123-126), not of the smoothed load
+        const T Fz = -(x[5 + i] * (m * g0));
+        c[11 + i] = o.lambda[i] / tire_lambda_max(i < 2 ? tf : tr, Fz);
+    }
+    f = x[11] * sp.cax + x[12] * sp.cay;
 }
 
 } // namespace oracle

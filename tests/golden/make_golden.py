@@ -109,3 +109,19 @@ def steady_state_golden():
 if __name__ == "__main__":
     main()
     steady_state_golden()
+    f1_steady_state_golden()
+
+
+def f1_steady_state_golden():
+    """src/test/applications/data/f1_steady_state_test.xml (f1_steady_state_test.cpp, tolerance 2e-4): maximum lateral
+    acceleration over speed and the G-G diagrams at 100 ... 300 km/h of limebeer-2014-f1."""
+    import xml.etree.ElementTree as ET
+    root = ET.fromstring(open(DATA + "f1_steady_state_test.xml").read())
+    vec = lambda p: np.array([float(t) for t in root.find(p).text.split(",")])
+    d = dict(params=vehicle_from_xml(REF + "database/vehicles/f1/limebeer-2014-f1.xml").params,
+             v=vec("max_lateral_acceleration/velocity"), ay_max=vec("max_lateral_acceleration/acceleration-y"), ax_at_ay_max=vec("max_lateral_acceleration/acceleration-x"))
+    for k in (100, 150, 200, 250, 300):
+        for q, nm in (("maximum_x_acceleration", "ax_max"), ("minimum_x_acceleration", "ax_min"), ("y_acceleration", "ay")):
+            d["gg%d_%s" % (k, nm)] = vec("gg_diagram_%d/%s" % (k, q))
+    np.savez_compressed(os.path.join(HERE, "f1_steady_state.npz"), **d)
+    print("f1_steady_state", len(d["v"]), "speeds")

@@ -41,3 +41,27 @@ def test_derivatives_match_finite_differences():
         gl = lambda q: q["grad"] + q["jac"].T @ lam
         dh = (gl(rp) - gl(rm)) / (2 * h)
         assert np.max(np.abs(dh - r["hess"][:, k]) / np.maximum(1.0, np.abs(dh))) <= 1e-5
+
+
+def test_f1_steady_state_oracle_reproduces_the_reference_maximum_lateral_acceleration():
+    """limebeer2014f1::steady_state_equations restated (oracle/steady.hpp) + scipy's trust-constr: the maximum lateral
+    acceleration at two speeds of f1_steady_state_test.xml (f1_steady_state_test.cpp:47-80, tolerance 2e-4)."""
+    import scipy.optimize as so
+    import warnings
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "f1_steady_state.npz"))
+    P = g["params"]
+    lb = np.array([-1.15, -1.15, -1.15, -1.15, 0, -2, -2, -2, -2, 0, -1, -8.0, -8.0])
+    ub = np.array([0.25, 0.25, 1, 1, 1.5, 0.1, 0.1, 0.1, 0.1, 1.5, 1, 8.0, 8.0])
+    cl, cu = np.array([0.0] * 11 + [-1.0] * 4), np.array([0.0] * 11 + [1.2] * 4)
+
+    def solve(v, x0, free, cay):
+        F = lambda x: orc.f1_steady(x, P, v, 0.0, 0.0, free, free, 0.0, cay)
+        cons = [so.NonlinearConstraint(lambda x: F(x)["c"], cl, cu, jac=lambda x: F(x)["jac"])]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return so.minimize(lambda x: F(x)["f"], x0, jac=lambda x: F(x)["grad"], method="trust-constr", constraints=cons,
+                               bounds=so.Bounds(lb, ub), options=dict(xtol=1e-12, gtol=1e-10, maxiter=2000)).x
+    x0 = np.array([0, 0, 0, 0, 0, -0.25, -0.25, -0.25, -0.25, 0, 0, 0, 0.0])
+    for i in (0, 50):
+        x = solve(g["v"][i], solve(g["v"][i], x0, False, 0.0), True, -1.0)
+        assert abs(x[12] * 9.81 - g["ay_max"][i]) <= 2e-4 and abs(x[11] * 9.81 - g["ax_at_ay_max"][i]) <= 2e-4
