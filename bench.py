@@ -193,7 +193,7 @@ def batched_leg(args, torch, dist, world, rank, local, peak):
     return res
 
 
-N_SOLVE = 1024
+N_SOLVE = 4096
 
 
 def solve_leg(args, torch, dist, world, rank, local):

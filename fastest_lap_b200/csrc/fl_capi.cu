@@ -483,12 +483,18 @@ int fl_nlp_sync(fl_nlp* h)
     return 1;
 }
 
-int fl_eval_device(fl_nlp* h, int what, double obj_factor)
+int fl_eval_device(fl_nlp* h, int what, double obj_factor) { return fl_eval_device_masked(h, what, obj_factor, nullptr); }
+
+} // extern "C"
+
+// internal: the same for the laps whose mask entry is non-zero (device pointer, [batch]); used by the interior-point driver
+int fl_eval_device_masked(fl_nlp* h, int what, double obj_factor, const int* d_active)
 {
     FL_CUDA(cudaSetDevice(h->device));
     if (!scatter_x(h)) return 0;
     fl_dev P = h->P;
     P.obj_factor = obj_factor;
+    P.active = d_active;
     // the values pass also writes the checkpoints every derivative pass loads: it always runs (x may have been rewritten
     // on the device since the last call)
     h->v->launch_values(P, h->D0.data(), h->shared_d, h->stream);
@@ -505,6 +511,8 @@ int fl_eval_device(fl_nlp* h, int what, double obj_factor)
     FL_CUDA(cudaGetLastError());
     return 1;
 }
+
+extern "C" {
 
 double fl_time_device(fl_nlp* h, int what, double obj_factor, int reps)
 {

@@ -8,6 +8,8 @@
 #include "nlp_kernels.cuh"
 
 void fl_set_error(const std::string& msg);
+struct fl_nlp;
+int fl_eval_device_masked(fl_nlp* h, int what, double obj_factor, const int* d_active);
 
 struct fl_nlp
 {

@@ -329,7 +329,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     {
         s->n_rounds = round;
         // callbacks at (x, y), state of the iterate
-        { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device(nlp, ALL, 1.0)) return 0; }
+        { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, ALL, 1.0, round == 0 ? nullptr : I.act_run)) return 0; }
         s->n_eval_full += 1;
         if (!zero_counters(s)) return 0;
         k_ipm_state<<<B, IPM_BLOCK, 0, st>>>(I);
@@ -365,7 +365,9 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
                 k_ipm_soc_direction<<<B, IPM_BLOCK, 0, st>>>(I);
                 s->launches += 2;
             }
-            { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device(nlp, FL_EVAL_FG, 1.0)) return 0; }
+            k_ipm_mask_trials<<<blocks_b, 128, 0, st>>>(I, B);
+            s->launches += 1;
+            { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, FL_EVAL_FG, 1.0, I.act_factor)) return 0; }
             s->n_eval_fg += 1;
             if (!zero_counters(s)) return 0;
             k_ipm_line_search<<<B, IPM_BLOCK, 0, st>>>(I);

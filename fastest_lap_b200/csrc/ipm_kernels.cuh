@@ -656,6 +656,15 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
     }
 }
 
+// mask of the laps whose trial point is waiting to be evaluated
+__global__ void k_ipm_mask_trials(const fl_ipm_dev I, int batch)
+{
+    const int lap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lap >= batch) return;
+    const fl_ipm_lap& L = I.lap[lap];
+    I.act_factor[lap] = (L.status == IPM_RUNNING && (L.ls == LS_TRIAL || L.ls == LS_SOC_TRIAL)) ? 1 : 0;
+}
+
 __global__ void k_ipm_count_running(const fl_ipm_dev I, int batch)
 {
     const int lap = blockIdx.x * blockDim.x + threadIdx.x;

@@ -52,6 +52,7 @@ struct fl_dev
     double* grad;                // [batch][n]
     double* jac;                 // [batch][nnz_jac]
     double* hess;                // [batch][nnz_hess]
+    const int* active;           // [batch] or null: laps with active == 0 are skipped (device-resident solvers)
 };
 
 // offset of slot 0 of `node` inside a chunked [chunk][nslot][32] array
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant_
     const int part = blockIdx.y;
     const int prob = blockIdx.z;
     if (node >= P.n_points) return;
+    if (P.active && !P.active[prob]) return;
     ValuesIO<G, CD> io;
     io.xn = P.x + ((size_t)prob * P.n_points + node) * G::NV;
     io.tcn = P.tc + fl_chunk_base(node, G::NTC);
@@ -205,6 +207,7 @@ __device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, co
 template <class G>
 __global__ void __launch_bounds__(FL_ABLOCK) k_assemble(const __grid_constant__ fl_dev P)
 {
+    if (P.active && !P.active[blockIdx.y]) return;
     assemble_block<G, FL_ABLOCK>(P, blockIdx.x, gridDim.x, blockIdx.y);
 }
 
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __gri
     const int vn = blockIdx.x * FL_DBLOCK + threadIdx.x;     // variable-node index
     const int part = blockIdx.y;
     const int prob = blockIdx.z;
+    if (P.active && !P.active[prob]) return;
     if (ASSEMBLE && part == deriv_parts<G, WHAT>::N)         // the slice that assembles g and f (block-uniform branch)
     {
         const int nbx = (P.n_elements + FL_DBLOCK - 1) / FL_DBLOCK;

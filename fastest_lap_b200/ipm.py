@@ -128,3 +128,4 @@ def lap_time(problem, x, obj):
         du = np.roll(X[:, n_in + c], -1) - X[:, n_in + c]
         pen += problem.dissipation[c] * np.sum(du * du / h)
     return float(obj) - pen
+
