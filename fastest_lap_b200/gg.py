@@ -23,6 +23,7 @@ def _model_of(params):
 def _options(tol=1.0e-8):
     o = default_options()
     o.tol, o.constr_viol_tol, o.acceptable_tol = tol, tol, 1.0e-6        # steady_state.hpp:84-88
+    o.max_iter = 300          # an NLP of 8-13 variables that has not converged by then is retried by continuation instead
     return o
 
 
