@@ -216,11 +216,11 @@ def solve_leg(args, torch, dist, world, rank, local):
     opts = default_options()
     opts.max_iter = args.solve_max_iter       # laps that need more count as not converged (reported below); Ipopt's default is 3000
     solver = LapSolver(nlp, options=opts)
-    x0 = workloads.f1_start_point(p, 50.0)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    x0 = workloads.f1_start_point(p, 50.0, device=local)      # the reference's start: steady state at 50 km/h (GPU steady-state solve)
     out = solver.solve(x0)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0

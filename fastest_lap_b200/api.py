@@ -188,17 +188,6 @@ def _kart_start_node(vehicle, speed, form):
     return np.array(node)
 
 
-def _f1_start_node(vehicle, speed):
-    """Steady state of the F1 at `speed` (0 g), solved on the GPU, as one node of the direct-form lap NLP."""
-    from . import gg
-    out = gg.solve_batch(vehicle.params, np.array([[speed, 0, 0, 0, 0, 0, 0.0]]), gg.X0_F1[None, :])
-    if out["status"][0] < 1:
-        raise FastestLapError("[ERROR] steady-state computation did not converge")
-    x = out["x"][0]
-    psi, delta = x[4] * 10.0 * np.pi / 180.0, x[9] * 10.0 * np.pi / 180.0
-    return np.array([x[0], x[1], x[2], x[3], speed * np.cos(psi), -speed * np.sin(psi), 0.0, x[5], x[6], x[7], x[8], 0.0, psi, delta, x[10]])
-
-
 def optimal_laptime(vehicle, track, s, options=""):
     """Computes the optimal lap of `vehicle` on `track` over the mesh `s` and stores the outputs in the table under
     `<prefix>`.  Returns (prefix, variable names), as the reference's Python wrapper does."""
@@ -215,7 +204,7 @@ def optimal_laptime(vehicle, track, s, options=""):
         raise FastestLapError("[ERROR] optimal_laptime -> open meshes need <initial_condition> (not supported by the B200 path yet)")
     p = LapProblem.from_vehicle_track(veh, trk, s, form=form, closed=True, dissipation=o["dissipation"], sigma=o["sigma"])
     if veh.model == MODEL_F1:
-        x0 = np.tile(_f1_start_node(veh, o["speed"] * KMH), p.n_points)
+        x0 = workloads.f1_start_point(p, o["speed"])
     else:
         x0 = np.tile(_kart_start_node(veh, o["speed"] * KMH, form), p.n_points)
     nlp = CollocationNLP(p)
