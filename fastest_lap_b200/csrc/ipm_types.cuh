@@ -22,6 +22,7 @@ struct fl_ipm_lap            // state of one lap's iteration
 {
     double mu, tau, theta, phi, dphi, alpha, alpha_max, alpha_dual, dw, dw_last, dc, theta_max, theta_min;
     double f, cviol, dual_inf, compl_inf, err0, theta_soc_old, alpha_soc;
+    double dw_prev;          // regularisation the previous iteration's factorisation ended with
     int status, ls, iter, acc_count, n_filter, n_backtrack, n_soc, n_reg, n_fact, switching, n_restart, n_small, pad_;
     double filter[2 * IPM_FILTER_MAX];
 };

@@ -141,13 +141,14 @@ __device__ __forceinline__ double* kkt_invert(double* A, double* B, int& n_neg, 
                 const double f = KM(M, lane, p);
                 if (lane != p)
                 {
+                    const double fpv = f * pv;
 #pragma unroll
                     for (int i = 0; i < CB; ++i)
                     {
                         const int c = w + KW * i;
-                        if (NB % KW == 0 || c < NB) KM(N, lane, c) = KM(M, lane, c) - f * (KM(M, p, c) * pv);
+                        if (NB % KW == 0 || c < NB) KM(N, lane, c) = KM(M, lane, c) - fpv * KM(M, p, c);
                     }
-                    if ((p & (KW - 1)) == w) KM(N, lane, p) = -f * pv;
+                    if ((p & (KW - 1)) == w) KM(N, lane, p) = -fpv;
                 }
                 else
                 {
@@ -317,6 +318,8 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
     const int AQ = K.NINEQ * (NV + 1);
     const double dc = Lp ? Lp->dc : K.dc[lap];
     double dw = Lp ? Lp->dw : K.dw[lap];
+    // (tried: starting from the decayed regularisation of the previous iteration instead of 0 -- it saves failed
+    //  factorisations but nearly doubles the iteration count: Algorithm IC's "try 0 first" is kept)
 
     for (int attempt = 0;; ++attempt)
     {
@@ -518,6 +521,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
             {
                 if (dw > 0.0) Lp->dw_last = dw;
                 Lp->dw = dw;
+                Lp->dw_prev = dw;
                 sm.flag = 1;
             }
             else
