@@ -353,6 +353,7 @@ def main():
     val_ms = timed(0, K)
     ker_ms -= val_ms
     fg_ms = timed(EVAL_FG, K)
+    fp64_peak = nlp.measure_fp64_peak()            # DFMA/s, micro-kernel (no FP64 figure in MEASURED_PEAKS.json)
     # ---- end-to-end leg: host buffers in, host buffers out
     for k in range(3):
         ring[k % R].eval_all(hx, hl, 1.0, out=out)
@@ -400,7 +401,11 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "k_node_derivs<%s, all>" % v, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                             "bytes_per_node_eval": per_node_read + per_node_write, "fp64_ops_per_node_eval": nlp.ops_per_node["all"]},
+                             "bytes_per_node_eval": per_node_read + per_node_write, "fp64_ops_per_node_eval": nlp.ops_per_node["all"],
+                             "fp64": {"peak_measured_tflops": 2.0 * fp64_peak / 1e12, "peak_unit": "TFLOP/s (2 x DFMA/s, micro-kernel on this GPU)",
+                                      "achieved_gops": nlp.ops_per_node["all"] * p.n_points * B / (ker_ms / K * 1e-3) / 1e9,
+                                      "frac_of_instruction_peak": nlp.ops_per_node["all"] * p.n_points * B / (ker_ms / K * 1e-3) / fp64_peak,
+                                      "note": "operations of the generated code (add/mul/fma each one instruction) per second over the DFMA issue rate"}},
                 "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(p, x, lam)

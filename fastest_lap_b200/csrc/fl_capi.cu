@@ -540,6 +540,47 @@ int fl_flush_l2(fl_nlp* h)
     return 1;
 }
 
+} // extern "C"
+
+// FP64 pipe peak: every thread runs 8 independent chains of dependent DFMAs; 148 x 8 blocks of 256 threads
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i)
+    {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" {
+
+// Measured FP64 (non-tensor) peak of the handle's device in DFMA/s (the roofline denominator SURVEY.md 8d asks for).
+double fl_measure_fp64_peak(fl_nlp* h)
+{
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int blocks = sms * 8, iters = 1 << 14;
+    double* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double)) != cudaSuccess) return -1.0;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep)
+    {
+        cudaEventRecord(h->ev0, h->stream);
+        k_dfma_peak<<<blocks, 256, 0, h->stream>>>(out, iters, 0.999999, 1.0e-6);
+        cudaEventRecord(h->ev1, h->stream);
+        if (cudaEventSynchronize(h->ev1) != cudaSuccess) { cudaFree(out); return -1.0; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        const double rate = (double)blocks * 256 * 8 * iters / (ms * 1.0e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaFree(out);
+    return best;
+}
+
 void* fl_host_alloc(size_t bytes)
 {
     void* p = nullptr;

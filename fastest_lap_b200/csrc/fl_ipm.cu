@@ -48,6 +48,15 @@ struct fl_ipm
     long n_factor_launches = 0, n_solve_launches = 0, n_eval_full = 0, n_eval_fg = 0, n_rounds = 0;
     double ms_factor = 0.0, ms_solve = 0.0, ms_eval = 0.0, ms_total = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // partitioned (parallel-in-the-stages) mode
+    fl_kkt_part Q{};
+    int P = 0;                                   // separators (0: the mode is not available for this problem)
+    int part_policy = 0;                         // 0 auto (few active laps), 1 always, -1 never
+    int part_max_laps = 48;
+    bool part_round = false;                     // the current factorisation is a partitioned one
+    double *rDinv = nullptr, *rF = nullptr, *rLst = nullptr, *rAq = nullptr, *rywork = nullptr;
+    int *d_redneg = nullptr, *d_redzero = nullptr;
+    long n_part_factor = 0;
 };
 
 namespace {
@@ -72,6 +81,19 @@ template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, con
         else { fl_set_error("no KKT kernel for this stage size"); return 0; } \
     } while (0)
 
+template <int NV, int NEQ> void launch_factor_seg(fl_ipm* s, const fl_kkt_dev& K)
+{
+    k_kkt_factor_seg<NV, NEQ><<<dim3(s->P, s->B), KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K, s->Q);
+}
+template <int NV, int NEQ> void launch_solve_seg_fwd(fl_ipm* s, const fl_kkt_dev& K, const double* r1, const double* r2)
+{
+    k_kkt_solve_seg_fwd<NV, NEQ><<<dim3(s->P, s->B), KT, 0, s->nlp->stream>>>(K, s->Q, r1, r2);
+}
+template <int NV, int NEQ> void launch_solve_seg_bwd(fl_ipm* s, const fl_kkt_dev& K, const double* r2, double* dx, double* dy)
+{
+    k_kkt_solve_seg_bwd<NV, NEQ><<<dim3(s->P, s->B), KT, 0, s->nlp->stream>>>(K, s->Q, s->rywork, r2, dx, dy);
+}
+
 // FL_IPM_PROFILE=1: synchronise around the phases and accumulate their device time (diagnosis only)
 bool profiling() { static const bool on = std::getenv("FL_IPM_PROFILE") != nullptr; return on; }
 struct phase_timer
@@ -94,11 +116,44 @@ int kkt_factor(fl_ipm* s, const int* active, int ls_mode, bool with_ic)
     return 1;
 }
 
+// the reduced system over the separators, as the sequential kernels see it
+fl_kkt_dev reduced_system(const fl_ipm* s, const fl_kkt_dev& K)
+{
+    fl_kkt_dev R = K;
+    R.sep = s->Q.sep; R.P = s->P; R.redP = s->Q.redP; R.redT = s->Q.redT; R.redL = s->Q.redL; R.segcarry = s->Q.segcarry; R.segrb = s->Q.segrb;
+    R.Dinv = s->rDinv; R.F = s->rF; R.Lst = s->rLst; R.Aq = s->rAq; R.ywork = s->rywork; R.n_neg = s->d_redneg; R.n_zero = s->d_redzero;
+    return R;
+}
+
+// one pass of the partitioned factorisation with the dw / dc arrays (pivot counts per segment and of the reduced system)
+int kkt_factor_part(fl_ipm* s, const int* active, int ls_mode)
+{
+    phase_timer pt(s, &s->ms_factor);
+    fl_kkt_dev K = s->K;
+    K.active = active; K.ls_mode = ls_mode; K.laps = nullptr; K.o = s->I.o;
+    FLI_DISPATCH(launch_factor_seg, K);
+    const fl_kkt_dev R = reduced_system(s, K);
+    FLI_DISPATCH(launch_factor, R);
+    s->launches += 2; s->n_factor_launches += 1; s->n_part_factor += 1;
+    FLI_CUDA(cudaGetLastError());
+    return 1;
+}
+
 int kkt_solve(fl_ipm* s, const int* active, int ls_mode, const double* r1, const double* r2, double* dx, double* dy)
 {
     phase_timer pt(s, &s->ms_solve);
     fl_kkt_dev K = s->K;
     K.active = active; K.ls_mode = ls_mode; K.laps = nullptr;
+    if (s->part_round)
+    {
+        FLI_DISPATCH(launch_solve_seg_fwd, K, r1, r2);
+        const fl_kkt_dev R = reduced_system(s, K);
+        FLI_DISPATCH(launch_solve, R, r1, r2, dx, dy);
+        FLI_DISPATCH(launch_solve_seg_bwd, K, r2, dx, dy);
+        s->launches += 3; s->n_solve_launches += 1;
+        FLI_CUDA(cudaGetLastError());
+        return 1;
+    }
     FLI_DISPATCH(launch_solve, K, r1, r2, dx, dy);
     s->launches += 1; s->n_solve_launches += 1;
     FLI_CUDA(cudaGetLastError());
@@ -262,6 +317,26 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
         fl_ipm_destroy(s);
         return nullptr;
     }
+    // partitioned mode: about sqrt(S) separators
+    if (S >= 64)
+    {
+        int Pn = (int)std::lround(std::sqrt((double)S));
+        Pn = Pn < 3 ? 3 : (Pn > 128 ? 128 : Pn);
+        std::vector<int> sep;
+        for (int k = 0; k < Pn; ++k) { const int v0 = (int)((long)k * S / Pn); if (sep.empty() || v0 > sep.back()) sep.push_back(v0); }
+        s->P = (int)sep.size();
+        const size_t BP = (size_t)B * s->P;
+        s->Q.sep = dupload(sep, own); s->Q.P = s->P;
+        s->Q.redP = dalloc<double>(BP * NV * NV, own); s->Q.redT = dalloc<double>(BP * NB2, own); s->Q.redL = dalloc<double>(BP * s->NB * NV, own);
+        s->Q.segcarry = dalloc<double>(BP * NV, own); s->Q.segrb = dalloc<double>(BP * s->NB, own);
+        s->Q.segneg = dalloc<int>(BP, own); s->Q.segzero = dalloc<int>(BP, own);
+        s->rDinv = dalloc<double>(BP * NB2, own); s->rF = dalloc<double>(BP * NB2, own); s->rLst = dalloc<double>(BP * s->NB * NV, own);
+        s->rAq = dalloc<double>(BP * NINEQ * (NV + 1), own); s->rywork = dalloc<double>(BP * s->NB, own);
+        s->d_redneg = dalloc<int>(B, own); s->d_redzero = dalloc<int>(B, own);
+        if (!K.F) K.F = dalloc<double>((size_t)B * S * NB2, own);          // open laps: the segments' fill blocks
+        if (!s->rywork || !s->rDinv || !K.F) { fl_set_error("out of device memory for the partitioned factorisation"); fl_ipm_destroy(s); return nullptr; }
+        if (const char* e = std::getenv("FL_IPM_PART_MAX")) s->part_max_laps = std::atoi(e);
+    }
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
     if (P.closed && S == 2) { fl_set_error("closed laps need at least three nodes"); fl_ipm_destroy(s); return nullptr; }
     return s;
@@ -290,7 +365,9 @@ int fl_kkt_factor_solve(fl_ipm* s, const double* x, const double* lambda, const 
     std::vector<fl_ipm_lap> laps(B);
     for (size_t b = 0; b < B; ++b) { std::memset(&laps[b], 0, sizeof(fl_ipm_lap)); laps[b].dw = dw[b]; laps[b].dc = dc[b]; }
     FLI_CUDA(cudaMemcpyAsync(I.lap, laps.data(), B * sizeof(fl_ipm_lap), cudaMemcpyHostToDevice, st));
-    if (!kkt_factor(s, nullptr, ls_mode, false)) return 0;
+    s->part_round = s->P > 0 && s->part_policy > 0;
+    if (s->part_round) { if (!kkt_factor_part(s, nullptr, ls_mode)) return 0; }
+    else if (!kkt_factor(s, nullptr, ls_mode, false)) return 0;
     fl_ipm_options keep = s->I.o;
     s->I.o.refine_steps = refine_steps;
     const int ok = solve_refined(s, nullptr, ls_mode, I.dx, I.dy);
@@ -298,9 +375,19 @@ int fl_kkt_factor_solve(fl_ipm* s, const double* x, const double* lambda, const 
     if (!ok) return 0;
     FLI_CUDA(cudaMemcpyAsync(dx, I.dx, B * I.n * sizeof(double), cudaMemcpyDeviceToHost, st));
     FLI_CUDA(cudaMemcpyAsync(dy, I.dy, B * I.m * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (n_neg) FLI_CUDA(cudaMemcpyAsync(n_neg, s->d_neg, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (n_zero) FLI_CUDA(cudaMemcpyAsync(n_zero, s->d_zero, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n_neg) FLI_CUDA(cudaMemcpyAsync(n_neg, s->part_round ? s->d_redneg : s->d_neg, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n_zero) FLI_CUDA(cudaMemcpyAsync(n_zero, s->part_round ? s->d_redzero : s->d_zero, B * sizeof(int), cudaMemcpyDeviceToHost, st));
     FLI_CUDA(cudaStreamSynchronize(st));
+    if (s->part_round)
+    {
+        // add the pivots of the segment interiors
+        std::vector<int> sn(B * s->P), sz(B * s->P);
+        FLI_CUDA(cudaMemcpy(sn.data(), s->Q.segneg, sn.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        FLI_CUDA(cudaMemcpy(sz.data(), s->Q.segzero, sz.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t b = 0; b < B; ++b)
+            for (int k = 0; k < s->P; ++k) { if (n_neg) n_neg[b] += sn[b * s->P + k]; if (n_zero) n_zero[b] += sz[b * s->P + k]; }
+        s->part_round = false;
+    }
     return 1;
 }
 
@@ -320,6 +407,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     k_ipm_init_slacks<<<B, IPM_BLOCK, 0, st>>>(I);
     s->launches += 2; s->n_eval_full += 1;
     // least-squares multipliers (Ipopt's default start): [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
+    s->part_round = false;
     if (!kkt_factor(s, nullptr, 1, false)) return 0;
     if (!solve_refined(s, nullptr, 1, I.dx, I.dy)) return 0;
     k_ipm_take_multipliers<<<B, IPM_BLOCK, 0, st>>>(I);
@@ -344,8 +432,21 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
                          l0.cviol, l0.dual_inf, l0.mu, l0.dw_last, l0.alpha, l0.status);
         }
         if (cnt[0] == 0) break;
-        // factorisation; the inertia correction (Algorithm IC) runs inside the kernel, lap by lap
-        if (!kkt_factor(s, I.act_run, 0, true)) return 0;
+        // factorisation.  Many active laps: one block per lap walks the whole chain, the inertia correction (Algorithm IC)
+        // runs inside the kernel.  Few active laps: the chain is cut into segments factorised by their own blocks, and IC
+        // runs between the attempts.
+        s->part_round = s->P > 0 && (s->part_policy > 0 || (s->part_policy == 0 && cnt[0] <= s->part_max_laps));
+        if (!s->part_round) { if (!kkt_factor(s, I.act_run, 0, true)) return 0; }
+        else
+            for (int attempt = 0; attempt < 200; ++attempt)
+            {
+                if (!kkt_factor_part(s, I.act_factor, 0)) return 0;
+                if (!zero_counters(s)) return 0;
+                k_ipm_inertia_part<<<blocks_b, 128, 0, st>>>(I, s->Q, s->d_redneg, s->d_redzero, B);
+                s->launches += 1;
+                if (!read_counters(s, cnt)) return 0;
+                if (cnt[1] == 0) break;
+            }
         // search direction
         k_ipm_rhs<<<B, IPM_BLOCK, 0, st>>>(I, 0);
         s->launches += 1;
@@ -406,6 +507,15 @@ int fl_ipm_results(fl_ipm* s, double* x, double* y, double* zl, double* zu, doub
         if (errors) { errors[4 * b] = laps[b].err0; errors[4 * b + 1] = laps[b].cviol; errors[4 * b + 2] = laps[b].dual_inf; errors[4 * b + 3] = laps[b].mu; }
     }
     return 1;
+}
+
+// Partitioned (parallel-in-the-stages) factorisation: policy 0 = automatic (when at most `max_laps` laps are active), 1 = always,
+// -1 = never.  Returns the number of separators (0: not available for this problem).
+int fl_ipm_set_partitioned(fl_ipm* s, int policy, int max_laps)
+{
+    s->part_policy = policy;
+    if (max_laps > 0) s->part_max_laps = max_laps;
+    return s->P;
 }
 
 // counters of the last solve: [0] kernel launches of the solver (callbacks excluded), [1] factorisation launches, [2] solve launches,

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cmath>
 #include "kkt_kernels.cuh"
+#include "kkt_part_kernels.cuh"
 
 constexpr int IPM_BLOCK = 128;
 constexpr int IPM_NVMAX = 17, IPM_NCPEMAX = 21, IPM_MAX_RESTARTS = 3;
@@ -654,6 +655,31 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
             if (threadIdx.x == 0) { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; }
         }
     }
+}
+
+// Algorithm IC between the attempts of the partitioned factorisation: the inertia is the sum of the negative pivots of
+// the segment blocks and of the reduced system.  Laps with a correct inertia leave the mask, the others get a larger dw.
+__global__ void k_ipm_inertia_part(const fl_ipm_dev I, const fl_kkt_part Q, const int* redneg, const int* redzero, int batch)
+{
+    const int lap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lap >= batch || !I.act_factor[lap]) return;
+    fl_ipm_lap& L = I.lap[lap];
+    const fl_ipm_options& o = I.o;
+    int neg = redneg[lap], zero = redzero[lap];
+    for (int k = 0; k < Q.P; ++k) { neg += Q.segneg[(size_t)lap * Q.P + k]; zero += Q.segzero[(size_t)lap * Q.P + k]; }
+    L.n_fact += 1;
+    if (neg == I.S * I.NEQ && zero == 0)
+    {
+        I.act_factor[lap] = 0;
+        if (L.dw > 0.0) L.dw_last = L.dw;
+        return;
+    }
+    L.n_reg += 1;
+    if (L.dw == 0.0) L.dw = (L.dw_last == 0.0) ? o.delta_w_0 : fmax(o.delta_w_min, o.kappa_w_minus * L.dw_last);
+    else L.dw *= (L.dw_last == 0.0) ? o.kappa_w_plus_bar : o.kappa_w_plus;
+    if (L.dw > o.delta_w_max) { L.status = IPM_REGULARISATION_FAILED; I.act_factor[lap] = 0; I.act_run[lap] = 0; return; }
+    I.dw[lap] = L.dw;
+    atomicAdd(I.counters + 1, 1);
 }
 
 // mask of the laps whose trial point is waiting to be evaluated

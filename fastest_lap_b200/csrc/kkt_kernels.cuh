@@ -62,6 +62,14 @@ struct fl_kkt_dev
     int* n_neg;               // [batch] negative pivots
     int* n_zero;              // [batch] vanishing pivots
     int ls_mode;              // 1: least-squares multiplier system (W = 0, Sigma_x = 1, D_ineq = 1)
+    // partitioned (parallel-in-the-stages) mode, see kkt_part_kernels.cuh: the reduced system over the separator stages
+    const int* sep;           // [P] separator stages (ascending, sep[0] = 0), or null: the kernels below then run over all stages
+    int P;
+    const double* redP;       // [batch][P][NV*NV]  Schur term onto separator k's x-x block from its right segment
+    const double* redT;       // [batch][P][NB*NB]  Schur term onto separator k from its left segment (through the fill blocks)
+    const double* redL;       // [batch][P][NB*NV]  coupling K~[separator k, separator k-1] (k = 0: the corner block of closed laps)
+    const double* segcarry;   // [batch][P][NV]     solves: right-hand-side update of separator k from its right segment
+    const double* segrb;      // [batch][P][NB]     solves: the same from its left segment
     fl_ipm_lap* laps;         // [batch] or null.  Not null: dw is read from / written to the lap records and the inertia
                               // correction loop runs in the kernel; null: one pass with dw[], the pivot counts are reported
     fl_ipm_options o;
@@ -309,13 +317,26 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
     if (K.active && !K.active[lap]) return;
     fl_ipm_lap* Lp = K.laps ? K.laps + lap : nullptr;
     if (Lp && Lp->status != IPM_RUNNING) return;
-    const int S = K.S;
+    const int S = K.sep ? K.P : K.S;           // reduced system over the separators, or the whole chain
     const bool cyc = K.closed && S > 2;
     double* gD = K.Dinv + (size_t)lap * S * NB * NB;
     double* gF = K.F ? K.F + (size_t)lap * S * NB * NB : nullptr;
     double* gL = K.Lst + (size_t)lap * S * NB * NV;
     double* gA = K.Aq + (size_t)lap * S * (K.NINEQ * (NV + 1));
     const int AQ = K.NINEQ * (NV + 1);
+    const double* rP = K.sep ? K.redP + (size_t)lap * S * NV * NV : nullptr;
+    const double* rT = K.sep ? K.redT + (size_t)lap * S * NB * NB : nullptr;
+    const double* rL = K.sep ? K.redL + (size_t)lap * S * NB * NV : nullptr;
+    // coupling block of (reduced) stage j into sm.L
+    auto coupling = [&](int j) {
+        if (!K.sep) { St::gather_coupling(K, lap, j, sm.L); return; }
+        if (lane < NB)
+        {
+#pragma unroll
+            for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.L, lane, c) = rL[(size_t)j * NB * NV + lane + NB * c]; }
+        }
+        __syncthreads();
+    };
     const double dc = Lp ? Lp->dc : K.dc[lap];
     double dw = Lp ? Lp->dw : K.dw[lap];
     // (tried: starting from the decayed regularisation of the previous iteration instead of 0 -- it saves failed
@@ -336,14 +357,29 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
         if (cyc)
         {
             // F_{S-1} = K[0, S-1]: coupling of stage 0 with its left neighbour (the closing element)
-            St::gather_coupling(K, lap, 0, sm.L);
+            coupling(0);
 #pragma unroll
             for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) KM(sm.F, lane, c) = KM(sm.L, lane, c); }
             __syncthreads();
         }
         for (int j = S - 1; j >= 0; --j)
         {
-            St::gather_diag(K, lap, j, dw, dc, sm.M, sm.aq);
+            St::gather_diag(K, lap, K.sep ? K.sep[j] : j, dw, dc, sm.M, sm.aq);
+            if (K.sep && lane < NB)
+            {
+                // what the eliminated segments on both sides of this separator hand to it
+#pragma unroll
+                for (int i = 0; i < CB; ++i)
+                {
+                    const int c = w + KW * i;
+                    if (c < NB)
+                    {
+                        double v = rT[(size_t)j * NB * NB + lane + NB * c];
+                        if (lane < NV && c < NV) v += rP[(size_t)j * NV * NV + lane + NV * c];
+                        KM(sm.M, lane, c) -= v;
+                    }
+                }
+            }
             // keep the inequality rows and 1/D for the solves
             for (int k = t; k < K.NINEQ * NV; k += KT) gA[(size_t)j * AQ + k] = sm.aq[(k / NV) * KLD + (k % NV)];
             if (t < K.NINEQ) gA[(size_t)j * AQ + K.NINEQ * NV + t] = sm.aq[K.NINEQ * KLD + t];
@@ -363,9 +399,10 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
             // non-zero columns of the fill block: x of stage j, except at stage 1 where K[0, 1] = L_1^T brings the multiplier columns
             const int KF = (cyc && j == 1) ? NB : NV;
             const int ncpl = K.ls_mode ? 0 : K.NCPL;
+            const int kL0 = K.sep ? 0 : NV;            // first row of L that can be non-zero (reduced couplings are dense)
             if (j >= 1)
             {
-                St::gather_coupling(K, lap, j, sm.L);
+                coupling(j);
                 if (lane < NB)
                 {
 #pragma unroll
@@ -414,14 +451,14 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
 #pragma unroll
                     for (int i = 0; i < CV; ++i) acc[i] = 0.0;
                     // rows of L that can be non-zero: the NEQ multiplier rows, and the diagonal coupling entries (cp, cp)
-#pragma unroll
-                    for (int k = NV; k < NB; ++k)
+#pragma unroll 4
+                    for (int k = kL0; k < NB; ++k)
                     {
                         const double a = KM(Mi, lane, k);
 #pragma unroll
                         for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.L, k, c); }
                     }
-                    for (int q = 0; q < ncpl; ++q)
+                    for (int q = 0; q < (K.sep ? 0 : ncpl); ++q)
                     {
                         const int cp = K.t.ctrl_pos[q];
 #pragma unroll
@@ -455,14 +492,14 @@ __global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
                 for (int i = 0; i < CV; ++i) acc[i] = 0.0;
                 if (chain)
                 {
-#pragma unroll
-                    for (int k = NV; k < NB; ++k)
+#pragma unroll 4
+                    for (int k = kL0; k < NB; ++k)
                     {
                         const double a = KM(sm.L, k, lane);
 #pragma unroll
                         for (int i = 0; i < CV; ++i) { const int c = w + KW * i; if (c < NV) acc[i] += a * KM(sm.XL, k, c); }
                     }
-                    for (int q = 0; q < ncpl; ++q)
+                    for (int q = 0; q < (K.sep ? 0 : ncpl); ++q)
                     {
                         const int cp = K.t.ctrl_pos[q];
                         if (lane == cp)
@@ -555,27 +592,31 @@ __global__ void __launch_bounds__(KT) k_kkt_solve(const fl_kkt_dev K, const doub
     const int lap = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
     if (K.laps && K.laps[lap].status != IPM_RUNNING) return;
-    const int S = K.S;
+    const int S = K.sep ? K.P : K.S;
     const bool cyc = K.closed && S > 2;
     const double* gD = K.Dinv + (size_t)lap * S * NB * NB;
     const double* gF = K.F ? K.F + (size_t)lap * S * NB * NB : nullptr;
     const double* gL = K.Lst + (size_t)lap * S * NB * NV;
     const double* gA = K.Aq + (size_t)lap * S * (K.NINEQ * (NV + 1));
     double* yw = K.ywork + (size_t)lap * S * NB;
+    const double* sc = K.sep ? K.segcarry + (size_t)lap * S * NV : nullptr;
+    const double* sb = K.sep ? K.segrb + (size_t)lap * S * NB : nullptr;
     r1 += (size_t)lap * K.n; r2 += (size_t)lap * K.m; dx += (size_t)lap * K.n; dy += (size_t)lap * K.m;
     const int AQ = K.NINEQ * (NV + 1);
 
     // condensed right-hand side of stage j (before the updates from later stages); threads t < NB
     auto rhs = [&](int j) -> double {
-        const int e = St::e_in(K, j);
+        const int js = K.sep ? K.sep[j] : j;          // stage of the chain
+        const int e = St::e_in(K, js);
         double b = 0.0;
+        if (K.sep && t < NB) b = sb[(size_t)j * NB + t] + (t < NV ? sc[(size_t)j * NV + t] : 0.0);
         if (t < NV)
         {
-            b = r1[(size_t)j * NV + t];
+            b += r1[(size_t)js * NV + t];
             for (int q = 0; q < K.NINEQ; ++q)
                 b += gA[(size_t)j * AQ + q * NV + t] * gA[(size_t)j * AQ + K.NINEQ * NV + q] * r2[(size_t)e * K.NCPE + K.t.ineq_rows[q]];
         }
-        else if (t < NB) b = r2[(size_t)e * K.NCPE + K.t.eq_rows[t - NV]];
+        else if (t < NB) b += r2[(size_t)e * K.NCPE + K.t.eq_rows[t - NV]];
         return b;
     };
     double dreg[CB], freg[CB], lreg[CB];
@@ -709,9 +750,10 @@ __global__ void __launch_bounds__(KT) k_kkt_solve(const fl_kkt_dev K, const doub
     // ---- scatter: dx, equality multipliers, then the condensed inequality multipliers dy_q = (a_q . dx_j - r2_q) / D_q
     for (int j = w; j < S; j += KW)
     {
-        const int e = St::e_in(K, j);
+        const int js = K.sep ? K.sep[j] : j;
+        const int e = St::e_in(K, js);
         const double z = (lane < NB) ? yw[(size_t)j * NB + lane] : 0.0;
-        if (lane < NV) dx[(size_t)j * NV + lane] = z;
+        if (lane < NV) dx[(size_t)js * NV + lane] = z;
         else if (lane < NB) dy[(size_t)e * K.NCPE + K.t.eq_rows[lane - NV]] = z;
         for (int q = 0; q < K.NINEQ; ++q)
         {

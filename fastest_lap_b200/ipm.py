@@ -37,6 +37,7 @@ def _bind(lib):
     lib.fl_ipm_results.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
     lib.fl_ipm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_long), _dp]
     lib.fl_kkt_factor_solve.argtypes = [C.c_void_p] + [_dp] * 8 + [C.c_int, C.c_int, _dp, _dp, _ip, _ip]
+    lib.fl_ipm_set_partitioned.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib._ipm_bound = True
 
 
@@ -63,6 +64,11 @@ class LapSolver:
         self._h = self._lib.fl_ipm_create(nlp._h, C.byref(options) if options is not None else None, *args)
         if not self._h:
             raise RuntimeError("fl_ipm_create: " + self._lib.fl_last_error().decode())
+
+    def set_partitioned(self, policy=0, max_laps=0):
+        """Schedule of the KKT factorisation: 0 automatic, 1 always parallel in the stages, -1 always one block per lap.
+        Returns the number of separator stages (0: not available for this problem)."""
+        return int(self._lib.fl_ipm_set_partitioned(self._h, int(policy), int(max_laps)))
 
     def close(self):
         if getattr(self, "_h", None):

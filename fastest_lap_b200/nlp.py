@@ -47,6 +47,8 @@ def load_library():
     lib.fl_nlp_batch.argtypes = [C.c_void_p]
     lib.fl_nlp_bounds.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     lib.fl_problem_bounds.argtypes = [C.POINTER(_Desc), _dp, _dp, _dp, _dp]
+    lib.fl_measure_fp64_peak.restype = C.c_double
+    lib.fl_measure_fp64_peak.argtypes = [C.c_void_p]
     lib.fl_nlp_structure.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
     lib.fl_nlp_ops_per_node.argtypes = [C.c_void_p, _ip]
     lib.fl_nlp_workspace_slots.argtypes = [C.c_void_p, _ip, _ip]
@@ -231,6 +233,10 @@ class CollocationNLP:
         if ms < 0:
             raise RuntimeError("fl_time_device: " + self._lib.fl_last_error().decode())
         return ms
+
+    def measure_fp64_peak(self):
+        """DFMA/s of the device's FP64 pipe (micro-kernel measurement)."""
+        return float(self._lib.fl_measure_fp64_peak(self._h))
 
     def flush_l2(self):
         self._check(self._lib.fl_flush_l2(self._h), "fl_flush_l2")

@@ -132,6 +132,8 @@ double fl_time_device(fl_nlp* nlp, int what, double obj_factor, int reps);
 long fl_kernel_launches(const fl_nlp* nlp);                      /* kernels launched by this handle so far */
 /* Writes a scratch buffer larger than the L2 cache on the handle's stream (benchmark hygiene between timed iterations). */
 int  fl_flush_l2(fl_nlp* nlp);
+/* FP64 (non-tensor) pipe peak of the handle's device, measured with a DFMA micro-kernel: fused multiply-adds per second */
+double fl_measure_fp64_peak(fl_nlp* nlp);
 /* Page-locked host memory for the host-buffer entry points (pageable memory works too, at lower PCIe throughput). */
 void* fl_host_alloc(size_t bytes);
 void  fl_host_free(void* p);
@@ -169,6 +171,10 @@ int fl_ipm_solve(fl_ipm* ipm, const double* x0, int verbose);
 int fl_ipm_results(fl_ipm* ipm, double* x, double* y, double* zl, double* zu, double* obj, int* status, int* iters, double* errors);
 /* [0] solver kernel launches, [1] factorisation launches, [2] solve launches, [3] full callback rounds, [4] f/g-only rounds, [5] outer rounds */
 void fl_ipm_stats(const fl_ipm* ipm, long stats[6], double* device_ms);
+/* The factorisation has two schedules: one block per lap walking the whole chain (throughput: many laps), or the chain cut
+ * at ~sqrt(n_stages) separators whose segments are factorised in parallel (latency: few laps).  policy 0 = automatic (the
+ * second one when at most max_laps laps are still active), 1 = always the second, -1 = never.  Returns the number of separators. */
+int fl_ipm_set_partitioned(fl_ipm* ipm, int policy, int max_laps);
 /* One factorisation + solve of  [W + diag(sigx) + dw, J^T; J, -D][dx; dy] = [r1; r2]  at (x, lambda) for every lap of the batch
  * (D = dc on equality rows, 1/(sigs + dw) + dc on inequality rows; sigs is [batch][n_elements * 6], element-major);
  * ls_mode = 1 solves the least-squares multiplier system instead (W = 0, sigx = 1, D = 1 on inequality rows).

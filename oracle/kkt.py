@@ -225,3 +225,84 @@ class BlockCyclicLDL:
             if cyc:
                 z[j] -= self.XF[j] @ z[0]
         return z
+
+
+class PartitionedLDL:
+    """The same elimination with the chain cut at P separator stages (parallel in the stages: what the device runs when few
+    laps are active).  The interior of every segment (a, b) between consecutive separators is eliminated backwards,
+    independently of the other segments, carrying the fill G_j = K[b, j] towards its right separator exactly as the
+    sequential algorithm carries F_j = K[0, j] towards stage 0; what is left is a block-(cyclic-)tridiagonal system over
+    the separators with couplings of the original shape (only the x columns of the left separator are non-zero), which
+    the sequential algorithm factorises.  The inertia is the sum over all pivot blocks, interior and separator ones."""
+
+    def __init__(self, Dg, Lo, cyclic, n_sep):
+        S, nb, _ = Dg.shape
+        self.S, self.nb, self.cyclic = S, nb, bool(cyclic)
+        P = max(3 if cyclic else 1, min(n_sep, S // 2))
+        self.sep = np.array(sorted(set((np.arange(P) * S) // P)))
+        P = self.P = len(self.sep)
+        self.Lo, self.Dinv = Lo, np.zeros((S, nb, nb))
+        self.G = np.zeros((S, nb, nb))           # G[j] = K[b, j] for interior stage j of segment (a, b)
+        self.right = np.full(S, -1)              # right separator of every interior stage
+        Dr = np.array([Dg[s].copy() for s in self.sep])
+        Lr = np.zeros((P, nb, nb))
+        pos = neg = zero = 0
+        self.segments = []
+        for k in range(P):
+            a = self.sep[k]
+            b = self.sep[(k + 1) % P] if (k + 1 < P or self.cyclic) else None      # right separator (None: open end)
+            hi = (self.sep[k + 1] if k + 1 < P else S) - 1
+            inter = list(range(a + 1, hi + 1))
+            self.segments.append((a, b, inter))
+            kb = (k + 1) % P
+            if not inter:
+                if b is not None:
+                    Lr[kb] = Lo[b]               # adjacent separators keep their original coupling
+                continue
+            Gcur = Lo[b].copy() if b is not None else None         # K[b, b-1] (for b = 0: the corner block K[0, S-1])
+            for j in reversed(inter):
+                Dj = 0.5 * (Dg[j] + Dg[j].T)
+                Di, q, z = pivoted_gauss_jordan(Dj)
+                pos, neg, zero = pos + nb - q - z, neg + q, zero + z
+                self.Dinv[j] = Di
+                XL = Di @ Lo[j]
+                tgt = Dg[j - 1] if j - 1 != a else Dr[k]
+                tgt -= Lo[j].T @ XL
+                if Gcur is not None:
+                    self.G[j] = Gcur
+                    self.right[j] = kb
+                    Dr[kb] -= Gcur @ (Di @ Gcur.T)
+                    Gcur = -Gcur @ XL
+            if b is not None:
+                Lr[kb] = Gcur                    # reduced coupling K~[b, a]
+        self.red = BlockCyclicLDL(Dr, Lr, self.cyclic and P > 2)
+        rp, rn, rz = self.red.inertia
+        self.inertia = (pos + rp, neg + rn, zero + rz)
+        self.ok = self.red.ok
+
+    def solve(self, rhs):
+        S, nb, P = self.S, self.nb, self.P
+        b = np.array(rhs, dtype=float)
+        y = np.zeros_like(b)
+        br = np.array([b[s] for s in self.sep])
+        for k, (a, bb, inter) in enumerate(self.segments):
+            for j in reversed(inter):
+                y[j] = self.Dinv[j] @ b[j]
+                if j - 1 != a:
+                    b[j - 1] -= self.Lo[j].T @ y[j]
+                else:
+                    br[k] -= self.Lo[j].T @ y[j]
+                if self.right[j] >= 0:
+                    br[self.right[j]] -= self.G[j] @ y[j]
+        zr = self.red.solve(br)
+        z = np.zeros_like(b)
+        for k, (a, bb, inter) in enumerate(self.segments):
+            z[a] = zr[k]
+            prev = zr[k]
+            for j in inter:
+                w = self.Lo[j] @ prev
+                if self.right[j] >= 0:
+                    w = w + self.G[j].T @ zr[self.right[j]]
+                z[j] = y[j] - self.Dinv[j] @ w
+                prev = z[j]
+        return z

@@ -17,8 +17,9 @@ def _ineq_rows(p):
     return np.array([r for r in range(p.ncpe) if r not in eq])
 
 
+@pytest.mark.parametrize("partitioned", [False, True])
 @pytest.mark.parametrize("case", CASES)
-def test_kkt_factor_solve_matches_sparse_lu(case):
+def test_kkt_factor_solve_matches_sparse_lu(case, partitioned):
     """[W + Sigma + dw, J^T; J, -D] solved by the device block factorisation == scipy's sparse LU of the same matrix built
     from the oracle's derivatives; the pivot signs give the inertia (n, m_eq) of the condensed matrix."""
     from fastest_lap_b200.nlp import CollocationNLP
@@ -43,6 +44,9 @@ def test_kkt_factor_solve_matches_sparse_lu(case):
     sol = spla.splu(K).solve(np.concatenate([r1, r2]))
     nlp = CollocationNLP(p)
     solver = LapSolver(nlp)
+    if partitioned:
+        # the chain cut at ~sqrt(n_stages) separators, segments factorised in parallel (kkt_part_kernels.cuh)
+        assert solver.set_partitioned(1) >= 3
     dx, dy, neg, zero = solver.kkt_factor_solve(x, lam, sigx, sigs, dw, dc, r1, r2, refine_steps=2)
     n_eq = p.n_elements * (p.ncpe - len(ineq))
     assert neg[0] == n_eq and zero[0] == 0
@@ -64,6 +68,22 @@ def test_wrong_inertia_is_reported():
     ni = p.n_elements * 6
     _, _, neg, _ = solver.kkt_factor_solve(ex["x"], ex["lam"], np.full(p.n, -1.0e4), np.ones(ni), 0.0, 1e-9, np.zeros(p.n), np.zeros(p.m))
     assert neg[0] > p.n_elements * (p.ncpe - 6)
+    solver.close(); nlp.close()
+
+
+def test_partitioned_schedule_converges_to_the_same_lap():
+    """The parallel-in-the-stages factorisation drives the same iteration: F1 Catalunya from the steady-state start, lap
+    time of the reference to 1e-6."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    from fastest_lap_b200 import workloads
+    p, ex = load_golden("f1_catalunya_discrete")
+    nlp = CollocationNLP(p)
+    solver = LapSolver(nlp)
+    solver.set_partitioned(1)
+    out = solver.solve(workloads.f1_start_point(p, 50.0))
+    assert out["status"][0] == 1
+    assert abs(lap_time(p, out["x"][0], out["obj"][0]) - float(ex["laptime"])) <= 1e-6 * float(ex["laptime"])
     solver.close(); nlp.close()
 
 
