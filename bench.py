@@ -277,6 +277,34 @@ def gg_leg(args, torch, dist, world, rank, local):
             "reference_cpu": "the reference solves these NLPs one after the other with Ipopt (steady_state.hpp:594-880), ~130 solves per speed"}
 
 
+
+def single_lap_leg(args, torch, local):
+    """One lap at a time (replicas only): BASELINE configs[0] (F1, Catalunya, 500 nodes: the reference's README example,
+    "approximately 1 minute") and configs[2] (8000 nodes), solved from the steady-state start on this rank's GPU with the
+    parallel-in-the-stages factorisation; wall time through the public API."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    out = {}
+    for name, n in (("f1_catalunya_500", 500), ("f1_catalunya_8000", args.nodes)):
+        p = workloads.f1_catalunya(n)
+        nlp = CollocationNLP(p, device=local)
+        solver = LapSolver(nlp)
+        x0 = workloads.f1_start_point(p, 50.0, device=local)
+        solver.solve(x0) if n == 500 else None            # warm-up of the 500-node case (library initialisation)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = solver.solve(x0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[name] = {"nodes": n, "seconds": dt, "status": int(r["status"][0]), "iterations": int(r["iters"][0]),
+                     "lap_time_s": lap_time(p, r["x"][0], r["obj"][0]), "factorisations": int(r["stats"]["factor_launches"])}
+        solver.close(); nlp.close()
+    out["f1_catalunya_500"]["reference_lap_time_s"] = 77.791438
+    out["reference_cpu"] = "README.md:26 of the reference: approximately 1 minute for the 500-point lap"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -288,6 +316,7 @@ def main():
     ap.add_argument("--laps", type=int, default=N_LAPS, help="laps of the batched callback leg (0 = skip)")
     ap.add_argument("--solve-laps", type=int, default=N_SOLVE, help="laps solved to convergence in the laps/s leg (0 = skip)")
     ap.add_argument("--solve-max-iter", type=int, default=250)
+    ap.add_argument("--single-laps", type=int, default=1, help="1: also time single-lap solves (500 and --nodes nodes) on rank 0")
     ap.add_argument("--gg-speeds", type=int, default=32, help="speeds of the G-G sweep leg (0 = skip)")
     ap.add_argument("--gg-lat", type=int, default=64)
     args = ap.parse_args()
@@ -424,6 +453,8 @@ def main():
         if rank == 0:
             line["batched_solve"] = sl
             line["gpu_launches"] += int(sl["rank0_launches"]["solver_launches"]) + 3 * int(sl["rank0_launches"]["full_rounds"]) + 2 * int(sl["rank0_launches"]["fg_rounds"])
+    if args.single_laps and rank == 0:
+        line["single_lap_solve"] = single_lap_leg(args, torch, local)
     if args.gg_speeds > 0:
         gl = gg_leg(args, torch, dist, world, rank, local)
         if rank == 0:

@@ -51,6 +51,8 @@ struct fl_ipm
     // partitioned (parallel-in-the-stages) mode
     fl_kkt_part Q{};
     int P = 0;                                   // separators (0: the mode is not available for this problem)
+    int vec_block = IPM_BLOCK;                   // threads per lap of the vector kernels (IPM_BLOCK_MAX for small batches)
+    size_t vec_smem = (size_t)IPM_NCPEMAX * IPM_BLOCK * sizeof(double);
     int part_policy = 0;                         // 0 auto (few active laps), 1 always, -1 never
     int part_max_laps = 48;
     bool part_round = false;                     // the current factorisation is a partitioned one
@@ -166,16 +168,16 @@ int solve_refined(fl_ipm* s, const int* active, int ls_mode, double* ox, double*
     const fl_ipm_dev& I = s->I;
     cudaStream_t st = s->nlp->stream;
     if (!kkt_solve(s, active, ls_mode, I.r1, I.r2, s->wx, s->wy)) return 0;
-    k_ipm_axpy_sol<<<s->B, IPM_BLOCK, 0, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 1);
+    k_ipm_axpy_sol<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 1);
     if (refine_steps < 0) refine_steps = I.o.refine_steps;
     for (int k = 0; k < refine_steps; ++k)
     {
-        k_ipm_residual<<<s->B, IPM_BLOCK, 0, st>>>(I, active, ls_mode);
+        k_ipm_residual<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, ls_mode);
         if (!kkt_solve(s, active, ls_mode, I.e1, I.e2, s->wx, s->wy)) return 0;
-        k_ipm_axpy_sol<<<s->B, IPM_BLOCK, 0, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 0);
+        k_ipm_axpy_sol<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 0);
         s->launches += 2;
     }
-    k_ipm_axpy_sol<<<s->B, IPM_BLOCK, 0, st>>>(I, active, I.tx, I.ty, ox, oy, 1);
+    k_ipm_axpy_sol<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, I.tx, I.ty, ox, oy, 1);
     s->launches += 2;
     FLI_CUDA(cudaGetLastError());
     return 1;
@@ -337,6 +339,16 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
         if (!s->rywork || !s->rDinv || !K.F) { fl_set_error("out of device memory for the partitioned factorisation"); fl_ipm_destroy(s); return nullptr; }
         if (const char* e = std::getenv("FL_IPM_PART_MAX")) s->part_max_laps = std::atoi(e);
     }
+    // vector kernels: one block per lap; wide blocks when the batch alone cannot fill the machine
+    if (B <= 64) s->vec_block = IPM_BLOCK_MAX;
+    else if (B <= 512) s->vec_block = 256;
+    s->vec_smem = (size_t)IPM_NCPEMAX * s->vec_block * sizeof(double);
+    {
+        const void* kernels[] = { (const void*)k_ipm_init, (const void*)k_ipm_init_slacks, (const void*)k_ipm_take_multipliers, (const void*)k_ipm_state,
+                                  (const void*)k_ipm_rhs, (const void*)k_ipm_residual, (const void*)k_ipm_axpy_sol, (const void*)k_ipm_direction,
+                                  (const void*)k_ipm_soc_direction, (const void*)k_ipm_line_search };
+        for (const void* kf : kernels) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->vec_smem);
+    }
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
     if (P.closed && S == 2) { fl_set_error("closed laps need at least three nodes"); fl_ipm_destroy(s); return nullptr; }
     return s;
@@ -402,15 +414,15 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     int cnt[4];
     cudaEventRecord(s->ev0, st);
     FLI_CUDA(cudaMemcpyAsync(nlp->d_xuser, x0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_ipm_init<<<B, IPM_BLOCK, 0, st>>>(I);
+    k_ipm_init<<<B, s->vec_block, s->vec_smem, st>>>(I);
     if (!fl_eval_device(nlp, ALL, 1.0)) return 0;
-    k_ipm_init_slacks<<<B, IPM_BLOCK, 0, st>>>(I);
+    k_ipm_init_slacks<<<B, s->vec_block, s->vec_smem, st>>>(I);
     s->launches += 2; s->n_eval_full += 1;
     // least-squares multipliers (Ipopt's default start): [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
     s->part_round = false;
     if (!kkt_factor(s, nullptr, 1, false)) return 0;
     if (!solve_refined(s, nullptr, 1, I.dx, I.dy)) return 0;
-    k_ipm_take_multipliers<<<B, IPM_BLOCK, 0, st>>>(I);
+    k_ipm_take_multipliers<<<B, s->vec_block, s->vec_smem, st>>>(I);
     s->launches += 1;
     const int blocks_b = (B + 127) / 128;
     for (long round = 0;; ++round)
@@ -420,7 +432,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
         { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, ALL, 1.0, round == 0 ? nullptr : I.act_run)) return 0; }
         s->n_eval_full += 1;
         if (!zero_counters(s)) return 0;
-        k_ipm_state<<<B, IPM_BLOCK, 0, st>>>(I);
+        k_ipm_state<<<B, s->vec_block, s->vec_smem, st>>>(I);
         k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B);
         s->launches += 2;
         if (!read_counters(s, cnt)) return 0;
@@ -448,11 +460,11 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
                 if (cnt[1] == 0) break;
             }
         // search direction
-        k_ipm_rhs<<<B, IPM_BLOCK, 0, st>>>(I, 0);
+        k_ipm_rhs<<<B, s->vec_block, s->vec_smem, st>>>(I, 0);
         s->launches += 1;
         if (!solve_refined(s, I.act_run, 0, I.dx, I.dy)) return 0;
         if (!zero_counters(s)) return 0;
-        k_ipm_direction<<<B, IPM_BLOCK, 0, st>>>(I);
+        k_ipm_direction<<<B, s->vec_block, s->vec_smem, st>>>(I);
         s->launches += 1;
         if (!read_counters(s, cnt)) return 0;
         // filter line search, all laps in lock step
@@ -461,9 +473,9 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
         {
             if (cnt[3] > 0)
             {
-                k_ipm_rhs<<<B, IPM_BLOCK, 0, st>>>(I, 1);
+                k_ipm_rhs<<<B, s->vec_block, s->vec_smem, st>>>(I, 1);
                 if (!solve_refined(s, I.act_soc, 0, I.dxs, I.dys, 0)) return 0;
-                k_ipm_soc_direction<<<B, IPM_BLOCK, 0, st>>>(I);
+                k_ipm_soc_direction<<<B, s->vec_block, s->vec_smem, st>>>(I);
                 s->launches += 2;
             }
             k_ipm_mask_trials<<<blocks_b, 128, 0, st>>>(I, B);
@@ -471,7 +483,7 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
             { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, FL_EVAL_FG, 1.0, I.act_factor)) return 0; }
             s->n_eval_fg += 1;
             if (!zero_counters(s)) return 0;
-            k_ipm_line_search<<<B, IPM_BLOCK, 0, st>>>(I);
+            k_ipm_line_search<<<B, s->vec_block, s->vec_smem, st>>>(I);
             s->launches += 1;
             if (!read_counters(s, cnt)) return 0;
         }

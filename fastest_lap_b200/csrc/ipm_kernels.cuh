@@ -19,7 +19,8 @@
 #include "kkt_kernels.cuh"
 #include "kkt_part_kernels.cuh"
 
-constexpr int IPM_BLOCK = 128;
+constexpr int IPM_BLOCK = 128;          // threads per lap when many laps share the GPU
+constexpr int IPM_BLOCK_MAX = 1024;     // ... when few do (fl_ipm.cu picks per launch; kernels use blockDim.x)
 constexpr int IPM_NVMAX = 17, IPM_NCPEMAX = 21, IPM_MAX_RESTARTS = 3;
 
 struct fl_ipm_dev
@@ -52,7 +53,7 @@ __device__ __forceinline__ double ipm_block_sum(double v, double* red)
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double r = 0.0;
-    for (int w = 0; w < IPM_BLOCK / 32; ++w) r += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += red[w];
     return r;
 }
 __device__ __forceinline__ double ipm_block_max(double v, double* red)
@@ -63,7 +64,7 @@ __device__ __forceinline__ double ipm_block_max(double v, double* red)
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double r = red[0];
-    for (int w = 1; w < IPM_BLOCK / 32; ++w) r = fmax(r, red[w]);
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmax(r, red[w]);
     return r;
 }
 __device__ __forceinline__ double ipm_block_min(double v, double* red) { return -ipm_block_max(-v, red); }
@@ -71,28 +72,28 @@ __device__ __forceinline__ double ipm_block_min(double v, double* red) { return 
 __device__ __forceinline__ int ipm_row_of_ineq(const fl_ipm_dev& I, int k) { return (k / I.NINEQ) * I.NCPE + I.t.ineq_rows[k % I.NINEQ]; }
 
 // ---- sparse products with the slot-major Jacobian / Hessian of one lap ------------------------------------------------
-// out[n] (+)= J^T w : thread per variable node, accumulators in shared memory (acc[NVMAX][IPM_BLOCK])
+// out[n] (+)= J^T w : thread per variable node, accumulators in shared memory (acc[NVMAX][(int)blockDim.x])
 __device__ void ipm_JT_mul(const fl_ipm_dev& I, const double* jac, const double* w, double* out, bool accumulate, double* acc)
 {
     const int NV = I.NV;
-    for (int base = 0; base < I.S; base += IPM_BLOCK)
+    for (int base = 0; base < I.S; base += (int)blockDim.x)
     {
         const int j = base + threadIdx.x;
         if (j < I.S)
         {
-            for (int c = 0; c < NV; ++c) acc[c * IPM_BLOCK + threadIdx.x] = accumulate ? out[(size_t)j * NV + c] : 0.0;
+            for (int c = 0; c < NV; ++c) acc[c * (int)blockDim.x + threadIdx.x] = accumulate ? out[(size_t)j * NV + c] : 0.0;
             const int node = j + I.node0;
             const int e_in = node == 0 ? I.n_points - 1 : node - 1;
             for (int k = 0; k < I.NJA; ++k)
-                acc[I.t.ja_col[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)k * I.n_el + e_in] * w[(size_t)e_in * I.NCPE + I.t.ja_row[k]];
+                acc[I.t.ja_col[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)k * I.n_el + e_in] * w[(size_t)e_in * I.NCPE + I.t.ja_row[k]];
             const bool has_out = I.closed || node + 1 < I.n_points;
             if (has_out)
             {
                 const int e_out = node, eb = e_out - I.node0;
                 for (int k = 0; k < I.NJB; ++k)
-                    acc[I.t.jb_col[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * w[(size_t)e_out * I.NCPE + I.t.jb_row[k]];
+                    acc[I.t.jb_col[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * w[(size_t)e_out * I.NCPE + I.t.jb_row[k]];
             }
-            for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * IPM_BLOCK + threadIdx.x];
+            for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * (int)blockDim.x + threadIdx.x];
         }
     }
 }
@@ -101,21 +102,21 @@ __device__ void ipm_JT_mul(const fl_ipm_dev& I, const double* jac, const double*
 __device__ void ipm_J_mul(const fl_ipm_dev& I, const double* jac, const double* v, double* out, double* acc)
 {
     const int NV = I.NV, NCPE = I.NCPE;
-    for (int base = 0; base < I.n_el; base += IPM_BLOCK)
+    for (int base = 0; base < I.n_el; base += (int)blockDim.x)
     {
         const int e = base + threadIdx.x;
         if (e < I.n_el)
         {
-            for (int r = 0; r < NCPE; ++r) acc[r * IPM_BLOCK + threadIdx.x] = 0.0;
+            for (int r = 0; r < NCPE; ++r) acc[r * (int)blockDim.x + threadIdx.x] = 0.0;
             const int nj = (e + 1 == I.n_points) ? 0 : e + 1;          // right node
             const int sj = nj - I.node0;
             for (int k = 0; k < I.NJA; ++k)
-                acc[I.t.ja_row[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)k * I.n_el + e] * v[(size_t)sj * NV + I.t.ja_col[k]];
+                acc[I.t.ja_row[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)k * I.n_el + e] * v[(size_t)sj * NV + I.t.ja_col[k]];
             const int eb = e - I.node0;
             if (eb >= 0)
                 for (int k = 0; k < I.NJB; ++k)
-                    acc[I.t.jb_row[k] * IPM_BLOCK + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * v[(size_t)eb * NV + I.t.jb_col[k]];
-            for (int r = 0; r < NCPE; ++r) out[(size_t)e * NCPE + r] = acc[r * IPM_BLOCK + threadIdx.x];
+                    acc[I.t.jb_row[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * v[(size_t)eb * NV + I.t.jb_col[k]];
+            for (int r = 0; r < NCPE; ++r) out[(size_t)e * NCPE + r] = acc[r * (int)blockDim.x + threadIdx.x];
         }
     }
 }
@@ -124,18 +125,18 @@ __device__ void ipm_J_mul(const fl_ipm_dev& I, const double* jac, const double* 
 __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const double* v, double* out, double* acc)
 {
     const int NV = I.NV;
-    for (int base = 0; base < I.S; base += IPM_BLOCK)
+    for (int base = 0; base < I.S; base += (int)blockDim.x)
     {
         const int j = base + threadIdx.x;
         if (j < I.S)
         {
-            for (int c = 0; c < NV; ++c) acc[c * IPM_BLOCK + threadIdx.x] = out[(size_t)j * NV + c];
+            for (int c = 0; c < NV; ++c) acc[c * (int)blockDim.x + threadIdx.x] = out[(size_t)j * NV + c];
             for (int k = 0; k < I.NH; ++k)
             {
                 const int r = I.t.h_row[k], c = I.t.h_col[k];
                 const double h = hes[(size_t)k * I.S + j];
-                acc[r * IPM_BLOCK + threadIdx.x] += h * v[(size_t)j * NV + c];
-                if (r != c) acc[c * IPM_BLOCK + threadIdx.x] += h * v[(size_t)j * NV + r];
+                acc[r * (int)blockDim.x + threadIdx.x] += h * v[(size_t)j * NV + c];
+                if (r != c) acc[c * (int)blockDim.x + threadIdx.x] += h * v[(size_t)j * NV + r];
             }
             // couplings with the previous node (element e_in) and with the next node (element e_out)
             const int node = j + I.node0;
@@ -147,7 +148,7 @@ __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const doub
                 for (int q = 0; q < I.NCPL; ++q)
                 {
                     const int cp = I.t.ctrl_pos[q];
-                    acc[cp * IPM_BLOCK + threadIdx.x] += hes[(size_t)I.NH * I.S + (size_t)q * I.nC + eb_in] * v[(size_t)jp * NV + cp];
+                    acc[cp * (int)blockDim.x + threadIdx.x] += hes[(size_t)I.NH * I.S + (size_t)q * I.nC + eb_in] * v[(size_t)jp * NV + cp];
                 }
             }
             const bool has_out = I.closed || node + 1 < I.n_points;
@@ -158,10 +159,10 @@ __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const doub
                 for (int q = 0; q < I.NCPL; ++q)
                 {
                     const int cp = I.t.ctrl_pos[q];
-                    acc[cp * IPM_BLOCK + threadIdx.x] += hes[(size_t)I.NH * I.S + (size_t)q * I.nC + eb_out] * v[(size_t)jn * NV + cp];
+                    acc[cp * (int)blockDim.x + threadIdx.x] += hes[(size_t)I.NH * I.S + (size_t)q * I.nC + eb_out] * v[(size_t)jn * NV + cp];
                 }
             }
-            for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * IPM_BLOCK + threadIdx.x];
+            for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * (int)blockDim.x + threadIdx.x];
         }
     }
 }
@@ -170,7 +171,7 @@ __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const doub
     const int lap = blockIdx.x; \
     fl_ipm_lap& L = I.lap[lap]; \
     const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni; \
-    __shared__ double red[IPM_BLOCK / 32]; \
+    __shared__ double red[IPM_BLOCK_MAX / 32]; \
     (void)on; (void)om; (void)oi; (void)red;
 
 __device__ __forceinline__ double ipm_push(double v, double lo, double hi, const fl_ipm_options& o)
@@ -181,16 +182,16 @@ __device__ __forceinline__ double ipm_push(double v, double lo, double hi, const
 }
 
 // ---- start ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_init(const fl_ipm_dev I)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
     {
         const double v = ipm_push(I.nx[on + i], I.xl[i], I.xu[i], I.o);
         I.x[on + i] = v; I.nx[on + i] = v;
         I.zl[on + i] = 1.0; I.zu[on + i] = 1.0;
     }
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
     if (threadIdx.x == 0)
     {
         L.mu = I.o.mu_init; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
@@ -202,48 +203,48 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_init(const fl_ipm_dev I)
 
 // after the first evaluation: slacks pushed inside their bounds, multipliers 1; right-hand side of the least-squares
 // multiplier system  [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_init_slacks(const fl_ipm_dev I)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
     {
         I.s[oi + k] = ipm_push(I.ng[om + ipm_row_of_ineq(I, k)], I.sl[k], I.su[k], I.o);
         I.vl[oi + k] = 1.0; I.vu[oi + k] = 1.0;
     }
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.r1[on + i] = -(I.ngrad[on + i] - I.zl[on + i] + I.zu[on + i]);
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) I.r2[om + i] = 0.0;
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.r1[on + i] = -(I.ngrad[on + i] - I.zl[on + i] + I.zu[on + i]);
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) I.r2[om + i] = 0.0;
 }
 
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_take_multipliers(const fl_ipm_dev I)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_take_multipliers(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
     double mx = 0.0;
     bool bad = false;
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { const double v = I.dy[om + i]; if (!isfinite(v)) bad = true; mx = fmax(mx, fabs(v)); }
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { const double v = I.dy[om + i]; if (!isfinite(v)) bad = true; mx = fmax(mx, fabs(v)); }
     mx = ipm_block_max(bad ? 1.0e300 : mx, red);
     const bool take = mx <= I.o.y_init_max;
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { const double v = take ? I.dy[om + i] : 0.0; I.y[om + i] = v; I.nlam[om + i] = v; }
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { const double v = take ? I.dy[om + i] : 0.0; I.y[om + i] = v; I.nlam[om + i] = v; }
 }
 
 // ---- state of the current iterate: optimality error, barrier update, right-hand sides ----------------------------------
 // Needs the callbacks evaluated at (x, y): f, g, grad f, Jacobian.
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
-    __shared__ double acc[IPM_NCPEMAX * IPM_BLOCK];
+    extern __shared__ double acc[];          // [IPM_NCPEMAX][blockDim.x]
     __shared__ double sh_mu;
     if (L.status != IPM_RUNNING) return;
     const fl_ipm_options& o = I.o;
     const double* jac = I.njac + (size_t)lap * I.nnz_jac;
     // gx = grad f + J^T y
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.gx[on + i] = I.ngrad[on + i];
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.gx[on + i] = I.ngrad[on + i];
     __syncthreads();
     ipm_JT_mul(I, jac, I.y + om, I.gx + on, true, acc);
     __syncthreads();
     // constraint residual c = g - gl (equality rows), g - s (inequality rows)
     double th = 0.0, cmax = 0.0, ysum = 0.0;
     bool bad = false;
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
     {
         const int r = i % I.NCPE;
         const int q = I.t.ineq_of_row[r];
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
     th = ipm_block_sum(th, red); cmax = ipm_block_max(cmax, red); ysum = ipm_block_sum(ysum, red);
     // dual infeasibility, complementarity products, multiplier sums
     double dmax = 0.0, zsum = 0.0, pmin = 1.0e300, pmax = -1.0e300;
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
     {
         const double zl = I.zl[on + i], zu = I.zu[on + i], x = I.x[on + i];
         const double rx = I.gx[on + i] - zl + zu;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
         pmin = fmin(pmin, fmin(p1, p2)); pmax = fmax(pmax, fmax(p1, p2));
         if (!isfinite(rx)) bad = true;
     }
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
     {
         const double vl = I.vl[oi + k], vu = I.vu[oi + k], s = I.s[oi + k];
         const double rs = -I.y[om + ipm_row_of_ineq(I, k)] - vl + vu;
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
     const double mu = sh_mu;
     // Sigma, barrier function, gradient of the barrier Lagrangian
     double lg = 0.0;
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
     {
         const double x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x;
         const double zl = I.zl[on + i], zu = I.zu[on + i];
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
         // r1 = -(grad phi_x + J^T y) = -(gx - mu/dl + mu/du)
         I.r1[on + i] = -(I.gx[on + i] - mu / dl + mu / du);
     }
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
     {
         const double s = I.s[oi + k], dl = s - I.sl[k], du = I.su[k] - s;
         I.sigs[oi + k] = I.vl[oi + k] / dl + I.vu[oi + k] / du;
@@ -335,14 +336,14 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_state(const fl_ipm_dev I)
 
 // ---- right-hand side of the augmented system: r2 = -c, inequality rows -= rs_bar / (Sigma_s + dw) ------------------------
 // which = 0: c of the iterate, for every running lap; which = 1: the second-order-correction residual, for laps in LS_SOC_SOLVE
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_rhs(const fl_ipm_dev I, int which)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_rhs(const fl_ipm_dev I, int which)
 {
     IPM_LAP_PROLOGUE
     if (L.status != IPM_RUNNING) return;
     if (which == 1 && L.ls != LS_SOC_SOLVE) return;
     const double* cv = (which == 0 ? I.c : I.csoc) + om;
     const double dw = L.dw;
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
     {
         const int q = I.t.ineq_of_row[i % I.NCPE];
         double v = -cv[i];
@@ -356,10 +357,10 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_rhs(const fl_ipm_dev I, int w
 }
 
 // ---- residual of the full augmented system for iterative refinement: e = (r1, r2) - K (tx, ty) -----------------------------
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_residual(const fl_ipm_dev I, const int* active, int ls_mode)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_residual(const fl_ipm_dev I, const int* active, int ls_mode)
 {
     IPM_LAP_PROLOGUE
-    __shared__ double acc[IPM_NCPEMAX * IPM_BLOCK];
+    extern __shared__ double acc[];          // [IPM_NCPEMAX][blockDim.x]
     if (active && !active[lap]) return;
     const double* jac = I.njac + (size_t)lap * I.nnz_jac;
     const double* hes = I.nhess + (size_t)lap * I.nnz_hess;
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_residual(const fl_ipm_dev I, 
     // e2 = r2 - (J tx - D ty)
     ipm_J_mul(I, jac, tx, e2, acc);
     __syncthreads();
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
     {
         const int q = I.t.ineq_of_row[i % I.NCPE];
         double D = dc;
@@ -381,22 +382,22 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_residual(const fl_ipm_dev I, 
         e2[i] = I.r2[om + i] - (e2[i] - D * ty[i]);
     }
     // e1 = r1 - (H tx + (sigx + dw) tx + J^T ty)
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) e1[i] = ls_mode ? tx[i] : (I.sigx[on + i] + dw) * tx[i];
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) e1[i] = ls_mode ? tx[i] : (I.sigx[on + i] + dw) * tx[i];
     __syncthreads();
     if (!ls_mode) ipm_H_mul_add(I, hes, tx, e1, acc);
     __syncthreads();
     ipm_JT_mul(I, jac, ty, e1, true, acc);
     __syncthreads();
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) e1[i] = I.r1[on + i] - e1[i];
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) e1[i] = I.r1[on + i] - e1[i];
 }
 
 // (tx, ty) += (dx, dy) of the refinement solve;  or initialise
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_axpy_sol(const fl_ipm_dev I, const int* active, const double* sx, const double* sy, double* tx, double* ty, int init)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_axpy_sol(const fl_ipm_dev I, const int* active, const double* sx, const double* sy, double* tx, double* ty, int init)
 {
     IPM_LAP_PROLOGUE
     if (active && !active[lap]) return;
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) tx[on + i] = (init ? 0.0 : tx[on + i]) + sx[on + i];
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) ty[om + i] = (init ? 0.0 : ty[om + i]) + sy[om + i];
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) tx[on + i] = (init ? 0.0 : tx[on + i]) + sx[on + i];
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) ty[om + i] = (init ? 0.0 : ty[om + i]) + sy[om + i];
 }
 
 // fraction to the boundary (15): largest alpha in (0, 1] with v + alpha dv >= lo + (1 - tau)(v - lo) and the same at the upper bound
@@ -410,19 +411,19 @@ __device__ __forceinline__ double ipm_ftb(double v, double dv, double lo, double
 __device__ __forceinline__ void ipm_write_trial(const fl_ipm_dev& I, int lap, const double* dx, const double* ds, double alpha)
 {
     const size_t on = (size_t)lap * I.n, oi = (size_t)lap * I.ni;
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.nx[on + i] = I.x[on + i] + alpha * dx[on + i];
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK) I.st[oi + k] = I.s[oi + k] + alpha * ds[oi + k];
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.nx[on + i] = I.x[on + i] + alpha * dx[on + i];
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x) I.st[oi + k] = I.s[oi + k] + alpha * ds[oi + k];
 }
 
 // ---- search direction: slacks, step lengths, directional derivative, first trial point --------------------------------
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_direction(const fl_ipm_dev I)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_direction(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
     if (L.status != IPM_RUNNING) return;
     const double mu = L.mu, tau = L.tau, dw = L.dw;
     double amax = 1.0, adual = 1.0, dphi = 0.0;
     bool bad = false;
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
     {
         const double ds = (I.dy[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
         I.ds[oi + k] = ds;
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_direction(const fl_ipm_dev I)
         dphi += (-mu / dl + mu / du) * ds;
         if (!isfinite(ds)) bad = true;
     }
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
     {
         const double dx = I.dx[on + i], x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x, zl = I.zl[on + i], zu = I.zu[on + i];
         amax = fmin(amax, ipm_ftb(x, dx, I.xl[i], I.xu[i], tau));
@@ -458,19 +459,19 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_direction(const fl_ipm_dev I)
 }
 
 // step length of a second-order-corrected step and its trial point (laps in LS_SOC_SOLVE, after the solve)
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_soc_direction(const fl_ipm_dev I)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_soc_direction(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
     if (L.status != IPM_RUNNING || L.ls != LS_SOC_SOLVE) return;
     const double tau = L.tau, dw = L.dw;
     double amax = 1.0;
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
     {
         const double ds = (I.dys[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
         I.dss[oi + k] = ds;
         amax = fmin(amax, ipm_ftb(I.s[oi + k], ds, I.sl[k], I.su[k], tau));
     }
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) amax = fmin(amax, ipm_ftb(I.x[on + i], I.dxs[on + i], I.xl[i], I.xu[i], tau));
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) amax = fmin(amax, ipm_ftb(I.x[on + i], I.dxs[on + i], I.xl[i], I.xu[i], tau));
     amax = ipm_block_min(amax, red);
     if (threadIdx.x == 0) { L.alpha_soc = amax; L.ls = LS_SOC_TRIAL; }
     __syncthreads();
@@ -496,22 +497,22 @@ __device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L)
     }
     __syncthreads();
     const double mu = sh_mu;
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
     {
         const double x = I.x[on + i];
         I.nx[on + i] = x;
         I.zl[on + i] = mu / (x - I.xl[i]); I.zu[on + i] = mu / (I.xu[i] - x);
     }
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
     {
         const double s = I.s[oi + k];
         I.vl[oi + k] = mu / (s - I.sl[k]); I.vu[oi + k] = mu / (I.su[k] - s);
     }
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
 }
 
 // ---- filter line search: judge the trial point (f, g evaluated at it) --------------------------------------------------
-__global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev I)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
     __shared__ int sh_decision;      // 0 backtrack, 1 accept, 2 start / continue SOC, 3 fail
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
     // theta and barrier function at the trial point; c_trial into e2 (scratch)
     double th = 0.0, lg = 0.0;
     bool bad = false;
-    for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK)
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
     {
         const int q = I.t.ineq_of_row[i % I.NCPE];
         const double g = I.ng[om + i];
@@ -532,8 +533,8 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
         th += fabs(c);
         if (!isfinite(g)) bad = true;
     }
-    for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) { const double x = I.nx[on + i]; lg += log(x - I.xl[i]) + log(I.xu[i] - x); }
-    for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK) { const double s = I.st[oi + k]; lg += log(s - I.sl[k]) + log(I.su[k] - s); }
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) { const double x = I.nx[on + i]; lg += log(x - I.xl[i]) + log(I.xu[i] - x); }
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x) { const double s = I.st[oi + k]; lg += log(s - I.sl[k]) + log(I.su[k] - s); }
     th = ipm_block_sum(th, red); lg = ipm_block_sum(lg, red);
     const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
     if (threadIdx.x == 0)
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
         // accept: new iterate, multiplier steps, reset (16)
         const double alpha = sh_alpha, ad = L.alpha_dual, ks = o.kappa_sigma;
         const double* dxa = soc ? I.dxs : I.dx; const double* dsa = soc ? I.dss : I.ds; const double* dya = soc ? I.dys : I.dy;
-        for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK)
+        for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
         {
             const double x0 = I.x[on + i], dl0 = x0 - I.xl[i], du0 = I.xu[i] - x0, dx = I.dx[on + i];
             double zl = I.zl[on + i], zu = I.zu[on + i];
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
             I.zl[on + i] = fmax(fmin(zl, ks * mu / dl), mu / (ks * dl));
             I.zu[on + i] = fmax(fmin(zu, ks * mu / du), mu / (ks * du));
         }
-        for (int k = threadIdx.x; k < I.ni; k += IPM_BLOCK)
+        for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
         {
             const double s0 = I.s[oi + k], dl0 = s0 - I.sl[k], du0 = I.su[k] - s0, ds = I.ds[oi + k];
             double vl = I.vl[oi + k], vu = I.vu[oi + k];
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
             I.vl[oi + k] = fmax(fmin(vl, ks * mu / dl), mu / (ks * dl));
             I.vu[oi + k] = fmax(fmin(vu, ks * mu / du), mu / (ks * du));
         }
-        for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) { const double y = I.y[om + i] + alpha * dya[om + i]; I.y[om + i] = y; I.nlam[om + i] = y; }
+        for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { const double y = I.y[om + i] + alpha * dya[om + i]; I.y[om + i] = y; I.nlam[om + i] = y; }
         __shared__ int sh_restart;
         if (threadIdx.x == 0)
         {
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
         // second-order correction: c_soc = alpha c_prev + c(trial), a solve with that residual follows
         const double alpha = sh_alpha;
         const double* prev = soc ? I.csoc : I.c;
-        for (int i = threadIdx.x; i < I.m; i += IPM_BLOCK) I.csoc[om + i] = alpha * prev[om + i] + I.e2[om + i];
+        for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) I.csoc[om + i] = alpha * prev[om + i] + I.e2[om + i];
         if (threadIdx.x == 0) { L.ls = LS_SOC_SOLVE; I.act_soc[lap] = 1; atomicAdd(I.counters + 2, 1); atomicAdd(I.counters + 3, 1); }
     }
     else if (decision == 0)
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(IPM_BLOCK) k_ipm_line_search(const fl_ipm_dev 
         }
         else
         {
-            for (int i = threadIdx.x; i < I.n; i += IPM_BLOCK) I.nx[on + i] = I.x[on + i];
+            for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.nx[on + i] = I.x[on + i];
             if (threadIdx.x == 0) { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; }
         }
     }
