@@ -54,7 +54,7 @@ struct fl_ipm
     int vec_block = IPM_BLOCK;                   // threads per lap of the vector kernels (IPM_BLOCK_MAX for small batches)
     size_t vec_smem = (size_t)IPM_NCPEMAX * IPM_BLOCK * sizeof(double);
     int part_policy = 0;                         // 0 auto (few active laps), 1 always, -1 never
-    int part_max_laps = 48;
+    int part_max_laps = 512;
     bool part_round = false;                     // the current factorisation is a partitioned one
     double *rDinv = nullptr, *rF = nullptr, *rLst = nullptr, *rAq = nullptr, *rywork = nullptr;
     int *d_redneg = nullptr, *d_redzero = nullptr;
