@@ -61,3 +61,28 @@ def test_interior_point_returns_to_the_reference_solution():
     assert np.max(np.abs(res.x - ex["x"])) <= 1e-5
     f_gold = o.eval(ex["x"], derivs=False)["f"]
     assert abs(res.f - f_gold) <= 1e-8 * abs(f_gold)
+
+
+@pytest.mark.parametrize("case,n_sep", [("f1_catalunya_chicane", 8), ("kart_vendrell", 22)])
+def test_partitioned_factorisation_equals_the_sequential_one(case, n_sep):
+    """The chain cut at separators (oracle/kkt.py::PartitionedLDL, the statement of csrc/kkt_part_kernels.cuh): same solution,
+    same inertia -- also when the Hessian is shifted to be indefinite."""
+    p, ex = load_golden(case)
+    rng = np.random.default_rng(0)
+    x = ex["x"] * (1 + 1e-3 * rng.standard_normal(p.n))
+    r = ipm.oracle_evaluator(oracle_nlp(p))(x, ex["lam"], 1.0, True)
+    H, J = r["H"], r["J"]
+    lay = kkt.StageLayout(p.n_points, p.n_elements, p.nv, p.ncpe, equality_rows(p), p.closed)
+    sig_x = rng.uniform(0.01, 10.0, p.n)
+    D = np.full(p.m, 1e-9)
+    D[lay.all_ineq] = rng.uniform(0.1, 10.0, len(lay.all_ineq))
+    b = kkt.condense_rhs(lay, J, D, rng.standard_normal(p.n), rng.standard_normal(p.m))
+    for shift in (0.0, -50.0):
+        Dg, Lo = kkt.assemble_blocks(lay, H, J, sig_x + shift, D)
+        F0 = kkt.BlockCyclicLDL(Dg.copy(), Lo.copy(), p.closed)
+        Fp = kkt.PartitionedLDL(Dg.copy(), Lo.copy(), p.closed, n_sep)
+        assert Fp.inertia == F0.inertia
+        if shift == 0.0:
+            assert F0.inertia == (p.n, lay.n_stages * lay.neq, 0)
+            z0, zp = F0.solve(b), Fp.solve(b)
+            assert np.max(np.abs(z0 - zp)) <= 1e-9 * np.max(np.abs(z0))
