@@ -31,5 +31,5 @@ stub = os.path.join(d, "stubs.cu")
 with open(stub, "w") as fh:
     fh.write('struct fl_variant;\n' + "".join('extern "C" const fl_variant* fl_variant_%s() { return nullptr; }\n' % n for n in G.VARIANTS if n != variant))
 subprocess.check_call(["nvcc", "-Xcompiler", "-fPIC", "-c", stub, "-o", os.path.join(d, "stubs.o")])
-objs = [obj, os.path.join(d, "stubs.o"), os.path.join(std, "fl_capi.o")]
+objs = [obj, os.path.join(d, "stubs.o"), os.path.join(std, "fl_capi.o"), os.path.join(std, "fl_ipm.o")]
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", os.path.join(d, "lib.so")] + objs + ["-lcudart"])

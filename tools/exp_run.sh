@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for d in exp/*/; do
   n=$(basename $d)
   [ -f $d/lib.so ] || continue
-  FL_LIB=$PWD/$d/lib.so python bench.py --steps 50 --warmup 10 --no-cpu-baseline --laps ${EXP_LAPS:-1024} > gpurun_out/exp_$n.json 2> gpurun_out/exp_$n.err
+  FL_LIB=$PWD/$d/lib.so python bench.py --steps 50 --warmup 10 --no-cpu-baseline --laps ${EXP_LAPS:-1024} --solve-laps 0 --gg-speeds 0 --single-laps 0 > gpurun_out/exp_$n.json 2> gpurun_out/exp_$n.err
   python - "$n" gpurun_out/exp_$n.json >> gpurun_out/exp_results.txt <<'PY'
 import json, sys
 try:
