@@ -417,6 +417,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = ker_bytes / (ker_ms / K * 1e-3) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_node_derivs<f1_direct, all> @ 8000 nodes"]
+            if p.n_points == 8000 and B == 1:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]          # per launch, from the committed ncu --set full capture
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": nodes / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "limebeer-2014-f1 3DOF, Catalunya, closed, direct form, %d trapezoidal nodes, one full callback round per step" % p.n_points,
@@ -428,7 +435,8 @@ def main():
                 "gpu_launches": int(launches),
                 "kernels_ms": {"node_values": val_ms / K, "values+assemble": fg_ms / K, "node_derivs": ker_ms / K},
                 "roofline": {"bound": "hbm", "kernel": "k_node_derivs<%s, all>" % v, "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "algorithmic_bytes_per_launch": ker_bytes, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                              "bytes_per_node_eval": per_node_read + per_node_write, "fp64_ops_per_node_eval": nlp.ops_per_node["all"],
                              "fp64": {"peak_measured_tflops": 2.0 * fp64_peak / 1e12, "peak_unit": "TFLOP/s (2 x DFMA/s, micro-kernel on this GPU)",
