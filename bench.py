@@ -211,17 +211,14 @@ def solve_leg(args, torch, dist, world, rank, local):
     B = hi - lo
     params = workloads.sweep_parameters(MODEL_F1, args.solve_laps)
     params[0] = p.params                                     # lap 0 drives the reference vehicle (known answer)
-    nlp = CollocationNLP(p, vehicle_params=params[lo:hi], device=local)
-    from fastest_lap_b200.ipm import default_options
+    from fastest_lap_b200.ipm import default_options, solve_sweep
     opts = default_options()
-    opts.max_iter = args.solve_max_iter       # laps that need more count as not converged (reported below); Ipopt's default is 3000
-    solver = LapSolver(nlp, options=opts)
+    opts.max_iter = args.solve_max_iter       # first pass; laps that need more go to the retry passes (reported below); Ipopt's default is 3000
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    x0 = workloads.f1_start_point(p, 50.0, device=local)      # the reference's start: steady state at 50 km/h (GPU steady-state solve)
-    out = solver.solve(x0)
+    out = solve_sweep(p, params[lo:hi], options=opts, device=local)      # start: steady state at 50 km/h (GPU steady-state solve), then retries
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     t = torch.tensor([wall, out["device_ms"]], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
@@ -231,7 +228,7 @@ def solve_leg(args, torch, dist, world, rank, local):
     times = np.array([lap_time(p, out["x"][b], out["obj"][b]) for b in range(B)])
     local_res = np.stack([times, out["status"].astype(np.float64), out["iters"].astype(np.float64)], axis=1)
     res = gather_results(local_res, args.solve_laps)          # the final gather of per-lap results
-    ok = res[:, 1] == 1
+    ok = res[:, 1] >= 1
     st = out["stats"]
     golden = 77.791438
     r = {"workload": "%d independent limebeer-2014-f1 laps, Catalunya, 500 nodes, closed, direct form, vehicles drawn per lap (rng 2), start = steady state at 50 km/h; "
@@ -240,8 +237,7 @@ def solve_leg(args, torch, dist, world, rank, local):
          "converged": int(ok.sum()), "not_converged": int((~ok).sum()), "iterations_median": float(np.median(res[:, 2])), "iterations_max": float(res[:, 2].max()),
          "lap0_time_s": float(res[0, 0]), "lap0_reference_s": golden, "lap0_rel_err": abs(float(res[0, 0]) - golden) / golden,
          "lap_time_range_s": [float(res[ok, 0].min()), float(res[ok, 0].max())] if ok.any() else None,
-         "rank0_launches": st, "reference_cpu": "Ipopt+MUMPS in the reference: 82.7 s for a 697-node lap (docs quickstart.rst:134), about 1 lap/minute/core"}
-    solver.close(); nlp.close()
+         "rank0_launches": st, "rank0_passes": out["passes"], "reference_cpu": "Ipopt+MUMPS in the reference: 82.7 s for a 697-node lap (docs quickstart.rst:134), about 1 lap/minute/core"}
     return r
 
 

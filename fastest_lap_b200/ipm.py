@@ -135,3 +135,39 @@ def lap_time(problem, x, obj):
         pen += problem.dissipation[c] * np.sum(du * du / h)
     return float(obj) - pen
 
+
+
+def solve_sweep(problem, vehicle_params, options=None, device=0, start_speeds_kmh=(50.0, 100.0, 150.0), retry_mu_init=1.0, retry_max_iter=600):
+    """Vehicle-parameter sweep: one lap per row of `vehicle_params`, all from the reference's starting point (steady state
+    at start_speeds_kmh[0] replicated over the mesh, fastestlapc.cpp:1508-1545).  The interior-point method has no
+    restoration phase: the few laps that do not converge are solved again in a small second (third) batch from another
+    starting speed and a larger initial barrier parameter -- the retry-from-another-start loop the reference itself uses
+    around Ipopt where it fails (steady_state.hpp:200-226, 786-800).  Returns LapSolver.solve's dict, plus `passes`."""
+    from . import workloads
+    params = np.ascontiguousarray(vehicle_params, dtype=np.float64)
+    nlp = CollocationNLP(problem, vehicle_params=params, device=device)
+    solver = LapSolver(nlp, options=options)
+    out = solver.solve(workloads.f1_start_point(problem, start_speeds_kmh[0], device=device))
+    solver.close(); nlp.close()
+    passes = [dict(laps=int(params.shape[0]), converged=int((out["status"] >= 1).sum()), device_ms=out["device_ms"])]
+    for speed in start_speeds_kmh[1:]:
+        bad = np.where(out["status"] < 1)[0]
+        if bad.size == 0:
+            break
+        o2 = default_options() if options is None else options
+        keep = (o2.mu_init, o2.max_iter)
+        o2.mu_init, o2.max_iter = retry_mu_init, max(retry_max_iter, o2.max_iter)
+        nlp2 = CollocationNLP(problem, vehicle_params=params[bad], device=device)
+        s2 = LapSolver(nlp2, options=o2)
+        r = s2.solve(workloads.f1_start_point(problem, speed, device=device))
+        s2.close(); nlp2.close()
+        o2.mu_init, o2.max_iter = keep
+        good = r["status"] >= 1
+        for k in ("x", "y", "zl", "zu", "obj", "status", "error", "constr_viol", "dual_inf", "mu"):
+            out[k][bad[good]] = r[k][good]
+        out["iters"][bad[good]] += r["iters"][good]
+        for k in out["stats"]:
+            out["stats"][k] += r["stats"][k]
+        passes.append(dict(laps=int(bad.size), converged=int(good.sum()), device_ms=r["device_ms"], start_speed_kmh=speed, mu_init=retry_mu_init))
+    out["passes"] = passes
+    return out
