@@ -7,8 +7,10 @@
 // reformulation of the inequality rows, monotone barrier update (7), fraction to the boundary (15), filter line search
 // (18)-(20) with second-order correction, multiplier reset (16), inertia-correcting regularisation (Algorithm IC) on the
 // exact inertia reported by the block factorisation of kkt_kernels.cuh.  oracle/ipm.py is the numpy statement of the
-// same iteration.  Deviations from Ipopt: no NLP scaling, no restoration phase (a lap whose line search fails stops with
-// that status), Jacobian regularisation dc always on (closed laps with an even node count have dependent rows).
+// same iteration.  Deviations from Ipopt: no NLP scaling; no restoration phase (when the line search finds no acceptable
+// step, or after 8 consecutive steps shorter than 0.05, the barrier problem is restarted from the current primal point
+// with a larger mu, an empty filter and reset multipliers, at most IPM_MAX_RESTARTS times, see ipm_restart); Jacobian
+// regularisation dc always on (closed laps with an even node count have dependent rows).
 //
 // One block per lap; every reduction is a fixed-order tree (results do not depend on scheduling).  The host only
 // sequences phases and reads a few counters per phase: all laps advance in lock step, each with its own state.
@@ -38,7 +40,8 @@ struct fl_ipm_dev
     double *dx, *ds, *dy, *dxs, *dss, *dys, *st;   // step, second-order-corrected step, trial slacks
     double *sigx, *sigs, *r1, *r2, *c, *csoc, *rsbar, *gx, *e1, *e2, *tx, *ty;
     double *dw, *dc;                               // [batch] mirrors of lap.dw / lap.dc for the factorisation
-    int *act_factor, *act_soc, *act_run;           // [batch] masks
+    int *act_factor, *act_soc, *act_run;           // [batch] masks: act_run = lap still iterating; act_soc = needs a second-order-correction solve;
+                                                   // act_factor = pending factorisation (partitioned schedule), reused as "trial point pending" in the line search
     int* counters;                                 // [8]: 0 running laps, 1 pending factorisations, 2 laps in line search, 3 pending SOC solves
     const int* n_neg; const int* n_zero;
     fl_ipm_lap* lap;

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- CPU statement of the interior-point iteration the device solver runs (fastest_lap_b200/csrc/ipm_*.cu).
+"""TEST INFRASTRUCTURE ONLY -- CPU statement of the interior-point iteration the device solver runs (fastest_lap_b200/csrc/ipm_kernels.cuh).
 
 The reference hands its collocation NLP to Ipopt (lion::ipopt_cppad_solve, call site
 /root/reference/src/core/applications/optimal_laptime.hpp:546-551; options :528-541: tol 1e-10, constr_viol_tol 1e-10,
@@ -7,12 +7,14 @@ restates the published algorithm (Waechter & Biegler, "On the implementation of 
 algorithm for large-scale nonlinear programming", Math. Program. 106, 2006 -- the equation numbers below are that
 paper's) with numpy / scipy.sparse: slack reformulation of the inequality rows, monotone barrier update (7), fraction
 to the boundary (15), filter line search (18)-(20) with second-order correction, primal-dual Hessian damping reset (16),
-and regularisation of the augmented system.  Deviations from Ipopt, shared with the device solver: no NLP scaling, no
-restoration phase (the step is refused and the status says so), the regularisation test is the inertia-free curvature
-test of Chiang & Zavala (Comput. Optim. Appl. 64, 2016) instead of the inertia of a MUMPS factorisation.
+and inertia-correcting regularisation of the augmented system (Algorithm IC).  With a `layout` the augmented system goes
+through oracle/kkt.py (the statement of the device's block factorisation, exact inertia from its pivot signs, Jacobian
+regularisation always on); without one, through scipy's sparse LU with the inertia-free curvature test of Chiang &
+Zavala (Comput. Optim. Appl. 64, 2016).  Deviations from Ipopt, shared with the device solver: no NLP scaling, no
+restoration phase (here the step is refused and the status says so; the device solver restarts the barrier problem).
 
-Parity: this solver is pinned on the reference's converged laps (tests/golden/*.npz: lap time, x*) in
-tests/test_ipm_oracle.py; the device solver is then compared with it iterate by iterate.
+Parity: this solver is pinned on a converged lap of the reference in tests/test_oracle_kkt_ipm.py; the device solver is
+pinned on the reference's laps directly (tests/test_gpu_ipm.py).
 """
 import numpy as np
 import scipy.sparse as sp
