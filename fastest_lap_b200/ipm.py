@@ -87,6 +87,8 @@ class LapSolver:
         x0 = np.asarray(x0, dtype=np.float64)
         if x0.size == nlp.n:
             x0 = np.tile(x0.reshape(1, -1), (B, 1))
+        if x0.size != B * nlp.n:
+            raise ValueError("x0 must have %d or %d x %d entries" % (nlp.n, B, nlp.n))
         x0 = np.ascontiguousarray(x0.reshape(B, nlp.n))
         if not self._lib.fl_ipm_solve(self._h, _ptr(x0), int(verbose)):
             raise RuntimeError("fl_ipm_solve: " + self._lib.fl_last_error().decode())

@@ -160,3 +160,29 @@ def test_open_section_returns_to_the_reference_solution():
     assert abs(out["obj"][0] - f_gold) <= 1e-8 * abs(f_gold)
     assert np.max(np.abs(out["x"][0] - ex["x"])) <= 1e-5
     solver.close(); nlp.close()
+
+
+def test_invalid_solver_inputs_are_refused():
+    """Error behaviour of the solver entry points: bounds that do not match the rows, closed laps too short, wrong shapes."""
+    import ctypes as C
+    from fastest_lap_b200.nlp import CollocationNLP, SteadyStateNLP, load_library
+    from fastest_lap_b200.ipm import LapSolver
+    from fastest_lap_b200.vehicle import MODEL_KART
+    p, ex = load_golden("f1_catalunya_chicane")
+    nlp = CollocationNLP(p)
+    xl, xu, gl, gu = nlp.bounds()
+    bad_gu = gu.copy(); bad_gu[0] = gl[0] + 1.0            # an equality row declared as an inequality
+    with pytest.raises(RuntimeError, match="row classification"):
+        LapSolver(nlp, bounds=(xl, xu, gl, bad_gu))
+    bad_xu = xu.copy(); bad_xu[3] = xl[3]                   # empty interior
+    with pytest.raises(RuntimeError, match="lower < upper"):
+        LapSolver(nlp, bounds=(xl, bad_xu, gl, gu))
+    solver = LapSolver(nlp)
+    with pytest.raises(ValueError):
+        solver.solve(np.zeros(p.n + 1))
+    solver.close(); nlp.close()
+    with pytest.raises((RuntimeError, ValueError)):
+        SteadyStateNLP(7, np.zeros(72), np.zeros((1, 7)))      # unknown model
+    with pytest.raises(ValueError):
+        SteadyStateNLP(MODEL_KART, np.zeros(5), np.zeros((1, 7)))
+    assert load_library().fl_last_error() is not None
