@@ -64,3 +64,22 @@ def test_gg_diagram_of_the_kart(tmp_path):
     assert abs(ay[-1] * 9.81 - g["x"][i, 7]) <= 1e-6 * g["x"][i, 7]
     assert len(ay) == 12 and ay[0] == 0.0 and all(a >= b - 1e-9 for a, b in zip(ax_max, ax_min))
     assert ay_minus[3] == -ay[3]
+
+
+def test_optimal_laptime_of_the_kart(tmp_path):
+    """kart-6dof on Vendrell, 250 points, the C API's defaults for karts (derivative form; start from the GPU steady state)."""
+    from fastest_lap_b200 import api, workloads
+    from fastest_lap_b200.track import track_from_npz
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api.create_vehicle_from_xml("kart", paths["kart"])
+    api._table["vendrell"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "vendrell.npz"), "vendrell")
+    L = api.track_download_length("vendrell")
+    s = np.linspace(0.0, L, 251)[:-1]
+    prefix, names = api.optimal_laptime("kart", "vendrell", s, "<options><output_variables><prefix>k/</prefix></output_variables></options>")
+    t = api.download_scalar("k/laptime")
+    assert 55.0 < t < 70.0
+    u = api.download_vector("k/chassis.velocity.x")
+    assert u.shape == (250,) and u.min() > 5.0 and u.max() < 40.0
+    time = api.download_vector("k/time")
+    assert np.all(np.diff(time) > 0.0) and abs(time[-1] + (t - time[-1]) - t) < 1e-9

@@ -186,3 +186,19 @@ def test_invalid_solver_inputs_are_refused():
     with pytest.raises(ValueError):
         SteadyStateNLP(MODEL_KART, np.zeros(5), np.zeros((1, 7)))
     assert load_library().fl_last_error() is not None
+
+
+def test_f1_lap_on_the_3d_track_returns_to_the_reference_solution():
+    """F1 on the track with elevation (f1_optimal_laptime_catalunya_3d.xml; all 13 equations differential): warm start 1 % off."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver
+    p, ex = load_golden("f1_catalunya_3d")
+    rng = np.random.default_rng(0)
+    x0 = ex["x"] * (1 + 0.01 * rng.standard_normal(p.n))
+    nlp = CollocationNLP(p)
+    f_gold = nlp.eval_all(ex["x"], want=("f",))["f"][0]
+    solver = LapSolver(nlp)
+    out = solver.solve(x0)
+    assert out["status"][0] == 1, out["status"]
+    assert abs(out["obj"][0] - f_gold) <= 1e-6 * abs(f_gold)
+    solver.close(); nlp.close()
