@@ -9,8 +9,10 @@ the computation runs in libfastestlap_b200.so (callback kernels + device interio
 Supported options of `optimal_laptime` (fastestlapc.cpp:1379-1492): <sigma>, <steady_state_speed> (km/h; the reference
 reads <initial_speed> for it, quirk ix of SURVEY 8a-1: both spellings are accepted), <output_variables><prefix>,
 <control_variables> dissipations of the two full-mesh controls, <print_level>.  Closed and open meshes; F1 flat and 3-D
-tracks (direct form), kart (derivative form, the C API's default).  Warm start, hypermesh controls, integral constraints
-and sensitivities are not supported yet (a clear exception is raised).
+tracks (direct form), kart (derivative form, the C API's default); <save_warm_start> keeps the solution (per vehicle
+type, fastestlapc.cpp:60-71, 1712-1713) and <warm_start> restarts from it with its multipliers (:1561-1568) -- the use
+the reference makes of it is a parameter sweep with vehicle_set_parameter.  Hypermesh controls, integral constraints and
+sensitivities are not supported yet (a clear exception is raised).
 """
 import xml.etree.ElementTree as ET
 import numpy as np
@@ -23,6 +25,7 @@ from . import workloads
 
 KMH = 1.0 / 3.6
 _table = {}
+_warm_start = {}          # per vehicle type: the last simulation saved with <save_warm_start> (fastestlapc.cpp:60-71)
 _print_level = 0
 
 
@@ -151,7 +154,7 @@ def vehicle_type_get_names(vehicle_type_name):
 # ---------------------------------------------------------------------------------------------------------------------
 def _options(options):
     root = ET.fromstring(options) if options and options.strip() else ET.Element("options")
-    for tag in ("warm_start", "integral_constraints", "compute_sensitivity"):
+    for tag in ("integral_constraints", "compute_sensitivity"):
         node = root.find(tag)
         if node is not None and (node.text or "").strip().lower() in ("true", "1") or (tag == "integral_constraints" and node is not None and len(node)):
             raise FastestLapError("[ERROR] optimal_laptime -> option <%s> is not supported by the B200 path yet" % tag)
@@ -170,7 +173,8 @@ def _options(options):
     closed = True
     if root.find("closed_simulation") is not None:
         closed = (root.find("closed_simulation").text or "").strip().lower() in ("true", "1")
-    return dict(sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
+    flag = lambda tag: root.find(tag) is not None and (root.find(tag).text or "").strip().lower() in ("true", "1")
+    return dict(warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
 
 
 def _kart_start_node(vehicle, speed, form):
@@ -202,15 +206,28 @@ def optimal_laptime(vehicle, track, s, options=""):
     form = FORM_DIRECT if veh.model == MODEL_F1 else FORM_DERIVATIVE
     if not closed:
         raise FastestLapError("[ERROR] optimal_laptime -> open meshes need <initial_condition> (not supported by the B200 path yet)")
+    warm = None
+    if o["warm_start"]:
+        # the saved simulation's mesh, start point and multipliers with the vehicle as it is now (fastestlapc.cpp:1561-1568)
+        if veh.model not in _warm_start:
+            raise FastestLapError("[ERROR] optimal_laptime -> <warm_start> without a simulation saved by <save_warm_start>")
+        ws = _warm_start[veh.model]
+        s = ws["s"].copy()
+        if ws["track"] is not trk:
+            raise FastestLapError("[ERROR] optimal_laptime -> the warm start was saved for another track")
     p = LapProblem.from_vehicle_track(veh, trk, s, form=form, closed=True, dissipation=o["dissipation"], sigma=o["sigma"])
-    if veh.model == MODEL_F1:
+    if o["warm_start"]:
+        x0, warm = ws["x"], (ws["lam"], ws["zl"], ws["zu"])
+    elif veh.model == MODEL_F1:
         x0 = workloads.f1_start_point(p, o["speed"])
     else:
         x0 = np.tile(_kart_start_node(veh, o["speed"] * KMH, form), p.n_points)
     nlp = CollocationNLP(p)
     solver = LapSolver(nlp)
-    out = solver.solve(x0, verbose=o["print_level"] >= 5)
+    out = solver.solve(x0, verbose=o["print_level"] >= 5, warm=warm)
     solver.close(); nlp.close()
+    if o["save_warm_start"] and out["status"][0] >= 1:
+        _warm_start[veh.model] = dict(s=s.copy(), track=trk, x=out["x"][0].copy(), lam=out["y"][0].copy(), zl=out["zl"][0].copy(), zu=out["zu"][0].copy())
     if out["status"][0] < 1:
         raise FastestLapError("[ERROR] optimal_laptime -> the optimization did not converge (status %d)" % out["status"][0])
     X = out["x"][0].reshape(p.n_points, p.nv)

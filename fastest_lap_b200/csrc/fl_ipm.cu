@@ -346,7 +346,7 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     {
         const void* kernels[] = { (const void*)k_ipm_init, (const void*)k_ipm_init_slacks, (const void*)k_ipm_take_multipliers, (const void*)k_ipm_state,
                                   (const void*)k_ipm_rhs, (const void*)k_ipm_residual, (const void*)k_ipm_axpy_sol, (const void*)k_ipm_direction,
-                                  (const void*)k_ipm_soc_direction, (const void*)k_ipm_line_search };
+                                  (const void*)k_ipm_soc_direction, (const void*)k_ipm_line_search, (const void*)k_ipm_init_warm, (const void*)k_ipm_init_slacks_warm };
         for (const void* kf : kernels) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->vec_smem);
     }
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
@@ -403,7 +403,22 @@ int fl_kkt_factor_solve(fl_ipm* s, const double* x, const double* lambda, const 
     return 1;
 }
 
-int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
+static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const double* zl0, const double* zu0, double warm_push, double warm_mu, int verbose);
+
+int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose) { return ipm_solve_impl(s, x0, nullptr, nullptr, nullptr, 0.0, 0.0, verbose); }
+
+// Warm start from a previous solution: x0 [batch][n], lambda0 [batch][m], zl0, zu0 [batch][n] (what the reference passes to
+// ipopt_cppad_solve when warm_start is set, optimal_laptime.hpp:550-551).  push: Ipopt's warm_start_bound_push (1e-3);
+// mu_init: starting barrier parameter (e.g. 1e-4 close to a solution).
+int fl_ipm_solve_warm(fl_ipm* s, const double* x0, const double* lambda0, const double* zl0, const double* zu0, double push, double mu_init, int verbose)
+{
+    if (!lambda0 || !zl0 || !zu0 || !(push > 0.0) || !(mu_init > 0.0)) { fl_set_error("warm start needs lambda, zl, zu, push > 0 and mu_init > 0"); return 0; }
+    return ipm_solve_impl(s, x0, lambda0, zl0, zu0, push, mu_init, verbose);
+}
+
+} // extern "C"
+
+static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const double* zl0, const double* zu0, double warm_push, double warm_mu, int verbose)
 {
     fl_nlp* nlp = s->nlp;
     FLI_CUDA(cudaSetDevice(nlp->device));
@@ -414,16 +429,29 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     int cnt[4];
     cudaEventRecord(s->ev0, st);
     FLI_CUDA(cudaMemcpyAsync(nlp->d_xuser, x0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_ipm_init<<<B, s->vec_block, s->vec_smem, st>>>(I);
-    if (!fl_eval_device(nlp, ALL, 1.0)) return 0;
-    k_ipm_init_slacks<<<B, s->vec_block, s->vec_smem, st>>>(I);
-    s->launches += 2; s->n_eval_full += 1;
-    // least-squares multipliers (Ipopt's default start): [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
-    s->part_round = false;
-    if (!kkt_factor(s, nullptr, 1, false)) return 0;
-    if (!solve_refined(s, nullptr, 1, I.dx, I.dy)) return 0;
-    k_ipm_take_multipliers<<<B, s->vec_block, s->vec_smem, st>>>(I);
-    s->launches += 1;
+    if (y0)
+    {
+        FLI_CUDA(cudaMemcpyAsync(I.y, y0, (size_t)B * I.m * sizeof(double), cudaMemcpyHostToDevice, st));
+        FLI_CUDA(cudaMemcpyAsync(I.zl, zl0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
+        FLI_CUDA(cudaMemcpyAsync(I.zu, zu0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_ipm_init_warm<<<B, s->vec_block, s->vec_smem, st>>>(I, warm_push, warm_mu);
+        if (!fl_eval_device(nlp, FL_EVAL_FG, 1.0)) return 0;
+        k_ipm_init_slacks_warm<<<B, s->vec_block, s->vec_smem, st>>>(I, warm_push);
+        s->launches += 2; s->n_eval_fg += 1;
+    }
+    else
+    {
+        k_ipm_init<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        if (!fl_eval_device(nlp, ALL, 1.0)) return 0;
+        k_ipm_init_slacks<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        s->launches += 2; s->n_eval_full += 1;
+        // least-squares multipliers (Ipopt's default start): [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
+        s->part_round = false;
+        if (!kkt_factor(s, nullptr, 1, false)) return 0;
+        if (!solve_refined(s, nullptr, 1, I.dx, I.dy)) return 0;
+        k_ipm_take_multipliers<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        s->launches += 1;
+    }
     const int blocks_b = (B + 127) / 128;
     for (long round = 0;; ++round)
     {
@@ -498,6 +526,8 @@ int fl_ipm_solve(fl_ipm* s, const double* x0, int verbose)
     FLI_CUDA(cudaGetLastError());
     return 1;
 }
+
+extern "C" {
 
 int fl_ipm_results(fl_ipm* s, double* x, double* y, double* zl, double* zu, double* obj, int* status, int* iters, double* errors)
 {

@@ -204,6 +204,45 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init(const fl_ipm_dev I)
     }
 }
 
+// Warm start (Ipopt's warm_start_init_point; the reference passes lambda, zl, zu of a previous solution,
+// optimal_laptime.hpp:546-551): x is pushed inside its bounds by `push` only, the given multipliers are kept (bound
+// multipliers at least `push`), the barrier parameter starts at mu0.  y, zl, zu have been copied into I.y, I.zl, I.zu.
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_warm(const fl_ipm_dev I, double push, double mu0)
+{
+    IPM_LAP_PROLOGUE
+    fl_ipm_options o = I.o;
+    o.bound_push = push; o.bound_frac = push;
+    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+    {
+        const double v = ipm_push(I.nx[on + i], I.xl[i], I.xu[i], o);
+        I.x[on + i] = v; I.nx[on + i] = v;
+        I.zl[on + i] = fmax(I.zl[on + i], push); I.zu[on + i] = fmax(I.zu[on + i], push);
+    }
+    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) I.nlam[om + i] = I.y[om + i];
+    if (threadIdx.x == 0)
+    {
+        L.mu = mu0; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
+        L.theta_max = -1.0; L.theta_min = -1.0; L.status = IPM_RUNNING; L.ls = LS_IDLE; L.iter = 0; L.acc_count = 0; L.n_filter = 0;
+        L.n_backtrack = 0; L.n_soc = 0; L.n_reg = 0; L.n_fact = 0; L.switching = 0; L.n_restart = 0; L.n_small = 0; L.dw_prev = 0.0;
+        I.dw[lap] = 0.0; I.dc[lap] = L.dc; I.act_run[lap] = 1; I.act_factor[lap] = 1; I.act_soc[lap] = 0;
+    }
+}
+
+// slacks of a warm start: pushed by `push`; their bound multipliers from the sign of the row's multiplier (vu - vl = y)
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks_warm(const fl_ipm_dev I, double push)
+{
+    IPM_LAP_PROLOGUE
+    fl_ipm_options o = I.o;
+    o.bound_push = push; o.bound_frac = push;
+    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    {
+        const int row = ipm_row_of_ineq(I, k);
+        I.s[oi + k] = ipm_push(I.ng[om + row], I.sl[k], I.su[k], o);
+        const double y = I.y[om + row];
+        I.vl[oi + k] = fmax(-y, 0.0) + push; I.vu[oi + k] = fmax(y, 0.0) + push;
+    }
+}
+
 // after the first evaluation: slacks pushed inside their bounds, multipliers 1; right-hand side of the least-squares
 // multiplier system  [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
 __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks(const fl_ipm_dev I)

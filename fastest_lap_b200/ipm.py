@@ -38,6 +38,7 @@ def _bind(lib):
     lib.fl_ipm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_long), _dp]
     lib.fl_kkt_factor_solve.argtypes = [C.c_void_p] + [_dp] * 8 + [C.c_int, C.c_int, _dp, _dp, _ip, _ip]
     lib.fl_ipm_set_partitioned.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.fl_ipm_solve_warm.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int]
     lib._ipm_bound = True
 
 
@@ -81,8 +82,9 @@ class LapSolver:
         except Exception:
             pass
 
-    def solve(self, x0, verbose=False):
-        """x0: [batch][n] (or [n], replicated).  Returns a dict of per-lap results."""
+    def solve(self, x0, verbose=False, warm=None, warm_push=1.0e-3, warm_mu=1.0e-4):
+        """x0: [batch][n] (or [n], replicated).  warm = (lambda, zl, zu) of a previous solution starts the iteration from
+        it (the reference's warm start, optimal_laptime.hpp:550-551).  Returns a dict of per-lap results."""
         nlp, B = self.nlp, self.nlp.batch
         x0 = np.asarray(x0, dtype=np.float64)
         if x0.size == nlp.n:
@@ -90,7 +92,13 @@ class LapSolver:
         if x0.size != B * nlp.n:
             raise ValueError("x0 must have %d or %d x %d entries" % (nlp.n, B, nlp.n))
         x0 = np.ascontiguousarray(x0.reshape(B, nlp.n))
-        if not self._lib.fl_ipm_solve(self._h, _ptr(x0), int(verbose)):
+        if warm is not None:
+            w = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1, sz) if np.size(a) != sz else np.asarray(a, dtype=np.float64).reshape(1, sz), (B, sz)))
+                 for a, sz in zip(warm, (nlp.m, nlp.n, nlp.n))]
+            ok = self._lib.fl_ipm_solve_warm(self._h, _ptr(x0), _ptr(w[0]), _ptr(w[1]), _ptr(w[2]), float(warm_push), float(warm_mu), int(verbose))
+        else:
+            ok = self._lib.fl_ipm_solve(self._h, _ptr(x0), int(verbose))
+        if not ok:
             raise RuntimeError("fl_ipm_solve: " + self._lib.fl_last_error().decode())
         x, y = np.empty((B, nlp.n)), np.empty((B, nlp.m))
         zl, zu = np.empty((B, nlp.n)), np.empty((B, nlp.n))

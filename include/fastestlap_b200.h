@@ -166,6 +166,10 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
 void    fl_ipm_destroy(fl_ipm* ipm);
 /* x0: [batch][n] starting points (host).  Returns 1 when the iteration ran (per-lap outcomes are in fl_ipm_results). */
 int fl_ipm_solve(fl_ipm* ipm, const double* x0, int verbose);
+/* Warm start from a previous solution (what the reference passes to ipopt_cppad_solve when warm_start is set,
+ * optimal_laptime.hpp:550-551): lambda0 [batch][m], zl0, zu0 [batch][n]; push = Ipopt's warm_start_bound_push (1e-3);
+ * mu_init = starting barrier parameter. */
+int fl_ipm_solve_warm(fl_ipm* ipm, const double* x0, const double* lambda0, const double* zl0, const double* zu0, double push, double mu_init, int verbose);
 /* any output may be NULL: x [batch][n], y [batch][m], zl, zu [batch][n], obj [batch], status [batch], iters [batch],
  * errors [batch][4] = (scaled NLP error, constraint violation, dual infeasibility, barrier parameter) */
 int fl_ipm_results(fl_ipm* ipm, double* x, double* y, double* zl, double* zu, double* obj, int* status, int* iters, double* errors);

@@ -83,3 +83,28 @@ def test_optimal_laptime_of_the_kart(tmp_path):
     assert u.shape == (250,) and u.min() > 5.0 and u.max() < 40.0
     time = api.download_vector("k/time")
     assert np.all(np.diff(time) > 0.0) and abs(time[-1] + (t - time[-1]) - t) < 1e-9
+
+
+def test_warm_start_parameter_sweep(tmp_path):
+    """The reference's use of <save_warm_start>/<warm_start> (fastestlapc.cpp:1561-1568, 1712-1713): solve once, change a
+    vehicle parameter, restart from the saved primal-dual solution.  The warm run agrees with a cold run of the modified
+    vehicle and takes fewer iterations."""
+    from fastest_lap_b200 import api, workloads
+    from fastest_lap_b200.track import track_from_npz
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api._warm_start.clear()
+    api.create_vehicle_from_xml("car", paths["f1"])
+    api._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    s = np.linspace(0.0, api.track_download_length("catalunya"), 501)[:-1]
+    with pytest.raises(api.FastestLapError):
+        api.optimal_laptime("car", "catalunya", s, "<options><warm_start>true</warm_start></options>")      # nothing saved yet
+    api.optimal_laptime("car", "catalunya", s, "<options><save_warm_start>true</save_warm_start><output_variables><prefix>base/</prefix></output_variables></options>")
+    api.vehicle_set_parameter("car", "vehicle/chassis/mass", 680.0)
+    api.optimal_laptime("car", "catalunya", s, "<options><warm_start>true</warm_start><output_variables><prefix>warm/</prefix></output_variables></options>")
+    api.optimal_laptime("car", "catalunya", s, "<options><output_variables><prefix>cold/</prefix></output_variables></options>")
+    t0, tw, tc = (api.download_scalar(k + "/laptime") for k in ("base", "warm", "cold"))
+    assert tw > t0 + 1e-3                         # 20 kg heavier is slower
+    assert abs(tw - tc) <= 2e-5 * tc              # two converged runs from different starts: neighbouring local minima, 4e-4 s apart
+    iw, ic = (api.download_scalar(k + "/optimization_data.number_of_iterations") for k in ("warm", "cold"))
+    assert iw < ic

@@ -202,3 +202,31 @@ def test_f1_lap_on_the_3d_track_returns_to_the_reference_solution():
     assert out["status"][0] == 1, out["status"]
     assert abs(out["obj"][0] - f_gold) <= 1e-6 * abs(f_gold)
     solver.close(); nlp.close()
+
+
+def test_warm_start_from_the_reference_multipliers():
+    """The reference's warm start (optimal_laptime.hpp:546-551) hands x, lambda, zl, zu of a converged run to Ipopt.  From
+    the golden file's own primal and dual solution the device solver is at the optimum within a handful of iterations, and
+    a second solve warm-started from its own result does not move; a cold start from the same x needs several times more."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    p, ex = load_golden("f1_catalunya_discrete")
+    nlp = CollocationNLP(p)
+    solver = LapSolver(nlp)
+    cold = solver.solve(ex["x"])
+    warm = solver.solve(ex["x"], warm=(ex["lam"], ex["zl"], ex["zu"]), warm_mu=1e-6)
+    assert cold["status"][0] == 1 and warm["status"][0] == 1
+    print("iterations: cold", cold["iters"][0], "warm", warm["iters"][0])
+    assert warm["iters"][0] <= 15 and warm["iters"][0] < cold["iters"][0]          # the push of 1e-3 off the active bounds costs a few
+    t = lap_time(p, warm["x"][0], warm["obj"][0])
+    assert abs(t - float(ex["laptime"])) <= 1e-7 * float(ex["laptime"])
+    assert np.max(np.abs(warm["x"][0] - ex["x"])) <= 1e-5
+    # the reference's multipliers are ours up to its convergence tolerance (same sign convention as Ipopt)
+    assert np.max(np.abs(warm["y"][0] - ex["lam"])) <= 1e-3 * max(1.0, np.max(np.abs(ex["lam"])))
+    again = solver.solve(warm["x"][0], warm=(warm["y"][0], warm["zl"][0], warm["zu"][0]), warm_mu=1e-8)
+    print("iterations: second warm start", again["iters"][0])
+    assert again["status"][0] == 1 and again["iters"][0] <= 15
+    assert abs(again["obj"][0] - warm["obj"][0]) <= 1e-9 * abs(warm["obj"][0])
+    with pytest.raises(RuntimeError):
+        solver.solve(ex["x"], warm=(ex["lam"], ex["zl"], ex["zu"]), warm_mu=0.0)
+    solver.close(); nlp.close()
