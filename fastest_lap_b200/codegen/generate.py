@@ -28,10 +28,13 @@ OUT_DIR = os.path.join(HERE, "..", "csrc", "generated")
 
 # warps (= straight-line code partitions) per group of 32 nodes in each derivative kernel
 NPARTS = {"jac": int(os.environ.get("FL_NP_JAC", 4)), "hess": int(os.environ.get("FL_NP_HESS", 8)), "all": int(os.environ.get("FL_NP_ALL", 8)),
-          "values": int(os.environ.get("FL_NP_VALUES", 1))}
+          "values": int(os.environ.get("FL_NP_VALUES", 1)), "tape": int(os.environ.get("FL_NP_TAPE", 1))}
 
 # arithmetic statements per fenced segment of a derivative partition (0 = no fences, all loads where the compiler puts them)
 SEGMENT = int(os.environ.get("FL_SEGMENT", 0))
+
+# > 0: tape nodes that this many (or more) derivative partitions share are checkpointed by the values pass (see shared_tape)
+SHARE = int(os.environ.get("FL_SHARE", 0))
 
 VARIANTS = {
     "f1_direct": Variant("f1", "direct"),
@@ -73,6 +76,42 @@ def checkpoints(g, pt, outs):
     from .expr import SIN, COS, ATAN, TANH, EXP, RCP, SQRT
     heavy = (SIN, COS, ATAN, TANH, EXP, RCP, SQRT)
     return [n for n in g.topo(outs) if g.kind[n] in heavy and not pt.param_only(n)]
+
+
+def _groups(p, out_grad, out_ja, out_jb, out_h, out_c, ja, jb, hs):
+    """Output groups that share most of their expression cone: per variable k the k-th Jacobian column (+ df/dx_k) and the
+    k-th column of the Hessian's lower triangle."""
+    grp_j, grp_h = [], []
+    for k in range(p.nv):
+        grp_j.append([out_grad[k]] + [o for o, key in zip(out_ja, ja) if key[1] == k] + [o for o, key in zip(out_jb, jb) if key[1] == k])
+        grp_h.append([o for o, key in zip(out_h, hs) if key[1] == k])
+    grp_h.append(out_c)
+    return grp_j, grp_h
+
+
+def shared_tape(g, pt, groups, n_parts, heavy, share):
+    """The part of the primal / adjoint tape that `share` or more derivative partitions would each recompute and keep in
+    registers from its definition to its last use (the live set that spills, profiles/README.md): its frontier -- the
+    shared nodes with a user outside the shared set -- becomes checkpoints too, computed once by the values pass."""
+    from .expr import NEG
+    grp_j, grp_h = groups
+    outs, _ = partition(g, grp_j + grp_h, n_parts, stop=heavy)
+    count = {}
+    cones = [_cone(g, [e for e, _ in o], heavy) for o in outs]
+    for c in cones:
+        for n in c:
+            count[n] = count.get(n, 0) + 1
+    S = {n for n, c in count.items() if c >= share}
+    users = {}
+    for c in cones:
+        for n in c:
+            for o in g.operands(n):
+                while g.kind[o] == NEG:
+                    o = g.a[o]
+                users.setdefault(o, set()).add(n)
+    roots = {e for o in outs for e, _ in o}
+    F = [n for n in sorted(S) if n in roots or any(u not in S for u in users.get(n, ()))]
+    return F
 
 
 def partition(g, groups, n_parts, stop=()):
@@ -139,10 +178,19 @@ def generate(name, variant):
 
     # checkpoints: slot k of the per-node checkpoint buffer holds node ck[k]
     ck = checkpoints(g, pt, [e for e, _ in out_grad + out_ja + out_jb + out_h + out_c])
-    cut = {n: "io.c(%d)" % k for k, n in enumerate(ck)}
-    out_ck = [(n, "io.cs(%d, %%s);" % k) for k, n in enumerate(ck)]
+    n_heavy = len(ck)
+    if SHARE > 0:
+        # a full round (Jacobian AND Hessian) loads the shared tape too: it depends on the multipliers, so it is written by
+        # the `tape` pass, which replaces the values pass in those rounds; Jacobian-only / Hessian-only rounds load slots
+        # [0, NCKV) only
+        ck = ck + shared_tape(g, pt, _groups(p, out_grad, out_ja, out_jb, out_h, out_c, ja, jb, hs), NPARTS["all"], set(ck), SHARE)
+    cut_all = {n: "io.c(%d)" % k for k, n in enumerate(ck)}
+    cut_heavy = {n: "io.c(%d)" % k for k, n in enumerate(ck[:n_heavy])}
+    out_ck = [(n, "io.cs(%d, %%s);" % k) for k, n in enumerate(ck[:n_heavy])]
+    out_ck_all = [(n, "io.cs(%d, %%s);" % k) for k, n in enumerate(ck)]
 
-    def fn(fname, outputs, pres, use_cut=True):
+    def fn(fname, outputs, pres, use_cut=True, cut=None):
+        cut = cut_heavy if cut is None else cut
         lazy = {}
         if use_cut and SEGMENT > 0:
             # derivative partitions: every input is loaded at first use and software-prefetched one segment ahead
@@ -157,11 +205,7 @@ def generate(name, variant):
 
     # output groups that share most of their expression cone: per variable k the k-th Jacobian column (+ df/dx_k) and the
     # k-th column of the Hessian's lower triangle
-    grp_j, grp_h = [], []
-    for k in range(p.nv):
-        grp_j.append([out_grad[k]] + [o for o, key in zip(out_ja, ja) if key[1] == k] + [o for o, key in zip(out_jb, jb) if key[1] == k])
-        grp_h.append([o for o, key in zip(out_h, hs) if key[1] == k])
-    grp_h.append(out_c)
+    grp_j, grp_h = _groups(p, out_grad, out_ja, out_jb, out_h, out_c, ja, jb, hs)
     parts = []
     part_sizes = {}
     # values pass: the node values and checkpoints, split the same way (every output is its own group; the pass is one
@@ -175,11 +219,24 @@ def generate(name, variant):
         disp.append("        case %d: values_p%d(io); break;" % (w, w))
     disp += ["        default: break;", "        }", "    }", ""]
     parts.append("\n".join(disp))
+    # tape pass: the values pass of a full round = node values + every checkpoint, the shared tape included
+    outs, sizes = partition(g, [[o] for o in out_values + out_ck_all], NPARTS["tape"] if SHARE > 0 else NPARTS["values"])
+    part_sizes["tape"] = sizes
+    n_tape = len(outs)
+    if SHARE > 0:
+        for w, o in enumerate(outs):
+            parts.append(fn("tape_p%d" % w, o, [pre, pre_w, pre_n], use_cut=False))
+    disp = ["    template <class IO> static __device__ __forceinline__ void tape_part(int w, IO& io)", "    {", "        switch (w)", "        {"]
+    for w in range(len(outs)):
+        disp.append("        case %d: %s_p%d(io); break;" % (w, "tape" if SHARE > 0 else "values", w))
+    disp += ["        default: break;", "        }", "    }", ""]
+    parts.append("\n".join(disp))
     for mode, groups, pres in (("jac", grp_j, [pre, pre_n]), ("hess", grp_h, [pre, pre_w]), ("all", grp_j + grp_h, [pre, pre_w, pre_n])):
-        outs, sizes = partition(g, groups, NPARTS[mode], stop=set(ck))
+        mcut = cut_all if mode == "all" else cut_heavy
+        outs, sizes = partition(g, groups, NPARTS[mode], stop=set(mcut))
         part_sizes[mode] = sizes
         for w, o in enumerate(outs):
-            parts.append(fn("%s_p%d" % (mode, w), o, pres))
+            parts.append(fn("%s_p%d" % (mode, w), o, pres, cut=mcut))
         disp = ["    template <class IO> static __device__ __forceinline__ void %s_part(int w, IO& io)" % mode, "    {", "        switch (w)", "        {"]
         for w in range(len(outs)):
             disp.append("        case %d: %s_p%d(io); break;" % (w, mode, w))
@@ -210,7 +267,8 @@ def generate(name, variant):
     L.append("    static constexpr int NJA = %d, NJB = %d, NH = %d, NCPL = %d;" % (len(ja), len(jb), len(hs), len(p.coupling)))
     L.append("    static constexpr int IS_DERIVATIVE = %d, IS_3D = %d;" % (int(variant.form == "derivative"), int(variant.elevation)))
     L.append("    static constexpr int NP_VALUES = %d, NP_JAC = %d, NP_HESS = %d, NP_ALL = %d;   // code partitions of each pass" % (NPARTS["values"], NPARTS["jac"], NPARTS["hess"], NPARTS["all"]))
-    for mode in ("values", "jac", "hess", "all"):
+    L.append("    static constexpr int NCKV = %d, HAS_TAPE = %d, NP_TAPE = %d;   // checkpoints of the values pass; the tape pass writes all NCK" % (n_heavy, int(SHARE > 0), n_tape))
+    for mode in ("values", "tape", "jac", "hess", "all"):
         L.append("    // %s partition operation counts: %s (sum %d)" % (mode, part_sizes[mode], sum(part_sizes[mode])))
     L.append("    static constexpr int OPS_VALUES = %d, OPS_JAC = %d, OPS_HESS = %d, OPS_ALL = %d;" %
              (sum(counts_val.values()), sum(counts_jac.values()), sum(counts_hes.values()), sum(counts_all.values())))

@@ -69,6 +69,12 @@ constexpr int FL_BLOCK = FL_VBLOCK_N;        // values pass: nodes per block (x 
 #ifndef FL_DMINB
 #define FL_DMINB 1
 #endif
+#ifndef FL_STAGE
+#define FL_STAGE 0
+#endif
+#ifndef FL_PREFETCH
+#define FL_PREFETCH 0
+#endif
 constexpr int FL_DBLOCK = FL_DBLOCK_N;
 constexpr int FL_ABLOCK = FL_DBLOCK;
 
@@ -82,6 +88,12 @@ template <class G, bool CD>
 struct ValuesIO
 {
     const double* xn; const double* tcn; const double* Dp; const DVec<G>* Dk; double* Vn; double* Cn;
+    const double* xp; const double* xq; const double* lin_; const double* lout_; double obj_;     // tape pass only
+    __device__ __forceinline__ double lin(int r) const { return lin_[r]; }
+    __device__ __forceinline__ double lout(int r) const { return lout_[r]; }
+    __device__ __forceinline__ double obj() const { return obj_; }
+    __device__ __forceinline__ double uprev(int c) const { return xp[G::ctrl_pos(c)]; }
+    __device__ __forceinline__ double unext(int c) const { return xq[G::ctrl_pos(c)]; }
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
     __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
     __device__ __forceinline__ double d(int k) const { if constexpr (CD) return Dk->d[k]; else return __ldg(Dp + k); }
@@ -90,7 +102,9 @@ struct ValuesIO
     __device__ __forceinline__ void fence(double) const {}
 };
 
-template <class G, bool CD>
+// TAPE: the values pass of a full round (Jacobian and Hessian): it also writes the shared part of the primal / adjoint
+// tape, which depends on the multipliers (codegen/generate.py shared_tape), for the derivative partitions to load.
+template <class G, bool CD, bool TAPE>
 __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
 {
     const int node = blockIdx.x * FL_BLOCK + threadIdx.x;
@@ -105,7 +119,22 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant_
     io.Dk = &Dk;
     io.Vn = P.V + (size_t)prob * G::NVAL * P.n_pad + fl_chunk_base(node, G::NVAL);
     io.Cn = P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node, G::NCK);
-    G::values_part(part, io);
+    if constexpr (TAPE)
+    {
+        const int np = P.n_points;
+        const int prev = (node == 0) ? np - 1 : node - 1;
+        const int next = (node + 1 == np) ? 0 : node + 1;
+        const double* xb = P.x + (size_t)prob * np * G::NV;
+        const double* lam = P.lambda + (size_t)prob * P.m;
+        io.xp = xb + (size_t)prev * G::NV;
+        io.xq = xb + (size_t)next * G::NV;
+        io.lin_ = (P.closed || node > 0) ? lam + (size_t)prev * G::NCPE : P.zeros;          // element e starts at node e
+        io.lout_ = (P.closed || node + 1 < np) ? lam + (size_t)node * G::NCPE : P.zeros;
+        io.obj_ = P.obj_factor;
+        G::tape_part(part, io);
+    }
+    else
+        G::values_part(part, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -224,7 +253,7 @@ struct DerivIO
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
     __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
     __device__ __forceinline__ double d(int k) const { if constexpr (CD) return Dk->d[k]; else return __ldg(Dp + k); }
-    __device__ __forceinline__ double c(int k) const { return Cn[k * 32]; }
+    __device__ __forceinline__ double c(int k) const { return Cn[k * 32]; }          // global workspace, or the warp's staged copy in shared memory
     __device__ __forceinline__ double lin(int r) const { return lin_[r]; }
     __device__ __forceinline__ double lout(int r) const { return lout_[r]; }
     __device__ __forceinline__ double obj() const { return obj_; }
@@ -254,10 +283,17 @@ template <class G> struct deriv_parts<G, FL_DERIV_ALL>  { static constexpr int N
 // executed exactly once per thread, which makes instruction fetch, not data, the first bottleneck (profiles/).
 // A lap of 8000 nodes spreads over 32 x N blocks instead of 63 blocks of one thread per node.
 
+// Staging (FL_STAGE): a warp = one 32-node chunk of the workspace, whose NCK checkpoint rows are contiguous (NCK x 256
+// bytes).  Lane 0 brings them into the warp's shared-memory slice with ONE bulk asynchronous copy (cp.async.bulk, the
+// 1-D TMA path, completion on an mbarrier); the straight-line code then reads its checkpoints with LDS at immediate
+// offsets instead of ~70 dependent global loads per partition (the long-scoreboard stalls of profiles/prof_r1g).
+template <class G> constexpr size_t fl_stage_bytes() { return FL_STAGE ? (size_t)(FL_DBLOCK / 32) * (G::NCK * 256 + 8) : 0; }
+
 template <class G, int WHAT, bool ASSEMBLE, bool CD>
 __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
 {
-    const int vn = blockIdx.x * FL_DBLOCK + threadIdx.x;     // variable-node index
+    const int node = blockIdx.x * FL_DBLOCK + threadIdx.x;   // warps are aligned with the 32-node chunks of the workspace
+    const int vn = node - P.node0;                           // variable-node index
     const int part = blockIdx.y;
     const int prob = blockIdx.z;
     if (P.active && !P.active[prob]) return;
@@ -267,9 +303,42 @@ __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __gri
         if ((int)blockIdx.x < nbx) assemble_block<G, FL_DBLOCK>(P, blockIdx.x, nbx, prob);
         return;
     }
-    if (vn >= P.n_var_nodes) return;
     const int np = P.n_points;
-    const int node = vn + P.node0;
+#if FL_STAGE
+    extern __shared__ __align__(128) unsigned char fl_stage_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (node - lane >= np) return;                           // the whole warp is beyond the lap
+    double* sC = reinterpret_cast<double*>(fl_stage_smem) + (size_t)warp * (G::NCK * 32);
+    {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(fl_stage_smem + (size_t)(FL_DBLOCK / 32) * (G::NCK * 256) + warp * 8);
+        if (lane == 0)
+        {
+            const double* src = P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node, G::NCK);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sC);
+            constexpr unsigned bytes = G::NCK * 256;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        }
+        __syncwarp();
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    }
+#endif
+#if FL_PREFETCH
+    {
+        // warm L1 with the rows this warp is going to read: its chunk's checkpoints, its nodes' variables and multipliers
+        const int lane_ = threadIdx.x & 31;
+        const char* cb = reinterpret_cast<const char*>(P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node - lane_, G::NCK));
+        for (int off = lane_ * 128; off < G::NCK * 256; off += 32 * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(cb + off));
+        const char* xb_ = reinterpret_cast<const char*>(P.x + ((size_t)prob * np + (node - lane_)) * G::NV);
+        if (lane_ * 128 < 32 * G::NV * 8 && node - lane_ + 32 <= np) asm volatile("prefetch.global.L1 [%0];" :: "l"(xb_ + lane_ * 128));
+    }
+#endif
+    if (vn < 0 || node >= np) return;
     const int prev = (node == 0) ? np - 1 : node - 1;
     const int next = (node + 1 == np) ? 0 : node + 1;
     const int e_in = prev;                                     // element e starts at node e
@@ -287,7 +356,11 @@ __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __gri
     io.lin_ = lam + (size_t)e_in * G::NCPE;
     io.lout_ = has_out ? lam + (size_t)e_out * G::NCPE : P.zeros;
     io.obj_ = P.obj_factor;
+#if FL_STAGE
+    io.Cn = sC + lane;
+#else
     io.Cn = P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node, G::NCK);
+#endif
     io.gradn = P.grad + (size_t)prob * P.n + (size_t)vn * G::NV;
     double* jac = P.jac + (size_t)prob * P.nnz_jac;
     double* hes = P.hess + (size_t)prob * P.nnz_hess;
@@ -313,7 +386,8 @@ struct fl_variant
     int P_SIGMA, P_DISS0, P_DISS1, P_F_WHEEL_SCALE, P_R_WHEEL_SCALE;     // -1 when the model has no such slot
     void (*derive)(double* D);
     // `D0` = host copy of the parameter vector of problem 0; `shared_d` = every problem of the batch has that same vector
-    void (*launch_values)(const fl_dev&, const double* D0, int shared_d, cudaStream_t);
+    int HAS_TAPE;      // a full round runs the tape pass (launch_values with tape = 1) instead of the values pass
+    void (*launch_values)(const fl_dev&, const double* D0, int shared_d, int tape, cudaStream_t);
     void (*launch_assemble)(const fl_dev&, cudaStream_t);
     void (*launch_derivs)(const fl_dev&, const double* D0, int shared_d, int what, int with_assemble, cudaStream_t);
     int (*assemble_blocks)(const fl_dev&);
@@ -328,13 +402,18 @@ template <class G>
 struct variant_ops
 {
     static dim3 grid(int items, int batch) { return dim3((items + FL_BLOCK - 1) / FL_BLOCK, batch, 1); }
-    static void values(const fl_dev& P, const double* D0, int shared_d, cudaStream_t s)
+    static void values(const fl_dev& P, const double* D0, int shared_d, int tape, cudaStream_t s)
     {
         DVec<G> Dk;
         memcpy(Dk.d, D0, sizeof(Dk.d));
-        const dim3 grid((P.n_points + FL_BLOCK - 1) / FL_BLOCK, G::NP_VALUES, P.batch);
-        if (shared_d) k_node_values<G, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
-        else k_node_values<G, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        const dim3 grid((P.n_points + FL_BLOCK - 1) / FL_BLOCK, tape ? G::NP_TAPE : G::NP_VALUES, P.batch);
+        if (tape && G::HAS_TAPE)
+        {
+            if (shared_d) k_node_values<G, true, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+            else k_node_values<G, false, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        }
+        else if (shared_d) k_node_values<G, true, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        else k_node_values<G, false, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
     }
     static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<dim3((P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK, P.batch, 1), FL_ABLOCK, 0, s>>>(P); }
     static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK; }
@@ -342,11 +421,23 @@ struct variant_ops
     static void derivs_cd(const fl_dev& P, const DVec<G>& Dk, int what, int with_assemble, cudaStream_t s)
     {
         // n_elements <= n_var_nodes + 1: one more block column covers the assembly slice of an open problem
-        const unsigned nb = ((with_assemble ? P.n_points : P.n_var_nodes) + FL_DBLOCK - 1) / FL_DBLOCK;
-        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC, false, CD><<<dim3(nb, G::NP_JAC, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
-        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS, false, CD><<<dim3(nb, G::NP_HESS, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
-        else if (!with_assemble) k_node_derivs<G, FL_DERIV_ALL, false, CD><<<dim3(nb, G::NP_ALL, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
-        else k_node_derivs<G, FL_DERIV_ALL, true, CD><<<dim3(nb, G::NP_ALL + 1, P.batch), FL_DBLOCK, 0, s>>>(P, Dk);
+        const unsigned nb = (P.n_points + FL_DBLOCK - 1) / FL_DBLOCK;
+        const size_t sm = fl_stage_bytes<G>();
+        static unsigned long long attr_set = 0;          // per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!((attr_set >> dev) & 1ull) && sm > 48 * 1024)
+        {
+            cudaFuncSetAttribute(k_node_derivs<G, FL_DERIV_JAC, false, CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_node_derivs<G, FL_DERIV_HESS, false, CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_node_derivs<G, FL_DERIV_ALL, false, CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_node_derivs<G, FL_DERIV_ALL, true, CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            attr_set |= 1ull << dev;
+        }
+        if (what == FL_DERIV_JAC) k_node_derivs<G, FL_DERIV_JAC, false, CD><<<dim3(nb, G::NP_JAC, P.batch), FL_DBLOCK, sm, s>>>(P, Dk);
+        else if (what == FL_DERIV_HESS) k_node_derivs<G, FL_DERIV_HESS, false, CD><<<dim3(nb, G::NP_HESS, P.batch), FL_DBLOCK, sm, s>>>(P, Dk);
+        else if (!with_assemble) k_node_derivs<G, FL_DERIV_ALL, false, CD><<<dim3(nb, G::NP_ALL, P.batch), FL_DBLOCK, sm, s>>>(P, Dk);
+        else k_node_derivs<G, FL_DERIV_ALL, true, CD><<<dim3(nb, G::NP_ALL + 1, P.batch), FL_DBLOCK, sm, s>>>(P, Dk);
     }
     static void derivs(const fl_dev& P, const double* D0, int shared_d, int what, int with_assemble, cudaStream_t s)
     {
@@ -360,6 +451,7 @@ struct variant_ops
         fl_variant v;
         v.name = G::name;
         v.NV = G::NV; v.NCPE = G::NCPE; v.NTD = G::NTD; v.NALG = G::NALG; v.NEXT = G::NEXT; v.NCR = G::NCR; v.NFM = G::NFM;
+        v.HAS_TAPE = G::HAS_TAPE;
         v.NVAL = G::NVAL; v.NCK = G::NCK; v.NTC = G::NTC; v.NTRACK = G::NTRACK; v.NRAW = G::NRAW; v.ND = G::ND;
         v.NJA = G::NJA; v.NJB = G::NJB; v.NH = G::NH; v.NCPL = G::NCPL; v.IS_DERIVATIVE = G::IS_DERIVATIVE; v.IS_3D = G::IS_3D;
         v.OPS_VALUES = G::OPS_VALUES; v.OPS_JAC = G::OPS_JAC; v.OPS_HESS = G::OPS_HESS; v.OPS_ALL = G::OPS_ALL;
