@@ -53,6 +53,7 @@ struct fl_ipm
     int P = 0;                                   // separators (0: the mode is not available for this problem)
     int vec_block = IPM_BLOCK;                   // threads per lap of the vector kernels (IPM_BLOCK_MAX for small batches)
     size_t vec_smem = (size_t)IPM_NCPEMAX * IPM_BLOCK * sizeof(double);
+    int vec_cluster = 1;                         // blocks per lap of the vector kernels (a thread-block cluster when > 1: long laps, few of them)
     int part_policy = 0;                         // 0 auto (few active laps), 1 always, -1 never
     int part_max_laps = 512;
     bool part_round = false;                     // the current factorisation is a partitioned one
@@ -94,6 +95,23 @@ template <int NV, int NEQ> void launch_solve_seg_fwd(fl_ipm* s, const fl_kkt_dev
 template <int NV, int NEQ> void launch_solve_seg_bwd(fl_ipm* s, const fl_kkt_dev& K, const double* r2, double* dx, double* dy)
 {
     k_kkt_solve_seg_bwd<NV, NEQ><<<dim3(s->P, s->B), KT, 0, s->nlp->stream>>>(K, s->Q, s->rywork, r2, dx, dy);
+}
+
+// vector kernels: one block per lap, or one cluster of `vec_cluster` blocks per lap
+template <class... KArgs, class... Args>
+static void vec_launch(fl_ipm* s, void (*kernel)(KArgs...), Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(s->B * s->vec_cluster), 1, 1);
+    cfg.blockDim = dim3((unsigned)s->vec_block, 1, 1);
+    cfg.dynamicSmemBytes = s->vec_smem;
+    cfg.stream = s->nlp->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)s->vec_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->vec_cluster > 1 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // FL_IPM_PROFILE=1: synchronise around the phases and accumulate their device time (diagnosis only)
@@ -168,16 +186,16 @@ int solve_refined(fl_ipm* s, const int* active, int ls_mode, double* ox, double*
     const fl_ipm_dev& I = s->I;
     cudaStream_t st = s->nlp->stream;
     if (!kkt_solve(s, active, ls_mode, I.r1, I.r2, s->wx, s->wy)) return 0;
-    k_ipm_axpy_sol<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 1);
+    vec_launch(s, k_ipm_axpy_sol, I, active, s->wx, s->wy, I.tx, I.ty, 1);
     if (refine_steps < 0) refine_steps = I.o.refine_steps;
     for (int k = 0; k < refine_steps; ++k)
     {
-        k_ipm_residual<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, ls_mode);
+        vec_launch(s, k_ipm_residual, I, active, ls_mode);
         if (!kkt_solve(s, active, ls_mode, I.e1, I.e2, s->wx, s->wy)) return 0;
-        k_ipm_axpy_sol<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, s->wx, s->wy, I.tx, I.ty, 0);
+        vec_launch(s, k_ipm_axpy_sol, I, active, s->wx, s->wy, I.tx, I.ty, 0);
         s->launches += 2;
     }
-    k_ipm_axpy_sol<<<s->B, s->vec_block, s->vec_smem, st>>>(I, active, I.tx, I.ty, ox, oy, 1);
+    vec_launch(s, k_ipm_axpy_sol, I, active, I.tx, I.ty, ox, oy, 1);
     s->launches += 2;
     FLI_CUDA(cudaGetLastError());
     return 1;
@@ -343,6 +361,9 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     if (B <= 64) s->vec_block = IPM_BLOCK_MAX;
     else if (B <= 512) s->vec_block = 256;
     s->vec_smem = (size_t)IPM_NCPEMAX * s->vec_block * sizeof(double);
+    // long laps, few of them: a cluster of blocks per lap (each block strides over 1 / vec_cluster of the lap's vectors)
+    if (const char* e = std::getenv("FL_IPM_CLUSTER")) s->vec_cluster = std::max(1, std::min(8, std::atoi(e)));
+    else while (s->vec_cluster < 8 && (size_t)B * s->vec_cluster * 2 <= 148 && S >= s->vec_cluster * 3 * s->vec_block / 2) s->vec_cluster *= 2;
     {
         const void* kernels[] = { (const void*)k_ipm_init, (const void*)k_ipm_init_slacks, (const void*)k_ipm_take_multipliers, (const void*)k_ipm_state,
                                   (const void*)k_ipm_rhs, (const void*)k_ipm_residual, (const void*)k_ipm_axpy_sol, (const void*)k_ipm_direction,
@@ -434,22 +455,22 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
         FLI_CUDA(cudaMemcpyAsync(I.y, y0, (size_t)B * I.m * sizeof(double), cudaMemcpyHostToDevice, st));
         FLI_CUDA(cudaMemcpyAsync(I.zl, zl0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
         FLI_CUDA(cudaMemcpyAsync(I.zu, zu0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
-        k_ipm_init_warm<<<B, s->vec_block, s->vec_smem, st>>>(I, warm_push, warm_mu);
+        vec_launch(s, k_ipm_init_warm, I, warm_push, warm_mu);
         if (!fl_eval_device(nlp, FL_EVAL_FG, 1.0)) return 0;
-        k_ipm_init_slacks_warm<<<B, s->vec_block, s->vec_smem, st>>>(I, warm_push);
+        vec_launch(s, k_ipm_init_slacks_warm, I, warm_push);
         s->launches += 2; s->n_eval_fg += 1;
     }
     else
     {
-        k_ipm_init<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        vec_launch(s, k_ipm_init, I);
         if (!fl_eval_device(nlp, ALL, 1.0)) return 0;
-        k_ipm_init_slacks<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        vec_launch(s, k_ipm_init_slacks, I);
         s->launches += 2; s->n_eval_full += 1;
         // least-squares multipliers (Ipopt's default start): [I J^T; J -D][w; y] = -[grad f - zl + zu; 0]
         s->part_round = false;
         if (!kkt_factor(s, nullptr, 1, false)) return 0;
         if (!solve_refined(s, nullptr, 1, I.dx, I.dy)) return 0;
-        k_ipm_take_multipliers<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        vec_launch(s, k_ipm_take_multipliers, I);
         s->launches += 1;
     }
     const int blocks_b = (B + 127) / 128;
@@ -460,7 +481,7 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
         { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, ALL, 1.0, round == 0 ? nullptr : I.act_run)) return 0; }
         s->n_eval_full += 1;
         if (!zero_counters(s)) return 0;
-        k_ipm_state<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        vec_launch(s, k_ipm_state, I);
         k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B);
         s->launches += 2;
         if (!read_counters(s, cnt)) return 0;
@@ -488,11 +509,11 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
                 if (cnt[1] == 0) break;
             }
         // search direction
-        k_ipm_rhs<<<B, s->vec_block, s->vec_smem, st>>>(I, 0);
+        vec_launch(s, k_ipm_rhs, I, 0);
         s->launches += 1;
         if (!solve_refined(s, I.act_run, 0, I.dx, I.dy)) return 0;
         if (!zero_counters(s)) return 0;
-        k_ipm_direction<<<B, s->vec_block, s->vec_smem, st>>>(I);
+        vec_launch(s, k_ipm_direction, I);
         s->launches += 1;
         if (!read_counters(s, cnt)) return 0;
         // filter line search, all laps in lock step
@@ -501,9 +522,9 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
         {
             if (cnt[3] > 0)
             {
-                k_ipm_rhs<<<B, s->vec_block, s->vec_smem, st>>>(I, 1);
+                vec_launch(s, k_ipm_rhs, I, 1);
                 if (!solve_refined(s, I.act_soc, 0, I.dxs, I.dys, 0)) return 0;
-                k_ipm_soc_direction<<<B, s->vec_block, s->vec_smem, st>>>(I);
+                vec_launch(s, k_ipm_soc_direction, I);
                 s->launches += 2;
             }
             k_ipm_mask_trials<<<blocks_b, 128, 0, st>>>(I, B);
@@ -511,7 +532,7 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
             { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, FL_EVAL_FG, 1.0, I.act_factor)) return 0; }
             s->n_eval_fg += 1;
             if (!zero_counters(s)) return 0;
-            k_ipm_line_search<<<B, s->vec_block, s->vec_smem, st>>>(I);
+            vec_launch(s, k_ipm_line_search, I);
             s->launches += 1;
             if (!read_counters(s, cnt)) return 0;
         }

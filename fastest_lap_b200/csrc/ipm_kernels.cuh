@@ -12,12 +12,16 @@
 // with a larger mu, an empty filter and reset multipliers, at most IPM_MAX_RESTARTS times, see ipm_restart); Jacobian
 // regularisation dc always on (closed laps with an even node count have dependent rows).
 //
-// One block per lap; every reduction is a fixed-order tree (results do not depend on scheduling).  The host only
-// sequences phases and reads a few counters per phase: all laps advance in lock step, each with its own state.
+// One block per lap -- or, for long laps that would leave the GPU idle, one thread-block CLUSTER per lap (up to 8 blocks
+// on neighbouring SMs): the blocks stride over the lap's vectors together, reductions and the leader's decisions cross
+// the cluster through distributed shared memory and cluster barriers.  Every reduction is a fixed-order tree (results
+// do not depend on scheduling).  The host only sequences phases and reads a few counters per phase: all laps advance in
+// lock step, each with its own state.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cmath>
+#include <cooperative_groups.h>
 #include "kkt_kernels.cuh"
 #include "kkt_part_kernels.cuh"
 
@@ -47,39 +51,61 @@ struct fl_ipm_dev
     fl_ipm_lap* lap;
 };
 
-// ---- block reductions (fixed order) -----------------------------------------------------------------------------------
-__device__ __forceinline__ double ipm_block_sum(double v, double* red)
+// ---- the lap's thread group: one block, or the blocks of one cluster ---------------------------------------------------
+__device__ __forceinline__ unsigned ipm_nranks() { unsigned v; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(v)); return v; }
+__device__ __forceinline__ unsigned ipm_rank() { unsigned v; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v)); return v; }
+// barrier over the lap's threads; global and shared-memory writes before it are visible after it
+__device__ __forceinline__ void ipm_sync()
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += red[w];
-    return r;
+    if (ipm_nranks() > 1) cooperative_groups::this_cluster().sync();
+    else __syncthreads();
 }
-__device__ __forceinline__ double ipm_block_max(double v, double* red)
+// value the leader block (rank 0) left in its shared variable `sh` before this call
+template <class T> __device__ __forceinline__ T ipm_bcast(T* sh)
+{
+    ipm_sync();
+    const T v = (ipm_nranks() > 1) ? *cooperative_groups::this_cluster().map_shared_rank(sh, 0) : *sh;
+    ipm_sync();          // the variable may be rewritten, the leader may exit
+    return v;
+}
+
+struct ipm_verdict { double a, b; int code; };     // what the leader thread decided, for the rest of the lap's threads
+
+// ---- reductions over the lap's threads (fixed order) --------------------------------------------------------------------
+template <class OP> __device__ __forceinline__ double ipm_reduce(double v, double* red, OP op)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double r = red[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmax(r, red[w]);
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = op(r, red[w]);
+    const unsigned nrk = ipm_nranks();
+    if (nrk == 1) return r;
+    __shared__ double part;
+    if (threadIdx.x == 0) part = r;
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    cl.sync();
+    r = *cl.map_shared_rank(&part, 0);
+    for (unsigned q = 1; q < nrk; ++q) r = op(r, *cl.map_shared_rank(&part, q));
+    cl.sync();
     return r;
 }
+__device__ __forceinline__ double ipm_block_sum(double v, double* red) { return ipm_reduce(v, red, [](double a, double b) { return a + b; }); }
+__device__ __forceinline__ double ipm_block_max(double v, double* red) { return ipm_reduce(v, red, [](double a, double b) { return fmax(a, b); }); }
 __device__ __forceinline__ double ipm_block_min(double v, double* red) { return -ipm_block_max(-v, red); }
 
 __device__ __forceinline__ int ipm_row_of_ineq(const fl_ipm_dev& I, int k) { return (k / I.NINEQ) * I.NCPE + I.t.ineq_rows[k % I.NINEQ]; }
 
 // ---- sparse products with the slot-major Jacobian / Hessian of one lap ------------------------------------------------
+// The matrix slots and the vector multiplied are read through the non-coherent path (__ldg: neither is written by the
+// calling kernel), so that the loads of several slots are in flight together.
 // out[n] (+)= J^T w : thread per variable node, accumulators in shared memory (acc[NVMAX][(int)blockDim.x])
 __device__ void ipm_JT_mul(const fl_ipm_dev& I, const double* jac, const double* w, double* out, bool accumulate, double* acc)
 {
     const int NV = I.NV;
-    for (int base = 0; base < I.S; base += (int)blockDim.x)
+    for (int base = ipm_rank() * blockDim.x; base < I.S; base += ipm_nranks() * blockDim.x)
     {
         const int j = base + threadIdx.x;
         if (j < I.S)
@@ -87,14 +113,16 @@ __device__ void ipm_JT_mul(const fl_ipm_dev& I, const double* jac, const double*
             for (int c = 0; c < NV; ++c) acc[c * (int)blockDim.x + threadIdx.x] = accumulate ? out[(size_t)j * NV + c] : 0.0;
             const int node = j + I.node0;
             const int e_in = node == 0 ? I.n_points - 1 : node - 1;
+#pragma unroll 8
             for (int k = 0; k < I.NJA; ++k)
-                acc[I.t.ja_col[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)k * I.n_el + e_in] * w[(size_t)e_in * I.NCPE + I.t.ja_row[k]];
+                acc[I.t.ja_col[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)k * I.n_el + e_in) * __ldg(w + (size_t)e_in * I.NCPE + I.t.ja_row[k]);
             const bool has_out = I.closed || node + 1 < I.n_points;
             if (has_out)
             {
                 const int e_out = node, eb = e_out - I.node0;
+#pragma unroll 8
                 for (int k = 0; k < I.NJB; ++k)
-                    acc[I.t.jb_col[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * w[(size_t)e_out * I.NCPE + I.t.jb_row[k]];
+                    acc[I.t.jb_col[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb) * __ldg(w + (size_t)e_out * I.NCPE + I.t.jb_row[k]);
             }
             for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * (int)blockDim.x + threadIdx.x];
         }
@@ -105,7 +133,7 @@ __device__ void ipm_JT_mul(const fl_ipm_dev& I, const double* jac, const double*
 __device__ void ipm_J_mul(const fl_ipm_dev& I, const double* jac, const double* v, double* out, double* acc)
 {
     const int NV = I.NV, NCPE = I.NCPE;
-    for (int base = 0; base < I.n_el; base += (int)blockDim.x)
+    for (int base = ipm_rank() * blockDim.x; base < I.n_el; base += ipm_nranks() * blockDim.x)
     {
         const int e = base + threadIdx.x;
         if (e < I.n_el)
@@ -113,12 +141,14 @@ __device__ void ipm_J_mul(const fl_ipm_dev& I, const double* jac, const double* 
             for (int r = 0; r < NCPE; ++r) acc[r * (int)blockDim.x + threadIdx.x] = 0.0;
             const int nj = (e + 1 == I.n_points) ? 0 : e + 1;          // right node
             const int sj = nj - I.node0;
+#pragma unroll 8
             for (int k = 0; k < I.NJA; ++k)
-                acc[I.t.ja_row[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)k * I.n_el + e] * v[(size_t)sj * NV + I.t.ja_col[k]];
+                acc[I.t.ja_row[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)k * I.n_el + e) * __ldg(v + (size_t)sj * NV + I.t.ja_col[k]);
             const int eb = e - I.node0;
             if (eb >= 0)
+#pragma unroll 8
                 for (int k = 0; k < I.NJB; ++k)
-                    acc[I.t.jb_row[k] * (int)blockDim.x + threadIdx.x] += jac[(size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb] * v[(size_t)eb * NV + I.t.jb_col[k]];
+                    acc[I.t.jb_row[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb) * __ldg(v + (size_t)eb * NV + I.t.jb_col[k]);
             for (int r = 0; r < NCPE; ++r) out[(size_t)e * NCPE + r] = acc[r * (int)blockDim.x + threadIdx.x];
         }
     }
@@ -128,18 +158,19 @@ __device__ void ipm_J_mul(const fl_ipm_dev& I, const double* jac, const double* 
 __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const double* v, double* out, double* acc)
 {
     const int NV = I.NV;
-    for (int base = 0; base < I.S; base += (int)blockDim.x)
+    for (int base = ipm_rank() * blockDim.x; base < I.S; base += ipm_nranks() * blockDim.x)
     {
         const int j = base + threadIdx.x;
         if (j < I.S)
         {
             for (int c = 0; c < NV; ++c) acc[c * (int)blockDim.x + threadIdx.x] = out[(size_t)j * NV + c];
+#pragma unroll 8
             for (int k = 0; k < I.NH; ++k)
             {
                 const int r = I.t.h_row[k], c = I.t.h_col[k];
-                const double h = hes[(size_t)k * I.S + j];
-                acc[r * (int)blockDim.x + threadIdx.x] += h * v[(size_t)j * NV + c];
-                if (r != c) acc[c * (int)blockDim.x + threadIdx.x] += h * v[(size_t)j * NV + r];
+                const double h = __ldg(hes + (size_t)k * I.S + j);
+                acc[r * (int)blockDim.x + threadIdx.x] += h * __ldg(v + (size_t)j * NV + c);
+                if (r != c) acc[c * (int)blockDim.x + threadIdx.x] += h * __ldg(v + (size_t)j * NV + r);
             }
             // couplings with the previous node (element e_in) and with the next node (element e_out)
             const int node = j + I.node0;
@@ -171,11 +202,12 @@ __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const doub
 }
 
 #define IPM_LAP_PROLOGUE \
-    const int lap = blockIdx.x; \
+    const int lap = blockIdx.x / ipm_nranks(); \
+    const int t0 = ipm_rank() * blockDim.x + threadIdx.x, tstride = ipm_nranks() * blockDim.x;   /* this thread's share of the lap's vectors */ \
     fl_ipm_lap& L = I.lap[lap]; \
     const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni; \
     __shared__ double red[IPM_BLOCK_MAX / 32]; \
-    (void)on; (void)om; (void)oi; (void)red;
+    (void)on; (void)om; (void)oi; (void)red; (void)t0; (void)tstride;
 
 __device__ __forceinline__ double ipm_push(double v, double lo, double hi, const fl_ipm_options& o)
 {
@@ -188,14 +220,14 @@ __device__ __forceinline__ double ipm_push(double v, double lo, double hi, const
 __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+    for (int i = t0; i < I.n; i += tstride)
     {
         const double v = ipm_push(I.nx[on + i], I.xl[i], I.xu[i], I.o);
         I.x[on + i] = v; I.nx[on + i] = v;
         I.zl[on + i] = 1.0; I.zu[on + i] = 1.0;
     }
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
-    if (threadIdx.x == 0)
+    for (int i = t0; i < I.m; i += tstride) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
+    if (t0 == 0)
     {
         L.mu = I.o.mu_init; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
         L.theta_max = -1.0; L.theta_min = -1.0; L.status = IPM_RUNNING; L.ls = LS_IDLE; L.iter = 0; L.acc_count = 0; L.n_filter = 0;
@@ -212,14 +244,14 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_warm(const fl_ipm_de
     IPM_LAP_PROLOGUE
     fl_ipm_options o = I.o;
     o.bound_push = push; o.bound_frac = push;
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+    for (int i = t0; i < I.n; i += tstride)
     {
         const double v = ipm_push(I.nx[on + i], I.xl[i], I.xu[i], o);
         I.x[on + i] = v; I.nx[on + i] = v;
         I.zl[on + i] = fmax(I.zl[on + i], push); I.zu[on + i] = fmax(I.zu[on + i], push);
     }
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) I.nlam[om + i] = I.y[om + i];
-    if (threadIdx.x == 0)
+    for (int i = t0; i < I.m; i += tstride) I.nlam[om + i] = I.y[om + i];
+    if (t0 == 0)
     {
         L.mu = mu0; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
         L.theta_max = -1.0; L.theta_min = -1.0; L.status = IPM_RUNNING; L.ls = LS_IDLE; L.iter = 0; L.acc_count = 0; L.n_filter = 0;
@@ -234,7 +266,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks_warm(const fl
     IPM_LAP_PROLOGUE
     fl_ipm_options o = I.o;
     o.bound_push = push; o.bound_frac = push;
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    for (int k = t0; k < I.ni; k += tstride)
     {
         const int row = ipm_row_of_ineq(I, k);
         I.s[oi + k] = ipm_push(I.ng[om + row], I.sl[k], I.su[k], o);
@@ -248,13 +280,13 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks_warm(const fl
 __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    for (int k = t0; k < I.ni; k += tstride)
     {
         I.s[oi + k] = ipm_push(I.ng[om + ipm_row_of_ineq(I, k)], I.sl[k], I.su[k], I.o);
         I.vl[oi + k] = 1.0; I.vu[oi + k] = 1.0;
     }
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.r1[on + i] = -(I.ngrad[on + i] - I.zl[on + i] + I.zu[on + i]);
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) I.r2[om + i] = 0.0;
+    for (int i = t0; i < I.n; i += tstride) I.r1[on + i] = -(I.ngrad[on + i] - I.zl[on + i] + I.zu[on + i]);
+    for (int i = t0; i < I.m; i += tstride) I.r2[om + i] = 0.0;
 }
 
 __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_take_multipliers(const fl_ipm_dev I)
@@ -262,10 +294,10 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_take_multipliers(const fl
     IPM_LAP_PROLOGUE
     double mx = 0.0;
     bool bad = false;
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { const double v = I.dy[om + i]; if (!isfinite(v)) bad = true; mx = fmax(mx, fabs(v)); }
+    for (int i = t0; i < I.m; i += tstride) { const double v = I.dy[om + i]; if (!isfinite(v)) bad = true; mx = fmax(mx, fabs(v)); }
     mx = ipm_block_max(bad ? 1.0e300 : mx, red);
     const bool take = mx <= I.o.y_init_max;
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { const double v = take ? I.dy[om + i] : 0.0; I.y[om + i] = v; I.nlam[om + i] = v; }
+    for (int i = t0; i < I.m; i += tstride) { const double v = take ? I.dy[om + i] : 0.0; I.y[om + i] = v; I.nlam[om + i] = v; }
 }
 
 // ---- state of the current iterate: optimality error, barrier update, right-hand sides ----------------------------------
@@ -274,19 +306,19 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
     extern __shared__ double acc[];          // [IPM_NCPEMAX][blockDim.x]
-    __shared__ double sh_mu;
+    __shared__ ipm_verdict sh;
     if (L.status != IPM_RUNNING) return;
     const fl_ipm_options& o = I.o;
     const double* jac = I.njac + (size_t)lap * I.nnz_jac;
     // gx = grad f + J^T y
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.gx[on + i] = I.ngrad[on + i];
-    __syncthreads();
+    for (int i = t0; i < I.n; i += tstride) I.gx[on + i] = I.ngrad[on + i];
+    ipm_sync();
     ipm_JT_mul(I, jac, I.y + om, I.gx + on, true, acc);
-    __syncthreads();
+    ipm_sync();
     // constraint residual c = g - gl (equality rows), g - s (inequality rows)
     double th = 0.0, cmax = 0.0, ysum = 0.0;
     bool bad = false;
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
+    for (int i = t0; i < I.m; i += tstride)
     {
         const int r = i % I.NCPE;
         const int q = I.t.ineq_of_row[r];
@@ -299,7 +331,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
     th = ipm_block_sum(th, red); cmax = ipm_block_max(cmax, red); ysum = ipm_block_sum(ysum, red);
     // dual infeasibility, complementarity products, multiplier sums
     double dmax = 0.0, zsum = 0.0, pmin = 1.0e300, pmax = -1.0e300;
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+    for (int i = t0; i < I.n; i += tstride)
     {
         const double zl = I.zl[on + i], zu = I.zu[on + i], x = I.x[on + i];
         const double rx = I.gx[on + i] - zl + zu;
@@ -308,7 +340,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
         pmin = fmin(pmin, fmin(p1, p2)); pmax = fmax(pmax, fmax(p1, p2));
         if (!isfinite(rx)) bad = true;
     }
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    for (int k = t0; k < I.ni; k += tstride)
     {
         const double vl = I.vl[oi + k], vu = I.vu[oi + k], s = I.s[oi + k];
         const double rs = -I.y[om + ipm_row_of_ineq(I, k)] - vl + vu;
@@ -319,7 +351,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
     dmax = ipm_block_max(dmax, red); zsum = ipm_block_sum(zsum, red);
     pmin = ipm_block_min(pmin, red); pmax = ipm_block_max(pmax, red);
     const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
-    if (threadIdx.x == 0)
+    if (t0 == 0)
     {
         const double nz = 2.0 * I.n + 2.0 * I.ni;
         const double sd = fmax(o.s_max, (ysum + zsum) / (I.m + nz)) / o.s_max;
@@ -349,14 +381,14 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
             L.ls = LS_IDLE;
         }
         else { I.act_run[lap] = 0; I.act_factor[lap] = 0; }
-        sh_mu = L.mu;
+        sh.a = L.mu; sh.code = L.status;
     }
-    __syncthreads();
-    if (L.status != IPM_RUNNING) return;
-    const double mu = sh_mu;
+    const ipm_verdict v = ipm_bcast(&sh);
+    if (v.code != IPM_RUNNING) return;
+    const double mu = v.a;
     // Sigma, barrier function, gradient of the barrier Lagrangian
     double lg = 0.0;
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+    for (int i = t0; i < I.n; i += tstride)
     {
         const double x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x;
         const double zl = I.zl[on + i], zu = I.zu[on + i];
@@ -365,7 +397,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
         // r1 = -(grad phi_x + J^T y) = -(gx - mu/dl + mu/du)
         I.r1[on + i] = -(I.gx[on + i] - mu / dl + mu / du);
     }
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    for (int k = t0; k < I.ni; k += tstride)
     {
         const double s = I.s[oi + k], dl = s - I.sl[k], du = I.su[k] - s;
         I.sigs[oi + k] = I.vl[oi + k] / dl + I.vu[oi + k] / du;
@@ -373,7 +405,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
         I.rsbar[oi + k] = -mu / dl + mu / du - I.y[om + ipm_row_of_ineq(I, k)];
     }
     lg = ipm_block_sum(lg, red);
-    if (threadIdx.x == 0) L.phi = L.f - mu * lg;
+    if (t0 == 0) L.phi = L.f - mu * lg;
 }
 
 // ---- right-hand side of the augmented system: r2 = -c, inequality rows -= rs_bar / (Sigma_s + dw) ------------------------
@@ -385,7 +417,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_rhs(const fl_ipm_dev I, i
     if (which == 1 && L.ls != LS_SOC_SOLVE) return;
     const double* cv = (which == 0 ? I.c : I.csoc) + om;
     const double dw = L.dw;
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
+    for (int i = t0; i < I.m; i += tstride)
     {
         const int q = I.t.ineq_of_row[i % I.NCPE];
         double v = -cv[i];
@@ -411,8 +443,8 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_residual(const fl_ipm_dev
     const double* tx = I.tx + on; const double* ty = I.ty + om;
     // e2 = r2 - (J tx - D ty)
     ipm_J_mul(I, jac, tx, e2, acc);
-    __syncthreads();
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
+    ipm_sync();
+    for (int i = t0; i < I.m; i += tstride)
     {
         const int q = I.t.ineq_of_row[i % I.NCPE];
         double D = dc;
@@ -424,13 +456,13 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_residual(const fl_ipm_dev
         e2[i] = I.r2[om + i] - (e2[i] - D * ty[i]);
     }
     // e1 = r1 - (H tx + (sigx + dw) tx + J^T ty)
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) e1[i] = ls_mode ? tx[i] : (I.sigx[on + i] + dw) * tx[i];
-    __syncthreads();
+    for (int i = t0; i < I.n; i += tstride) e1[i] = ls_mode ? tx[i] : (I.sigx[on + i] + dw) * tx[i];
+    ipm_sync();
     if (!ls_mode) ipm_H_mul_add(I, hes, tx, e1, acc);
-    __syncthreads();
+    ipm_sync();
     ipm_JT_mul(I, jac, ty, e1, true, acc);
-    __syncthreads();
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) e1[i] = I.r1[on + i] - e1[i];
+    ipm_sync();
+    for (int i = t0; i < I.n; i += tstride) e1[i] = I.r1[on + i] - e1[i];
 }
 
 // (tx, ty) += (dx, dy) of the refinement solve;  or initialise
@@ -438,8 +470,8 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_axpy_sol(const fl_ipm_dev
 {
     IPM_LAP_PROLOGUE
     if (active && !active[lap]) return;
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) tx[on + i] = (init ? 0.0 : tx[on + i]) + sx[on + i];
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) ty[om + i] = (init ? 0.0 : ty[om + i]) + sy[om + i];
+    for (int i = t0; i < I.n; i += tstride) tx[on + i] = (init ? 0.0 : tx[on + i]) + sx[on + i];
+    for (int i = t0; i < I.m; i += tstride) ty[om + i] = (init ? 0.0 : ty[om + i]) + sy[om + i];
 }
 
 // fraction to the boundary (15): largest alpha in (0, 1] with v + alpha dv >= lo + (1 - tau)(v - lo) and the same at the upper bound
@@ -453,8 +485,9 @@ __device__ __forceinline__ double ipm_ftb(double v, double dv, double lo, double
 __device__ __forceinline__ void ipm_write_trial(const fl_ipm_dev& I, int lap, const double* dx, const double* ds, double alpha)
 {
     const size_t on = (size_t)lap * I.n, oi = (size_t)lap * I.ni;
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.nx[on + i] = I.x[on + i] + alpha * dx[on + i];
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x) I.st[oi + k] = I.s[oi + k] + alpha * ds[oi + k];
+    const int t0 = ipm_rank() * blockDim.x + threadIdx.x, tstride = ipm_nranks() * blockDim.x;
+    for (int i = t0; i < I.n; i += tstride) I.nx[on + i] = I.x[on + i] + alpha * dx[on + i];
+    for (int k = t0; k < I.ni; k += tstride) I.st[oi + k] = I.s[oi + k] + alpha * ds[oi + k];
 }
 
 // ---- search direction: slacks, step lengths, directional derivative, first trial point --------------------------------
@@ -465,7 +498,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_direction(const fl_ipm_de
     const double mu = L.mu, tau = L.tau, dw = L.dw;
     double amax = 1.0, adual = 1.0, dphi = 0.0;
     bool bad = false;
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    for (int k = t0; k < I.ni; k += tstride)
     {
         const double ds = (I.dy[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
         I.ds[oi + k] = ds;
@@ -477,7 +510,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_direction(const fl_ipm_de
         dphi += (-mu / dl + mu / du) * ds;
         if (!isfinite(ds)) bad = true;
     }
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+    for (int i = t0; i < I.n; i += tstride)
     {
         const double dx = I.dx[on + i], x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x, zl = I.zl[on + i], zu = I.zu[on + i];
         amax = fmin(amax, ipm_ftb(x, dx, I.xl[i], I.xu[i], tau));
@@ -489,14 +522,13 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_direction(const fl_ipm_de
     }
     amax = ipm_block_min(amax, red); adual = ipm_block_min(adual, red); dphi = ipm_block_sum(dphi, red);
     const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
-    if (threadIdx.x == 0)
+    if (t0 == 0)
     {
         L.alpha_max = amax; L.alpha = amax; L.alpha_dual = adual; L.dphi = dphi; L.n_backtrack = 0; L.n_soc = 0;
         if (badf > 0.0) { L.status = IPM_NOT_FINITE; I.act_run[lap] = 0; L.ls = LS_IDLE; }
         else { L.ls = LS_TRIAL; atomicAdd(I.counters + 2, 1); }
     }
-    __syncthreads();
-    if (L.status != IPM_RUNNING) return;
+    if (badf > 0.0) return;          // every thread of the lap holds the same reduced value
     ipm_write_trial(I, lap, I.dx, I.ds, amax);
 }
 
@@ -507,16 +539,15 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_soc_direction(const fl_ip
     if (L.status != IPM_RUNNING || L.ls != LS_SOC_SOLVE) return;
     const double tau = L.tau, dw = L.dw;
     double amax = 1.0;
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    for (int k = t0; k < I.ni; k += tstride)
     {
         const double ds = (I.dys[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
         I.dss[oi + k] = ds;
         amax = fmin(amax, ipm_ftb(I.s[oi + k], ds, I.sl[k], I.su[k], tau));
     }
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) amax = fmin(amax, ipm_ftb(I.x[on + i], I.dxs[on + i], I.xl[i], I.xu[i], tau));
+    for (int i = t0; i < I.n; i += tstride) amax = fmin(amax, ipm_ftb(I.x[on + i], I.dxs[on + i], I.xl[i], I.xu[i], tau));
     amax = ipm_block_min(amax, red);
-    if (threadIdx.x == 0) { L.alpha_soc = amax; L.ls = LS_SOC_TRIAL; }
-    __syncthreads();
+    if (t0 == 0) { L.alpha_soc = amax; L.ls = LS_SOC_TRIAL; }
     ipm_write_trial(I, lap, I.dxs, I.dss, amax);
 }
 
@@ -528,7 +559,8 @@ __device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L)
 {
     const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni;
     __shared__ double sh_mu;
-    if (threadIdx.x == 0)
+    const int t0 = ipm_rank() * blockDim.x + threadIdx.x, tstride = ipm_nranks() * blockDim.x;
+    if (t0 == 0)
     {
         L.n_restart += 1;
         L.mu = fmin(I.o.mu_init, fmax(100.0 * L.mu, 1.0e-4));
@@ -537,28 +569,26 @@ __device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L)
         L.theta_max = 1.0e4 * fmax(1.0, L.theta); L.theta_min = 1.0e-4 * fmax(1.0, L.theta);
         sh_mu = L.mu;
     }
-    __syncthreads();
-    const double mu = sh_mu;
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+    const double mu = ipm_bcast(&sh_mu);
+    for (int i = t0; i < I.n; i += tstride)
     {
         const double x = I.x[on + i];
         I.nx[on + i] = x;
         I.zl[on + i] = mu / (x - I.xl[i]); I.zu[on + i] = mu / (I.xu[i] - x);
     }
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+    for (int k = t0; k < I.ni; k += tstride)
     {
         const double s = I.s[oi + k];
         I.vl[oi + k] = mu / (s - I.sl[k]); I.vu[oi + k] = mu / (I.su[k] - s);
     }
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
+    for (int i = t0; i < I.m; i += tstride) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
 }
 
 // ---- filter line search: judge the trial point (f, g evaluated at it) --------------------------------------------------
 __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_dev I)
 {
     IPM_LAP_PROLOGUE
-    __shared__ int sh_decision;      // 0 backtrack, 1 accept, 2 start / continue SOC, 3 fail
-    __shared__ double sh_alpha;
+    __shared__ ipm_verdict sh;       // code: 0 backtrack, 1 accept, 2 start / continue SOC, 3 fail;  a: step length judged;  b: next one
     if (L.status != IPM_RUNNING || (L.ls != LS_TRIAL && L.ls != LS_SOC_TRIAL)) return;
     const fl_ipm_options& o = I.o;
     const bool soc = L.ls == LS_SOC_TRIAL;
@@ -566,7 +596,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
     // theta and barrier function at the trial point; c_trial into e2 (scratch)
     double th = 0.0, lg = 0.0;
     bool bad = false;
-    for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x)
+    for (int i = t0; i < I.m; i += tstride)
     {
         const int q = I.t.ineq_of_row[i % I.NCPE];
         const double g = I.ng[om + i];
@@ -575,11 +605,11 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
         th += fabs(c);
         if (!isfinite(g)) bad = true;
     }
-    for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) { const double x = I.nx[on + i]; lg += log(x - I.xl[i]) + log(I.xu[i] - x); }
-    for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x) { const double s = I.st[oi + k]; lg += log(s - I.sl[k]) + log(I.su[k] - s); }
+    for (int i = t0; i < I.n; i += tstride) { const double x = I.nx[on + i]; lg += log(x - I.xl[i]) + log(I.xu[i] - x); }
+    for (int k = t0; k < I.ni; k += tstride) { const double s = I.st[oi + k]; lg += log(s - I.sl[k]) + log(I.su[k] - s); }
     th = ipm_block_sum(th, red); lg = ipm_block_sum(lg, red);
     const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
-    if (threadIdx.x == 0)
+    if (t0 == 0)
     {
         const double ft = I.nf[lap];
         const double phi_t = ft - mu * lg;
@@ -622,17 +652,16 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
             L.n_backtrack += 1;
             if (L.alpha < 1.0e-13 || L.n_backtrack >= o.max_backtracks) decision = 3;
         }
-        sh_decision = decision;
-        sh_alpha = alpha;
+        sh.code = decision; sh.a = alpha; sh.b = L.alpha;
     }
-    __syncthreads();
-    const int decision = sh_decision;
+    const ipm_verdict v = ipm_bcast(&sh);
+    const int decision = v.code;
     if (decision == 1)
     {
         // accept: new iterate, multiplier steps, reset (16)
-        const double alpha = sh_alpha, ad = L.alpha_dual, ks = o.kappa_sigma;
+        const double alpha = v.a, ad = L.alpha_dual, ks = o.kappa_sigma;
         const double* dxa = soc ? I.dxs : I.dx; const double* dsa = soc ? I.dss : I.ds; const double* dya = soc ? I.dys : I.dy;
-        for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x)
+        for (int i = t0; i < I.n; i += tstride)
         {
             const double x0 = I.x[on + i], dl0 = x0 - I.xl[i], du0 = I.xu[i] - x0, dx = I.dx[on + i];
             double zl = I.zl[on + i], zu = I.zu[on + i];
@@ -644,7 +673,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
             I.zl[on + i] = fmax(fmin(zl, ks * mu / dl), mu / (ks * dl));
             I.zu[on + i] = fmax(fmin(zu, ks * mu / du), mu / (ks * du));
         }
-        for (int k = threadIdx.x; k < I.ni; k += (int)blockDim.x)
+        for (int k = t0; k < I.ni; k += tstride)
         {
             const double s0 = I.s[oi + k], dl0 = s0 - I.sl[k], du0 = I.su[k] - s0, ds = I.ds[oi + k];
             double vl = I.vl[oi + k], vu = I.vu[oi + k];
@@ -656,46 +685,43 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
             I.vl[oi + k] = fmax(fmin(vl, ks * mu / dl), mu / (ks * dl));
             I.vu[oi + k] = fmax(fmin(vu, ks * mu / du), mu / (ks * du));
         }
-        for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) { const double y = I.y[om + i] + alpha * dya[om + i]; I.y[om + i] = y; I.nlam[om + i] = y; }
+        for (int i = t0; i < I.m; i += tstride) { const double y = I.y[om + i] + alpha * dya[om + i]; I.y[om + i] = y; I.nlam[om + i] = y; }
         __shared__ int sh_restart;
-        if (threadIdx.x == 0)
+        if (t0 == 0)
         {
             L.ls = LS_DONE; L.iter += 1; I.act_soc[lap] = 0;
             L.n_small = (alpha < 0.05) ? L.n_small + 1 : 0;
             sh_restart = (L.n_small >= 8 && L.n_restart < IPM_MAX_RESTARTS) ? 1 : 0;
         }
-        __syncthreads();
-        if (sh_restart) ipm_restart(I, lap, L);
+        if (ipm_bcast(&sh_restart)) ipm_restart(I, lap, L);
     }
     else if (decision == 2)
     {
         // second-order correction: c_soc = alpha c_prev + c(trial), a solve with that residual follows
-        const double alpha = sh_alpha;
+        const double alpha = v.a;
         const double* prev = soc ? I.csoc : I.c;
-        for (int i = threadIdx.x; i < I.m; i += (int)blockDim.x) I.csoc[om + i] = alpha * prev[om + i] + I.e2[om + i];
-        if (threadIdx.x == 0) { L.ls = LS_SOC_SOLVE; I.act_soc[lap] = 1; atomicAdd(I.counters + 2, 1); atomicAdd(I.counters + 3, 1); }
+        for (int i = t0; i < I.m; i += tstride) I.csoc[om + i] = alpha * prev[om + i] + I.e2[om + i];
+        if (t0 == 0) { L.ls = LS_SOC_SOLVE; I.act_soc[lap] = 1; atomicAdd(I.counters + 2, 1); atomicAdd(I.counters + 3, 1); }
     }
     else if (decision == 0)
     {
-        __syncthreads();
-        ipm_write_trial(I, lap, I.dx, I.ds, L.alpha);
-        if (threadIdx.x == 0) { L.ls = LS_TRIAL; I.act_soc[lap] = 0; atomicAdd(I.counters + 2, 1); }
+        ipm_write_trial(I, lap, I.dx, I.ds, v.b);
+        if (t0 == 0) { L.ls = LS_TRIAL; I.act_soc[lap] = 0; atomicAdd(I.counters + 2, 1); }
     }
     else
     {
         // The line search found no acceptable step: restart the barrier problem from the current iterate, or give up.
         __shared__ int sh_can;
-        if (threadIdx.x == 0) { I.act_soc[lap] = 0; sh_can = L.n_restart < IPM_MAX_RESTARTS ? 1 : 0; }
-        __syncthreads();
-        if (sh_can)
+        if (t0 == 0) { I.act_soc[lap] = 0; sh_can = L.n_restart < IPM_MAX_RESTARTS ? 1 : 0; }
+        if (ipm_bcast(&sh_can))
         {
             ipm_restart(I, lap, L);
-            if (threadIdx.x == 0) { L.ls = LS_DONE; L.iter += 1; }
+            if (t0 == 0) { L.ls = LS_DONE; L.iter += 1; }
         }
         else
         {
-            for (int i = threadIdx.x; i < I.n; i += (int)blockDim.x) I.nx[on + i] = I.x[on + i];
-            if (threadIdx.x == 0) { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; }
+            for (int i = t0; i < I.n; i += tstride) I.nx[on + i] = I.x[on + i];
+            if (t0 == 0) { L.status = IPM_LINE_SEARCH_FAILED; L.ls = LS_IDLE; I.act_run[lap] = 0; }
         }
     }
 }
