@@ -11,8 +11,10 @@ reads <initial_speed> for it, quirk ix of SURVEY 8a-1: both spellings are accept
 <control_variables> dissipations of the two full-mesh controls, <print_level>.  Closed and open meshes; F1 flat and 3-D
 tracks (direct form), kart (derivative form, the C API's default); <save_warm_start> keeps the solution (per vehicle
 type, fastestlapc.cpp:60-71, 1712-1713) and <warm_start> restarts from it with its multipliers (:1561-1568) -- the use
-the reference makes of it is a parameter sweep with vehicle_set_parameter.  Hypermesh controls, integral constraints and
-sensitivities are not supported yet (a clear exception is raised).
+the reference makes of it is a parameter sweep with vehicle_set_parameter.  Open meshes take their first node from
+<initial_condition><q from_table=.../><u from_table=.../> (fastestlapc.cpp:1237-1249) and start from it replicated
+(:1546-1557); <write_xml> / <xml_file_name> write the reference's solution file (optimal_laptime.hpp xml()).  Hypermesh
+controls, integral constraints and sensitivities are not supported yet (a clear exception is raised).
 """
 import xml.etree.ElementTree as ET
 import numpy as np
@@ -174,7 +176,29 @@ def _options(options):
     if root.find("closed_simulation") is not None:
         closed = (root.find("closed_simulation").text or "").strip().lower() in ("true", "1")
     flag = lambda tag: root.find(tag) is not None and (root.find(tag).text or "").strip().lower() in ("true", "1")
-    return dict(warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
+    q_start = u_start = None
+    if not closed:
+        ic = root.find("initial_condition")
+        if ic is None or ic.find("q") is None or ic.find("u") is None:
+            raise FastestLapError("For open simulations, the initial condition must be providedin 'options/initial_condition'")     # the reference's message
+        q_start = _get(ic.find("q").attrib.get("from_table", ""), np.ndarray)
+        u_start = _get(ic.find("u").attrib.get("from_table", ""), np.ndarray)
+    # <variable_bounds><name><lower/><upper/></name>...: fastestlapc.cpp:1308-1376, same checks and messages
+    var_bounds = {}
+    vb = root.find("variable_bounds")
+    if vb is not None:
+        for var in vb:
+            kids = [k.tag for k in var]
+            if not (1 <= len(kids) <= 2) or any(k not in ("lower", "upper") for k in kids) or len(set(kids)) != len(kids):
+                raise FastestLapError("[ERROR] Optimal_laptime_configuration -> variable_bounds \"%s\" shall have only children named \"lower\" and/or \"upper\"" % var.tag)
+            var_bounds[var.tag] = (float(var.find("lower").text) if var.find("lower") is not None else None,
+                                   float(var.find("upper").text) if var.find("upper") is not None else None)
+    xml_file = None
+    if flag("write_xml"):
+        if root.find("xml_file_name") is None:
+            raise FastestLapError("[ERROR] optimal_laptime -> <write_xml> needs <xml_file_name>")
+        xml_file = (root.find("xml_file_name").text or "").strip()
+    return dict(q_start=q_start, u_start=u_start, xml_file=xml_file, var_bounds=var_bounds, warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
 
 
 def _kart_start_node(vehicle, speed, form):
@@ -204,8 +228,14 @@ def optimal_laptime(vehicle, track, s, options=""):
         raise FastestLapError("[ERROR] optimal_laptime -> provide at least two values of arclength")
     closed = o["closed"]          # <closed_simulation>, true by default (fastestlapc.cpp:1237, 1386)
     form = FORM_DIRECT if veh.model == MODEL_F1 else FORM_DERIVATIVE
+    inputs, controls = names_of(veh.model)
+    n_in = len(inputs)
+    full_mesh = (0, 2) if veh.model == MODEL_F1 else (0, 1)
     if not closed:
-        raise FastestLapError("[ERROR] optimal_laptime -> open meshes need <initial_condition> (not supported by the B200 path yet)")
+        if len(o["q_start"]) != n_in or len(o["u_start"]) != len(controls):
+            raise FastestLapError("[ERROR] optimal_laptime -> the initial condition must have %d states and %d controls" % (n_in, len(controls)))
+        if o["warm_start"]:
+            raise FastestLapError("[ERROR] optimal_laptime -> <warm_start> of open simulations is not supported by the B200 path yet")
     warm = None
     if o["warm_start"]:
         # the saved simulation's mesh, start point and multipliers with the vehicle as it is now (fastestlapc.cpp:1561-1568)
@@ -215,33 +245,63 @@ def optimal_laptime(vehicle, track, s, options=""):
         s = ws["s"].copy()
         if ws["track"] is not trk:
             raise FastestLapError("[ERROR] optimal_laptime -> the warm start was saved for another track")
-    p = LapProblem.from_vehicle_track(veh, trk, s, form=form, closed=True, dissipation=o["dissipation"], sigma=o["sigma"])
+    p = LapProblem.from_vehicle_track(veh, trk, s, form=form, closed=closed, dissipation=o["dissipation"], sigma=o["sigma"],
+                                      q0=o["q_start"], u0=o["u_start"])
     if o["warm_start"]:
         x0, warm = ws["x"], (ws["lam"], ws["zl"], ws["zu"])
+    elif not closed:
+        # the given first node replicated over the free nodes (fastestlapc.cpp:1546-1557); control rates 0
+        q = np.delete(np.asarray(o["q_start"], dtype=np.float64), n_in - 3)          # time is not an NLP variable
+        node = np.concatenate([q, [o["u_start"][c] for c in full_mesh], [0.0, 0.0] if form == FORM_DERIVATIVE else []])
+        x0 = np.tile(node, p.n_points - 1)
     elif veh.model == MODEL_F1:
         x0 = workloads.f1_start_point(p, o["speed"])
     else:
         x0 = np.tile(_kart_start_node(veh, o["speed"] * KMH, form), p.n_points)
+    bounds = None
+    if o["var_bounds"]:
+        from .nlp import problem_bounds
+        bounds = problem_bounds(p)
+        XL, XU = bounds[0].reshape(-1, p.nv), bounds[1].reshape(-1, p.nv)
+        state_cols = [nm for nm in inputs if nm != "time"]
+        for nm, (lo, hi) in o["var_bounds"].items():
+            if nm in state_cols:
+                col = state_cols.index(nm)
+            elif nm in controls:
+                if controls.index(nm) not in full_mesh:
+                    continue                                  # bounds of a control that is not optimised have no effect
+                col = len(state_cols) + full_mesh.index(controls.index(nm))
+            else:
+                raise FastestLapError("[ERROR] Optimal_laptime_configuration -> variable \"%s\" not found" % nm)
+            if lo is not None:
+                XL[:, col] = lo
+            if hi is not None:
+                XU[:, col] = hi
     nlp = CollocationNLP(p)
-    solver = LapSolver(nlp)
+    solver = LapSolver(nlp, bounds=bounds)
     out = solver.solve(x0, verbose=o["print_level"] >= 5, warm=warm)
     solver.close(); nlp.close()
     if o["save_warm_start"] and out["status"][0] >= 1:
         _warm_start[veh.model] = dict(s=s.copy(), track=trk, x=out["x"][0].copy(), lam=out["y"][0].copy(), zl=out["zl"][0].copy(), zu=out["zu"][0].copy())
     if out["status"][0] < 1:
         raise FastestLapError("[ERROR] optimal_laptime -> the optimization did not converge (status %d)" % out["status"][0])
-    X = out["x"][0].reshape(p.n_points, p.nv)
-    inputs, controls = names_of(veh.model)
-    n_in = len(inputs)
-    h = np.diff(np.append(s, trk.track_length))
+    X = out["x"][0].reshape(-1, p.nv)
+    if not closed:
+        X = np.vstack([node, X])          # the fixed first node
+    h = np.diff(np.append(s, trk.track_length)) if closed else np.diff(s)
     # time: trapezoid integral of dt/ds, recovered from the objective's lap-time part through the callbacks' own values is
     # not exposed; integrate 1 / (ds/dt) with the curvilinear kinematics (road_curvilinear.hpp:9)
     iu, iv = (4, 5) if veh.model == MODEL_F1 else (1, 2)
     n_col, a_col = n_in - 3, n_in - 2          # positions of n and alpha in x (time removed)
     kz = trk("yaw_dot", s)
     dtds = (1.0 - X[:, n_col] * kz) / (X[:, iu] * np.cos(X[:, a_col]) - X[:, iv] * np.sin(X[:, a_col]))
-    time = np.concatenate([[0.0], np.cumsum(h[:-1] * 0.5 * (dtds[:-1] + dtds[1:]))])
-    laptime = float(np.sum(h * 0.5 * (dtds + np.roll(dtds, -1))))
+    if closed:
+        time = np.concatenate([[0.0], np.cumsum(h[:-1] * 0.5 * (dtds[:-1] + dtds[1:]))])
+        laptime = float(np.sum(h * 0.5 * (dtds + np.roll(dtds, -1))))
+    else:
+        t_start = float(o["q_start"][n_in - 3])
+        time = t_start + np.concatenate([[0.0], np.cumsum(h * 0.5 * (dtds[:-1] + dtds[1:]))])
+        laptime = float(time[-1])          # the time of the last node (optimal_laptime.hpp:631)
     pre = o["prefix"]
     names = []
 
@@ -255,7 +315,6 @@ def optimal_laptime(vehicle, track, s, options=""):
             put("time", time)
         else:
             put(nm, X[:, k].copy()); k += 1
-    full_mesh = (0, 2) if veh.model == MODEL_F1 else (0, 1)
     for c, nm in enumerate(controls):
         put(nm, X[:, k + full_mesh.index(c)].copy() if c in full_mesh else np.full(p.n_points, p.ctrl_default[c]))
     pos = trk.position(s)
@@ -263,7 +322,32 @@ def optimal_laptime(vehicle, track, s, options=""):
     put("x", pos[:, 0] - X[:, n_col] * np.sin(yaw)); put("y", pos[:, 1] + X[:, n_col] * np.cos(yaw)); put("psi", yaw + X[:, a_col])
     put("laptime", laptime)
     put("optimization_data.number_of_iterations", float(out["iters"][0]))
+    if o["xml_file"]:
+        _write_solution_xml(o["xml_file"], veh.model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, pos, yaw, n_col, a_col)
     return pre, names
+
+
+def _write_solution_xml(path, model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, pos, yaw, n_col, a_col):
+    """The reference's solution file (Optimal_laptime::xml(), optimal_laptime.hpp: mesh, inputs, controls, x, y, psi,
+    multipliers), the format solution.solution_from_xml reads back and <warm_start> files use."""
+    from .solution import Solution, Control
+    sol = Solution(model)
+    sol.is_closed, sol.is_direct, sol.n_points, sol.laptime, sol.s = closed, form == FORM_DIRECT, len(s), laptime, s.copy()
+    n_in = len(names_of(model)[0])
+    sol.inputs = np.insert(X[:, :n_in - 1], n_in - 3, time, axis=1)
+    k = n_in - 1
+    for c in range(len(controls)):
+        if c in full_mesh:
+            j = full_mesh.index(c)
+            ctl = Control("full-mesh", values=X[:, k + j].copy(), derivatives=X[:, k + 2 + j].copy() if form == FORM_DERIVATIVE else None)
+        else:
+            ctl = Control("dont optimize")
+        sol.controls.append(ctl)
+    sol.x_coord, sol.y_coord, sol.psi = pos[:, 0] - X[:, n_col] * np.sin(yaw), pos[:, 1] + X[:, n_col] * np.cos(yaw), yaw + X[:, a_col]
+    sol.iter_count, sol.zl, sol.zu, sol.lam = int(out["iters"][0]), out["zl"][0], out["zu"][0], out["y"][0]
+    sol.n_variables_per_point, sol.n_constraints_per_element = p.nv, p.ncpe
+    with open(path, "w") as fh:
+        fh.write(sol.to_xml())
 
 
 def gg_diagram(vehicle, speed, n_points):

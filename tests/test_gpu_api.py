@@ -108,3 +108,67 @@ def test_warm_start_parameter_sweep(tmp_path):
     assert abs(tw - tc) <= 2e-5 * tc              # two converged runs from different starts: neighbouring local minima, 4e-4 s apart
     iw, ic = (api.download_scalar(k + "/optimization_data.number_of_iterations") for k in ("warm", "cold"))
     assert iw < ic
+
+
+def test_open_section_with_initial_condition_and_solution_file(tmp_path):
+    """<closed_simulation> false with <initial_condition> from the tables (fastestlapc.cpp:1237-1249): nodes 0..99 of the
+    500-node lap, started from the closed lap's state at node 0 replicated.  The first node stays fixed; with its end
+    free the section cannot be slower than the same stretch of the closed lap; <write_xml> writes the reference's solution
+    format, which the loader reads back to the same vectors."""
+    from fastest_lap_b200 import api, workloads
+    from fastest_lap_b200.track import track_from_npz
+    from fastest_lap_b200.solution import solution_from_xml, names_of
+    from fastest_lap_b200.vehicle import MODEL_F1
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api.create_vehicle_from_xml("car", paths["f1"])
+    api._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    s = np.linspace(0.0, api.track_download_length("catalunya"), 501)[:-1]
+    api.optimal_laptime("car", "catalunya", s, "<options><output_variables><prefix>lap/</prefix></output_variables></options>")
+    inputs, controls = names_of(MODEL_F1)
+    i0, i1 = 0, 100          # the main straight and the first corners
+    api.create_vector("q_start", [api.download_vector("lap/" + nm)[i0] for nm in inputs])
+    api.create_vector("u_start", [api.download_vector("lap/" + nm)[i0] for nm in controls])
+    xml = str(tmp_path / "section.xml")
+    opts = ("<options><closed_simulation>false</closed_simulation><initial_condition><q from_table=\"q_start\"/><u from_table=\"u_start\"/></initial_condition>"
+            "<write_xml>true</write_xml><xml_file_name>%s</xml_file_name><output_variables><prefix>open/</prefix></output_variables></options>" % xml)
+    with pytest.raises(api.FastestLapError):
+        api.optimal_laptime("car", "catalunya", s[i0:i1], "<options><closed_simulation>false</closed_simulation></options>")
+    api.optimal_laptime("car", "catalunya", s[i0:i1], opts)
+    t_lap = api.download_vector("lap/time")
+    u = api.download_vector("open/chassis.velocity.x")
+    t = api.download_vector("open/time")
+    assert u.shape == (i1 - i0,) and u[0] == api.download_vector("lap/chassis.velocity.x")[i0] and t[0] == t_lap[i0]
+    assert api.download_scalar("open/laptime") == t[-1]
+    assert t[-1] - t[0] <= t_lap[i1 - 1] - t_lap[i0] + 1e-6
+    assert t[-1] - t[0] >= 0.9 * (t_lap[i1 - 1] - t_lap[i0])
+    # the first stretch is the closed lap's (the free end only changes the approach to the last corner)
+    assert np.max(np.abs(u[:20] - api.download_vector("lap/chassis.velocity.x")[i0:i0 + 20])) <= 0.5
+    sol = solution_from_xml(xml, MODEL_F1)
+    assert not sol.is_closed and sol.is_direct and sol.n_points == i1 - i0
+    assert np.array_equal(sol.inputs[:, inputs.index("chassis.velocity.x")], u) and np.array_equal(sol.inputs[:, inputs.index("time")], t)
+    assert np.array_equal(sol.controls[2].values, api.download_vector("open/chassis.throttle")) and sol.controls[3].kind == "dont optimize"
+    assert abs(sol.laptime - t[-1]) <= 1e-6
+    assert sol.lam.size == (i1 - i0 - 1) * 19 and sol.zl.size == (i1 - i0 - 1) * 15 and sol.pack_x().size == sol.zl.size
+
+
+def test_variable_bounds_option(tmp_path):
+    """<variable_bounds> (fastestlapc.cpp:1308-1376): a speed limit of 70 m/s is respected and costs lap time; malformed
+    entries and unknown names raise the reference's errors."""
+    from fastest_lap_b200 import api, workloads
+    from fastest_lap_b200.track import track_from_npz
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api.create_vehicle_from_xml("car", paths["f1"])
+    api._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    s = np.linspace(0.0, api.track_download_length("catalunya"), 501)[:-1]
+    api.optimal_laptime("car", "catalunya", s, "<options><output_variables><prefix>free/</prefix></output_variables></options>")
+    api.optimal_laptime("car", "catalunya", s, "<options><variable_bounds><chassis.velocity.x><upper>70.0</upper></chassis.velocity.x></variable_bounds>"
+                                               "<output_variables><prefix>limited/</prefix></output_variables></options>")
+    assert api.download_vector("free/chassis.velocity.x").max() > 80.0
+    assert api.download_vector("limited/chassis.velocity.x").max() <= 70.0 + 1e-6
+    assert api.download_scalar("limited/laptime") > api.download_scalar("free/laptime") + 0.5
+    with pytest.raises(api.FastestLapError, match="shall have only children"):
+        api.optimal_laptime("car", "catalunya", s, "<options><variable_bounds><chassis.velocity.x><max>70.0</max></chassis.velocity.x></variable_bounds></options>")
+    with pytest.raises(api.FastestLapError, match="not found"):
+        api.optimal_laptime("car", "catalunya", s, "<options><variable_bounds><chassis.speed><upper>70.0</upper></chassis.speed></variable_bounds></options>")
