@@ -1,7 +1,12 @@
 """Straight-line fp64 CUDA / C emission of expression DAGs (see expr.py)."""
 from .expr import CONST, SYM, ADD, SUB, MUL, NEG, RCP, SQRT, SIN, COS, ATAN, TANH, EXP
 
+import os
+
 _FN = {SQRT: "sqrt", SIN: "sin", COS: "cos", ATAN: "atan", TANH: "tanh", EXP: "exp"}
+# device code: the branch-free versions of csrc/fl_math.cuh (FL_LIBM=1 keeps the CUDA math library, for comparison)
+LIBM = int(os.environ.get("FL_LIBM", 0))
+_FN_DEV = _FN if LIBM else {k: "fl_" + v for k, v in _FN.items()}
 
 
 def lit(v):
@@ -142,15 +147,15 @@ class Emitter:
                 elif k == MUL:
                     rhs = "%s * %s" % (ref(A[n]), ref(B[n]))
                 elif k == RCP:
-                    rhs = "1.0 / %s" % ref(A[n])
+                    rhs = ("1.0 / %s" if LIBM else "fl_rcp(%s)") % ref(A[n])
                 elif k in (SIN, COS) and A[n] in pair:
                     s_id, c_id = pair[A[n]]
                     if s_id not in name and c_id not in name:
-                        lines.append("%sdouble t%d, t%d; sincos(%s, &t%d, &t%d);" % (indent, s_id, c_id, ref(A[n]), s_id, c_id))
+                        lines.append("%sdouble t%d, t%d; %s(%s, &t%d, &t%d);" % (indent, s_id, c_id, "sincos" if LIBM else "fl_sincos", ref(A[n]), s_id, c_id))
                         name[s_id], name[c_id] = "t%d" % s_id, "t%d" % c_id
                     continue
                 else:
-                    rhs = "%s(%s)" % (_FN[k], ref(A[n]))
+                    rhs = "%s(%s)" % (_FN_DEV[k], ref(A[n]))
                 lines.append("%sconst double %s = %s;" % (indent, t, rhs))
                 name[n] = t
 

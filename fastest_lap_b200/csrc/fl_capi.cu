@@ -542,6 +542,41 @@ int fl_flush_l2(fl_nlp* h)
 
 } // extern "C"
 
+__global__ void k_math_eval(int fn, const double* x, double* y, long n)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r = 0.0;
+    switch (fn)
+    {
+    case 0: r = fl_rcp(v); break;
+    case 1: r = fl_sqrt(v); break;
+    case 2: r = fl_sin(v); break;
+    case 3: r = fl_cos(v); break;
+    case 4: r = fl_atan(v); break;
+    case 5: r = fl_tanh(v); break;
+    case 6: r = fl_exp(v); break;
+    default: break;
+    }
+    y[i] = r;
+}
+
+extern "C" int fl_math_eval(int device, int fn, const double* x, double* y, long n)
+{
+    if (n <= 0 || !x || !y || fn < 0 || fn > 6) return fail("fl_math_eval: bad arguments") ? 1 : 0;
+    FL_CUDA(cudaSetDevice(device));
+    double *dx = nullptr, *dy = nullptr;
+    FL_CUDA(cudaMalloc(&dx, (size_t)n * sizeof(double)));
+    if (cudaMalloc(&dy, (size_t)n * sizeof(double)) != cudaSuccess) { cudaFree(dx); return fail("fl_math_eval: out of device memory") ? 1 : 0; }
+    bool ok = cudaMemcpy(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) { k_math_eval<<<(unsigned)((n + 255) / 256), 256>>>(fn, dx, dy, n); ok = cudaGetLastError() == cudaSuccess; }
+    ok = ok && cudaMemcpy(y, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(dx); cudaFree(dy);
+    if (!ok) return fail(cudaGetErrorString(cudaGetLastError())) ? 1 : 0;
+    return 1;
+}
+
 // FP64 pipe peak: every thread runs 8 independent chains of dependent DFMAs; 148 x 8 blocks of 256 threads
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b)
 {

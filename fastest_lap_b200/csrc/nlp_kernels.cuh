@@ -27,6 +27,7 @@
 // any fixed order, so the order is chosen for the GPU, not for the CPU.
 #pragma once
 #include <cuda_runtime.h>
+#include "fl_math.cuh"
 #include <cstdint>
 #include <cstring>
 

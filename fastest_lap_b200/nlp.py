@@ -49,6 +49,7 @@ def load_library():
     lib.fl_problem_bounds.argtypes = [C.POINTER(_Desc), _dp, _dp, _dp, _dp]
     lib.fl_measure_fp64_peak.restype = C.c_double
     lib.fl_measure_fp64_peak.argtypes = [C.c_void_p]
+    lib.fl_math_eval.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_long]
     lib.fl_nlp_structure.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
     lib.fl_nlp_ops_per_node.argtypes = [C.c_void_p, _ip]
     lib.fl_nlp_workspace_slots.argtypes = [C.c_void_p, _ip, _ip]
@@ -107,6 +108,16 @@ def _describe(lib, p, vehicle_params=None, device=0):
     d.dissipation[0], d.dissipation[1] = float(p.dissipation[0]), float(p.dissipation[1])
     d.q0, d.u0, d.du0, d.ctrl_default, d.device = _ptr(p.q0), _ptr(p.u0), _ptr(p.du0), _ptr(p.ctrl_default), int(device)
     return d, keep, params.shape[0]
+
+
+def math_eval(fn, x, device=0):
+    """The node programs' elementary function `fn` (0 reciprocal, 1 sqrt, 2 sin, 3 cos, 4 atan, 5 tanh, 6 exp) on the device."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    if not lib.fl_math_eval(int(device), int(fn), _ptr(x), _ptr(y), x.size):
+        raise RuntimeError("fl_math_eval: " + lib.fl_last_error().decode())
+    return y
 
 
 def problem_bounds(problem):

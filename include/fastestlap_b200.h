@@ -134,6 +134,9 @@ long fl_kernel_launches(const fl_nlp* nlp);                      /* kernels laun
 int  fl_flush_l2(fl_nlp* nlp);
 /* FP64 (non-tensor) pipe peak of the handle's device, measured with a DFMA micro-kernel: fused multiply-adds per second */
 double fl_measure_fp64_peak(fl_nlp* nlp);
+/* The node programs' branch-free elementary functions (csrc/fl_math.cuh) evaluated on the device, for the accuracy tests:
+ * fn 0 reciprocal, 1 sqrt, 2 sin, 3 cos, 4 atan, 5 tanh, 6 exp; x and y are host arrays of n doubles. */
+int fl_math_eval(int device, int fn, const double* x, double* y, long n);
 /* Page-locked host memory for the host-buffer entry points (pageable memory works too, at lower PCIe throughput). */
 void* fl_host_alloc(size_t bytes);
 void  fl_host_free(void* p);

@@ -15,7 +15,7 @@ os.makedirs(os.path.join(d, "generated"), exist_ok=True)
 G.OUT_DIR = os.path.join(d, "generated")
 print(G.generate(variant, G.VARIANTS[variant]))
 csrc = os.path.join(ROOT, "fastest_lap_b200", "csrc")
-for f in ("variant.cu", "nlp_kernels.cuh"):
+for f in ("variant.cu", "nlp_kernels.cuh", "fl_math.cuh"):
     shutil.copy(os.path.join(csrc, f), d)
 obj = os.path.join(d, "variant.o")
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
