@@ -58,7 +58,7 @@ class ParamTable:
 class Emitter:
     """Emits one function body: `inputs` maps symbol name -> C expression; outputs are (expr id, "statement with one %s") pairs."""
 
-    def __init__(self, graph, ptable, inputs, dfmt="D[%d]", cut=None, lazy_inputs=None, segment=0):
+    def __init__(self, graph, ptable, inputs, dfmt="D[%d]", cut=None, lazy_inputs=None, segment=0, order="dfs"):
         # cut: node id -> C expression that LOADS the node's value (a checkpoint written by an earlier pass) instead of
         # recomputing it; the load is emitted lazily, right before the first use
         # lazy_inputs: symbol name -> (local name, C expression that loads it), emitted at first use instead of up front
@@ -66,6 +66,10 @@ class Emitter:
         #          loads a segment needs are issued at the start of the PREVIOUS segment (software prefetch into registers)
         self.g, self.pt, self.inputs, self.dfmt, self.cut = graph, ptable, inputs, dfmt, (cut or {})
         self.lazy_inputs, self.segment = (lazy_inputs or {}), int(segment)
+        # order: "dfs" = each output's expression tree in post-order (short live ranges, consecutive statements depend on each
+        # other); "level" = by latency-weighted depth (independent chains, e.g. the four tyres, interleaved statement by
+        # statement, so that a lone warp has several instructions in flight)
+        self.order = order
 
     def body(self, outputs, indent="    "):
         g, pt = self.g, self.pt
@@ -159,9 +163,34 @@ class Emitter:
                 lines.append("%sconst double %s = %s;" % (indent, t, rhs))
                 name[n] = t
 
-        for e, fmt in outputs:
-            emit(e)
-            lines.append(indent + (fmt % ref(e)))
+        if self.order == "level":
+            weight = {RCP: 8, SQRT: 10, SIN: 25, COS: 25, ATAN: 30, TANH: 35, EXP: 20}
+            level = {}
+            for i in needed:                                   # topological order
+                if K[i] in (CONST, SYM) or i in self.cut or pt.param_only(i):
+                    level[i] = 0
+                else:
+                    level[i] = max(level[o] for o in g.operands(i)) + (0 if K[i] == NEG else weight.get(K[i], 1))
+            stores = {}
+            for e, fmt in outputs:
+                stores.setdefault(e, []).append(fmt)
+            # the nodes to compute: reachable from the outputs without going below a loaded value
+            cone, stack = set(), [e for e, _ in outputs]
+            while stack:
+                i = stack.pop()
+                if i in cone:
+                    continue
+                cone.add(i)
+                if not (K[i] in (CONST, SYM) or i in self.cut or pt.param_only(i)):
+                    stack.extend(g.operands(i))
+            for i in sorted(cone, key=lambda n: (level[n], n)):
+                emit(i)
+                for fmt in stores.get(i, ()):
+                    lines.append(indent + (fmt % ref(i)))
+        else:
+            for e, fmt in outputs:
+                emit(e)
+                lines.append(indent + (fmt % ref(e)))
         if self.segment > 0:
             lines = self._pipeline(lines, is_load, indent)
         return "\n".join(lines)

@@ -33,6 +33,10 @@ NPARTS = {"jac": int(os.environ.get("FL_NP_JAC", 4)), "hess": int(os.environ.get
 # arithmetic statements per fenced segment of a derivative partition (0 = no fences, all loads where the compiler puts them)
 SEGMENT = int(os.environ.get("FL_SEGMENT", 0))
 
+# statement order of the values pass (emit.py): "level" interleaves the independent chains of a node
+VALUES_ORDER = os.environ.get("FL_VALUES_ORDER", "level")
+DERIV_ORDER = os.environ.get("FL_DERIV_ORDER", "dfs")
+
 # > 0: tape nodes that this many (or more) derivative partitions share are checkpointed by the values pass (see shared_tape)
 SHARE = int(os.environ.get("FL_SHARE", 0))
 
@@ -189,7 +193,7 @@ def generate(name, variant):
     out_ck = [(n, "io.cs(%d, %%s);" % k) for k, n in enumerate(ck[:n_heavy])]
     out_ck_all = [(n, "io.cs(%d, %%s);" % k) for k, n in enumerate(ck)]
 
-    def fn(fname, outputs, pres, use_cut=True, cut=None):
+    def fn(fname, outputs, pres, use_cut=True, cut=None, order="dfs"):
         cut = cut_heavy if cut is None else cut
         lazy = {}
         if use_cut and SEGMENT > 0:
@@ -198,7 +202,7 @@ def generate(name, variant):
                 m = re.match(r"const double (\w+) = (io\.\w+\(\d*\));", l)
                 lazy[m.group(1)] = (m.group(1), m.group(2))
             pres = []
-        em = Emitter(g, pt, inputs, dfmt="io.d(%d)", cut=cut if use_cut else None, lazy_inputs=lazy, segment=SEGMENT if use_cut else 0)
+        em = Emitter(g, pt, inputs, dfmt="io.d(%d)", order=order, cut=cut if use_cut else None, lazy_inputs=lazy, segment=SEGMENT if use_cut else 0)
         body = em.body(outputs, indent="        ")
         head = "\n".join("        " + l for l in sum(pres, []))
         return ("    template <class IO> static __device__ __forceinline__ void %s(IO& io)\n    {\n%s\n%s\n    }\n" % (fname, head, body))
@@ -213,7 +217,7 @@ def generate(name, variant):
     outs, sizes = partition(g, [[o] for o in out_values + out_ck], NPARTS["values"])
     part_sizes["values"] = sizes
     for w, o in enumerate(outs):
-        parts.append(fn("values_p%d" % w, o, [pre], use_cut=False))
+        parts.append(fn("values_p%d" % w, o, [pre], use_cut=False, order=VALUES_ORDER))
     disp = ["    template <class IO> static __device__ __forceinline__ void values_part(int w, IO& io)", "    {", "        switch (w)", "        {"]
     for w in range(len(outs)):
         disp.append("        case %d: values_p%d(io); break;" % (w, w))
@@ -225,7 +229,7 @@ def generate(name, variant):
     n_tape = len(outs)
     if SHARE > 0:
         for w, o in enumerate(outs):
-            parts.append(fn("tape_p%d" % w, o, [pre, pre_w, pre_n], use_cut=False))
+            parts.append(fn("tape_p%d" % w, o, [pre, pre_w, pre_n], use_cut=False, order=VALUES_ORDER))
     disp = ["    template <class IO> static __device__ __forceinline__ void tape_part(int w, IO& io)", "    {", "        switch (w)", "        {"]
     for w in range(len(outs)):
         disp.append("        case %d: %s_p%d(io); break;" % (w, "tape" if SHARE > 0 else "values", w))
@@ -236,7 +240,7 @@ def generate(name, variant):
         outs, sizes = partition(g, groups, NPARTS[mode], stop=set(mcut))
         part_sizes[mode] = sizes
         for w, o in enumerate(outs):
-            parts.append(fn("%s_p%d" % (mode, w), o, pres, cut=mcut))
+            parts.append(fn("%s_p%d" % (mode, w), o, pres, cut=mcut, order=DERIV_ORDER))
         disp = ["    template <class IO> static __device__ __forceinline__ void %s_part(int w, IO& io)" % mode, "    {", "        switch (w)", "        {"]
         for w in range(len(outs)):
             disp.append("        case %d: %s_p%d(io); break;" % (w, mode, w))
