@@ -274,6 +274,36 @@ def gg_leg(args, torch, dist, world, rank, local):
 
 
 
+def kart_leg(args, torch, local):
+    """Callback rounds of BASELINE configs[3]: roberto-lot-kart-2016 (6DOF) on Vendrell, 2000 nodes, derivative form, at the
+    golden solution interpolated to the mesh; same ring-of-instances hygiene as the headline leg (rank 0 only)."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS
+    p = workloads.kart_vendrell(2000)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "kart_vendrell.npz"))
+    x = workloads.resample_point(p, g["s"], g["x"], p.nv)
+    lam = np.random.default_rng(1).standard_normal(p.m)
+    nlp = CollocationNLP(p, device=local)
+    per_instance = 8 * (2 * nlp.n + 2 * nlp.m + nlp.nnz_jac + nlp.nnz_hess + (nlp.n_values + nlp.n_checkpoints) * p.n_points)
+    R = max(2, int(np.ceil(1.5 * torch.cuda.get_device_properties(local).L2_cache_size / per_instance)) + 1)
+    ring = [nlp] + [CollocationNLP(p, device=local) for _ in range(R - 1)]
+    for h in ring:
+        h.eval_all(x, lam, 1.0, want=("f",))
+    K = max(args.steps, R)
+    timed = lambda what, count: sum(ring[k % R].time_device(what, 1.0, 1) for k in range(count))
+    timed(EVAL_ALL, R)
+    torch.cuda.synchronize()
+    dev_ms = timed(EVAL_ALL, K) / K
+    ker_ms = (timed(EVAL_JAC | EVAL_HESS, K) - timed(0, K)) / K
+    res = {"workload": "roberto-lot-kart-2016 6DOF, Vendrell, closed, derivative form, 2000 trapezoidal nodes, one full callback round per step; ring of %d instances" % R,
+           "variant": nlp.variant, "value": p.n_points / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms, "steps": K,
+           "kernels_ms": {"node_derivs": ker_ms}, "fp64_ops_per_node_eval": nlp.ops_per_node["all"], "n": nlp.n, "m": nlp.m,
+           "nnz_jac": nlp.nnz_jac, "nnz_hess": nlp.nnz_hess}
+    for h in ring:
+        h.close()
+    return res
+
+
 def single_lap_leg(args, torch, local):
     """One lap at a time (replicas only): BASELINE configs[0] (F1, Catalunya, 500 nodes: the reference's README example,
     "approximately 1 minute") and configs[2] (8000 nodes), solved from the steady-state start on this rank's GPU with the
@@ -458,6 +488,7 @@ def main():
             line["batched_solve"] = sl
             line["gpu_launches"] += int(sl["rank0_launches"]["solver_launches"]) + 3 * int(sl["rank0_launches"]["full_rounds"]) + 2 * int(sl["rank0_launches"]["fg_rounds"])
     if args.single_laps and rank == 0:
+        line["kart_callbacks"] = kart_leg(args, torch, local)
         line["single_lap_solve"] = single_lap_leg(args, torch, local)
     if args.gg_speeds > 0:
         gl = gg_leg(args, torch, dist, world, rank, local)

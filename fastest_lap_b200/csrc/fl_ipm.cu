@@ -190,9 +190,12 @@ int solve_refined(fl_ipm* s, const int* active, int ls_mode, double* ox, double*
     if (refine_steps < 0) refine_steps = I.o.refine_steps;
     for (int k = 0; k < refine_steps; ++k)
     {
-        vec_launch(s, k_ipm_residual, I, active, ls_mode);
-        if (!kkt_solve(s, active, ls_mode, I.e1, I.e2, s->wx, s->wy)) return 0;
-        vec_launch(s, k_ipm_axpy_sol, I, active, s->wx, s->wy, I.tx, I.ty, 0);
+        // the refinement solve runs for the laps whose residual asks for it (Ipopt's residual_ratio_max; Ipopt always takes
+        // one step, min_refinement_steps = 1: FL_IPM_REFINE_ALWAYS=1 does the same)
+        static const double ratio_max = std::getenv("FL_IPM_REFINE_ALWAYS") ? -1.0 : 1.0e-10;
+        vec_launch(s, k_ipm_residual, I, active, ls_mode, ratio_max);
+        if (!kkt_solve(s, I.act_refine, ls_mode, I.e1, I.e2, s->wx, s->wy)) return 0;
+        vec_launch(s, k_ipm_axpy_sol, I, (const int*)I.act_refine, s->wx, s->wy, I.tx, I.ty, 0);
         s->launches += 2;
     }
     vec_launch(s, k_ipm_axpy_sol, I, active, I.tx, I.ty, ox, oy, 1);
@@ -314,6 +317,7 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     s->wx = dalloc<double>(Bn, own); s->wy = dalloc<double>(Bm, own);
     I.dw = dalloc<double>(B, own); I.dc = dalloc<double>(B, own);
     I.act_factor = dalloc<int>(B, own); I.act_soc = dalloc<int>(B, own); I.act_run = dalloc<int>(B, own);
+    I.act_refine = dalloc<int>(B, own);
     I.counters = dalloc<int>(8, own);
     s->d_neg = dalloc<int>(B, own); s->d_zero = dalloc<int>(B, own);
     I.n_neg = s->d_neg; I.n_zero = s->d_zero;

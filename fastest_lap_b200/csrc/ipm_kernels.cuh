@@ -9,7 +9,9 @@
 // exact inertia reported by the block factorisation of kkt_kernels.cuh.  oracle/ipm.py is the numpy statement of the
 // same iteration.  Deviations from Ipopt: no NLP scaling; no restoration phase (when the line search finds no acceptable
 // step, or after 8 consecutive steps shorter than 0.05, the barrier problem is restarted from the current primal point
-// with a larger mu, an empty filter and reset multipliers, at most IPM_MAX_RESTARTS times, see ipm_restart); Jacobian
+// with a larger mu, an empty filter, bound multipliers on the central path, equality multipliers kept unless they have
+// blown up, and a cap on the constraint violation tied to the current one; at most IPM_MAX_RESTARTS times, see
+// ipm_restart); iterative refinement on demand (Ipopt's residual_ratio_max without its minimum of one step); Jacobian
 // regularisation dc always on (closed laps with an even node count have dependent rows).
 //
 // One block per lap -- or, for long laps that would leave the GPU idle, one thread-block CLUSTER per lap (up to 8 blocks
@@ -44,6 +46,7 @@ struct fl_ipm_dev
     double *dx, *ds, *dy, *dxs, *dss, *dys, *st;   // step, second-order-corrected step, trial slacks
     double *sigx, *sigs, *r1, *r2, *c, *csoc, *rsbar, *gx, *e1, *e2, *tx, *ty;
     double *dw, *dc;                               // [batch] mirrors of lap.dw / lap.dc for the factorisation
+    int* act_refine;                               // [batch] mask: the residual of the last solve asks for a refinement step
     int *act_factor, *act_soc, *act_run;           // [batch] masks: act_run = lap still iterating; act_soc = needs a second-order-correction solve;
                                                    // act_factor = pending factorisation (partitioned schedule), reused as "trial point pending" in the line search
     int* counters;                                 // [8]: 0 running laps, 1 pending factorisations, 2 laps in line search, 3 pending SOC solves
@@ -431,11 +434,14 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_rhs(const fl_ipm_dev I, i
 }
 
 // ---- residual of the full augmented system for iterative refinement: e = (r1, r2) - K (tx, ty) -----------------------------
-__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_residual(const fl_ipm_dev I, const int* active, int ls_mode)
+// Also decides whether the lap needs the refinement solve at all (Ipopt's residual_ratio_max): act_refine[lap] =
+// |e|_inf > ratio_max (|rhs|_inf + |solution|_inf).
+__global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_residual(const fl_ipm_dev I, const int* active, int ls_mode, double ratio_max)
 {
     IPM_LAP_PROLOGUE
     extern __shared__ double acc[];          // [IPM_NCPEMAX][blockDim.x]
-    if (active && !active[lap]) return;
+    if (active && !active[lap]) { if (t0 == 0) I.act_refine[lap] = 0; return; }
+    double emax = 0.0, rmax = 0.0, smax = 0.0;
     const double* jac = I.njac + (size_t)lap * I.nnz_jac;
     const double* hes = I.nhess + (size_t)lap * I.nnz_hess;
     const double dw = ls_mode ? 0.0 : L.dw, dc = L.dc;
@@ -453,7 +459,9 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_residual(const fl_ipm_dev
             const size_t k = oi + (size_t)(i / I.NCPE) * I.NINEQ + q;
             D = ls_mode ? 1.0 : 1.0 / (I.sigs[k] + dw) + dc;
         }
-        e2[i] = I.r2[om + i] - (e2[i] - D * ty[i]);
+        const double r = I.r2[om + i], e = r - (e2[i] - D * ty[i]);
+        e2[i] = e;
+        emax = fmax(emax, fabs(e)); rmax = fmax(rmax, fabs(r)); smax = fmax(smax, fabs(ty[i]));
     }
     // e1 = r1 - (H tx + (sigx + dw) tx + J^T ty)
     for (int i = t0; i < I.n; i += tstride) e1[i] = ls_mode ? tx[i] : (I.sigx[on + i] + dw) * tx[i];
@@ -462,7 +470,14 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_residual(const fl_ipm_dev
     ipm_sync();
     ipm_JT_mul(I, jac, ty, e1, true, acc);
     ipm_sync();
-    for (int i = t0; i < I.n; i += tstride) e1[i] = I.r1[on + i] - e1[i];
+    for (int i = t0; i < I.n; i += tstride)
+    {
+        const double r = I.r1[on + i], e = r - e1[i];
+        e1[i] = e;
+        emax = fmax(emax, fabs(e)); rmax = fmax(rmax, fabs(r)); smax = fmax(smax, fabs(tx[i]));
+    }
+    emax = ipm_block_max(emax, red); rmax = ipm_block_max(rmax, red); smax = ipm_block_max(smax, red);
+    if (t0 == 0) I.act_refine[lap] = (emax > ratio_max * (rmax + smax) || !isfinite(emax)) ? 1 : 0;
 }
 
 // (tx, ty) += (dx, dy) of the refinement solve;  or initialise
@@ -552,21 +567,32 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_soc_direction(const fl_ip
 }
 
 // Restart of the barrier problem at the current primal point (stands in for Ipopt's restoration phase, which this solver
-// does not have): larger mu, empty filter, equality multipliers forgotten, bound multipliers on the central path.
+// does not have): larger mu, empty filter, bound multipliers on the central path, equality multipliers forgotten when they
+// exceed y_init_max, theta_max tied to the current violation when the iterate is nearly feasible.  (Forgetting moderate
+// multipliers and the loose theta_max of a fresh start threw a nearly converged 8000-node lap back to a violation of 1.5;
+// with this form 4091 instead of 4057 laps of the 4096-lap sweep converge within 250 iterations.)
 // Used when the line search finds no acceptable step, or when the iteration has crawled with tiny steps for a while
 // (the multipliers then typically blow up).  At most IPM_MAX_RESTARTS times per lap.
-__device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L)
+__device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L, double* red)
 {
     const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni;
     __shared__ double sh_mu;
     const int t0 = ipm_rank() * blockDim.x + threadIdx.x, tstride = ipm_nranks() * blockDim.x;
+    // the equality multipliers are forgotten only when they have blown up (the crawl this restart is meant to end)
+    double ymax = 0.0;
+    for (int i = t0; i < I.m; i += tstride) ymax = fmax(ymax, fabs(I.y[om + i]));
+    ymax = ipm_block_max(ymax, red);
+    const bool keep_y = ymax <= I.o.y_init_max;
     if (t0 == 0)
     {
         L.n_restart += 1;
         L.mu = fmin(I.o.mu_init, fmax(100.0 * L.mu, 1.0e-4));
         L.tau = fmax(I.o.tau_min, 1.0 - L.mu);
         L.n_filter = 0; L.acc_count = 0; L.n_small = 0; L.dw_last = 0.0; L.dw_prev = 0.0;
-        L.theta_max = 1.0e4 * fmax(1.0, L.theta); L.theta_min = 1.0e-4 * fmax(1.0, L.theta);
+        // a nearly feasible iterate must stay nearly feasible: the restarted problem may not buy barrier decrease with
+        // more than 100 times the current constraint violation
+        L.theta_max = (L.theta > 1.0e-2) ? 1.0e4 * fmax(1.0, L.theta) : fmax(100.0 * L.theta, 1.0e-3);
+        L.theta_min = 1.0e-4 * fmax(1.0, L.theta);
         sh_mu = L.mu;
     }
     const double mu = ipm_bcast(&sh_mu);
@@ -581,7 +607,8 @@ __device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L)
         const double s = I.s[oi + k];
         I.vl[oi + k] = mu / (s - I.sl[k]); I.vu[oi + k] = mu / (I.su[k] - s);
     }
-    for (int i = t0; i < I.m; i += tstride) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
+    if (!keep_y)
+        for (int i = t0; i < I.m; i += tstride) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
 }
 
 // ---- filter line search: judge the trial point (f, g evaluated at it) --------------------------------------------------
@@ -693,7 +720,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
             L.n_small = (alpha < 0.05) ? L.n_small + 1 : 0;
             sh_restart = (L.n_small >= 8 && L.n_restart < IPM_MAX_RESTARTS) ? 1 : 0;
         }
-        if (ipm_bcast(&sh_restart)) ipm_restart(I, lap, L);
+        if (ipm_bcast(&sh_restart)) ipm_restart(I, lap, L, red);
     }
     else if (decision == 2)
     {
@@ -715,7 +742,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
         if (t0 == 0) { I.act_soc[lap] = 0; sh_can = L.n_restart < IPM_MAX_RESTARTS ? 1 : 0; }
         if (ipm_bcast(&sh_can))
         {
-            ipm_restart(I, lap, L);
+            ipm_restart(I, lap, L, red);
             if (t0 == 0) { L.ls = LS_DONE; L.iter += 1; }
         }
         else

@@ -15,7 +15,10 @@ p = workloads.f1_catalunya(nodes)
 params = workloads.sweep_parameters(MODEL_F1, laps)
 params[0] = p.params
 nlp = CollocationNLP(p, vehicle_params=params)
-solver = LapSolver(nlp)
+from fastest_lap_b200.ipm import default_options
+opts = default_options()
+opts.max_iter = int(os.environ.get('MAX_ITER', 3000))
+solver = LapSolver(nlp, opts)
 t0 = time.time()
 out = solver.solve(workloads.f1_start_point(p, 50.0), verbose=verbose)
 dt = time.time() - t0
