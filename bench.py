@@ -278,7 +278,7 @@ def kart_leg(args, torch, local):
     """Callback rounds of BASELINE configs[3]: roberto-lot-kart-2016 (6DOF) on Vendrell, 2000 nodes, derivative form, at the
     golden solution interpolated to the mesh; same ring-of-instances hygiene as the headline leg (rank 0 only)."""
     from fastest_lap_b200 import workloads
-    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, time_device_ring
     p = workloads.kart_vendrell(2000)
     g = np.load(os.path.join(ROOT, "tests", "golden", "kart_vendrell.npz"))
     x = workloads.resample_point(p, g["s"], g["x"], p.nv)
@@ -290,7 +290,7 @@ def kart_leg(args, torch, local):
     for h in ring:
         h.eval_all(x, lam, 1.0, want=("f",))
     K = max(args.steps, R)
-    timed = lambda what, count: sum(ring[k % R].time_device(what, 1.0, 1) for k in range(count))
+    timed = lambda what, count: time_device_ring(ring, what, count)
     timed(EVAL_ALL, R)
     torch.cuda.synchronize()
     dev_ms = timed(EVAL_ALL, K) / K
@@ -359,7 +359,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, pinned_empty
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, pinned_empty, time_device_ring
     p, x, lam = workload(args.nodes)
     # Ring of independent instances of the same lap: consecutive timed steps touch different buffers, and one trip round
     # the ring moves more bytes than the L2 holds, so every step finds its data in HBM (no flush kernel in between).
@@ -389,10 +389,9 @@ def main():
             h.sync()
 
     def timed(what, count):
-        ms = 0.0
-        for k in range(count):
-            ms += ring[k % R].time_device(what, 1.0, 1)
-        return ms
+        # `count` steps issued back to back on one stream, step k on instance k mod R, one pair of CUDA events around the
+        # sequence (fl_time_device_ring): device time of exactly `count` steps, free of the host's launch latency
+        return time_device_ring(ring, what, count)
 
     # ---- device-resident leg
     timed(EVAL_ALL, max(W, R))

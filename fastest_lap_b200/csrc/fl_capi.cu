@@ -526,6 +526,31 @@ double fl_time_device(fl_nlp* h, int what, double obj_factor, int reps)
     return (double)ms / reps;
 }
 
+// `steps` evaluations issued back to back on ONE stream, step k on instance k mod count (a ring of independent instances of
+// the same problem defeats the L2 between steps), bracketed by one pair of events: device time of the sequence in ms.
+// The host only has to keep the queue filled, so the figure does not contain its launch latency.
+double fl_time_device_ring(fl_nlp** hs, int count, int what, double obj_factor, int steps)
+{
+    if (!hs || count < 1 || steps < 1) return -1.0;
+    fl_nlp* h0 = hs[0];
+    if (cudaSetDevice(h0->device) != cudaSuccess) return -1.0;
+    for (int k = 0; k < count; ++k)
+    {
+        if (hs[k]->device != h0->device) { g_error = "fl_time_device_ring: instances on different devices"; return -1.0; }
+        if (cudaStreamSynchronize(hs[k]->stream) != cudaSuccess) return -1.0;
+    }
+    std::vector<cudaStream_t> own(count);
+    for (int k = 0; k < count; ++k) { own[k] = hs[k]->stream; hs[k]->stream = h0->stream; }
+    bool ok = cudaEventRecord(h0->ev0, h0->stream) == cudaSuccess;
+    for (int k = 0; ok && k < steps; ++k) ok = fl_eval_device(hs[k % count], what, obj_factor) != 0;
+    ok = ok && cudaEventRecord(h0->ev1, h0->stream) == cudaSuccess && cudaEventSynchronize(h0->ev1) == cudaSuccess;
+    for (int k = 0; k < count; ++k) hs[k]->stream = own[k];
+    if (!ok) { g_error = cudaGetErrorString(cudaGetLastError()); return -1.0; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h0->ev0, h0->ev1);
+    return (double)ms;
+}
+
 int fl_flush_l2(fl_nlp* h)
 {
     FL_CUDA(cudaSetDevice(h->device));

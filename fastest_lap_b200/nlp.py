@@ -66,6 +66,8 @@ def load_library():
     lib.fl_nlp_sync.argtypes = [C.c_void_p]
     lib.fl_time_device.restype = C.c_double
     lib.fl_time_device.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+    lib.fl_time_device_ring.restype = C.c_double
+    lib.fl_time_device_ring.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, C.c_int]
     lib.fl_kernel_launches.restype = C.c_long
     lib.fl_kernel_launches.argtypes = [C.c_void_p]
     lib.fl_host_alloc.restype = C.c_void_p
@@ -118,6 +120,16 @@ def math_eval(fn, x, device=0):
     if not lib.fl_math_eval(int(device), int(fn), _ptr(x), _ptr(y), x.size):
         raise RuntimeError("fl_math_eval: " + lib.fl_last_error().decode())
     return y
+
+
+def time_device_ring(ring, what, steps, obj_factor=1.0):
+    """Device milliseconds of `steps` evaluations issued back to back, step k on ring[k % len(ring)] (fl_time_device_ring)."""
+    lib = load_library()
+    hs = (C.c_void_p * len(ring))(*[h._h for h in ring])
+    ms = lib.fl_time_device_ring(hs, len(ring), int(what), float(obj_factor), int(steps))
+    if ms < 0:
+        raise RuntimeError("fl_time_device_ring: " + lib.fl_last_error().decode())
+    return float(ms)
 
 
 def problem_bounds(problem):

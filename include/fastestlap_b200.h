@@ -129,6 +129,9 @@ int  fl_nlp_sync(fl_nlp* nlp);
 void* fl_nlp_stream(fl_nlp* nlp);                                /* cudaStream_t */
 /* Times `reps` back-to-back enqueues of `what` with CUDA events on the handle's stream; returns ms per enqueue (< 0 on error). */
 double fl_time_device(fl_nlp* nlp, int what, double obj_factor, int reps);
+/* `steps` evaluations back to back on one stream, step k on instance k mod count (a ring of independent instances of the same
+ * problem, so that no step finds its data in L2), one pair of events around the sequence: device ms, -1 on error. */
+double fl_time_device_ring(fl_nlp** nlps, int count, int what, double obj_factor, int steps);
 long fl_kernel_launches(const fl_nlp* nlp);                      /* kernels launched by this handle so far */
 /* Writes a scratch buffer larger than the L2 cache on the handle's stream (benchmark hygiene between timed iterations). */
 int  fl_flush_l2(fl_nlp* nlp);
