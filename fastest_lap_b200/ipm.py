@@ -132,19 +132,27 @@ class LapSolver:
 
 
 def lap_time(problem, x, obj):
-    """Lap time of a solution: the objective minus the control-rate penalty (direct form, optimal_laptime.hpp:1358-1368)."""
+    """Lap time of a closed lap's solution: the objective minus the control-rate penalty -- direct form
+    diss ((u_j - u_i) / h)^2 h per element (optimal_laptime.hpp:1358-1368); derivative form 0.5 diss (du_l^2 + du_r^2) h with
+    the left rate taken at node 0 on every non-closing element, as the reference does (:1553, :1611)."""
     from .problem import FORM_DIRECT
     X = np.asarray(x).reshape(-1, problem.nv)
-    if problem.form != FORM_DIRECT or not problem.closed:
-        raise NotImplementedError("lap time from the objective: closed laps in direct form")
+    if not problem.closed:
+        raise NotImplementedError("lap time from the objective: closed laps")
     h = np.diff(np.append(problem.s, problem.track_length))
-    n_in = problem.nv - 2
     pen = 0.0
-    for c in range(2):
-        du = np.roll(X[:, n_in + c], -1) - X[:, n_in + c]
-        pen += problem.dissipation[c] * np.sum(du * du / h)
+    if problem.form == FORM_DIRECT:
+        n_in = problem.nv - 2
+        for c in range(2):
+            du = np.roll(X[:, n_in + c], -1) - X[:, n_in + c]
+            pen += problem.dissipation[c] * np.sum(du * du / h)
+    else:
+        n_in = problem.nv - 4
+        for c in range(2):
+            rate = X[:, n_in + 2 + c]
+            left = np.full(len(h), rate[0]); left[-1] = rate[-1]
+            pen += 0.5 * problem.dissipation[c] * np.sum((left * left + np.roll(rate, -1) ** 2) * h)
     return float(obj) - pen
-
 
 
 def solve_sweep(problem, vehicle_params, options=None, device=0, start_speeds_kmh=(50.0, 100.0, 150.0), retry_mu_init=1.0, retry_max_iter=600):

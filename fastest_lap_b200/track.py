@@ -131,3 +131,104 @@ def track_to_npz(track, path):
 def track_from_npz(path, name=""):
     d = np.load(path)
     return Track(d["s"], *[d[k] for k in _NPZ_KEYS], float(d["track_length"]), bool(int(d["closed"])), bool(int(d["with_elevation"])), name)
+
+
+class TrackByArcs:
+    """Straight-and-corner tracks of the reference's tests (src/core/vehicles/track_by_arcs.hpp:9-184; XML
+    `<track type="straight-and-curve" width=...>` with `<straight length=.../>` and `<corner sweep radius direction/>`
+    children): analytic centreline, constant half width `scale * width / 2` on both sides, no elevation.  Left-hand
+    corners have NEGATIVE curvature in the file's convention (track_by_arcs.hpp:42-43); the heading rate handed to the
+    road is `dot((-r'_y, r'_x), r'') / |r'|^2` (:127-137), which is what `node_data` returns.  On closed tracks the last
+    segment is not read but closes the loop (:69-76).  Same interface as `Track`."""
+
+    def __init__(self, source, scale=1.0, closed=True, name=""):
+        text = source if source.lstrip().startswith("<") else open(source).read()
+        root = ET.fromstring(text)
+        segs = list(root)
+        if not segs:
+            raise ValueError("Track is empty, and it cannot be used.")
+        self.name, self.closed = name, bool(closed)
+        self.half_width = 0.5 * scale * float(root.attrib["width"])
+        n = len(segs)
+        P, D, S0, K = np.zeros((n, 2)), np.tile([1.0, 0.0], (n, 1)), np.zeros(n), np.zeros(n)
+        total = 0.0
+
+        def corner(el):
+            R, theta = scale * float(el.attrib["radius"]), float(el.attrib["sweep"])
+            return (-1.0 / R if el.attrib["direction"].strip() == "left" else 1.0 / R), R, theta
+
+        for i, el in enumerate(segs[:-1]):
+            if el.tag == "straight":
+                L = scale * float(el.attrib["length"])
+                P[i + 1], D[i + 1], S0[i + 1] = P[i] + D[i] * L, D[i], S0[i] + L
+                total += L
+            elif el.tag == "corner":
+                k, R, theta = corner(el)
+                K[i] = k
+                nrm = np.array([-D[i][1], D[i][0]])
+                c2s = -nrm / k
+                centre = P[i] - c2s
+                d1, d2 = c2s / np.linalg.norm(c2s), D[i] / np.linalg.norm(D[i])
+                P[i + 1] = centre + R * (d1 * np.cos(theta) + d2 * np.sin(theta))
+                S0[i + 1] = S0[i] + R * theta
+                D[i + 1] = d2 * np.cos(theta) - d1 * np.sin(theta)
+                total += R * theta
+            else:
+                raise ValueError("Node not recognized")
+        last = segs[-1]
+        if last.tag == "straight":
+            total += np.linalg.norm(P[-1] - P[0]) if closed else scale * float(last.attrib["length"])
+        elif last.tag == "corner":
+            k, R, theta = corner(last)
+            K[-1] = k
+            total += R * theta
+        else:
+            raise ValueError("Node not recognized")
+        self._P, self._D, self._S0, self._K = P, D, S0, K
+        self.track_length = float(total)
+
+    def has_elevation(self):
+        return False
+
+    def _at(self, s):
+        """r, r', r'' at arclength s (track_by_arcs.hpp:140-184)."""
+        i = 0
+        while i < len(self._S0) - 1 and s >= self._S0[i + 1]:
+            i += 1
+        s0, k, p, d = s - self._S0[i], self._K[i], self._P[i], self._D[i]
+        if abs(k) < 1.0e-10:
+            return p + s0 * d, d.copy(), np.zeros(2)
+        theta = s0 * abs(k)
+        nrm = np.array([-d[1], d[0]]) / k
+        centre = p + nrm
+        d1 = -nrm / np.linalg.norm(nrm)
+        dr = d * np.cos(theta) - d1 * np.sin(theta)
+        return centre + (d1 * np.cos(theta) + d * np.sin(theta)) / abs(k), dr, np.array([-dr[1], dr[0]]) * k
+
+    def __call__(self, key, s):
+        s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+        out = np.zeros(len(s))
+        for j, sj in enumerate(s):
+            r, dr, d2r = self._at(float(sj))
+            if key == "x":
+                out[j] = r[0]
+            elif key == "y":
+                out[j] = r[1]
+            elif key == "yaw":
+                out[j] = np.arctan2(dr[1], dr[0])
+            elif key == "yaw_dot":
+                out[j] = (-dr[1] * d2r[0] + dr[0] * d2r[1]) / (dr[0] * dr[0] + dr[1] * dr[1])
+            elif key in ("nl", "nr"):
+                out[j] = self.half_width
+            elif key not in ("z", "pitch", "roll", "dpitch", "droll"):
+                raise KeyError(key)
+        return out
+
+    def left_track_limit(self, s):
+        return self("nl", s)
+
+    def right_track_limit(self, s):
+        return self("nr", s)
+
+    node_data = Track.node_data
+    position = Track.position

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from fastest_lap_b200 import vehicle_from_xml, track_from_xml, MODEL_F1, MODEL_KART      # noqa: E402
 from fastest_lap_b200.problem import LapProblem, FORM_DIRECT, FORM_DERIVATIVE            # noqa: E402
 from fastest_lap_b200.solution import solution_from_xml                                  # noqa: E402
-from fastest_lap_b200.track import track_to_npz                                          # noqa: E402
+from fastest_lap_b200.track import track_to_npz, TrackByArcs                                          # noqa: E402
 
 REF = "/root/reference/"
 DATA = REF + "src/test/applications/data/"
@@ -75,6 +75,16 @@ def main():
     # optimal_laptime_test.cpp:516-572
     golden_case("kart_vendrell", rental, vendrell, solution_from_xml(DATA + "vendrell_optimal.xml", MODEL_KART), (1.0e-2, 200 * 200.0 * 1.0e-10))
 
+    # straight-and-corner tracks (Track_by_arcs): f1_optimal_laptime_test.cpp:694-733 (closed, 100 points) and :655-692 (open,
+    # 401 points), dissipations 1e2 / 2e-3; optimal_laptime_test.cpp:283-334: the kart with direct torque, derivative form,
+    # oval scaled by 0.2, dissipations 1e-3 / 2e-9 -- the golden that pins the kart's direct-torque variants
+    oval = TrackByArcs(DATA + "ovaltrack.xml", 1.0, True)
+    golden_case("f1_ovaltrack_closed", f1, oval, solution_from_xml(DATA + "f1_ovaltrack_closed.xml", MODEL_F1), (1.0e2, 2.0e-3))
+    golden_case("f1_ovaltrack_open", f1, oval, solution_from_xml(DATA + "f1_ovaltrack_open.xml", MODEL_F1), (1.0e2, 2.0e-3))
+    oval_kart = TrackByArcs(DATA + "ovaltrack.xml", 0.2, True)
+    golden_case("kart_ovaltrack_derivative", kart, oval_kart, solution_from_xml(DATA + "ovaltrack_derivative.xml", MODEL_KART), (1.0e-3, 2.0e-9),
+                kart_direct_torque=True)
+
     # input data of the benchmark configurations: tracks and vehicle parameter vectors
     data_dir = os.path.join(HERE, "..", "..", "fastest_lap_b200", "data")
     os.makedirs(data_dir, exist_ok=True)
@@ -106,12 +116,6 @@ def steady_state_golden():
     print("kart_steady_state", len(names), "points")
 
 
-if __name__ == "__main__":
-    main()
-    steady_state_golden()
-    f1_steady_state_golden()
-
-
 def f1_steady_state_golden():
     """src/test/applications/data/f1_steady_state_test.xml (f1_steady_state_test.cpp, tolerance 2e-4): maximum lateral
     acceleration over speed and the G-G diagrams at 100 ... 300 km/h of limebeer-2014-f1."""
@@ -125,3 +129,9 @@ def f1_steady_state_golden():
             d["gg%d_%s" % (k, nm)] = vec("gg_diagram_%d/%s" % (k, q))
     np.savez_compressed(os.path.join(HERE, "f1_steady_state.npz"), **d)
     print("f1_steady_state", len(d["v"]), "speeds")
+
+
+if __name__ == "__main__":
+    main()
+    steady_state_golden()
+    f1_steady_state_golden()

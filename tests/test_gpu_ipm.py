@@ -9,7 +9,8 @@ from tests.helpers import load_golden, oracle_nlp, equality_rows
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["f1_catalunya_discrete", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell", "f1_catalunya_3d"]
+CASES = ["f1_catalunya_discrete", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell", "f1_catalunya_3d",
+         "f1_ovaltrack_closed", "kart_ovaltrack_derivative"]
 
 
 def _ineq_rows(p):
@@ -230,3 +231,29 @@ def test_warm_start_from_the_reference_multipliers():
     with pytest.raises(RuntimeError):
         solver.solve(ex["x"], warm=(ex["lam"], ex["zl"], ex["zu"]), warm_mu=0.0)
     solver.close(); nlp.close()
+
+
+def test_oval_track_laps_return_to_the_reference_solutions():
+    """The reference's oval-track tests (Track_by_arcs): the F1 on the closed oval (f1_ovaltrack_closed.xml) and the kart
+    with direct torque in derivative form on the oval scaled by 0.2 (ovaltrack_derivative.xml, the golden of the kart's
+    direct-torque variants; torque bounds +-200 as optimal_laptime_test.cpp:322-324), each from its golden point perturbed."""
+    from fastest_lap_b200.nlp import CollocationNLP, problem_bounds
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    rng = np.random.default_rng(0)
+    for name, rel, tol_x in (("f1_ovaltrack_closed", 1.0e-2, 1e-5), ("kart_ovaltrack_derivative", 1.0e-3, 1e-4)):
+        p, ex = load_golden(name)
+        nlp = CollocationNLP(p)
+        bounds = None
+        if name.startswith("kart"):
+            assert nlp.variant == "kart_derivative_torque"
+            xl, xu, gl, gu = problem_bounds(p)
+            xl.reshape(-1, p.nv)[:, 13], xu.reshape(-1, p.nv)[:, 13] = -200.0, 200.0          # [12 states, steering, torque, rates]
+            bounds = (xl, xu, gl, gu)
+        f_gold = nlp.eval_all(ex["x"], want=("f",))["f"][0]
+        solver = LapSolver(nlp, bounds=bounds)
+        out = solver.solve(ex["x"] * (1 + rel * rng.standard_normal(p.n)))
+        assert out["status"][0] == 1, (name, out["status"])
+        assert abs(out["obj"][0] - f_gold) <= 1e-7 * abs(f_gold), name
+        assert abs(lap_time(p, out["x"][0], out["obj"][0]) - float(ex["laptime"])) <= 2e-6 * float(ex["laptime"]), name
+        assert np.max(np.abs(out["x"][0] - ex["x"])) <= tol_x * max(1.0, np.max(np.abs(ex["x"]))), name
+        solver.close(); nlp.close()

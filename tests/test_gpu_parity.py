@@ -17,7 +17,8 @@ from tests.helpers import load_golden, oracle_nlp, rel_err
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell"]
+CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell",
+         "f1_ovaltrack_closed", "f1_ovaltrack_open", "kart_ovaltrack_derivative"]
 RTOL = 1.0e-10
 
 

@@ -10,7 +10,8 @@ import pytest
 
 from tests.helpers import load_golden, oracle_nlp, equality_rows
 
-CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell"]
+CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell",
+         "f1_ovaltrack_closed", "f1_ovaltrack_open", "kart_ovaltrack_derivative"]
 
 
 @pytest.fixture(scope="module", params=CASES)
