@@ -85,6 +85,23 @@ def main():
     golden_case("kart_ovaltrack_derivative", kart, oval_kart, solution_from_xml(DATA + "ovaltrack_derivative.xml", MODEL_KART), (1.0e-3, 2.0e-9),
                 kart_direct_torque=True)
 
+    # optimal_laptime_test.cpp:337-459: the kart on Catalunya "by arcs" scaled by 0.2, 500 points: direct form with direct
+    # torque (pins kart_direct_torque), derivative form with direct torque, derivative form with the throttle law
+    cat_arcs = TrackByArcs(DATA + "catalunya.xml", 0.2, True)
+    golden_case("kart_catalunya_direct", kart, cat_arcs, solution_from_xml(DATA + "optimal_laptime_catalunya_discrete.xml", MODEL_KART), (5.0, 8.0e-6),
+                kart_direct_torque=True)
+    golden_case("kart_catalunya_derivative", kart, cat_arcs, solution_from_xml(DATA + "catalunya_derivative.xml", MODEL_KART), (1.0e-2, 1.0e-10),
+                kart_direct_torque=True)
+    golden_case("kart_catalunya_derivative_throttle", kart, cat_arcs, solution_from_xml(DATA + "catalunya_derivative_throttle.xml", MODEL_KART),
+                (1.0e-2, 200 * 200.0 * 1.0e-10))
+    # f1_optimal_laptime_test.cpp:215-258: non-uniform ("adapted") mesh of the track file
+    golden_case("f1_catalunya_adapted", f1, catalunya_adapted, solution_from_xml(DATA + "f1_optimal_laptime_catalunya_adapted.xml", MODEL_F1), (50.0, 20.0 * 8.0e-4))
+    # f1_optimal_laptime_test.cpp:736-778 and :857-906: ferrari-2022-australia on Melbourne, 700 points, both forms
+    ferrari = vehicle_from_xml(REF + "database/vehicles/f1/ferrari-2022-australia.xml")
+    melbourne = track_from_xml(REF + "database/tracks/melbourne/melbourne.xml")
+    golden_case("f1_melbourne_direct", ferrari, melbourne, solution_from_xml(DATA + "f1_optimal_laptime_melbourne_700_direct.xml", MODEL_F1), (50.0, 20.0 * 8.0e-4))
+    golden_case("f1_melbourne_derivative", ferrari, melbourne, solution_from_xml(DATA + "f1_optimal_laptime_melbourne_700_derivative.xml", MODEL_F1), (1.0e-1, 1.0e-5))
+
     # input data of the benchmark configurations: tracks and vehicle parameter vectors
     data_dir = os.path.join(HERE, "..", "..", "fastest_lap_b200", "data")
     os.makedirs(data_dir, exist_ok=True)

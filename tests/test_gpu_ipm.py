@@ -10,7 +10,7 @@ from tests.helpers import load_golden, oracle_nlp, equality_rows
 pytestmark = pytest.mark.gpu
 
 CASES = ["f1_catalunya_discrete", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell", "f1_catalunya_3d",
-         "f1_ovaltrack_closed", "kart_ovaltrack_derivative"]
+         "f1_ovaltrack_closed", "kart_ovaltrack_derivative", "kart_catalunya_direct", "f1_catalunya_adapted", "f1_melbourne_derivative"]
 
 
 def _ineq_rows(p):

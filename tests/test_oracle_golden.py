@@ -11,7 +11,8 @@ import pytest
 from tests.helpers import load_golden, oracle_nlp, equality_rows
 
 CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell",
-         "f1_ovaltrack_closed", "f1_ovaltrack_open", "kart_ovaltrack_derivative"]
+         "f1_ovaltrack_closed", "f1_ovaltrack_open", "kart_ovaltrack_derivative", "kart_catalunya_direct", "kart_catalunya_derivative",
+         "kart_catalunya_derivative_throttle", "f1_catalunya_adapted", "f1_melbourne_direct", "f1_melbourne_derivative"]
 
 
 @pytest.fixture(scope="module", params=CASES)
@@ -24,7 +25,7 @@ def case(request):
 def test_equality_rows_vanish(case):
     p, ex, r = case
     g = r["g"].reshape(p.n_elements, p.ncpe)
-    assert np.abs(g[:, equality_rows(p)]).max() < 5.0e-11
+    assert np.abs(g[:, equality_rows(p)]).max() < 1.0e-10          # the constr_viol_tol the reference solved them to
 
 
 def test_laptime(case):
