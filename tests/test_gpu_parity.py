@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell",
          "f1_ovaltrack_closed", "f1_ovaltrack_open", "kart_ovaltrack_derivative", "kart_catalunya_direct", "kart_catalunya_derivative",
-         "kart_catalunya_derivative_throttle", "f1_catalunya_adapted", "f1_melbourne_direct", "f1_melbourne_derivative"]
+         "kart_catalunya_derivative_throttle", "f1_catalunya_adapted", "f1_melbourne_direct", "f1_melbourne_derivative", "f1_catalunya_2022_3d", "f1_laguna_seca_3d"]
 RTOL = 1.0e-10
 
 
