@@ -100,20 +100,23 @@ def track_from_xml(source, name=""):
         if len(a) != n:
             raise ValueError("track arrays must have number_of_points entries")
     length = float(root.find("header/track_length").text)
-    # kerbs (track_by_polynomial.hpp:93-108) widen nl / nr where a used kerb covers the sample
+    # kerbs (track_by_polynomial.hpp:93-108; XML layout kerb.h:158-170: every child of <left> / <right> is a kerb with
+    # arclength_start, arclength_finish, width and a `used` attribute): a sample inside a used kerb gets nl / nr widened by
+    # the width of the FIRST such kerb
     kerbs = root.find("kerbs")
     if kerbs is not None:
         for side, arr in (("left", nl), ("right", nr)):
             node = kerbs.find(side)
             if node is None:
                 continue
-            for kerb in node.findall("kerb"):
-                used = (kerb.findtext("used") or "true").strip().lower() == "true"
-                if not used:
+            done = np.zeros(len(s), dtype=bool)
+            for kerb in node:
+                if kerb.attrib.get("used", "").strip().lower() not in ("1", "true"):
                     continue
                 s0, s1, wd = float(kerb.findtext("arclength_start")), float(kerb.findtext("arclength_finish")), float(kerb.findtext("width"))
-                mask = (s > s0 - 1.0e-12) & (s < s1 + 1.0e-12)
+                mask = (s > s0 - 1.0e-12) & (s < s1 + 1.0e-12) & ~done
                 arr[mask] += wd
+                done |= mask
     return Track(s, x, y, z, yaw, pitch, roll, yaw_dot, dpitch, droll, nl, nr, length, ttype == "closed", elev, name)
 
 

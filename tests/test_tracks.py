@@ -45,3 +45,22 @@ def test_malformed_tracks_are_refused():
         TrackByArcs('<t type="straight-and-curve" width="1.0"></t>')
     with pytest.raises(ValueError):
         TrackByArcs('<t type="straight-and-curve" width="1.0"><straight length="1.0"/><chicane/><straight length="1.0"/></t>')
+
+
+def test_kerbs_widen_the_track_limits():
+    """track_by_polynomial.hpp:93-108 with the XML layout of kerb.h:158-170: used kerbs widen nl / nr on their stretch (the
+    first matching kerb only), unused ones do nothing."""
+    from fastest_lap_b200.track import track_from_xml
+    n = 11
+    arr = lambda v: ", ".join(repr(float(x)) for x in v)
+    s = np.linspace(0.0, 100.0, n)
+    zeros = arr(np.zeros(n))
+    xml = ("<circuit format=\"discrete\" type=\"open\" dimensions=\"2\"><header><track_length>100.0</track_length></header>"
+           "<data number_of_points=\"%d\"><arclength>%s</arclength><centerline><x>%s</x><y>%s</y></centerline><yaw>%s</yaw><yaw_dot>%s</yaw_dot><nl>%s</nl><nr>%s</nr></data>"
+           "<kerbs><left><kerb_element_1 used=\"1\"><arclength_start>20.0</arclength_start><arclength_finish>40.0</arclength_finish><width>1.5</width></kerb_element_1>"
+           "<kerb_element_2 used=\"1\"><arclength_start>30.0</arclength_start><arclength_finish>60.0</arclength_finish><width>0.5</width></kerb_element_2></left>"
+           "<right><kerb_element_1 used=\"0\"><arclength_start>0.0</arclength_start><arclength_finish>100.0</arclength_finish><width>2.0</width></kerb_element_1></right></kerbs></circuit>"
+           % (n, arr(s), arr(s), zeros, zeros, zeros, arr(np.full(n, 5.0)), arr(np.full(n, 6.0))))
+    t = track_from_xml(xml)
+    np.testing.assert_allclose(t.left_track_limit(s), [5, 5, 6.5, 6.5, 6.5, 5.5, 5.5, 5, 5, 5, 5])
+    np.testing.assert_allclose(t.right_track_limit(s), 6.0)
