@@ -69,7 +69,7 @@ class Track:
         return np.stack([self("x", s), self("y", s), self("z", s)], axis=-1)
 
 
-def track_from_xml(source, name=""):
+def track_from_xml(source, name="", use_kerbs=True):
     text = source if source.lstrip().startswith("<") else open(source).read()
     root = ET.fromstring(text)
     if root.attrib.get("format") != "discrete":
@@ -103,7 +103,7 @@ def track_from_xml(source, name=""):
     # kerbs (track_by_polynomial.hpp:93-108; XML layout kerb.h:158-170: every child of <left> / <right> is a kerb with
     # arclength_start, arclength_finish, width and a `used` attribute): a sample inside a used kerb gets nl / nr widened by
     # the width of the FIRST such kerb
-    kerbs = root.find("kerbs")
+    kerbs = root.find("kerbs") if use_kerbs else None
     if kerbs is not None:
         for side, arr in (("left", nl), ("right", nr)):
             node = kerbs.find(side)

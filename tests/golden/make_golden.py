@@ -103,8 +103,10 @@ def main():
     golden_case("f1_melbourne_derivative", ferrari, melbourne, solution_from_xml(DATA + "f1_optimal_laptime_melbourne_700_derivative.xml", MODEL_F1), (1.0e-1, 1.0e-5))
 
     # f1_optimal_laptime_test.cpp:1249-1292 and :1343-1388: two more 3-D tracks, each on the mesh of its track file
+    # (the stored Laguna Seca run predates the used="1" kerbs of today's track file: with the limits widened by them the
+    # optimum is 0.56 s faster, 58.7284 s; without them the stored 59.287501 s is reproduced to 4e-10 from a cold start)
     for nm, trk in (("f1_catalunya_2022_3d", "catalunya_2022/catalunya_2022_3d.xml"), ("f1_laguna_seca_3d", "laguna_seca/laguna_seca_3d.xml")):
-        golden_case(nm, f1, track_from_xml(REF + "database/tracks/" + trk), solution_from_xml(DATA + "f1_optimal_laptime_%s.xml" % nm[3:], MODEL_F1), (50.0, 50.0 * 8.0e-4))
+        golden_case(nm, f1, track_from_xml(REF + "database/tracks/" + trk, use_kerbs=False), solution_from_xml(DATA + "f1_optimal_laptime_%s.xml" % nm[3:], MODEL_F1), (50.0, 50.0 * 8.0e-4))
 
     # input data of the benchmark configurations: tracks and vehicle parameter vectors
     data_dir = os.path.join(HERE, "..", "..", "fastest_lap_b200", "data")
