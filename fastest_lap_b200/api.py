@@ -280,7 +280,25 @@ def optimal_laptime(vehicle, track, s, options=""):
     nlp = CollocationNLP(p)
     solver = LapSolver(nlp, bounds=bounds)
     out = solver.solve(x0, verbose=o["print_level"] >= 5, warm=warm)
-    solver.close(); nlp.close()
+    solver.close()
+    if out["status"][0] < 1 and closed and warm is None:
+        # The solver has no restoration phase: a closed lap that does not converge from the requested starting speed is tried
+        # again from faster steady states with a larger initial barrier parameter (ipm.solve_sweep does the same for batches;
+        # the reference wraps such retry loops around Ipopt itself, steady_state.hpp:200-226).
+        from .ipm import default_options
+        opts = default_options()
+        opts.mu_init = 1.0
+        for factor in (2.0, 3.0):
+            if veh.model == MODEL_F1:
+                x_try = workloads.f1_start_point(p, factor * o["speed"])
+            else:
+                x_try = np.tile(_kart_start_node(veh, factor * o["speed"] * KMH, form), p.n_points)
+            solver = LapSolver(nlp, opts, bounds=bounds)
+            out = solver.solve(x_try, verbose=o["print_level"] >= 5)
+            solver.close()
+            if out["status"][0] >= 1:
+                break
+    nlp.close()
     if o["save_warm_start"] and out["status"][0] >= 1:
         _warm_start[veh.model] = dict(s=s.copy(), track=trk, x=out["x"][0].copy(), lam=out["y"][0].copy(), zl=out["zl"][0].copy(), zu=out["zu"][0].copy())
     if out["status"][0] < 1:
