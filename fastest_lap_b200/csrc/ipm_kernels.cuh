@@ -116,16 +116,21 @@ __device__ void ipm_JT_mul(const fl_ipm_dev& I, const double* jac, const double*
             for (int c = 0; c < NV; ++c) acc[c * (int)blockDim.x + threadIdx.x] = accumulate ? out[(size_t)j * NV + c] : 0.0;
             const int node = j + I.node0;
             const int e_in = node == 0 ? I.n_points - 1 : node - 1;
+            // the element's entries of w, once, into a per-thread array: indexed by the (warp-uniform) row of slot k it is a
+            // coalesced local-memory access, where w[e * NCPE + row] was a 32-sector gather per slot
+            double wr[IPM_NCPEMAX];
+            for (int r = 0; r < I.NCPE; ++r) wr[r] = __ldg(w + (size_t)e_in * I.NCPE + r);
 #pragma unroll 8
             for (int k = 0; k < I.NJA; ++k)
-                acc[I.t.ja_col[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)k * I.n_el + e_in) * __ldg(w + (size_t)e_in * I.NCPE + I.t.ja_row[k]);
+                acc[I.t.ja_col[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)k * I.n_el + e_in) * wr[I.t.ja_row[k]];
             const bool has_out = I.closed || node + 1 < I.n_points;
             if (has_out)
             {
                 const int e_out = node, eb = e_out - I.node0;
+                for (int r = 0; r < I.NCPE; ++r) wr[r] = __ldg(w + (size_t)e_out * I.NCPE + r);
 #pragma unroll 8
                 for (int k = 0; k < I.NJB; ++k)
-                    acc[I.t.jb_col[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb) * __ldg(w + (size_t)e_out * I.NCPE + I.t.jb_row[k]);
+                    acc[I.t.jb_col[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb) * wr[I.t.jb_row[k]];
             }
             for (int c = 0; c < NV; ++c) out[(size_t)j * NV + c] = acc[c * (int)blockDim.x + threadIdx.x];
         }
@@ -144,14 +149,19 @@ __device__ void ipm_J_mul(const fl_ipm_dev& I, const double* jac, const double* 
             for (int r = 0; r < NCPE; ++r) acc[r * (int)blockDim.x + threadIdx.x] = 0.0;
             const int nj = (e + 1 == I.n_points) ? 0 : e + 1;          // right node
             const int sj = nj - I.node0;
+            double vr[IPM_NVMAX];
+            for (int c = 0; c < NV; ++c) vr[c] = __ldg(v + (size_t)sj * NV + c);
 #pragma unroll 8
             for (int k = 0; k < I.NJA; ++k)
-                acc[I.t.ja_row[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)k * I.n_el + e) * __ldg(v + (size_t)sj * NV + I.t.ja_col[k]);
+                acc[I.t.ja_row[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)k * I.n_el + e) * vr[I.t.ja_col[k]];
             const int eb = e - I.node0;
             if (eb >= 0)
+            {
+                for (int c = 0; c < NV; ++c) vr[c] = __ldg(v + (size_t)eb * NV + c);
 #pragma unroll 8
                 for (int k = 0; k < I.NJB; ++k)
-                    acc[I.t.jb_row[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb) * __ldg(v + (size_t)eb * NV + I.t.jb_col[k]);
+                    acc[I.t.jb_row[k] * (int)blockDim.x + threadIdx.x] += __ldg(jac + (size_t)I.NJA * I.n_el + (size_t)k * I.nB + eb) * vr[I.t.jb_col[k]];
+            }
             for (int r = 0; r < NCPE; ++r) out[(size_t)e * NCPE + r] = acc[r * (int)blockDim.x + threadIdx.x];
         }
     }
@@ -167,13 +177,15 @@ __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const doub
         if (j < I.S)
         {
             for (int c = 0; c < NV; ++c) acc[c * (int)blockDim.x + threadIdx.x] = out[(size_t)j * NV + c];
+            double vr[IPM_NVMAX];
+            for (int c = 0; c < NV; ++c) vr[c] = __ldg(v + (size_t)j * NV + c);
 #pragma unroll 8
             for (int k = 0; k < I.NH; ++k)
             {
                 const int r = I.t.h_row[k], c = I.t.h_col[k];
                 const double h = __ldg(hes + (size_t)k * I.S + j);
-                acc[r * (int)blockDim.x + threadIdx.x] += h * __ldg(v + (size_t)j * NV + c);
-                if (r != c) acc[c * (int)blockDim.x + threadIdx.x] += h * __ldg(v + (size_t)j * NV + r);
+                acc[r * (int)blockDim.x + threadIdx.x] += h * vr[c];
+                if (r != c) acc[c * (int)blockDim.x + threadIdx.x] += h * vr[r];
             }
             // couplings with the previous node (element e_in) and with the next node (element e_out)
             const int node = j + I.node0;
