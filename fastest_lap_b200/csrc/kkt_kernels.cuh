@@ -76,7 +76,10 @@ struct fl_kkt_dev
 };
 
 constexpr int KLD = 32;                                   // leading dimension of the stage matrices in shared memory
-constexpr int KT = 128;                                   // threads per lap
+#ifndef FL_KT
+#define FL_KT 128
+#endif
+constexpr int KT = FL_KT;                                   // threads per lap
 constexpr int KW = KT / 32;                               // warps per lap: columns are dealt round-robin to the warps
 #define KM(M, r, c) (M)[(r) + KLD * (c)]
 
