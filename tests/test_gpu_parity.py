@@ -269,3 +269,38 @@ def test_batch_linearity_in_the_multipliers():
     scale = np.maximum(np.abs(h1) + np.abs(h2), 1.0)
     assert np.max(np.abs(h12 - h1 - h2) / scale) <= 1e-9       # entries are sums of ~40 products of mixed sign: fp64 cancellation
     nlp.close()
+
+
+# ---- the two generated variants without a golden of their own ---------------------------------------------------------
+@pytest.mark.parametrize("name, form", [("kart_vendrell", 0), ("kart_catalunya_direct", 1), ("f1_catalunya_3d", 1), ("f1_laguna_seca_3d", 1)])
+def test_variants_without_a_golden_match_the_oracle(name, form):
+    """`kart_direct` (throttle law, direct form), `f1_derivative_3d` and, for good measure, the other form of two more
+    goldens: the problem of a golden rebuilt in the OTHER form (control rates dropped from / appended to the stored point),
+    every callback against the oracle at perturbed points.  The oracle's form handling is the one its pinned cases use."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.problem import FORM_DIRECT
+    p, ex = load_golden(name)
+    assert p.form != form
+    n_state = p.nv - (2 if p.form == FORM_DIRECT else 4)
+    X = ex["x"].reshape(-1, p.nv)
+    X = X[:, :n_state + 2] if form == FORM_DIRECT else np.hstack([X, np.zeros((X.shape[0], 2))])
+    diss = (5.0, 8.0e-6) if (form == FORM_DIRECT and p.model == 1) else ((50.0, 1.6e-2) if form == FORM_DIRECT else (1.0e-1, 1.0e-5))
+    q = type(p)(p.model, form, p.closed, p.s, p.track_length, p.track_nodes, p.wl, p.wr, p.params, diss, p.sigma, p.elevation,
+                p.q0, p.u0, p.du0, p.ctrl_default, p.kart_direct_torque)
+    nlp, o = CollocationNLP(q), oracle_nlp(q)
+    expected = {("kart_vendrell", 0): "kart_direct", ("kart_catalunya_direct", 1): "kart_derivative_torque",
+                ("f1_catalunya_3d", 1): "f1_derivative_3d", ("f1_laguna_seca_3d", 1): "f1_derivative_3d"}[(name, form)]
+    assert nlp.variant == expected
+    jr, jc, hr, hc = nlp.structure()
+    rng = np.random.default_rng(11)
+    x0 = np.ascontiguousarray(X).ravel()
+    for _ in range(3):
+        x = x0 * (1.0 + 0.01 * rng.standard_normal(q.n)) + 1.0e-4 * rng.standard_normal(q.n)
+        lam, obj = rng.standard_normal(q.m) * 0.1, float(rng.uniform(0.1, 1.0))
+        ref, out = o.eval(x, lam, obj), nlp.eval_all(x, lam, obj)
+        assert abs(out["f"][0] - ref["f"]) <= RTOL * max(1.0, abs(ref["f"]))
+        assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
+        assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
+        _matrix_close(_csr(jr, jc, out["jac"][0], (q.m, q.n)), _csr(*ref["jac"], (q.m, q.n)), "jacobian", q.ncpe)
+        _matrix_close(_csr(hr, hc, out["hess"][0], (q.n, q.n)), _csr(*ref["hess"], (q.n, q.n)), "hessian", q.nv, rtol=1.0e-8)
+    nlp.close()
