@@ -173,14 +173,14 @@ FLM double fl_exp(double y)
 {
     double sc, p;
     flm_exp_parts(y, sc, p);
-    return fma(sc, p, sc);
+    return y != y ? y : fma(sc, p, sc);          // fmin / fmax above swallow a NaN
 }
 
 FLM double fl_expm1(double y)
 {
     double sc, p;
     flm_exp_parts(y, sc, p);
-    return fma(sc, p, sc - 1.0);
+    return y != y ? y : fma(sc, p, sc - 1.0);
 }
 
 // tanh(x) = -em / (2 + em), em = expm1(-2 |x|)
@@ -189,5 +189,5 @@ FLM double fl_tanh(double x)
     const double a = fmin(fabs(x), 40.0);
     const double em = fl_expm1(-2.0 * a);
     const double t = fl_div(-em, 2.0 + em);
-    return x < 0.0 ? -t : t;
+    return x != x ? x : (x < 0.0 ? -t : t);
 }

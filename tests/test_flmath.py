@@ -72,6 +72,8 @@ def test_exponential_and_hyperbolic_tangent(flm):
     x = x[x != 0]
     assert _ulps(flm(5, x), np.tanh(x)) <= 3.5          # the division after expm1 adds to its 1.5 ulp
     assert flm(5, np.array([0.0]))[0] == 0.0 and flm(5, np.array([1e3]))[0] == 1.0
+    for fn in range(7):          # a NaN argument stays a NaN (the solver's non-finite checks rely on it)
+        assert np.isnan(flm(fn, np.array([np.nan]))[0]), fn
 
 
 @pytest.mark.gpu
