@@ -309,8 +309,11 @@ struct kkt_smem
     int flag;
 };
 
+#ifndef FL_KMINB
+#define FL_KMINB 6          // 80 registers instead of 96: six laps per SM instead of five (factor phase of the 4096-lap sweep 10.25 -> 9.98 s)
+#endif
 template <int NV, int NEQ>
-__global__ void __launch_bounds__(KT) k_kkt_factor(const fl_kkt_dev K)
+__global__ void __launch_bounds__(KT, FL_KMINB) k_kkt_factor(const fl_kkt_dev K)
 {
     using St = kkt_stage<NV, NEQ>;
     constexpr int NB = St::NB, CB = St::CB, CV = St::CV;
