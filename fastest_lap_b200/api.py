@@ -59,6 +59,27 @@ def print_variables():
         print("%-40s %s" % (k, type(v).__name__))
 
 
+def print_variable(variable_name):
+    v = _get(variable_name)
+    if isinstance(v, Vehicle):
+        print(v.to_xml())
+    elif isinstance(v, Track):
+        print("track \"%s\": length %.6f m, %s" % (variable_name, v.track_length, "closed" if v.closed else "open"))
+    else:
+        print(v)
+
+
+def create_vehicle_empty(name, vehicle_type):
+    """A vehicle of the given type with every parameter 0, to be filled with vehicle_set_parameter (fastestlapc.cpp
+    create_vehicle_empty)."""
+    _check_free(name)
+    model = {"f1-3dof": MODEL_F1, "kart-6dof": MODEL_KART}.get(vehicle_type)
+    if model is None:
+        raise FastestLapError("[ERROR] vehicle type \"%s\" not recognized" % vehicle_type)
+    from .vehicle import F1_PARAM_PATHS, KART_PARAM_PATHS
+    _table[name] = Vehicle(model, np.zeros(len(F1_PARAM_PATHS if model == MODEL_F1 else KART_PARAM_PATHS)), name)
+
+
 def create_vehicle_from_xml(name, database_file):
     _check_free(name)
     _table[name] = vehicle_from_xml(database_file, name)
@@ -130,6 +151,39 @@ def download_variables(prefix, variable_list):
 
 def vehicle_set_parameter(vehicle, parameter_name, parameter_value):
     _get(vehicle, Vehicle).set_parameter(parameter_name, float(parameter_value))
+
+
+def vehicle_save_as_xml(vehicle_name, xml_file_name):
+    with open(xml_file_name, "w") as fh:
+        fh.write(_get(vehicle_name, Vehicle).to_xml())
+
+
+def vehicle_declare_new_constant_parameter(vehicle_name, parameter_path, parameter_alias, parameter_value):
+    """The reference registers `parameter_path` under an alias for its sensitivity analysis and sets its value; the
+    sensitivities are not computed on this path, the value is set."""
+    _get(vehicle_name, Vehicle).set_parameter(parameter_path, float(parameter_value))
+
+
+def vehicle_change_track(vehicle_name, track_name):
+    """Vehicles of the reference carry their road; here the track is an argument of optimal_laptime: only checked."""
+    _get(vehicle_name, Vehicle); _get(track_name, Track)
+
+
+def vehicle_type_get_sizes(vehicle_type_name):
+    model = {"f1-3dof": MODEL_F1, "kart-6dof": MODEL_KART}.get(vehicle_type_name)
+    if model is None:
+        raise FastestLapError("[ERROR] vehicle type \"%s\" not recognized" % vehicle_type_name)
+    inputs, controls = names_of(model)
+    return len(inputs), len(controls), 4          # outputs stored by this path: laptime, x, y, psi
+
+
+def track_coordinates(track):
+    """Centreline, left and right boundary and heading (fastest_lap.py:329-338)."""
+    t = _get(track, Track)
+    s = t.s_data
+    x, y, th = t("x", s), t("y", s), t("yaw", s)
+    nl, nr = t("nl", s), t("nr", s)
+    return x, y, x + nl * np.sin(th), y - nl * np.cos(th), x - nr * np.sin(th), y + nr * np.cos(th), th
 
 
 def track_download_length(track_name):

@@ -81,6 +81,19 @@ class Vehicle:
         key = path[len("vehicle/"):] if path.startswith("vehicle/") else path
         return float(self.params[self.paths.index(key)])
 
+    def to_xml(self):
+        """The vehicle as a database file (vehicle_save_as_xml of the reference): <vehicle type=...> with one leaf per
+        parameter path; `vehicle_from_xml` reads it back to the same parameter vector."""
+        root = ET.Element("vehicle", type="f1-3dof" if self.model == MODEL_F1 else "kart-6dof")
+        for path, value in zip(self.paths, self.params):
+            node = root
+            for part in path.split("/"):
+                nxt = node.find(part)
+                node = ET.SubElement(node, part) if nxt is None else nxt
+            node.text = repr(float(value))
+        ET.indent(root, space="    ")
+        return ET.tostring(root, encoding="unicode")
+
 
 def vehicle_from_xml(source, name=""):
     """`source` is a file name or an XML string."""

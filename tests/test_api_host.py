@@ -1,0 +1,55 @@
+"""Host-only part of the fastest_lap.py-style surface (no GPU): the table of named objects, vehicle files, track data."""
+import os
+import numpy as np
+import pytest
+
+from fastest_lap_b200 import api, workloads
+from fastest_lap_b200.track import track_from_npz
+from fastest_lap_b200.vehicle import vehicle_from_xml
+
+
+def test_vehicle_table_and_files(tmp_path, capsys):
+    api.delete_variable("*")
+    api.create_vehicle_empty("car", "f1-3dof")
+    assert api.variable_type("car") == "f1-3dof"
+    with pytest.raises(api.FastestLapError):
+        api.create_vehicle_empty("car", "f1-3dof")              # the name is taken
+    with pytest.raises(api.FastestLapError):
+        api.create_vehicle_empty("other", "truck")
+    ref = workloads._vehicles()["limebeer_2014_f1"]
+    for path, value in zip(api._get("car").paths, ref):
+        api.vehicle_set_parameter("car", "vehicle/" + path, value)
+    api.vehicle_declare_new_constant_parameter("car", "vehicle/chassis/mass", "mass", 700.0)
+    xml = str(tmp_path / "car.xml")
+    api.vehicle_save_as_xml("car", xml)
+    back = vehicle_from_xml(xml)
+    assert back.model == api._get("car").model and back.get_parameter("vehicle/chassis/mass") == 700.0
+    assert np.array_equal(np.delete(back.params, 0), np.delete(ref, 0))
+    assert api.vehicle_type_get_sizes("f1-3dof") == (14, 4, 4) and api.vehicle_type_get_sizes("kart-6dof")[:2] == (13, 2)
+    key, q, u, out = api.vehicle_type_get_names("kart-6dof")
+    assert key == "road.arclength" and len(q) == 13 and len(u) == 2 and "laptime" in out
+    api.print_variable("car")
+    assert "<vehicle type=\"f1-3dof\">" in capsys.readouterr().out
+    api.copy_variable("car", "car2"); api.move_variable("car2", "car3")
+    assert api.variable_type("car3") == "f1-3dof"
+    with pytest.raises(api.FastestLapError):
+        api.download_scalar("car2")
+
+
+def test_track_data():
+    api.delete_variable("*")
+    api._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    api.create_vehicle_empty("car", "f1-3dof")
+    api.vehicle_change_track("car", "catalunya")
+    with pytest.raises(api.FastestLapError):
+        api.vehicle_change_track("car", "monza")
+    L = api.track_download_length("catalunya")
+    assert 4600.0 < L < 4700.0
+    x, y, xl, yl, xr, yr, th = api.track_coordinates("catalunya")
+    nl, nr = api.track_download_data("catalunya", "distance-left-boundary"), api.track_download_data("catalunya", "distance-right-boundary")
+    np.testing.assert_allclose(np.hypot(xl - x, yl - y), nl, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.hypot(xr - x, yr - y), nr, rtol=0, atol=1e-9)
+    # the left boundary is to the left of the direction of travel
+    assert np.all((xl - x) * -np.sin(th) + (yl - y) * np.cos(th) <= 0.0) or np.all((xl - x) * -np.sin(th) + (yl - y) * np.cos(th) >= 0.0)
+    with pytest.raises(api.FastestLapError):
+        api.track_download_data("catalunya", "banking")
