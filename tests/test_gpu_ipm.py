@@ -310,3 +310,28 @@ def test_kart_cold_start_reproduces_the_reference_run(name):
     assert abs(t - float(ex["laptime"])) <= 1e-6 * float(ex["laptime"])
     assert out["iters"][0] < int(ex["iter_count"]) + 15
     solver.close(); nlp.close()
+
+
+def test_cluster_vector_kernels_give_the_same_iterates(monkeypatch):
+    """Long laps run the vector kernels of the iteration on a thread-block cluster per lap (reductions and the leader's
+    decisions through distributed shared memory): a 2000-node F1 lap solved with clusters of 2 and of 4 blocks and with
+    one block (FL_IPM_CLUSTER) takes the same number of iterations to the same lap."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    p = workloads.f1_catalunya(2000)
+    x0 = workloads.f1_start_point(p, 50.0)
+    nlp = CollocationNLP(p)
+    res = {}
+    for c in ("1", "2", "4"):
+        monkeypatch.setenv("FL_IPM_CLUSTER", c)
+        solver = LapSolver(nlp)
+        out = solver.solve(x0)
+        res[c] = (int(out["status"][0]), int(out["iters"][0]), lap_time(p, out["x"][0], out["obj"][0]))
+        solver.close()
+    nlp.close()
+    assert res["1"][0] == 1 and res["2"][0] == 1 and res["4"][0] == 1, res
+    # the reductions are fixed-order trees per block plus a fixed-order sum over the blocks: the grouping differs with the
+    # cluster size, so the iterates agree to rounding, not bitwise
+    assert abs(res["1"][2] - res["2"][2]) <= 1e-8 * res["1"][2] and abs(res["1"][2] - res["4"][2]) <= 1e-8 * res["1"][2], res
+    assert abs(res["1"][1] - res["2"][1]) <= 10 and abs(res["1"][1] - res["4"][1]) <= 10, res
