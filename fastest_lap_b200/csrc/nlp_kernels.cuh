@@ -415,12 +415,16 @@ struct variant_ops
         DVec<G> Dk;
         memcpy(Dk.d, D0, sizeof(Dk.d));
         const dim3 grid((P.n_points + FL_BLOCK - 1) / FL_BLOCK, tape ? G::NP_TAPE : G::NP_VALUES, P.batch);
-        if (tape && G::HAS_TAPE)
+        if constexpr (G::HAS_TAPE != 0)          // (the tape kernels exist only in builds generated with FL_SHARE > 0)
         {
-            if (shared_d) k_node_values<G, true, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
-            else k_node_values<G, false, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+            if (tape)
+            {
+                if (shared_d) k_node_values<G, true, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+                else k_node_values<G, false, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+                return;
+            }
         }
-        else if (shared_d) k_node_values<G, true, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        if (shared_d) k_node_values<G, true, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
         else k_node_values<G, false, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
     }
     static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<dim3((P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK, P.batch, 1), FL_ABLOCK, 0, s>>>(P); }
