@@ -79,39 +79,61 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def host_threads():
+    """Host cores this process may use -- not OMP_NUM_THREADS, which torchrun sets to 1 for every rank."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def headline_config(p, nlp_sizes=None):
+    """The `config` object of the JSON line: the same keys and values in the b200 arm and in the reference arm."""
+    return {"workload": "limebeer-2014-f1 3DOF, Catalunya, closed, direct form, %d trapezoidal nodes, one full callback round per step" % p.n_points,
+            "nodes": p.n_points, "n": p.n, "m": p.m,
+            "point": "golden 500-node solution interpolated to the mesh, lambda ~ N(0,1) seed 1, obj_factor 1"}
+
+
 def cpu_baseline(p, x, lam, budget_s=12.0, threads=0):
     """Times the CPU oracle port on a bounded sample: whole callback rounds of the same lap, about `budget_s` seconds."""
     from tests.helpers import oracle_nlp
-    from oracle import oracle as orc
     o = oracle_nlp(p)
-    cores = int(orc.lib().orc_max_threads()) if threads == 0 else threads
+    cores = host_threads() if threads == 0 else threads
     t1 = o.time_eval(x, lam, 1.0, reps=1, threads=cores)
     reps = max(1, min(200, int(budget_s / max(t1, 1e-6))))
     t = o.time_eval(x, lam, 1.0, reps=reps, threads=cores)
     return {"value": p.n_points / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d full callback rounds (f, g, grad, Jacobian, Hessian) of the %d-node lap, C++ second-order jets, OpenMP over nodes" % (reps, p.n_points)}, t
+            "sample": "%d full callback rounds (f, g, grad, Jacobian, Hessian) of the %d-node lap, C++ second-order jets (-O3), OpenMP over element chunks" % (reps, p.n_points)}, t
 
 
 def run_reference(args):
+    """Reference arm: the CPU statement of the path (oracle port; the reference's own stack -- lion, CppAD, Ipopt, MUMPS -- cannot
+    be built offline) on all host cores, same metric / config; W warm-up and K timed steps as asked.  A step is a full callback
+    round of the 8000-node lap while K rounds fit a couple of minutes, else a round of a shorter closed lap (the per-node work
+    does not depend on the mesh; the sample is named)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    p, x, lam = workload()
+    p, x, lam = workload(args.nodes)
     from tests.helpers import oracle_nlp
-    from oracle import oracle as orc
+    cores = host_threads()
     o = oracle_nlp(p)
-    cores = int(orc.lib().orc_max_threads())
-    for _ in range(min(args.warmup, 2)):
-        o.time_eval(x, lam, 1.0, reps=1, threads=cores)
-    steps = min(args.steps, 50)
-    t = o.time_eval(x, lam, 1.0, reps=steps, threads=cores)
-    v = p.n_points / t
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "limebeer-2014-f1 3DOF, Catalunya, closed, direct form, 8000 trapezoidal nodes, one full callback round per step",
-                       "nodes": p.n_points, "n": p.n, "m": p.m},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d full callback rounds of the %d-node lap on the CPU oracle port (the reference itself cannot be built offline)" % (steps, p.n_points)},
+    t1 = o.time_eval(x, lam, 1.0, reps=1, threads=cores)
+    ps, xs, ls, os_ = p, x, lam, o
+    if t1 * (args.steps + args.warmup) > 150.0:
+        n_s = max(64, int(p.n_points * 150.0 / (t1 * (args.steps + args.warmup))))
+        ps, xs, ls = workload(n_s)
+        os_ = oracle_nlp(ps)
+    for _ in range(args.warmup):
+        os_.time_eval(xs, ls, 1.0, reps=1, threads=cores)
+    t = os_.time_eval(xs, ls, 1.0, reps=args.steps, threads=cores)
+    v = ps.n_points / t
+    sample = "%d full callback rounds of %s on the CPU oracle port, %d threads (the reference itself cannot be built offline)" % (
+        args.steps, "the %d-node lap" % p.n_points if ps is p else "a %d-node closed lap of the same track (bounded sample of the %d-node workload)" % (ps.n_points, p.n_points), cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t * 1e3 * (p.n_points / ps.n_points), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": headline_config(p),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -124,7 +146,7 @@ def batched_leg(args, torch, dist, world, rank, local, peak):
     contiguously over the ranks (no data-path collective; one gather of the objective values at the end).  A step = one
     full callback round of every lap.  The batch's buffers (GBs) exceed the L2 many times over: no flush needed."""
     from fastest_lap_b200 import workloads
-    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, pinned_empty
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, EVAL_NO_VALUES, pinned_empty
     from fastest_lap_b200.problem import LapProblem
     from fastest_lap_b200.sharding import shard_range, gather_results
     from fastest_lap_b200.vehicle import MODEL_F1
@@ -157,9 +179,8 @@ def batched_leg(args, torch, dist, world, rank, local, peak):
     dev_ms = sum(nlp.time_device(EVAL_ALL, 1.0, 1) for _ in range(K))
     barrier()
     launches = nlp.kernel_launches - l0
-    ker_ms = sum(nlp.time_device(EVAL_JAC | EVAL_HESS, 1.0, 1) for _ in range(K))
     val_ms = sum(nlp.time_device(0, 1.0, 1) for _ in range(K))
-    ker_ms -= val_ms
+    ker_ms = sum(nlp.time_device(EVAL_JAC | EVAL_HESS | EVAL_NO_VALUES, 1.0, 1) for _ in range(K))     # the derivative kernel alone, its own duration
     Ke = 2
     nlp.eval_all(hx, hl, 1.0, out=out)
     barrier()
@@ -278,7 +299,7 @@ def kart_leg(args, torch, local):
     """Callback rounds of BASELINE configs[3]: roberto-lot-kart-2016 (6DOF) on Vendrell, 2000 nodes, derivative form, at the
     golden solution interpolated to the mesh; same ring-of-instances hygiene as the headline leg (rank 0 only)."""
     from fastest_lap_b200 import workloads
-    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, time_device_ring
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_NO_VALUES, time_device_ring
     p = workloads.kart_vendrell(2000)
     g = np.load(os.path.join(ROOT, "tests", "golden", "kart_vendrell.npz"))
     x = workloads.resample_point(p, g["s"], g["x"], p.nv)
@@ -294,7 +315,7 @@ def kart_leg(args, torch, local):
     timed(EVAL_ALL, R)
     torch.cuda.synchronize()
     dev_ms = timed(EVAL_ALL, K) / K
-    ker_ms = (timed(EVAL_JAC | EVAL_HESS, K) - timed(0, K)) / K
+    ker_ms = timed(EVAL_JAC | EVAL_HESS | EVAL_NO_VALUES, K) / K          # the derivative kernel alone
     res = {"workload": "roberto-lot-kart-2016 6DOF, Vendrell, closed, derivative form, 2000 trapezoidal nodes, one full callback round per step; ring of %d instances" % R,
            "variant": nlp.variant, "value": p.n_points / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms, "steps": K,
            "kernels_ms": {"node_derivs": ker_ms}, "fp64_ops_per_node_eval": nlp.ops_per_node["all"], "n": nlp.n, "m": nlp.m,
@@ -345,6 +366,8 @@ def main():
     ap.add_argument("--single-laps", type=int, default=1, help="1: also time single-lap solves (500 and --nodes nodes) on rank 0")
     ap.add_argument("--gg-speeds", type=int, default=32, help="speeds of the G-G sweep leg (0 = skip)")
     ap.add_argument("--gg-lat", type=int, default=64)
+    ap.add_argument("--cpu-solver-arms", type=int, default=1, help="1: time the CPU arms of laps/s and NLPs/s (N = 1, rank 0)")
+    ap.add_argument("--cpu-arm-procs", type=int, default=32, help="processes of the CPU solver arms (at most the host cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -359,7 +382,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, pinned_empty, time_device_ring
+    from fastest_lap_b200.nlp import CollocationNLP, EVAL_ALL, EVAL_JAC, EVAL_HESS, EVAL_FG, EVAL_NO_VALUES, pinned_empty, time_device_ring
     p, x, lam = workload(args.nodes)
     # Ring of independent instances of the same lap: consecutive timed steps touch different buffers, and one trip round
     # the ring moves more bytes than the L2 holds, so every step finds its data in HBM (no flush kernel in between).
@@ -393,7 +416,8 @@ def main():
         # sequence (fl_time_device_ring): device time of exactly `count` steps, free of the host's launch latency
         return time_device_ring(ring, what, count)
 
-    # ---- device-resident leg
+    # ---- device-resident leg: blocks of exactly K steps, repeated until at least 50 ms of steps have been timed (a single
+    # block of 20 steps is 0.7 ms: +-5 % run to run); the reported time per step is the mean over all blocks
     timed(EVAL_ALL, max(W, R))
     sampler = ClockSampler(local); sampler.start()
     barrier()
@@ -401,12 +425,26 @@ def main():
     dev_ms = timed(EVAL_ALL, K)
     barrier()
     launches = sum(h.kernel_launches for h in ring) - launches0
-    # dominant kernel alone (grad f + Jacobian + Hessian of every node; needs the checkpoints of the values pass), same hygiene
-    timed(EVAL_JAC | EVAL_HESS, R)
-    ker_ms = timed(EVAL_JAC | EVAL_HESS, K) - 0.0
-    val_ms = timed(0, K)
+    repeats = 1
+    blocks = [dev_ms]
+    while sum(blocks) < 50.0 and repeats < 2000:
+        blocks.append(timed(EVAL_ALL, K))
+        repeats += 1
+    dev_ms = sum(blocks) / repeats
+    barrier()
+    M = max(1, int(np.ceil(50.0 / max(dev_ms, 1e-3))))
+
+    def timed_mean(what):
+        timed(what, R)
+        return sum(timed(what, K) for _ in range(M)) / M
+    # dominant kernel (grad f + Jacobian + Hessian of every node; it needs the checkpoints of the values pass): (a) values +
+    # derivatives minus values alone, as the step runs them (programmatic dependent launch lets the two overlap); (b) the
+    # derivative kernel launched ALONE on the checkpoints left by the last values pass, its own duration between two events
+    ker_ms = timed_mean(EVAL_JAC | EVAL_HESS)
+    val_ms = timed_mean(0)
     ker_ms -= val_ms
-    fg_ms = timed(EVAL_FG, K)
+    ker_alone_ms = timed_mean(EVAL_JAC | EVAL_HESS | EVAL_NO_VALUES)
+    fg_ms = timed_mean(EVAL_FG)
     fp64_peak = nlp.measure_fp64_peak()            # DFMA/s, micro-kernel (no FP64 figure in MEASURED_PEAKS.json)
     # ---- end-to-end leg: host buffers in, host buffers out
     for k in range(3):
@@ -419,12 +457,12 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    t = torch.tensor([dev_ms, e2e_s, ker_ms, fg_ms], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
+    t = torch.tensor([dev_ms, e2e_s, ker_ms, fg_ms, ker_alone_ms], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         fs = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
         dist.all_gather(fs, torch.tensor([float(out["f"][0])], dtype=torch.float64, device="cuda"))     # the final gather of results
-    dev_ms, e2e_s, ker_ms, fg_ms = [float(v) for v in t.tolist()]
+    dev_ms, e2e_s, ker_ms, fg_ms, ker_alone_ms = [float(v) for v in t.tolist()]
 
     if rank == 0:
         nodes = p.n_points * B * world
@@ -441,7 +479,8 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = ker_bytes / (ker_ms / K * 1e-3) / 1e9
+        # the roofline figure uses the kernel's OWN duration (launched alone between two events), not the subtraction
+        achieved = ker_bytes / (ker_alone_ms / K * 1e-3) / 1e9
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_node_derivs<f1_direct, all> @ 8000 nodes"]
@@ -451,22 +490,21 @@ def main():
             pass
         line = {"metric": METRIC, "value": nodes / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "limebeer-2014-f1 3DOF, Catalunya, closed, direct form, %d trapezoidal nodes, one full callback round per step" % p.n_points,
-                           "nodes": p.n_points, "laps_per_gpu": B, "n": nlp.n, "m": nlp.m, "nnz_jac": nlp.nnz_jac, "nnz_hess": nlp.nnz_hess, "variant": v,
-                           "point": "golden 500-node solution interpolated to the mesh, lambda ~ N(0,1) seed 1, obj_factor 1",
-                           "l2": "ring of %d independent instances of the lap (%.0f MB touched per trip > %.0f MB L2), one per timed step in turn" % (R, R * per_instance / 1e6, l2_bytes / 1e6), "parallelism": "1 lap per GPU, replicas"},
+                "config": headline_config(p),
+                "details": {"laps_per_gpu": B, "nnz_jac": nlp.nnz_jac, "nnz_hess": nlp.nnz_hess, "variant": v, "timed_blocks": repeats, "timed_ms": sum(blocks),
+                            "l2": "ring of %d independent instances of the lap (%.0f MB touched per trip > %.0f MB L2), one per timed step in turn" % (R, R * per_instance / 1e6, l2_bytes / 1e6), "parallelism": "1 lap per GPU, replicas"},
                 "e2e": {"value": nodes / (e2e_s / K), "unit": UNIT, "h2d_bytes_per_step": int(B * (nlp.n + nlp.m) * 8),
                         "d2h_bytes_per_step": int(B * (1 + nlp.m + nlp.n + nlp.nnz_jac + nlp.nnz_hess) * 8), "ms_per_step": e2e_s / K * 1e3},
                 "gpu_launches": int(launches),
-                "kernels_ms": {"node_values": val_ms / K, "values+assemble": fg_ms / K, "node_derivs": ker_ms / K},
+                "kernels_ms": {"node_values": val_ms / K, "values+assemble": fg_ms / K, "node_derivs": ker_ms / K, "node_derivs_alone": ker_alone_ms / K},
                 "roofline": {"bound": "hbm", "kernel": "k_node_derivs<%s, all>" % v, "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "algorithmic_bytes_per_launch": ker_bytes, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                              "bytes_per_node_eval": per_node_read + per_node_write, "fp64_ops_per_node_eval": nlp.ops_per_node["all"],
                              "fp64": {"peak_measured_tflops": 2.0 * fp64_peak / 1e12, "peak_unit": "TFLOP/s (2 x DFMA/s, micro-kernel on this GPU)",
-                                      "achieved_gops": nlp.ops_per_node["all"] * p.n_points * B / (ker_ms / K * 1e-3) / 1e9,
-                                      "frac_of_instruction_peak": nlp.ops_per_node["all"] * p.n_points * B / (ker_ms / K * 1e-3) / fp64_peak,
+                                      "achieved_gops": nlp.ops_per_node["all"] * p.n_points * B / (ker_alone_ms / K * 1e-3) / 1e9,
+                                      "frac_of_instruction_peak": nlp.ops_per_node["all"] * p.n_points * B / (ker_alone_ms / K * 1e-3) / fp64_peak,
                                       "note": "operations of the generated code (add/mul/fma each one instruction) per second over the DFMA issue rate"}},
                 "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
@@ -494,6 +532,33 @@ def main():
         if rank == 0:
             line["gg_sweep"] = gl
     if rank == 0:
+        # timed CPU arms of the two solver metrics (rank 0, N = 1 only): P processes x 1 core, bounded samples
+        if not args.no_cpu_baseline and world == 1 and args.cpu_solver_arms:
+            from oracle import cpu_arms
+            P = max(1, min(host_threads(), args.cpu_arm_procs))
+            if args.solve_laps > 0:
+                line["batched_solve"]["cpu_baseline"] = cpu_arms.laps_per_s(ROOT, P)
+            if args.gg_speeds > 0:
+                line["gg_sweep"]["cpu_baseline"] = cpu_arms.nlps_per_s(ROOT, P)
+        # compact summary as the LAST key, so that the tail of the line carries it at every N
+        sc = {"n_gpus": world, "node_evals_per_s": line["value"]}
+        if "batched" in line:
+            sc["batch_node_evals_per_s"] = line["batched"]["value"]; sc["batch_roofline_frac"] = round(line["batched"]["roofline"]["frac"], 4)
+        if "batched_solve" in line:
+            bs = line["batched_solve"]
+            sc.update(laps_per_s=bs["value"], laps=bs["laps"], laps_converged=bs["converged"], laps_seconds=bs["seconds"], laps_scaling="strong",
+                      laps_phase_s_max_over_ranks=bs.get("phases_s"))
+            if "weak" in bs:
+                sc.update(laps_per_s_weak=bs["weak"]["value"], laps_weak=bs["weak"]["laps"])
+            if "cpu_baseline" in bs:
+                sc.update(cpu_laps_per_s=bs["cpu_baseline"]["value"], cpu_cores=bs["cpu_baseline"]["cores"])
+        if "gg_sweep" in line:
+            gs = line["gg_sweep"]
+            sc.update(nlps_per_s=gs["value"], nlps=gs["nlps"], nlps_solved_fraction=min(gs["solved_fraction_max"], gs["solved_fraction_min"]))
+            if "cpu_baseline" in gs:
+                sc.update(cpu_nlps_per_s=gs["cpu_baseline"]["value"])
+        sc["roofline_frac"] = round(line["roofline"]["frac"], 4)
+        line["scale"] = sc
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

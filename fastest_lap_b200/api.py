@@ -270,6 +270,31 @@ def _kart_start_node(vehicle, speed, form):
     return np.array(node)
 
 
+def trajectory(track_nodes, centreline, s, track_length, closed, u, v, n, alpha, t_start=0.0):
+    """Time, lap time, position and heading of a solution, the quantities Optimal_laptime exports besides the NLP variables
+    (optimal_laptime.hpp:598-631): time = trapezoid integral of dt/ds = (1 - n kz) / (u cos(alpha) - v sin(alpha))
+    (road_curvilinear.hpp:9) with kz the z component of the 3-D road-frame curvature, -sin(phi) dmu/ds + cos(mu) cos(phi)
+    dtheta/ds (road_curvilinear.h:49-60; the formula the kernels' per-node constants are built with, csrc/fl_capi.cu);
+    position = centreline + n * normal vector of the pitched and rolled road frame, psi = alpha + theta
+    (road_curvilinear.hpp:17-18, 125-127).  track_nodes: [n][6] theta, mu, phi and their s-derivatives."""
+    nd = np.asarray(track_nodes)
+    theta, mu_t, phi_t = nd[:, 0], nd[:, 1], nd[:, 2]
+    kz = -np.sin(phi_t) * nd[:, 4] + np.cos(mu_t) * np.cos(phi_t) * nd[:, 3]
+    dtds = (1.0 - n * kz) / (u * np.cos(alpha) - v * np.sin(alpha))
+    h = np.diff(np.append(s, track_length)) if closed else np.diff(s)
+    if closed:
+        time = np.concatenate([[0.0], np.cumsum(h[:-1] * 0.5 * (dtds[:-1] + dtds[1:]))])
+        laptime = float(np.sum(h * 0.5 * (dtds + np.roll(dtds, -1))))
+    else:
+        time = t_start + np.concatenate([[0.0], np.cumsum(h * 0.5 * (dtds[:-1] + dtds[1:]))])
+        laptime = float(time[-1])          # the time of the last node (optimal_laptime.hpp:631)
+    normal = np.stack([np.cos(theta) * np.sin(mu_t) * np.sin(phi_t) - np.sin(theta) * np.cos(phi_t),
+                       np.sin(theta) * np.sin(mu_t) * np.sin(phi_t) + np.cos(theta) * np.cos(phi_t),
+                       np.cos(mu_t) * np.sin(phi_t)], axis=1)
+    xyz = np.asarray(centreline) + np.asarray(n)[:, None] * normal
+    return time, laptime, xyz, theta
+
+
 def optimal_laptime(vehicle, track, s, options=""):
     """Computes the optimal lap of `vehicle` on `track` over the mesh `s` and stores the outputs in the table under
     `<prefix>`.  Returns (prefix, variable names), as the reference's Python wrapper does."""
@@ -362,20 +387,10 @@ def optimal_laptime(vehicle, track, s, options=""):
     X = out["x"][0].reshape(-1, p.nv)
     if not closed:
         X = np.vstack([node, X])          # the fixed first node
-    h = np.diff(np.append(s, trk.track_length)) if closed else np.diff(s)
-    # time: trapezoid integral of dt/ds, recovered from the objective's lap-time part through the callbacks' own values is
-    # not exposed; integrate 1 / (ds/dt) with the curvilinear kinematics (road_curvilinear.hpp:9)
     iu, iv = (4, 5) if veh.model == MODEL_F1 else (1, 2)
     n_col, a_col = n_in - 3, n_in - 2          # positions of n and alpha in x (time removed)
-    kz = trk("yaw_dot", s)
-    dtds = (1.0 - X[:, n_col] * kz) / (X[:, iu] * np.cos(X[:, a_col]) - X[:, iv] * np.sin(X[:, a_col]))
-    if closed:
-        time = np.concatenate([[0.0], np.cumsum(h[:-1] * 0.5 * (dtds[:-1] + dtds[1:]))])
-        laptime = float(np.sum(h * 0.5 * (dtds + np.roll(dtds, -1))))
-    else:
-        t_start = float(o["q_start"][n_in - 3])
-        time = t_start + np.concatenate([[0.0], np.cumsum(h * 0.5 * (dtds[:-1] + dtds[1:]))])
-        laptime = float(time[-1])          # the time of the last node (optimal_laptime.hpp:631)
+    t_start = 0.0 if closed else float(o["q_start"][n_in - 3])
+    time, laptime, xyz, yaw = trajectory(trk.node_data(s), trk.position(s), s, trk.track_length, closed, X[:, iu], X[:, iv], X[:, n_col], X[:, a_col], t_start)
     pre = o["prefix"]
     names = []
 
@@ -391,17 +406,15 @@ def optimal_laptime(vehicle, track, s, options=""):
             put(nm, X[:, k].copy()); k += 1
     for c, nm in enumerate(controls):
         put(nm, X[:, k + full_mesh.index(c)].copy() if c in full_mesh else np.full(p.n_points, p.ctrl_default[c]))
-    pos = trk.position(s)
-    yaw = trk("yaw", s)
-    put("x", pos[:, 0] - X[:, n_col] * np.sin(yaw)); put("y", pos[:, 1] + X[:, n_col] * np.cos(yaw)); put("psi", yaw + X[:, a_col])
+    put("x", xyz[:, 0].copy()); put("y", xyz[:, 1].copy()); put("psi", yaw + X[:, a_col])
     put("laptime", laptime)
     put("optimization_data.number_of_iterations", float(out["iters"][0]))
     if o["xml_file"]:
-        _write_solution_xml(o["xml_file"], veh.model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, pos, yaw, n_col, a_col)
+        _write_solution_xml(o["xml_file"], veh.model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, xyz, yaw, n_col, a_col)
     return pre, names
 
 
-def _write_solution_xml(path, model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, pos, yaw, n_col, a_col):
+def _write_solution_xml(path, model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, xyz, yaw, n_col, a_col):
     """The reference's solution file (Optimal_laptime::xml(), optimal_laptime.hpp: mesh, inputs, controls, x, y, psi,
     multipliers), the format solution.solution_from_xml reads back and <warm_start> files use."""
     from .solution import Solution, Control
@@ -417,7 +430,7 @@ def _write_solution_xml(path, model, p, form, closed, s, time, X, out, laptime, 
         else:
             ctl = Control("dont optimize")
         sol.controls.append(ctl)
-    sol.x_coord, sol.y_coord, sol.psi = pos[:, 0] - X[:, n_col] * np.sin(yaw), pos[:, 1] + X[:, n_col] * np.cos(yaw), yaw + X[:, a_col]
+    sol.x_coord, sol.y_coord, sol.psi = xyz[:, 0].copy(), xyz[:, 1].copy(), yaw + X[:, a_col]
     sol.iter_count, sol.zl, sol.zu, sol.lam = int(out["iters"][0]), out["zl"][0], out["zu"][0], out["y"][0]
     sol.n_variables_per_point, sol.n_constraints_per_element = p.nv, p.ncpe
     with open(path, "w") as fh:

@@ -498,8 +498,11 @@ int fl_eval_device_masked(fl_nlp* h, int what, double obj_factor, const int* d_a
     // the values pass also writes the checkpoints every derivative pass loads: it always runs (x may have been rewritten
     // on the device since the last call)
     const int dw = ((what & FL_EVAL_JAC) ? FL_DERIV_JAC : 0) | ((what & FL_EVAL_HESS) ? FL_DERIV_HESS : 0);
-    h->v->launch_values(P, h->D0.data(), h->shared_d, dw == FL_DERIV_ALL, h->stream);
-    h->launches += 1;
+    if (!(what & FL_EVAL_NO_VALUES))
+    {
+        h->v->launch_values(P, h->D0.data(), h->shared_d, dw == FL_DERIV_ALL, h->stream);
+        h->launches += 1;
+    }
     // a full round (f, g, grad f, Jacobian, Hessian) assembles the rows inside the derivative launch
     const int fold = (what & FL_EVAL_FG) && dw == FL_DERIV_ALL;
     if ((what & FL_EVAL_FG) && !fold)

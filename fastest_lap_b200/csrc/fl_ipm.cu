@@ -264,7 +264,8 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     std::vector<double> xl(n), xu(n), gl(m), gu(m);
     if (x_l && x_u && g_l && g_u) { xl.assign(x_l, x_l + n); xu.assign(x_u, x_u + n); gl.assign(g_l, g_l + m); gu.assign(g_u, g_u + m); }
     else if (!fl_nlp_bounds(nlp, xl.data(), xu.data(), gl.data(), gu.data())) { delete s; return nullptr; }
-    auto rel = [&](double b) { return o.bound_relax_factor * std::fmax(1.0, std::fabs(b)); };
+    // Ipopt caps the relaxation at constr_viol_tol (IpTNLPAdapter: bound_relax_factor * max(1, |b|), at most constr_viol_tol)
+    auto rel = [&](double b) { return std::fmin(o.constr_viol_tol, o.bound_relax_factor * std::fmax(1.0, std::fabs(b))); };
     // row classification: the NEXT "extra" rows of every element are the inequalities (optimal_laptime.hpp:447-476)
     std::vector<int> eq_of(NCPE, -1), ineq_of(NCPE, -1), eq_rows, ineq_rows;
     for (int r = 0; r < NCPE; ++r)
@@ -367,12 +368,26 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     s->vec_smem = (size_t)IPM_NCPEMAX * s->vec_block * sizeof(double);
     // long laps, few of them: a cluster of blocks per lap (each block strides over 1 / vec_cluster of the lap's vectors)
     if (const char* e = std::getenv("FL_IPM_CLUSTER")) s->vec_cluster = std::max(1, std::min(8, std::atoi(e)));
-    else while (s->vec_cluster < 8 && (size_t)B * s->vec_cluster * 2 <= 148 && S >= s->vec_cluster * 3 * s->vec_block / 2) s->vec_cluster *= 2;
+    else
     {
+        int n_sm = 0;
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, nlp->device) != cudaSuccess || n_sm <= 0) { fl_set_error("cannot read the SM count of the device"); fl_ipm_destroy(s); return nullptr; }
+        while (s->vec_cluster < 8 && (size_t)B * s->vec_cluster * 2 <= (size_t)n_sm && S >= s->vec_cluster * 3 * s->vec_block / 2) s->vec_cluster *= 2;
+    }
+    {
+        // The attribute is per device and process-wide: it is set to the largest request any solver can make (never to this
+        // solver's own size, which would lower the limit under a live solver created for a smaller batch).
         const void* kernels[] = { (const void*)k_ipm_init, (const void*)k_ipm_init_slacks, (const void*)k_ipm_take_multipliers, (const void*)k_ipm_state,
                                   (const void*)k_ipm_rhs, (const void*)k_ipm_residual, (const void*)k_ipm_axpy_sol, (const void*)k_ipm_direction,
                                   (const void*)k_ipm_soc_direction, (const void*)k_ipm_line_search, (const void*)k_ipm_init_warm, (const void*)k_ipm_init_slacks_warm };
-        for (const void* kf : kernels) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->vec_smem);
+        const int smem_max = (int)((size_t)IPM_NCPEMAX * IPM_BLOCK_MAX * sizeof(double));
+        for (const void* kf : kernels)
+            if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess)
+            {
+                fl_set_error(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: ") + cudaGetErrorString(cudaGetLastError()));
+                fl_ipm_destroy(s);
+                return nullptr;
+            }
     }
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
     if (P.closed && S == 2) { fl_set_error("closed laps need at least three nodes"); fl_ipm_destroy(s); return nullptr; }
@@ -452,6 +467,9 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
     cudaStream_t st = nlp->stream;
     const int ALL = FL_EVAL_FG | FL_EVAL_JAC | FL_EVAL_HESS;
     int cnt[4];
+    // counters of THIS solve (fl_ipm_stats)
+    s->launches = 0; s->n_factor_launches = 0; s->n_solve_launches = 0; s->n_eval_full = 0; s->n_eval_fg = 0; s->n_rounds = 0; s->n_part_factor = 0;
+    s->ms_factor = s->ms_solve = s->ms_eval = 0.0;
     cudaEventRecord(s->ev0, st);
     FLI_CUDA(cudaMemcpyAsync(nlp->d_xuser, x0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
     if (y0)

@@ -17,6 +17,7 @@ _lib = None
 
 EVAL_FG, EVAL_JAC, EVAL_HESS = 1, 2, 4
 EVAL_ALL = 7
+EVAL_NO_VALUES = 8     # measurement only: the derivative kernel alone, on the checkpoints of the previous call
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -116,7 +116,8 @@ int fl_eval_all(fl_nlp* nlp, const double* x, const double* lambda, double obj_f
 
 /* Device-resident path (what an on-device interior-point loop uses): pointers are device pointers on the handle's
  * device and stay owned by the handle; inputs are read from fl_dev_x / fl_dev_lambda.  `what` is a bit mask. */
-enum { FL_EVAL_FG = 1, FL_EVAL_JAC = 2, FL_EVAL_HESS = 4 };
+enum { FL_EVAL_FG = 1, FL_EVAL_JAC = 2, FL_EVAL_HESS = 4,
+       FL_EVAL_NO_VALUES = 8 };  /* measurement only: skip the values pass and run the derivative kernel alone on the checkpoints the previous call left */
 double* fl_dev_x(fl_nlp* nlp);          /* [batch][n] */
 double* fl_dev_lambda(fl_nlp* nlp);     /* [batch][m] */
 const double* fl_dev_f(fl_nlp* nlp);    /* [batch]    */

@@ -10,6 +10,7 @@
 #define ORACLE_NLP_HPP
 
 #include <vector>
+#include <omp.h>
 #include <cstring>
 #include "jet.hpp"
 #include "f1_model.hpp"
@@ -203,162 +204,228 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
     const int np = d.n_points;
     const bool deriv = d.form == FORM_DERIVATIVE;
     const double sigma = d.sigma;
-    std::vector<NodeRows<NV>> R(np);
-
     auto var0 = [&](int node) { return d.closed ? node * NV : (node - 1) * NV; };     // -NV for the fixed node of open problems
-    #pragma omp parallel for schedule(static)
-    for (int i = 0; i < np; ++i)
-    {
+    // node rows are evaluated where the assembly needs them (one pass over the lap per thread chunk, two live nodes per
+    // thread), not stored for the whole lap: a lap of 8000 nodes would be 435 MB of second-order jets
+    auto node_rows = [&](int i, NodeRows<NV>& Rn) {
         const double* xn = (d.closed || i > 0) ? x + var0(i) : nullptr;
-        eval_node<NV>(d, L, i, xn, R[i]);
-    }
+        eval_node<NV>(d, L, i, xn, Rn);
+    };
+    // derivative form: the control rates of nodes 0 and n-1 enter the penalty of every element (reference quirk, see below)
+    std::vector<NodeRows<NV>> Rends(deriv ? 2 : 0);
+    if (deriv) { node_rows(0, Rends[0]); node_rows(np - 1, Rends[1]); }
 
     out.f = 0.0;
     out.g.assign(L.m, 0.0);
     out.grad.assign(L.n, 0.0);
     out.jac = Triplets();
     out.hess = Triplets();
-    // per-node Hessian accumulators (lower triangle)
+
+    // Element assembly: the elements are cut into contiguous chunks, one per thread.  Every chunk accumulates the gradient and
+    // the per-node Hessian blocks of ITS nodes (first left node .. last right node) in private arrays and emits its triplets
+    // into private lists; the chunks are then joined in element order, so the result does not depend on the thread count
+    // except for the order of the two additions at a node shared by two chunks.
+    struct Chunk
+    {
+        int e0 = 0, e1 = 0;
+        double f = 0.0;
+        std::vector<double> grad, H;     // [(e1 - e0 + 1) nodes][NV], [..][NV*NV]
+        Triplets jac, hess;
+    };
+    int n_chunks = 1;
+    #pragma omp parallel
+    {
+        #pragma omp single
+        n_chunks = omp_get_num_threads();
+    }
+    if (n_chunks > L.n_elements) n_chunks = L.n_elements > 0 ? L.n_elements : 1;
+    std::vector<Chunk> chunks(n_chunks);
+
+    #pragma omp parallel for schedule(static, 1)
+    for (int ck = 0; ck < n_chunks; ++ck)
+    {
+        Chunk& C = chunks[ck];
+        C.e0 = (int)((long)L.n_elements * ck / n_chunks);
+        C.e1 = (int)((long)L.n_elements * (ck + 1) / n_chunks);
+        const int nn = C.e1 - C.e0 + 1;
+        if (want_derivs) { C.grad.assign((size_t)nn * NV, 0.0); C.H.assign((size_t)nn * NV * NV, 0.0); }
+        // local slot of a node of this chunk: left node of element e is slot e - e0, right node slot e - e0 + 1
+        auto add_grad = [&](int slot, int node, const J& a, double c) {
+            if (!want_derivs) return;
+            if (!d.closed && node == 0) return;
+            double* gr = C.grad.data() + (size_t)slot * NV;
+            for (int k = 0; k < NV; ++k) gr[k] += c * a.g[k];
+        };
+        auto add_hess = [&](int slot, int node, const J& a, double c) {
+            if (!want_derivs) return;
+            if (!d.closed && node == 0) return;
+            double* Hn = C.H.data() + (size_t)slot * NV * NV;
+            for (int r = 0; r < NV; ++r) for (int cc = 0; cc <= r; ++cc) Hn[r * NV + cc] += c * a.h[r][cc];
+        };
+        auto add_jac = [&](int row, int node, const J& a, double c) {
+            if (!want_derivs) return;
+            if (!d.closed && node == 0) return;
+            const int c0 = var0(node);
+            for (int k = 0; k < NV; ++k) C.jac.add(row, c0 + k, c * a.g[k]);
+        };
+
+        std::vector<NodeRows<NV>> pair(2);
+        int cur = 0;
+        if (C.e1 > C.e0) node_rows(C.e0, pair[0]);         // (element e starts at node e)
+        for (int e = C.e0; e < C.e1; ++e, cur ^= 1)
+        {
+            // element e joins node i -> j ; the closing element of a closed lap joins n-1 -> 0 with h = L - s.back()
+            const bool closing = d.closed && e == np - 1;
+            const int i = closing ? np - 1 : e;
+            const int j = closing ? 0 : e + 1;
+            const int si = e - C.e0, sj = si + 1;
+            const double h = closing ? d.track_length - d.s[np - 1] : d.s[j] - d.s[i];
+            node_rows(j, pair[cur ^ 1]);
+            const NodeRows<NV>& A = pair[cur];
+            const NodeRows<NV>& B = pair[cur ^ 1];
+            int row = e * L.ncpe;
+
+            // objective: integral of time (optimal_laptime.hpp:1333, 1378)
+            C.f += h * ((1.0 - sigma) * A.dtds.v + sigma * B.dtds.v);
+            add_grad(si, i, A.dtds, h * (1.0 - sigma));
+            add_grad(sj, j, B.dtds, h * sigma);
+            add_hess(si, i, A.dtds, obj_factor * h * (1.0 - sigma));
+            add_hess(sj, j, B.dtds, obj_factor * h * sigma);
+
+            // control penalisation
+            for (int c = 0; c < L.n_fm; ++c)
+            {
+                const double diss = d.dissipation[c];
+                if (!deriv)
+                {
+                    // optimal_laptime.hpp:1362-1366, 1401-1402
+                    const double du = B.ctrl[c].v - A.ctrl[c].v;
+                    const double derivative = du / h;
+                    C.f += diss * (derivative * derivative) * h;
+                    if (want_derivs)
+                    {
+                        const int pi = var0(i) + L.ctrl_pos[c], pj = var0(j) + L.ctrl_pos[c];
+                        const bool vi = d.closed || i > 0;
+                        if (vi) C.grad[(size_t)si * NV + L.ctrl_pos[c]] += -2.0 * diss * du / h;
+                        C.grad[(size_t)sj * NV + L.ctrl_pos[c]] += 2.0 * diss * du / h;
+                        const double hv = obj_factor * 2.0 * diss / h;
+                        if (vi) C.hess.add(pi, pi, hv);
+                        C.hess.add(pj, pj, hv);
+                        if (vi) C.hess.add(pi > pj ? pi : pj, pi > pj ? pj : pi, -hv);
+                    }
+                }
+                else
+                {
+                    // optimal_laptime.hpp:1553 (note the reference's dcontrols_dt[i-i] = dcontrols_dt[0]) and :1611
+                    const int il = closing ? np - 1 : 0;
+                    const J& dl = Rends[closing ? 1 : 0].dctrl[c];
+                    const J& dr = B.dctrl[c];
+                    C.f += 0.5 * diss * (dl.v * dl.v + dr.v * dr.v) * h;
+                    if (want_derivs)
+                    {
+                        // node `il` may lie outside this chunk: its gradient entry and Hessian diagonal go out as triplets
+                        const int pl = var0(il) + L.dctrl_pos[c], pr = var0(j) + L.dctrl_pos[c];
+                        const bool vl = d.closed || il > 0;
+                        if (vl) { C.hess.add(pl, pl, obj_factor * diss * h); C.hess.add(-1 - pl, 0, diss * dl.v * h); }
+                        C.grad[(size_t)sj * NV + L.dctrl_pos[c]] += diss * dr.v * h;
+                        C.hess.add(pr, pr, obj_factor * diss * h);
+                    }
+                }
+            }
+
+            // trapezoidal rows (optimal_laptime.hpp:1337-1338, 1383-1384)
+            for (int r = 0; r < L.n_td; ++r, ++row)
+            {
+                out.g[row] = B.q[r].v - A.q[r].v - h * ((1.0 - sigma) * A.qd[r].v + sigma * B.qd[r].v);
+                const double lam = lambda ? lambda[row] : 0.0;
+                add_jac(row, i, A.q[r], -1.0);  add_jac(row, i, A.qd[r], -h * (1.0 - sigma));
+                add_jac(row, j, B.q[r], 1.0);   add_jac(row, j, B.qd[r], -h * sigma);
+                add_hess(si, i, A.q[r], -lam);      add_hess(si, i, A.qd[r], -lam * h * (1.0 - sigma));
+                add_hess(sj, j, B.q[r], lam);       add_hess(sj, j, B.qd[r], -lam * h * sigma);
+            }
+            // algebraic rows (optimal_laptime.hpp:1340-1341, 1386-1387)
+            for (int r = 0; r < L.n_alg; ++r, ++row)
+            {
+                out.g[row] = B.alg[r].v;
+                const double lam = lambda ? lambda[row] : 0.0;
+                add_jac(row, j, B.alg[r], 1.0);
+                add_hess(sj, j, B.alg[r], lam);
+            }
+            // extra constraints (optimal_laptime.hpp:1344-1347, 1390-1394)
+            for (int r = 0; r < L.n_ext; ++r, ++row)
+            {
+                out.g[row] = B.ext[r].v;
+                const double lam = lambda ? lambda[row] : 0.0;
+                add_jac(row, j, B.ext[r], 1.0);
+                add_hess(sj, j, B.ext[r], lam);
+            }
+            // derivative form: control rate rows (optimal_laptime.hpp:1573-1583, 1632-1641)
+            for (int c = 0; c < L.n_ctrl_rows; ++c, ++row)
+            {
+                out.g[row] = B.ctrl[c].v - A.ctrl[c].v - h * ((1.0 - sigma) * A.cdot[c].v + sigma * B.cdot[c].v);
+                const double lam = lambda ? lambda[row] : 0.0;
+                add_jac(row, i, A.ctrl[c], -1.0); add_jac(row, i, A.cdot[c], -h * (1.0 - sigma));
+                add_jac(row, j, B.ctrl[c], 1.0);  add_jac(row, j, B.cdot[c], -h * sigma);
+                add_hess(si, i, A.cdot[c], -lam * h * (1.0 - sigma));
+                add_hess(sj, j, B.cdot[c], -lam * h * sigma);
+            }
+        }
+
+        if (want_derivs)
+        {
+            // merge the duplicate jacobian triplets (q and qd contributions of the same (row, col))
+            Triplets merged;
+            const size_t nt = C.jac.val.size();
+            size_t k = 0;
+            while (k < nt)
+            {
+                // contributions of one (row, node) come in runs of NV, possibly two consecutive runs for the same node
+                if (k + 2 * NV <= nt && C.jac.row[k] == C.jac.row[k + NV] && C.jac.col[k] == C.jac.col[k + NV])
+                {
+                    for (int q = 0; q < NV; ++q) merged.add(C.jac.row[k + q], C.jac.col[k + q], C.jac.val[k + q] + C.jac.val[k + NV + q]);
+                    k += 2 * NV;
+                }
+                else
+                {
+                    for (int q = 0; q < NV; ++q) merged.add(C.jac.row[k + q], C.jac.col[k + q], C.jac.val[k + q]);
+                    k += NV;
+                }
+            }
+            C.jac = merged;
+        }
+    }
+
+    // join the chunks in element order
     std::vector<double> H;
     if (want_derivs) H.assign((size_t)np * NV * NV, 0.0);
-
-    auto add_grad = [&](int node, const J& a, double c) {
-        if (!want_derivs) return;
-        if (!d.closed && node == 0) return;
-        double* gr = out.grad.data() + var0(node);
-        for (int k = 0; k < NV; ++k) gr[k] += c * a.g[k];
-    };
-    auto add_hess = [&](int node, const J& a, double c) {
-        if (!want_derivs) return;
-        if (!d.closed && node == 0) return;
-        double* Hn = H.data() + (size_t)node * NV * NV;
-        for (int r = 0; r < NV; ++r) for (int cc = 0; cc <= r; ++cc) Hn[r * NV + cc] += c * a.h[r][cc];
-    };
-    auto add_jac = [&](int row, int node, const J& a, double c) {
-        if (!want_derivs) return;
-        if (!d.closed && node == 0) return;
-        const int c0 = var0(node);
-        for (int k = 0; k < NV; ++k) out.jac.add(row, c0 + k, c * a.g[k]);
-    };
-
-    for (int e = 0; e < L.n_elements; ++e)
+    for (int ck = 0; ck < n_chunks; ++ck)
     {
-        // element e joins node i -> j ; the closing element of a closed lap joins n-1 -> 0 with h = L - s.back()
-        const bool closing = d.closed && e == np - 1;
-        const int i = closing ? np - 1 : e;
-        const int j = closing ? 0 : e + 1;
-        const double h = closing ? d.track_length - d.s[np - 1] : d.s[j] - d.s[i];
-        const NodeRows<NV>& A = R[i];
-        const NodeRows<NV>& B = R[j];
-        int row = e * L.ncpe;
-
-        // objective: integral of time (optimal_laptime.hpp:1333, 1378)
-        out.f += h * ((1.0 - sigma) * A.dtds.v + sigma * B.dtds.v);
-        add_grad(i, A.dtds, h * (1.0 - sigma));
-        add_grad(j, B.dtds, h * sigma);
-        add_hess(i, A.dtds, obj_factor * h * (1.0 - sigma));
-        add_hess(j, B.dtds, obj_factor * h * sigma);
-
-        // control penalisation
-        for (int c = 0; c < L.n_fm; ++c)
+        const Chunk& C = chunks[ck];
+        out.f += C.f;
+        if (!want_derivs) continue;
+        for (int slot = 0; slot <= C.e1 - C.e0 && C.e1 > C.e0; ++slot)
         {
-            const double diss = d.dissipation[c];
-            if (!deriv)
-            {
-                // optimal_laptime.hpp:1362-1366, 1401-1402
-                const double du = B.ctrl[c].v - A.ctrl[c].v;
-                const double derivative = du / h;
-                out.f += diss * (derivative * derivative) * h;
-                if (want_derivs)
-                {
-                    const int pi = var0(i) + L.ctrl_pos[c], pj = var0(j) + L.ctrl_pos[c];
-                    const bool vi = d.closed || i > 0;
-                    if (vi) out.grad[pi] += -2.0 * diss * du / h;
-                    out.grad[pj] += 2.0 * diss * du / h;
-                    const double hv = obj_factor * 2.0 * diss / h;
-                    if (vi) out.hess.add(pi, pi, hv);
-                    out.hess.add(pj, pj, hv);
-                    if (vi) out.hess.add(pi > pj ? pi : pj, pi > pj ? pj : pi, -hv);
-                }
-            }
-            else
-            {
-                // optimal_laptime.hpp:1553 (note the reference's dcontrols_dt[i-i] = dcontrols_dt[0]) and :1611
-                const int il = closing ? np - 1 : 0;
-                const J& dl = R[il].dctrl[c];
-                const J& dr = B.dctrl[c];
-                out.f += 0.5 * diss * (dl.v * dl.v + dr.v * dr.v) * h;
-                if (want_derivs)
-                {
-                    const int pl = var0(il) + L.dctrl_pos[c], pr = var0(j) + L.dctrl_pos[c];
-                    const bool vl = d.closed || il > 0;
-                    if (vl) { out.grad[pl] += diss * dl.v * h; out.hess.add(pl, pl, obj_factor * diss * h); }
-                    out.grad[pr] += diss * dr.v * h;
-                    out.hess.add(pr, pr, obj_factor * diss * h);
-                }
-            }
+            int node = C.e0 + slot;
+            if (node >= np) node -= np;                       // right node of the closing element
+            if (!d.closed && node == 0) continue;
+            double* gr = out.grad.data() + var0(node);
+            for (int k = 0; k < NV; ++k) gr[k] += C.grad[(size_t)slot * NV + k];
+            double* Hn = H.data() + (size_t)node * NV * NV;
+            const double* Hc = C.H.data() + (size_t)slot * NV * NV;
+            for (int k = 0; k < NV * NV; ++k) Hn[k] += Hc[k];
         }
-
-        // trapezoidal rows (optimal_laptime.hpp:1337-1338, 1383-1384)
-        for (int r = 0; r < L.n_td; ++r, ++row)
+        out.jac.row.insert(out.jac.row.end(), C.jac.row.begin(), C.jac.row.end());
+        out.jac.col.insert(out.jac.col.end(), C.jac.col.begin(), C.jac.col.end());
+        out.jac.val.insert(out.jac.val.end(), C.jac.val.begin(), C.jac.val.end());
+        for (size_t k = 0; k < C.hess.val.size(); ++k)
         {
-            out.g[row] = B.q[r].v - A.q[r].v - h * ((1.0 - sigma) * A.qd[r].v + sigma * B.qd[r].v);
-            const double lam = lambda ? lambda[row] : 0.0;
-            add_jac(row, i, A.q[r], -1.0);  add_jac(row, i, A.qd[r], -h * (1.0 - sigma));
-            add_jac(row, j, B.q[r], 1.0);   add_jac(row, j, B.qd[r], -h * sigma);
-            add_hess(i, A.q[r], -lam);      add_hess(i, A.qd[r], -lam * h * (1.0 - sigma));
-            add_hess(j, B.q[r], lam);       add_hess(j, B.qd[r], -lam * h * sigma);
-        }
-        // algebraic rows (optimal_laptime.hpp:1340-1341, 1386-1387)
-        for (int r = 0; r < L.n_alg; ++r, ++row)
-        {
-            out.g[row] = B.alg[r].v;
-            const double lam = lambda ? lambda[row] : 0.0;
-            add_jac(row, j, B.alg[r], 1.0);
-            add_hess(j, B.alg[r], lam);
-        }
-        // extra constraints (optimal_laptime.hpp:1344-1347, 1390-1394)
-        for (int r = 0; r < L.n_ext; ++r, ++row)
-        {
-            out.g[row] = B.ext[r].v;
-            const double lam = lambda ? lambda[row] : 0.0;
-            add_jac(row, j, B.ext[r], 1.0);
-            add_hess(j, B.ext[r], lam);
-        }
-        // derivative form: control rate rows (optimal_laptime.hpp:1573-1583, 1632-1641)
-        for (int c = 0; c < L.n_ctrl_rows; ++c, ++row)
-        {
-            out.g[row] = B.ctrl[c].v - A.ctrl[c].v - h * ((1.0 - sigma) * A.cdot[c].v + sigma * B.cdot[c].v);
-            const double lam = lambda ? lambda[row] : 0.0;
-            add_jac(row, i, A.ctrl[c], -1.0); add_jac(row, i, A.cdot[c], -h * (1.0 - sigma));
-            add_jac(row, j, B.ctrl[c], 1.0);  add_jac(row, j, B.cdot[c], -h * sigma);
-            add_hess(i, A.cdot[c], -lam * h * (1.0 - sigma));
-            add_hess(j, B.cdot[c], -lam * h * sigma);
+            if (C.hess.row[k] < 0) out.grad[-1 - C.hess.row[k]] += C.hess.val[k];      // gradient entry of a node outside the chunk
+            else out.hess.add(C.hess.row[k], C.hess.col[k], C.hess.val[k]);
         }
     }
 
     if (want_derivs)
     {
-        // merge the duplicate jacobian triplets (q and qd contributions of the same (row, col))
-        Triplets merged;
-        const size_t nt = out.jac.val.size();
-        size_t k = 0;
-        while (k < nt)
-        {
-            // contributions of one (row, node) come in runs of NV, possibly two consecutive runs for the same node
-            if (k + 2 * NV <= nt && out.jac.row[k] == out.jac.row[k + NV] && out.jac.col[k] == out.jac.col[k + NV])
-            {
-                for (int q = 0; q < NV; ++q) merged.add(out.jac.row[k + q], out.jac.col[k + q], out.jac.val[k + q] + out.jac.val[k + NV + q]);
-                k += 2 * NV;
-            }
-            else
-            {
-                for (int q = 0; q < NV; ++q) merged.add(out.jac.row[k + q], out.jac.col[k + q], out.jac.val[k + q]);
-                k += NV;
-            }
-        }
-        out.jac = merged;
-
         for (int node = 0; node < np; ++node)
         {
             if (!d.closed && node == 0) continue;

@@ -27,8 +27,10 @@ class _Desc(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    if force or not os.path.exists(so):
-        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    # make decides by the sources' time stamps; a prebuilt library without a compiler at hand is used as it is
+    r = subprocess.run(["make"] + (["-B"] if force else []) + ["-C", _HERE, "liboracle.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0 and not os.path.exists(so):
+        raise RuntimeError("building the CPU oracle failed:\n" + r.stdout[-2000:])
     return so
 
 

@@ -49,6 +49,14 @@ def golden_case(name, vehicle, track, sol, dissipation, **kw):
     print(name, "n =", p.n, "m =", p.m, "laptime", sol.laptime)
 
 
+def trajectory_case(name, track, sol):
+    """x, y, psi and time the reference stored with a solution on a 3-D track, next to the centreline the track gives at
+    the mesh nodes: pins api.trajectory (position = centreline + n * normal vector, road_curvilinear.hpp:17-18)."""
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), s=sol.s, track_nodes=track.node_data(sol.s), centreline=track.position(sol.s),
+                        track_length=track.track_length, inputs=sol.inputs, x_coord=sol.x_coord, y_coord=sol.y_coord, psi=sol.psi, laptime=sol.laptime)
+    print(name, "points", len(sol.s))
+
+
 def main():
     f1 = vehicle_from_xml(REF + "database/vehicles/f1/limebeer-2014-f1.xml")
     kart = vehicle_from_xml(REF + "database/vehicles/kart/roberto-lot-kart-2016.xml")
@@ -107,6 +115,8 @@ def main():
     # optimum is 0.56 s faster, 58.7284 s; without them the stored 59.287501 s is reproduced to 4e-10 from a cold start)
     for nm, trk in (("f1_catalunya_2022_3d", "catalunya_2022/catalunya_2022_3d.xml"), ("f1_laguna_seca_3d", "laguna_seca/laguna_seca_3d.xml")):
         golden_case(nm, f1, track_from_xml(REF + "database/tracks/" + trk, use_kerbs=False), solution_from_xml(DATA + "f1_optimal_laptime_%s.xml" % nm[3:], MODEL_F1), (50.0, 50.0 * 8.0e-4))
+
+    trajectory_case("f1_catalunya_3d_trajectory", catalunya_3d, solution_from_xml(DATA + "f1_optimal_laptime_catalunya_3d.xml", MODEL_F1))
 
     # input data of the benchmark configurations: tracks and vehicle parameter vectors
     data_dir = os.path.join(HERE, "..", "..", "fastest_lap_b200", "data")

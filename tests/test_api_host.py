@@ -53,3 +53,18 @@ def test_track_data():
     assert np.all((xl - x) * -np.sin(th) + (yl - y) * np.cos(th) <= 0.0) or np.all((xl - x) * -np.sin(th) + (yl - y) * np.cos(th) >= 0.0)
     with pytest.raises(api.FastestLapError):
         api.track_download_data("catalunya", "banking")
+
+
+def test_trajectory_on_a_track_with_elevation():
+    """Time, x, y and psi exported with a solution (optimal_laptime.hpp:598-631) on Catalunya 3-D: the reference's stored
+    trajectory (f1_optimal_laptime_catalunya_3d.xml, fixture by tests/golden/make_golden.py::trajectory_case) is reproduced
+    from its stored states -- the flat-track formulas are 8 cm off in x, y on this track."""
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "f1_catalunya_3d_trajectory.npz"))
+    q = d["inputs"]
+    time, laptime, xyz, theta = api.trajectory(d["track_nodes"], d["centreline"], d["s"], float(d["track_length"]), True, q[:, 4], q[:, 5], q[:, 12], q[:, 13])
+    assert abs(laptime - float(d["laptime"])) <= 1e-6
+    assert np.max(np.abs(time - q[:, 11])) <= 1e-9
+    assert np.max(np.abs(xyz[:, 0] - d["x_coord"])) <= 1e-9 and np.max(np.abs(xyz[:, 1] - d["y_coord"])) <= 1e-9
+    assert np.max(np.abs(theta + q[:, 13] - d["psi"])) <= 1e-12
+    yaw = d["track_nodes"][:, 0]
+    assert np.max(np.abs(d["centreline"][:, 0] - q[:, 12] * np.sin(yaw) - d["x_coord"])) > 1e-2

@@ -5,7 +5,7 @@ import pytest
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from tests.helpers import load_golden, oracle_nlp, equality_rows
+from tests.helpers import load_golden, oracle_nlp, equality_rows, state_control_deviation
 
 pytestmark = pytest.mark.gpu
 
@@ -90,7 +90,7 @@ def test_partitioned_schedule_converges_to_the_same_lap():
 
 def test_warm_started_lap_converges_to_the_reference_solution():
     """F1, Catalunya, 500 nodes: from the golden solution perturbed by 1 % the solver returns to the reference's converged
-    lap (f1_optimal_laptime_catalunya_discrete.xml): lap time within 1e-6 relative, controls and states within 1e-5."""
+    lap (f1_optimal_laptime_catalunya_discrete.xml): lap time within 1e-6 relative, controls and states within 1e-6 relative."""
     from fastest_lap_b200.nlp import CollocationNLP
     from fastest_lap_b200.ipm import LapSolver, lap_time
     p, ex = load_golden("f1_catalunya_discrete")
@@ -102,7 +102,9 @@ def test_warm_started_lap_converges_to_the_reference_solution():
     assert out["status"][0] == 1, out["status"]
     t = lap_time(p, out["x"][0], out["obj"][0])
     assert abs(t - float(ex["laptime"])) <= 1e-6 * float(ex["laptime"])
-    assert np.max(np.abs(out["x"][0] - ex["x"])) <= 1e-5
+    dev = state_control_deviation(out["x"][0], ex["x"])
+    print("states / controls vs the reference's stored lap: %.2e" % dev)
+    assert dev <= 1e-6
     assert out["constr_viol"][0] <= 1e-10
     solver.close(); nlp.close()
 
@@ -159,7 +161,9 @@ def test_open_section_returns_to_the_reference_solution():
     out = solver.solve(x0)
     assert out["status"][0] == 1, out["status"]
     assert abs(out["obj"][0] - f_gold) <= 1e-8 * abs(f_gold)
-    assert np.max(np.abs(out["x"][0] - ex["x"])) <= 1e-5
+    dev = state_control_deviation(out["x"][0], ex["x"])
+    print("states / controls vs the reference's stored section: %.2e" % dev)
+    assert dev <= 1e-6
     solver.close(); nlp.close()
 
 
@@ -221,7 +225,7 @@ def test_warm_start_from_the_reference_multipliers():
     assert warm["iters"][0] <= 15 and warm["iters"][0] < cold["iters"][0]          # the push of 1e-3 off the active bounds costs a few
     t = lap_time(p, warm["x"][0], warm["obj"][0])
     assert abs(t - float(ex["laptime"])) <= 1e-7 * float(ex["laptime"])
-    assert np.max(np.abs(warm["x"][0] - ex["x"])) <= 1e-5
+    assert state_control_deviation(warm["x"][0], ex["x"]) <= 1e-6
     # the reference's multipliers are ours up to its convergence tolerance (same sign convention as Ipopt)
     assert np.max(np.abs(warm["y"][0] - ex["lam"])) <= 1e-3 * max(1.0, np.max(np.abs(ex["lam"])))
     again = solver.solve(warm["x"][0], warm=(warm["y"][0], warm["zl"][0], warm["zu"][0]), warm_mu=1e-8)
@@ -240,7 +244,7 @@ def test_oval_track_laps_return_to_the_reference_solutions():
     from fastest_lap_b200.nlp import CollocationNLP, problem_bounds
     from fastest_lap_b200.ipm import LapSolver, lap_time
     rng = np.random.default_rng(0)
-    for name, rel, tol_x in (("f1_ovaltrack_closed", 1.0e-2, 1e-5), ("kart_ovaltrack_derivative", 1.0e-3, 1e-4)):
+    for name, rel, tol_x in (("f1_ovaltrack_closed", 1.0e-2, 1e-6), ("kart_ovaltrack_derivative", 1.0e-3, 1e-6)):
         p, ex = load_golden(name)
         nlp = CollocationNLP(p)
         bounds = None
@@ -255,7 +259,9 @@ def test_oval_track_laps_return_to_the_reference_solutions():
         assert out["status"][0] == 1, (name, out["status"])
         assert abs(out["obj"][0] - f_gold) <= 1e-7 * abs(f_gold), name
         assert abs(lap_time(p, out["x"][0], out["obj"][0]) - float(ex["laptime"])) <= 2e-6 * float(ex["laptime"]), name
-        assert np.max(np.abs(out["x"][0] - ex["x"])) <= tol_x * max(1.0, np.max(np.abs(ex["x"]))), name
+        dev = state_control_deviation(out["x"][0], ex["x"])
+        print("%s: states / controls vs the reference's stored lap: %.2e" % (name, dev))
+        assert dev <= tol_x, name
         solver.close(); nlp.close()
 
 
@@ -264,7 +270,7 @@ def test_cold_start_reproduces_the_reference_run(name):
     """The reference's own runs, end to end: from its starting point (steady state at 50 km/h replicated over the mesh,
     computed here by the GPU steady-state solver for the case's vehicle) the device solver arrives at the solution stored in
     the reference's golden file -- lap time within 1e-6 relative (`north_star`; measured 4e-10 ... 2e-8), states and
-    controls within 1e-5 -- and, as the reference's tests ask of Ipopt (`iter_count < saved + 5`), in no more iterations
+    controls within 1e-6 relative -- and, as the reference's tests ask of Ipopt (`iter_count < saved + 5`), in no more iterations
     than the stored run plus 5 (39 vs 39, 96 vs 92, 46 vs 44, 94 vs 174, 101 vs 113, 51 vs 55)."""
     from fastest_lap_b200 import workloads
     from fastest_lap_b200.nlp import CollocationNLP
@@ -276,7 +282,9 @@ def test_cold_start_reproduces_the_reference_run(name):
     assert out["status"][0] == 1, out["status"]
     t = lap_time(p, out["x"][0], out["obj"][0])
     assert abs(t - float(ex["laptime"])) <= 1e-6 * float(ex["laptime"])
-    assert np.max(np.abs(out["x"][0] - ex["x"])) <= 1e-5
+    dev = state_control_deviation(out["x"][0], ex["x"])
+    print("%s: %d iterations (stored run %d), lap time %.9f (stored %.6f), states / controls %.2e" % (name, out["iters"][0], int(ex["iter_count"]), t, float(ex["laptime"]), dev))
+    assert dev <= 1e-6
     assert out["iters"][0] < int(ex["iter_count"]) + 5, (out["iters"][0], int(ex["iter_count"]))
     solver.close(); nlp.close()
 
