@@ -134,6 +134,10 @@ void fl_nlp_destroy(fl_nlp* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    {
+        const std::vector<fl_ipm*> deps = h->dependents;
+        for (fl_ipm* s : deps) fl_ipm_orphan(s);
+    }
     double* bufs[] = { h->d_xfull, h->P.node0 ? h->d_xuser : nullptr, h->d_tc, h->d_D, h->d_lambda, h->d_zeros, h->d_V, h->d_C, h->d_g, h->d_f, h->d_fpart,
                        h->d_grad, h->d_jac, h->d_hess };
     for (double* b : bufs) if (b) cudaFree(b);

@@ -9,6 +9,10 @@
 
 void fl_set_error(const std::string& msg);
 struct fl_nlp;
+struct fl_ipm;
+// a solver outlives its problem handle only as an empty shell: fl_nlp_destroy releases the device memory of the solvers
+// still bound to the handle and detaches them (a garbage collector may finalise the two in either order)
+void fl_ipm_orphan(fl_ipm* s);
 int fl_eval_device_masked(fl_nlp* h, int what, double obj_factor, const int* d_active);
 
 struct fl_nlp
@@ -31,4 +35,5 @@ struct fl_nlp
     int n_in = 0, n_ctrl = 0;
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
+    std::vector<fl_ipm*> dependents;                // interior-point solvers bound to this handle
 };

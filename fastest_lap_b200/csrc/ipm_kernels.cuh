@@ -12,7 +12,8 @@
 // with a larger mu, an empty filter, bound multipliers on the central path, equality multipliers kept unless they have
 // blown up, and a cap on the constraint violation tied to the current one; at most IPM_MAX_RESTARTS times, see
 // ipm_restart); iterative refinement on demand (Ipopt's residual_ratio_max without its minimum of one step); Jacobian
-// regularisation dc always on (closed laps with an even node count have dependent rows).
+// regularisation dc always on (closed laps with an even node count have dependent rows); bounds relaxed by
+// bound_relax_factor max(1, |b|) = 1e-8 without Ipopt's cap at constr_viol_tol (1e-10 with the reference's options).
 //
 // One block per lap -- or, for long laps that would leave the GPU idle, one thread-block CLUSTER per lap (up to 8 blocks
 // on neighbouring SMs): the blocks stride over the lap's vectors together, reductions and the leader's decisions cross

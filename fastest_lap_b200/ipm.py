@@ -65,6 +65,7 @@ class LapSolver:
         self._h = self._lib.fl_ipm_create(nlp._h, C.byref(options) if options is not None else None, *args)
         if not self._h:
             raise RuntimeError("fl_ipm_create: " + self._lib.fl_last_error().decode())
+        nlp._register_dependent(self)
 
     def set_partitioned(self, policy=0, max_laps=0):
         """Schedule of the KKT factorisation: 0 automatic, 1 always parallel in the stages, -1 always one block per lap.

@@ -168,8 +168,21 @@ class CollocationNLP:
 
     def close(self):
         if getattr(self, "_h", None):
+            # solvers bound to this handle hold a pointer to it: they are destroyed first (also when the garbage collector
+            # finalises an abandoned NLP before its solver, e.g. after an exception)
+            for ref in list(getattr(self, "_dependents", ())):
+                dep = ref()
+                if dep is not None:
+                    dep.close()
+            self._dependents = []
             self._lib.fl_nlp_destroy(self._h)
             self._h = None
+
+    def _register_dependent(self, obj):
+        import weakref
+        if not hasattr(self, "_dependents"):
+            self._dependents = []
+        self._dependents.append(weakref.ref(obj))
 
     def __del__(self):
         try:

@@ -110,9 +110,15 @@ def truth_node(p, x, lam, obj, node, digits=40):
 _PROGRAMS = {}
 
 
-def state_control_deviation(x, x_ref):
+def state_control_deviation(x, x_ref, problem=None):
     """Largest deviation of a converged solution from the reference's stored one, relative to max(1, |value|): `north_star`
-    asks for converged controls (and states) within 1e-6 relative; the reference's own comparator is EXPECT_NEAR(..., 1e-6)
-    on every state and control (src/test/applications/f1_optimal_laptime_test.cpp:19-165)."""
+    asks for converged controls within 1e-6 relative; the reference's own comparator is EXPECT_NEAR(..., 1e-6) on every state
+    and control (src/test/applications/f1_optimal_laptime_test.cpp:19-165).  With `problem` the result is the pair
+    (states, controls): the full-mesh controls are the two columns after the states (and, derivative form, their rates)."""
     x, x_ref = np.asarray(x, dtype=np.float64).ravel(), np.asarray(x_ref, dtype=np.float64).ravel()
-    return float(np.max(np.abs(x - x_ref) / np.maximum(1.0, np.abs(x_ref))))
+    d = np.abs(x - x_ref) / np.maximum(1.0, np.abs(x_ref))
+    if problem is None:
+        return float(np.max(d))
+    D = d.reshape(-1, problem.nv)
+    n_state = problem.nv - (2 if problem.form == 0 else 4)
+    return float(np.max(D[:, :n_state])), float(np.max(D[:, n_state:n_state + 2]))
