@@ -60,17 +60,23 @@ struct fl_ipm
     double *rDinv = nullptr, *rF = nullptr, *rLst = nullptr, *rAq = nullptr, *rywork = nullptr;
     int *d_redneg = nullptr, *d_redzero = nullptr;
     long n_part_factor = 0;
+    bool warp_kkt = false;                       // the warp-per-lap schedule of kkt_warp_kernels.cuh serves the unpartitioned rounds
+    bool warp_kkt_ok = false;                    // ... and is available for this variant
 };
 
 namespace {
 
+// The whole chain of every lap: one warp per lap with the stage matrix in registers (kkt_warp_kernels.cuh) -- the batch schedule --
+// or one block of four warps per lap (kkt_kernels.cuh), which also serves the reduced system of the partitioned mode.
 template <int NV, int NEQ> void launch_factor(fl_ipm* s, const fl_kkt_dev& K)
 {
-    k_kkt_factor<NV, NEQ><<<s->B, KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K);
+    if (s->warp_kkt && !K.sep) k_kkt_factor_w<NV, NEQ><<<s->B, 32, sizeof(kw_smem<NV, NEQ>), s->nlp->stream>>>(K);
+    else k_kkt_factor<NV, NEQ><<<s->B, KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K);
 }
 template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, const double* r1, const double* r2, double* dx, double* dy)
 {
-    k_kkt_solve<NV, NEQ><<<s->B, KT, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
+    if (s->warp_kkt && !K.sep) k_kkt_solve_w<NV, NEQ><<<s->B, 32, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
+    else k_kkt_solve<NV, NEQ><<<s->B, KT, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
 }
 
 #define FLI_DISPATCH(fn, ...) \
@@ -95,6 +101,20 @@ template <int NV, int NEQ> void launch_solve_seg_fwd(fl_ipm* s, const fl_kkt_dev
 template <int NV, int NEQ> void launch_solve_seg_bwd(fl_ipm* s, const fl_kkt_dev& K, const double* r2, double* dx, double* dy)
 {
     k_kkt_solve_seg_bwd<NV, NEQ><<<dim3(s->P, s->B), KT, 0, s->nlp->stream>>>(K, s->Q, s->rywork, r2, dx, dy);
+}
+
+// the warp-per-lap factorisation keeps ~20 KB of shared memory per lap: ask for the largest shared-memory carve-out, so that
+// the registers, not the default L1 / shared split, decide how many laps an SM holds
+template <int NV, int NEQ> void carveout_w(fl_ipm*, int* ok)
+{
+    *ok = cudaFuncSetAttribute(k_kkt_factor_w<NV, NEQ>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+}
+int set_warp_carveout(fl_ipm* s)
+{
+    int ok = 0;
+    FLI_DISPATCH(carveout_w, &ok);
+    if (!ok) { fl_set_error(std::string("cudaFuncSetAttribute(PreferredSharedMemoryCarveout) failed: ") + cudaGetErrorString(cudaGetLastError())); return 0; }
+    return 1;
 }
 
 // vector kernels: one block per lap, or one cluster of `vec_cluster` blocks per lap
@@ -406,6 +426,14 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
                 return nullptr;
             }
     }
+    // warp-per-lap KKT kernels: the control couplings must sit on the last two variables of a node (direct form), and the compact
+    // fill block holds 16 rows.  FL_KKT_WARP=0 keeps the block-per-lap kernels (comparison runs).
+    s->warp_kkt_ok = (v->NCPL == 0 || (v->NCPL == 2 && v->CTRL_POS[0] == NV - 2 && v->CTRL_POS[1] == NV - 1)) && NEQ + v->NCPL <= 16;
+    // automatic choice: batches.  A lap alone (or a handful) is latency-bound on its chain of stages, where four warps per lap
+    // (and the parallel-in-the-stages schedule) are the better mapping.  fl_ipm_set_warp_kkt / FL_KKT_WARP override it.
+    s->warp_kkt = s->warp_kkt_ok && B >= 64;
+    if (const char* e = std::getenv("FL_KKT_WARP")) s->warp_kkt = s->warp_kkt_ok && std::atoi(e) != 0;
+    if (s->warp_kkt_ok && !set_warp_carveout(s)) { fl_ipm_destroy(s); return nullptr; }
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
     if (P.closed && S == 2) { fl_set_error("closed laps need at least three nodes"); fl_ipm_destroy(s); return nullptr; }
     nlp->dependents.push_back(s);
@@ -622,6 +650,17 @@ int fl_ipm_set_partitioned(fl_ipm* s, int policy, int max_laps)
     s->part_policy = policy;
     if (max_laps > 0) s->part_max_laps = max_laps;
     return s->P;
+}
+
+// Schedule of the unpartitioned KKT factorisation and solves: 1 = one warp per lap with the stage matrix in registers
+// (kkt_warp_kernels.cuh), -1 = one block of four warps per lap (kkt_kernels.cuh), 0 = automatic (warp per lap for batches of
+// 64 laps or more).  Returns 1 if the warp-per-lap kernels are in use afterwards.
+int fl_ipm_set_warp_kkt(fl_ipm* s, int mode)
+{
+    if (mode > 0) s->warp_kkt = s->warp_kkt_ok;
+    else if (mode < 0) s->warp_kkt = false;
+    else s->warp_kkt = s->warp_kkt_ok && s->B >= 64;
+    return s->warp_kkt ? 1 : 0;
 }
 
 // counters of the last solve: [0] kernel launches of the solver (callbacks excluded), [1] factorisation launches, [2] solve launches,

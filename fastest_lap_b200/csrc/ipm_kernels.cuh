@@ -27,6 +27,7 @@
 #include <cooperative_groups.h>
 #include "kkt_kernels.cuh"
 #include "kkt_part_kernels.cuh"
+#include "kkt_warp_kernels.cuh"
 
 constexpr int IPM_BLOCK = 128;          // threads per lap when many laps share the GPU
 constexpr int IPM_BLOCK_MAX = 1024;     // ... when few do (fl_ipm.cu picks per launch; kernels use blockDim.x)

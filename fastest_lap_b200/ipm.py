@@ -38,6 +38,7 @@ def _bind(lib):
     lib.fl_ipm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_long), _dp]
     lib.fl_kkt_factor_solve.argtypes = [C.c_void_p] + [_dp] * 8 + [C.c_int, C.c_int, _dp, _dp, _ip, _ip]
     lib.fl_ipm_set_partitioned.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.fl_ipm_set_warp_kkt.argtypes = [C.c_void_p, C.c_int]
     lib.fl_ipm_solve_warm.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int]
     lib._ipm_bound = True
 
@@ -71,6 +72,11 @@ class LapSolver:
         """Schedule of the KKT factorisation: 0 automatic, 1 always parallel in the stages, -1 always one block per lap.
         Returns the number of separator stages (0: not available for this problem)."""
         return int(self._lib.fl_ipm_set_partitioned(self._h, int(policy), int(max_laps)))
+
+    def set_warp_kkt(self, mode=0):
+        """Mapping of the unpartitioned factorisation: 1 one warp per lap (registers), -1 one block per lap, 0 automatic
+        (warp per lap for batches of 64 laps or more).  Returns True if the warp-per-lap kernels are in use."""
+        return bool(self._lib.fl_ipm_set_warp_kkt(self._h, int(mode)))
 
     def close(self):
         if getattr(self, "_h", None):

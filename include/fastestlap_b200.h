@@ -186,6 +186,9 @@ void fl_ipm_stats(const fl_ipm* ipm, long stats[6], double* device_ms);
  * at ~sqrt(n_stages) separators whose segments are factorised in parallel (latency: few laps).  policy 0 = automatic (the
  * second one when at most max_laps laps are still active), 1 = always the second, -1 = never.  Returns the number of separators. */
 int fl_ipm_set_partitioned(fl_ipm* ipm, int policy, int max_laps);
+/* Mapping of the first schedule: mode 1 = one warp per lap with the stage matrix in registers (batches), -1 = one block of
+ * four warps per lap, 0 = automatic (warp per lap for batches of 64 laps or more).  Returns 1 if warp per lap is in use. */
+int fl_ipm_set_warp_kkt(fl_ipm* ipm, int mode);
 /* One factorisation + solve of  [W + diag(sigx) + dw, J^T; J, -D][dx; dy] = [r1; r2]  at (x, lambda) for every lap of the batch
  * (D = dc on equality rows, 1/(sigs + dw) + dc on inequality rows; sigs is [batch][n_elements * 6], element-major);
  * ls_mode = 1 solves the least-squares multiplier system instead (W = 0, sigx = 1, D = 1 on inequality rows).
