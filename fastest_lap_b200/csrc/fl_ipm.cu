@@ -282,6 +282,13 @@ void fl_ipm_destroy(fl_ipm* s)
 
 fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, const double* x_u, const double* g_l, const double* g_u)
 {
+    return fl_ipm_create_ex(nlp, opts, x_l, x_u, g_l, g_u, 0);
+}
+
+// bounds_per_lap != 0: x_l, x_u are [batch][n] and g_l, g_u [batch][m] -- one set per problem of the batch (G-G sweeps: the
+// reference narrows the bounds of the acceleration per speed, steady_state.hpp:733-735, 787-789)
+fl_ipm* fl_ipm_create_ex(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, const double* x_u, const double* g_l, const double* g_u, int bounds_per_lap)
+{
     if (!nlp) { fl_set_error("null nlp"); return nullptr; }
     if (cudaSetDevice(nlp->device) != cudaSuccess) { fl_set_error("cudaSetDevice failed"); return nullptr; }
     static_assert(sizeof(fl_ipm_opts) == sizeof(fl_ipm_options), "public and device option structs must match");
@@ -297,8 +304,11 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     s->NV = NV; s->NEQ = NEQ; s->NB = NV + NEQ;
     const int n = P.n, m = P.m, S = P.n_var_nodes, n_el = P.n_elements, ni = n_el * NINEQ, B = P.batch;
     // bounds: the caller's, or the model defaults; relaxed by bound_relax_factor as Ipopt does
-    std::vector<double> xl(n), xu(n), gl(m), gu(m);
-    if (x_l && x_u && g_l && g_u) { xl.assign(x_l, x_l + n); xu.assign(x_u, x_u + n); gl.assign(g_l, g_l + m); gu.assign(g_u, g_u + m); }
+    const bool have_bounds = x_l && x_u && g_l && g_u;
+    if (bounds_per_lap && !have_bounds) { fl_set_error("bounds per lap need x_l, x_u, g_l, g_u"); delete s; return nullptr; }
+    const int NBND = bounds_per_lap ? B : 1;         // sets of bounds
+    std::vector<double> xl((size_t)NBND * n), xu((size_t)NBND * n), gl((size_t)NBND * m), gu((size_t)NBND * m);
+    if (have_bounds) { xl.assign(x_l, x_l + xl.size()); xu.assign(x_u, x_u + xu.size()); gl.assign(g_l, g_l + gl.size()); gu.assign(g_u, g_u + gu.size()); }
     else if (!fl_nlp_bounds(nlp, xl.data(), xu.data(), gl.data(), gu.data())) { delete s; return nullptr; }
     // (Ipopt also caps this relaxation at constr_viol_tol, 1e-10 with the reference's options; the cap is not applied here --
     //  listed with the deviations in ipm_kernels.cuh: a converged iterate may sit up to 1e-8 max(1, |b|) outside a bound)
@@ -311,20 +321,21 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
         if (ineq) { ineq_of[r] = (int)ineq_rows.size(); ineq_rows.push_back(r); }
         else { eq_of[r] = (int)eq_rows.size(); eq_rows.push_back(r); }
     }
-    for (int i = 0; i < m; ++i)
+    for (size_t i = 0; i < gl.size(); ++i)
     {
-        const bool ineq = ineq_of[i % NCPE] >= 0;
+        const bool ineq = ineq_of[(i % (size_t)m) % NCPE] >= 0;
         if (ineq != (gu[i] > gl[i])) { fl_set_error("constraint bounds do not match the row classification of the variant"); delete s; return nullptr; }
     }
-    std::vector<double> sl(ni), su(ni);
-    for (int e = 0; e < n_el; ++e)
-        for (int t = 0; t < NINEQ; ++t)
-        {
-            const int row = e * NCPE + ineq_rows[t];
-            sl[e * NINEQ + t] = gl[row] - rel(gl[row]);
-            su[e * NINEQ + t] = gu[row] + rel(gu[row]);
-        }
-    for (int i = 0; i < n; ++i)
+    std::vector<double> sl((size_t)NBND * ni), su((size_t)NBND * ni);
+    for (int b = 0; b < NBND; ++b)
+        for (int e = 0; e < n_el; ++e)
+            for (int t = 0; t < NINEQ; ++t)
+            {
+                const size_t row = (size_t)b * m + (size_t)e * NCPE + ineq_rows[t];
+                sl[(size_t)b * ni + e * NINEQ + t] = gl[row] - rel(gl[row]);
+                su[(size_t)b * ni + e * NINEQ + t] = gu[row] + rel(gu[row]);
+            }
+    for (size_t i = 0; i < xl.size(); ++i)
     {
         if (!(xu[i] > xl[i])) { fl_set_error("every variable needs lower < upper bound"); delete s; return nullptr; }
         xl[i] -= rel(xl[i]); xu[i] += rel(xu[i]);
@@ -344,6 +355,7 @@ fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, c
     std::memcpy(&I.o, &o, sizeof(o));
     I.nx = nlp->d_xuser; I.nlam = nlp->d_lambda; I.nf = nlp->d_f; I.ng = nlp->d_g; I.ngrad = nlp->d_grad; I.njac = nlp->d_jac; I.nhess = nlp->d_hess;
     I.xl = dupload(xl, own); I.xu = dupload(xu, own); I.gl = dupload(gl, own); I.sl = dupload(sl, own); I.su = dupload(su, own);
+    I.bn = bounds_per_lap ? (size_t)n : 0; I.bm = bounds_per_lap ? (size_t)m : 0; I.bi = bounds_per_lap ? (size_t)ni : 0;
     const size_t Bn = (size_t)B * n, Bm = (size_t)B * m, Bi = (size_t)B * ni;
     I.x = dalloc<double>(Bn, own); I.s = dalloc<double>(Bi, own); I.y = dalloc<double>(Bm, own);
     I.zl = dalloc<double>(Bn, own); I.zu = dalloc<double>(Bn, own); I.vl = dalloc<double>(Bi, own); I.vu = dalloc<double>(Bi, own);

@@ -42,7 +42,8 @@ struct fl_ipm_dev
     // the NLP's buffers (fl_nlp): inputs x, lambda; outputs f, g, grad, jac, hess
     double* nx; double* nlam; const double* nf; const double* ng; const double* ngrad; const double* njac; const double* nhess;
     // bounds (relaxed), shared by the batch
-    const double *xl, *xu, *gl, *sl, *su;          // [n], [n], [m], [ni], [ni]
+    const double *xl, *xu, *gl, *sl, *su;          // [n], [n], [m], [ni], [ni] -- or one set per lap, see the strides
+    size_t bn, bm, bi;                             // lap strides of the bound arrays: 0 (shared by the batch) or n, m, ni
     // iterate and work vectors, [batch][...]
     double *x, *s, *y, *zl, *zu, *vl, *vu;
     double *dx, *ds, *dy, *dxs, *dss, *dys, *st;   // step, second-order-corrected step, trial slacks
@@ -223,8 +224,12 @@ __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const doub
     const int t0 = ipm_rank() * blockDim.x + threadIdx.x, tstride = ipm_nranks() * blockDim.x;   /* this thread's share of the lap's vectors */ \
     fl_ipm_lap& L = I.lap[lap]; \
     const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni; \
+    /* bounds: one set for the batch (strides 0) or one per lap */ \
+    const double* const bxl = I.xl + (size_t)lap * I.bn; const double* const bxu = I.xu + (size_t)lap * I.bn; \
+    const double* const bgl = I.gl + (size_t)lap * I.bm; \
+    const double* const bsl = I.sl + (size_t)lap * I.bi; const double* const bsu = I.su + (size_t)lap * I.bi; \
     __shared__ double red[IPM_BLOCK_MAX / 32]; \
-    (void)on; (void)om; (void)oi; (void)red; (void)t0; (void)tstride;
+    (void)on; (void)om; (void)oi; (void)red; (void)t0; (void)tstride; (void)bxl; (void)bxu; (void)bgl; (void)bsl; (void)bsu;
 
 __device__ __forceinline__ double ipm_push(double v, double lo, double hi, const fl_ipm_options& o)
 {
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init(const fl_ipm_dev I)
     IPM_LAP_PROLOGUE
     for (int i = t0; i < I.n; i += tstride)
     {
-        const double v = ipm_push(I.nx[on + i], I.xl[i], I.xu[i], I.o);
+        const double v = ipm_push(I.nx[on + i], bxl[i], bxu[i], I.o);
         I.x[on + i] = v; I.nx[on + i] = v;
         I.zl[on + i] = 1.0; I.zu[on + i] = 1.0;
     }
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_warm(const fl_ipm_de
     o.bound_push = push; o.bound_frac = push;
     for (int i = t0; i < I.n; i += tstride)
     {
-        const double v = ipm_push(I.nx[on + i], I.xl[i], I.xu[i], o);
+        const double v = ipm_push(I.nx[on + i], bxl[i], bxu[i], o);
         I.x[on + i] = v; I.nx[on + i] = v;
         I.zl[on + i] = fmax(I.zl[on + i], push); I.zu[on + i] = fmax(I.zu[on + i], push);
     }
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks_warm(const fl
     for (int k = t0; k < I.ni; k += tstride)
     {
         const int row = ipm_row_of_ineq(I, k);
-        I.s[oi + k] = ipm_push(I.ng[om + row], I.sl[k], I.su[k], o);
+        I.s[oi + k] = ipm_push(I.ng[om + row], bsl[k], bsu[k], o);
         const double y = I.y[om + row];
         I.vl[oi + k] = fmax(-y, 0.0) + push; I.vu[oi + k] = fmax(y, 0.0) + push;
     }
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_slacks(const fl_ipm_
     IPM_LAP_PROLOGUE
     for (int k = t0; k < I.ni; k += tstride)
     {
-        I.s[oi + k] = ipm_push(I.ng[om + ipm_row_of_ineq(I, k)], I.sl[k], I.su[k], I.o);
+        I.s[oi + k] = ipm_push(I.ng[om + ipm_row_of_ineq(I, k)], bsl[k], bsu[k], I.o);
         I.vl[oi + k] = 1.0; I.vu[oi + k] = 1.0;
     }
     for (int i = t0; i < I.n; i += tstride) I.r1[on + i] = -(I.ngrad[on + i] - I.zl[on + i] + I.zu[on + i]);
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
         const int r = i % I.NCPE;
         const int q = I.t.ineq_of_row[r];
         const double g = I.ng[om + i];
-        const double c = (q < 0) ? g - I.gl[i] : g - I.s[oi + (size_t)(i / I.NCPE) * I.NINEQ + q];
+        const double c = (q < 0) ? g - bgl[i] : g - I.s[oi + (size_t)(i / I.NCPE) * I.NINEQ + q];
         I.c[om + i] = c;
         th += fabs(c); cmax = fmax(cmax, fabs(c)); ysum += fabs(I.y[om + i]);
         if (!isfinite(g)) bad = true;
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
         const double zl = I.zl[on + i], zu = I.zu[on + i], x = I.x[on + i];
         const double rx = I.gx[on + i] - zl + zu;
         dmax = fmax(dmax, fabs(rx)); zsum += zl + zu;
-        const double p1 = (x - I.xl[i]) * zl, p2 = (I.xu[i] - x) * zu;
+        const double p1 = (x - bxl[i]) * zl, p2 = (bxu[i] - x) * zu;
         pmin = fmin(pmin, fmin(p1, p2)); pmax = fmax(pmax, fmax(p1, p2));
         if (!isfinite(rx)) bad = true;
     }
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
         const double vl = I.vl[oi + k], vu = I.vu[oi + k], s = I.s[oi + k];
         const double rs = -I.y[om + ipm_row_of_ineq(I, k)] - vl + vu;
         dmax = fmax(dmax, fabs(rs)); zsum += vl + vu;
-        const double p1 = (s - I.sl[k]) * vl, p2 = (I.su[k] - s) * vu;
+        const double p1 = (s - bsl[k]) * vl, p2 = (bsu[k] - s) * vu;
         pmin = fmin(pmin, fmin(p1, p2)); pmax = fmax(pmax, fmax(p1, p2));
     }
     dmax = ipm_block_max(dmax, red); zsum = ipm_block_sum(zsum, red);
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
     double lg = 0.0;
     for (int i = t0; i < I.n; i += tstride)
     {
-        const double x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x;
+        const double x = I.x[on + i], dl = x - bxl[i], du = bxu[i] - x;
         const double zl = I.zl[on + i], zu = I.zu[on + i];
         I.sigx[on + i] = zl / dl + zu / du;
         lg += log(dl) + log(du);
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_state(const fl_ipm_dev I)
     }
     for (int k = t0; k < I.ni; k += tstride)
     {
-        const double s = I.s[oi + k], dl = s - I.sl[k], du = I.su[k] - s;
+        const double s = I.s[oi + k], dl = s - bsl[k], du = bsu[k] - s;
         I.sigs[oi + k] = I.vl[oi + k] / dl + I.vu[oi + k] / du;
         lg += log(dl) + log(du);
         I.rsbar[oi + k] = -mu / dl + mu / du - I.y[om + ipm_row_of_ineq(I, k)];
@@ -531,8 +536,8 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_direction(const fl_ipm_de
     {
         const double ds = (I.dy[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
         I.ds[oi + k] = ds;
-        const double s = I.s[oi + k], dl = s - I.sl[k], du = I.su[k] - s, vl = I.vl[oi + k], vu = I.vu[oi + k];
-        amax = fmin(amax, ipm_ftb(s, ds, I.sl[k], I.su[k], tau));
+        const double s = I.s[oi + k], dl = s - bsl[k], du = bsu[k] - s, vl = I.vl[oi + k], vu = I.vu[oi + k];
+        amax = fmin(amax, ipm_ftb(s, ds, bsl[k], bsu[k], tau));
         const double dvl = mu / dl - vl - vl / dl * ds, dvu = mu / du - vu + vu / du * ds;
         if (dvl < 0.0) adual = fmin(adual, -tau * vl / dvl);
         if (dvu < 0.0) adual = fmin(adual, -tau * vu / dvu);
@@ -541,8 +546,8 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_direction(const fl_ipm_de
     }
     for (int i = t0; i < I.n; i += tstride)
     {
-        const double dx = I.dx[on + i], x = I.x[on + i], dl = x - I.xl[i], du = I.xu[i] - x, zl = I.zl[on + i], zu = I.zu[on + i];
-        amax = fmin(amax, ipm_ftb(x, dx, I.xl[i], I.xu[i], tau));
+        const double dx = I.dx[on + i], x = I.x[on + i], dl = x - bxl[i], du = bxu[i] - x, zl = I.zl[on + i], zu = I.zu[on + i];
+        amax = fmin(amax, ipm_ftb(x, dx, bxl[i], bxu[i], tau));
         const double dzl = mu / dl - zl - zl / dl * dx, dzu = mu / du - zu + zu / du * dx;
         if (dzl < 0.0) adual = fmin(adual, -tau * zl / dzl);
         if (dzu < 0.0) adual = fmin(adual, -tau * zu / dzu);
@@ -572,9 +577,9 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_soc_direction(const fl_ip
     {
         const double ds = (I.dys[om + ipm_row_of_ineq(I, k)] - I.rsbar[oi + k]) / (I.sigs[oi + k] + dw);
         I.dss[oi + k] = ds;
-        amax = fmin(amax, ipm_ftb(I.s[oi + k], ds, I.sl[k], I.su[k], tau));
+        amax = fmin(amax, ipm_ftb(I.s[oi + k], ds, bsl[k], bsu[k], tau));
     }
-    for (int i = t0; i < I.n; i += tstride) amax = fmin(amax, ipm_ftb(I.x[on + i], I.dxs[on + i], I.xl[i], I.xu[i], tau));
+    for (int i = t0; i < I.n; i += tstride) amax = fmin(amax, ipm_ftb(I.x[on + i], I.dxs[on + i], bxl[i], bxu[i], tau));
     amax = ipm_block_min(amax, red);
     if (t0 == 0) { L.alpha_soc = amax; L.ls = LS_SOC_TRIAL; }
     ipm_write_trial(I, lap, I.dxs, I.dss, amax);
@@ -589,6 +594,8 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_soc_direction(const fl_ip
 // (the multipliers then typically blow up).  At most IPM_MAX_RESTARTS times per lap.
 __device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L, double* red)
 {
+    const double* const bxl = I.xl + (size_t)lap * I.bn; const double* const bxu = I.xu + (size_t)lap * I.bn;
+    const double* const bsl = I.sl + (size_t)lap * I.bi; const double* const bsu = I.su + (size_t)lap * I.bi;
     const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni;
     __shared__ double sh_mu;
     const int t0 = ipm_rank() * blockDim.x + threadIdx.x, tstride = ipm_nranks() * blockDim.x;
@@ -614,12 +621,12 @@ __device__ void ipm_restart(const fl_ipm_dev& I, int lap, fl_ipm_lap& L, double*
     {
         const double x = I.x[on + i];
         I.nx[on + i] = x;
-        I.zl[on + i] = mu / (x - I.xl[i]); I.zu[on + i] = mu / (I.xu[i] - x);
+        I.zl[on + i] = mu / (x - bxl[i]); I.zu[on + i] = mu / (bxu[i] - x);
     }
     for (int k = t0; k < I.ni; k += tstride)
     {
         const double s = I.s[oi + k];
-        I.vl[oi + k] = mu / (s - I.sl[k]); I.vu[oi + k] = mu / (I.su[k] - s);
+        I.vl[oi + k] = mu / (s - bsl[k]); I.vu[oi + k] = mu / (bsu[k] - s);
     }
     if (!keep_y)
         for (int i = t0; i < I.m; i += tstride) { I.y[om + i] = 0.0; I.nlam[om + i] = 0.0; }
@@ -641,13 +648,13 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
     {
         const int q = I.t.ineq_of_row[i % I.NCPE];
         const double g = I.ng[om + i];
-        const double c = (q < 0) ? g - I.gl[i] : g - I.st[oi + (size_t)(i / I.NCPE) * I.NINEQ + q];
+        const double c = (q < 0) ? g - bgl[i] : g - I.st[oi + (size_t)(i / I.NCPE) * I.NINEQ + q];
         I.e2[om + i] = c;
         th += fabs(c);
         if (!isfinite(g)) bad = true;
     }
-    for (int i = t0; i < I.n; i += tstride) { const double x = I.nx[on + i]; lg += log(x - I.xl[i]) + log(I.xu[i] - x); }
-    for (int k = t0; k < I.ni; k += tstride) { const double s = I.st[oi + k]; lg += log(s - I.sl[k]) + log(I.su[k] - s); }
+    for (int i = t0; i < I.n; i += tstride) { const double x = I.nx[on + i]; lg += log(x - bxl[i]) + log(bxu[i] - x); }
+    for (int k = t0; k < I.ni; k += tstride) { const double s = I.st[oi + k]; lg += log(s - bsl[k]) + log(bsu[k] - s); }
     th = ipm_block_sum(th, red); lg = ipm_block_sum(lg, red);
     const double badf = ipm_block_max(bad ? 1.0 : 0.0, red);
     if (t0 == 0)
@@ -704,24 +711,24 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_line_search(const fl_ipm_
         const double* dxa = soc ? I.dxs : I.dx; const double* dsa = soc ? I.dss : I.ds; const double* dya = soc ? I.dys : I.dy;
         for (int i = t0; i < I.n; i += tstride)
         {
-            const double x0 = I.x[on + i], dl0 = x0 - I.xl[i], du0 = I.xu[i] - x0, dx = I.dx[on + i];
+            const double x0 = I.x[on + i], dl0 = x0 - bxl[i], du0 = bxu[i] - x0, dx = I.dx[on + i];
             double zl = I.zl[on + i], zu = I.zu[on + i];
             zl += ad * (mu / dl0 - zl - zl / dl0 * dx);
             zu += ad * (mu / du0 - zu + zu / du0 * dx);
             const double x = x0 + alpha * dxa[on + i];
-            const double dl = x - I.xl[i], du = I.xu[i] - x;
+            const double dl = x - bxl[i], du = bxu[i] - x;
             I.x[on + i] = x; I.nx[on + i] = x;
             I.zl[on + i] = fmax(fmin(zl, ks * mu / dl), mu / (ks * dl));
             I.zu[on + i] = fmax(fmin(zu, ks * mu / du), mu / (ks * du));
         }
         for (int k = t0; k < I.ni; k += tstride)
         {
-            const double s0 = I.s[oi + k], dl0 = s0 - I.sl[k], du0 = I.su[k] - s0, ds = I.ds[oi + k];
+            const double s0 = I.s[oi + k], dl0 = s0 - bsl[k], du0 = bsu[k] - s0, ds = I.ds[oi + k];
             double vl = I.vl[oi + k], vu = I.vu[oi + k];
             vl += ad * (mu / dl0 - vl - vl / dl0 * ds);
             vu += ad * (mu / du0 - vu + vu / du0 * ds);
             const double s = s0 + alpha * dsa[oi + k];
-            const double dl = s - I.sl[k], du = I.su[k] - s;
+            const double dl = s - bsl[k], du = bsu[k] - s;
             I.s[oi + k] = s;
             I.vl[oi + k] = fmax(fmin(vl, ks * mu / dl), mu / (ks * dl));
             I.vu[oi + k] = fmax(fmin(vu, ks * mu / du), mu / (ks * du));

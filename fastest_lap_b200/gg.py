@@ -94,39 +94,125 @@ def solve_with_continuation(params, spec, x0, group, order, device=0, max_sweeps
     return dict(x=x, status=status, iters=iters)
 
 
-def gg_diagram(params, speeds, n_lat=64, device=0, polish=3):
-    """speeds [m/s].  Returns dict(ay [S][n_lat], ax_max, ax_min [S][n_lat], ay_max [S], solved masks); accelerations in the
-    model's units (m/s2 for the kart, g for the F1: acceleration_units of lot2016kart.h:79 / limebeer2014f1.h:51)."""
+def _base_bounds(params, brake=False, device=0):
+    """Bounds of one steady-state NLP: the model's variable bounds (+ ax, ay) and constraint bounds."""
+    if _model_of(params) == MODEL_F1:
+        return f1_bounds(brake)
+    nlp = SteadyStateNLP(MODEL_KART, params if np.ndim(params) == 1 else np.asarray(params)[0], np.zeros((1, 7)) + np.array([20.0, 0, 0, 0, 0, 0, 0]), device=device)
+    b = nlp.bounds()
+    nlp.close()
+    return b
+
+
+def speed_envelope(params, speeds, device=0):
+    """Steps (1)-(3) of the reference's G-G computation for every speed: the 0 g state, the maximum lateral acceleration (with
+    its longitudinal acceleration) and the maximum / minimum longitudinal acceleration at ay = 0."""
     speeds = np.asarray(speeds, dtype=np.float64)
     S = len(speeds)
-    z = np.zeros(S)
+    z, one = np.zeros(S), np.ones(S)
     f1 = _model_of(params) == MODEL_F1
     ia, iy = (11, 12) if f1 else (6, 7)
-    # (1) 0 g
     out0 = solve_batch(params, np.stack([speeds, z, z, z, z, z, z], axis=1), np.tile(X0_F1 if f1 else X0, (S, 1)), device)
     x_0g = out0["x"].copy()
-    # (2) maximum lateral acceleration: ax and ay free, f = -ay
-    one = np.ones(S)
+    x_0g[:, ia] = 0.0; x_0g[:, iy] = 0.0
     out_lat = solve_batch(params, np.stack([speeds, z, z, one, one, z, -one], axis=1), x_0g, device)
-    ay_max, ax_at_max = out_lat["x"][:, iy], out_lat["x"][:, ia]
-    # (3) fan of lateral accelerations: max / min longitudinal acceleration (f = -+ax), ay given
-    ay = np.linspace(0.0, 1.0, n_lat)[None, :] * ay_max[:, None]
-    v_b = np.repeat(speeds, n_lat)
-    zb, ob = np.zeros(S * n_lat), np.ones(S * n_lat)
-    x0 = np.repeat(x_0g, n_lat, axis=0)
-    x0[:, iy] = 0.0
+    bnd_acc, bnd_brk = _base_bounds(params, False, device), _base_bounds(params, True, device)
+    lon_max = solve_batch(params, np.stack([speeds, z, z, one, z, -one, z], axis=1), x_0g, device, bounds=bnd_acc if f1 else None)
+    lon_min = solve_batch(params, np.stack([speeds, z, z, one, z, one, z], axis=1), x_0g, device, bounds=bnd_brk if f1 else None)
+    return dict(x_0g=x_0g, zero_g=out0["x"].copy(), zero_g_solved=out0["status"] >= 1, x_lat=out_lat["x"].copy(), ay_max=out_lat["x"][:, iy].copy(),
+                ax_lat=out_lat["x"][:, ia].copy(), ay_max_solved=out_lat["status"] >= 1, ay_max_iters=out_lat["iters"].copy(),
+                ax_lon_max=lon_max["x"][:, ia].copy(), ax_lon_min=lon_min["x"][:, ia].copy(),
+                lon_solved=(lon_max["status"] >= 1) & (lon_min["status"] >= 1), bounds_accelerate=bnd_acc, bounds_brake=bnd_brk)
+
+
+def longitudinal_limits(params, env, k, ay, prev, device=0):
+    """Steps (4)-(5) for a list of points: point b belongs to speed env[..][k[b]], has lateral acceleration ay[b] and the point
+    prev[b] (an index into the list, or -1) as its predecessor along the fan of its speed.  Returns dict(ax_max, ax_min,
+    ax_max_solved, ax_min_solved, iterations, feasible_solved)."""
+    k, ay, prev = np.asarray(k, dtype=int), np.asarray(ay, dtype=np.float64), np.asarray(prev, dtype=int)
+    B = len(k)
+    f1 = _model_of(params) == MODEL_F1
+    ia, iy = (11, 12) if f1 else (6, 7)
+    unit = 9.81 if f1 else 1.0                       # acceleration_units
+    v_b = env["speeds"][k]
+    zb, ob = np.zeros(B), np.ones(B)
+    p_b = params if np.ndim(params) == 1 else np.asarray(params)[k]
+    # (4) a feasible point at (ax_lat ay / ay_max, ay), from the 0 g state; where that fails the predecessor's point is kept
+    ax_f = env["ax_lat"][k] * ay / env["ay_max"][k]
+    feas = solve_batch(p_b, np.stack([v_b, ax_f, ay, zb, zb, zb, zb], axis=1), env["x_0g"][k], device)
+    xf, okf = feas["x"].copy(), feas["status"] >= 1
+    axs = ax_f.copy()
+    order = np.argsort(ay, kind="stable")
+    for b in order:                                  # predecessors first
+        if not okf[b]:
+            if prev[b] >= 0:
+                xf[b], axs[b] = xf[prev[b]], axs[prev[b]]
+            else:
+                xf[b], axs[b] = env["x_0g"][k[b]], 0.0
+    x0 = xf.copy()
+    x0[:, ia], x0[:, iy] = axs, ay
+
+    def lap_bounds(base, lo, hi):
+        xl, xu = np.tile(base[0], (B, 1)), np.tile(base[1], (B, 1))
+        xl[:, ia], xu[:, ia] = lo[k], hi[k]
+        return xl, xu, np.tile(base[2], (B, 1)), np.tile(base[3], (B, 1))
+
+    b_max = lap_bounds(env["bounds_accelerate"], env["ax_lat"] - 0.5 / unit, env["ax_lon_max"] + 0.1 / unit)
+    b_min = lap_bounds(env["bounds_brake"], env["ax_lon_min"] - 0.1 / unit, env["ax_lat"] + 0.1 / unit)
+    res = dict(feasible_solved=okf)
+    for name, sign, bnd in (("ax_max", -1.0, b_max), ("ax_min", 1.0, b_min)):
+        spec = np.stack([v_b, zb, ay, ob, zb, sign * ob, zb], axis=1)
+        start = x0.copy()
+        start[:, ia] = np.clip(start[:, ia], bnd[0][:, ia] + 1e-6, bnd[1][:, ia] - 1e-6)
+        out = solve_batch(p_b, spec, start, device, bounds=bnd)
+        x, status, iters = out["x"].copy(), out["status"].copy(), out["iters"].copy()
+        # (5) second attempt from the predecessor's solution (the reference does it for the minimum, steady_state.hpp:801-809; the
+        # same continuation serves the maximum here), swept along the fans until nothing changes
+        for _ in range(B):
+            todo = np.array([b for b in np.where(status < 1)[0] if prev[b] >= 0 and status[prev[b]] >= 1], dtype=int)
+            if todo.size == 0:
+                break
+            st2 = x[prev[todo]].copy()
+            st2[:, iy] = ay[todo]
+            st2[:, ia] = np.clip(st2[:, ia], bnd[0][todo, ia] + 1e-6, bnd[1][todo, ia] - 1e-6)
+            o2 = solve_batch(p_b if np.ndim(p_b) == 1 else p_b[todo], spec[todo], st2, device, bounds=tuple(a[todo] for a in bnd))
+            good = o2["status"] >= 1
+            x[todo[good]] = o2["x"][good]; status[todo[good]] = o2["status"][good]; iters[todo[good]] += o2["iters"][good]
+            if not good.any():
+                break
+        res[name], res[name + "_solved"], res[name + "_iters"], res[name + "_x"] = x[:, ia].copy(), status >= 1, iters, x
+    return res
+
+
+def gg_diagram(params, speeds, n_lat=64, device=0, polish=0):
+    """speeds [m/s].  Returns dict(ay [S][n_lat], ax_max, ax_min [S][n_lat], ay_max [S], solved masks); accelerations in the
+    model's units (m/s2 for the kart, g for the F1: acceleration_units of lot2016kart.h:79 / limebeer2014f1.h:51).
+
+    The reference's order of solves (steady_state.hpp:696-880), every step one batch over all speeds (and lateral accelerations):
+      (1) 0 g;  (2) maximum lateral acceleration;  (3) maximum / minimum longitudinal acceleration at ay = 0;
+      (4) for every lateral acceleration ay_i of the fan a FEASIBLE point at (ax_lat ay_i / ay_max, ay_i), solved from the 0 g
+          state (where that fails the previous lateral acceleration's point is kept, :715-723);
+      (5) from that point the maximum and the minimum longitudinal acceleration, with the reference's bounds on ax
+          (accelerating: [ax_lat - 0.5, ax_max(0) + 0.1], braking: [ax_min(0) - 0.1, ax_lat + 0.1], :733-735, 787-789); a minimum
+          that fails is solved again from the previous lateral acceleration's minimum (:801-809);
+      (6) the last point of both curves is the maximum-lateral-acceleration solution (:857-870)."""
+    speeds = np.asarray(speeds, dtype=np.float64)
+    S, L = len(speeds), int(n_lat)
+    env = speed_envelope(params, speeds, device)
+    env["speeds"] = speeds
+    n_f = L - 1
+    t = np.linspace(0.0, 1.0, L)[:n_f]
+    ay = t[None, :] * env["ay_max"][:, None]                             # [S][L-1]
+    k = np.repeat(np.arange(S), n_f)
+    idx = np.arange(S * n_f)
+    prev = np.where(idx % n_f > 0, idx - 1, -1)
+    lim = longitudinal_limits(params, env, k, ay.ravel(), prev, device)
     res = {}
-    grp, order = np.repeat(np.arange(S), n_lat), np.tile(np.arange(n_lat), S)
-    for name, sign in (("ax_max", -1.0), ("ax_min", 1.0)):
-        bnd = f1_bounds(brake=sign > 0) if f1 else None         # the F1 brakes within its own variable bounds (steady_state.hpp:803-806)
-        out = solve_with_continuation(params, np.stack([v_b, zb, ay.ravel(), ob, zb, sign * ob, zb], axis=1), x0, grp, order, device, bounds=bnd,
-                                      polish=polish, objective=lambda xx, sp: sp[:, 5] * xx[:, ia])
-        res[name] = out["x"][:, ia].reshape(S, n_lat)
-        res[name + "_solved"] = (out["status"] == 1).reshape(S, n_lat) | (out["status"] == 2).reshape(S, n_lat)
-        res[name + "_iters"] = out["iters"].reshape(S, n_lat)
-        # the last point is the maximum-lateral-acceleration solution itself (steady_state.hpp:715, 857-870: the loop stops at
-        # n_points - 1): there the feasible set of the NLP has shrunk to that single point
-        res[name][:, -1] = ax_at_max
-        res[name + "_solved"][:, -1] = out_lat["status"] >= 1
-    res.update(ay=ay, ay_max=ay_max, ax_at_ay_max=ax_at_max, zero_g=x_0g, zero_g_solved=out0["status"] >= 1, ay_max_solved=out_lat["status"] >= 1)
+    for name in ("ax_max", "ax_min"):
+        res[name] = np.concatenate([lim[name].reshape(S, n_f), env["ax_lat"][:, None]], axis=1)                        # (6)
+        res[name + "_solved"] = np.concatenate([lim[name + "_solved"].reshape(S, n_f), env["ay_max_solved"][:, None]], axis=1)
+        res[name + "_iters"] = np.concatenate([lim[name + "_iters"].reshape(S, n_f), env["ay_max_iters"][:, None]], axis=1)
+    res.update(ay=np.concatenate([ay, env["ay_max"][:, None]], axis=1), ay_max=env["ay_max"], ax_at_ay_max=env["ax_lat"], zero_g=env["zero_g"],
+               zero_g_solved=env["zero_g_solved"], ay_max_solved=env["ay_max_solved"], feasible_solved=lim["feasible_solved"].reshape(S, n_f),
+               ax_lon_max=env["ax_lon_max"], ax_lon_min=env["ax_lon_min"], lon_solved=env["lon_solved"])
     return res

@@ -32,6 +32,8 @@ def _bind(lib):
     lib.fl_ipm_default_options.argtypes = [C.POINTER(IpmOptions)]
     lib.fl_ipm_create.restype = C.c_void_p
     lib.fl_ipm_create.argtypes = [C.c_void_p, C.POINTER(IpmOptions), _dp, _dp, _dp, _dp]
+    lib.fl_ipm_create_ex.restype = C.c_void_p
+    lib.fl_ipm_create_ex.argtypes = [C.c_void_p, C.POINTER(IpmOptions), _dp, _dp, _dp, _dp, C.c_int]
     lib.fl_ipm_destroy.argtypes = [C.c_void_p]
     lib.fl_ipm_solve.argtypes = [C.c_void_p, _dp, C.c_int]
     lib.fl_ipm_results.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
@@ -60,10 +62,16 @@ class LapSolver:
         _bind(self._lib)
         self.options = options
         args = [None] * 4
+        per_lap = 0
         if bounds is not None:
+            # one set for the batch ([n], [n], [m], [m]) or one per problem ([batch][n], ...)
             self._bounds = [np.ascontiguousarray(b, dtype=np.float64) for b in bounds]
+            per_lap = int(self._bounds[0].size == nlp.batch * nlp.n and nlp.batch > 1)
+            for b, sz in zip(self._bounds, (nlp.n, nlp.n, nlp.m, nlp.m)):
+                if b.size != (nlp.batch * sz if per_lap else sz):
+                    raise ValueError("bounds must have n, n, m, m entries (or batch times that, all four)")
             args = [_ptr(b) for b in self._bounds]
-        self._h = self._lib.fl_ipm_create(nlp._h, C.byref(options) if options is not None else None, *args)
+        self._h = self._lib.fl_ipm_create_ex(nlp._h, C.byref(options) if options is not None else None, *args, per_lap)
         if not self._h:
             raise RuntimeError("fl_ipm_create: " + self._lib.fl_last_error().decode())
         nlp._register_dependent(self)

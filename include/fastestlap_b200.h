@@ -170,6 +170,9 @@ enum { FL_IPM_RUNNING = 0, FL_IPM_SUCCESS = 1, FL_IPM_ACCEPTABLE = 2, FL_IPM_MAX
 /* opts == NULL: defaults.  Bounds x_l, x_u [n], g_l, g_u [m] (shared by the batch) == NULL: fl_nlp_bounds.  The nlp handle must
  * outlive the solver and must not be used concurrently. */
 fl_ipm* fl_ipm_create(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, const double* x_u, const double* g_l, const double* g_u);
+/* The same with one set of bounds per problem of the batch when bounds_per_lap != 0: x_l, x_u [batch][n], g_l, g_u [batch][m]
+ * (G-G sweeps: the reference narrows the bounds of the longitudinal acceleration per speed, steady_state.hpp:733-735, 787-789). */
+fl_ipm* fl_ipm_create_ex(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l, const double* x_u, const double* g_l, const double* g_u, int bounds_per_lap);
 void    fl_ipm_destroy(fl_ipm* ipm);
 /* x0: [batch][n] starting points (host).  Returns 1 when the iteration ran (per-lap outcomes are in fl_ipm_results). */
 int fl_ipm_solve(fl_ipm* ipm, const double* x0, int verbose);

@@ -41,35 +41,42 @@ def test_callbacks_match_oracle():
     nlp.close()
 
 
-def test_converged_steady_states_match_the_reference():
-    """max / min longitudinal acceleration at given lateral acceleration, and the maximum lateral acceleration, for every
-    stored case: ax (ay) within 1e-6 relative of steady_state.xml."""
+def test_kart_acceleration_limits_match_the_reference():
+    """Maximum / minimum longitudinal acceleration at given lateral acceleration, and the maximum lateral acceleration, for every
+    case stored in steady_state.xml (steady_state_ad_test.cpp:17-29 ff. asserts `solved` on every point): all of them solved,
+    by the reference's own sequence of solves (feasible point first, then the optimisation, gg.longitudinal_limits), ax and
+    ay within 1e-6 relative of the stored values."""
     from fastest_lap_b200 import gg
     names, v, xg = GOLD["names"], GOLD["v"], GOLD["x"]
-    spec, ref, col, group, order = [], [], [], [], []
+    speeds = np.unique(np.round(v * 3.6)) / 3.6
+    env = gg.speed_envelope(GOLD["params"], speeds)
+    env["speeds"] = speeds
+    assert env["zero_g_solved"].all() and env["ay_max_solved"].all() and env["lon_solved"].all()
+    ks, ays, kinds, refs = [], [], [], []
     for nm, vv, x in zip(names, v, xg):
         case = nm.split("/")[1]
-        kind = 0 if case.startswith("max_lon") else 1 if case.startswith("min_lon") else 2 if case == "max_lat_acc" else -1
+        kk = int(np.argmin(np.abs(speeds - vv)))
+        if case == "max_lat_acc":
+            assert abs(env["ay_max"][kk] - x[7]) <= 1e-6 * x[7], nm
+            continue
+        kind = 0 if case.startswith("max_lon") else 1 if case.startswith("min_lon") else -1
         if kind < 0:
             continue
-        spec.append([[vv, 0, x[7], 1, 0, -1, 0], [vv, 0, x[7], 1, 0, 1, 0], [vv, 0, 0, 1, 1, 0, -1]][kind])
-        ref.append(x[7] if kind == 2 else x[6]); col.append(7 if kind == 2 else 6)
-        group.append(3 * int(round(vv * 3.6)) + kind); order.append(x[7])
-    spec, ref, col, group, order = np.array(spec, dtype=float), np.array(ref), np.array(col), np.array(group), np.array(order)
-    B = len(spec)
-    # start: the 0 g state of each speed, as the reference does (steady_state.hpp:605-615)
-    sp0 = np.zeros((B, 7)); sp0[:, 0] = spec[:, 0]
-    out0 = gg.solve_batch(GOLD["params"], sp0, np.tile(gg.X0, (B, 1)))
-    assert np.all(out0["status"] >= 1)
-    # cold start from 0 g; the points at the tip of the diagram need the reference's continuation in lateral acceleration
-    out = gg.solve_with_continuation(GOLD["params"], spec, out0["x"], group, order)
-    ok = out["status"] >= 1
-    # the stored lateral accelerations are 3 m/s2 apart: a few minimum-ax points at the very tip of the diagram (ay = 14 of a
-    # 14.3 maximum) are out of reach of a continuation that coarse; the reference gets there in steps of ~0.1 m/s2
-    assert ok.mean() >= 0.95, (ok.sum(), B)
-    got = out["x"][np.arange(B), col]
-    err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
-    assert np.max(err[ok]) <= 1e-6, np.max(err[ok])
+        ks.append(kk); ays.append(x[7]); kinds.append(kind); refs.append(x[6])
+    ks, ays, kinds, refs = np.array(ks), np.array(ays), np.array(kinds), np.array(refs)
+    # one fan per speed, by increasing lateral acceleration (max and min cases share the lateral accelerations)
+    uniq = sorted(set(zip(ks.tolist(), np.round(ays, 9).tolist())))
+    pk, pay = np.array([u[0] for u in uniq]), np.array([u[1] for u in uniq])
+    prev = np.array([i - 1 if i > 0 and pk[i - 1] == pk[i] else -1 for i in range(len(uniq))])
+    lim = gg.longitudinal_limits(GOLD["params"], env, pk, pay, prev)
+    assert lim["ax_max_solved"].all() and lim["ax_min_solved"].all(), (lim["ax_max_solved"].sum(), lim["ax_min_solved"].sum(), len(uniq))
+    where = {u: i for i, u in enumerate(uniq)}
+    worst = 0.0
+    for kk, a, kind, ref in zip(ks, ays, kinds, refs):
+        got = lim["ax_max" if kind == 0 else "ax_min"][where[(int(kk), round(float(a), 9))]]
+        worst = max(worst, abs(got - ref) / max(1.0, abs(ref)))
+    print("kart stored acceleration limits: %d points, worst relative deviation %.2e" % (len(refs), worst))
+    assert worst <= 1e-6
 
 
 def test_gg_diagram_sweep_is_consistent():
@@ -79,9 +86,8 @@ def test_gg_diagram_sweep_is_consistent():
     speeds = np.array([50.0, 70.0, 90.0, 110.0]) / 3.6
     r = gg.gg_diagram(GOLD["params"], speeds, n_lat=16)
     assert r["zero_g_solved"].all() and r["ay_max_solved"].all()
-    assert r["ax_max_solved"].mean() >= 0.9 and r["ax_min_solved"].mean() >= 0.9, (r["ax_max_solved"].mean(), r["ax_min_solved"].mean())
-    ok = r["ax_max_solved"] & r["ax_min_solved"]
-    assert np.all(r["ax_max"][ok] >= r["ax_min"][ok] - 1e-6)
+    assert r["ax_max_solved"].all() and r["ax_min_solved"].all(), (r["ax_max_solved"].mean(), r["ax_min_solved"].mean())
+    assert np.all(r["ax_max"] >= r["ax_min"] - 1e-6)
     for k, vk in enumerate((50, 70, 90, 110)):
         i = list(GOLD["names"]).index("velocity_%d/max_lat_acc" % vk)
         assert abs(r["ay_max"][k] - GOLD["x"][i, 7]) <= 1e-6 * GOLD["x"][i, 7]
@@ -135,13 +141,17 @@ def test_f1_gg_diagram_150_matches_the_reference():
     """f1_steady_state_test.cpp:128-163: G-G diagram at 150 km/h, 49 lateral accelerations, 2e-4 m/s2."""
     from fastest_lap_b200 import gg
     r = gg.gg_diagram(F1G["params"], np.array([150.0 / 3.6]), n_lat=49)
-    ok = r["ax_max_solved"][0] & r["ax_min_solved"][0]
-    assert ok.mean() >= 0.9
+    assert r["ax_max_solved"][0].all() and r["ax_min_solved"][0].all(), (r["ax_max_solved"][0].sum(), r["ax_min_solved"][0].sum())
     assert np.max(np.abs(r["ay"][0] * 9.81 - F1G["gg150_ay"])) <= 2e-4
-    assert np.max(np.abs(r["ax_max"][0][ok] * 9.81 - F1G["gg150_ax_max"][ok])) <= 2e-4
-    # braking side: the NLPs near the tip of the diagram have several local optima (the stored curve itself jumps there);
-    # away from them the stored values are reproduced to 1e-9, and where they differ this solver's optimum is often the
-    # lower one.  At least 85 % of the points must agree within the reference's tolerance.
-    err = np.abs(r["ax_min"][0] * 9.81 - F1G["gg150_ax_min"])
-    assert np.mean(err[ok] <= 2e-4) >= 0.85, err
-    assert np.max(err[:40][ok[:40]]) <= 0.05
+    assert np.max(np.abs(r["ax_max"][0] * 9.81 - F1G["gg150_ax_max"])) <= 2e-4
+    # braking side: within the reference's tolerance -- or BELOW the stored value (these NLPs have several local optima near the
+    # tip of the diagram; a lower minimum longitudinal acceleration at the same lateral acceleration is the better answer to
+    # the NLP the reference poses, and the stored curve itself jumps between branches there)
+    ref = F1G["gg150_ax_min"]
+    got = r["ax_min"][0] * 9.81
+    err = np.abs(got - ref)
+    lower = got < ref - 2e-4
+    print("F1 150 km/h braking side: %d of %d points within 2e-4 m/s2 of the stored curve (worst %.2e), %d below it (by %s m/s2)" % (
+        int((err <= 2e-4).sum()), len(ref), err[err <= 2e-4].max(), int(lower.sum()), np.array2string(ref[lower] - got[lower], precision=3)))
+    assert np.all((err <= 2e-4) | lower), err
+    assert lower.sum() <= 3
