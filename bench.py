@@ -217,7 +217,7 @@ def batched_leg(args, torch, dist, world, rank, local, peak):
 N_SOLVE = 4096
 
 
-def solve_leg(args, torch, dist, world, rank, local):
+def solve_leg(args, torch, dist, world, rank, local, weak=False):
     """Batched laps/s: `--solve-laps` independent F1 laps (Catalunya, 500 nodes, perturbed vehicles, configs[4] scaled to a
     default bench run) solved to Ipopt's tolerances by the device interior-point solver from the reference's starting point
     (steady state at 50 km/h replicated).  Sharded contiguously over the ranks; one final all_gather of (lap time, status,
@@ -228,9 +228,10 @@ def solve_leg(args, torch, dist, world, rank, local):
     from fastest_lap_b200.sharding import shard_range, gather_results
     from fastest_lap_b200.vehicle import MODEL_F1
     p = workloads.f1_catalunya(500)
-    lo, hi = shard_range(args.solve_laps, world, rank)
+    n_total = args.solve_laps * (world if weak else 1)
+    lo, hi = shard_range(n_total, world, rank)
     B = hi - lo
-    params = workloads.sweep_parameters(MODEL_F1, args.solve_laps)
+    params = workloads.sweep_parameters(MODEL_F1, n_total)
     params[0] = p.params                                     # lap 0 drives the reference vehicle (known answer)
     from fastest_lap_b200.ipm import default_options, solve_sweep
     opts = default_options()
@@ -242,19 +243,22 @@ def solve_leg(args, torch, dist, world, rank, local):
     out = solve_sweep(p, params[lo:hi], options=opts, device=local)      # start: steady state at 50 km/h (GPU steady-state solve), then retries
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    t = torch.tensor([wall, out["device_ms"]], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
+    ph = out["phases_s"]
+    t = torch.tensor([wall, out["device_ms"], ph["allocate"], ph["start_point"], ph["first_pass"], ph["retries"]], dtype=torch.float64, device="cuda" if dist is not None else "cpu")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall, dev_ms = [float(v) for v in t.tolist()]
+    wall, dev_ms = [float(v) for v in t.tolist()[:2]]
+    phases = dict(zip(("allocate", "start_point", "first_pass", "retries"), [round(float(v), 3) for v in t.tolist()[2:]]))
     times = np.array([lap_time(p, out["x"][b], out["obj"][b]) for b in range(B)])
     local_res = np.stack([times, out["status"].astype(np.float64), out["iters"].astype(np.float64)], axis=1)
-    res = gather_results(local_res, args.solve_laps)          # the final gather of per-lap results
+    res = gather_results(local_res, n_total)          # the final gather of per-lap results
     ok = res[:, 1] >= 1
     st = out["stats"]
     golden = 77.791438
     r = {"workload": "%d independent limebeer-2014-f1 laps, Catalunya, 500 nodes, closed, direct form, vehicles drawn per lap (rng 2), start = steady state at 50 km/h; "
-                     "tol 1e-10 (the reference's Ipopt options), at most %d iterations per lap; contiguous shards over %d GPU(s)" % (args.solve_laps, args.solve_max_iter, world),
-         "laps": args.solve_laps, "laps_per_gpu": B, "scaling": "strong", "value": args.solve_laps / wall, "unit": "laps/s", "seconds": wall, "device_ms": dev_ms,
+                     "tol 1e-10 (the reference's Ipopt options), at most %d iterations per lap; contiguous shards over %d GPU(s)" % (n_total, args.solve_max_iter, world),
+         "laps": n_total, "laps_per_gpu": B, "scaling": "weak" if weak else "strong", "value": n_total / wall, "unit": "laps/s", "seconds": wall, "device_ms": dev_ms,
+         "phases_s": phases,
          "converged": int(ok.sum()), "not_converged": int((~ok).sum()), "iterations_median": float(np.median(res[:, 2])), "iterations_max": float(res[:, 2].max()),
          "lap0_time_s": float(res[0, 0]), "lap0_reference_s": golden, "lap0_rel_err": abs(float(res[0, 0]) - golden) / golden,
          "lap_time_range_s": [float(res[ok, 0].min()), float(res[ok, 0].max())] if ok.any() else None,
@@ -521,6 +525,10 @@ def main():
             line["gpu_launches"] += b["gpu_launches"]
     if args.solve_laps > 0:
         sl = solve_leg(args, torch, dist, world, rank, local)
+        if world > 1:
+            # the same sweep per GPU (weak scaling: world x laps in all), next to the fixed-size sweep above (strong scaling)
+            wk = solve_leg(args, torch, dist, world, rank, local, weak=True)
+            sl["weak"] = {k: wk[k] for k in ("laps", "laps_per_gpu", "value", "unit", "seconds", "converged", "phases_s")}
         if rank == 0:
             line["batched_solve"] = sl
             line["gpu_launches"] += int(sl["rank0_launches"]["solver_launches"]) + 3 * int(sl["rank0_launches"]["full_rounds"]) + 2 * int(sl["rank0_launches"]["fg_rounds"])

@@ -164,6 +164,16 @@ def vehicle_declare_new_constant_parameter(vehicle_name, parameter_path, paramet
     _get(vehicle_name, Vehicle).set_parameter(parameter_path, float(parameter_value))
 
 
+def vehicle_declare_new_variable_parameter(vehicle_name, parameter_path, parameter_alias, parameter_values, mesh_parameter_indexes, mesh_points):
+    """A vehicle parameter as a piecewise-linear function of the arclength (fastest_lap.py / fastestlapc.cpp:941-981; evaluated
+    by Model_parameter::operator()(s), model_parameter.h:51-77): optimal_laptime evaluates it at every mesh node and the kernels
+    read one parameter vector per node.  (The aliases name the parameter in the reference's sensitivity analysis, not computed here.)"""
+    try:
+        _get(vehicle_name, Vehicle).declare_variable_parameter(parameter_path, parameter_values, mesh_parameter_indexes, mesh_points)
+    except (KeyError, ValueError) as e:
+        raise FastestLapError("[ERROR] vehicle_declare_new_variable_parameter -> %s" % e)
+
+
 def vehicle_change_track(vehicle_name, track_name):
     """Vehicles of the reference carry their road; here the track is an argument of optimal_laptime: only checked."""
     _get(vehicle_name, Vehicle); _get(track_name, Track)

@@ -178,7 +178,8 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
     if (!v) { fail(d->model == FL_MODEL_KART_6DOF && d->elevation ? "lot2016kart does not support tracks with elevation" : "unknown model / form"); return nullptr; }
     if (d->n_points < 2 && !steady_spec) { fail("provide at least two values of arclength"); return nullptr; }
     if (d->batch < 1) { fail("batch must be >= 1"); return nullptr; }
-    if (!d->s || !d->track_nodes || !d->wl || !d->wr || !d->vehicle_params) { fail("null array in problem description"); return nullptr; }
+    if (!d->s || !d->track_nodes || !d->wl || !d->wr || (!d->vehicle_params && !d->node_params)) { fail("null array in problem description"); return nullptr; }
+    if (d->node_params && steady_spec) { fail("steady-state problems have no arclength to vary the parameters with"); return nullptr; }
     for (int i = 1; i < d->n_points; ++i)
         if (!(d->s[i] > d->s[i - 1])) { fail("arclength must be strictly increasing"); return nullptr; }
     if (d->closed && !(d->track_length > d->s[d->n_points - 1])) { fail("closed meshes must end before the track length"); return nullptr; }
@@ -195,8 +196,17 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
     const int np = d->n_points, NV = v->NV, batch = d->batch;
     const int nvp = fl_n_vehicle_params(d->model);
     h->s.assign(d->s, d->s + np); h->wl.assign(d->wl, d->wl + np); h->wr.assign(d->wr, d->wr + np);
-    h->params.assign(d->vehicle_params, d->vehicle_params + (size_t)batch * nvp);
+    if (d->node_params)
+    {
+        // parameters that vary along the lap: one vector per node; the per-problem vector (bounds, queries) is node 0's
+        h->node_params.assign(d->node_params, d->node_params + (size_t)batch * np * nvp);
+        h->params.resize((size_t)batch * nvp);
+        for (int b = 0; b < batch; ++b) std::memcpy(h->params.data() + (size_t)b * nvp, h->node_params.data() + (size_t)b * np * nvp, nvp * sizeof(double));
+    }
+    else
+        h->params.assign(d->vehicle_params, d->vehicle_params + (size_t)batch * nvp);
     h->desc.s = h->s.data(); h->desc.wl = h->wl.data(); h->desc.wr = h->wr.data(); h->desc.vehicle_params = h->params.data();
+    h->desc.node_params = d->node_params ? h->node_params.data() : nullptr;
     h->desc.track_nodes = nullptr; h->desc.q0 = h->desc.u0 = h->desc.du0 = h->desc.ctrl_default = nullptr;
 
     fl_dev& P = h->P;
@@ -261,12 +271,14 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
         }
     }
 
-    // ---- parameter vectors [batch][ND]: vehicle parameters, host-side slots, parameter-only sub-expressions
-    std::vector<double> D((size_t)batch * v->ND, 0.0);
-    for (int b = 0; b < batch; ++b)
+    // ---- parameter vectors [batch][ND] (or [batch][n_points][ND]): vehicle parameters, host-side slots, parameter-only sub-expressions
+    const int nvec = d->node_params ? batch * np : batch;
+    const double* raw = d->node_params ? h->node_params.data() : h->params.data();
+    std::vector<double> D((size_t)nvec * v->ND, 0.0);
+    for (int b = 0; b < nvec; ++b)
     {
         double* Db = D.data() + (size_t)b * v->ND;
-        std::memcpy(Db, d->vehicle_params + (size_t)b * nvp, nvp * sizeof(double));
+        std::memcpy(Db, raw + (size_t)b * nvp, nvp * sizeof(double));
         if (v->P_F_WHEEL_SCALE >= 0)
         {
             // axle_car_3dof.hpp:294: wheel equations are scaled by 1/m when the wheels have no inertia
@@ -280,9 +292,11 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
         if (steady_spec) std::memcpy(Db + v->P_DISS1 + 1, steady_spec + (size_t)b * 7, 7 * sizeof(double));    // ss_v ... ss_cay follow diss1
         v->derive(Db);
     }
+    P.d_prob_stride = d->node_params ? (size_t)np * v->ND : (size_t)v->ND;
+    P.d_node_stride = d->node_params ? (size_t)v->ND : 0;
 
     h->D0.assign(D.begin(), D.begin() + v->ND);
-    for (int b = 1; b < batch && h->shared_d; ++b)
+    for (int b = 1; b < nvec && h->shared_d; ++b)
         if (std::memcmp(D.data() + (size_t)b * v->ND, D.data(), v->ND * sizeof(double)) != 0) h->shared_d = 0;
 
     // ---- x with the fixed first node of open problems
@@ -364,7 +378,7 @@ int fl_nlp_structure(const fl_nlp* h, int* jac_row, int* jac_col, int* hess_row,
 
 int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double* g_l, double* g_u)
 {
-    if (!d || !d->wl || !d->wr || !d->vehicle_params) return fail("null problem description") ? 1 : 0;
+    if (!d || !d->wl || !d->wr || (!d->vehicle_params && !d->node_params)) return fail("null problem description") ? 1 : 0;
     const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque);
     if (!v) return fail("unknown model / form") ? 1 : 0;
     const int node0 = d->closed ? 0 : 1, n_points = d->n_points;
@@ -372,7 +386,7 @@ int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double
     const int NV = v->NV, n_in = d->model == FL_MODEL_F1_3DOF ? F1_NIN : KART_NIN;
     const double big = std::numeric_limits<double>::max();
     std::vector<double> lb(NV), ub(NV);
-    const double* par = d->vehicle_params;        // bounds that depend on parameters use problem 0
+    const double* par = d->vehicle_params ? d->vehicle_params : d->node_params;        // bounds that depend on parameters use problem 0
     if (d->form == FL_FORM_STEADY && d->model == FL_MODEL_F1_3DOF)
     {
         // limebeer2014f1.h:57-86: steady_state_variable_bounds, then ax, ay in g (the reference widens them until they are
@@ -443,10 +457,11 @@ int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double
         if (d->model == FL_MODEL_F1_3DOF)
         {
             // limebeer2014f1.h:232-262: +-max(lambda_max(0), lambda_max(m g0)) per tyre, track limits for n +- t/2 cos(alpha)
-            const double m = par[0];
+            const double* pj = d->node_params ? d->node_params + (size_t)j * fl_n_vehicle_params(d->model) : par;      // (problem 0)
+            const double m = pj[0];
             for (int t = 0; t < 4; ++t)
             {
-                const double* tp = par + (t < 2 ? 32 : 45);
+                const double* tp = pj + (t < 2 ? 32 : 45);
                 const double l1 = tp[9] * DEG, l2 = tp[10] * DEG, Fz1 = tp[1], Fz2 = tp[2];
                 const double a = (0.0 - Fz1) * (l2 - l1) / (Fz2 - Fz1) + l1, b = (m * G0 - Fz1) * (l2 - l1) / (Fz2 - Fz1) + l1;
                 eu[t] = a > b ? a : b; el[t] = -eu[t];

@@ -15,7 +15,8 @@
 //   xfull  [problem][node][NV]      node-major, the reference's variable order (optimal_laptime.hpp:1269-1303); the fixed
 //                                   first node of open problems occupies slot 0 and is filled by the host
 //   tc     [chunk][NTC][32]         per-node track / mesh constants, shared by the whole batch
-//   D      [problem][ND]            vehicle parameters followed by their parameter-only sub-expressions
+//   D      [problem][ND]            vehicle parameters followed by their parameter-only sub-expressions ([problem][node][ND] when
+//                                   they vary along the lap)
 //   V, C   [problem][chunk][NVAL|NCK][32]  structure-of-arrays in chunks of 32 nodes (one warp): slot k of a node sits at a
 //                                   fixed byte offset k*256 from the node's base, so every access is base + immediate and a
 //                                   warp's access to a slot is one contiguous 256-byte segment
@@ -40,7 +41,8 @@ struct fl_dev
     long nnz_jac, nnz_hess;      // per problem
     const double* x;             // [batch][n_points*NV]
     const double* tc;            // [n_pad/32][NTC][32]
-    const double* D;             // [batch][ND]
+    const double* D;             // [batch][ND], or [batch][n_points][ND] when the parameters vary along the lap
+    size_t d_prob_stride, d_node_stride;     // ND, 0   or   n_points * ND, ND
     const double* lambda;        // [batch][m]
     const double* zeros;         // >= NCPE zeros
     double obj_factor;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant_
     ValuesIO<G, CD> io;
     io.xn = P.x + ((size_t)prob * P.n_points + node) * G::NV;
     io.tcn = P.tc + fl_chunk_base(node, G::NTC);
-    io.Dp = P.D + (size_t)prob * G::ND;
+    io.Dp = P.D + (size_t)prob * P.d_prob_stride + (size_t)node * P.d_node_stride;
     io.Dk = &Dk;
     io.Vn = P.V + (size_t)prob * G::NVAL * P.n_pad + fl_chunk_base(node, G::NVAL);
     io.Cn = P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node, G::NCK);
@@ -160,7 +162,7 @@ __device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, co
         const int i = e;
         const int j = (e + 1 == np) ? 0 : e + 1;
         const bool closing = (e + 1 == np);
-        const double* D = P.D + (size_t)prob * G::ND;
+        const double* D = P.D + (size_t)prob * P.d_prob_stride;          // sigma, dissipations: the same at every node
         const double sigma = __ldg(D + G::P_SIGMA), oms = 1.0 - sigma;
         const double h = __ldg(P.tc + fl_chunk_base(i, G::NTC) + (G::NTRACK + 1) * 32);           // hout of the left node
         const double* Vi = P.V + (size_t)prob * G::NVAL * P.n_pad + fl_chunk_base(i, G::NVAL);
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __gri
     io.xp = xb + (size_t)prev * G::NV;
     io.xq = xb + (size_t)next * G::NV;
     io.tcn = P.tc + fl_chunk_base(node, G::NTC);
-    io.Dp = P.D + (size_t)prob * G::ND;
+    io.Dp = P.D + (size_t)prob * P.d_prob_stride + (size_t)node * P.d_node_stride;
     io.lin_ = lam + (size_t)e_in * G::NCPE;
     io.lout_ = has_out ? lam + (size_t)e_out * G::NCPE : P.zeros;
     io.obj_ = P.obj_factor;

@@ -176,13 +176,21 @@ def solve_sweep(problem, vehicle_params, options=None, device=0, start_speeds_km
     restoration phase: the few laps that do not converge are solved again in a small second (third) batch from another
     starting speed and a larger initial barrier parameter -- the retry-from-another-start loop the reference itself uses
     around Ipopt where it fails (steady_state.hpp:200-226, 786-800).  Returns LapSolver.solve's dict, plus `passes`."""
+    import time
     from . import workloads
+    t0 = time.perf_counter()
     params = np.ascontiguousarray(vehicle_params, dtype=np.float64)
     nlp = CollocationNLP(problem, vehicle_params=params, device=device)
     solver = LapSolver(nlp, options=options)
-    out = solver.solve(workloads.f1_start_point(problem, start_speeds_kmh[0], device=device))
+    t1 = time.perf_counter()
+    x_start = workloads.f1_start_point(problem, start_speeds_kmh[0], device=device)
+    t2 = time.perf_counter()
+    out = solver.solve(x_start)
+    t3 = time.perf_counter()
     solver.close(); nlp.close()
     passes = [dict(laps=int(params.shape[0]), converged=int((out["status"] >= 1).sum()), device_ms=out["device_ms"])]
+    phases = dict(allocate=t1 - t0, start_point=t2 - t1, first_pass=t3 - t2, retries=0.0)
+    t4 = time.perf_counter()
     for speed in start_speeds_kmh[1:]:
         bad = np.where(out["status"] < 1)[0]
         if bad.size == 0:
@@ -203,4 +211,6 @@ def solve_sweep(problem, vehicle_params, options=None, device=0, start_speeds_km
             out["stats"][k] += r["stats"][k]
         passes.append(dict(laps=int(bad.size), converged=int(good.sum()), device_ms=r["device_ms"], start_speed_kmh=speed, mu_init=retry_mu_init))
     out["passes"] = passes
+    phases["retries"] = time.perf_counter() - t4
+    out["phases_s"] = phases
     return out

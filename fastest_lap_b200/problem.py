@@ -22,8 +22,11 @@ class LapProblem:
     _SCALARS = ("model", "form", "closed", "elevation", "track_length", "sigma", "kart_direct_torque")
 
     def __init__(self, model, form, closed, s, track_length, track_nodes, wl, wr, params, dissipation=None, sigma=0.5,
-                 elevation=False, q0=None, u0=None, du0=None, ctrl_default=None, kart_direct_torque=False):
+                 elevation=False, q0=None, u0=None, du0=None, ctrl_default=None, kart_direct_torque=False, node_params=None):
         self.model, self.form, self.closed, self.elevation = int(model), int(form), bool(closed), bool(elevation)
+        # parameters that vary with the arclength (Model_parameter, src/core/foundation/model_parameter.h:51-77): one parameter
+        # vector per mesh node, [n_points][n_params]; `params` is then node 0's
+        self.node_params = None if node_params is None else np.ascontiguousarray(node_params, dtype=np.float64)
         self.kart_direct_torque = bool(kart_direct_torque)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         self.s = f64(s)
@@ -85,8 +88,11 @@ class LapProblem:
         elevation = track.has_elevation()
         if elevation and vehicle.model == MODEL_KART:
             raise ValueError("lot2016kart does not support tracks with elevation")      # lot2016kart.h:63-68
+        # parameters declared as functions of the arclength are evaluated at the mesh nodes (dynamic_model_car.hpp:62-63)
+        node_params = vehicle.params_at(s) if getattr(vehicle, "has_variable_parameters", lambda: False)() else None
         return cls(vehicle.model, form, closed, s, track.track_length, track.node_data(s), track.left_track_limit(s),
-                   track.right_track_limit(s), vehicle.params, dissipation, sigma, elevation, q0, u0, du0, None, kart_direct_torque)
+                   track.right_track_limit(s), vehicle.params if node_params is None else node_params[0], dissipation, sigma, elevation, q0, u0, du0,
+                   None, kart_direct_torque, node_params=node_params)
 
     def save_npz(self, path, **extra):
         d = {k: getattr(self, k) for k in self._ARRAYS}

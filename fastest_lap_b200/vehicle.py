@@ -68,7 +68,51 @@ class Vehicle:
         self.paths = F1_PARAM_PATHS if model == MODEL_F1 else KART_PARAM_PATHS
 
     def copy(self):
-        return Vehicle(self.model, self.params.copy(), self.name)
+        v = Vehicle(self.model, self.params.copy(), self.name)
+        v.variable = {k: tuple(np.array(a) for a in val) for k, val in getattr(self, "variable", {}).items()}
+        return v
+
+    def declare_variable_parameter(self, path, values, mesh_indexes, mesh_points):
+        """A parameter that varies with the arclength (vehicle_declare_new_variable_parameter, fastestlapc.cpp:941-981;
+        Model_parameter, src/core/foundation/model_parameter.h:18-77): `values` and a mesh of (arclength, index into values)
+        pairs, blended piecewise linearly between consecutive mesh points."""
+        key = path[len("vehicle/"):] if path.startswith("vehicle/") else path
+        if key not in self.paths:
+            raise KeyError('Parameter "%s" was not found' % path)
+        values, idx, pts = np.asarray(values, dtype=np.float64), np.asarray(mesh_indexes, dtype=int), np.asarray(mesh_points, dtype=np.float64)
+        if len(idx) != len(pts) or len(values) == 0 or (len(pts) and (idx.min() < 0 or idx.max() >= len(values))):
+            raise ValueError("mesh indexes must address the parameter values, one per mesh point")
+        if np.any(np.diff(pts) < 0.0):
+            raise ValueError("mesh points must be sorted")
+        if not hasattr(self, "variable"):
+            self.variable = {}
+        self.variable[key] = (values, idx, pts)
+        self.params[self.paths.index(key)] = values[0]
+
+    def has_variable_parameters(self):
+        return bool(getattr(self, "variable", {}))
+
+    def params_at(self, s):
+        """[len(s)][n_params]: the parameter vector at every arclength of `s` -- Model_parameter::operator()(s)
+        (model_parameter.h:51-77): the first value before the first mesh point, the last value after the last one (the
+        reference returns _values.front() / _values.back() there, whatever the mesh indexes say), linear in between."""
+        s = np.asarray(s, dtype=np.float64)
+        out = np.tile(self.params, (len(s), 1))
+        for key, (values, idx, pts) in getattr(self, "variable", {}).items():
+            col = self.paths.index(key)
+            if len(values) == 1 or len(pts) == 0:
+                out[:, col] = values[0]
+                continue
+            k = np.searchsorted(pts, s, side="right")              # first mesh point > s (std::upper_bound)
+            v = np.empty(len(s))
+            lo, hi = k == 0, k == len(pts)
+            v[lo], v[hi] = values[0], values[-1]
+            mid = ~(lo | hi)
+            km = k[mid]
+            xi = (s[mid] - pts[km - 1]) / (pts[km] - pts[km - 1])
+            v[mid] = values[idx[km - 1]] + xi * (values[idx[km]] - values[idx[km - 1]])
+            out[:, col] = v
+        return out
 
     def set_parameter(self, path, value):
         """Mirror of vehicle_set_parameter (fastestlapc.cpp): `path` is "vehicle/..." as in the reference."""

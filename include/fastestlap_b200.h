@@ -58,6 +58,10 @@ typedef struct fl_problem_desc
     const double* du0;          /* open problems, derivative form: control rates of node 0 [2]                         */
     const double* ctrl_default; /* value of every control [n_controls]; used for the ones that are not optimised       */
     int device;                 /* CUDA device ordinal                                                                 */
+    const double* node_params;  /* NULL, or [batch][n_points][fl_n_vehicle_params(model)]: the vehicle parameters AT EVERY NODE --
+                                   parameters that vary with the arclength (Model_parameter::operator()(s),
+                                   src/core/foundation/model_parameter.h:51-77, evaluated per node at
+                                   src/core/vehicles/dynamic_model_car.hpp:62-63).  vehicle_params is then ignored.       */
 } fl_problem_desc;
 
 fl_nlp* fl_nlp_create(const fl_problem_desc* desc);       /* NULL on failure */

@@ -34,6 +34,9 @@ struct Desc
     const double* u0;           // open problems: controls of node 0 [NCTRL]
     const double* du0;          // open problems, derivative form: dcontrols_dt of the full-mesh controls at node 0 [2]
     const double* ctrl_default; // default value of every control [NCTRL] (used for the not-optimised ones)
+    const double* node_params = nullptr;   // [n_points][n_params]: parameters that vary with the arclength (Model_parameter::operator()(s),
+    int n_params = 0;                      //  model_parameter.h:51-77, applied per node at dynamic_model_car.hpp:62-63), or null
+    const double* params_at(int node) const { return node_params ? node_params + (size_t)node * n_params : params; }
 };
 
 constexpr int MAX_ROWS = 14;
@@ -144,7 +147,7 @@ inline void eval_node(const Desc& d, const Layout& L, int i, const double* xn, N
             if (deriv) { R.dctrl[0] = J(d.du0[0]); R.dctrl[1] = J(d.du0[1]); }
         }
         F1Out<J> o;
-        f1_car(q, u, d.params, tk, o);
+        f1_car(q, u, d.params_at(i), tk, o);
         for (int r = 0; r < L.n_td; ++r) { R.q[r] = o.states[L.td_ids[r]]; R.qd[r] = o.dstates[L.td_ids[r]]; }
         for (int r = 0; r < L.n_alg; ++r) R.alg[r] = o.dstates[L.alg_ids[r]] / o.dtds;      // optimal_laptime.hpp:1341
         for (int r = 0; r < L.n_ext; ++r) R.ext[r] = o.extra[r];
@@ -172,7 +175,7 @@ inline void eval_node(const Desc& d, const Layout& L, int i, const double* xn, N
             if (deriv) { R.dctrl[0] = J(d.du0[0]); R.dctrl[1] = J(d.du0[1]); }
         }
         KartOut<J> o;
-        kart_car(q, u, d.params, tk, d.kart_direct_torque != 0, true, o);
+        kart_car(q, u, d.params_at(i), tk, d.kart_direct_torque != 0, true, o);
         for (int r = 0; r < L.n_td; ++r) { R.q[r] = o.states[L.td_ids[r]]; R.qd[r] = o.dstates[L.td_ids[r]]; }
         for (int r = 0; r < L.n_ext; ++r) R.ext[r] = o.extra[r];
         R.dtds = o.dstates[KART_ITIME];

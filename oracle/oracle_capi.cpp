@@ -24,6 +24,7 @@ struct orc_desc
     const double* u0;
     const double* du0;
     const double* ctrl_default;
+    const double* node_params;     // [n_points][orc_nparams(model)] or null
 };
 
 static Desc to_desc(const orc_desc* c)
@@ -34,6 +35,7 @@ static Desc to_desc(const orc_desc* c)
     d.s = c->s; d.track_length = c->track_length; d.track = c->track; d.params = c->params; d.sigma = c->sigma;
     d.dissipation[0] = c->dissipation[0]; d.dissipation[1] = c->dissipation[1];
     d.q0 = c->q0; d.u0 = c->u0; d.du0 = c->du0; d.ctrl_default = c->ctrl_default;
+    d.node_params = c->node_params; d.n_params = c->model == MODEL_F1 ? (int)F1_NPARAMS : (int)K_NPARAMS;
     return d;
 }
 

@@ -14,7 +14,8 @@ def load_golden(name):
 
 def oracle_nlp(p):
     return orc.OracleNLP(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.params, p.dissipation, p.sigma, p.elevation,
-                         ctrl_default=p.ctrl_default, q0=p.q0, u0=p.u0, du0=p.du0, kart_direct_torque=p.kart_direct_torque)
+                         ctrl_default=p.ctrl_default, q0=p.q0, u0=p.u0, du0=p.du0, kart_direct_torque=p.kart_direct_torque,
+                         node_params=getattr(p, "node_params", None))
 
 
 def equality_rows(p):
@@ -122,3 +123,21 @@ def state_control_deviation(x, x_ref, problem=None):
     D = d.reshape(-1, problem.nv)
     n_state = problem.nv - (2 if problem.form == 0 else 4)
     return float(np.max(D[:, :n_state])), float(np.max(D[:, n_state:n_state + 2]))
+
+
+def oracle_kkt(p, out):
+    """Stationarity, feasibility and complementarity of a returned point, all from the oracle's callbacks."""
+    import scipy.sparse as sp
+    from fastest_lap_b200.nlp import problem_bounds
+    x, y, zl, zu = out["x"][0], out["y"][0], out["zl"][0], out["zu"][0]
+    r = oracle_nlp(p).eval(x, y, 1.0)
+    J = sp.csr_matrix((r["jac"][2], (r["jac"][0], r["jac"][1])), shape=(p.m, p.n))
+    xl, xu, gl, gu = problem_bounds(p)
+    stat = np.abs(r["grad"] + J.T @ y - zl + zu).max()
+    g = r["g"]
+    eq = gu <= gl
+    viol_eq = np.abs(g[eq] - gl[eq]).max()
+    # (bounds are relaxed by 1e-8 max(1, |b|) as in Ipopt: a point may sit that far outside)
+    viol_bnd = max(np.maximum(gl - g, 0).max(), np.maximum(g - gu, 0).max(), np.maximum(xl - x, 0).max(), np.maximum(x - xu, 0).max())
+    comp = max(np.abs((x - xl) * zl).max(), np.abs((xu - x) * zu).max())
+    return stat, viol_eq, viol_bnd, comp

@@ -68,3 +68,28 @@ def test_trajectory_on_a_track_with_elevation():
     assert np.max(np.abs(theta + q[:, 13] - d["psi"])) <= 1e-12
     yaw = d["track_nodes"][:, 0]
     assert np.max(np.abs(d["centreline"][:, 0] - q[:, 12] * np.sin(yaw) - d["x_coord"])) > 1e-2
+
+
+def test_variable_parameter_follows_model_parameter():
+    """Model_parameter::operator()(s) (src/core/foundation/model_parameter.h:51-77): upper_bound on the mesh points, the FIRST
+    VALUE before the first point and the LAST VALUE after the last one (whatever the mesh indexes say), linear blend of the
+    two indexed values in between; a mesh may reuse a value."""
+    from fastest_lap_b200.vehicle import Vehicle, MODEL_F1
+    veh = Vehicle(MODEL_F1, workloads._vehicles()["limebeer_2014_f1"].copy())
+    values, idx, pts = [700.0, 650.0, 720.0], [1, 0, 2, 0], [100.0, 200.0, 400.0, 500.0]
+    veh.declare_variable_parameter("vehicle/chassis/mass", values, idx, pts)
+    s = np.array([0.0, 99.9, 100.0, 150.0, 200.0, 300.0, 399.9, 450.0, 500.0, 600.0])
+    got = veh.params_at(s)[:, 0]
+    # before the first point: values.front(); [100, 200): 650 -> 700; [200, 400): 700 -> 720; [400, 500): 720 -> 700; from 500: values.back()
+    expect = np.array([700.0, 700.0, 650.0, 675.0, 700.0, 710.0, 700.0 + 20.0 * 199.9 / 200.0, 710.0, 720.0, 720.0])
+    np.testing.assert_allclose(got, expect, rtol=0, atol=1e-12)
+    other = veh.params_at(s)
+    assert np.array_equal(other[:, 1:], np.tile(veh.params[1:], (len(s), 1)))          # every other parameter is constant
+    with pytest.raises(KeyError):
+        veh.declare_variable_parameter("vehicle/chassis/wings", values, idx, pts)
+    api.delete_variable("*")
+    api._table["car"] = veh.copy()
+    api.vehicle_declare_new_variable_parameter("car", "vehicle/chassis/aerodynamics/cd", "cd_a;cd_b", [0.9, 1.1], [0, 1], [0.0, 1000.0])
+    assert api._get("car").has_variable_parameters() and abs(api._get("car").params_at(np.array([500.0]))[0, 6] - 1.0) <= 1e-15
+    with pytest.raises(api.FastestLapError):
+        api.vehicle_declare_new_variable_parameter("car", "vehicle/chassis/cd", "a", [1.0], [0], [0.0])

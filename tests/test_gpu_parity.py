@@ -304,3 +304,85 @@ def test_variants_without_a_golden_match_the_oracle(name, form):
         _matrix_close(_csr(jr, jc, out["jac"][0], (q.m, q.n)), _csr(*ref["jac"], (q.m, q.n)), "jacobian", q.ncpe)
         _matrix_close(_csr(hr, hc, out["hess"][0], (q.n, q.n)), _csr(*ref["hess"], (q.n, q.n)), "hessian", q.nv, rtol=1.0e-8)
     nlp.close()
+
+
+def test_parameters_that_vary_along_the_lap():
+    """Model_parameter (src/core/foundation/model_parameter.h:51-77; evaluated per node, dynamic_model_car.hpp:62-63): mass, lift
+    and engine power declared as piecewise-linear functions of the arclength.  The kernels read one parameter vector per node
+    (fl_problem_desc::node_params): f, g, grad f, Jacobian and Hessian equal the oracle's, which evaluates every node with
+    that node's parameters; with the same vector at every node the result is bit-identical to the constant-parameter path."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.problem import LapProblem
+    from fastest_lap_b200.vehicle import Vehicle, MODEL_F1
+    p0, ex = load_golden("f1_catalunya_discrete")
+    veh = Vehicle(MODEL_F1, p0.params.copy())
+    L = p0.track_length
+    veh.declare_variable_parameter("vehicle/chassis/mass", [660.0, 700.0, 640.0], [0, 1, 2, 0], [0.0, 0.3 * L, 0.6 * L, L])
+    veh.declare_variable_parameter("vehicle/chassis/aerodynamics/cl", [3.0, 2.6], [0, 1], [0.2 * L, 0.8 * L])
+    veh.declare_variable_parameter("vehicle/rear-axle/engine/maximum-power", [735.0, 600.0], [0, 1], [0.5 * L, 0.51 * L])
+    node_params = veh.params_at(p0.s)
+    assert np.ptp(node_params[:, 0]) > 50.0
+    p = LapProblem(p0.model, p0.form, p0.closed, p0.s, p0.track_length, p0.track_nodes, p0.wl, p0.wr, node_params[0], p0.dissipation, p0.sigma,
+                   p0.elevation, node_params=node_params)
+    rng = np.random.default_rng(5)
+    x = ex["x"] * (1 + 1e-3 * rng.standard_normal(p.n))
+    lam = rng.standard_normal(p.m)
+    nlp = CollocationNLP(p)
+    out = nlp.eval_all(x, lam, 0.9)
+    ref = oracle_nlp(p).eval(x, lam, 0.9)
+    jr, jc, hr, hc = nlp.structure()
+    assert abs(out["f"][0] - ref["f"]) <= 1e-10 * abs(ref["f"])
+    assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(1.0, np.abs(ref["g"]))) <= 1e-10
+    assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(1.0, np.abs(ref["grad"]))) <= 1e-10
+    import scipy.sparse as sp
+    J = sp.coo_matrix((out["jac"][0], (jr, jc)), shape=(p.m, p.n)).tocsr()
+    Jr = sp.coo_matrix((ref["jac"][2], (ref["jac"][0], ref["jac"][1])), shape=(p.m, p.n)).tocsr()
+    assert abs(J - Jr).max() <= 1e-10 * max(1.0, abs(Jr).max())
+    H = sp.coo_matrix((out["hess"][0], (hr, hc)), shape=(p.n, p.n)).tocsr()
+    Hr = sp.coo_matrix((ref["hess"][2], (ref["hess"][0], ref["hess"][1])), shape=(p.n, p.n)).tocsr()
+    assert abs(H - Hr).max() <= 1e-8 * max(1.0, abs(Hr).max())
+    # the varying mass is felt: the constant-parameter problem gives other constraint values
+    plain = CollocationNLP(p0)
+    o0 = plain.eval_all(x, lam, 0.9)
+    assert np.max(np.abs(o0["g"][0] - out["g"][0])) > 1e-3
+    # ... and the same vector at every node is the constant-parameter problem, bit for bit
+    pc = LapProblem(p0.model, p0.form, p0.closed, p0.s, p0.track_length, p0.track_nodes, p0.wl, p0.wr, p0.params, p0.dissipation, p0.sigma,
+                    p0.elevation, node_params=np.tile(p0.params, (p0.n_points, 1)))
+    same = CollocationNLP(pc)
+    o1 = same.eval_all(x, lam, 0.9)
+    for k in ("f", "g", "grad", "jac", "hess"):
+        assert np.array_equal(o0[k], o1[k]), k
+    nlp.close(); plain.close(); same.close()
+
+
+def test_lap_with_a_mass_that_varies_along_the_lap():
+    """A lap solved with the mass declared per node (fuel burnt along the lap: 700 -> 640 kg): it converges, the CPU oracle finds
+    the KKT conditions satisfied at the returned point, and the lap time lies between the laps of the two constant masses."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_time
+    from fastest_lap_b200.problem import LapProblem
+    from fastest_lap_b200.vehicle import Vehicle, MODEL_F1
+    from tests.helpers import oracle_kkt
+    p0 = workloads.f1_catalunya(500)
+    times = {}
+    for name in ("heavy", "light", "burning"):
+        veh = Vehicle(MODEL_F1, p0.params.copy())
+        if name == "burning":
+            veh.declare_variable_parameter("vehicle/chassis/mass", [700.0, 640.0], [0, 1], [0.0, p0.track_length])
+        else:
+            veh.set_parameter("vehicle/chassis/mass", 700.0 if name == "heavy" else 640.0)
+        node_params = veh.params_at(p0.s) if veh.has_variable_parameters() else None
+        p = LapProblem(p0.model, p0.form, p0.closed, p0.s, p0.track_length, p0.track_nodes, p0.wl, p0.wr, veh.params, p0.dissipation, p0.sigma,
+                       p0.elevation, node_params=node_params)
+        nlp = CollocationNLP(p)
+        solver = LapSolver(nlp)
+        out = solver.solve(workloads.f1_start_point(p, 50.0))
+        assert out["status"][0] == 1, (name, out["status"])
+        times[name] = lap_time(p, out["x"][0], out["obj"][0])
+        if name == "burning":
+            stat, veq, vb, comp = oracle_kkt(p, out)
+            assert stat <= 1e-8 and veq <= 1e-9, (stat, veq)
+        solver.close(); nlp.close()
+    print("lap times: 700 kg %.4f s, 700 -> 640 kg along the lap %.4f s, 640 kg %.4f s" % (times["heavy"], times["burning"], times["light"]))
+    assert times["light"] < times["burning"] < times["heavy"]
