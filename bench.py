@@ -332,25 +332,23 @@ def kart_leg(args, torch, local):
 def single_lap_leg(args, torch, local):
     """One lap at a time (replicas only): BASELINE configs[0] (F1, Catalunya, 500 nodes: the reference's README example,
     "approximately 1 minute") and configs[2] (8000 nodes), solved from the steady-state start on this rank's GPU with the
-    parallel-in-the-stages factorisation; wall time through the public API."""
+    parallel-in-the-stages factorisation (the 8000-node mesh by mesh sequencing from the lap on 500 of its nodes, ipm.solve_lap);
+    wall time through the public API."""
     from fastest_lap_b200 import workloads
-    from fastest_lap_b200.nlp import CollocationNLP
-    from fastest_lap_b200.ipm import LapSolver, lap_time
+    from fastest_lap_b200.ipm import solve_lap, lap_time
     out = {}
     for name, n in (("f1_catalunya_500", 500), ("f1_catalunya_8000", args.nodes)):
         p = workloads.f1_catalunya(n)
-        nlp = CollocationNLP(p, device=local)
-        solver = LapSolver(nlp)
-        x0 = workloads.f1_start_point(p, 50.0, device=local)
-        solver.solve(x0) if n == 500 else None            # warm-up of the 500-node case (library initialisation)
+        node = workloads.f1_start_point(p, 50.0, device=local)[:p.nv]
+        if n == 500:
+            solve_lap(p, node, device=local)            # warm-up of the 500-node case (library initialisation)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        r = solver.solve(x0)
+        r, levels = solve_lap(p, node, device=local)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        out[name] = {"nodes": n, "seconds": dt, "status": int(r["status"][0]), "iterations": int(r["iters"][0]),
-                     "lap_time_s": lap_time(p, r["x"][0], r["obj"][0]), "factorisations": int(r["stats"]["factor_launches"])}
-        solver.close(); nlp.close()
+        out[name] = {"nodes": n, "seconds": dt, "status": int(r["status"][0]), "iterations": int(sum(l["iterations"] for l in levels)),
+                     "lap_time_s": lap_time(p, r["x"][0], r["obj"][0]), "levels": levels}
     out["f1_catalunya_500"]["reference_lap_time_s"] = 77.791438
     out["reference_cpu"] = "README.md:26 of the reference: approximately 1 minute for the 500-point lap"
     return out

@@ -163,8 +163,11 @@ def f1_model(q, u, P, trk):
                    Tax[l][1] + Tax[r][1],
                    -(yt[l] * Fax[l][0]) - yt[r] * Fax[r][0]))
 
-    # aerodynamics (chassis.hpp:264-288), no wind
-    av = (-vx, -vy, -w)
+    # aerodynamics (chassis.hpp:264-288).  Wind: (eastward, -northward, 0) in the absolute frame, brought to body axes with the
+    # transpose of the road frame's rotation (:269-274).  Its components along the track's tangent / normal / binormal (wt, wn,
+    # wb) are per-node constants; the yaw alpha of the car in the road frame is the only rotation left for the node program.
+    wt, wn, wb = trk.get("wt", 0.0), trk.get("wn", 0.0), trk.get("wb", 0.0)
+    av = (-vx + (ca * wt + sa * wn), -vy + (ca * wn - sa * wt), -w + wb)
     avn = sqrt(av[0] * av[0] + av[1] * av[1])
     qd = 0.5 * P["rho"] * P["cd"] * P["area"]
     Faero = [qd * av[0] * avn, qd * av[1] * avn, qd * av[2] * avn + (0.5 * P["rho"] * P["cl"] * P["area"]) * (av[0] * av[0])]
@@ -322,7 +325,11 @@ def kart_model(q, u, P, trk, direct_torque=False, curvilinear=True):
 
     domega_axle = (T_ax + sum_long_torque) / P["r_inertia"]              # axle_car_6dof.hpp:160-164
     F[2] = F[2] + m * G0                                                  # chassis_car_6dof.hpp:127
-    av = (-vx, -vy)
+    if curvilinear and trk is not None and "wt" in trk:
+        wt, wn = trk["wt"], trk["wn"]                                     # wind along the track's tangent / normal (see f1_model)
+        av = (-vx + (ca * wt + sa * wn), -vy + (ca * wn - sa * wt))
+    else:
+        av = (-vx, -vy)
     avn = sqrt(av[0] * av[0] + av[1] * av[1])
     qd = 0.5 * P["rho"] * P["cd"] * P["area"]
     Fa = (qd * av[0] * avn, qd * av[1] * avn, (0.5 * P["rho"] * P["cl"] * P["area"]) * (av[0] * av[0]))

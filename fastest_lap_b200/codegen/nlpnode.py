@@ -71,12 +71,13 @@ class NodeProgram:
         # ---- symbols
         self.x = [S("x%d" % k, "x") for k in range(self.nv)]
         P = self.P = {n: S("p_" + n, "p") for n in self.param_names}
+        # (wt, wn, wb: wind along the track's tangent, normal, binormal -- per-node constants, chassis.hpp:269-274)
         if v.elevation:
-            self.track_names = ["kx", "ky", "kz", "smu", "cmu", "sph", "cph"]
+            self.track_names = ["kx", "ky", "kz", "smu", "cmu", "sph", "cph", "wt", "wn", "wb"]
             trk = {n: S("t_" + n, "t") for n in self.track_names}
         else:
-            self.track_names = ["kz"]
-            trk = dict(kx=0.0, ky=0.0, kz=S("t_kz", "t"), smu=0.0, cmu=1.0, sph=0.0, cph=1.0)
+            self.track_names = ["kz", "wt", "wn"]
+            trk = dict(kx=0.0, ky=0.0, kz=S("t_kz", "t"), smu=0.0, cmu=1.0, sph=0.0, cph=1.0, wt=S("t_wt", "t"), wn=S("t_wn", "t"), wb=0.0)
         # per-node mesh constants: lengths of the element that ends / starts at the node; direct form: their inverses
         # (0 where the element does not exist); derivative form: total length weighting the node's control-rate penalty
         self.geom_names = ["hin", "hout"] + (["penw"] if deriv else ["ihin", "ihout"])

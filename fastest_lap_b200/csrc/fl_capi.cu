@@ -235,13 +235,22 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
         const double kx = dph - std::sin(mu) * dth;
         const double ky = std::cos(phi) * dmu + std::cos(mu) * std::sin(phi) * dth;
         const double kz = -std::sin(phi) * dmu + std::cos(mu) * std::cos(phi) * dth;
+        // wind (eastward, -northward, 0) along the track's tangent, normal and binormal (road_curvilinear.hpp:121-131,
+        // chassis.hpp:269-274): the rotation by the car's own yaw alpha is left to the node program
+        const double th = t[0], wE = steady_spec ? 0.0 : d->wind[1], wS = steady_spec ? 0.0 : -d->wind[0];
+        const double cth = std::cos(th), sth = std::sin(th), cmu_ = std::cos(mu), smu_ = std::sin(mu), cph_ = std::cos(phi), sph_ = std::sin(phi);
+        const double wt = cth * cmu_ * wE + sth * cmu_ * wS;
+        const double wn = (cth * smu_ * sph_ - sth * cph_) * wE + (sth * smu_ * sph_ + cth * cph_) * wS;
+        const double wb = (cth * smu_ * cph_ + sth * sph_) * wE + (sth * smu_ * cph_ - cth * sph_) * wS;
         int k = 0;
         if (v->IS_3D)
         {
             TC(k++, i) = kx; TC(k++, i) = ky; TC(k++, i) = kz;
-            TC(k++, i) = std::sin(mu); TC(k++, i) = std::cos(mu);
-            TC(k++, i) = std::sin(phi); TC(k++, i) = std::cos(phi);
+            TC(k++, i) = smu_; TC(k++, i) = cmu_;
+            TC(k++, i) = sph_; TC(k++, i) = cph_;
+            TC(k++, i) = wt; TC(k++, i) = wn; TC(k++, i) = wb;
         }
+        else if (v->NTRACK == 3) { TC(k++, i) = kz; TC(k++, i) = wt; TC(k++, i) = wn; }
         else
             TC(k++, i) = kz;
         const double hin = i > 0 ? d->s[i] - d->s[i - 1] : (d->closed ? L - d->s[np - 1] : 0.0);

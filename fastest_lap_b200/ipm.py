@@ -170,6 +170,44 @@ def lap_time(problem, x, obj):
     return float(obj) - pen
 
 
+def solve_lap(problem, x_start, options=None, device=0, bounds=None, coarse_nodes=500, sequence_from=3000, verbose=False):
+    """One closed lap.  Meshes of `sequence_from` nodes or more are solved by mesh sequencing: the lap on every k-th node (about
+    `coarse_nodes` of them) from `x_start`, then the full mesh from that solution interpolated to it; coarser meshes directly,
+    with the sequence as the second attempt.  (Measured on the F1 Catalunya lap, tools/mesh_study.py: from the steady-state
+    start the 8000-node lap ends in a failed line search or -- 4000 nodes -- in a slower local optimum; from the 500-node lap
+    both reach the optimum the mesh study converges to.  The solver has no restoration phase.)
+    x_start: one node's variables, replicated.  Returns (LapSolver.solve's dict, list of the levels solved)."""
+    from . import workloads
+    node = np.asarray(x_start, dtype=np.float64).ravel()[:problem.nv]
+    levels = []
+
+    def run(p, x0, bnd):
+        nlp = CollocationNLP(p, device=device)
+        solver = LapSolver(nlp, options=options, bounds=bnd)
+        out = solver.solve(x0, verbose=verbose)
+        solver.close(); nlp.close()
+        levels.append(dict(nodes=p.n_points, status=int(out["status"][0]), iterations=int(out["iters"][0])))
+        return out
+
+    def sequence():
+        every = max(2, int(round(problem.n_points / float(coarse_nodes))))
+        pc = problem.coarsened(every)
+        bc = None if bounds is None else tuple(np.asarray(b).reshape(problem.n_points, -1)[::every].ravel() for b in bounds)
+        oc = run(pc, np.tile(node, pc.n_points), bc)
+        if oc["status"][0] < 1:
+            return oc
+        return run(problem, workloads.resample_point(problem, pc.s, oc["x"][0], problem.nv), bounds)
+
+    if not problem.closed or problem.n_points < 4 * coarse_nodes // 2:
+        return run(problem, np.tile(node, problem.n_points if problem.closed else problem.n_points - 1), bounds), levels
+    if problem.n_points >= sequence_from:
+        return sequence(), levels
+    out = run(problem, np.tile(node, problem.n_points), bounds)
+    if out["status"][0] < 1:
+        out = sequence()
+    return out, levels
+
+
 def solve_sweep(problem, vehicle_params, options=None, device=0, start_speeds_kmh=(50.0, 100.0, 150.0), retry_mu_init=1.0, retry_max_iter=600):
     """Vehicle-parameter sweep: one lap per row of `vehicle_params`, all from the reference's starting point (steady state
     at start_speeds_kmh[0] replicated over the mesh, fastestlapc.cpp:1508-1545).  The interior-point method has no

@@ -27,7 +27,7 @@ class _Desc(C.Structure):
     _fields_ = [("model", C.c_int), ("form", C.c_int), ("closed", C.c_int), ("elevation", C.c_int), ("kart_direct_torque", C.c_int),
                 ("n_points", C.c_int), ("s", _dp), ("track_length", C.c_double), ("track_nodes", _dp), ("wl", _dp), ("wr", _dp),
                 ("batch", C.c_int), ("vehicle_params", _dp), ("sigma", C.c_double), ("dissipation", C.c_double * 2),
-                ("q0", _dp), ("u0", _dp), ("du0", _dp), ("ctrl_default", _dp), ("device", C.c_int), ("node_params", _dp)]
+                ("q0", _dp), ("u0", _dp), ("du0", _dp), ("ctrl_default", _dp), ("device", C.c_int), ("node_params", _dp), ("wind", C.c_double * 2)]
 
 
 def load_library():
@@ -110,6 +110,8 @@ def _describe(lib, p, vehicle_params=None, device=0):
     d.batch, d.vehicle_params, d.sigma = params.shape[0], _ptr(params), p.sigma
     d.dissipation[0], d.dissipation[1] = float(p.dissipation[0]), float(p.dissipation[1])
     d.q0, d.u0, d.du0, d.ctrl_default, d.device = _ptr(p.q0), _ptr(p.u0), _ptr(p.du0), _ptr(p.ctrl_default), int(device)
+    wind = getattr(p, "wind", (0.0, 0.0))
+    d.wind[0], d.wind[1] = float(wind[0]), float(wind[1])          # northward, eastward [m/s]
     node_params = getattr(p, "node_params", None)
     if node_params is not None:
         # parameters that vary along the lap (Model_parameter, model_parameter.h:51-77): [n_points][nvp], or [batch][n_points][nvp]

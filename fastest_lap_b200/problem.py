@@ -22,11 +22,13 @@ class LapProblem:
     _SCALARS = ("model", "form", "closed", "elevation", "track_length", "sigma", "kart_direct_torque")
 
     def __init__(self, model, form, closed, s, track_length, track_nodes, wl, wr, params, dissipation=None, sigma=0.5,
-                 elevation=False, q0=None, u0=None, du0=None, ctrl_default=None, kart_direct_torque=False, node_params=None):
+                 elevation=False, q0=None, u0=None, du0=None, ctrl_default=None, kart_direct_torque=False, node_params=None, wind=(0.0, 0.0)):
         self.model, self.form, self.closed, self.elevation = int(model), int(form), bool(closed), bool(elevation)
         # parameters that vary with the arclength (Model_parameter, src/core/foundation/model_parameter.h:51-77): one parameter
         # vector per mesh node, [n_points][n_params]; `params` is then node 0's
         self.node_params = None if node_params is None else np.ascontiguousarray(node_params, dtype=np.float64)
+        # (northward, eastward) wind velocity [m/s]: vehicle/chassis/aerodynamics/wind_velocity/... (chassis.h:276-277)
+        self.wind = (float(wind[0]), float(wind[1]))
         self.kart_direct_torque = bool(kart_direct_torque)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         self.s = f64(s)
@@ -92,7 +94,16 @@ class LapProblem:
         node_params = vehicle.params_at(s) if getattr(vehicle, "has_variable_parameters", lambda: False)() else None
         return cls(vehicle.model, form, closed, s, track.track_length, track.node_data(s), track.left_track_limit(s),
                    track.right_track_limit(s), vehicle.params if node_params is None else node_params[0], dissipation, sigma, elevation, q0, u0, du0,
-                   None, kart_direct_torque, node_params=node_params)
+                   None, kart_direct_torque, node_params=node_params, wind=getattr(vehicle, "wind", (0.0, 0.0)))
+
+    def coarsened(self, every):
+        """The same lap on every `every`-th node of the mesh (closed laps): the coarse level of a mesh sequence."""
+        if not self.closed:
+            raise ValueError("mesh sequencing is for closed laps")
+        k = slice(None, None, int(every))
+        return LapProblem(self.model, self.form, True, self.s[k], self.track_length, self.track_nodes[k], self.wl[k], self.wr[k], self.params,
+                          self.dissipation, self.sigma, self.elevation, None, None, None, self.ctrl_default, self.kart_direct_torque,
+                          node_params=None if self.node_params is None else self.node_params[k], wind=self.wind)
 
     def save_npz(self, path, **extra):
         d = {k: getattr(self, k) for k in self._ARRAYS}

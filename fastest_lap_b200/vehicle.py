@@ -44,6 +44,9 @@ KART_PARAM_PATHS = (
      "rear-axle/smooth_throttle_coeff", "rear-axle/brakes/max_torque", "rear-axle/engine/maximum-power"]
     + ["front-tire/" + p for p in _KART_TIRE] + ["rear-tire/" + p for p in _KART_TIRE])
 
+# optional parameters that are not part of the kernels' parameter vector: (northward, eastward) wind (chassis.h:276-277, default 0)
+WIND_PATHS = ("chassis/aerodynamics/wind_velocity/northward", "chassis/aerodynamics/wind_velocity/eastward")
+
 _VEC3 = {"x": 0, "y": 1, "z": 2}
 
 
@@ -66,9 +69,11 @@ class Vehicle:
         self.params = np.ascontiguousarray(params, dtype=np.float64)
         self.name = name
         self.paths = F1_PARAM_PATHS if model == MODEL_F1 else KART_PARAM_PATHS
+        self.wind = [0.0, 0.0]
 
     def copy(self):
         v = Vehicle(self.model, self.params.copy(), self.name)
+        v.wind = list(self.wind)
         v.variable = {k: tuple(np.array(a) for a in val) for k, val in getattr(self, "variable", {}).items()}
         return v
 
@@ -117,19 +122,25 @@ class Vehicle:
     def set_parameter(self, path, value):
         """Mirror of vehicle_set_parameter (fastestlapc.cpp): `path` is "vehicle/..." as in the reference."""
         key = path[len("vehicle/"):] if path.startswith("vehicle/") else path
+        if key in WIND_PATHS:
+            self.wind[WIND_PATHS.index(key)] = float(value)
+            return
         if key not in self.paths:
             raise KeyError('Parameter "%s" was not found' % path)
         self.params[self.paths.index(key)] = float(value)
 
     def get_parameter(self, path):
         key = path[len("vehicle/"):] if path.startswith("vehicle/") else path
+        if key in WIND_PATHS:
+            return float(self.wind[WIND_PATHS.index(key)])
         return float(self.params[self.paths.index(key)])
 
     def to_xml(self):
         """The vehicle as a database file (vehicle_save_as_xml of the reference): <vehicle type=...> with one leaf per
         parameter path; `vehicle_from_xml` reads it back to the same parameter vector."""
         root = ET.Element("vehicle", type="f1-3dof" if self.model == MODEL_F1 else "kart-6dof")
-        for path, value in zip(self.paths, self.params):
+        extra = [(pth, w) for pth, w in zip(WIND_PATHS, self.wind) if w != 0.0]
+        for path, value in list(zip(self.paths, self.params)) + extra:
             node = root
             for part in path.split("/"):
                 nxt = node.find(part)
@@ -156,4 +167,14 @@ def vehicle_from_xml(source, name=""):
         if v is None:
             raise ValueError('vehicle parameter "%s" is missing' % p)
         values.append(v)
-    return Vehicle(model, values, name)
+    veh = Vehicle(model, values, name)
+    for k, pth in enumerate(WIND_PATHS):
+        w = _lookup(root, pth)
+        if w is not None:
+            veh.wind[k] = w
+    # the engine as a power curve over the engine speed (rpm-data / power-data / gear-ratio, src/core/actuators/engine.hpp:17-28)
+    # interpolates with lion's sPolynomial, which is not part of the reference tree: refused rather than approximated
+    for axle in ("rear-axle", "front-axle"):
+        if root.find(axle + "/engine/rpm-data") is not None or root.find(axle + "/engine/power-data") is not None:
+            raise ValueError('engine power curves ("%s/engine/rpm-data") are not supported: only engine/maximum-power' % axle)
+    return veh

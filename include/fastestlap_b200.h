@@ -62,6 +62,8 @@ typedef struct fl_problem_desc
                                    parameters that vary with the arclength (Model_parameter::operator()(s),
                                    src/core/foundation/model_parameter.h:51-77, evaluated per node at
                                    src/core/vehicles/dynamic_model_car.hpp:62-63).  vehicle_params is then ignored.       */
+    double wind[2];             /* northward, eastward wind velocity [m/s] (vehicle/chassis/aerodynamics/wind_velocity/...,
+                                   src/core/chassis/chassis.h:276-277; enters the aerodynamic velocity, chassis.hpp:264-288) */
 } fl_problem_desc;
 
 fl_nlp* fl_nlp_create(const fl_problem_desc* desc);       /* NULL on failure */

@@ -32,6 +32,17 @@ struct TrackNode
 {
     double theta, mu, phi;        // Frenet frame Euler angles (yaw, pitch, roll)
     double dtheta, dmu, dphi;     // their arclength derivatives
+    double wind_north = 0.0, wind_east = 0.0;   // wind velocity [m/s] (chassis.h:276-277)
+    // wind (eastward, -northward, 0) along the track's tangent / normal / binormal (road_curvilinear.hpp:121-131): the rows of the
+    // transposed road-frame rotation of chassis.hpp:269-274, before the car's own yaw alpha
+    void wind_in_track_axes(double& wt, double& wn, double& wb) const
+    {
+        const double wE = wind_east, wS = -wind_north;
+        const double ct = std::cos(theta), st = std::sin(theta), cm = std::cos(mu), sm = std::sin(mu), cp = std::cos(phi), sp = std::sin(phi);
+        wt = ct * cm * wE + st * cm * wS;
+        wn = (ct * sm * sp - st * cp) * wE + (st * sm * sp + ct * cp) * wS;
+        wb = (ct * sm * cp + st * sp) * wE + (st * sm * cp - ct * sp) * wS;
+    }
 };
 
 // Vehicle parameter vector of the F1 (database/vehicles/f1/limebeer-2014-f1.xml paths in comments)
@@ -224,8 +235,10 @@ inline void f1_car(const T q[F1_NIN], const T u[F1_NCTRL], const double* P, cons
         Ta[a][2] = Tax[l][2] - yt[l] * Fax[l][0] + Tax[r][2] - yt[r] * Fax[r][0];
     }
 
-    // --- aerodynamics: chassis/chassis.hpp:264-288 (no wind)
-    const T av[3] = { -vx, -vy, -w };
+    // --- aerodynamics: chassis/chassis.hpp:264-288; wind_body = R^T (E, -N, 0), R = road frame (track frame turned by alpha)
+    double wt, wn, wb;
+    tk.wind_in_track_axes(wt, wn, wb);
+    const T av[3] = { -vx + (ca * wt + sa * wn), -vy + (ca * wn - sa * wt), -w + wb };
     const T avn = sqrt(av[0] * av[0] + av[1] * av[1]);
     const double qd = 0.5 * P[F1_RHO] * P[F1_CD] * P[F1_AREA];
     T Faero[3] = { qd * av[0] * avn, qd * av[1] * avn, qd * av[2] * avn };

@@ -92,12 +92,16 @@ inline void kart_car(const T q[KART_NIN], const T u[KART_NCTRL], const double* P
 
     // --- road
     T dtds(1.0), dr1, dr2;      // derivatives of the last two road states
+    T wind_x(0.0), wind_y(0.0); // wind velocity in body axes (chassis.hpp:269-274), curvilinear road only
     if (curvilinear)
     {
         const T& n = q[KART_IN];
         const T& alpha = q[KART_IALPHA];
         const double kz = tk.dtheta;
         const T ca = cos(alpha), sa = sin(alpha);
+        double wt, wn, wb;
+        tk.wind_in_track_axes(wt, wn, wb);
+        wind_x = ca * wt + sa * wn; wind_y = ca * wn - sa * wt;
         dtds = (1.0 - n * kz) / (vx * ca - vy * sa);       // road_curvilinear.hpp:9
         dr1 = vx * sa + vy * ca;                           // :12
         dr2 = Om - kz / dtds;                              // :15
@@ -202,7 +206,7 @@ inline void kart_car(const T q[KART_NIN], const T u[KART_NCTRL], const double* P
 
     // gravity and aerodynamics: chassis_car_6dof.hpp:127-136, chassis.hpp:264-288
     F[2] = F[2] + m * g0;
-    const T av[3] = { -vx, -vy, T(0.0) };
+    const T av[3] = { -vx + wind_x, -vy + wind_y, T(0.0) };
     const T avn = sqrt(av[0] * av[0] + av[1] * av[1]);
     const double qd = 0.5 * P[K_RHO] * P[K_CD] * P[K_AREA];
     const T Fa[3] = { qd * av[0] * avn, qd * av[1] * avn, 0.5 * P[K_RHO] * P[K_CL] * P[K_AREA] * av[0] * av[0] };

@@ -37,6 +37,7 @@ struct Desc
     const double* node_params = nullptr;   // [n_points][n_params]: parameters that vary with the arclength (Model_parameter::operator()(s),
     int n_params = 0;                      //  model_parameter.h:51-77, applied per node at dynamic_model_car.hpp:62-63), or null
     const double* params_at(int node) const { return node_params ? node_params + (size_t)node * n_params : params; }
+    double wind[2] = { 0.0, 0.0 };         // northward, eastward wind velocity [m/s] (chassis.h:276-277)
 };
 
 constexpr int MAX_ROWS = 14;
@@ -124,6 +125,7 @@ inline void eval_node(const Desc& d, const Layout& L, int i, const double* xn, N
     TrackNode tk;
     const double* t = d.track + 6 * i;
     tk.theta = t[0]; tk.mu = t[1]; tk.phi = t[2]; tk.dtheta = t[3]; tk.dmu = t[4]; tk.dphi = t[5];
+    tk.wind_north = d.wind[0]; tk.wind_east = d.wind[1];
 
     if (d.model == MODEL_F1)
     {

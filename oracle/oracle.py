@@ -22,7 +22,7 @@ class _Desc(C.Structure):
                 ("s", C.POINTER(C.c_double)), ("track_length", C.c_double), ("track", C.POINTER(C.c_double)),
                 ("params", C.POINTER(C.c_double)), ("sigma", C.c_double), ("dissipation", C.c_double * 2),
                 ("q0", C.POINTER(C.c_double)), ("u0", C.POINTER(C.c_double)), ("du0", C.POINTER(C.c_double)),
-                ("ctrl_default", C.POINTER(C.c_double)), ("node_params", C.POINTER(C.c_double))]
+                ("ctrl_default", C.POINTER(C.c_double)), ("node_params", C.POINTER(C.c_double)), ("wind", C.c_double * 2)]
 
 
 def build(force=False):
@@ -50,7 +50,7 @@ class OracleNLP:
     """The collocation NLP of one lap, evaluated on the CPU."""
 
     def __init__(self, model, form, closed, s, track_length, track_nodes, params, dissipation, sigma=0.5, elevation=False,
-                 ctrl_default=None, q0=None, u0=None, du0=None, kart_direct_torque=False, node_params=None):
+                 ctrl_default=None, q0=None, u0=None, du0=None, kart_direct_torque=False, node_params=None, wind=(0.0, 0.0)):
         self._keep = []
 
         def arr(a):
@@ -72,6 +72,7 @@ class OracleNLP:
         d.dissipation[0], d.dissipation[1] = float(dissipation[0]), float(dissipation[1])
         d.q0, d.u0, d.du0, d.ctrl_default = _dp(arr(q0)), _dp(arr(u0)), _dp(arr(du0)), _dp(arr(ctrl_default))
         d.node_params = _dp(arr(node_params))          # [n_points][n_params]: parameters that vary along the lap, or None
+        d.wind[0], d.wind[1] = float(wind[0]), float(wind[1])
         self.desc = d
         n, m, nv, ncpe = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         mj, mh = C.c_long(), C.c_long()
@@ -112,6 +113,11 @@ def triplets_to_dict(rows, cols, vals, drop_zeros=True):
     if drop_zeros:
         d = {k: v for k, v in d.items() if v != 0.0}
     return dict(d)
+
+
+def set_wind(northward=0.0, eastward=0.0):
+    """Wind used by the single-node entry points f1_car / kart_car (chassis.h:276-277)."""
+    lib().orc_set_wind(C.c_double(northward), C.c_double(eastward))
 
 
 def f1_car(q, u, params, track6=None):

@@ -25,6 +25,7 @@ struct orc_desc
     const double* du0;
     const double* ctrl_default;
     const double* node_params;     // [n_points][orc_nparams(model)] or null
+    double wind[2];                // northward, eastward [m/s]
 };
 
 static Desc to_desc(const orc_desc* c)
@@ -36,6 +37,7 @@ static Desc to_desc(const orc_desc* c)
     d.dissipation[0] = c->dissipation[0]; d.dissipation[1] = c->dissipation[1];
     d.q0 = c->q0; d.u0 = c->u0; d.du0 = c->du0; d.ctrl_default = c->ctrl_default;
     d.node_params = c->node_params; d.n_params = c->model == MODEL_F1 ? (int)F1_NPARAMS : (int)K_NPARAMS;
+    d.wind[0] = c->wind[0]; d.wind[1] = c->wind[1];
     return d;
 }
 
@@ -92,11 +94,16 @@ double orc_time_eval(const orc_desc* c, const double* x, const double* lambda, d
 
 int orc_max_threads() { return omp_get_max_threads(); }
 
+// wind used by the single-node entry points below (orc_f1_car, orc_kart_car): northward, eastward [m/s]
+static double g_wind[2] = { 0.0, 0.0 };
+void orc_set_wind(double northward, double eastward) { g_wind[0] = northward; g_wind[1] = eastward; }
+
 // One node of the F1, values only (unit-level checks against the reference's closed-form tests)
 void orc_f1_car(const double* q, const double* u, const double* P, const double* track6,
                 double* states, double* dstates, double* dtds, double* extra, double* diag /* kappa[4], lambda[4], omega_w[4], Fx[4], Fy[4], N[4] */)
 {
     TrackNode tk; tk.theta = track6[0]; tk.mu = track6[1]; tk.phi = track6[2]; tk.dtheta = track6[3]; tk.dmu = track6[4]; tk.dphi = track6[5];
+    tk.wind_north = g_wind[0]; tk.wind_east = g_wind[1];
     F1Out<double> o;
     f1_car<double>(q, u, P, tk, o);
     for (int i = 0; i < F1_NIN; ++i) { states[i] = o.states[i]; dstates[i] = o.dstates[i]; }
@@ -114,6 +121,7 @@ void orc_kart_car(const double* q, const double* u, const double* P, const doubl
                   double* states, double* dstates, double* dtds, double* extra, double* diag /* kappa[4], lambda[4], N[4], Fx[4], Fy[4], w[4], force[3], torque[3] */)
 {
     TrackNode tk; tk.theta = track6[0]; tk.mu = track6[1]; tk.phi = track6[2]; tk.dtheta = track6[3]; tk.dmu = track6[4]; tk.dphi = track6[5];
+    tk.wind_north = g_wind[0]; tk.wind_east = g_wind[1];
     KartOut<double> o;
     kart_car<double>(q, u, P, tk, direct_torque != 0, curvilinear != 0, o);
     for (int i = 0; i < KART_NIN; ++i) { states[i] = o.states[i]; dstates[i] = o.dstates[i]; }

@@ -15,7 +15,7 @@ def load_golden(name):
 def oracle_nlp(p):
     return orc.OracleNLP(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.params, p.dissipation, p.sigma, p.elevation,
                          ctrl_default=p.ctrl_default, q0=p.q0, u0=p.u0, du0=p.du0, kart_direct_torque=p.kart_direct_torque,
-                         node_params=getattr(p, "node_params", None))
+                         node_params=getattr(p, "node_params", None), wind=getattr(p, "wind", (0.0, 0.0)))
 
 
 def equality_rows(p):
@@ -66,7 +66,7 @@ def truth_node(p, x, lam, obj, node, digits=40):
     th, mu, ph, dth, dmu, dph = p.track_nodes[node]
     trk = dict(kx=dph - np.sin(mu) * dth, ky=np.cos(ph) * dmu + np.cos(mu) * np.sin(ph) * dth, kz=-np.sin(ph) * dmu + np.cos(mu) * np.cos(ph) * dth,
                smu=np.sin(mu), cmu=np.cos(mu), sph=np.sin(ph), cph=np.cos(ph), hin=hin, hout=hout,
-               ihin=1.0 / hin if hin > 0 else 0.0, ihout=1.0 / hout if hout > 0 else 0.0)
+               ihin=1.0 / hin if hin > 0 else 0.0, ihout=1.0 / hout if hout > 0 else 0.0, wt=0.0, wn=0.0, wb=0.0)      # (no wind in the golden runs)
     if p.form != 0:
         penw = 0.0
         for e in range(p.n_elements):

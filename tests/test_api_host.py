@@ -93,3 +93,21 @@ def test_variable_parameter_follows_model_parameter():
     assert api._get("car").has_variable_parameters() and abs(api._get("car").params_at(np.array([500.0]))[0, 6] - 1.0) <= 1e-15
     with pytest.raises(api.FastestLapError):
         api.vehicle_declare_new_variable_parameter("car", "vehicle/chassis/cd", "a", [1.0], [0], [0.0])
+
+
+def test_wind_and_engine_curve_in_the_vehicle_file(tmp_path):
+    """Optional parameters outside the kernels' parameter vector: the wind is read (default 0) and settable by its reference
+    path; an engine given as a power curve is refused by name (lion's sPolynomial is not in the reference tree), never dropped."""
+    from fastest_lap_b200.vehicle import Vehicle, vehicle_from_xml, MODEL_F1
+    veh = Vehicle(MODEL_F1, workloads._vehicles()["limebeer_2014_f1"].copy())
+    assert veh.wind == [0.0, 0.0]
+    veh.set_parameter("vehicle/chassis/aerodynamics/wind_velocity/northward", 5.0)
+    veh.set_parameter("vehicle/chassis/aerodynamics/wind_velocity/eastward", -3.0)
+    back = vehicle_from_xml(veh.to_xml())
+    assert back.wind == [5.0, -3.0] and back.get_parameter("vehicle/chassis/aerodynamics/wind_velocity/eastward") == -3.0
+    assert np.array_equal(back.params, veh.params)
+    xml = veh.to_xml().replace("<maximum-power>", "<rpm-data>1000 2000</rpm-data><maximum-power>", 1)
+    with pytest.raises(ValueError, match="power curves"):
+        vehicle_from_xml(xml)
+    with pytest.raises(KeyError):
+        veh.set_parameter("vehicle/chassis/aerodynamics/wind_velocity/upward", 1.0)

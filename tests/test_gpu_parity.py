@@ -386,3 +386,33 @@ def test_lap_with_a_mass_that_varies_along_the_lap():
         solver.close(); nlp.close()
     print("lap times: 700 kg %.4f s, 700 -> 640 kg along the lap %.4f s, 640 kg %.4f s" % (times["heavy"], times["burning"], times["light"]))
     assert times["light"] < times["burning"] < times["heavy"]
+
+
+@pytest.mark.parametrize("case", ["f1_catalunya_discrete", "f1_catalunya_3d", "kart_vendrell", "f1_catalunya_chicane_derivative"])
+def test_wind(case):
+    """vehicle/chassis/aerodynamics/wind_velocity/{northward, eastward} (chassis.h:276-277; chassis.hpp:264-288): callbacks with a
+    wind of (12, -7) m/s equal the oracle's (pinned on the reference's closed-form test in tests/test_oracle_golden.py) on flat
+    and 3-D tracks, both models and forms; and they differ from the calm ones."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    import copy, scipy.sparse as sp
+    p, ex = load_golden(case)
+    pw = copy.copy(p)
+    pw.wind = (12.0, -7.0)
+    rng = np.random.default_rng(11)
+    x = ex["x"] * (1 + 1e-3 * rng.standard_normal(p.n))
+    lam = rng.standard_normal(p.m)
+    nlp, calm = CollocationNLP(pw), CollocationNLP(p)
+    out, out0 = nlp.eval_all(x, lam, 1.0), calm.eval_all(x, lam, 1.0)
+    ref = oracle_nlp(pw).eval(x, lam, 1.0)
+    jr, jc, hr, hc = nlp.structure()
+    assert abs(out["f"][0] - ref["f"]) <= 1e-10 * abs(ref["f"])
+    assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(1.0, np.abs(ref["g"]))) <= 1e-10
+    assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(1.0, np.abs(ref["grad"]))) <= 1e-10
+    J = sp.coo_matrix((out["jac"][0], (jr, jc)), shape=(p.m, p.n)).tocsr()
+    Jr = sp.coo_matrix((ref["jac"][2], (ref["jac"][0], ref["jac"][1])), shape=(p.m, p.n)).tocsr()
+    assert abs(J - Jr).max() <= 1e-10 * max(1.0, abs(Jr).max())
+    H = sp.coo_matrix((out["hess"][0], (hr, hc)), shape=(p.n, p.n)).tocsr()
+    Hr = sp.coo_matrix((ref["hess"][2], (ref["hess"][0], ref["hess"][1])), shape=(p.n, p.n)).tocsr()
+    assert abs(H - Hr).max() <= 1e-8 * max(1.0, abs(Hr).max())
+    assert np.max(np.abs(out["g"][0] - out0["g"][0])) > 1e-4
+    nlp.close(); calm.close()

@@ -87,3 +87,42 @@ def test_hessian_matches_finite_differences_of_gradient():
         e = np.zeros(p.n); e[k] = h
         col = (grad_lagr(x + e) - grad_lagr(x - e)) / (2 * h)
         assert np.abs(col - H[:, k]).max() <= 2.0e-6 * max(1.0, np.abs(H[:, k]).max())
+
+
+def test_wind_in_the_aerodynamic_force():
+    """chassis_car_3dof_test.cpp:296-336 (aerodynamic_force_wind): with a northward wind of 50 km/h and an eastward one of 30 km/h
+    the wind in body axes is (E cos(psi) - N sin(psi), -N cos(psi) - E sin(psi)), the aerodynamic velocity -(u, v) + wind, drag
+    0.5 rho cd A |va| va and lift 0.5 rho cl A va_x^2.  The oracle's F1 node is checked through its accelerations: the wind
+    changes nothing but the aerodynamic force, so m (du, dv)(wind) - m (du, dv)(calm) is the change of the drag, and the
+    change of the vertical force the change of the lift.  psi = track heading + alpha."""
+    from oracle import oracle as orc
+    from fastest_lap_b200 import workloads
+    P = workloads._vehicles()["limebeer_2014_f1"].copy()
+    KMH, DEG = 1.0 / 3.6, np.pi / 180.0
+    N, E = 50.0 * KMH, 30.0 * KMH
+    theta, alpha = 35.0 * DEG, -20.0 * DEG
+    psi = theta + alpha
+    u, v = 60.0, 1.5
+    q = np.array([0.01, 0.01, 0.02, 0.02, u, v, 0.1, -0.25, -0.25, -0.3, -0.3, 0.0, 0.5, alpha])
+    ctl = np.array([0.02, 0.0, 0.3, P[18]])
+    track6 = np.array([theta, 0.0, 0.0, 0.01, 0.0, 0.0])
+    orc.set_wind(0.0, 0.0)
+    calm = orc.f1_car(q, ctl, P, track6)
+    orc.set_wind(N, E)
+    wind = orc.f1_car(q, ctl, P, track6)
+    orc.set_wind(0.0, 0.0)
+    m, rho, A, cd, cl = P[0], P[4], P[5], P[6], P[7]
+    wx, wy = E * np.cos(psi) - N * np.sin(psi), -N * np.cos(psi) - E * np.sin(psi)
+
+    def aero(vax, vay):
+        nrm = np.hypot(vax, vay)
+        return 0.5 * rho * cd * A * nrm * vax, 0.5 * rho * cd * A * nrm * vay, 0.5 * rho * cl * A * vax * vax
+    d0, d1 = aero(-u, -v), aero(-u + wx, -v + wy)
+    # dstates are s-derivatives: time derivatives times dt/ds (the same in both evaluations)
+    du = (wind["dstates"][4] - calm["dstates"][4]) / calm["dtds"]
+    dv = (wind["dstates"][5] - calm["dstates"][5]) / calm["dtds"]
+    dw = (wind["dstates"][7] - calm["dstates"][7]) / calm["dtds"] * 9.81          # the vertical equation is scaled by 1 / g0
+    assert abs(m * du - (d1[0] - d0[0])) <= 2e-11 * max(1.0, abs(d1[0]))
+    assert abs(m * dv - (d1[1] - d0[1])) <= 2e-11 * max(1.0, abs(d1[1]))
+    assert abs(m * dw - (d1[2] - d0[2])) <= 2e-9 * max(1.0, abs(d1[2]))
+    assert abs(d1[0] - d0[0]) > 100.0          # the wind is felt

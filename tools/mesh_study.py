@@ -9,17 +9,23 @@ from fastest_lap_b200.ipm import LapSolver, lap_time
 from tests.helpers import oracle_kkt
 
 
-def study(nodes, refine=False, verbose=True):
+def study(nodes, refine=False, verbose=True, sequencing=False):
     """refine: every mesh after the first starts from the previous mesh's solution interpolated to it (mesh refinement);
-    otherwise every mesh starts from the steady state at 50 km/h, the reference's starting point."""
+    sequencing: ipm.solve_lap (meshes of 3000 nodes or more start from the lap on ~500 of their nodes); otherwise every mesh
+    starts from the steady state at 50 km/h, the reference's starting point."""
+    from fastest_lap_b200.ipm import solve_lap
     rows, prev = [], None
     for n in nodes:
         p = workloads.f1_catalunya(n)
         nlp = CollocationNLP(p)
         s = LapSolver(nlp)
         t0 = time.time()
-        x0 = workloads.resample_point(p, prev[0].s, prev[1], p.nv) if (refine and prev is not None) else workloads.f1_start_point(p, 50.0)
-        out = s.solve(x0)
+        if sequencing:
+            out, levels = solve_lap(p, workloads.f1_start_point(p, 50.0)[:p.nv])
+            out["iters"][0] = sum(l["iterations"] for l in levels)
+        else:
+            x0 = workloads.resample_point(p, prev[0].s, prev[1], p.nv) if (refine and prev is not None) else workloads.f1_start_point(p, 50.0)
+            out = s.solve(x0)
         dt = time.time() - t0
         stat, veq, vb, comp = oracle_kkt(p, out)
         lt = lap_time(p, out["x"][0], out["obj"][0])
@@ -35,8 +41,9 @@ def study(nodes, refine=False, verbose=True):
 
 if __name__ == "__main__":
     nodes = [int(a) for a in sys.argv[1:]] or [500, 1000, 2000, 4000, 8000]
-    for refine in (False, True):
-        print("---- every mesh from the steady-state start" if not refine else "---- every mesh from the previous mesh's solution")
-        rows = study(nodes, refine)
+    for mode in ("steady", "refine", "sequencing"):
+        print({"steady": "---- every mesh from the steady-state start", "refine": "---- every mesh from the previous mesh's solution",
+               "sequencing": "---- ipm.solve_lap: meshes of 3000 nodes or more from the lap on ~500 of their nodes"}[mode])
+        rows = study(nodes, mode == "refine", sequencing=mode == "sequencing")
         lts = [r["lap_time"] for r in rows]
         print("differences between consecutive meshes [ms]:", ["%.2f" % (1e3 * (b - a)) for a, b in zip(lts[:-1], lts[1:])])
