@@ -120,6 +120,25 @@ def track_from_xml(source, name="", use_kerbs=True):
     return Track(s, x, y, z, yaw, pitch, roll, yaw_dot, dpitch, droll, nl, nr, length, ttype == "closed", elev, name)
 
 
+def track_to_xml(track):
+    """The track as a database file of the reference's discrete format (the one track_from_xml and the C entry
+    create_track_from_xml read: track_by_polynomial.hpp:78-153)."""
+    n = track.n_points
+    fmt = lambda a: ", ".join(repr(float(v)) for v in np.asarray(a)[:n])
+    elev = track.with_elevation
+    root = ET.Element("circuit", format="discrete", type="closed" if track.closed else "open", dimensions="3" if elev else "2")
+    ET.SubElement(ET.SubElement(root, "header"), "track_length").text = repr(float(track.track_length))
+    data = ET.SubElement(root, "data", number_of_points=str(n))
+    ET.SubElement(data, "arclength").text = fmt(track.s_data)
+    cl = ET.SubElement(data, "centerline")
+    ET.SubElement(cl, "x").text = fmt(track._a["x"]); ET.SubElement(cl, "y").text = fmt(track._a["y"])
+    if elev:
+        ET.SubElement(cl, "z").text = fmt(track._a["z"])
+    for tag, key in (("yaw", "yaw"), ("yaw_dot", "yaw_dot"), ("nl", "nl"), ("nr", "nr")) + ((("pitch", "pitch"), ("roll", "roll"), ("dpitch_dot", "dpitch"), ("droll_dot", "droll")) if elev else ()):
+        ET.SubElement(data, tag).text = fmt(track._a[key])
+    return ET.tostring(root, encoding="unicode")
+
+
 _NPZ_KEYS = ("x", "y", "z", "yaw", "pitch", "roll", "yaw_dot", "dpitch", "droll", "nl", "nr")
 
 

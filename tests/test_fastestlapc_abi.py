@@ -1,0 +1,180 @@
+"""The reference's C API (include/fastestlapc.h <- src/main/c/fastestlapc.h:28-107) exported by libfastestlap_b200.so: bound
+with ctypes exactly as the reference's Python module binds libfastestlapc (src/main/python/fastest_lap.py:10-14 and the
+wrappers below it: c_char_p names, c_double arrays), host-side entries on the CPU, the README example on the GPU."""
+import ctypes as c
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fastest_lap_b200 import build
+    L = c.CDLL(build.build())
+    # fastest_lap.py:12-14
+    L.download_scalar.restype = c.c_double
+    L.track_download_length.restype = c.c_double
+    L.vehicle_type_get_sizes.argtypes = [c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int), c.c_char_p]
+    L.fastestlapc_last_error.restype = c.c_char_p
+    L.delete_variable(b"*")
+    return L
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    """Vehicle / track database files rebuilt from the packaged data (the reference's database is not on the GPU box)."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.vehicle import Vehicle, MODEL_F1, MODEL_KART
+    from fastest_lap_b200.track import track_from_npz, track_to_xml
+    d = tmp_path_factory.mktemp("db")
+    veh = workloads._vehicles()
+    out = {}
+    for name, model, key in (("f1", MODEL_F1, "limebeer_2014_f1"), ("kart", MODEL_KART, "roberto_lot_kart_2016")):
+        out[name] = str(d / (name + ".xml"))
+        open(out[name], "w").write(Vehicle(model, veh[key]).to_xml())
+    data = os.path.join(os.path.dirname(workloads.__file__), "data")
+    for name in ("catalunya", "vendrell"):
+        out[name] = str(d / (name + ".xml"))
+        open(out[name], "w").write(track_to_xml(track_from_npz(os.path.join(data, name + ".npz"))))
+    return out
+
+
+def b(s):
+    return c.c_char_p(s.encode("utf-8"))
+
+
+def err(lib):
+    return lib.fastestlapc_last_error().decode()
+
+
+def test_library_exports_the_reference_c_api(lib):
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fastestlapc.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b([a-z_]+)\s*\(", text)) - {"defined"})
+    expected = {"set_print_level", "print_variables", "print_variable", "print_variable_to_string", "create_vehicle_from_xml", "create_vehicle_empty",
+                "create_track_from_xml", "create_vector", "create_scalar", "copy_variable", "move_variable", "delete_variable", "variable_type",
+                "download_scalar", "download_vector_size", "download_vector", "vehicle_type_get_sizes", "vehicle_type_get_names", "vehicle_get_output",
+                "vehicle_save_as_xml", "track_download_number_of_points", "track_download_data", "track_download_length", "vehicle_set_parameter",
+                "vehicle_declare_new_constant_parameter", "vehicle_declare_new_variable_parameter", "vehicle_change_track",
+                "track_set_track_limit_correction", "steady_state", "propagate_vehicle", "gg_diagram", "optimal_laptime", "circuit_preprocessor"}
+    assert expected <= set(names), expected - set(names)          # the 33 functions of fastestlapc.h:28-107
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_tables_and_loaders_on_the_host(lib, files, tmp_path):
+    lib.delete_variable(b"*")
+    # scalars and vectors
+    lib.create_scalar(b("a/k"), c.c_double(2.5))
+    v = (c.c_double * 3)(1.0, 2.0, 3.0)
+    lib.create_vector(b("a/v"), c.c_int(3), v)
+    assert lib.download_scalar(b("a/k")) == 2.5 and lib.download_vector_size(b("a/v")) == 3
+    back = (c.c_double * 3)()
+    lib.download_vector(back, c.c_int(3), b("a/v"))
+    assert list(back) == [1.0, 2.0, 3.0]
+    lib.create_scalar(b("a/k"), c.c_double(1.0))
+    assert "already exists" in err(lib)
+    lib.copy_variable(b("a/v"), b("b/v")); lib.move_variable(b("a/k"), b("b/k"))
+    assert lib.download_scalar(b("b/k")) == 2.5 and lib.download_vector_size(b("b/v")) == 3
+    lib.download_scalar(b("a/k"))
+    assert "does not exist" in err(lib)
+    lib.delete_variable(b("b/*"))
+    lib.download_vector_size(b("b/v"))
+    assert "does not exist" in err(lib)
+    # vehicles
+    lib.create_vehicle_from_xml(b("car"), b(files["f1"]))
+    assert err(lib) == ""
+    buf = c.create_string_buffer(64)
+    lib.variable_type(buf, c.c_int(64), b("car"))
+    assert buf.value == b"f1-3dof"
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/mass"), c.c_double(700.0))
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/wings"), c.c_double(1.0))
+    assert "was not found" in err(lib)
+    out = str(tmp_path / "car.xml")
+    lib.vehicle_save_as_xml(b("car"), b(out))
+    from fastest_lap_b200.vehicle import vehicle_from_xml
+    from fastest_lap_b200 import workloads
+    again = vehicle_from_xml(out)
+    ref = workloads._vehicles()["limebeer_2014_f1"].copy(); ref[0] = 700.0
+    assert np.array_equal(again.params, ref)
+    ni, nc, no = c.c_int(), c.c_int(), c.c_int()
+    lib.vehicle_type_get_sizes(c.byref(ni), c.byref(nc), c.byref(no), b("kart-6dof"))
+    assert (ni.value, nc.value, no.value) == (13, 2, 4)
+    vals, idx, pts = (c.c_double * 2)(700.0, 640.0), (c.c_int * 2)(0, 1), (c.c_double * 2)(0.0, 4000.0)
+    lib.vehicle_declare_new_variable_parameter(b("car"), b("vehicle/chassis/mass"), b("m0;m1"), c.c_int(2), vals, c.c_int(2), idx, pts)
+    assert err(lib) == ""
+    # tracks
+    lib.create_track_from_xml(b("catalunya"), b(files["catalunya"]))
+    assert err(lib) == ""
+    n = lib.track_download_number_of_points(b("catalunya"))
+    from fastest_lap_b200.track import track_from_npz
+    trk = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"))
+    assert n == trk.n_points and abs(lib.track_download_length(b("catalunya")) - trk.track_length) == 0.0
+    data = (c.c_double * n)()
+    for key, mine in (("arclength", trk.s_data), ("centerline.x", trk("x", trk.s_data)), ("heading-angle", trk("yaw", trk.s_data)),
+                      ("distance-left-boundary", trk("nl", trk.s_data))):
+        lib.track_download_data(data, b("catalunya"), c.c_int(n), b(key))
+        assert np.array_equal(np.array(data), mine), key
+    lib.track_download_data(data, b("catalunya"), c.c_int(n), b("left.x"))
+    th, x, nl = trk("yaw", trk.s_data), trk("x", trk.s_data), trk("nl", trk.s_data)
+    np.testing.assert_allclose(np.array(data), x + nl * np.sin(th), rtol=0, atol=1e-12)
+    lib.track_download_data(data, b("catalunya"), c.c_int(n), b("banking"))
+    assert "is not valid" in err(lib)
+    lib.vehicle_change_track(b("car"), b("monza"))
+    assert "does not exist" in err(lib)
+    lib.circuit_preprocessor(b("<options/>"))
+    assert "not part of the B200 path" in err(lib)
+    lib.delete_variable(b"*")
+
+
+@pytest.mark.gpu
+def test_readme_example_through_the_c_api(lib, files):
+    """The reference's README example (limebeer-2014-f1, Catalunya, 500 points) exactly as fastest_lap.py drives libfastestlapc:
+    create_vehicle_from_xml, create_track_from_xml, optimal_laptime(vehicle, track, s, options), download_*: lap time
+    77.791438 s (f1_optimal_laptime_catalunya_discrete.xml of the reference, Ixx = Iyy = 0 as in its test)."""
+    lib.delete_variable(b"*")
+    lib.create_vehicle_from_xml(b("car"), b(files["f1"]))
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/inertia/Ixx"), c.c_double(0.0))
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/inertia/Iyy"), c.c_double(0.0))
+    lib.create_track_from_xml(b("catalunya"), b(files["catalunya"]))
+    L = lib.track_download_length(b("catalunya"))
+    s = np.linspace(0.0, L, 501)[:-1]
+    c_s = (c.c_double * len(s))(*s)
+    options = "<options><output_variables><prefix>run/</prefix></output_variables><print_level>0</print_level></options>"
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b(options))
+    assert err(lib) == ""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "f1_catalunya_discrete.npz"))
+    assert abs(lib.download_scalar(b("run/laptime")) - float(gold["laptime"])) <= 1e-6 * float(gold["laptime"])
+    assert lib.download_vector_size(b("run/chassis.velocity.x")) == 500
+    u = (c.c_double * 500)()
+    lib.download_vector(u, c.c_int(500), b("run/chassis.velocity.x"))
+    assert np.max(np.abs(np.array(u) - gold["x"].reshape(500, 15)[:, 4])) <= 1e-4
+    t = (c.c_double * 500)()
+    lib.download_vector(t, c.c_int(500), b("run/time"))
+    assert np.max(np.abs(np.array(t) - gold["time"])) <= 1e-5
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><integral_constraints><x><upper_bound>1</upper_bound></x></integral_constraints></options>"))
+    assert "not supported" in err(lib)
+    lib.delete_variable(b"*")
+
+
+@pytest.mark.gpu
+def test_gg_diagram_through_the_c_api(lib, files):
+    """gg_diagram(ay, ax_max, ax_min, vehicle, v, n) (fastestlapc.h:103) for the kart at 70 km/h: the envelope equals the Python
+    surface's (same sequence of GPU solves), in m/s2 as the reference's C entry returns it."""
+    from fastest_lap_b200 import gg, workloads
+    lib.delete_variable(b"*")
+    lib.create_vehicle_from_xml(b("kart"), b(files["kart"]))
+    n = 16
+    ay, amax, amin = (c.c_double * n)(), (c.c_double * n)(), (c.c_double * n)()
+    lib.gg_diagram(ay, amax, amin, b("kart"), c.c_double(70.0 / 3.6), c.c_int(n))
+    assert err(lib) == ""
+    r = gg.gg_diagram(workloads._vehicles()["roberto_lot_kart_2016"], np.array([70.0 / 3.6]), n_lat=n)
+    assert r["ax_max_solved"].all() and r["ax_min_solved"].all()
+    np.testing.assert_allclose(np.array(ay), r["ay"][0], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(np.array(amax), r["ax_max"][0], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(np.array(amin), r["ax_min"][0], rtol=0, atol=1e-6)
+    assert np.all(np.array(amax) >= np.array(amin) - 1e-9)
+    lib.delete_variable(b"*")
