@@ -728,7 +728,7 @@ static int ensure_values(fl_nlp* h)
     return 1;
 }
 
-int fl_eval_f(int n, const double* x, int new_x, double* obj_value, void* ud)
+bool fl_eval_f(int n, double* x, bool new_x, double* obj_value, void* ud)
 {
     fl_nlp* h = (fl_nlp*)ud;
     if (!upload_x(h, n, x, new_x) || !ensure_values(h)) return 0;
@@ -737,7 +737,7 @@ int fl_eval_f(int n, const double* x, int new_x, double* obj_value, void* ud)
     return 1;
 }
 
-int fl_eval_g(int n, const double* x, int new_x, int m, double* g, void* ud)
+bool fl_eval_g(int n, double* x, bool new_x, int m, double* g, void* ud)
 {
     fl_nlp* h = (fl_nlp*)ud;
     if (m != h->P.m) return fail("eval_g: wrong number of constraints") ? 1 : 0;
@@ -755,7 +755,7 @@ static int ensure_jac(fl_nlp* h)
     return 1;
 }
 
-int fl_eval_grad_f(int n, const double* x, int new_x, double* grad_f, void* ud)
+bool fl_eval_grad_f(int n, double* x, bool new_x, double* grad_f, void* ud)
 {
     fl_nlp* h = (fl_nlp*)ud;
     if (!upload_x(h, n, x, new_x) || !ensure_jac(h)) return 0;
@@ -764,7 +764,7 @@ int fl_eval_grad_f(int n, const double* x, int new_x, double* grad_f, void* ud)
     return 1;
 }
 
-int fl_eval_jac_g(int n, const double* x, int new_x, int m, int nele_jac, int* iRow, int* jCol, double* values, void* ud)
+bool fl_eval_jac_g(int n, double* x, bool new_x, int m, int nele_jac, int* iRow, int* jCol, double* values, void* ud)
 {
     fl_nlp* h = (fl_nlp*)ud;
     if (nele_jac != (int)h->P.nnz_jac || m != h->P.m) return fail("eval_jac_g: wrong sizes") ? 1 : 0;
@@ -775,7 +775,7 @@ int fl_eval_jac_g(int n, const double* x, int new_x, int m, int nele_jac, int* i
     return 1;
 }
 
-int fl_eval_h(int n, const double* x, int new_x, double obj_factor, int m, const double* lambda, int new_lambda,
+bool fl_eval_h(int n, double* x, bool new_x, double obj_factor, int m, double* lambda, bool new_lambda,
               int nele_hess, int* iRow, int* jCol, double* values, void* ud)
 {
     fl_nlp* h = (fl_nlp*)ud;

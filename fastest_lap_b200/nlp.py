@@ -55,11 +55,14 @@ def load_library():
     lib.fl_nlp_ops_per_node.argtypes = [C.c_void_p, _ip]
     lib.fl_nlp_workspace_slots.argtypes = [C.c_void_p, _ip, _ip]
     lib.fl_eval_all.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp]
-    lib.fl_eval_f.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_void_p]
-    lib.fl_eval_grad_f.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_void_p]
-    lib.fl_eval_g.argtypes = [C.c_int, _dp, C.c_int, C.c_int, _dp, C.c_void_p]
-    lib.fl_eval_jac_g.argtypes = [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, C.c_void_p]
-    lib.fl_eval_h.argtypes = [C.c_int, _dp, C.c_int, C.c_double, C.c_int, _dp, C.c_int, C.c_int, _ip, _ip, _dp, C.c_void_p]
+    # the signatures of Ipopt's Eval_*_CB (bool in, bool out)
+    lib.fl_eval_f.argtypes = [C.c_int, _dp, C.c_bool, _dp, C.c_void_p]
+    lib.fl_eval_grad_f.argtypes = [C.c_int, _dp, C.c_bool, _dp, C.c_void_p]
+    lib.fl_eval_g.argtypes = [C.c_int, _dp, C.c_bool, C.c_int, _dp, C.c_void_p]
+    lib.fl_eval_jac_g.argtypes = [C.c_int, _dp, C.c_bool, C.c_int, C.c_int, _ip, _ip, _dp, C.c_void_p]
+    lib.fl_eval_h.argtypes = [C.c_int, _dp, C.c_bool, C.c_double, C.c_int, _dp, C.c_bool, C.c_int, _ip, _ip, _dp, C.c_void_p]
+    for fn in (lib.fl_eval_f, lib.fl_eval_grad_f, lib.fl_eval_g, lib.fl_eval_jac_g, lib.fl_eval_h):
+        fn.restype = C.c_bool
     for name in ("fl_dev_x", "fl_dev_lambda", "fl_dev_f", "fl_dev_g", "fl_dev_grad", "fl_dev_jac", "fl_dev_hess", "fl_nlp_stream"):
         getattr(lib, name).restype = C.c_void_p
         getattr(lib, name).argtypes = [C.c_void_p]
@@ -244,32 +247,32 @@ class CollocationNLP:
     def eval_f(self, x, new_x=True):
         v = C.c_double()
         x = np.ascontiguousarray(x, dtype=np.float64)
-        self._check(self._lib.fl_eval_f(self.n, _ptr(x), int(new_x), C.byref(v), self._h), "fl_eval_f")
+        self._check(self._lib.fl_eval_f(self.n, _ptr(x), bool(new_x), C.byref(v), self._h), "fl_eval_f")
         return v.value
 
     def eval_g(self, x, new_x=True):
         g = np.empty(self.m)
         x = np.ascontiguousarray(x, dtype=np.float64)
-        self._check(self._lib.fl_eval_g(self.n, _ptr(x), int(new_x), self.m, _ptr(g), self._h), "fl_eval_g")
+        self._check(self._lib.fl_eval_g(self.n, _ptr(x), bool(new_x), self.m, _ptr(g), self._h), "fl_eval_g")
         return g
 
     def eval_grad_f(self, x, new_x=True):
         g = np.empty(self.n)
         x = np.ascontiguousarray(x, dtype=np.float64)
-        self._check(self._lib.fl_eval_grad_f(self.n, _ptr(x), int(new_x), _ptr(g), self._h), "fl_eval_grad_f")
+        self._check(self._lib.fl_eval_grad_f(self.n, _ptr(x), bool(new_x), _ptr(g), self._h), "fl_eval_grad_f")
         return g
 
     def eval_jac_g(self, x, new_x=True):
         v = np.empty(self.nnz_jac)
         x = np.ascontiguousarray(x, dtype=np.float64)
-        self._check(self._lib.fl_eval_jac_g(self.n, _ptr(x), int(new_x), self.m, self.nnz_jac, None, None, _ptr(v), self._h), "fl_eval_jac_g")
+        self._check(self._lib.fl_eval_jac_g(self.n, _ptr(x), bool(new_x), self.m, self.nnz_jac, None, None, _ptr(v), self._h), "fl_eval_jac_g")
         return v
 
     def eval_h(self, x, lam, obj_factor=1.0, new_x=True):
         v = np.empty(self.nnz_hess)
         x = np.ascontiguousarray(x, dtype=np.float64)
         lam = np.ascontiguousarray(lam, dtype=np.float64)
-        self._check(self._lib.fl_eval_h(self.n, _ptr(x), int(new_x), float(obj_factor), self.m, _ptr(lam), 1, self.nnz_hess, None, None, _ptr(v), self._h),
+        self._check(self._lib.fl_eval_h(self.n, _ptr(x), bool(new_x), float(obj_factor), self.m, _ptr(lam), True, self.nnz_hess, None, None, _ptr(v), self._h),
                     "fl_eval_h")
         return v
 

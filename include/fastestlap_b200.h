@@ -20,6 +20,9 @@
 
 #include <stddef.h>
 
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -108,13 +111,16 @@ void fl_nlp_workspace_slots(const fl_nlp* nlp, int* n_values, int* n_checkpoints
 /* fp64 operations per node of each pass (values, jac, hess, all): the algorithmic work the roofline is quoted on */
 void fl_nlp_ops_per_node(const fl_nlp* nlp, int ops[4]);
 
-/* Ipopt C-interface callbacks (problem 0 of the batch); user_data = fl_nlp*. */
-int fl_eval_f     (int n, const double* x, int new_x, double* obj_value, void* user_data);
-int fl_eval_grad_f(int n, const double* x, int new_x, double* grad_f, void* user_data);
-int fl_eval_g     (int n, const double* x, int new_x, int m, double* g, void* user_data);
-int fl_eval_jac_g (int n, const double* x, int new_x, int m, int nele_jac, int* iRow, int* jCol, double* values, void* user_data);
-int fl_eval_h     (int n, const double* x, int new_x, double obj_factor, int m, const double* lambda, int new_lambda,
-                   int nele_hess, int* iRow, int* jCol, double* values, void* user_data);
+/* Ipopt C-interface callbacks (problem 0 of the batch); user_data = fl_nlp*.  The signatures are those of Ipopt 3.14's
+ * IpStdCInterface.h (Eval_F_CB, Eval_Grad_F_CB, Eval_G_CB, Eval_Jac_G_CB, Eval_H_CB: ipindex = int, ipnumber = double, C99 bool;
+ * x and lambda are not const there), so the five functions can be handed to CreateIpoptProblem as they are --
+ * tests/ipopt_callbacks_check.c compiles exactly that assignment against the restated typedefs. */
+bool fl_eval_f     (int n, double* x, bool new_x, double* obj_value, void* user_data);
+bool fl_eval_grad_f(int n, double* x, bool new_x, double* grad_f, void* user_data);
+bool fl_eval_g     (int n, double* x, bool new_x, int m, double* g, void* user_data);
+bool fl_eval_jac_g (int n, double* x, bool new_x, int m, int nele_jac, int* iRow, int* jCol, double* values, void* user_data);
+bool fl_eval_h     (int n, double* x, bool new_x, double obj_factor, int m, double* lambda, bool new_lambda,
+                    int nele_hess, int* iRow, int* jCol, double* values, void* user_data);
 
 /* Whole batch, one call: every output may be NULL.  Arrays are [batch][...] contiguous. */
 int fl_eval_all(fl_nlp* nlp, const double* x, const double* lambda, double obj_factor,

@@ -10,33 +10,42 @@
 
 #include <cmath>
 
+// The real type the jets carry.  double: the oracle proper (what every test compares with).  Built a second time with
+// -DORACLE_REAL="long double" (liboracle_ld.so: x87 extended precision, 64-bit mantissa) the same formulas give second
+// derivatives with three more digits -- the arbiter where fp64 cancellation inside the tyre model limits the entry-wise
+// agreement of two correct double evaluations to ~1e-8 (tests/test_gpu_parity.py).
+#ifndef ORACLE_REAL
+#define ORACLE_REAL double
+#endif
+typedef ORACLE_REAL oreal;
+
 template <int N>
 struct Jet2
 {
-    double v;
-    double g[N];
-    double h[N][N];   // full symmetric storage, only j<=i is maintained and read
+    oreal v;
+    oreal g[N];
+    oreal h[N][N];   // full symmetric storage, only j<=i is maintained and read
 
     Jet2() : v(0.0)
     {
         for (int i = 0; i < N; ++i) { g[i] = 0.0; for (int j = 0; j <= i; ++j) h[i][j] = 0.0; }
     }
-    Jet2(double c) : v(c)
+    Jet2(oreal c) : v(c)
     {
         for (int i = 0; i < N; ++i) { g[i] = 0.0; for (int j = 0; j <= i; ++j) h[i][j] = 0.0; }
     }
-    static Jet2 variable(double value, int index)
+    static Jet2 variable(oreal value, int index)
     {
         Jet2 r(value);
         if (index >= 0 && index < N) r.g[index] = 1.0;
         return r;
     }
-    double hess(int i, int j) const { return (j <= i) ? h[i][j] : h[j][i]; }
+    oreal hess(int i, int j) const { return (j <= i) ? h[i][j] : h[j][i]; }
 };
 
 // y = f(a) given f, f', f'' at a.v
 template <int N>
-inline Jet2<N> jet_chain(const Jet2<N>& a, double f0, double f1, double f2)
+inline Jet2<N> jet_chain(const Jet2<N>& a, oreal f0, oreal f1, oreal f2)
 {
     Jet2<N> r;
     r.v = f0;
@@ -83,7 +92,7 @@ template <int N> inline Jet2<N> operator*(const Jet2<N>& a, const Jet2<N>& b)
 }
 template <int N> inline Jet2<N> inv(const Jet2<N>& b)
 {
-    const double f0 = 1.0 / b.v;
+    const oreal f0 = 1.0 / b.v;
     return jet_chain(b, f0, -f0 * f0, 2.0 * f0 * f0 * f0);
 }
 template <int N> inline Jet2<N> operator/(const Jet2<N>& a, const Jet2<N>& b) { return a * inv(b); }
@@ -112,37 +121,37 @@ template <int N> inline Jet2<N>& operator*=(Jet2<N>& a, double b) { a = a * b; r
 
 template <int N> inline Jet2<N> sqrt(const Jet2<N>& a)
 {
-    const double s = std::sqrt(a.v);
+    const oreal s = std::sqrt(a.v);
     return jet_chain(a, s, 0.5 / s, -0.25 / (s * a.v));
 }
 template <int N> inline Jet2<N> sin(const Jet2<N>& a)
 {
-    const double s = std::sin(a.v), c = std::cos(a.v);
+    const oreal s = std::sin(a.v), c = std::cos(a.v);
     return jet_chain(a, s, c, -s);
 }
 template <int N> inline Jet2<N> cos(const Jet2<N>& a)
 {
-    const double s = std::sin(a.v), c = std::cos(a.v);
+    const oreal s = std::sin(a.v), c = std::cos(a.v);
     return jet_chain(a, c, -s, -c);
 }
 template <int N> inline Jet2<N> atan(const Jet2<N>& a)
 {
-    const double d = 1.0 / (1.0 + a.v * a.v);
+    const oreal d = 1.0 / (1.0 + a.v * a.v);
     return jet_chain(a, std::atan(a.v), d, -2.0 * a.v * d * d);
 }
 template <int N> inline Jet2<N> tanh(const Jet2<N>& a)
 {
-    const double t = std::tanh(a.v);
-    const double d = 1.0 - t * t;
+    const oreal t = std::tanh(a.v);
+    const oreal d = 1.0 - t * t;
     return jet_chain(a, t, d, -2.0 * t * d);
 }
 template <int N> inline Jet2<N> exp(const Jet2<N>& a)
 {
-    const double e = std::exp(a.v);
+    const oreal e = std::exp(a.v);
     return jet_chain(a, e, e, e);
 }
 
 inline double value_of(double x) { return x; }
-template <int N> inline double value_of(const Jet2<N>& x) { return x.v; }
+template <int N> inline double value_of(const Jet2<N>& x) { return (double)x.v; }
 
 #endif

@@ -234,7 +234,7 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
     {
         int e0 = 0, e1 = 0;
         double f = 0.0;
-        std::vector<double> grad, H;     // [(e1 - e0 + 1) nodes][NV], [..][NV*NV]
+        std::vector<oreal> grad, H;      // [(e1 - e0 + 1) nodes][NV], [..][NV*NV]
         Triplets jac, hess;
     };
     int n_chunks = 1;
@@ -258,13 +258,13 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
         auto add_grad = [&](int slot, int node, const J& a, double c) {
             if (!want_derivs) return;
             if (!d.closed && node == 0) return;
-            double* gr = C.grad.data() + (size_t)slot * NV;
+            oreal* gr = C.grad.data() + (size_t)slot * NV;
             for (int k = 0; k < NV; ++k) gr[k] += c * a.g[k];
         };
         auto add_hess = [&](int slot, int node, const J& a, double c) {
             if (!want_derivs) return;
             if (!d.closed && node == 0) return;
-            double* Hn = C.H.data() + (size_t)slot * NV * NV;
+            oreal* Hn = C.H.data() + (size_t)slot * NV * NV;
             for (int r = 0; r < NV; ++r) for (int cc = 0; cc <= r; ++cc) Hn[r * NV + cc] += c * a.h[r][cc];
         };
         auto add_jac = [&](int row, int node, const J& a, double c) {
@@ -401,7 +401,7 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
     }
 
     // join the chunks in element order
-    std::vector<double> H;
+    std::vector<oreal> H;
     if (want_derivs) H.assign((size_t)np * NV * NV, 0.0);
     for (int ck = 0; ck < n_chunks; ++ck)
     {
@@ -415,8 +415,8 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
             if (!d.closed && node == 0) continue;
             double* gr = out.grad.data() + var0(node);
             for (int k = 0; k < NV; ++k) gr[k] += C.grad[(size_t)slot * NV + k];
-            double* Hn = H.data() + (size_t)node * NV * NV;
-            const double* Hc = C.H.data() + (size_t)slot * NV * NV;
+            oreal* Hn = H.data() + (size_t)node * NV * NV;
+            const oreal* Hc = C.H.data() + (size_t)slot * NV * NV;
             for (int k = 0; k < NV * NV; ++k) Hn[k] += Hc[k];
         }
         out.jac.row.insert(out.jac.row.end(), C.jac.row.begin(), C.jac.row.end());
@@ -434,7 +434,7 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
         for (int node = 0; node < np; ++node)
         {
             if (!d.closed && node == 0) continue;
-            const double* Hn = H.data() + (size_t)node * NV * NV;
+            const oreal* Hn = H.data() + (size_t)node * NV * NV;
             const int c0 = var0(node);
             for (int r = 0; r < NV; ++r) for (int c = 0; c <= r; ++c) out.hess.add(c0 + r, c0 + c, Hn[r * NV + c]);
         }

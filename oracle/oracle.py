@@ -42,6 +42,21 @@ def lib():
     return _LIB
 
 
+_LIB_LD = None
+
+
+def lib_ld():
+    """The same oracle with its jets in x87 extended precision (long double, 64-bit mantissa): oracle/jet.hpp."""
+    global _LIB_LD
+    if _LIB_LD is None:
+        so = os.path.join(_HERE, "liboracle_ld.so")
+        r = subprocess.run(["make", "-C", _HERE, "liboracle_ld.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0 and not os.path.exists(so):
+            raise RuntimeError("building the extended-precision oracle failed:\n" + r.stdout[-2000:])
+        _LIB_LD = C.CDLL(so)
+    return _LIB_LD
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 
@@ -50,8 +65,9 @@ class OracleNLP:
     """The collocation NLP of one lap, evaluated on the CPU."""
 
     def __init__(self, model, form, closed, s, track_length, track_nodes, params, dissipation, sigma=0.5, elevation=False,
-                 ctrl_default=None, q0=None, u0=None, du0=None, kart_direct_torque=False, node_params=None, wind=(0.0, 0.0)):
+                 ctrl_default=None, q0=None, u0=None, du0=None, kart_direct_torque=False, node_params=None, wind=(0.0, 0.0), extended=False):
         self._keep = []
+        self._lib = lib_ld() if extended else lib()
 
         def arr(a):
             if a is None:
@@ -76,7 +92,7 @@ class OracleNLP:
         self.desc = d
         n, m, nv, ncpe = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         mj, mh = C.c_long(), C.c_long()
-        lib().orc_sizes(C.byref(d), C.byref(n), C.byref(m), C.byref(nv), C.byref(ncpe), C.byref(mj), C.byref(mh))
+        self._lib.orc_sizes(C.byref(d), C.byref(n), C.byref(m), C.byref(nv), C.byref(ncpe), C.byref(mj), C.byref(mh))
         self.n, self.m, self.nv, self.ncpe, self._mj, self._mh = n.value, m.value, nv.value, ncpe.value, mj.value, mh.value
 
     def eval(self, x, lam=None, obj_factor=1.0, derivs=True, threads=0):
@@ -89,7 +105,7 @@ class OracleNLP:
         hr, hc, hv = np.zeros(self._mh, np.int32), np.zeros(self._mh, np.int32), np.zeros(self._mh)
         nj, nh = C.c_long(), C.c_long()
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
-        lib().orc_eval(C.byref(self.desc), _dp(x), _dp(lam), C.c_double(obj_factor), int(derivs), int(threads), C.byref(f), _dp(grad), _dp(g),
+        self._lib.orc_eval(C.byref(self.desc), _dp(x), _dp(lam), C.c_double(obj_factor), int(derivs), int(threads), C.byref(f), _dp(grad), _dp(g),
                        ip(jr), ip(jc), _dp(jv), C.byref(nj), ip(hr), ip(hc), _dp(hv), C.byref(nh))
         out = {"f": f.value, "g": g}
         if derivs:

@@ -12,10 +12,11 @@ def load_golden(name):
     return LapProblem.load_npz(os.path.join(GOLDEN, name + ".npz"))
 
 
-def oracle_nlp(p):
+def oracle_nlp(p, extended=False):
+    """extended: the oracle built with its jets in long double (oracle/jet.hpp) -- the arbiter of ill-conditioned entries."""
     return orc.OracleNLP(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.params, p.dissipation, p.sigma, p.elevation,
                          ctrl_default=p.ctrl_default, q0=p.q0, u0=p.u0, du0=p.du0, kart_direct_torque=p.kart_direct_torque,
-                         node_params=getattr(p, "node_params", None), wind=getattr(p, "wind", (0.0, 0.0)))
+                         node_params=getattr(p, "node_params", None), wind=getattr(p, "wind", (0.0, 0.0)), extended=extended)
 
 
 def equality_rows(p):

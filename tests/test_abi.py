@@ -47,3 +47,13 @@ def test_no_cpu_fallback_without_a_device(lib):
     p, _ = load_golden("f1_catalunya_chicane")
     with pytest.raises(RuntimeError, match="no CUDA device"):
         CollocationNLP(p)
+
+
+def test_callbacks_have_ipopts_types(tmp_path):
+    """Compile-only: `Eval_F_CB f = fl_eval_f;` ... against the typedefs of Ipopt 3.14's IpStdCInterface.h (restated in
+    tests/IpStdCInterface_3_14.h), in C, with incompatible pointer types as errors."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-Werror=incompatible-pointer-types", "-c", os.path.join(here, "ipopt_callbacks_check.c"),
+                        "-o", str(tmp_path / "check.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout

@@ -1,13 +1,15 @@
 """Parity of the CUDA callbacks (through the C-ABI, host buffers) with the CPU oracle.
 
-Tolerance (BASELINE.json north_star): callback values and derivative entries within 1e-10 relative, fp64.  "Relative" is
-taken against max(|reference entry|, 1) for f, g and grad f, and against max(|reference entry|, 0.1 * largest entry of the
-same block) for matrix entries, the block being the node's Hessian block / the element's Jacobian rows.  The floor is needed
-because some small entries are ill-conditioned in fp64 whichever way they are differentiated (e.g. d2/dkappa2 of
-kappa/rho = lambda_n^2/rho^3 evaluated as 1/rho - kappa_n^2/rho^3 on a straight): there the oracle itself is only good to
-1e-8 of the entry.  test_ill_conditioned_entries_against_40_digit_truth shows that on those entries the CUDA result is as
-close to a 40-digit evaluation as the oracle is.  Entries are compared by (row, col) with duplicates summed -- never by
-position.
+Tolerance (BASELINE.json north_star): callback values and derivative entries within 1e-10 relative, fp64 -- Jacobian AND
+Hessian entries, at golden points, perturbed points, full-size meshes and with N(0,1) multipliers.  "Relative" is taken against
+max(|reference entry|, 1) for f, g and grad f, and against max(|reference entry|, 0.1 * largest entry of the same block) for
+matrix entries, the block being the node's Hessian block / the element's Jacobian rows: the floor is there because some small
+entries are ill-conditioned in fp64 whichever way they are differentiated (e.g. d2/dkappa2 of kappa/rho = lambda_n^2/rho^3
+evaluated as 1/rho - kappa_n^2/rho^3 on a straight).  The reference for second derivatives is the oracle's own derivative mode
+(dense second-order jets over its restatement of the reference's formulas); where its double evaluation could itself be the
+limit, the same formulas in extended precision arbitrate (_hessian_close), and test_ill_conditioned_entries_against_40_digit_truth
+puts the rounding of the CUDA code's expression graph next to a 40-digit evaluation.  Entries are compared by (row, col) with
+duplicates summed -- never by position.
 """
 import numpy as np
 import pytest
@@ -42,6 +44,17 @@ def _matrix_close(A, B, what, block, rtol=RTOL):
     err = np.abs(D.data) / scale
     k = int(np.argmax(err))
     assert err[k] <= rtol, "%s: entry (%d, %d) differs by %.3e relative (ref %.6e)" % (what, D.row[k], D.col[k], err[k], ref[k])
+
+
+def _hessian_close(p, H, x, lam, obj, ref_hess, what="hessian"):
+    """north_star's 1e-10 on every Hessian entry (relative to max(|entry|, 0.1 x the largest entry of its block)) against the
+    oracle.  Should fp64 cancellation in the oracle's own double evaluation ever exceed that on an entry, the same formulas
+    evaluated in extended precision (oracle/jet.hpp, liboracle_ld.so) arbitrate: the CUDA value must then be within 1e-10 of THAT."""
+    A, B = _csr(*H, (p.n, p.n)), _csr(*ref_hess, (p.n, p.n))
+    try:
+        _matrix_close(A, B, what, p.nv)
+    except AssertionError:
+        _matrix_close(A, _csr(*oracle_nlp(p, extended=True).eval(x, lam, obj)["hess"], (p.n, p.n)), what + " (extended-precision oracle)", p.nv)
 
 
 def _points(p, ex, count=3, seed=0):
@@ -90,12 +103,12 @@ def test_callbacks_match_oracle(case):
         assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
         assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
         _matrix_close(_csr(jr, jc, out["jac"][0], (p.m, p.n)), _csr(*ref["jac"], (p.m, p.n)), "jacobian", p.ncpe)
-        _matrix_close(_csr(hr, hc, out["hess"][0], (p.n, p.n)), _csr(*ref["hess"], (p.n, p.n)), "hessian", p.nv)
+        _hessian_close(p, (hr, hc, out["hess"][0]), x, lam, obj, ref["hess"])
 
 
 def test_stress_point_random_multipliers(case):
-    """N(0,1) multipliers: values, gradient and Jacobian keep 1e-10; Hessian entries keep 1e-8 against the
-    oracle because of fp64 cancellation (see _stress_point), which the 40-digit test below quantifies."""
+    """N(0,1) multipliers: values, gradient, Jacobian and Hessian entries all within 1e-10 of the oracle
+    (measured: <= 2.1e-11 against the oracle evaluated in extended precision, tools/hess_arbiter.py)."""
     p, ex, nlp, o = case
     jr, jc, hr, hc = nlp.structure()
     x, lam, obj = _stress_point(p, ex)
@@ -105,7 +118,7 @@ def test_stress_point_random_multipliers(case):
     assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
     assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
     _matrix_close(_csr(jr, jc, out["jac"][0], (p.m, p.n)), _csr(*ref["jac"], (p.m, p.n)), "jacobian", p.ncpe)
-    _matrix_close(_csr(hr, hc, out["hess"][0], (p.n, p.n)), _csr(*ref["hess"], (p.n, p.n)), "hessian", p.nv, rtol=1.0e-8)
+    _hessian_close(p, (hr, hc, out["hess"][0]), x, lam, obj, ref["hess"])
 
 
 def test_ill_conditioned_entries_against_40_digit_truth(case):
@@ -224,7 +237,7 @@ def test_full_size_f1_8000_nodes_against_oracle():
     assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
     assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
     _matrix_close(_csr(jr, jc, out["jac"][0], (p.m, p.n)), _csr(*ref["jac"], (p.m, p.n)), "jacobian", p.ncpe)
-    _matrix_close(_csr(hr, hc, out["hess"][0], (p.n, p.n)), _csr(*ref["hess"], (p.n, p.n)), "hessian", p.nv, rtol=1.0e-8)
+    _hessian_close(p, (hr, hc, out["hess"][0]), x, lam, 1.0, ref["hess"])
     from fastest_lap_b200.ipm import lap_time
     assert abs(lap_time(p, x, out["f"][0]) - float(ex["laptime"])) <= 5.0e-2       # 77.82 s vs 77.79 s: interpolation of a 500-node solution
     nlp.close()
@@ -247,7 +260,7 @@ def test_full_size_kart_2000_nodes_against_oracle():
     assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
     assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
     _matrix_close(_csr(jr, jc, out["jac"][0], (p.m, p.n)), _csr(*ref["jac"], (p.m, p.n)), "jacobian", p.ncpe)
-    _matrix_close(_csr(hr, hc, out["hess"][0], (p.n, p.n)), _csr(*ref["hess"], (p.n, p.n)), "hessian", p.nv, rtol=1.0e-8)
+    _hessian_close(p, (hr, hc, out["hess"][0]), x, lam, 1.0, ref["hess"])
     nlp.close()
 
 
@@ -302,7 +315,7 @@ def test_variants_without_a_golden_match_the_oracle(name, form):
         assert np.max(np.abs(out["g"][0] - ref["g"]) / np.maximum(np.abs(ref["g"]), 1.0)) <= RTOL
         assert np.max(np.abs(out["grad"][0] - ref["grad"]) / np.maximum(np.abs(ref["grad"]), 1.0)) <= RTOL
         _matrix_close(_csr(jr, jc, out["jac"][0], (q.m, q.n)), _csr(*ref["jac"], (q.m, q.n)), "jacobian", q.ncpe)
-        _matrix_close(_csr(hr, hc, out["hess"][0], (q.n, q.n)), _csr(*ref["hess"], (q.n, q.n)), "hessian", q.nv, rtol=1.0e-8)
+        _hessian_close(q, (hr, hc, out["hess"][0]), x, lam, obj, ref["hess"])
     nlp.close()
 
 
@@ -340,7 +353,7 @@ def test_parameters_that_vary_along_the_lap():
     assert abs(J - Jr).max() <= 1e-10 * max(1.0, abs(Jr).max())
     H = sp.coo_matrix((out["hess"][0], (hr, hc)), shape=(p.n, p.n)).tocsr()
     Hr = sp.coo_matrix((ref["hess"][2], (ref["hess"][0], ref["hess"][1])), shape=(p.n, p.n)).tocsr()
-    assert abs(H - Hr).max() <= 1e-8 * max(1.0, abs(Hr).max())
+    assert abs(H - Hr).max() <= 1e-10 * max(1.0, abs(Hr).max())
     # the varying mass is felt: the constant-parameter problem gives other constraint values
     plain = CollocationNLP(p0)
     o0 = plain.eval_all(x, lam, 0.9)
@@ -413,6 +426,53 @@ def test_wind(case):
     assert abs(J - Jr).max() <= 1e-10 * max(1.0, abs(Jr).max())
     H = sp.coo_matrix((out["hess"][0], (hr, hc)), shape=(p.n, p.n)).tocsr()
     Hr = sp.coo_matrix((ref["hess"][2], (ref["hess"][0], ref["hess"][1])), shape=(p.n, p.n)).tocsr()
-    assert abs(H - Hr).max() <= 1e-8 * max(1.0, abs(Hr).max())
+    assert abs(H - Hr).max() <= 1e-10 * max(1.0, abs(Hr).max())
     assert np.max(np.abs(out["g"][0] - out0["g"][0])) > 1e-4
     nlp.close(); calm.close()
+
+
+def test_callbacks_in_ipopts_call_order():
+    """The five callbacks driven straight through the C ABI the way Ipopt drives a TNLP: first the two structure calls with
+    values == NULL (triplets of the Jacobian and of the Hessian's lower triangle), then, per iterate, eval_f with new_x = true
+    followed by eval_grad_f / eval_g / eval_jac_g / eval_h with new_x = false on the same x; then a new iterate announced
+    by eval_g (Ipopt may start an iterate with any callback), and a Hessian call with new multipliers on an old x."""
+    import ctypes as C
+    from fastest_lap_b200.nlp import CollocationNLP, load_library, _ptr
+    p, ex = load_golden("f1_catalunya_chicane")
+    nlp = CollocationNLP(p)
+    lib, h, n, m = load_library(), nlp._h, nlp.n, nlp.m
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    jr, jc = np.empty(nlp.nnz_jac, np.int32), np.empty(nlp.nnz_jac, np.int32)
+    hr, hc = np.empty(nlp.nnz_hess, np.int32), np.empty(nlp.nnz_hess, np.int32)
+    assert lib.fl_eval_jac_g(n, None, False, m, nlp.nnz_jac, ip(jr), ip(jc), None, h)
+    assert lib.fl_eval_h(n, None, False, 1.0, m, None, False, nlp.nnz_hess, ip(hr), ip(hc), None, h)
+    sj, sc, sh, shc = nlp.structure()
+    assert np.array_equal(jr, sj) and np.array_equal(jc, sc) and np.array_equal(hr, sh) and np.array_equal(hc, shc)
+    assert np.all(hr >= hc) and jr.max() == m - 1 and jc.max() == n - 1
+    rng = np.random.default_rng(8)
+    f, g, gr, jv, hv = C.c_double(), np.empty(m), np.empty(n), np.empty(nlp.nnz_jac), np.empty(nlp.nnz_hess)
+    for it in range(3):
+        x = np.ascontiguousarray(ex["x"] * (1 + 1e-3 * rng.standard_normal(n)))
+        lam = np.ascontiguousarray(rng.standard_normal(m))
+        ref = nlp.eval_all(x, lam, 0.5 + it)
+        if it < 2:
+            assert lib.fl_eval_f(n, _ptr(x), True, C.byref(f), h)
+            assert lib.fl_eval_grad_f(n, _ptr(x), False, _ptr(gr), h)
+            assert lib.fl_eval_g(n, _ptr(x), False, m, _ptr(g), h)
+        else:
+            assert lib.fl_eval_g(n, _ptr(x), True, m, _ptr(g), h)
+            assert lib.fl_eval_f(n, _ptr(x), False, C.byref(f), h)
+            assert lib.fl_eval_grad_f(n, _ptr(x), False, _ptr(gr), h)
+        assert lib.fl_eval_jac_g(n, _ptr(x), False, m, nlp.nnz_jac, None, None, _ptr(jv), h)
+        assert lib.fl_eval_h(n, _ptr(x), False, 0.5 + it, m, _ptr(lam), True, nlp.nnz_hess, None, None, _ptr(hv), h)
+        assert f.value == ref["f"][0] and np.array_equal(g, ref["g"][0])
+        np.testing.assert_allclose(gr, ref["grad"][0], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(jv, ref["jac"][0], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(hv, ref["hess"][0], rtol=1e-9, atol=1e-10)
+        # new multipliers on the old x
+        lam2 = np.ascontiguousarray(rng.standard_normal(m))
+        assert lib.fl_eval_h(n, _ptr(x), False, 1.0, m, _ptr(lam2), True, nlp.nnz_hess, None, None, _ptr(hv), h)
+        np.testing.assert_allclose(hv, nlp.eval_all(x, lam2, 1.0)["hess"][0], rtol=1e-9, atol=1e-10)
+    # a wrong size is refused, not read past
+    assert not lib.fl_eval_g(n, _ptr(x), False, m + 1, _ptr(g), h)
+    nlp.close()
