@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "fl_internal.h"
@@ -556,6 +557,11 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
         s->launches += 1;
     }
     const int blocks_b = (B + 127) / 128;
+    // FL_IPM_TRACE=<file>: one line per lock-step round (running laps, schedule of the factorisation, host clock at the round's first
+    // synchronisation point) -- where the time of a batch goes as its laps converge
+    std::FILE* trace = nullptr;
+    if (const char* e = std::getenv("FL_IPM_TRACE")) { trace = std::fopen(e, "a"); if (trace) std::fprintf(trace, "round,running,partitioned,ms,ms_factor,ms_solve,ms_eval\n"); }
+    const auto t_start = std::chrono::steady_clock::now();
     for (long round = 0;; ++round)
     {
         s->n_rounds = round;
@@ -574,6 +580,9 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
             std::fprintf(stderr, "%4ld  running %d  lap0: it %d f %.10f inf_pr %.2e inf_du %.2e mu %.1e dw %.1e alpha %.2e status %d\n", round, cnt[0], l0.iter, l0.f,
                          l0.cviol, l0.dual_inf, l0.mu, l0.dw_last, l0.alpha, l0.status);
         }
+        if (trace)
+            std::fprintf(trace, "%ld,%d,%d,%.3f,%.3f,%.3f,%.3f\n", round, cnt[0], (int)(s->P > 0 && (s->part_policy > 0 || (s->part_policy == 0 && cnt[0] <= s->part_max_laps))),
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), s->ms_factor, s->ms_solve, s->ms_eval);
         if (cnt[0] == 0) break;
         // factorisation.  Many active laps: one block per lap walks the whole chain, the inertia correction (Algorithm IC)
         // runs inside the kernel.  Few active laps: the chain is cut into segments factorised by their own blocks, and IC
@@ -619,6 +628,7 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
             if (!read_counters(s, cnt)) return 0;
         }
     }
+    if (trace) std::fclose(trace);
     cudaEventRecord(s->ev1, st);
     FLI_CUDA(cudaEventSynchronize(s->ev1));
     float ms = 0.f;
