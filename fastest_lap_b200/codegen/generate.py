@@ -51,6 +51,7 @@ VARIANTS = {
     "kart_derivative_torque": Variant("kart", "derivative", direct_torque=True),
     "kart_steady": Variant("kart", "steady"),
     "f1_steady": Variant("f1", "steady"),
+    "f1_direct_aug": Variant("f1", "direct", aug=True),
 }
 
 
@@ -270,6 +271,9 @@ def generate(name, variant):
     L.append("    static constexpr int NVAL = %d, NTC = %d, NTRACK = %d, NRAW = %d, ND = %d, NCK = %d;" % (len(p.values), len(tnames), len(p.track_names), len(raw_names), pt.size, len(ck)))
     L.append("    static constexpr int NJA = %d, NJB = %d, NH = %d, NCPL = %d;" % (len(ja), len(jb), len(hs), len(p.coupling)))
     L.append("    static constexpr int IS_DERIVATIVE = %d, IS_3D = %d;" % (int(variant.form == "derivative"), int(variant.elevation)))
+    n_aug = getattr(p, "n_aug", 0)
+    L.append("    static constexpr int NAUG = %d, AUG_POS = %d, P_AUG = %d;   // augmented states (the last NAUG trapezoid rows); node variable a (q follows); first aug_* parameter" %
+             (n_aug, p.aug_pos[0] if n_aug else -1, raw_names.index("aug_bb") if n_aug else -1))
     L.append("    static constexpr int NP_VALUES = %d, NP_JAC = %d, NP_HESS = %d, NP_ALL = %d;   // code partitions of each pass" % (NPARTS["values"], NPARTS["jac"], NPARTS["hess"], NPARTS["all"]))
     L.append("    static constexpr int NCKV = %d, HAS_TAPE = %d, NP_TAPE = %d;   // checkpoints of the values pass; the tape pass writes all NCK" % (n_heavy, int(SHARE > 0), n_tape))
     for mode in ("values", "tape", "jac", "hess", "all"):

@@ -112,7 +112,7 @@ def f1_model(q, u, P, trk):
     pre = ["ft_", "ft_", "rt_", "rt_"]
     cd, sd = cos(delta), sin(delta)
 
-    lam, omega_w, Fx_t, Fy_t, rc = [], [], [], [], []
+    lam, omega_w, Fx_t, Fy_t, rc, vt = [], [], [], [], [], []
     Fax, Tax = [], []
     for i in range(4):
         R0 = P[pre[i] + "R0"]
@@ -126,6 +126,7 @@ def f1_model(q, u, P, trk):
         else:
             vtx, vty = vcx, vcy
         lam_i = -vty / vtx                                               # tire.h:157
+        vt.append((vtx, vty))
         kappa, Fx, Fy = f1_tire(P, pre[i], k_hat[i], lam_i, N[i])
         lam.append(lam_i)
         omega_w.append((1.0 + kappa) * vtx / R0)                         # tire.hpp:102
@@ -215,7 +216,12 @@ def f1_model(q, u, P, trk):
     # un-scaled time derivatives and wheel balances (the steady-state equations use them, limebeer2014f1.h:148-169)
     rates = dict(du=du, dv=dv, domega=domega, dw_g=dw * (1.0 / G0), dLroll_mg=dLroll * inv_mg, dLpitch_mg=dLpitch * inv_mg,
                  roll_balance_mg=roll_balance * inv_mg, dL=dL, lam=lam)
-    return dict(states=states, dstates=dstates, dtds=dtds, extra=extra, rates=rates)
+    # integrands of the integral quantities (limebeer2014f1.h:291-306): engine power [MW] (engine.hpp:43), and minus the power
+    # each tyre dissipates, F . v_slip with v_slip = (v_x - omega R0, v_y) at the contact point (tire.h:127)
+    integrands = [thr * (P["r_engine_power"] * 1.0e3) * 1.0e-6]
+    for i in range(4):
+        integrands.append(-(Fx_t[i] * (vt[i][0] - omega_w[i] * P[pre[i] + "R0"]) + Fy_t[i] * vt[i][1]) * 1.0e-6)
+    return dict(states=states, dstates=dstates, dtds=dtds, extra=extra, rates=rates, integrands=integrands)
 
 
 def kart_tire(P, pre, kappa, lam, N, only_lateral):

@@ -17,9 +17,14 @@ from . import models
 
 
 class Variant:
-    def __init__(self, model, form, elevation=False, direct_torque=False):
+    def __init__(self, model, form, elevation=False, direct_torque=False, aug=False):
         assert model in ("f1", "kart") and form in ("direct", "derivative", "steady")
         self.model, self.form, self.elevation, self.direct_torque = model, form, bool(elevation), bool(direct_torque)
+        # one augmented state per node (see NodeProgram): a control held constant over stretches of the lap (hypermesh / constant
+        # controls) or the running value of a restricted integral quantity
+        self.aug = bool(aug)
+        if aug:
+            assert model == "f1" and form == "direct", "the augmented state is offered for the F1, direct form"
         if model == "kart":
             assert not elevation, "lot2016kart rejects tracks with elevation (lot2016kart.h:63-68)"
 
@@ -32,6 +37,8 @@ class Variant:
             n += "_3d"
         if self.direct_torque:
             n += "_torque"
+        if self.aug:
+            n += "_aug"
         return n
 
 
@@ -60,12 +67,29 @@ class NodeProgram:
             td_ids = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 12]
             alg_ids = []
         self.param_names = self.param_names + ["diss0", "diss1"]
+        # Augmented state (Variant.aug).  The reference keeps a hypermesh / constant control as ONE variable per stretch, appended to
+        # x (optimal_laptime.hpp:378-404, control_array_at_s: detail/optimal_laptime_control_variables.h:190-222), and a restricted
+        # integral quantity as ONE dense constraint row (optimal_laptime.hpp:1316-1317, 1352-1353, 1409-1416): both couple every
+        # node of the lap.  Here they are restated node-wise so that the KKT system stays block-tridiagonal: every node carries
+        #   a  the control's value at the node / the integral accumulated up to the node,
+        #   q  a free variable that enters the row of the element ENDING at the node with the per-node constant rj (0 or 1),
+        # and every element one more trapezoid row  a_j + rj q_j - bout_i a_i - (awout_i I_i + awin_j I_j) = 0, I = integrand dt/ds.
+        # Control: I = 0, bout = 1, rj = 1 where a new stretch starts (free jump), 0 inside a stretch (a_j = a_i).  Integral on a
+        # closed lap: rj = 0, bout = 0 at node 0 only -- the accumulation starts from zero there and the closing element makes a_0 the
+        # value of the whole integral, restricted by a_0's own bounds [lower, upper]; q is inert.
+        # Same feasible set and objective as the reference's formulation, hence the same optimum.
+        self.n_aug = 1 if v.aug else 0
+        if v.aug:
+            self.param_names = self.param_names + ["aug_bb", "aug_w_engine", "aug_w_tfl", "aug_w_tfr", "aug_w_trl", "aug_w_trr"]
         self.td_ids, self.alg_ids = td_ids, alg_ids
-        self.n_td, self.n_alg, self.n_ext = len(td_ids), len(alg_ids), 6
+        self.n_td, self.n_alg, self.n_ext = len(td_ids) + self.n_aug, len(alg_ids), 6
         self.n_ctrl_rows = self.n_fm if deriv else 0
         self.ncpe = self.n_td + self.n_alg + self.n_ext + self.n_ctrl_rows
-        self.nv = (n_in - 1) + self.n_fm + (self.n_fm if deriv else 0)
-        self.ctrl_pos = [n_in - 1, n_in]
+        self.nv = (n_in - 1) + 2 * self.n_aug + self.n_fm + (self.n_fm if deriv else 0)
+        # the full-mesh controls stay the LAST variables of the node (the warp-per-lap KKT schedule relies on it): a, q sit between
+        # the inputs and the controls
+        self.aug_pos = [n_in - 1, n_in] if v.aug else []
+        self.ctrl_pos = [n_in - 1 + 2 * self.n_aug, n_in + 2 * self.n_aug]
         self.dctrl_pos = [n_in + 1, n_in + 2] if deriv else []
 
         # ---- symbols
@@ -78,6 +102,9 @@ class NodeProgram:
         else:
             self.track_names = ["kz", "wt", "wn"]
             trk = dict(kx=0.0, ky=0.0, kz=S("t_kz", "t"), smu=0.0, cmu=1.0, sph=0.0, cph=1.0, wt=S("t_wt", "t"), wn=S("t_wn", "t"), wb=0.0)
+        if v.aug:
+            self.track_names = self.track_names + ["rj", "bout", "awin", "awout"]
+            rj, bout, awin, awout = S("t_rj", "t"), S("t_bout", "t"), S("t_awin", "t"), S("t_awout", "t")
         # per-node mesh constants: lengths of the element that ends / starts at the node; direct form: their inverses
         # (0 where the element does not exist); derivative form: total length weighting the node's control-rate penalty
         self.geom_names = ["hin", "hout"] + (["penw"] if deriv else ["ihin", "ihout"])
@@ -100,7 +127,11 @@ class NodeProgram:
         if v.model == "f1":
             # controls: delta, boost, throttle, brake-bias; boost and brake-bias keep their default values
             # (Control_variables::control_array_at_s, detail/optimal_laptime_control_variables.h:190-222)
-            u = [ctrl[0], E(g, g.const(0.0)), ctrl[1], P["brake_bias"]]
+            bias = P["brake_bias"]
+            if v.aug:
+                a_var, q_var = self.x[self.aug_pos[0]], self.x[self.aug_pos[1]]
+                bias = P["aug_bb"] * a_var + (1.0 - P["aug_bb"]) * bias
+            u = [ctrl[0], E(g, g.const(0.0)), ctrl[1], bias]
             out = models.f1_model(q, u, P, trk)
         else:
             out = models.kart_model(q, ctrl, P, trk, direct_torque=v.direct_torque, curvilinear=True)
@@ -108,23 +139,37 @@ class NodeProgram:
 
         Q = [states[i] for i in td_ids]
         QD = [dstates[i] for i in td_ids]
+        QA = []
+        if v.aug:
+            # integrands of limebeer2014f1::compute_integral_quantities (limebeer2014f1.h:291-306) times dt/ds (optimal_laptime.hpp:1352)
+            iq = out["integrands"]
+            integrand = P["aug_w_engine"] * iq[0] + P["aug_w_tfl"] * iq[1] + P["aug_w_tfr"] * iq[2] + P["aug_w_trl"] * iq[3] + P["aug_w_trr"] * iq[4]
+            Q.append(bout * a_var)
+            QD.append(integrand * dtds)
+            QA.append(a_var + rj * q_var)
         ALG = [dstates[i] / dtds for i in alg_ids]              # optimal_laptime.hpp:1341 (= the un-scaled equation)
         EXT = list(extra)
         CDOT = [self.x[p] * dtds for p in self.dctrl_pos]       # optimal_laptime.hpp:1580-1581
         self.Q, self.QD, self.ALG, self.EXT, self.CDOT, self.DTDS = Q, QD, ALG, EXT, CDOT, dtds
 
         # ---- node values handed to the element assembly (g, f)
-        self.values = Q + QD + ALG + EXT + [dtds] + CDOT
+        self.values = Q + QD + ALG + EXT + [dtds] + CDOT + QA
         self.value_names = (["Q%d" % r for r in range(self.n_td)] + ["QD%d" % r for r in range(self.n_td)] +
                             ["ALG%d" % r for r in range(self.n_alg)] + ["EXT%d" % r for r in range(self.n_ext)] + ["DTDS"] +
-                            ["CDOT%d" % c for c in range(self.n_ctrl_rows)])
+                            ["CDOT%d" % c for c in range(self.n_ctrl_rows)] + ["QA%d" % r for r in range(self.n_aug)])
 
         # ---- rows as functions of x_j: A (j is the right node of its element), B (j is the left node)
         one_m_sigma = 1.0 - sigma
         rowsA, rowsB = [], []
-        for r in range(self.n_td):
+        for r in range(self.n_td - self.n_aug):
             rowsA.append(Q[r] - hin * sigma * QD[r])
             rowsB.append(-Q[r] - hout * one_m_sigma * QD[r])
+        for r in range(self.n_aug):
+            # weights of the node's integrand in the two elements it belongs to: per-node constants (the closing element of the
+            # reference swaps them, optimal_laptime.hpp:1409)
+            k = self.n_td - self.n_aug + r
+            rowsA.append(QA[r] - awin * QD[k])
+            rowsB.append(-Q[k] - awout * QD[k])
         for r in range(self.n_alg):
             rowsA.append(ALG[r]); rowsB.append(None)
         for r in range(self.n_ext):

@@ -22,6 +22,7 @@ FL_DECLARE_VARIANT(kart_direct_torque)
 FL_DECLARE_VARIANT(kart_derivative_torque)
 FL_DECLARE_VARIANT(kart_steady)
 FL_DECLARE_VARIANT(f1_steady)
+FL_DECLARE_VARIANT(f1_direct_aug)
 
 namespace {
 
@@ -38,8 +39,9 @@ constexpr double G0 = 9.81;
 constexpr int F1_NPARAMS = 58, KART_NPARAMS = 72;
 constexpr int F1_NIN = 14, KART_NIN = 13, F1_NCTRL = 4, KART_NCTRL = 2;
 
-const fl_variant* pick_variant(int model, int form, int elevation, int torque)
+const fl_variant* pick_variant(int model, int form, int elevation, int torque, int aug = 0)
 {
+    if (aug) return (model == FL_MODEL_F1_3DOF && form == FL_FORM_DIRECT && !elevation) ? fl_variant_f1_direct_aug() : nullptr;
     if (model == FL_MODEL_F1_3DOF)
     {
         if (form == FL_FORM_STEADY) return elevation ? nullptr : fl_variant_f1_steady();
@@ -174,8 +176,16 @@ fl_nlp* fl_steady_create(const fl_steady_desc* sd)
 static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
 {
     if (!d) { fail("null problem description"); return nullptr; }
-    const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque);
+    const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque, d->aug_kind);
+    if (!v && d->aug_kind) { fail("hypermesh / constant controls and integral constraints are offered for the F1, direct form, on flat tracks"); return nullptr; }
     if (!v) { fail(d->model == FL_MODEL_KART_6DOF && d->elevation ? "lot2016kart does not support tracks with elevation" : "unknown model / form"); return nullptr; }
+    if (d->aug_kind)
+    {
+        if (!d->closed) { fail("hypermesh / constant controls and integral constraints need a closed lap"); return nullptr; }
+        if (d->aug_kind != FL_AUG_BRAKE_BIAS && d->aug_kind != FL_AUG_INTEGRAL) { fail("unknown aug_kind"); return nullptr; }
+        if (d->aug_kind == FL_AUG_BRAKE_BIAS && !d->aug_jump) { fail("aug_jump is null"); return nullptr; }
+        if (!(d->aug_bounds[0] < d->aug_bounds[1])) { fail("aug_bounds must be an interval"); return nullptr; }
+    }
     if (d->n_points < 2 && !steady_spec) { fail("provide at least two values of arclength"); return nullptr; }
     if (d->batch < 1) { fail("batch must be >= 1"); return nullptr; }
     if (!d->s || !d->track_nodes || !d->wl || !d->wr || (!d->vehicle_params && !d->node_params)) { fail("null array in problem description"); return nullptr; }
@@ -208,6 +218,8 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
     h->desc.s = h->s.data(); h->desc.wl = h->wl.data(); h->desc.wr = h->wr.data(); h->desc.vehicle_params = h->params.data();
     h->desc.node_params = d->node_params ? h->node_params.data() : nullptr;
     h->desc.track_nodes = nullptr; h->desc.q0 = h->desc.u0 = h->desc.du0 = h->desc.ctrl_default = nullptr;
+    if (d->aug_kind == FL_AUG_BRAKE_BIAS) { h->aug_jump.assign(d->aug_jump, d->aug_jump + np); h->desc.aug_jump = h->aug_jump.data(); }
+    else h->desc.aug_jump = nullptr;
 
     fl_dev& P = h->P;
     P.n_points = np; P.closed = d->closed ? 1 : 0; P.batch = batch;
@@ -250,11 +262,21 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
             TC(k++, i) = sph_; TC(k++, i) = cph_;
             TC(k++, i) = wt; TC(k++, i) = wn; TC(k++, i) = wb;
         }
-        else if (v->NTRACK == 3) { TC(k++, i) = kz; TC(k++, i) = wt; TC(k++, i) = wn; }
+        else if (v->NTRACK >= 3) { TC(k++, i) = kz; TC(k++, i) = wt; TC(k++, i) = wn; }
         else
             TC(k++, i) = kz;
         const double hin = i > 0 ? d->s[i] - d->s[i - 1] : (d->closed ? L - d->s[np - 1] : 0.0);
         const double hout = i + 1 < np ? d->s[i + 1] - d->s[i] : (d->closed ? L - d->s[np - 1] : 0.0);
+        if (v->NAUG)
+        {
+            // rj, bout, awin, awout (codegen/nlpnode.py).  The closing element of the reference weights its integrands the other
+            // way round: (1 - sigma) at node 0, sigma at the last node (optimal_laptime.hpp:1409)
+            const bool integral = d->aug_kind == FL_AUG_INTEGRAL;
+            TC(k++, i) = integral ? 0.0 : (d->aug_jump[i] != 0.0 ? 1.0 : 0.0);
+            TC(k++, i) = (integral && i == 0) ? 0.0 : 1.0;
+            TC(k++, i) = hin * (i == 0 ? 1.0 - d->sigma : d->sigma);
+            TC(k++, i) = hout * (i + 1 == np ? d->sigma : 1.0 - d->sigma);
+        }
         TC(k++, i) = hin;
         TC(k++, i) = hout;
         if (!v->IS_DERIVATIVE)
@@ -299,6 +321,11 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
         Db[v->P_DISS0] = d->dissipation[0];
         Db[v->P_DISS1] = d->dissipation[1];
         if (steady_spec) std::memcpy(Db + v->P_DISS1 + 1, steady_spec + (size_t)b * 7, 7 * sizeof(double));    // ss_v ... ss_cay follow diss1
+        if (v->NAUG)
+        {
+            Db[v->P_AUG] = d->aug_kind == FL_AUG_BRAKE_BIAS ? 1.0 : 0.0;
+            for (int k = 0; k < 5; ++k) Db[v->P_AUG + 1 + k] = d->aug_kind == FL_AUG_INTEGRAL ? d->aug_weights[k] : 0.0;
+        }
         v->derive(Db);
     }
     P.d_prob_stride = d->node_params ? (size_t)np * v->ND : (size_t)v->ND;
@@ -388,7 +415,7 @@ int fl_nlp_structure(const fl_nlp* h, int* jac_row, int* jac_col, int* hess_row,
 int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double* g_l, double* g_u)
 {
     if (!d || !d->wl || !d->wr || (!d->vehicle_params && !d->node_params)) return fail("null problem description") ? 1 : 0;
-    const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque);
+    const fl_variant* v = pick_variant(d->model, d->form, d->elevation, d->kart_direct_torque, d->aug_kind);
     if (!v) return fail("unknown model / form") ? 1 : 0;
     const int node0 = d->closed ? 0 : 1, n_points = d->n_points;
     const int n_var_nodes = n_points - node0, n_elements = d->closed ? n_points : n_points - 1;
@@ -428,9 +455,19 @@ int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double
         const double l[13] = { -1, -1, -1, -1, 50.0 * KMH, -50.0 * KMH, -10.0, -3.0, -3.0, -3.0, -3.0, 0.0, -45.0 * DEG };
         const double u[13] = { 1, 1, 1, 1, 380.0 * KMH, 50.0 * KMH, 10.0, -0.01, -0.01, -0.01, -0.01, 0.0, 45.0 * DEG };
         for (int k = 0; k < 13; ++k) { lb[k] = l[k]; ub[k] = u[k]; }
-        lb[13] = -20.0 * DEG; ub[13] = 20.0 * DEG;      // steering
-        lb[14] = -1.0; ub[14] = 1.0;                    // throttle
+        lb[v->CTRL_POS[0]] = -20.0 * DEG; ub[v->CTRL_POS[0]] = 20.0 * DEG;      // steering
+        lb[v->CTRL_POS[1]] = -1.0; ub[v->CTRL_POS[1]] = 1.0;                    // throttle
         if (v->IS_DERIVATIVE) { lb[15] = -20.0 * DEG; ub[15] = 20.0 * DEG; lb[16] = -10.0; ub[16] = 10.0; }   // limebeer2014f1.h:227-230, by control id
+        if (v->NAUG)
+        {
+            // a: the control's own bounds / a wide box around the accumulated integral (node 0 holds the whole integral: its bounds,
+            // below); q: a jump as large as the control's range / inert
+            const double lo = d->aug_bounds[0], up = d->aug_bounds[1];
+            const double wide = 10.0 * std::fmax(1.0, std::fmax(std::fabs(lo), std::fabs(up)));
+            const bool integral = d->aug_kind == FL_AUG_INTEGRAL;
+            lb[v->AUG_POS] = integral ? -wide : lo; ub[v->AUG_POS] = integral ? wide : up;
+            lb[v->AUG_POS + 1] = integral ? -1.0 : -(up - lo); ub[v->AUG_POS + 1] = integral ? 1.0 : up - lo;
+        }
     }
     else
     {
@@ -454,6 +491,11 @@ int fl_problem_bounds(const fl_problem_desc* d, double* x_l, double* x_u, double
         {
             if (x_l) x_l[(size_t)vn * NV + k] = (k == n_pos) ? -d->wl[node] : lb[k];
             if (x_u) x_u[(size_t)vn * NV + k] = (k == n_pos) ? d->wr[node] : ub[k];
+        }
+        if (v->NAUG && d->aug_kind == FL_AUG_INTEGRAL && node == 0)
+        {
+            if (x_l) x_l[(size_t)vn * NV + v->AUG_POS] = d->aug_bounds[0];
+            if (x_u) x_u[(size_t)vn * NV + v->AUG_POS] = d->aug_bounds[1];
         }
     }
     (void)big;

@@ -27,7 +27,7 @@ struct fl_nlp
     double *d_xfull = nullptr, *d_xuser = nullptr, *d_tc = nullptr, *d_D = nullptr, *d_lambda = nullptr, *d_zeros = nullptr;
     double *d_C = nullptr, *d_V = nullptr, *d_g = nullptr, *d_f = nullptr, *d_fpart = nullptr, *d_grad = nullptr, *d_jac = nullptr, *d_hess = nullptr;
     unsigned int* d_fcount = nullptr;
-    std::vector<double> s, wl, wr, params, node_params, D0;      // D0: parameter vector (with derived slots) of problem 0
+    std::vector<double> s, wl, wr, params, node_params, aug_jump, D0;      // D0: parameter vector (with derived slots) of problem 0
     int shared_d = 1;                               // every problem of the batch has the parameter vector D0
     std::vector<int> jac_row, jac_col, hess_row, hess_col;
     bool values_valid = false, derivs_jac_valid = false;

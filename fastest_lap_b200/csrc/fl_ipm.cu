@@ -84,6 +84,7 @@ template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, con
     do { \
         if (s->NV == 15 && s->NEQ == 13) fn<15, 13>(s, __VA_ARGS__); \
         else if (s->NV == 17 && s->NEQ == 15) fn<17, 15>(s, __VA_ARGS__); \
+        else if (s->NV == 17 && s->NEQ == 14) fn<17, 14>(s, __VA_ARGS__); \
         else if (s->NV == 14 && s->NEQ == 12) fn<14, 12>(s, __VA_ARGS__); \
         else if (s->NV == 16 && s->NEQ == 14) fn<16, 14>(s, __VA_ARGS__); \
         else if (s->NV == 8 && s->NEQ == 6) fn<8, 6>(s, __VA_ARGS__); \

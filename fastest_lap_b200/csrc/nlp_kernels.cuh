@@ -172,8 +172,19 @@ __device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, co
         double* g = P.g + (size_t)prob * P.m + (size_t)e * G::NCPE;
         int row = 0;
 #pragma unroll
-        for (int r = 0; r < G::NTD; ++r, ++row)
+        for (int r = 0; r < G::NTD - G::NAUG; ++r, ++row)
             g[row] = Vj[(oQ + r) * 32] - Vi[(oQ + r) * 32] - h * (oms * Vi[(oQD + r) * 32] + sigma * Vj[(oQD + r) * 32]);
+        if constexpr (G::NAUG > 0)
+        {
+            // augmented rows (codegen/nlpnode.py): the right node's value carries the free jump, the integrand weights are per-node
+            // constants (the last two track slots: awin of the right node, awout of the left one)
+            constexpr int oQA = oCD + G::NCR;
+            const double awout = __ldg(P.tc + fl_chunk_base(i, G::NTC) + (G::NTRACK - 1) * 32);
+            const double awin = __ldg(P.tc + fl_chunk_base(j, G::NTC) + (G::NTRACK - 2) * 32);
+#pragma unroll
+            for (int r = G::NTD - G::NAUG; r < G::NTD; ++r, ++row)
+                g[row] = Vj[(oQA + r - (G::NTD - G::NAUG)) * 32] - Vi[(oQ + r) * 32] - (awout * Vi[(oQD + r) * 32] + awin * Vj[(oQD + r) * 32]);
+        }
 #pragma unroll
         for (int r = 0; r < G::NALG; ++r, ++row) g[row] = Vj[(oALG + r) * 32];
 #pragma unroll
@@ -391,6 +402,7 @@ struct fl_variant
 {
     const char* name;
     int NV, NCPE, NTD, NALG, NEXT, NCR, NFM, NVAL, NCK, NTC, NTRACK, NRAW, ND, NJA, NJB, NH, NCPL, IS_DERIVATIVE, IS_3D;
+    int NAUG, AUG_POS, P_AUG;      // augmented state (codegen/nlpnode.py): count, node variable of `a`, first aug_* parameter slot
     int OPS_VALUES, OPS_JAC, OPS_HESS, OPS_ALL;
     const int *CTRL_POS, *DCTRL_POS, *JA_ROW, *JA_COL, *JB_ROW, *JB_COL, *H_ROW, *H_COL;
     int P_SIGMA, P_DISS0, P_DISS1, P_F_WHEEL_SCALE, P_R_WHEEL_SCALE;     // -1 when the model has no such slot
@@ -476,6 +488,7 @@ struct variant_ops
         v.HAS_TAPE = G::HAS_TAPE;
         v.NVAL = G::NVAL; v.NCK = G::NCK; v.NTC = G::NTC; v.NTRACK = G::NTRACK; v.NRAW = G::NRAW; v.ND = G::ND;
         v.NJA = G::NJA; v.NJB = G::NJB; v.NH = G::NH; v.NCPL = G::NCPL; v.IS_DERIVATIVE = G::IS_DERIVATIVE; v.IS_3D = G::IS_3D;
+        v.NAUG = G::NAUG; v.AUG_POS = G::AUG_POS; v.P_AUG = G::P_AUG;
         v.OPS_VALUES = G::OPS_VALUES; v.OPS_JAC = G::OPS_JAC; v.OPS_HESS = G::OPS_HESS; v.OPS_ALL = G::OPS_ALL;
         v.CTRL_POS = G::CTRL_POS; v.DCTRL_POS = G::DCTRL_POS;
         v.JA_ROW = G::JA_ROW; v.JA_COL = G::JA_COL; v.JB_ROW = G::JB_ROW; v.JB_COL = G::JB_COL; v.H_ROW = G::H_ROW; v.H_COL = G::H_COL;

@@ -27,7 +27,8 @@ class _Desc(C.Structure):
     _fields_ = [("model", C.c_int), ("form", C.c_int), ("closed", C.c_int), ("elevation", C.c_int), ("kart_direct_torque", C.c_int),
                 ("n_points", C.c_int), ("s", _dp), ("track_length", C.c_double), ("track_nodes", _dp), ("wl", _dp), ("wr", _dp),
                 ("batch", C.c_int), ("vehicle_params", _dp), ("sigma", C.c_double), ("dissipation", C.c_double * 2),
-                ("q0", _dp), ("u0", _dp), ("du0", _dp), ("ctrl_default", _dp), ("device", C.c_int), ("node_params", _dp), ("wind", C.c_double * 2)]
+                ("q0", _dp), ("u0", _dp), ("du0", _dp), ("ctrl_default", _dp), ("device", C.c_int), ("node_params", _dp), ("wind", C.c_double * 2),
+                ("aug_kind", C.c_int), ("aug_jump", _dp), ("aug_bounds", C.c_double * 2), ("aug_weights", C.c_double * 5)]
 
 
 def load_library():
@@ -115,6 +116,16 @@ def _describe(lib, p, vehicle_params=None, device=0):
     d.q0, d.u0, d.du0, d.ctrl_default, d.device = _ptr(p.q0), _ptr(p.u0), _ptr(p.du0), _ptr(p.ctrl_default), int(device)
     wind = getattr(p, "wind", (0.0, 0.0))
     d.wind[0], d.wind[1] = float(wind[0]), float(wind[1])          # northward, eastward [m/s]
+    aug = getattr(p, "aug", None)
+    if aug:
+        d.aug_kind = int(aug["kind"])
+        if aug["jump"] is not None:
+            jump = np.ascontiguousarray(aug["jump"], dtype=np.float64)
+            keep.append(jump)
+            d.aug_jump = _ptr(jump)
+        d.aug_bounds[0], d.aug_bounds[1] = float(aug["bounds"][0]), float(aug["bounds"][1])
+        for k in range(5):
+            d.aug_weights[k] = float(aug["weights"][k])
     node_params = getattr(p, "node_params", None)
     if node_params is not None:
         # parameters that vary along the lap (Model_parameter, model_parameter.h:51-77): [n_points][nvp], or [batch][n_points][nvp]
@@ -175,7 +186,7 @@ class CollocationNLP:
             raise RuntimeError("fl_nlp_create: " + lib.fl_last_error().decode())
         n, m, nj, nh = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         lib.fl_nlp_sizes(self._h, C.byref(n), C.byref(m), C.byref(nj), C.byref(nh))
-        self.n, self.m, self.nnz_jac, self.nnz_hess, self.batch = n.value, m.value, nj.value, nh.value, params.shape[0]
+        self.n, self.m, self.nnz_jac, self.nnz_hess, self.batch = n.value, m.value, nj.value, nh.value, int(batch)
         self.variant = lib.fl_nlp_variant(self._h).decode()
         ops = (C.c_int * 4)()
         lib.fl_nlp_ops_per_node(self._h, ops)

@@ -67,7 +67,17 @@ typedef struct fl_problem_desc
                                    src/core/vehicles/dynamic_model_car.hpp:62-63).  vehicle_params is then ignored.       */
     double wind[2];             /* northward, eastward wind velocity [m/s] (vehicle/chassis/aerodynamics/wind_velocity/...,
                                    src/core/chassis/chassis.h:276-277; enters the aerodynamic velocity, chassis.hpp:264-288) */
+    /* One quantity that couples the whole lap in the reference -- a control optimised as a constant or on a hypermesh
+       (Control_variables::control_array_at_s, src/core/applications/detail/optimal_laptime_control_variables.h:190-222) or a restricted
+       integral quantity (limebeer2014f1.h:284-306, optimal_laptime.hpp:1316-1317, 1352-1353, 1409-1416) -- restated node-wise so the
+       NLP keeps its block structure: every node gains two variables (a, q: the value at the node / the integral up to it, and a free
+       jump) and every element one trapezoid row; see DESIGN.md.  F1, direct form, flat closed laps. */
+    int aug_kind;               /* FL_AUG_NONE, FL_AUG_BRAKE_BIAS (control constant over stretches), FL_AUG_INTEGRAL              */
+    const double* aug_jump;     /* FL_AUG_BRAKE_BIAS: [n_points], 1 where the node starts a new stretch of the hypermesh, else 0   */
+    double aug_bounds[2];       /* bounds of the control / of the integral quantity                                                */
+    double aug_weights[5];      /* FL_AUG_INTEGRAL: weights of engine-energy, tire-fl/-fr/-rl/-rr-energy in the integrand         */
 } fl_problem_desc;
+enum { FL_AUG_NONE = 0, FL_AUG_BRAKE_BIAS = 1, FL_AUG_INTEGRAL = 2 };
 
 fl_nlp* fl_nlp_create(const fl_problem_desc* desc);       /* NULL on failure */
 

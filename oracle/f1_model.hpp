@@ -76,6 +76,9 @@ struct F1Out
     // diagnostics used by the unit-level tests
     T kappa[4], lambda[4], omega_w[4], Fx_t[4], Fy_t[4], N[4];
     T dL[4];               // wheel angular-momentum balance, unscaled (axle_car_3dof.hpp:263-268)
+    // integrands of the integral quantities (vehicles/limebeer2014f1.h:291-306), per unit time: engine power [MW], minus the power
+    // dissipated by each tyre [MW] (tire/tire.h:127: F . v_slip)
+    T integrands[5];
 };
 
 // Pacejka_simple_model, tire/tire_pacejka.hpp:196-226 and tire/tire_pacejka.h:291-294
@@ -188,6 +191,7 @@ inline void f1_car(const T q[F1_NIN], const T u[F1_NCTRL], const double* P, cons
         T Fx, Fy;
         tire_forces(t, kappa, out.lambda[i], N[i], Fx, Fy);                  // tire_pacejka.hpp:107-120
         out.Fx_t[i] = Fx; out.Fy_t[i] = Fy;
+        out.integrands[1 + i] = -(Fx * (vtx - out.omega_w[i] * t.R0) + Fy * vty) * 1.0e-6;      // tire.h:127, limebeer2014f1.h:295-301
         // torque at wheel centre: cross((0,0,rc), F)
         const T Ttx = -rc[i] * Fy, Tty = rc[i] * Fx;
         if (i < 2)
@@ -216,6 +220,7 @@ inline void f1_car(const T q[F1_NIN], const T u[F1_NCTRL], const double* P, cons
         const T thr = smooth_pos(throttle, P[F1_R_SMOOTH_THROTTLE]);
         const T omega_mean = 0.5 * (out.omega_w[2] + out.omega_w[3]);
         const T engine_torque = thr * (P[F1_R_ENGINE_POWER] * 1.0e3) / omega_mean;           // actuators/engine.hpp:41-45
+        out.integrands[0] = thr * (P[F1_R_ENGINE_POWER] * 1.0e3) * 1.0e-6;                    // engine.hpp:43, limebeer2014f1.h:293
         const T diff_torque = P[F1_R_DIFF_STIFFNESS] * (out.omega_w[2] - out.omega_w[3]);
         const T boost_torque = (thr * boost) * (P[F1_R_BOOST_POWER] * 1.0e3) / omega_mean;
         Tq[2] += 0.5 * (engine_torque + boost_torque) - diff_torque;

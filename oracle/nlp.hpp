@@ -38,6 +38,15 @@ struct Desc
     int n_params = 0;                      //  model_parameter.h:51-77, applied per node at dynamic_model_car.hpp:62-63), or null
     const double* params_at(int node) const { return node_params ? node_params + (size_t)node * n_params : params; }
     double wind[2] = { 0.0, 0.0 };         // northward, eastward wind velocity [m/s] (chassis.h:276-277)
+    // One quantity that couples the whole lap in the reference, restated node-wise (the formulation of the product, see
+    // fastest_lap_b200/codegen/nlpnode.py): 1 = the brake bias as a control held constant over stretches of the lap
+    // (Control_variables::control_array_at_s with a hypermesh / constant control, detail/optimal_laptime_control_variables.h:190-222),
+    // 2 = a restricted integral quantity (limebeer2014f1.h:284-306; optimal_laptime.hpp:1316-1317, 1352-1353, 1409-1416).
+    // Every node gains the variables (a, q) after its inputs and every element one trapezoid row
+    //     a_j + rj q_j - bout_i a_i - (awout_i I_i + awin_j I_j) = 0,     I = integrand dt/ds.
+    int aug_kind = 0;
+    const double* aug_jump = nullptr;      // kind 1: [n_points], 1 where the node starts a new stretch
+    double aug_weights[5] = { 0, 0, 0, 0, 0 };   // kind 2: engine-energy, tire-fl, -fr, -rl, -rr energy
 };
 
 constexpr int MAX_ROWS = 14;
@@ -54,6 +63,7 @@ struct NodeRows
     Jet2<NV> cdot[2];          // derivative form: dcontrol_dt * dt/ds of the full-mesh controls
     Jet2<NV> ctrl[2];          // the full-mesh controls themselves
     Jet2<NV> dctrl[2];         // derivative form: dcontrols_dt variables
+    Jet2<NV> qa;               // augmented row: the value seen by the element that ENDS at the node (a + rj q)
 };
 
 struct Layout
@@ -67,6 +77,7 @@ struct Layout
     int n_nodes_var; // nodes that carry variables
     int n_elements;
     int n, m;
+    int n_aug, aug_pos;  // augmented state: count (its row is the last trapezoid row), position of `a` in the node (q follows)
 };
 
 inline Layout make_layout(const Desc& d)
@@ -91,8 +102,11 @@ inline Layout make_layout(const Desc& d)
         }
         L.n_ext = F1_NEXTRA;
         L.n_fm = 2;
-        L.nv = (F1_NIN - 1) + 2 + (deriv ? 2 : 0);
-        L.ctrl_pos[0] = 13; L.ctrl_pos[1] = 14;
+        L.n_aug = d.aug_kind ? 1 : 0;
+        L.aug_pos = F1_NIN - 1;
+        L.n_td += L.n_aug;
+        L.nv = (F1_NIN - 1) + 2 * L.n_aug + 2 + (deriv ? 2 : 0);
+        L.ctrl_pos[0] = 13 + 2 * L.n_aug; L.ctrl_pos[1] = 14 + 2 * L.n_aug;
         L.dctrl_pos[0] = 15; L.dctrl_pos[1] = 16;
     }
     else
@@ -138,6 +152,18 @@ inline void eval_node(const Desc& d, const Layout& L, int i, const double* xn, N
             for (int j = 0; j < F1_ITIME; ++j, ++k) q[j] = J::variable(xn[k], k);
             q[F1_ITIME] = J(0.0);
             for (int j = F1_ITIME + 1; j < F1_NIN; ++j, ++k) q[j] = J::variable(xn[k], k);
+            J a_var(0.0), q_var(0.0);
+            if (L.n_aug)
+            {
+                a_var = J::variable(xn[k], k); ++k;
+                q_var = J::variable(xn[k], k); ++k;
+                if (d.aug_kind == 1) u[F1_CBIAS] = a_var;
+                const bool integral = d.aug_kind == 2;
+                const double rj = integral ? 0.0 : (d.aug_jump[i] != 0.0 ? 1.0 : 0.0);
+                const double bout = (integral && i == 0) ? 0.0 : 1.0;
+                R.q[L.n_td - 1] = bout * a_var;
+                R.qa = a_var + rj * q_var;
+            }
             u[F1_CDELTA] = J::variable(xn[k], k); ++k;
             u[F1_CTHROTTLE] = J::variable(xn[k], k); ++k;
             if (deriv) { R.dctrl[0] = J::variable(xn[k], k); ++k; R.dctrl[1] = J::variable(xn[k], k); ++k; }
@@ -150,7 +176,14 @@ inline void eval_node(const Desc& d, const Layout& L, int i, const double* xn, N
         }
         F1Out<J> o;
         f1_car(q, u, d.params_at(i), tk, o);
-        for (int r = 0; r < L.n_td; ++r) { R.q[r] = o.states[L.td_ids[r]]; R.qd[r] = o.dstates[L.td_ids[r]]; }
+        for (int r = 0; r < L.n_td - L.n_aug; ++r) { R.q[r] = o.states[L.td_ids[r]]; R.qd[r] = o.dstates[L.td_ids[r]]; }
+        if (L.n_aug)
+        {
+            // integrand times dt/ds (optimal_laptime.hpp:1317, 1352)
+            J I(0.0);
+            for (int k = 0; k < 5; ++k) if (d.aug_kind == 2 && d.aug_weights[k] != 0.0) I = I + d.aug_weights[k] * o.integrands[k];
+            R.qd[L.n_td - 1] = I * o.dstates[F1_ITIME];
+        }
         for (int r = 0; r < L.n_alg; ++r) R.alg[r] = o.dstates[L.alg_ids[r]] / o.dtds;      // optimal_laptime.hpp:1341
         for (int r = 0; r < L.n_ext; ++r) R.ext[r] = o.extra[r];
         R.dtds = o.dstates[F1_ITIME];
@@ -339,7 +372,7 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
             }
 
             // trapezoidal rows (optimal_laptime.hpp:1337-1338, 1383-1384)
-            for (int r = 0; r < L.n_td; ++r, ++row)
+            for (int r = 0; r < L.n_td - L.n_aug; ++r, ++row)
             {
                 out.g[row] = B.q[r].v - A.q[r].v - h * ((1.0 - sigma) * A.qd[r].v + sigma * B.qd[r].v);
                 const double lam = lambda ? lambda[row] : 0.0;
@@ -347,6 +380,19 @@ void eval_nlp_t(const Desc& d, const double* x, const double* lambda, double obj
                 add_jac(row, j, B.q[r], 1.0);   add_jac(row, j, B.qd[r], -h * sigma);
                 add_hess(si, i, A.q[r], -lam);      add_hess(si, i, A.qd[r], -lam * h * (1.0 - sigma));
                 add_hess(sj, j, B.q[r], lam);       add_hess(sj, j, B.qd[r], -lam * h * sigma);
+            }
+            if (L.n_aug)
+            {
+                // augmented row; the closing element weights its two integrands the other way round (optimal_laptime.hpp:1409)
+                const int r = L.n_td - 1;
+                const double wa = h * (closing ? sigma : 1.0 - sigma), wb = h * (closing ? 1.0 - sigma : sigma);
+                out.g[row] = B.qa.v - A.q[r].v - (wa * A.qd[r].v + wb * B.qd[r].v);
+                const double lam = lambda ? lambda[row] : 0.0;
+                add_jac(row, i, A.q[r], -1.0);  add_jac(row, i, A.qd[r], -wa);
+                add_jac(row, j, B.qa, 1.0);     add_jac(row, j, B.qd[r], -wb);
+                add_hess(si, i, A.q[r], -lam);  add_hess(si, i, A.qd[r], -lam * wa);
+                add_hess(sj, j, B.qa, lam);     add_hess(sj, j, B.qd[r], -lam * wb);
+                ++row;
             }
             // algebraic rows (optimal_laptime.hpp:1340-1341, 1386-1387)
             for (int r = 0; r < L.n_alg; ++r, ++row)

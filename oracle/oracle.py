@@ -22,7 +22,8 @@ class _Desc(C.Structure):
                 ("s", C.POINTER(C.c_double)), ("track_length", C.c_double), ("track", C.POINTER(C.c_double)),
                 ("params", C.POINTER(C.c_double)), ("sigma", C.c_double), ("dissipation", C.c_double * 2),
                 ("q0", C.POINTER(C.c_double)), ("u0", C.POINTER(C.c_double)), ("du0", C.POINTER(C.c_double)),
-                ("ctrl_default", C.POINTER(C.c_double)), ("node_params", C.POINTER(C.c_double)), ("wind", C.c_double * 2)]
+                ("ctrl_default", C.POINTER(C.c_double)), ("node_params", C.POINTER(C.c_double)), ("wind", C.c_double * 2),
+                ("aug_kind", C.c_int), ("aug_jump", C.POINTER(C.c_double)), ("aug_weights", C.c_double * 5)]
 
 
 def build(force=False):
@@ -65,7 +66,7 @@ class OracleNLP:
     """The collocation NLP of one lap, evaluated on the CPU."""
 
     def __init__(self, model, form, closed, s, track_length, track_nodes, params, dissipation, sigma=0.5, elevation=False,
-                 ctrl_default=None, q0=None, u0=None, du0=None, kart_direct_torque=False, node_params=None, wind=(0.0, 0.0), extended=False):
+                 ctrl_default=None, q0=None, u0=None, du0=None, kart_direct_torque=False, node_params=None, wind=(0.0, 0.0), extended=False, aug=None):
         self._keep = []
         self._lib = lib_ld() if extended else lib()
 
@@ -89,6 +90,12 @@ class OracleNLP:
         d.q0, d.u0, d.du0, d.ctrl_default = _dp(arr(q0)), _dp(arr(u0)), _dp(arr(du0)), _dp(arr(ctrl_default))
         d.node_params = _dp(arr(node_params))          # [n_points][n_params]: parameters that vary along the lap, or None
         d.wind[0], d.wind[1] = float(wind[0]), float(wind[1])
+        if aug:
+            # a hypermesh / constant brake bias or a restricted integral quantity, node-wise (oracle/nlp.hpp)
+            d.aug_kind = int(aug["kind"])
+            d.aug_jump = _dp(arr(aug["jump"]))
+            for k in range(5):
+                d.aug_weights[k] = float(aug["weights"][k])
         self.desc = d
         n, m, nv, ncpe = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         mj, mh = C.c_long(), C.c_long()

@@ -26,6 +26,9 @@ struct orc_desc
     const double* ctrl_default;
     const double* node_params;     // [n_points][orc_nparams(model)] or null
     double wind[2];                // northward, eastward [m/s]
+    int aug_kind;                  // see oracle::Desc
+    const double* aug_jump;
+    double aug_weights[5];
 };
 
 static Desc to_desc(const orc_desc* c)
@@ -38,6 +41,8 @@ static Desc to_desc(const orc_desc* c)
     d.q0 = c->q0; d.u0 = c->u0; d.du0 = c->du0; d.ctrl_default = c->ctrl_default;
     d.node_params = c->node_params; d.n_params = c->model == MODEL_F1 ? (int)F1_NPARAMS : (int)K_NPARAMS;
     d.wind[0] = c->wind[0]; d.wind[1] = c->wind[1];
+    d.aug_kind = c->aug_kind; d.aug_jump = c->aug_jump;
+    for (int k = 0; k < 5; ++k) d.aug_weights[k] = c->aug_weights[k];
     return d;
 }
 

@@ -49,6 +49,21 @@ def golden_case(name, vehicle, track, sol, dissipation, **kw):
     print(name, "n =", p.n, "m =", p.m, "laptime", sol.laptime)
 
 
+def integral_case(name, vehicle, track, sol, dissipation, quantity, lower, upper):
+    """A golden run with ONE restricted integral quantity (Options::integral_quantities, f1_optimal_laptime_test.cpp:1057-1117): the file
+    holds the reference's variables (15 per node) and its multipliers -- 19 per element, then the multiplier of the integral's row.
+    Stored as they are (x_ref, lam_ref, nu); tests map them to the node-wise formulation of the integral (tests/helpers.py)."""
+    p = LapProblem.from_vehicle_track(vehicle, track, sol.s, form=FORM_DIRECT, closed=True, dissipation=dissipation)
+    x = sol.pack_x()
+    assert x.size == p.n and sol.lam.size == p.m + 1, (x.size, p.n, sol.lam.size, p.m)
+    lam = sol.lam[:p.m].copy()
+    lam.reshape(p.n_elements, p.ncpe)[:, 10] *= -1.0          # (the sign change of the roll-moment row, see golden_case)
+    pa = p.with_integral_constraint(quantity, lower, upper)
+    pa.save_npz(os.path.join(HERE, name + ".npz"), x_ref=x, lam_ref=lam, nu=sol.lam[p.m], zl_ref=sol.zl, zu_ref=sol.zu, laptime=sol.laptime,
+                iter_count=sol.iter_count)
+    print(name, "n =", pa.n, "m =", pa.m, "laptime", sol.laptime, "multiplier of the integral's row", sol.lam[p.m])
+
+
 def trajectory_case(name, track, sol):
     """x, y, psi and time the reference stored with a solution on a 3-D track, next to the centreline the track gives at
     the mesh nodes: pins api.trajectory (position = centreline + n * normal vector, road_curvilinear.hpp:17-18)."""
@@ -115,6 +130,14 @@ def main():
     # optimum is 0.56 s faster, 58.7284 s; without them the stored 59.287501 s is reproduced to 4e-10 from a cold start)
     for nm, trk in (("f1_catalunya_2022_3d", "catalunya_2022/catalunya_2022_3d.xml"), ("f1_laguna_seca_3d", "laguna_seca/laguna_seca_3d.xml")):
         golden_case(nm, f1, track_from_xml(REF + "database/tracks/" + trk, use_kerbs=False), solution_from_xml(DATA + "f1_optimal_laptime_%s.xml" % nm[3:], MODEL_F1), (50.0, 50.0 * 8.0e-4))
+
+    # f1_optimal_laptime_test.cpp:1057-1117: engine energy limited to 24 MJ (smooth throttle coefficient 1e-2, no boost power,
+    # throttle dissipation 8e-4)
+    v = f1.copy()
+    v.set_parameter("vehicle/rear-axle/smooth_throttle_coeff", 1.0e-2)
+    v.set_parameter("vehicle/rear-axle/boost/maximum-power", 0.0)
+    integral_case("f1_catalunya_engine_energy", v, catalunya, solution_from_xml(DATA + "f1_optimal_laptime_catalunya_engine_energy_limited.xml", MODEL_F1),
+                  (50.0, 8.0e-4), "engine-energy", 0.0, 24.0)
 
     trajectory_case("f1_catalunya_3d_trajectory", catalunya_3d, solution_from_xml(DATA + "f1_optimal_laptime_catalunya_3d.xml", MODEL_F1))
 

@@ -9,14 +9,38 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def load_golden(name):
-    return LapProblem.load_npz(os.path.join(GOLDEN, name + ".npz"))
+    """(problem, golden point).  Runs with a restricted integral quantity come with the point mapped to the node-wise formulation
+    (augmented_point); "f1_catalunya_hypermesh" is the Catalunya golden with the brake bias on a four-stretch hypermesh, every
+    stretch holding the vehicle's brake bias (a feasible point of that problem; there is no reference run of it with a vehicle of the database)."""
+    if name == "f1_catalunya_hypermesh":
+        p0, ex0 = LapProblem.load_npz(os.path.join(GOLDEN, "f1_catalunya_discrete.npz"))
+        p = p0.with_hypermesh_brake_bias([0.0, 1000.0, 2500.0, 4000.0])
+        ex = dict(ex0)
+        for k in ("x", "zl", "zu"):
+            v = np.zeros((p.n_points, p.nv))
+            r = ex0[k].reshape(p.n_points, p.nv - 2)
+            v[:, :p.aug_pos], v[:, p.aug_pos + 2:] = r[:, :p.aug_pos], r[:, p.aug_pos:]
+            if k == "x":
+                v[:, p.aug_pos] = p.params[18]
+            ex[k] = v.ravel()
+        row = p.ncpe - 6 - 4 - 1
+        lam = np.zeros((p.n_elements, p.ncpe))
+        lr = ex0["lam"].reshape(p.n_elements, p.ncpe - 1)
+        lam[:, :row], lam[:, row + 1:] = lr[:, :row], lr[:, row:]
+        ex["lam"] = lam.ravel()
+        return p, ex
+    p, ex = LapProblem.load_npz(os.path.join(GOLDEN, name + ".npz"))
+    if "x_ref" in ex:
+        ex = dict(ex)
+        ex["x"], ex["lam"], ex["zl"], ex["zu"] = augmented_point(p, ex)
+    return p, ex
 
 
 def oracle_nlp(p, extended=False):
     """extended: the oracle built with its jets in long double (oracle/jet.hpp) -- the arbiter of ill-conditioned entries."""
     return orc.OracleNLP(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.params, p.dissipation, p.sigma, p.elevation,
                          ctrl_default=p.ctrl_default, q0=p.q0, u0=p.u0, du0=p.du0, kart_direct_torque=p.kart_direct_torque,
-                         node_params=getattr(p, "node_params", None), wind=getattr(p, "wind", (0.0, 0.0)), extended=extended)
+                         node_params=getattr(p, "node_params", None), wind=getattr(p, "wind", (0.0, 0.0)), extended=extended, aug=getattr(p, "aug", None))
 
 
 def equality_rows(p):
@@ -142,3 +166,35 @@ def oracle_kkt(p, out):
     viol_bnd = max(np.maximum(gl - g, 0).max(), np.maximum(g - gu, 0).max(), np.maximum(xl - x, 0).max(), np.maximum(x - xu, 0).max())
     comp = max(np.abs((x - xl) * zl).max(), np.abs((xu - x) * zu).max())
     return stat, viol_eq, viol_bnd, comp
+
+
+def augmented_point(p, ex):
+    """The reference's converged point of a run with ONE restricted integral quantity (x_ref: 15 variables per node; lam_ref: 19
+    multipliers per element; nu: the multiplier of the integral's row) in the node-wise formulation of the product and the oracle
+    (codegen/nlpnode.py): per node [inputs, a, q, controls], per element one more trapezoid row after the model's.
+    a = the integral accumulated up to the node (a_0 = the whole integral), obtained from the augmented rows themselves, which are
+    linear in a; every augmented row carries the multiplier -nu, and a_0's active bound the multiplier |nu|."""
+    nv, a_pos = p.nv, p.aug_pos
+    x = np.zeros((p.n_points, nv))
+    xr = ex["x_ref"].reshape(p.n_points, nv - 2)
+    x[:, :a_pos] = xr[:, :a_pos]
+    x[:, a_pos + 2:] = xr[:, a_pos:]
+    row = p.ncpe - 6 - 4 - 1                                    # the last trapezoid row of the element (flat F1: 4 algebraic rows follow)
+    g = oracle_nlp(p).eval(x.ravel(), derivs=False)["g"].reshape(p.n_elements, p.ncpe)
+    c = -g[:, row]                                              # with a = 0: row = -(awout I_i + awin I_j)
+    a = np.zeros(p.n_points)
+    a[1:] = np.cumsum(c[:-1])
+    a[0] = a[-1] + c[-1]
+    x[:, a_pos] = a
+    lam = np.zeros((p.n_elements, p.ncpe))
+    lr = ex["lam_ref"].reshape(p.n_elements, p.ncpe - 1)
+    lam[:, :row] = lr[:, :row]
+    lam[:, row] = -float(ex["nu"])
+    lam[:, row + 1:] = lr[:, row:]
+    zl, zu = np.zeros((p.n_points, nv)), np.zeros((p.n_points, nv))
+    for z, zr in ((zl, ex["zl_ref"]), (zu, ex["zu_ref"])):
+        zr = zr.reshape(p.n_points, nv - 2)
+        z[:, :a_pos] = zr[:, :a_pos]
+        z[:, a_pos + 2:] = zr[:, a_pos:]
+    (zu if float(ex["nu"]) > 0.0 else zl)[0, a_pos] = abs(float(ex["nu"]))
+    return x.ravel(), lam.ravel(), zl.ravel(), zu.ravel()

@@ -21,7 +21,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell",
          "f1_ovaltrack_closed", "f1_ovaltrack_open", "kart_ovaltrack_derivative", "kart_catalunya_direct", "kart_catalunya_derivative",
-         "kart_catalunya_derivative_throttle", "f1_catalunya_adapted", "f1_melbourne_direct", "f1_melbourne_derivative", "f1_catalunya_2022_3d", "f1_laguna_seca_3d"]
+         "kart_catalunya_derivative_throttle", "f1_catalunya_adapted", "f1_melbourne_direct", "f1_melbourne_derivative", "f1_catalunya_2022_3d", "f1_laguna_seca_3d",
+         "f1_catalunya_engine_energy", "f1_catalunya_hypermesh"]
 RTOL = 1.0e-10
 
 
@@ -129,6 +130,8 @@ def test_ill_conditioned_entries_against_40_digit_truth(case):
     pytest.importorskip("mpmath")
     from tests.helpers import truth_node
     p, ex, nlp, o = case
+    if getattr(p, "aug", None):
+        pytest.skip("the 40-digit evaluation covers the reference's own node layout")
     x, lam, obj = _stress_point(p, ex)
     out = nlp.eval_all(x, lam, obj)
     ref = o.eval(x, lam, obj)
@@ -170,6 +173,8 @@ def test_ipopt_style_callbacks_agree_with_fused_call(case):
 
 def test_golden_point_is_a_kkt_point_on_the_gpu(case):
     p, ex, nlp, o = case
+    if getattr(p, "aug", None) and p.aug["kind"] == 1:
+        pytest.skip("the hypermesh case is a feasible point of its problem, not a converged run")
     out = nlp.eval_all(ex["x"], ex["lam"], 1.0)
     jr, jc, hr, hc = nlp.structure()
     JTl = np.zeros(p.n)

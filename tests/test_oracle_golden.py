@@ -12,7 +12,8 @@ from tests.helpers import load_golden, oracle_nlp, equality_rows
 
 CASES = ["f1_catalunya_discrete", "f1_catalunya_3d", "f1_catalunya_chicane", "f1_catalunya_chicane_derivative", "kart_vendrell",
          "f1_ovaltrack_closed", "f1_ovaltrack_open", "kart_ovaltrack_derivative", "kart_catalunya_direct", "kart_catalunya_derivative",
-         "kart_catalunya_derivative_throttle", "f1_catalunya_adapted", "f1_melbourne_direct", "f1_melbourne_derivative", "f1_catalunya_2022_3d", "f1_laguna_seca_3d"]
+         "kart_catalunya_derivative_throttle", "f1_catalunya_adapted", "f1_melbourne_direct", "f1_melbourne_derivative", "f1_catalunya_2022_3d", "f1_laguna_seca_3d",
+         "f1_catalunya_engine_energy"]
 
 
 @pytest.fixture(scope="module", params=CASES)
@@ -32,8 +33,7 @@ def test_laptime(case):
     p, ex, r = case
     # objective = lap time + control-rate penalty; lap time = sum h (0.5 dtds_i + 0.5 dtds_j) (optimal_laptime.hpp:616-634)
     o = oracle_nlp(p)
-    p0 = type(p)(p.model, p.form, p.closed, p.s, p.track_length, p.track_nodes, p.wl, p.wr, p.params, [0.0, 0.0], p.sigma, p.elevation,
-                 p.q0, p.u0, p.du0, p.ctrl_default, p.kart_direct_torque)
+    p0 = p._copy(dissipation=[0.0, 0.0])
     t = oracle_nlp(p0).eval(ex["x"], None, 1.0, derivs=False)["f"]
     t0 = 0.0 if p.closed else float(ex["time"][0])      # open sections keep integrating the time input of their first node
     assert abs(t0 + t - float(ex["laptime"])) < 1.0e-6
@@ -126,3 +126,24 @@ def test_wind_in_the_aerodynamic_force():
     assert abs(m * dv - (d1[1] - d0[1])) <= 2e-11 * max(1.0, abs(d1[1]))
     assert abs(m * dw - (d1[2] - d0[2])) <= 2e-9 * max(1.0, abs(d1[2]))
     assert abs(d1[0] - d0[0]) > 100.0          # the wind is felt
+
+
+def test_engine_energy_limited_run_is_a_kkt_point_of_the_node_wise_formulation():
+    """f1_optimal_laptime_test.cpp:1057-1117 (engine energy <= 24 MJ): the stored run, mapped to the node-wise statement of the
+    integral constraint (one accumulated-energy state per node), satisfies every row, holds 24 MJ at node 0 (EXPECT_NEAR 24, 1e-4,
+    :1115), reproduces the stored lap time and is stationary with the stored multipliers -- which pins the integrand
+    (limebeer2014f1.h:293, engine.hpp:43), its weights in the closing element (optimal_laptime.hpp:1409) and their derivatives."""
+    from tests.helpers import augmented_point
+    p, ex = load_golden("f1_catalunya_engine_energy")
+    x, lam, zl, zu = augmented_point(p, ex)
+    r = oracle_nlp(p).eval(x, lam, 1.0)
+    g = r["g"].reshape(p.n_elements, p.ncpe)
+    assert np.abs(g[:, equality_rows(p)]).max() < 1.0e-10
+    assert abs(x.reshape(p.n_points, p.nv)[0, p.aug_pos] - 24.0) < 1.0e-4
+    jr, jc, jv = r["jac"]
+    JTl = np.zeros(p.n)
+    np.add.at(JTl, jc, jv * lam[jr])
+    kkt = r["grad"] + JTl - zl + zu
+    assert np.abs(kkt).max() < 5.0e-10, np.abs(kkt).max()
+    p0 = p._copy(dissipation=[0.0, 0.0])
+    assert abs(oracle_nlp(p0).eval(x, None, 1.0, derivs=False)["f"] - float(ex["laptime"])) < 1.0e-6
