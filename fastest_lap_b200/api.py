@@ -13,8 +13,10 @@ tracks (direct form), kart (derivative form, the C API's default); <save_warm_st
 type, fastestlapc.cpp:60-71, 1712-1713) and <warm_start> restarts from it with its multipliers (:1561-1568) -- the use
 the reference makes of it is a parameter sweep with vehicle_set_parameter.  Open meshes take their first node from
 <initial_condition><q from_table=.../><u from_table=.../> (fastestlapc.cpp:1237-1249) and start from it replicated
-(:1546-1557); <write_xml> / <xml_file_name> write the reference's solution file (optimal_laptime.hpp xml()).  Hypermesh
-controls, integral constraints and sensitivities are not supported yet (a clear exception is raised).
+(:1546-1557); <write_xml> / <xml_file_name> write the reference's solution file (optimal_laptime.hpp xml()).
+<control_variables> with chassis.brake-bias optimal_control_type="constant" | "hypermesh" (+ <hypermesh>), or ONE entry of
+<integral_constraints> (engine-energy, tire-*-energy) on flat closed F1 laps: carried node-wise, see problem.py.  More than one
+of them, other controls on a hypermesh, boost-time and sensitivities raise an exception that names what was asked.
 """
 import xml.etree.ElementTree as ET
 import numpy as np
@@ -220,10 +222,17 @@ def vehicle_type_get_names(vehicle_type_name):
 # ---------------------------------------------------------------------------------------------------------------------
 def _options(options):
     root = ET.fromstring(options) if options and options.strip() else ET.Element("options")
-    for tag in ("integral_constraints", "compute_sensitivity"):
-        node = root.find(tag)
-        if node is not None and (node.text or "").strip().lower() in ("true", "1") or (tag == "integral_constraints" and node is not None and len(node)):
-            raise FastestLapError("[ERROR] optimal_laptime -> option <%s> is not supported by the B200 path yet" % tag)
+    node = root.find("compute_sensitivity")
+    if node is not None and (node.text or "").strip().lower() in ("true", "1"):
+        raise FastestLapError("[ERROR] optimal_laptime -> option <compute_sensitivity> is not supported by the B200 path yet")
+    # <integral_constraints><name><lower_bound/><upper_bound/></name></integral_constraints>: fastestlapc.cpp:1298-1306
+    integral = []
+    node = root.find("integral_constraints")
+    if node is not None:
+        for var in node:
+            if var.find("lower_bound") is None or var.find("upper_bound") is None:
+                raise FastestLapError("[ERROR] optimal_laptime -> integral constraint \"%s\" needs <lower_bound> and <upper_bound>" % var.tag)
+            integral.append((var.tag, float(var.find("lower_bound").text), float(var.find("upper_bound").text)))
     get = lambda tag, default: float(root.find(tag).text) if root.find(tag) is not None else default
     speed = get("steady_state_speed", get("initial_speed", 50.0))
     prefix = ""
@@ -231,11 +240,22 @@ def _options(options):
     if ov is not None and ov.find("prefix") is not None:
         prefix = (ov.find("prefix").text or "").strip()
     diss = None
+    hypermesh = {}           # control name -> hypermesh (a constant control = the hypermesh [0]): fastestlapc.cpp:1276-1283
     cv = root.find("control_variables")
     if cv is not None:
         vals = [float(n.find("dissipation").text) for n in cv if n.attrib.get("optimal_control_type", "") == "full-mesh" and n.find("dissipation") is not None]
         if len(vals) == 2:
             diss = vals
+        for n in cv:
+            kind = n.attrib.get("optimal_control_type", "")
+            if kind == "constant":
+                hypermesh[n.tag] = [0.0]
+            elif kind == "hypermesh":
+                if n.find("hypermesh") is None:
+                    raise FastestLapError("[ERROR] optimal_laptime -> control variable \"%s\" needs its <hypermesh>" % n.tag)
+                hypermesh[n.tag] = [float(v) for v in (n.find("hypermesh").text or "").replace(",", " ").split()]
+            elif kind not in ("dont optimize", "full-mesh"):
+                raise FastestLapError("[ERROR] Optimal control type \"%s\" not recognized" % kind)          # the reference's message
     closed = True
     if root.find("closed_simulation") is not None:
         closed = (root.find("closed_simulation").text or "").strip().lower() in ("true", "1")
@@ -262,7 +282,7 @@ def _options(options):
         if root.find("xml_file_name") is None:
             raise FastestLapError("[ERROR] optimal_laptime -> <write_xml> needs <xml_file_name>")
         xml_file = (root.find("xml_file_name").text or "").strip()
-    return dict(q_start=q_start, u_start=u_start, xml_file=xml_file, var_bounds=var_bounds, warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
+    return dict(integral=integral, hypermesh=hypermesh, q_start=q_start, u_start=u_start, xml_file=xml_file, var_bounds=var_bounds, warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
 
 
 def _kart_start_node(vehicle, speed, form):
@@ -336,6 +356,25 @@ def optimal_laptime(vehicle, track, s, options=""):
             raise FastestLapError("[ERROR] optimal_laptime -> the warm start was saved for another track")
     p = LapProblem.from_vehicle_track(veh, trk, s, form=form, closed=closed, dissipation=o["dissipation"], sigma=o["sigma"],
                                       q0=o["q_start"], u0=o["u_start"])
+    # One quantity that couples the whole lap -- the brake bias on a hypermesh / as a constant, or one restricted integral quantity --
+    # is carried node-wise (problem.py, codegen/nlpnode.py); more than one, or another control, is refused by name
+    if o["hypermesh"] or o["integral"]:
+        try:
+            if len(o["hypermesh"]) + len(o["integral"]) > 1:
+                raise ValueError("one hypermesh / constant control or one integral constraint per optimal_laptime call (asked: %s)" %
+                                 ", ".join(list(o["hypermesh"]) + [q[0] for q in o["integral"]]))
+            if o["hypermesh"]:
+                (name, sh), = o["hypermesh"].items()
+                if veh.model != MODEL_F1 or name != "chassis.brake-bias":
+                    raise ValueError("control \"%s\": only the F1's chassis.brake-bias can be optimised as a constant / on a hypermesh" % name)
+                p = p.with_hypermesh_brake_bias(sh)
+            else:
+                p = p.with_integral_constraint(*o["integral"][0])
+        except ValueError as e:
+            raise FastestLapError("[ERROR] optimal_laptime -> %s" % e)
+        if o["warm_start"] or o["save_warm_start"] or o["var_bounds"] or o["xml_file"]:
+            raise FastestLapError("[ERROR] optimal_laptime -> <warm_start>, <save_warm_start>, <variable_bounds> and <write_xml> together with "
+                                  "hypermesh controls or integral constraints are not supported")
     if o["warm_start"]:
         x0, warm = ws["x"], (ws["lam"], ws["zl"], ws["zu"])
     elif not closed:
@@ -395,6 +434,10 @@ def optimal_laptime(vehicle, track, s, options=""):
     if out["status"][0] < 1:
         raise FastestLapError("[ERROR] optimal_laptime -> the optimization did not converge (status %d)" % out["status"][0])
     X = out["x"][0].reshape(-1, p.nv)
+    aug_values = None
+    if p.aug:
+        aug_values = X[:, p.aug_pos].copy()                   # the control at every node / the integral accumulated up to the node
+        X = np.delete(X, [p.aug_pos, p.aug_pos + 1], axis=1)  # back to the reference's node layout
     if not closed:
         X = np.vstack([node, X])          # the fixed first node
     iu, iv = (4, 5) if veh.model == MODEL_F1 else (1, 2)
@@ -415,7 +458,12 @@ def optimal_laptime(vehicle, track, s, options=""):
         else:
             put(nm, X[:, k].copy()); k += 1
     for c, nm in enumerate(controls):
-        put(nm, X[:, k + full_mesh.index(c)].copy() if c in full_mesh else np.full(p.n_points, p.ctrl_default[c]))
+        if p.aug and p.aug["kind"] == 1 and nm == "chassis.brake-bias":
+            put(nm, aug_values)                                # constant inside every stretch of the hypermesh
+        else:
+            put(nm, X[:, k + full_mesh.index(c)].copy() if c in full_mesh else np.full(p.n_points, p.ctrl_default[c]))
+    if p.aug and p.aug["kind"] == 2:
+        put("integral_quantities." + p.aug["name"], float(aug_values[0]))      # fastestlapc.cpp:1619-1641
     put("x", xyz[:, 0].copy()); put("y", xyz[:, 1].copy()); put("psi", yaw + X[:, a_col])
     put("laptime", laptime)
     put("optimization_data.number_of_iterations", float(out["iters"][0]))

@@ -473,6 +473,12 @@ struct LapOptions
     bool have_diss = false;
     string prefix;
     int print_level = 0;
+    // one quantity that couples the whole lap, carried node-wise (include/fastestlap_b200.h, aug_*): the brake bias as a constant /
+    // on a hypermesh (fastestlapc.cpp:1276-1283) or one restricted integral quantity (:1298-1306)
+    int aug_kind = FL_AUG_NONE;
+    vec hypermesh;
+    string integral_name;
+    double integral_bounds[2] = { 0.0, 0.0 };
 };
 
 static LapOptions lap_options(const string& text, int model)
@@ -482,10 +488,16 @@ static LapOptions lap_options(const string& text, int model)
     if (model == FL_MODEL_F1_3DOF) { o.diss[0] = 50.0; o.diss[1] = 20.0 * 8.0e-4; } else { o.diss[0] = 1.0e-2; o.diss[1] = 200.0 * 200.0 * 1.0e-10; }
     if (trim(text).empty()) return o;
     const auto root = parse_xml(text);
-    for (const char* tag : { "integral_constraints", "compute_sensitivity" })
-        if (const Xml* n = root->child(tag))
-            if (truthy(n) || (string(tag) == "integral_constraints" && !n->kids.empty()))
-                throw error(string("[ERROR] optimal_laptime -> option <") + tag + "> is not supported by the B200 path");
+    if (truthy(root->child("compute_sensitivity"))) throw error("[ERROR] optimal_laptime -> option <compute_sensitivity> is not supported by the B200 path");
+    int n_coupling = 0;
+    if (const Xml* ic = root->child("integral_constraints"))
+        for (auto& q : ic->kids)
+        {
+            if (!q->child("lower_bound") || !q->child("upper_bound")) throw error("[ERROR] optimal_laptime -> integral constraint \"" + q->tag + "\" needs <lower_bound> and <upper_bound>");
+            o.aug_kind = FL_AUG_INTEGRAL; o.integral_name = q->tag;
+            o.integral_bounds[0] = numbers(q->child("lower_bound")->text).at(0); o.integral_bounds[1] = numbers(q->child("upper_bound")->text).at(0);
+            ++n_coupling;
+        }
     if (const Xml* n = root->child("closed_simulation")) if (!truthy(n)) throw error("[ERROR] optimal_laptime -> open simulations are served by the Python surface (fastest_lap_b200.api), not by this C entry yet");
     if (truthy(root->child("warm_start"))) throw error("[ERROR] optimal_laptime -> <warm_start> is served by the Python surface (fastest_lap_b200.api), not by this C entry yet");
     if (const Xml* n = root->child("initial_speed")) o.speed = numbers(n->text).at(0);
@@ -499,11 +511,21 @@ static LapOptions lap_options(const string& text, int model)
         for (auto& c : cv->kids)
         {
             const string type = c->attr.count("optimal_control_type") ? c->attr.at("optimal_control_type") : "";
-            if (type == "constant" || type == "hypermesh") throw error("[ERROR] optimal_laptime -> optimal_control_type \"" + type + "\" is not supported by the B200 path");
-            if (type == "full-mesh") if (const Xml* q = c->child("dissipation")) d.push_back(numbers(q->text).at(0));
+            if (type == "constant" || type == "hypermesh")
+            {
+                if (model != FL_MODEL_F1_3DOF || c->tag != "chassis.brake-bias")
+                    throw error("[ERROR] optimal_laptime -> control \"" + c->tag + "\": only the F1's chassis.brake-bias can be optimised as a constant / on a hypermesh");
+                if (type == "hypermesh" && !c->child("hypermesh")) throw error("[ERROR] optimal_laptime -> control variable \"" + c->tag + "\" needs its <hypermesh>");
+                o.aug_kind = FL_AUG_BRAKE_BIAS;
+                o.hypermesh = type == "constant" ? vec{ 0.0 } : numbers(c->child("hypermesh")->text);
+                ++n_coupling;
+            }
+            else if (type == "full-mesh") { if (const Xml* q = c->child("dissipation")) d.push_back(numbers(q->text).at(0)); }
+            else if (type != "dont optimize") throw error("[ERROR] Optimal control type \"" + type + "\" not recognized");
         }
         if (d.size() == 2) { o.diss[0] = d[0]; o.diss[1] = d[1]; }
     }
+    if (n_coupling > 1) throw error("[ERROR] optimal_laptime -> one hypermesh / constant control or one integral constraint per optimal_laptime call");
     return o;
 }
 
@@ -545,6 +567,26 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     d.node_params = node_params.empty() ? nullptr : node_params.data();
     d.wind[0] = veh.wind[0]; d.wind[1] = veh.wind[1];
     (void)nvp;
+    vec jump(np, 0.0);
+    static const char* IQ[5] = { "engine-energy", "tire-fl-energy", "tire-fr-energy", "tire-rl-energy", "tire-rr-energy" };
+    if (o.aug_kind == FL_AUG_BRAKE_BIAS)
+    {
+        // stretch of a node = the last hypermesh point <= s (control_array_at_s, optimal_laptime_control_variables.h:190-222)
+        const vec& sh = o.hypermesh;
+        if (sh.empty() || std::fabs(sh[0]) > 1.0e-12 || sh.back() >= trk.length) throw error("[ERROR] optimal_laptime -> the hypermesh starts at s = 0 and ends before the track length");
+        for (size_t k = 1; k < sh.size(); ++k) if (!(sh[k] > sh[k - 1])) throw error("[ERROR] optimal_laptime -> the hypermesh must increase strictly");
+        std::vector<int> stretch(np);
+        for (int i = 0; i < np; ++i) stretch[i] = (int)(std::upper_bound(sh.begin(), sh.end(), s[i]) - sh.begin()) - 1;
+        for (int i = 0; i < np; ++i) jump[i] = stretch[i] != stretch[(i + np - 1) % np] ? 1.0 : 0.0;
+        d.aug_kind = FL_AUG_BRAKE_BIAS; d.aug_jump = jump.data(); d.aug_bounds[0] = 0.0; d.aug_bounds[1] = 1.0;
+    }
+    else if (o.aug_kind == FL_AUG_INTEGRAL)
+    {
+        int which = -1;
+        for (int k = 0; k < 5; ++k) if (o.integral_name == IQ[k]) which = k;
+        if (!f1 || which < 0) throw error("[ERROR] optimal_laptime -> integral quantity \"" + o.integral_name + "\" is not offered (engine-energy, tire-fl/-fr/-rl/-rr-energy of the F1)");
+        d.aug_kind = FL_AUG_INTEGRAL; d.aug_weights[which] = 1.0; d.aug_bounds[0] = o.integral_bounds[0]; d.aug_bounds[1] = o.integral_bounds[1];
+    }
     fl_nlp* nlp = fl_nlp_create(&d);
     if (!nlp) throw error("[ERROR] optimal_laptime -> " + fl_error());
     int n = 0, m = 0;
@@ -562,7 +604,9 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         fl_ipm_opts io;
         fl_ipm_default_options(&io);
         if (attempt > 0) io.mu_init = 1.0;
-        const vec node = start_node(v0, factors[attempt] * o.speed * KMH, form == FL_FORM_DERIVATIVE);
+        vec node = start_node(v0, factors[attempt] * o.speed * KMH, form == FL_FORM_DERIVATIVE);
+        if (o.aug_kind != FL_AUG_NONE)      // (a, q) after the inputs: the vehicle's brake bias / the middle of the integral's bounds; no jump
+            node.insert(node.begin() + (n_in - 1), { o.aug_kind == FL_AUG_BRAKE_BIAS ? std::min(std::max(v0.params[18], 0.0), 1.0) : 0.5 * (o.integral_bounds[0] + o.integral_bounds[1]), 0.0 });
         vec x0(n);
         for (int i = 0; i < np; ++i) std::copy(node.begin(), node.begin() + NV, x0.begin() + (size_t)i * NV);
         fl_ipm* ipm = fl_ipm_create(nlp, &io, nullptr, nullptr, nullptr, nullptr);
@@ -576,12 +620,29 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     if (!msg.empty()) throw error("[ERROR] optimal_laptime -> " + msg);
     if (status[0] < 1) throw error("[ERROR] optimal_laptime -> the optimization did not converge (status " + std::to_string(status[0]) + ")");
 
+    // the augmented variables leave the node: what follows reads the reference's layout
+    vec aug_values;
+    int NVo = NV;
+    if (o.aug_kind != FL_AUG_NONE)
+    {
+        NVo = NV - 2;
+        vec Y((size_t)np * NVo);
+        aug_values.resize(np);
+        for (int i = 0; i < np; ++i)
+        {
+            const double* x = X.data() + (size_t)i * NV;
+            aug_values[i] = x[n_in - 1];
+            std::copy(x, x + (n_in - 1), Y.begin() + (size_t)i * NVo);
+            std::copy(x + (n_in + 1), x + NV, Y.begin() + (size_t)i * NVo + (n_in - 1));
+        }
+        X = Y;
+    }
     // ---- outputs (optimal_laptime.hpp:598-631): time by the trapezoid rule of dt/ds, position = centreline + n * normal, psi = alpha + theta
     const int iu = f1 ? 4 : 1, iv = f1 ? 5 : 2, n_col = n_in - 3, a_col = n_in - 2;
     vec dtds(np), time(np, 0.0), xs(np), ys(np), psi(np);
     for (int i = 0; i < np; ++i)
     {
-        const double* x = X.data() + (size_t)i * NV;
+        const double* x = X.data() + (size_t)i * NVo;
         const double th = nodes[(size_t)i * 6], mu = nodes[(size_t)i * 6 + 1], ph = nodes[(size_t)i * 6 + 2];
         const double kz = -std::sin(ph) * nodes[(size_t)i * 6 + 4] + std::cos(mu) * std::cos(ph) * nodes[(size_t)i * 6 + 3];
         dtds[i] = (1.0 - x[n_col] * kz) / (x[iu] * std::cos(x[a_col]) - x[iv] * std::sin(x[a_col]));
@@ -609,7 +670,7 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     {
         if (string(in_names[i]) == "time") { out_vec("time", time); continue; }
         vec col(np);
-        for (int q = 0; q < np; ++q) col[q] = X[(size_t)q * NV + k];
+        for (int q = 0; q < np; ++q) col[q] = X[(size_t)q * NVo + k];
         out_vec(in_names[i], col);
         ++k;
     }
@@ -617,12 +678,18 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     for (int c = 0; c < n_ctrl; ++c)
     {
         vec col(np, ctrl_default[c]);
+        if (o.aug_kind == FL_AUG_BRAKE_BIAS && c == 3) col = aug_values;          // constant inside every stretch
         for (int fm = 0; fm < 2; ++fm)
-            if (full_mesh[fm] == c) for (int q = 0; q < np; ++q) col[q] = X[(size_t)q * NV + k + fm];
+            if (full_mesh[fm] == c) for (int q = 0; q < np; ++q) col[q] = X[(size_t)q * NVo + k + fm];
         out_vec(ct_names[c], col);
     }
     out_vec("x", xs); out_vec("y", ys); out_vec("psi", psi);
     overwrite(pre + "laptime"); scalars[pre + "laptime"] = laptime;
+    if (o.aug_kind == FL_AUG_INTEGRAL)                                           // fastestlapc.cpp:1619-1641
+    {
+        overwrite(pre + "integral_quantities." + o.integral_name);
+        scalars[pre + "integral_quantities." + o.integral_name] = aug_values[0];
+    }
     overwrite(pre + "optimization_data.number_of_iterations"); scalars[pre + "optimization_data.number_of_iterations"] = (double)iters[0];
 }
 

@@ -156,7 +156,39 @@ def test_readme_example_through_the_c_api(lib, files):
     lib.download_vector(t, c.c_int(500), b("run/time"))
     assert np.max(np.abs(np.array(t) - gold["time"])) <= 1e-5
     lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><integral_constraints><x><upper_bound>1</upper_bound></x></integral_constraints></options>"))
-    assert "not supported" in err(lib)
+    assert "needs <lower_bound> and <upper_bound>" in err(lib)
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><integral_constraints><boost-time><lower_bound>0</lower_bound><upper_bound>10</upper_bound></boost-time></integral_constraints></options>"))
+    assert "is not offered" in err(lib)
+    lib.delete_variable(b"*")
+
+
+@pytest.mark.gpu
+def test_engine_energy_limited_lap_through_the_c_api(lib, files):
+    """<integral_constraints> of the C entry (fastestlapc.cpp:1298-1306) on the vehicle of Catalunya_engine_energy_limited
+    (f1_optimal_laptime_test.cpp:1057-1117: smooth throttle coefficient 1e-2, no boost power, throttle dissipation 8e-4): the lap
+    ends with 24 MJ of engine energy and within 2e-4 of the stored lap time (several local optima, tests/test_gpu_ipm.py); the
+    brake bias as a constant control comes back constant."""
+    lib.delete_variable(b"*")
+    lib.create_vehicle_from_xml(b("car"), b(files["f1"]))
+    lib.vehicle_set_parameter(b("car"), b("vehicle/rear-axle/smooth_throttle_coeff"), c.c_double(1.0e-2))
+    lib.vehicle_set_parameter(b("car"), b("vehicle/rear-axle/boost/maximum-power"), c.c_double(0.0))
+    lib.create_track_from_xml(b("catalunya"), b(files["catalunya"]))
+    s = np.linspace(0.0, lib.track_download_length(b("catalunya")), 501)[:-1]
+    c_s = (c.c_double * len(s))(*s)
+    options = ("<options><integral_constraints><engine-energy><lower_bound>0.0</lower_bound><upper_bound>24.0</upper_bound></engine-energy></integral_constraints>"
+               "<control_variables><front-axle.steering-angle optimal_control_type=\"full-mesh\"><dissipation>50.0</dissipation></front-axle.steering-angle>"
+               "<chassis.throttle optimal_control_type=\"full-mesh\"><dissipation>8.0e-4</dissipation></chassis.throttle></control_variables>"
+               "<output_variables><prefix>en/</prefix></output_variables></options>")
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b(options))
+    assert err(lib) == ""
+    assert abs(lib.download_scalar(b("en/integral_quantities.engine-energy")) - 24.0) <= 1e-4
+    assert abs(lib.download_scalar(b("en/laptime")) - 79.733713) <= 2e-4 * 79.733713
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s,
+                        b("<options><control_variables><chassis.brake-bias optimal_control_type=\"constant\"/></control_variables><output_variables><prefix>bb/</prefix></output_variables></options>"))
+    assert err(lib) == ""
+    bb = (c.c_double * 500)()
+    lib.download_vector(bb, c.c_int(500), b("bb/chassis.brake-bias"))
+    assert np.ptp(np.array(bb)) <= 1e-9 and 0.3 < bb[0] < 0.9
     lib.delete_variable(b"*")
 
 

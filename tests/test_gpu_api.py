@@ -172,3 +172,38 @@ def test_variable_bounds_option(tmp_path):
         api.optimal_laptime("car", "catalunya", s, "<options><variable_bounds><chassis.velocity.x><max>70.0</max></chassis.velocity.x></variable_bounds></options>")
     with pytest.raises(api.FastestLapError, match="not found"):
         api.optimal_laptime("car", "catalunya", s, "<options><variable_bounds><chassis.speed><upper>70.0</upper></chassis.speed></variable_bounds></options>")
+
+
+def test_hypermesh_control_and_integral_constraint_options(tmp_path):
+    """<control_variables><chassis.brake-bias optimal_control_type="hypermesh"> and <integral_constraints> (fastestlapc.cpp:1255-1306):
+    the brake bias comes back constant inside each stretch and the lap is not slower than with the fixed bias; with the engine
+    energy restricted to 26 MJ the integral ends at its bound and the lap is slower; what is not offered raises by name."""
+    from fastest_lap_b200 import api, workloads
+    from fastest_lap_b200.track import track_from_npz
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api.create_vehicle_from_xml("car", paths["f1"])
+    api._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    s = np.linspace(0.0, api.track_download_length("catalunya"), 501)[:-1]
+    api.optimal_laptime("car", "catalunya", s, "<options><output_variables><prefix>free/</prefix></output_variables></options>")
+    api.optimal_laptime("car", "catalunya", s, "<options><control_variables><chassis.brake-bias optimal_control_type=\"hypermesh\"><hypermesh>0.0, 2000.0</hypermesh>"
+                                               "</chassis.brake-bias></control_variables><output_variables><prefix>hm/</prefix></output_variables></options>")
+    bb = api.download_vector("hm/chassis.brake-bias")
+    first = s < 2000.0
+    assert np.ptp(bb[first]) <= 1e-9 and np.ptp(bb[~first]) <= 1e-9 and 0.0 < bb.min() and bb.max() < 1.0
+    assert api.download_scalar("hm/laptime") <= api.download_scalar("free/laptime") + 1e-6
+    # "Engine energy limits require a higher value of the smooth throttle coefficient" (f1_optimal_laptime_test.cpp:1068-1069)
+    api.vehicle_set_parameter("car", "vehicle/rear-axle/smooth_throttle_coeff", 1.0e-2)
+    _, names = api.optimal_laptime("car", "catalunya", s, "<options><integral_constraints><engine-energy><lower_bound>0.0</lower_bound><upper_bound>26.0</upper_bound>"
+                                                          "</engine-energy></integral_constraints><output_variables><prefix>en/</prefix></output_variables></options>")
+    assert "integral_quantities.engine-energy" in names
+    assert abs(api.download_scalar("en/integral_quantities.engine-energy") - 26.0) <= 1e-4
+    assert api.download_scalar("en/laptime") > api.download_scalar("free/laptime") + 0.1
+    assert api.download_vector("en/chassis.velocity.x").shape == (500,)
+    with pytest.raises(api.FastestLapError, match="one hypermesh / constant control or one integral constraint"):
+        api.optimal_laptime("car", "catalunya", s, "<options><integral_constraints><tire-fl-energy><lower_bound>0</lower_bound><upper_bound>0.8</upper_bound></tire-fl-energy>"
+                                                   "<tire-fr-energy><lower_bound>0</lower_bound><upper_bound>0.8</upper_bound></tire-fr-energy></integral_constraints></options>")
+    with pytest.raises(api.FastestLapError, match="boost-time"):
+        api.optimal_laptime("car", "catalunya", s, "<options><integral_constraints><boost-time><lower_bound>0</lower_bound><upper_bound>10</upper_bound></boost-time></integral_constraints></options>")
+    with pytest.raises(api.FastestLapError, match="only the F1's chassis.brake-bias"):
+        api.optimal_laptime("car", "catalunya", s, "<options><control_variables><chassis.throttle optimal_control_type=\"constant\"/></control_variables></options>")
