@@ -12,6 +12,8 @@ controls through the control-rate penalty), so eval_grad_f / eval_jac_g / eval_h
 The variable order inside a node is the reference's (optimal_laptime.hpp:1269-1285): inputs without `time`, then the
 full-mesh controls, then (derivative form) their rates.
 """
+import os
+
 from .expr import Graph, E
 from . import models
 
@@ -99,6 +101,9 @@ class NodeProgram:
         if v.elevation:
             self.track_names = ["kx", "ky", "kz", "smu", "cmu", "sph", "cph", "wt", "wn", "wb"]
             trk = {n: S("t_" + n, "t") for n in self.track_names}
+        elif os.environ.get("FL_NO_WIND"):          # experiment: the node programs without the wind terms
+            self.track_names = ["kz"]
+            trk = dict(kx=0.0, ky=0.0, kz=S("t_kz", "t"), smu=0.0, cmu=1.0, sph=0.0, cph=1.0, wt=0.0, wn=0.0, wb=0.0)
         else:
             self.track_names = ["kz", "wt", "wn"]
             trk = dict(kx=0.0, ky=0.0, kz=S("t_kz", "t"), smu=0.0, cmu=1.0, sph=0.0, cph=1.0, wt=S("t_wt", "t"), wn=S("t_wn", "t"), wb=0.0)

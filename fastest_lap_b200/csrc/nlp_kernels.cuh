@@ -87,10 +87,13 @@ constexpr int FL_ABLOCK = FL_DBLOCK;
 // ---------------------------------------------------------------------------------------------------------------------
 // Parameter vector of a problem handed over as a kernel argument: when every problem of the batch drives the same vehicle
 // (a single lap, replicas, G-G sweeps) the generated code reads D[k] as a constant-bank operand of the arithmetic
-// instruction itself -- no load, no register (CD = true).  Batches with per-problem vehicles read D from global memory.
+// instruction itself -- no load, no register (CD = FL_D_CONST).  Batches with per-problem vehicles read D from global memory at an
+// address that is uniform over the block (FL_D_LAP: it stays in uniform registers); parameters that vary along the lap are read per
+// node (FL_D_NODE).
+enum { FL_D_LAP = 0, FL_D_CONST = 1, FL_D_NODE = 2 };
 template <class G> struct DVec { double d[G::ND]; };
 
-template <class G, bool CD>
+template <class G, int CD>
 struct ValuesIO
 {
     const double* xn; const double* tcn; const double* Dp; const DVec<G>* Dk; double* Vn; double* Cn;
@@ -102,7 +105,7 @@ struct ValuesIO
     __device__ __forceinline__ double unext(int c) const { return xq[G::ctrl_pos(c)]; }
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
     __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
-    __device__ __forceinline__ double d(int k) const { if constexpr (CD) return Dk->d[k]; else return __ldg(Dp + k); }
+    __device__ __forceinline__ double d(int k) const { if constexpr (CD == FL_D_CONST) return Dk->d[k]; else return __ldg(Dp + k); }
     __device__ __forceinline__ void val(int k, double v) const { Vn[k * 32] = v; }
     __device__ __forceinline__ void cs(int k, double v) const { Cn[k * 32] = v; }
     __device__ __forceinline__ void fence(double) const {}
@@ -110,7 +113,7 @@ struct ValuesIO
 
 // TAPE: the values pass of a full round (Jacobian and Hessian): it also writes the shared part of the primal / adjoint
 // tape, which depends on the multipliers (codegen/generate.py shared_tape), for the derivative partitions to load.
-template <class G, bool CD, bool TAPE>
+template <class G, int CD, bool TAPE>
 __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
 {
     // programmatic dependent launch: the derivative grid that follows may be scheduled while this one runs; it waits
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant_
     ValuesIO<G, CD> io;
     io.xn = P.x + ((size_t)prob * P.n_points + node) * G::NV;
     io.tcn = P.tc + fl_chunk_base(node, G::NTC);
-    io.Dp = P.D + (size_t)prob * P.d_prob_stride + (size_t)node * P.d_node_stride;
+    io.Dp = CD == FL_D_NODE ? P.D + (size_t)prob * P.d_prob_stride + (size_t)node * P.d_node_stride : P.D + (size_t)prob * G::ND;
     io.Dk = &Dk;
     io.Vn = P.V + (size_t)prob * G::NVAL * P.n_pad + fl_chunk_base(node, G::NVAL);
     io.Cn = P.C + (size_t)prob * G::NCK * P.n_pad + fl_chunk_base(node, G::NCK);
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(FL_ABLOCK) k_assemble(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <class G, bool CD>
+template <class G, int CD>
 struct DerivIO
 {
     const double* xn; const double* xp; const double* xq;     // this node, previous node, next node
@@ -272,7 +275,7 @@ struct DerivIO
     bool hasB, hasC;
     __device__ __forceinline__ double x(int k) const { return xn[k]; }
     __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
-    __device__ __forceinline__ double d(int k) const { if constexpr (CD) return Dk->d[k]; else return __ldg(Dp + k); }
+    __device__ __forceinline__ double d(int k) const { if constexpr (CD == FL_D_CONST) return Dk->d[k]; else return __ldg(Dp + k); }
     __device__ __forceinline__ double c(int k) const { return Cn[k * 32]; }          // global workspace, or the warp's staged copy in shared memory
     __device__ __forceinline__ double lin(int r) const { return lin_[r]; }
     __device__ __forceinline__ double lout(int r) const { return lout_[r]; }
@@ -309,7 +312,7 @@ template <class G> struct deriv_parts<G, FL_DERIV_ALL>  { static constexpr int N
 // offsets instead of ~70 dependent global loads per partition (the long-scoreboard stalls of profiles/prof_r1g).
 template <class G> constexpr size_t fl_stage_bytes() { return FL_STAGE ? (size_t)(FL_DBLOCK / 32) * (G::NCK * 256 + 8) : 0; }
 
-template <class G, int WHAT, bool ASSEMBLE, bool CD>
+template <class G, int WHAT, bool ASSEMBLE, int CD>
 __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the values pass this launch may overlap with has completed
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __gri
     io.xp = xb + (size_t)prev * G::NV;
     io.xq = xb + (size_t)next * G::NV;
     io.tcn = P.tc + fl_chunk_base(node, G::NTC);
-    io.Dp = P.D + (size_t)prob * P.d_prob_stride + (size_t)node * P.d_node_stride;
+    io.Dp = CD == FL_D_NODE ? P.D + (size_t)prob * P.d_prob_stride + (size_t)node * P.d_node_stride : P.D + (size_t)prob * G::ND;
     io.lin_ = lam + (size_t)e_in * G::NCPE;
     io.lout_ = has_out ? lam + (size_t)e_out * G::NCPE : P.zeros;
     io.obj_ = P.obj_factor;
@@ -433,23 +436,25 @@ struct variant_ops
         {
             if (tape)
             {
-                if (shared_d) k_node_values<G, true, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
-                else k_node_values<G, false, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+                if (shared_d) k_node_values<G, FL_D_CONST, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+                else if (P.d_node_stride) k_node_values<G, FL_D_NODE, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+                else k_node_values<G, FL_D_LAP, true><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
                 return;
             }
         }
-        if (shared_d) k_node_values<G, true, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
-        else k_node_values<G, false, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        if (shared_d) k_node_values<G, FL_D_CONST, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        else if (P.d_node_stride) k_node_values<G, FL_D_NODE, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+        else k_node_values<G, FL_D_LAP, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
     }
     static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<dim3((P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK, P.batch, 1), FL_ABLOCK, 0, s>>>(P); }
     static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK; }
-    template <bool CD>
+    template <int CD>
     static void derivs_cd(const fl_dev& P, const DVec<G>& Dk, int what, int with_assemble, cudaStream_t s)
     {
         // n_elements <= n_var_nodes + 1: one more block column covers the assembly slice of an open problem
         const unsigned nb = (P.n_points + FL_DBLOCK - 1) / FL_DBLOCK;
         const size_t sm = fl_stage_bytes<G>();
-        static unsigned long long attr_set = 0;          // per device
+        static unsigned long long attr_set = 0;          // per device (and per instantiation of this function)
         int dev = 0;
         cudaGetDevice(&dev);
         if (!((attr_set >> dev) & 1ull) && sm > 48 * 1024)
@@ -477,8 +482,9 @@ struct variant_ops
     {
         DVec<G> Dk;
         memcpy(Dk.d, D0, sizeof(Dk.d));
-        if (shared_d) derivs_cd<true>(P, Dk, what, with_assemble, s);
-        else derivs_cd<false>(P, Dk, what, with_assemble, s);
+        if (shared_d) derivs_cd<FL_D_CONST>(P, Dk, what, with_assemble, s);
+        else if (P.d_node_stride) derivs_cd<FL_D_NODE>(P, Dk, what, with_assemble, s);
+        else derivs_cd<FL_D_LAP>(P, Dk, what, with_assemble, s);
     }
     static fl_variant make()
     {
