@@ -206,6 +206,10 @@ def track_download_data(track_name, variable_name):
     t = _get(track_name, Track)
     keys = {"arclength": None, "centerline.x": "x", "centerline.y": "y", "heading-angle": "yaw", "curvature": "yaw_dot",
             "distance-left-boundary": "nl", "distance-right-boundary": "nr"}
+    if variable_name in ("left.x", "left.y", "right.x", "right.y"):
+        # track boundaries: centreline -+ distance * (sin(theta), -cos(theta)) (fastestlapc.cpp track_download_data)
+        x, y, xl, yl, xr, yr, _ = track_coordinates(track_name)
+        return {"left.x": xl, "left.y": yl, "right.x": xr, "right.y": yr}[variable_name]
     if variable_name not in keys:
         raise FastestLapError("[ERROR] track_download_data -> variable_name \"%s\" is not valid" % variable_name)
     return t.s_data.copy() if keys[variable_name] is None else t(keys[variable_name], t.s_data)

@@ -32,6 +32,17 @@
 // words to consecutive rows touches all 32 banks once
 __host__ __device__ constexpr int kw_ld(int n) { return n % 4 == 2 ? n : (n % 4 == 3 ? n + 3 : (n % 4 == 0 ? n + 2 : n + 1)); }
 
+// factor stores: written once per factorisation and read back by the solves after the whole batch has been factorised -- streaming
+// (evict-first) so that they do not push the Jacobian / Hessian values of the coming stages out of the L2
+#ifndef FL_KW_STREAM
+#define FL_KW_STREAM 1
+#endif
+#if FL_KW_STREAM
+#define KW_STORE(p, v) __stcs((p), (v))
+#else
+#define KW_STORE(p, v) (*(p) = (v))
+#endif
+
 template <int NV, int NEQ>
 struct kw_smem
 {
@@ -359,7 +370,7 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
             if (j >= 1)
             {
                 St::gather_coupling(K, Lc, lap, j, lane);
-                for (int k = lane; k < (NEQ + 1) * LDV; k += 32) gL[(size_t)j * NB * NV + k] = Lc[k];
+                for (int k = lane; k < (NEQ + 1) * LDV; k += 32) KW_STORE(&gL[(size_t)j * NB * NV + k], Lc[k]);
             }
             if (cyc && j == 1)
             {
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
                 }
             }
             else if (cyc && j >= 2)
-                for (int k = lane; k < NV * FT; k += 32) gF[(size_t)j * NB * NB + k] = Ft[k];
+                for (int k = lane; k < NV * FT; k += 32) KW_STORE(&gF[(size_t)j * NB * NB + k], Ft[k]);
             const int neg_before = n_neg, zero_before = n_zero;
             kw_invert<NB>(m, diag, sm.pr, lane, n_neg, n_zero);
             if (Lp)
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
             if (lane < NB)
             {
 #pragma unroll
-                for (int c = 0; c < NB; ++c) gD[(size_t)j * NB * NB + lane + NB * c] = m[c];
+                for (int c = 0; c < NB; ++c) KW_STORE(&gD[(size_t)j * NB * NB + lane + NB * c], m[c]);
             }
             if (j == 0) break;
             if (cyc && j == 1)

@@ -49,6 +49,9 @@ def test_track_data():
     nl, nr = api.track_download_data("catalunya", "distance-left-boundary"), api.track_download_data("catalunya", "distance-right-boundary")
     np.testing.assert_allclose(np.hypot(xl - x, yl - y), nl, rtol=0, atol=1e-9)
     np.testing.assert_allclose(np.hypot(xr - x, yr - y), nr, rtol=0, atol=1e-9)
+    # the same through the C API's names (fastestlapc.cpp track_download_data: left.x, left.y, right.x, right.y)
+    for key, ref in (("left.x", xl), ("left.y", yl), ("right.x", xr), ("right.y", yr)):
+        np.testing.assert_array_equal(api.track_download_data("catalunya", key), ref)
     # the left boundary is to the left of the direction of travel
     assert np.all((xl - x) * -np.sin(th) + (yl - y) * np.cos(th) <= 0.0) or np.all((xl - x) * -np.sin(th) + (yl - y) * np.cos(th) >= 0.0)
     with pytest.raises(api.FastestLapError):
