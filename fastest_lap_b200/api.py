@@ -176,9 +176,14 @@ def vehicle_declare_new_variable_parameter(vehicle_name, parameter_path, paramet
         raise FastestLapError("[ERROR] vehicle_declare_new_variable_parameter -> %s" % e)
 
 
+_vehicle_track = {}          # vehicle name -> Track (vehicle_change_track): the road vehicle_get_output evaluates on
+
+
 def vehicle_change_track(vehicle_name, track_name):
-    """Vehicles of the reference carry their road; here the track is an argument of optimal_laptime: only checked."""
-    _get(vehicle_name, Vehicle); _get(track_name, Track)
+    """Vehicles of the reference carry their road; here the track is an argument of optimal_laptime, and remembered for
+    vehicle_get_output."""
+    _get(vehicle_name, Vehicle)
+    _vehicle_track[vehicle_name] = _get(track_name, Track)
 
 
 def vehicle_type_get_sizes(vehicle_type_name):
@@ -240,9 +245,12 @@ def _options(options):
     get = lambda tag, default: float(root.find(tag).text) if root.find(tag) is not None else default
     speed = get("steady_state_speed", get("initial_speed", 50.0))
     prefix = ""
+    variables = None          # <output_variables><variables><name/>...: what to store (fastestlapc.cpp:1215-1233); default: everything standard
     ov = root.find("output_variables")
     if ov is not None and ov.find("prefix") is not None:
         prefix = (ov.find("prefix").text or "").strip()
+    if ov is not None and ov.find("variables") is not None:
+        variables = [v.tag for v in ov.find("variables")]
     diss = None
     hypermesh = {}           # control name -> hypermesh (a constant control = the hypermesh [0]): fastestlapc.cpp:1276-1283
     cv = root.find("control_variables")
@@ -286,7 +294,7 @@ def _options(options):
         if root.find("xml_file_name") is None:
             raise FastestLapError("[ERROR] optimal_laptime -> <write_xml> needs <xml_file_name>")
         xml_file = (root.find("xml_file_name").text or "").strip()
-    return dict(integral=integral, hypermesh=hypermesh, q_start=q_start, u_start=u_start, xml_file=xml_file, var_bounds=var_bounds, warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
+    return dict(variables=variables, integral=integral, hypermesh=hypermesh, q_start=q_start, u_start=u_start, xml_file=xml_file, var_bounds=var_bounds, warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
 
 
 def _kart_start_node(vehicle, speed, form):
@@ -432,6 +440,15 @@ def optimal_laptime(vehicle, track, s, options=""):
             solver.close()
             if out["status"][0] >= 1:
                 break
+    channels = {}
+    if out["status"][0] >= 1 and o["variables"]:
+        # output channels of the model along the lap, evaluated on the GPU at the solution (fastestlapc.cpp:1643-1690)
+        known = set(nlp.output_names)
+        if any(v in known for v in o["variables"]):
+            if not closed:
+                raise FastestLapError("[ERROR] optimal_laptime -> output channels of open simulations are not supported")
+            ch = nlp.eval_outputs(out["x"][0])
+            channels = {v: ch[v][0].copy() for v in o["variables"] if v in known}
     nlp.close()
     if o["save_warm_start"] and out["status"][0] >= 1:
         _warm_start[veh.model] = dict(s=s.copy(), track=trk, x=out["x"][0].copy(), lam=out["y"][0].copy(), zl=out["zl"][0].copy(), zu=out["zu"][0].copy())
@@ -471,6 +488,12 @@ def optimal_laptime(vehicle, track, s, options=""):
     put("x", xyz[:, 0].copy()); put("y", xyz[:, 1].copy()); put("psi", yaw + X[:, a_col])
     put("laptime", laptime)
     put("optimization_data.number_of_iterations", float(out["iters"][0]))
+    for nm, val in channels.items():
+        put(nm, val)
+    if o["variables"]:
+        unknown = [v for v in o["variables"] if v not in names and v not in channels]
+        if unknown:
+            raise FastestLapError("[ERROR] optimal_laptime -> requested output variable \"%s\" is not offered by the B200 path" % unknown[0])
     if o["xml_file"]:
         _write_solution_xml(o["xml_file"], veh.model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, xyz, yaw, n_col, a_col)
     return pre, names
@@ -497,6 +520,34 @@ def _write_solution_xml(path, model, p, form, closed, s, time, X, out, laptime, 
     sol.n_variables_per_point, sol.n_constraints_per_element = p.nv, p.ncpe
     with open(path, "w") as fh:
         fh.write(sol.to_xml())
+
+
+def vehicle_get_output(vehicle, inputs, controls, s, property_name):
+    """One output channel of the vehicle at (inputs, controls), at arclength s of the vehicle's track (fastestlapc.h:72,
+    fastestlapc.cpp vehicle_get_output): evaluated on the GPU as node 0 of a two-node open section."""
+    from .nlp import CollocationNLP
+    veh = _get(vehicle, Vehicle)
+    trk = _vehicle_track.get(vehicle)
+    if trk is None:
+        raise FastestLapError("[ERROR] vehicle_get_output -> the vehicle has no track: call vehicle_change_track first")
+    n_in, n_u = (14, 4) if veh.model == MODEL_F1 else (13, 2)
+    q, u = np.asarray(inputs, dtype=np.float64), np.asarray(controls, dtype=np.float64)
+    if q.size != n_in or u.size != n_u:
+        raise FastestLapError("[ERROR] vehicle_get_output -> %d inputs and %d controls are expected" % (n_in, n_u))
+    form = FORM_DIRECT if veh.model == MODEL_F1 else FORM_DERIVATIVE
+    if veh.model == MODEL_F1:
+        veh = veh.copy()
+        veh.params[18] = u[3]          # the brake bias is a parameter of the node program when it is not optimised (boost: not evaluated)
+    ds = min(1.0, 0.5 * (trk.track_length - float(s)))
+    p = LapProblem.from_vehicle_track(veh, trk, np.array([float(s), float(s) + ds]), form=form, closed=False, q0=q, u0=u, du0=np.zeros(2))
+    nlp = CollocationNLP(p)
+    try:
+        if property_name not in nlp.output_names:
+            raise FastestLapError("[ERROR] vehicle_get_output -> output \"%s\" is not offered (available: %s)" % (property_name, ", ".join(nlp.output_names)))
+        node = np.concatenate([np.delete(q, n_in - 3), [u[c] for c in ((0, 2) if veh.model == MODEL_F1 else (0, 1))], [0.0, 0.0] if form == FORM_DERIVATIVE else []])
+        return float(nlp.eval_outputs(node)[property_name][0, 0])
+    finally:
+        nlp.close()
 
 
 def gg_diagram(vehicle, speed, n_points):

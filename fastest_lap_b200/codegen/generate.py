@@ -247,6 +247,12 @@ def generate(name, variant):
             disp.append("        case %d: %s_p%d(io); break;" % (w, mode, w))
         disp += ["        default: break;", "        }", "    }", ""]
         parts.append("\n".join(disp))
+    # output channels of the model (get_outputs_map of the reference): their own small program, values only
+    out_channels = list(getattr(p, "outputs", []))
+    if out_channels:
+        parts.append(fn("outputs", [(e.i, "io.out(%d, %%s);" % k) for k, (_, e) in enumerate(out_channels)], [pre], use_cut=False, order=VALUES_ORDER))
+    else:
+        parts.append("    template <class IO> static __device__ __forceinline__ void outputs(IO&) {}\n")
     host = emit_host_derive(g, pt, "derive")
     host = "    static inline " + host.replace("\n", "\n    ")
 
@@ -280,6 +286,8 @@ def generate(name, variant):
         L.append("    // %s partition operation counts: %s (sum %d)" % (mode, part_sizes[mode], sum(part_sizes[mode])))
     L.append("    static constexpr int OPS_VALUES = %d, OPS_JAC = %d, OPS_HESS = %d, OPS_ALL = %d;" %
              (sum(counts_val.values()), sum(counts_jac.values()), sum(counts_hes.values()), sum(counts_all.values())))
+    L.append("    static constexpr int NOUT = %d;   // named output channels (outputs())" % len(out_channels))
+    L.append("    static constexpr const char* OUT_NAMES[%d] = { %s };" % (max(1, len(out_channels)), ", ".join('"%s"' % nm for nm, _ in out_channels) or '""'))
     L.append(_int_table("CTRL_POS", p.ctrl_pos))
     L.append(_int_table("DCTRL_POS", p.dctrl_pos))
     L.append("    static __host__ __device__ constexpr int ctrl_pos(int c) { return c == 0 ? %d : %d; }" % tuple(p.ctrl_pos))

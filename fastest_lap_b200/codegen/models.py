@@ -81,6 +81,11 @@ def f1_tire(P, pre, kappa_hat, lam, N):
     return kappa, Fx, Fy
 
 
+def tire_kappa_max(P, pre, N):
+    Fz1, Fz2 = P[pre + "Fz1"], P[pre + "Fz2"]
+    return (N - Fz1) * ((P[pre + "kmax2"] - P[pre + "kmax1"]) * (1.0 / (Fz2 - Fz1))) + P[pre + "kmax1"]
+
+
 def f1_model(q, u, P, trk):
     """q[14], u[4]: E; P: dict name->E; trk: dict with kx, ky, kz, smu, cmu, sph, cph (E or float)."""
     k_hat = q[0:4]
@@ -221,7 +226,23 @@ def f1_model(q, u, P, trk):
     integrands = [thr * (P["r_engine_power"] * 1.0e3) * 1.0e-6]
     for i in range(4):
         integrands.append(-(Fx_t[i] * (vt[i][0] - omega_w[i] * P[pre[i] + "R0"]) + Fy_t[i] * vt[i][1]) * 1.0e-6)
-    return dict(states=states, dstates=dstates, dtds=dtds, extra=extra, rates=rates, integrands=integrands)
+    # output channels (get_outputs_map: tire.h:170-196, chassis.h:282-308; accelerations chassis.hpp:228-244)
+    outputs = []
+    tyre_names = ["front-axle.left-tire", "front-axle.right-tire", "rear-axle.left-tire", "rear-axle.right-tire"]
+    kap = [k_hat[i] * tire_kappa_max(P, pre[i], N[i]) for i in range(4)]
+    for i, nm in enumerate(tyre_names):
+        outputs += [(nm + ".lambda", lam[i]), (nm + ".true_kappa", kap[i]),
+                    (nm + ".dissipation", Fx_t[i] * (vt[i][0] - omega_w[i] * P[pre[i] + "R0"]) + Fy_t[i] * vt[i][1]),
+                    (nm + ".force.x", Fx_t[i]), (nm + ".force.y", Fy_t[i]), (nm + ".force.z", -N[i]), (nm + ".omega", omega_w[i]),
+                    (nm + ".velocity.x", vt[i][0]), (nm + ".velocity.y", vt[i][1])]
+    inv_speed = 1.0 / sqrt(vx * vx + vy * vy)
+    outputs += [("chassis.acceleration.x", (vx * F[0] + vy * F[1]) * inv_m * inv_speed),
+                ("chassis.acceleration.y", (vx * F[1] - vy * F[0]) * inv_m * inv_speed),
+                ("chassis.acceleration.yaw", domega),
+                ("chassis.force.x", F[0]), ("chassis.force.y", F[1]), ("chassis.force.z", F[2]),
+                ("chassis.aerodynamics.lift", (0.5 * P["rho"] * P["cl"] * P["area"]) * (av[0] * av[0])),
+                ("chassis.aerodynamics.drag.x", qd * av[0] * avn), ("chassis.aerodynamics.drag.y", qd * av[1] * avn)]
+    return dict(states=states, dstates=dstates, dtds=dtds, extra=extra, rates=rates, integrands=integrands, outputs=outputs)
 
 
 def kart_tire(P, pre, kappa, lam, N, only_lateral):
@@ -273,6 +294,7 @@ def kart_model(q, u, P, trk, direct_torque=False, curvilinear=True):
     F = [0.0, 0.0, 0.0]
     T = [0.0, 0.0, 0.0]
     kappa_l, lambda_l = [], []
+    tyre_out = []
     sum_long_torque = 0.0
     for a, ax in enumerate(("f_", "r_")):
         pre = "ft_" if a == 0 else "rt_"
@@ -319,6 +341,7 @@ def kart_model(q, u, P, trk, direct_torque=False, curvilinear=True):
             N = smooth_pos(kt * w + P[pre + "ct"] * dw, P[pre + "Fz_max_ref2"])    # tire_pacejka.hpp:100
             Fx, Fy = kart_tire(P, pre, kappa, lam, N, a == 0)
             kappa_l.append(kappa); lambda_l.append(lam)
+            tyre_out.append(dict(lam=lam, kappa=kappa, Fx=Fx, Fy=Fy, N=N, vtx=vtx, vty=vty, omega=(omega_axle if a == 1 else vtx * (1.0 / R0)), R0=R0))
             if a == 1:
                 sum_long_torque = sum_long_torque - Fx * (R0 - w)    # tire.h:107
             if a == 0:
@@ -366,5 +389,20 @@ def kart_model(q, u, P, trk, direct_torque=False, curvilinear=True):
     if curvilinear:
         dstates = [d * dtds for d in dstates]
     extra = [kappa_l[2], kappa_l[3], lambda_l[0], lambda_l[1], lambda_l[2], lambda_l[3]]      # lot2016kart.h:200-211
+    # output channels (tire.h:170-196, chassis.h:282-308); the front tyres are "only lateral": kappa = 0, no longitudinal force
+    outputs = []
+    for t, nm in zip(tyre_out, ["front-axle.left-tire", "front-axle.right-tire", "rear-axle.left-tire", "rear-axle.right-tire"]):
+        zero = 0.0 * vx
+        fx = zero if t["Fx"] is None else t["Fx"]
+        outputs += [(nm + ".lambda", t["lam"]), (nm + ".true_kappa", zero if t["kappa"] is None else t["kappa"]),
+                    (nm + ".dissipation", fx * (t["vtx"] - t["omega"] * t["R0"]) + t["Fy"] * t["vty"]),
+                    (nm + ".force.x", fx), (nm + ".force.y", t["Fy"]), (nm + ".force.z", -t["N"]), (nm + ".omega", t["omega"]),
+                    (nm + ".velocity.x", t["vtx"]), (nm + ".velocity.y", t["vty"])]
+    inv_speed = 1.0 / sqrt(vx * vx + vy * vy)
+    outputs += [("chassis.acceleration.x", (vx * F[0] + vy * F[1]) * inv_m * inv_speed),
+                ("chassis.acceleration.y", (vx * F[1] - vy * F[0]) * inv_m * inv_speed),
+                ("chassis.acceleration.yaw", x2),
+                ("chassis.force.x", F[0]), ("chassis.force.y", F[1]), ("chassis.force.z", F[2]),
+                ("chassis.aerodynamics.lift", Fa[2]), ("chassis.aerodynamics.drag.x", Fa[0]), ("chassis.aerodynamics.drag.y", Fa[1])]
     return dict(states=states, dstates=dstates, dtds=dtds, extra=extra, force=F, torque=T,
-                kappa=kappa_l, lam=lambda_l)
+                kappa=kappa_l, lam=lambda_l, outputs=outputs)

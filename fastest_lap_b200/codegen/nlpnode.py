@@ -141,6 +141,7 @@ class NodeProgram:
         else:
             out = models.kart_model(q, ctrl, P, trk, direct_torque=v.direct_torque, curvilinear=True)
         states, dstates, dtds, extra = out["states"], out["dstates"], out["dtds"], out["extra"]
+        self.outputs = out["outputs"]          # named output channels of the model at this node (get_outputs_map of the reference)
 
         Q = [states[i] for i in td_ids]
         QD = [dstates[i] for i in td_ids]

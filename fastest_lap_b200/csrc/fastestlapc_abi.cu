@@ -475,6 +475,7 @@ struct LapOptions
     int print_level = 0;
     // one quantity that couples the whole lap, carried node-wise (include/fastestlap_b200.h, aug_*): the brake bias as a constant /
     // on a hypermesh (fastestlapc.cpp:1276-1283) or one restricted integral quantity (:1298-1306)
+    std::vector<string> variables;             // <output_variables><variables>: names asked for (fastestlapc.cpp:1215-1233)
     int aug_kind = FL_AUG_NONE;
     vec hypermesh;
     string integral_name;
@@ -505,6 +506,7 @@ static LapOptions lap_options(const string& text, int model)
     if (const Xml* n = root->child("sigma")) o.sigma = numbers(n->text).at(0);
     if (const Xml* n = root->child("print_level")) o.print_level = (int)numbers(n->text).at(0);
     if (const Xml* ov = root->child("output_variables")) if (const Xml* p = ov->child("prefix")) o.prefix = trim(p->text);
+    if (const Xml* ov = root->child("output_variables")) if (const Xml* vs = ov->child("variables")) for (auto& v : vs->kids) o.variables.push_back(v->tag);
     if (const Xml* cv = root->child("control_variables"))
     {
         vec d;
@@ -616,6 +618,20 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         fl_ipm_destroy(ipm);
         if (!msg.empty()) break;
     }
+    // output channels of the model along the lap, at the solution (fastestlapc.cpp:1643-1690)
+    std::map<string, vec> channels;
+    if (msg.empty() && status[0] >= 1 && !o.variables.empty())
+    {
+        const int n_out = fl_nlp_n_outputs(nlp);
+        std::vector<int> wanted;
+        for (int k = 0; k < n_out; ++k) if (std::find(o.variables.begin(), o.variables.end(), string(fl_nlp_output_name(nlp, k))) != o.variables.end()) wanted.push_back(k);
+        if (!wanted.empty())
+        {
+            vec out((size_t)n_out * np);
+            if (!fl_eval_outputs(nlp, X.data(), out.data())) msg = fl_error();
+            else for (int k : wanted) channels[fl_nlp_output_name(nlp, k)] = vec(out.begin() + (size_t)k * np, out.begin() + (size_t)(k + 1) * np);
+        }
+    }
     fl_nlp_destroy(nlp);
     if (!msg.empty()) throw error("[ERROR] optimal_laptime -> " + msg);
     if (status[0] < 1) throw error("[ERROR] optimal_laptime -> the optimization did not converge (status " + std::to_string(status[0]) + ")");
@@ -684,6 +700,7 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         out_vec(ct_names[c], col);
     }
     out_vec("x", xs); out_vec("y", ys); out_vec("psi", psi);
+    for (auto& kv : channels) out_vec(kv.first, kv.second);
     overwrite(pre + "laptime"); scalars[pre + "laptime"] = laptime;
     if (o.aug_kind == FL_AUG_INTEGRAL)                                           // fastestlapc.cpp:1619-1641
     {
@@ -970,10 +987,57 @@ void vehicle_type_get_names(char* key_name, char* input_names[], char* control_n
     FLC_CATCH()
 }
 
-double vehicle_get_output(const char*, const double*, const double*, const double, const char* property)
+double vehicle_get_output(const char* vname, const double* inputs, const double* controls, const double s, const char* property)
 {
+    // one output channel of the vehicle at (inputs, controls), at arclength s of its track (fastestlapc.cpp vehicle_get_output):
+    // evaluated on the GPU as the fixed first node of a two-node open section
     FLC_TRY
-    throw flc::error(std::string("vehicle_get_output -> the model output channels (\"") + property + "\") are not computed by the B200 path");
+    flc::Vehicle veh = flc::vehicle(vname);
+    if (veh.track.empty()) throw flc::error("[ERROR] vehicle_get_output -> the vehicle has no track: call vehicle_change_track first");
+    flc::Track& trk = flc::track(veh.track);
+    const bool f1 = veh.model == FL_MODEL_F1_3DOF;
+    if (!veh.variable.empty()) veh.params = veh.params_at(s);
+    if (f1) veh.params[18] = controls[3];          // the brake bias is a parameter of the node program when it is not optimised
+    const double ds = std::min(1.0, 0.5 * (trk.length - s));
+    const flc::vec mesh = { s, s + ds };
+    flc::vec nodes(12), wl(2), wr(2);
+    const char* keys[6] = { "yaw", "pitch", "roll", "yaw_dot", "dpitch", "droll" };
+    for (int i = 0; i < 2; ++i)
+    {
+        for (int c = 0; c < 6; ++c) nodes[(size_t)i * 6 + c] = trk.at(keys[c], mesh[i]);
+        wl[i] = trk.at("nl", mesh[i]); wr[i] = trk.at("nr", mesh[i]);
+    }
+    const double du0[2] = { 0.0, 0.0 };
+    fl_problem_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.model = veh.model; d.form = f1 ? FL_FORM_DIRECT : FL_FORM_DERIVATIVE; d.closed = 0; d.elevation = trk.has_elevation() ? 1 : 0; d.n_points = 2;
+    d.s = mesh.data(); d.track_length = trk.length; d.track_nodes = nodes.data(); d.wl = wl.data(); d.wr = wr.data();
+    d.batch = 1; d.vehicle_params = veh.params.data(); d.sigma = 0.5; d.q0 = inputs; d.u0 = controls; d.du0 = du0; d.device = 0;
+    d.wind[0] = veh.wind[0]; d.wind[1] = veh.wind[1];
+    fl_nlp* nlp = fl_nlp_create(&d);
+    if (!nlp) throw flc::error("[ERROR] vehicle_get_output -> " + flc::fl_error());
+    int n = 0, m = 0, which = -1;
+    fl_nlp_sizes(nlp, &n, &m, nullptr, nullptr);
+    const int n_out = fl_nlp_n_outputs(nlp);
+    for (int k = 0; k < n_out; ++k) if (std::string(property) == fl_nlp_output_name(nlp, k)) which = k;
+    double value = 0.0;
+    std::string msg;
+    if (which < 0) msg = std::string("output \"") + property + "\" is not offered";
+    else
+    {
+        // variables of the free node: the same inputs and controls
+        const int n_in = f1 ? 14 : 13;
+        flc::vec x;
+        for (int j = 0; j < n_in; ++j) if (j != n_in - 3) x.push_back(inputs[j]);
+        x.push_back(controls[0]); x.push_back(controls[f1 ? 2 : 1]);
+        x.resize(n, 0.0);
+        flc::vec out((size_t)n_out * 2);
+        if (!fl_eval_outputs(nlp, x.data(), out.data())) msg = flc::fl_error();
+        else value = out[(size_t)which * 2];
+    }
+    fl_nlp_destroy(nlp);
+    if (!msg.empty()) throw flc::error("[ERROR] vehicle_get_output -> " + msg);
+    return value;
     FLC_CATCH(0.0)
 }
 

@@ -397,6 +397,33 @@ int fl_nlp_batch(const fl_nlp* h) { return h->P.batch; }
 const char* fl_nlp_variant(const fl_nlp* h) { return h->v->name; }
 void fl_nlp_ops_per_node(const fl_nlp* h, int ops[4]) { ops[0] = h->v->OPS_VALUES; ops[1] = h->v->OPS_JAC; ops[2] = h->v->OPS_HESS; ops[3] = h->v->OPS_ALL; }
 long fl_kernel_launches(const fl_nlp* h) { return h->launches; }
+int fl_nlp_n_outputs(const fl_nlp* h) { return h->v->NOUT; }
+
+const char* fl_nlp_output_name(const fl_nlp* h, int k) { return (k >= 0 && k < h->v->NOUT) ? h->v->OUT_NAMES[k] : nullptr; }
+
+int fl_eval_outputs(fl_nlp* h, const double* x, double* out)
+{
+    FL_CUDA(cudaSetDevice(h->device));
+    const fl_dev& P = h->P;
+    if (!x || !out) return fail("null argument") ? 1 : 0;
+    if (h->v->NOUT == 0) return fail("this problem has no output channels") ? 1 : 0;
+    const size_t count = (size_t)P.batch * h->v->NOUT * P.n_points;
+    double* d_out = nullptr;
+    FL_CUDA(cudaMalloc(&d_out, count * sizeof(double)));
+    int ok = 1;
+    if (cudaMemcpyAsync(h->d_xuser, x, (size_t)P.batch * P.n * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess || !scatter_x(h)) ok = 0;
+    if (ok)
+    {
+        h->values_valid = h->derivs_jac_valid = false;
+        h->v->launch_outputs(P, h->D0.data(), h->shared_d, d_out, h->stream);
+        h->launches += 1;
+        if (cudaMemcpyAsync(out, d_out, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) ok = 0;
+    }
+    if (!ok) g_error = cudaGetErrorString(cudaGetLastError());
+    cudaFree(d_out);
+    return ok;
+}
+
 void fl_nlp_workspace_slots(const fl_nlp* h, int* n_values, int* n_checkpoints)
 {
     if (n_values) *n_values = h->v->NVAL;

@@ -150,6 +150,36 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Output channels of the model at every node (get_outputs_map of the reference: tyre slips, forces, dissipation, chassis
+// accelerations ...): O[problem][channel][node], thread = node.  Not on the solver's path: post-processing of a solution.
+template <class G, int CD>
+struct OutputsIO
+{
+    const double* xn; const double* tcn; const double* Dp; const DVec<G>* Dk; double* On; size_t sO;
+    __device__ __forceinline__ double x(int k) const { return xn[k]; }
+    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
+    __device__ __forceinline__ double d(int k) const { if constexpr (CD == FL_D_CONST) return Dk->d[k]; else return __ldg(Dp + k); }
+    __device__ __forceinline__ void out(int k, double v) const { On[k * sO] = v; }
+    __device__ __forceinline__ void fence(double) const {}
+};
+
+template <class G, int CD>
+__global__ void __launch_bounds__(FL_BLOCK) k_node_outputs(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk, double* __restrict__ O)
+{
+    const int node = blockIdx.x * FL_BLOCK + threadIdx.x;
+    const int prob = blockIdx.z;
+    if (node >= P.n_points) return;
+    OutputsIO<G, CD> io;
+    io.xn = P.x + ((size_t)prob * P.n_points + node) * G::NV;
+    io.tcn = P.tc + fl_chunk_base(node, G::NTC);
+    io.Dp = CD == FL_D_NODE ? P.D + (size_t)prob * P.d_prob_stride + (size_t)node * P.d_node_stride : P.D + (size_t)prob * G::ND;
+    io.Dk = &Dk;
+    io.sO = P.n_points;
+    io.On = O + (size_t)prob * G::NOUT * P.n_points + node;
+    G::outputs(io);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Element assembly.  V offsets: Q [0,NTD) QD [NTD,2NTD) ALG EXT DTDS CDOT.
 // Runs as its own kernel (eval_f / eval_g alone) or as one extra blockIdx.y slice of the derivative kernel (a full
 // callback round: one launch less, and the rows are written while the derivative partitions compute).
@@ -406,6 +436,8 @@ struct fl_variant
     const char* name;
     int NV, NCPE, NTD, NALG, NEXT, NCR, NFM, NVAL, NCK, NTC, NTRACK, NRAW, ND, NJA, NJB, NH, NCPL, IS_DERIVATIVE, IS_3D;
     int NAUG, AUG_POS, P_AUG;      // augmented state (codegen/nlpnode.py): count, node variable of `a`, first aug_* parameter slot
+    int NOUT; const char* const* OUT_NAMES;                     // named output channels
+    void (*launch_outputs)(const fl_dev&, const double* D0, int shared_d, double* O, cudaStream_t);
     int OPS_VALUES, OPS_JAC, OPS_HESS, OPS_ALL;
     const int *CTRL_POS, *DCTRL_POS, *JA_ROW, *JA_COL, *JB_ROW, *JB_COL, *H_ROW, *H_COL;
     int P_SIGMA, P_DISS0, P_DISS1, P_F_WHEEL_SCALE, P_R_WHEEL_SCALE;     // -1 when the model has no such slot
@@ -445,6 +477,18 @@ struct variant_ops
         if (shared_d) k_node_values<G, FL_D_CONST, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
         else if (P.d_node_stride) k_node_values<G, FL_D_NODE, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
         else k_node_values<G, FL_D_LAP, false><<<grid, FL_BLOCK, 0, s>>>(P, Dk);
+    }
+    static void outputs(const fl_dev& P, const double* D0, int shared_d, double* O, cudaStream_t s)
+    {
+        if constexpr (G::NOUT > 0)
+        {
+            DVec<G> Dk;
+            memcpy(Dk.d, D0, sizeof(Dk.d));
+            const dim3 grid((P.n_points + FL_BLOCK - 1) / FL_BLOCK, 1, P.batch);
+            if (shared_d) k_node_outputs<G, FL_D_CONST><<<grid, FL_BLOCK, 0, s>>>(P, Dk, O);
+            else if (P.d_node_stride) k_node_outputs<G, FL_D_NODE><<<grid, FL_BLOCK, 0, s>>>(P, Dk, O);
+            else k_node_outputs<G, FL_D_LAP><<<grid, FL_BLOCK, 0, s>>>(P, Dk, O);
+        }
     }
     static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<dim3((P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK, P.batch, 1), FL_ABLOCK, 0, s>>>(P); }
     static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK; }
@@ -495,6 +539,7 @@ struct variant_ops
         v.NVAL = G::NVAL; v.NCK = G::NCK; v.NTC = G::NTC; v.NTRACK = G::NTRACK; v.NRAW = G::NRAW; v.ND = G::ND;
         v.NJA = G::NJA; v.NJB = G::NJB; v.NH = G::NH; v.NCPL = G::NCPL; v.IS_DERIVATIVE = G::IS_DERIVATIVE; v.IS_3D = G::IS_3D;
         v.NAUG = G::NAUG; v.AUG_POS = G::AUG_POS; v.P_AUG = G::P_AUG;
+        v.NOUT = G::NOUT; v.OUT_NAMES = G::OUT_NAMES; v.launch_outputs = &outputs;
         v.OPS_VALUES = G::OPS_VALUES; v.OPS_JAC = G::OPS_JAC; v.OPS_HESS = G::OPS_HESS; v.OPS_ALL = G::OPS_ALL;
         v.CTRL_POS = G::CTRL_POS; v.DCTRL_POS = G::DCTRL_POS;
         v.JA_ROW = G::JA_ROW; v.JA_COL = G::JA_COL; v.JB_ROW = G::JB_ROW; v.JB_COL = G::JB_COL; v.H_ROW = G::H_ROW; v.H_COL = G::H_COL;

@@ -56,6 +56,10 @@ def load_library():
     lib.fl_nlp_ops_per_node.argtypes = [C.c_void_p, _ip]
     lib.fl_nlp_workspace_slots.argtypes = [C.c_void_p, _ip, _ip]
     lib.fl_eval_all.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp]
+    lib.fl_nlp_n_outputs.argtypes = [C.c_void_p]
+    lib.fl_nlp_output_name.restype = C.c_char_p
+    lib.fl_nlp_output_name.argtypes = [C.c_void_p, C.c_int]
+    lib.fl_eval_outputs.argtypes = [C.c_void_p, _dp, _dp]
     # the signatures of Ipopt's Eval_*_CB (bool in, bool out)
     lib.fl_eval_f.argtypes = [C.c_int, _dp, C.c_bool, _dp, C.c_void_p]
     lib.fl_eval_grad_f.argtypes = [C.c_int, _dp, C.c_bool, _dp, C.c_void_p]
@@ -255,6 +259,19 @@ class CollocationNLP:
         return out
 
     # Ipopt-style callbacks (problem 0)
+    @property
+    def output_names(self):
+        """Names of the model's output channels (the reference's get_outputs_map keys this library evaluates)."""
+        return [self._lib.fl_nlp_output_name(self._h, k).decode() for k in range(self._lib.fl_nlp_n_outputs(self._h))]
+
+    def eval_outputs(self, x):
+        """Output channels along the lap at x ([n] or [batch][n]): dict name -> [batch][n_points]."""
+        names = self.output_names
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(self.batch, self.n))
+        out = np.empty((self.batch, len(names), self.problem.n_points))
+        self._check(self._lib.fl_eval_outputs(self._h, _ptr(x), _ptr(out)), "fl_eval_outputs")
+        return {nm: out[:, k, :] for k, nm in enumerate(names)}
+
     def eval_f(self, x, new_x=True):
         v = C.c_double()
         x = np.ascontiguousarray(x, dtype=np.float64)

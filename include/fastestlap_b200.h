@@ -118,6 +118,14 @@ int fl_nlp_structure(const fl_nlp* nlp, int* jac_row, int* jac_col, int* hess_ro
 /* per-node slots of the device workspace written by the values pass: node values handed to the element assembly, and
  * checkpointed intermediates (sin/cos/atan/tanh/exp/reciprocal/sqrt) the derivative pass loads */
 void fl_nlp_workspace_slots(const fl_nlp* nlp, int* n_values, int* n_checkpoints);
+
+/* Output channels of the vehicle model along the lap -- what the reference evaluates with get_outputs_map() after a solve
+ * (src/main/c/fastestlapc.cpp:1643-1690: tyre slips, forces, dissipation, omega, contact-point velocities: src/core/tire/tire.h:170-196;
+ * chassis accelerations, resultant force, aerodynamic forces: src/core/chassis/chassis.h:282-308, chassis.hpp:228-244) -- at x [batch][n]
+ * (host): out [batch][fl_nlp_n_outputs][n_points] (host), channel k named fl_nlp_output_name(nlp, k). */
+int fl_nlp_n_outputs(const fl_nlp* nlp);
+const char* fl_nlp_output_name(const fl_nlp* nlp, int k);
+int fl_eval_outputs(fl_nlp* nlp, const double* x, double* out);
 /* fp64 operations per node of each pass (values, jac, hess, all): the algorithmic work the roofline is quoted on */
 void fl_nlp_ops_per_node(const fl_nlp* nlp, int ops[4]);
 

@@ -79,6 +79,10 @@ struct F1Out
     // integrands of the integral quantities (vehicles/limebeer2014f1.h:291-306), per unit time: engine power [MW], minus the power
     // dissipated by each tyre [MW] (tire/tire.h:127: F . v_slip)
     T integrands[5];
+    // output channels (get_outputs_map: tire/tire.h:170-196, chassis/chassis.h:282-308, chassis.hpp:228-244), in the order of
+    // fastest_lap_b200's fl_nlp_output_name: per tyre (fl, fr, rl, rr) lambda, true_kappa, dissipation, force.x, .y, .z, omega, velocity.x,
+    // .y; then chassis acceleration.x, .y, .yaw, force.x, .y, .z, aerodynamics.lift, .drag.x, .drag.y
+    T channels[45];
 };
 
 // Pacejka_simple_model, tire/tire_pacejka.hpp:196-226 and tire/tire_pacejka.h:291-294
@@ -192,6 +196,11 @@ inline void f1_car(const T q[F1_NIN], const T u[F1_NCTRL], const double* P, cons
         tire_forces(t, kappa, out.lambda[i], N[i], Fx, Fy);                  // tire_pacejka.hpp:107-120
         out.Fx_t[i] = Fx; out.Fy_t[i] = Fy;
         out.integrands[1 + i] = -(Fx * (vtx - out.omega_w[i] * t.R0) + Fy * vty) * 1.0e-6;      // tire.h:127, limebeer2014f1.h:295-301
+        {
+            T* ch = out.channels + 9 * i;
+            ch[0] = out.lambda[i]; ch[1] = kappa; ch[2] = Fx * (vtx - out.omega_w[i] * t.R0) + Fy * vty; ch[3] = Fx; ch[4] = Fy; ch[5] = -N[i];
+            ch[6] = out.omega_w[i]; ch[7] = vtx; ch[8] = vty;
+        }
         // torque at wheel centre: cross((0,0,rc), F)
         const T Ttx = -rc[i] * Fy, Tty = rc[i] * Fx;
         if (i < 2)
@@ -305,6 +314,14 @@ inline void f1_car(const T q[F1_NIN], const T u[F1_NCTRL], const double* P, cons
     for (int i = 0; i < F1_NIN; ++i) out.dstates[i] = out.dstates[i] * dtds;     // dynamic_model_car.hpp:104-105
     out.dtds = dtds;
 
+    {
+        // chassis channels: accelerations along / across the velocity (chassis.hpp:228-244: dot and cross of (u, v, 0) with F / m)
+        const T speed = sqrt(vx * vx + vy * vy);
+        T* ch = out.channels + 36;
+        ch[0] = (vx * F[0] + vy * F[1]) / m / speed; ch[1] = (vx * F[1] - vy * F[0]) / m / speed; ch[2] = domega;
+        ch[3] = F[0]; ch[4] = F[1]; ch[5] = F[2];
+        ch[6] = 0.5 * P[F1_RHO] * P[F1_CL] * P[F1_AREA] * av[0] * av[0]; ch[7] = qd * av[0] * avn; ch[8] = qd * av[1] * avn;
+    }
     // extra constraints: limebeer2014f1.h:266-281
     for (int i = 0; i < 4; ++i) out.extra[i] = out.lambda[i];
     out.extra[4] = n + 0.5 * P[F1_F_TRACK] * ca;

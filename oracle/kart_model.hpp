@@ -44,6 +44,7 @@ struct KartOut
     T extra[KART_NEXTRA];   // vehicles/lot2016kart.h:200-211
     T kappa[4], lambda[4], N[4], Fx_t[4], Fy_t[4], w[4];   // order: fl, fr, rl, rr
     T force[3], torque[3];
+    T channels[45];         // output channels, same order as F1Out::channels
 };
 
 // Pacejka_standard_model: tire/tire_pacejka.hpp:123-179
@@ -186,6 +187,11 @@ inline void kart_car(const T q[KART_NIN], const T u[KART_NCTRL], const double* P
             T Fx, Fy;
             kart_tire_forces(tp, out.kappa[i], out.lambda[i], N, Fx, Fy);
             out.Fx_t[i] = Fx; out.Fy_t[i] = Fy;
+            {
+                T* ch = out.channels + 9 * i;          // tire.h:170-196
+                ch[0] = out.lambda[i]; ch[1] = out.kappa[i]; ch[2] = Fx * (vtx - omega_t * R0) + Fy * vty; ch[3] = Fx; ch[4] = Fy; ch[5] = -N;
+                ch[6] = omega_t; ch[7] = vtx; ch[8] = vty;
+            }
             if (a == 1) sum_long_torque = sum_long_torque + (-Fx * (R0 - w));  // tire.h:107
             // force in road axes
             T Fr[3];
@@ -239,6 +245,12 @@ inline void kart_car(const T q[KART_NIN], const T u[KART_NCTRL], const double* P
     const T x0 = (b0 - m02 * x2) / Ixx;
     const T x1 = (b1 - m12 * x2) / Iyy;
 
+    {
+        const T speed = sqrt(vx * vx + vy * vy);        // chassis.hpp:228-244, chassis.h:282-308
+        T* ch = out.channels + 36;
+        ch[0] = (vx * F[0] + vy * F[1]) / m / speed; ch[1] = (vx * F[1] - vy * F[0]) / m / speed; ch[2] = x2;
+        ch[3] = F[0]; ch[4] = F[1]; ch[5] = F[2]; ch[6] = Fa[2]; ch[7] = Fa[0]; ch[8] = Fa[1];
+    }
     // state vectors: axle_car_6dof.hpp:245-258, chassis.hpp:379-396, chassis_car_6dof.hpp:218-250
     out.states[0] = omega_axle; out.dstates[0] = domega_axle;
     out.states[1] = vx;         out.dstates[1] = du;

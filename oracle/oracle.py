@@ -121,6 +121,13 @@ class OracleNLP:
             out["hess"] = (hr[:nh.value], hc[:nh.value], hv[:nh.value])
         return out
 
+    def outputs(self, x):
+        """The 45 output channels of the model at every node ([45][n_points]), in the order of the product's fl_nlp_output_name."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros((45, self.desc.n_points))
+        self._lib.orc_outputs(C.byref(self.desc), _dp(x), _dp(out))
+        return out
+
     def time_eval(self, x, lam, obj_factor=1.0, reps=1, threads=0):
         x = np.ascontiguousarray(x, dtype=np.float64)
         lam = np.ascontiguousarray(lam, dtype=np.float64)

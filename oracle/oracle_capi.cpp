@@ -97,6 +97,52 @@ double orc_time_eval(const orc_desc* c, const double* x, const double* lambda, d
     return (t1 - t0) / reps;
 }
 
+// Output channels of the model at every node of a lap: out [45][n_points]; x as the NLP takes it (open problems: without node 0)
+int orc_outputs(const orc_desc* c, const double* x, double* out)
+{
+    const Desc d = to_desc(c);
+    const Layout L = make_layout(d);
+    const int np = d.n_points;
+    for (int i = 0; i < np; ++i)
+    {
+        const double* xn = (d.closed || i > 0) ? x + (size_t)(d.closed ? i : i - 1) * L.nv : nullptr;
+        TrackNode tk;
+        const double* t = d.track + 6 * i;
+        tk.theta = t[0]; tk.mu = t[1]; tk.phi = t[2]; tk.dtheta = t[3]; tk.dmu = t[4]; tk.dphi = t[5];
+        tk.wind_north = d.wind[0]; tk.wind_east = d.wind[1];
+        const int nin = d.model == MODEL_F1 ? (int)F1_NIN : (int)KART_NIN, nct = d.model == MODEL_F1 ? (int)F1_NCTRL : (int)KART_NCTRL;
+        const int itime = d.model == MODEL_F1 ? (int)F1_ITIME : (int)KART_ITIME;
+        double q[16], u[4];
+        for (int k = 0; k < nct; ++k) u[k] = d.ctrl_default[k];
+        if (xn)
+        {
+            int k = 0;
+            for (int j = 0; j < nin; ++j) q[j] = (j == itime) ? 0.0 : xn[k++];
+            if (L.n_aug) { if (d.aug_kind == 1) u[F1_CBIAS] = xn[k]; k += 2; }
+            if (d.model == MODEL_F1) { u[F1_CDELTA] = xn[k++]; u[F1_CTHROTTLE] = xn[k++]; }
+            else { u[0] = xn[k++]; u[1] = xn[k++]; }
+        }
+        else
+        {
+            for (int j = 0; j < nin; ++j) q[j] = d.q0[j];
+            for (int k = 0; k < nct; ++k) u[k] = d.u0[k];
+        }
+        if (d.model == MODEL_F1)
+        {
+            F1Out<double> o;
+            f1_car<double>(q, u, d.params_at(i), tk, o);
+            for (int k = 0; k < 45; ++k) out[(size_t)k * np + i] = o.channels[k];
+        }
+        else
+        {
+            KartOut<double> o;
+            kart_car<double>(q, u, d.params_at(i), tk, d.kart_direct_torque != 0, true, o);
+            for (int k = 0; k < 45; ++k) out[(size_t)k * np + i] = o.channels[k];
+        }
+    }
+    return 0;
+}
+
 int orc_max_threads() { return omp_get_max_threads(); }
 
 // wind used by the single-node entry points below (orc_f1_car, orc_kart_car): northward, eastward [m/s]

@@ -155,6 +155,33 @@ def test_readme_example_through_the_c_api(lib, files):
     t = (c.c_double * 500)()
     lib.download_vector(t, c.c_int(500), b("run/time"))
     assert np.max(np.abs(np.array(t) - gold["time"])) <= 1e-5
+    # output channels of the model along the lap (<output_variables><variables>, fastestlapc.cpp:1215-1233, 1643-1690) and the same
+    # channel at one node through vehicle_get_output (fastestlapc.h:72)
+    lib.vehicle_change_track(b("car"), b("catalunya"))
+    lib.vehicle_get_output.restype = c.c_double
+    lib.vehicle_get_output.argtypes = [c.c_char_p, c.POINTER(c.c_double), c.POINTER(c.c_double), c.c_double, c.c_char_p]
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><output_variables><prefix>ch/</prefix><variables><chassis.acceleration.y/>"
+                                                                          "<rear-axle.left-tire.dissipation/></variables></output_variables></options>"))
+    assert err(lib) == ""
+    ay = (c.c_double * 500)()
+    lib.download_vector(ay, c.c_int(500), b("ch/chassis.acceleration.y"))
+    assert np.abs(np.array(ay)).max() > 20.0
+    names_in = ["front-axle.left-tire.kappa", "front-axle.right-tire.kappa", "rear-axle.left-tire.kappa", "rear-axle.right-tire.kappa", "chassis.velocity.x",
+                "chassis.velocity.y", "chassis.omega.z", "chassis.force_z_fl_g", "chassis.force_z_fr_g", "chassis.force_z_rl_g", "chassis.force_z_rr_g", "time",
+                "road.lateral-displacement", "road.track-heading-angle"]
+    names_u = ["front-axle.steering-angle", "rear-axle.boost", "chassis.throttle", "chassis.brake-bias"]
+    k = 211
+
+    def column(name):
+        v = (c.c_double * 500)()
+        lib.download_vector(v, c.c_int(500), b("ch/" + name))
+        return v[k]
+    q = (c.c_double * 14)(*[column(nm) for nm in names_in])
+    uu = (c.c_double * 4)(*[column(nm) for nm in names_u])
+    val = lib.vehicle_get_output(b("car"), q, uu, c.c_double(s[k]), b("chassis.acceleration.y"))
+    assert err(lib) == "" and abs(val - ay[k]) <= 1e-9 * max(1.0, abs(ay[k]))
+    lib.vehicle_get_output(b("car"), q, uu, c.c_double(s[k]), b("chassis.banana"))
+    assert "is not offered" in err(lib)
     lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><integral_constraints><x><upper_bound>1</upper_bound></x></integral_constraints></options>"))
     assert "needs <lower_bound> and <upper_bound>" in err(lib)
     lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><integral_constraints><boost-time><lower_bound>0</lower_bound><upper_bound>10</upper_bound></boost-time></integral_constraints></options>"))

@@ -207,3 +207,33 @@ def test_hypermesh_control_and_integral_constraint_options(tmp_path):
         api.optimal_laptime("car", "catalunya", s, "<options><integral_constraints><boost-time><lower_bound>0</lower_bound><upper_bound>10</upper_bound></boost-time></integral_constraints></options>")
     with pytest.raises(api.FastestLapError, match="only the F1's chassis.brake-bias"):
         api.optimal_laptime("car", "catalunya", s, "<options><control_variables><chassis.throttle optimal_control_type=\"constant\"/></control_variables></options>")
+
+
+def test_output_channels_through_the_api(tmp_path):
+    """<output_variables><variables> with channels of the model (fastestlapc.cpp:1215-1233, 1643-1690) and vehicle_get_output
+    (fastestlapc.h:72): tyre dissipation integrated over the lap equals what the integral quantity of the same name accumulates;
+    the channel of one node equals vehicle_get_output at that node's inputs and controls; unknown names raise."""
+    from fastest_lap_b200 import api, workloads
+    from fastest_lap_b200.track import track_from_npz
+    paths = _write_xml_fixtures(tmp_path)
+    api.delete_variable("*")
+    api.create_vehicle_from_xml("car", paths["f1"])
+    api._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    api.vehicle_change_track("car", "catalunya")
+    s = np.linspace(0.0, api.track_download_length("catalunya"), 501)[:-1]
+    want = ["rear-axle.left-tire.dissipation", "rear-axle.left-tire.true_kappa", "chassis.acceleration.x", "chassis.acceleration.y", "chassis.aerodynamics.drag.x"]
+    api.optimal_laptime("car", "catalunya", s, "<options><output_variables><prefix>run/</prefix><variables>%s</variables></output_variables></options>" %
+                        "".join("<%s/>" % w for w in want))
+    ax, ay = api.download_vector("run/chassis.acceleration.x"), api.download_vector("run/chassis.acceleration.y")
+    assert ax.shape == (500,) and -60.0 < ax.min() < -20.0 and 5.0 < ax.max() < 25.0 and np.abs(ay).max() > 20.0      # an F1 car: ~4 g braking, >2 g lateral
+    assert api.download_vector("run/chassis.aerodynamics.drag.x").max() < 0.0                                       # drag opposes the motion
+    names_in, names_u = api.vehicle_type_get_names("f1-3dof")[1:3]
+    k = 137
+    q = np.array([api.download_vector("run/" + nm)[k] for nm in names_in])
+    u = np.array([api.download_vector("run/" + nm)[k] for nm in names_u])
+    for w in want:
+        assert abs(api.vehicle_get_output("car", q, u, s[k], w) - api.download_vector("run/" + w)[k]) <= 1e-9 * max(1.0, abs(api.download_vector("run/" + w)[k])), w
+    with pytest.raises(api.FastestLapError, match="is not offered"):
+        api.optimal_laptime("car", "catalunya", s, "<options><output_variables><variables><chassis.banana/></variables></output_variables></options>")
+    with pytest.raises(api.FastestLapError, match="is not offered"):
+        api.vehicle_get_output("car", q, u, s[k], "chassis.banana")

@@ -107,6 +107,25 @@ def test_callbacks_match_oracle(case):
         _hessian_close(p, (hr, hc, out["hess"][0]), x, lam, obj, ref["hess"])
 
 
+def test_output_channels_match_oracle(case):
+    """The model's output channels along the lap (get_outputs_map of the reference: tyre slips, forces, dissipation, wheel speeds,
+    contact-point velocities: tire.h:170-196; chassis accelerations, resultant force, aerodynamic forces: chassis.h:282-308,
+    chassis.hpp:228-244) at the golden point and at a perturbed one, against the oracle's own evaluation: 1e-10 relative to
+    max(|value|, largest value of the channel along the lap) -- with a floor of 1 N / 1 W for forces and powers: the vertical resultant
+    force of a converged flat lap is the residual of an equation, 1e-12 N of rounding on either side."""
+    p, ex, nlp, o = case
+    names = nlp.output_names
+    assert len(names) == 45 and names[0] == "front-axle.left-tire.lambda" and names[36] == "chassis.acceleration.x"
+    rng = np.random.default_rng(4)
+    for x in (ex["x"], ex["x"] * (1.0 + 0.01 * rng.standard_normal(p.n))):
+        out = nlp.eval_outputs(x)
+        ref = o.outputs(x)
+        for k, nm in enumerate(names):
+            floor = 1.0 if (".force." in nm or "aerodynamics" in nm or "dissipation" in nm) else 1e-3      # (slip of the kart's front tyres: exactly 0 here, 2e-16 of rounding in (omega R0 - v) / v there)
+            scale = np.maximum(np.abs(ref[k]), max(np.abs(ref[k]).max(), floor))
+            assert np.max(np.abs(out[nm][0] - ref[k]) / scale) <= RTOL, nm
+
+
 def test_stress_point_random_multipliers(case):
     """N(0,1) multipliers: values, gradient, Jacobian and Hessian entries all within 1e-10 of the oracle
     (measured: <= 2.1e-11 against the oracle evaluated in extended precision, tools/hess_arbiter.py)."""
