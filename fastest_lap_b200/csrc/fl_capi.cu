@@ -194,6 +194,15 @@ static fl_nlp* create_impl(const fl_problem_desc* d, const double* steady_spec)
         if (!(d->s[i] > d->s[i - 1])) { fail("arclength must be strictly increasing"); return nullptr; }
     if (d->closed && !(d->track_length > d->s[d->n_points - 1])) { fail("closed meshes must end before the track length"); return nullptr; }
     if (!d->closed && (!d->q0 || !d->u0 || (d->form == FL_FORM_DERIVATIVE && !d->du0))) { fail("open problems need the inputs and controls of the first node"); return nullptr; }
+    if (d->ctrl_default && d->model == FL_MODEL_F1_3DOF && !steady_spec)
+    {
+        // The controls that are not optimised do not travel through this field: the node programs take the boost as 0 and the brake
+        // bias from the vehicle parameters (chassis/brake_bias, slot 18).  A caller that asks for anything else is told so.
+        const double* p0 = d->node_params ? d->node_params : d->vehicle_params;
+        if (d->ctrl_default[1] != 0.0) { fail("ctrl_default: a boost other than 0 is not evaluated by the node programs"); return nullptr; }
+        if (std::fabs(d->ctrl_default[3] - p0[18]) > 1.0e-14)
+        { fail("ctrl_default: the brake bias of a lap is vehicle parameter 18 (chassis/brake_bias); set it there (it may differ per lap of a batch)"); return nullptr; }
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { fail("no CUDA device: this library has no CPU path"); return nullptr; }
     if (d->device < 0 || d->device >= ndev) { fail("invalid CUDA device ordinal"); return nullptr; }

@@ -117,7 +117,8 @@ def _describe(lib, p, vehicle_params=None, device=0):
     d.n_points, d.s, d.track_length, d.track_nodes, d.wl, d.wr = p.n_points, _ptr(p.s), p.track_length, _ptr(p.track_nodes), _ptr(p.wl), _ptr(p.wr)
     d.batch, d.vehicle_params, d.sigma = params.shape[0], _ptr(params), p.sigma
     d.dissipation[0], d.dissipation[1] = float(p.dissipation[0]), float(p.dissipation[1])
-    d.q0, d.u0, d.du0, d.ctrl_default, d.device = _ptr(p.q0), _ptr(p.u0), _ptr(p.du0), _ptr(p.ctrl_default), int(device)
+    # (ctrl_default stays NULL: the controls that are not optimised are vehicle parameters to the library, see the header)
+    d.q0, d.u0, d.du0, d.ctrl_default, d.device = _ptr(p.q0), _ptr(p.u0), _ptr(p.du0), None, int(device)
     wind = getattr(p, "wind", (0.0, 0.0))
     d.wind[0], d.wind[1] = float(wind[0]), float(wind[1])          # northward, eastward [m/s]
     aug = getattr(p, "aug", None)

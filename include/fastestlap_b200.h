@@ -59,7 +59,9 @@ typedef struct fl_problem_desc
     const double* q0;           /* open problems: inputs of node 0   [n_inputs]  (14 F1, 13 kart)                      */
     const double* u0;           /* open problems: controls of node 0 [n_controls] (4 F1, 2 kart)                       */
     const double* du0;          /* open problems, derivative form: control rates of node 0 [2]                         */
-    const double* ctrl_default; /* value of every control [n_controls]; used for the ones that are not optimised       */
+    const double* ctrl_default; /* NULL, or the value of every control [n_controls].  Not a way to set the controls that are not
+                                   optimised: the node programs take boost = 0 and the brake bias from vehicle parameter 18
+                                   (chassis/brake_bias); creation fails if this field asks for anything else               */
     int device;                 /* CUDA device ordinal                                                                 */
     const double* node_params;  /* NULL, or [batch][n_points][fl_n_vehicle_params(model)]: the vehicle parameters AT EVERY NODE --
                                    parameters that vary with the arclength (Model_parameter::operator()(s),

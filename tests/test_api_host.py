@@ -114,3 +114,24 @@ def test_wind_and_engine_curve_in_the_vehicle_file(tmp_path):
         vehicle_from_xml(xml)
     with pytest.raises(KeyError):
         veh.set_parameter("vehicle/chassis/aerodynamics/wind_velocity/upward", 1.0)
+
+
+def test_sweep_bounds_follow_each_laps_vehicle():
+    """The tyre-slip rows are bounded by +-max(lambda_max(0), lambda_max(m g0)) of each lap's own vehicle (limebeer2014f1.h:232-262):
+    a sweep over mass / aerodynamics / power shares one set of bounds (None), a sweep that changes a tyre's lambda-max gets its own
+    set per lap, equal to what a single-lap problem of that vehicle has."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.ipm import sweep_bounds
+    from fastest_lap_b200.nlp import problem_bounds
+    from fastest_lap_b200.vehicle import MODEL_F1, F1_PARAM_PATHS
+    p = workloads.f1_catalunya(60)
+    P = workloads.sweep_parameters(MODEL_F1, 5)
+    assert sweep_bounds(p, P) is None
+    k = F1_PARAM_PATHS.index("rear-tire/lambda-max-1")
+    P[3, k] *= 1.2
+    b = sweep_bounds(p, P)
+    assert b is not None and b[2].shape == (5, p.m)
+    single = problem_bounds(p._copy(params=P[3]))
+    np.testing.assert_array_equal(b[2][3], single[2]); np.testing.assert_array_equal(b[3][3], single[3])
+    np.testing.assert_array_equal(b[2][0], problem_bounds(p._copy(params=P[0]))[2])
+    assert np.any(b[3][3] != b[3][0])
