@@ -476,6 +476,8 @@ struct LapOptions
     // one quantity that couples the whole lap, carried node-wise (include/fastestlap_b200.h, aug_*): the brake bias as a constant /
     // on a hypermesh (fastestlapc.cpp:1276-1283) or one restricted integral quantity (:1298-1306)
     std::vector<string> variables;             // <output_variables><variables>: names asked for (fastestlapc.cpp:1215-1233)
+    bool closed = true, warm_start = false, save_warm_start = false;
+    vec q_start, u_start;                      // open simulations: <initial_condition><q from_table/><u from_table/> (fastestlapc.cpp:1237-1249)
     int aug_kind = FL_AUG_NONE;
     vec hypermesh;
     string integral_name;
@@ -499,8 +501,21 @@ static LapOptions lap_options(const string& text, int model)
             o.integral_bounds[0] = numbers(q->child("lower_bound")->text).at(0); o.integral_bounds[1] = numbers(q->child("upper_bound")->text).at(0);
             ++n_coupling;
         }
-    if (const Xml* n = root->child("closed_simulation")) if (!truthy(n)) throw error("[ERROR] optimal_laptime -> open simulations are served by the Python surface (fastest_lap_b200.api), not by this C entry yet");
-    if (truthy(root->child("warm_start"))) throw error("[ERROR] optimal_laptime -> <warm_start> is served by the Python surface (fastest_lap_b200.api), not by this C entry yet");
+    if (const Xml* n = root->child("closed_simulation")) o.closed = truthy(n);
+    o.warm_start = truthy(root->child("warm_start"));
+    o.save_warm_start = truthy(root->child("save_warm_start"));
+    if (!o.closed)
+    {
+        const Xml* ic = root->child("initial_condition");
+        if (!ic || !ic->child("q") || !ic->child("u")) throw error("For open simulations, the initial condition must be providedin 'options/initial_condition'");      // (the reference's message)
+        for (int k = 0; k < 2; ++k)
+        {
+            const Xml* n = ic->child(k == 0 ? "q" : "u");
+            const string from = n->attr.count("from_table") ? n->attr.at("from_table") : "";
+            if (!vectors.count(from)) throw error("[ERROR] optimal_laptime -> initial condition: vector \"" + from + "\" does not exist");
+            (k == 0 ? o.q_start : o.u_start) = vectors.at(from);
+        }
+    }
     if (const Xml* n = root->child("initial_speed")) o.speed = numbers(n->text).at(0);
     if (const Xml* n = root->child("steady_state_speed")) o.speed = numbers(n->text).at(0);
     if (const Xml* n = root->child("sigma")) o.sigma = numbers(n->text).at(0);
@@ -533,18 +548,36 @@ static LapOptions lap_options(const string& text, int model)
 
 static void put_vector(const string& name, const vec& v) { vectors[name] = v; }
 
-static void do_optimal_laptime(const string& vname, const string& tname, const vec& s, const string& options)
+// <save_warm_start> keeps the last solution per vehicle type, <warm_start> restarts from it with its multipliers on ITS mesh and with the
+// vehicle as it is now (fastestlapc.cpp:60-71, 1561-1568, 1712-1713)
+struct WarmStart { bool valid = false; string track; vec s, x, lam, zl, zu; };
+static WarmStart warm_starts[2];
+
+static void do_optimal_laptime(const string& vname, const string& tname, const vec& s_in, const string& options)
 {
     Vehicle& veh = vehicle(vname);
     Track& trk = track(tname);
     const LapOptions o = lap_options(options, veh.model);
+    const bool f1 = veh.model == FL_MODEL_F1_3DOF;
+    WarmStart& ws = warm_starts[f1 ? 0 : 1];
+    if (o.warm_start)
+    {
+        if (!ws.valid) throw error("[ERROR] optimal_laptime -> <warm_start> without a simulation saved by <save_warm_start>");
+        if (ws.track != tname) throw error("[ERROR] optimal_laptime -> the warm start was saved for another track");
+        if (!o.closed || o.aug_kind != FL_AUG_NONE) throw error("[ERROR] optimal_laptime -> <warm_start> of open simulations / with hypermesh controls or integral constraints is not supported");
+    }
+    if (o.save_warm_start && (!o.closed || o.aug_kind != FL_AUG_NONE))
+        throw error("[ERROR] optimal_laptime -> <save_warm_start> of open simulations / with hypermesh controls or integral constraints is not supported");
+    if (!o.closed && o.aug_kind != FL_AUG_NONE) throw error("[ERROR] optimal_laptime -> hypermesh controls and integral constraints need a closed simulation");
+    const vec s = o.warm_start ? ws.s : s_in;
     const int np = (int)s.size();
     if (np < 2) throw error("[ERROR] optimal_laptime -> provide at least two values of arclength");
-    const bool f1 = veh.model == FL_MODEL_F1_3DOF;
     const int form = f1 ? FL_FORM_DIRECT : FL_FORM_DERIVATIVE;
     const bool elevation = trk.has_elevation();
     if (elevation && !f1) throw error("lot2016kart does not support tracks with elevation");
-    if (s.back() >= trk.length) throw error("closed meshes must not repeat the first point");
+    if (o.closed && s.back() >= trk.length) throw error("closed meshes must not repeat the first point");
+    if (!o.closed && ((int)o.q_start.size() != (f1 ? 14 : 13) || (int)o.u_start.size() != (f1 ? 4 : 2)))
+        throw error("[ERROR] optimal_laptime -> the initial condition must have " + std::to_string(f1 ? 14 : 13) + " states and " + std::to_string(f1 ? 4 : 2) + " controls");
     vec nodes((size_t)np * 6), wl(np), wr(np);
     const char* keys[6] = { "yaw", "pitch", "roll", "yaw_dot", "dpitch", "droll" };
     for (int i = 0; i < np; ++i)
@@ -562,7 +595,9 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     vec ctrl_default = f1 ? vec{ 0.0, 0.0, 0.0, v0.params[18] } : vec{ 0.0, 0.0 };
     fl_problem_desc d;
     std::memset(&d, 0, sizeof d);
-    d.model = veh.model; d.form = form; d.closed = 1; d.elevation = elevation ? 1 : 0; d.kart_direct_torque = 0; d.n_points = np;
+    const double du0[2] = { 0.0, 0.0 };
+    d.model = veh.model; d.form = form; d.closed = o.closed ? 1 : 0; d.elevation = elevation ? 1 : 0; d.kart_direct_torque = 0; d.n_points = np;
+    if (!o.closed) { d.q0 = o.q_start.data(); d.u0 = o.u_start.data(); d.du0 = du0; }
     d.s = s.data(); d.track_length = trk.length; d.track_nodes = nodes.data(); d.wl = wl.data(); d.wr = wr.data();
     d.batch = 1; d.vehicle_params = v0.params.data(); d.sigma = o.sigma; d.dissipation[0] = o.diss[0]; d.dissipation[1] = o.diss[1];
     d.ctrl_default = ctrl_default.data(); d.device = 0;
@@ -593,8 +628,9 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     if (!nlp) throw error("[ERROR] optimal_laptime -> " + fl_error());
     int n = 0, m = 0;
     fl_nlp_sizes(nlp, &n, &m, nullptr, nullptr);
-    const int NV = n / np;
-    vec X(n);
+    const int nvn = o.closed ? np : np - 1;          // nodes that carry variables
+    const int NV = n / nvn;
+    vec X(n), Ylam(m), Zl(n), Zu(n);
     std::vector<int> status(1, 0), iters(1, 0);
     double obj = 0.0;
     string msg;
@@ -607,16 +643,26 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         fl_ipm_default_options(&io);
         if (attempt > 0) io.mu_init = 1.0;
         vec node = start_node(v0, factors[attempt] * o.speed * KMH, form == FL_FORM_DERIVATIVE);
+        if (!o.closed)
+        {
+            // the given first node replicated over the free nodes (fastestlapc.cpp:1546-1557); control rates 0
+            node.clear();
+            for (int j = 0; j < n_in; ++j) if (j != n_in - 3) node.push_back(o.q_start[j]);
+            node.push_back(o.u_start[0]); node.push_back(o.u_start[f1 ? 2 : 1]);
+            if (form == FL_FORM_DERIVATIVE) { node.push_back(0.0); node.push_back(0.0); }
+        }
         if (o.aug_kind != FL_AUG_NONE)      // (a, q) after the inputs: the vehicle's brake bias / the middle of the integral's bounds; no jump
             node.insert(node.begin() + (n_in - 1), { o.aug_kind == FL_AUG_BRAKE_BIAS ? std::min(std::max(v0.params[18], 0.0), 1.0) : 0.5 * (o.integral_bounds[0] + o.integral_bounds[1]), 0.0 });
         vec x0(n);
-        for (int i = 0; i < np; ++i) std::copy(node.begin(), node.begin() + NV, x0.begin() + (size_t)i * NV);
+        for (int i = 0; i < nvn; ++i) std::copy(node.begin(), node.begin() + NV, x0.begin() + (size_t)i * NV);
         fl_ipm* ipm = fl_ipm_create(nlp, &io, nullptr, nullptr, nullptr, nullptr);
         if (!ipm) { msg = fl_error(); break; }
-        if (!fl_ipm_solve(ipm, x0.data(), o.print_level >= 5 ? 1 : 0) || !fl_ipm_results(ipm, X.data(), nullptr, nullptr, nullptr, &obj, status.data(), iters.data(), nullptr))
-            msg = fl_error();
+        int ok;
+        if (o.warm_start) ok = fl_ipm_solve_warm(ipm, ws.x.data(), ws.lam.data(), ws.zl.data(), ws.zu.data(), 1.0e-3, 1.0e-4, o.print_level >= 5 ? 1 : 0);
+        else ok = fl_ipm_solve(ipm, x0.data(), o.print_level >= 5 ? 1 : 0);
+        if (!ok || !fl_ipm_results(ipm, X.data(), Ylam.data(), Zl.data(), Zu.data(), &obj, status.data(), iters.data(), nullptr)) msg = fl_error();
         fl_ipm_destroy(ipm);
-        if (!msg.empty()) break;
+        if (!msg.empty() || o.warm_start || !o.closed) break;          // (the retries are for closed laps from the steady-state start)
     }
     // output channels of the model along the lap, at the solution (fastestlapc.cpp:1643-1690)
     std::map<string, vec> channels;
@@ -635,6 +681,18 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     fl_nlp_destroy(nlp);
     if (!msg.empty()) throw error("[ERROR] optimal_laptime -> " + msg);
     if (status[0] < 1) throw error("[ERROR] optimal_laptime -> the optimization did not converge (status " + std::to_string(status[0]) + ")");
+    if (o.save_warm_start) { ws.valid = true; ws.track = tname; ws.s = s; ws.x = X; ws.lam = Ylam; ws.zl = Zl; ws.zu = Zu; }
+    double t_start = 0.0;
+    if (!o.closed)
+    {
+        // the fixed first node goes back in front of the free ones
+        vec first;
+        for (int j = 0; j < n_in; ++j) if (j != n_in - 3) first.push_back(o.q_start[j]);
+        first.push_back(o.u_start[0]); first.push_back(o.u_start[f1 ? 2 : 1]);
+        first.resize(NV, 0.0);
+        X.insert(X.begin(), first.begin(), first.end());
+        t_start = o.q_start[n_in - 3];
+    }
 
     // the augmented variables leave the node: what follows reads the reference's layout
     vec aug_values;
@@ -666,8 +724,9 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         const double ny = std::sin(th) * std::sin(mu) * std::sin(ph) + std::cos(th) * std::cos(ph);
         xs[i] = trk.at("x", s[i]) + x[n_col] * nx; ys[i] = trk.at("y", s[i]) + x[n_col] * ny; psi[i] = th + x[a_col];
     }
-    double laptime = 0.0;
-    for (int i = 0; i < np; ++i)
+    double laptime = t_start;
+    time[0] = t_start;
+    for (int i = 0; i < (o.closed ? np : np - 1); ++i)
     {
         const int j = (i + 1) % np;
         const double h = (i + 1 < np) ? s[i + 1] - s[i] : trk.length - s[np - 1];

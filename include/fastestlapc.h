@@ -10,8 +10,7 @@
  * (fastestlapc.cpp:14-28).  Here the same line is printed and the function returns; fastestlapc_last_error() holds the message
  * (empty after a successful call).  Not offered (they fail with a message naming the reason): propagate_vehicle,
  * circuit_preprocessor, output channels other than the 45 of fl_nlp_output_name (vehicle_get_output and <output_variables> serve the tyre
- * slips / forces / dissipation / speeds and the chassis accelerations / forces / aerodynamics), and the optimal_laptime options compute_sensitivity, open
- * simulations, warm start, boost-time, and more than one hypermesh / constant control or integral constraint per call (one is
+ * slips / forces / dissipation / speeds and the chassis accelerations / forces / aerodynamics), and the optimal_laptime options compute_sensitivity, boost-time, and more than one hypermesh / constant control or integral constraint per call (one is
  * served: the F1's chassis.brake-bias as "constant" / "hypermesh", or one of engine-energy, tire-fl/-fr/-rl/-rr-energy). */
 #ifndef FASTESTLAPC_B200_H
 #define FASTESTLAPC_B200_H

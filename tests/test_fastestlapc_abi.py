@@ -237,3 +237,50 @@ def test_gg_diagram_through_the_c_api(lib, files):
     np.testing.assert_allclose(np.array(amin), r["ax_min"][0], rtol=0, atol=1e-6)
     assert np.all(np.array(amax) >= np.array(amin) - 1e-9)
     lib.delete_variable(b"*")
+
+
+@pytest.mark.gpu
+def test_warm_start_and_open_section_through_the_c_api(lib, files):
+    """<save_warm_start> / <warm_start> (fastestlapc.cpp:1561-1568, 1712-1713) and <closed_simulation> false with <initial_condition>
+    from the tables (:1237-1249) through the C entry: the warm-started lap of a heavier car agrees with its cold lap in fewer
+    iterations; the open section keeps its first node and is not slower than the same stretch of the closed lap."""
+    lib.delete_variable(b"*")
+    lib.create_vehicle_from_xml(b("car"), b(files["f1"]))
+    lib.create_track_from_xml(b("catalunya"), b(files["catalunya"]))
+    s = np.linspace(0.0, lib.track_download_length(b("catalunya")), 501)[:-1]
+    c_s = (c.c_double * len(s))(*s)
+
+    def run(options, points=None):
+        m = c_s if points is None else (c.c_double * len(points))(*points)
+        lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s) if points is None else len(points)), m, b("<options>%s</options>" % options))
+        return err(lib)
+
+    def vec(name, n=500):
+        v = (c.c_double * n)()
+        lib.download_vector(v, c.c_int(n), b(name))
+        return np.array(v)
+    assert "without a simulation saved" in run("<warm_start>true</warm_start>")
+    assert run("<save_warm_start>true</save_warm_start><output_variables><prefix>base/</prefix></output_variables>") == ""
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/mass"), c.c_double(680.0))
+    assert run("<warm_start>true</warm_start><output_variables><prefix>warm/</prefix></output_variables>") == ""
+    assert run("<output_variables><prefix>cold/</prefix></output_variables>") == ""
+    t0, tw, tc = (lib.download_scalar(b(k + "/laptime")) for k in ("base", "warm", "cold"))
+    assert tw > t0 + 1e-3 and abs(tw - tc) <= 2e-5 * tc
+    assert lib.download_scalar(b("warm/optimization_data.number_of_iterations")) < lib.download_scalar(b("cold/optimization_data.number_of_iterations"))
+    # open section: nodes 0..99 from the closed lap's first node
+    names_in = ["front-axle.left-tire.kappa", "front-axle.right-tire.kappa", "rear-axle.left-tire.kappa", "rear-axle.right-tire.kappa", "chassis.velocity.x",
+                "chassis.velocity.y", "chassis.omega.z", "chassis.force_z_fl_g", "chassis.force_z_fr_g", "chassis.force_z_rl_g", "chassis.force_z_rr_g", "time",
+                "road.lateral-displacement", "road.track-heading-angle"]
+    names_u = ["front-axle.steering-angle", "rear-axle.boost", "chassis.throttle", "chassis.brake-bias"]
+    q = (c.c_double * 14)(*[vec("cold/" + nm)[0] for nm in names_in])
+    u = (c.c_double * 4)(*[vec("cold/" + nm)[0] for nm in names_u])
+    lib.create_vector(b("q_start"), c.c_int(14), q)
+    lib.create_vector(b("u_start"), c.c_int(4), u)
+    assert "initial condition must be provided" in run("<closed_simulation>false</closed_simulation>", s[:100])
+    assert run("<closed_simulation>false</closed_simulation><initial_condition><q from_table=\"q_start\"/><u from_table=\"u_start\"/></initial_condition>"
+               "<output_variables><prefix>open/</prefix></output_variables>", s[:100]) == ""
+    uo, to, tl = vec("open/chassis.velocity.x", 100), vec("open/time", 100), vec("cold/time")
+    assert uo[0] == q[4] and to[0] == tl[0] and lib.download_scalar(b("open/laptime")) == to[-1]
+    assert 0.9 * (tl[99] - tl[0]) <= to[-1] - to[0] <= tl[99] - tl[0] + 1e-6
+    assert np.max(np.abs(uo[:20] - vec("cold/chassis.velocity.x")[:20])) <= 0.5
+    lib.delete_variable(b"*")
