@@ -32,6 +32,8 @@ def build(force=False):
     r = subprocess.run(["make"] + (["-B"] if force else []) + ["-C", _HERE, "liboracle.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0 and not os.path.exists(so):
         raise RuntimeError("building the CPU oracle failed:\n" + r.stdout[-2000:])
+    # the extended-precision build (the arbiter of ill-conditioned Hessian entries) travels with it; lib_ld() reports a failure
+    subprocess.run(["make", "-C", _HERE, "liboracle_ld.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     return so
 
 
