@@ -280,9 +280,10 @@ def gg_leg(args, torch, dist, world, rank, local):
     params = workloads._vehicles()["roberto_lot_kart_2016"]
     speeds = np.linspace(50.0, 120.0, args.gg_speeds) / 3.6
     lo, hi = shard_range(args.gg_speeds, world, rank)
-    # untimed warm-up: one small diagram, so that the timed sweep does not pay the first-use loading of the steady-state kernels
-    # (measured on fresh boxes: the same sweep 0.18 s warm, 0.5 ... 1.4 s when it is the first to touch them)
-    gg.gg_diagram(params, speeds[lo:lo + 1], n_lat=8, device=local)
+    # untimed warm-up: the same sweep once.  The timed sweep then finds the steady-state kernels loaded and the device blocks of its
+    # dozen handles in the library's cache (cudaMalloc / cudaFree of a first sweep varied from 30 ms to 1.2 s on fresh boxes against
+    # 0.11 s of solves, profiles/README.md)
+    gg.gg_diagram(params, speeds[lo:hi], n_lat=args.gg_lat, device=local)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -60,7 +62,7 @@ const fl_variant* pick_variant(int model, int form, int elevation, int torque, i
 template <class T> T* dev_alloc(size_t count)
 {
     void* p = nullptr;
-    if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    if (fl_dev_malloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return nullptr;
     cudaMemset(p, 0, (count ? count : 1) * sizeof(T));
     return static_cast<T*>(p);
 }
@@ -125,6 +127,71 @@ void build_structure(fl_nlp* h)
 
 void fl_set_error(const std::string& msg) { g_error = msg; }
 
+// ---- cache of freed device blocks (see fl_internal.h) ----------------------------------------------------------------------
+namespace {
+struct DevCache
+{
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;      // (device, bytes) -> block
+    std::map<void*, std::pair<int, size_t>> live;                    // block -> (device, bytes)
+    size_t cached = 0;
+    size_t limit = [] { const char* e = std::getenv("FL_CACHE_BYTES"); return e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)8 << 30; }();
+    void release_all()
+    {
+        int cur = 0; cudaGetDevice(&cur);
+        for (auto& kv : free_blocks) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+        free_blocks.clear(); cached = 0;
+        cudaSetDevice(cur);
+    }
+};
+DevCache& dev_cache() { static DevCache c; return c; }
+}
+
+cudaError_t fl_dev_malloc(void** p, size_t bytes)
+{
+    DevCache& c = dev_cache();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bytes = (bytes + 255) / 256 * 256;
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.free_blocks.find({ dev, bytes });
+    if (it != c.free_blocks.end())
+    {
+        *p = it->second; c.free_blocks.erase(it); c.cached -= bytes;
+        c.live[*p] = { dev, bytes };
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && c.cached > 0) { cudaGetLastError(); c.release_all(); e = cudaMalloc(p, bytes); }
+    if (e == cudaSuccess) c.live[*p] = { dev, bytes };
+    return e;
+}
+
+void fl_dev_free(void* p)
+{
+    if (!p) return;
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) { cudaFree(p); return; }
+    const auto key = it->second;
+    c.live.erase(it);
+    if (key.second > c.limit / 4 || c.cached + key.second > c.limit)
+    {
+        int cur = 0; cudaGetDevice(&cur);
+        cudaSetDevice(key.first); cudaFree(p); cudaSetDevice(cur);
+        return;
+    }
+    c.free_blocks.insert({ key, p }); c.cached += key.second;
+}
+
+extern "C" void fl_release_cached_memory(void)
+{
+    DevCache& c = dev_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.release_all();
+}
+
 extern "C" {
 
 const char* fl_last_error(void) { return g_error.c_str(); }
@@ -142,9 +209,9 @@ void fl_nlp_destroy(fl_nlp* h)
     }
     double* bufs[] = { h->d_xfull, h->P.node0 ? h->d_xuser : nullptr, h->d_tc, h->d_D, h->d_lambda, h->d_zeros, h->d_V, h->d_C, h->d_g, h->d_f, h->d_fpart,
                        h->d_grad, h->d_jac, h->d_hess };
-    for (double* b : bufs) if (b) cudaFree(b);
-    if (h->d_fcount) cudaFree(h->d_fcount);
-    if (h->d_flush) cudaFree(h->d_flush);
+    for (double* b : bufs) if (b) fl_dev_free(b);
+    if (h->d_fcount) fl_dev_free(h->d_fcount);
+    if (h->d_flush) fl_dev_free(h->d_flush);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -418,7 +485,7 @@ int fl_eval_outputs(fl_nlp* h, const double* x, double* out)
     if (h->v->NOUT == 0) return fail("this problem has no output channels") ? 1 : 0;
     const size_t count = (size_t)P.batch * h->v->NOUT * P.n_points;
     double* d_out = nullptr;
-    FL_CUDA(cudaMalloc(&d_out, count * sizeof(double)));
+    FL_CUDA(fl_dev_malloc((void**)&d_out, count * sizeof(double)));
     int ok = 1;
     if (cudaMemcpyAsync(h->d_xuser, x, (size_t)P.batch * P.n * sizeof(double), cudaMemcpyHostToDevice, h->stream) != cudaSuccess || !scatter_x(h)) ok = 0;
     if (ok)
@@ -429,7 +496,7 @@ int fl_eval_outputs(fl_nlp* h, const double* x, double* out)
         if (cudaMemcpyAsync(out, d_out, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) ok = 0;
     }
     if (!ok) g_error = cudaGetErrorString(cudaGetLastError());
-    cudaFree(d_out);
+    fl_dev_free(d_out);
     return ok;
 }
 
@@ -610,7 +677,7 @@ int fl_eval_device_masked(fl_nlp* h, int what, double obj_factor, const int* d_a
         h->launches += 1;
     }
     // a full round (f, g, grad f, Jacobian, Hessian) assembles the rows inside the derivative launch
-    const int fold = (what & FL_EVAL_FG) && dw == FL_DERIV_ALL;
+    const int fold = (what & FL_EVAL_FG) && dw == FL_DERIV_ALL && P.n_points > 32;          // (one-node problems: see derivs_cd)
     if ((what & FL_EVAL_FG) && !fold)
     {
         h->v->launch_assemble(P, h->stream);
@@ -668,7 +735,7 @@ int fl_flush_l2(fl_nlp* h)
         int l2 = 0;
         FL_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device));
         h->flush_bytes = 2 * (size_t)(l2 > 0 ? l2 : (128 << 20));
-        FL_CUDA(cudaMalloc(&h->d_flush, h->flush_bytes));
+        FL_CUDA(fl_dev_malloc((void**)&h->d_flush, h->flush_bytes));
     }
     FL_CUDA(cudaMemsetAsync(h->d_flush, 0, h->flush_bytes, h->stream));
     return 1;

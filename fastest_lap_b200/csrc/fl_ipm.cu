@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <chrono>
 #include <vector>
 
@@ -21,7 +22,7 @@ namespace {
 template <class T> T* dalloc(size_t count, std::vector<void*>& owned)
 {
     void* p = nullptr;
-    if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    if (fl_dev_malloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return nullptr;
     cudaMemset(p, 0, (count ? count : 1) * sizeof(T));
     owned.push_back(p);
     return static_cast<T*>(p);
@@ -249,7 +250,7 @@ void fl_ipm_orphan(fl_ipm* s)
     fl_nlp* nlp = s->nlp;
     cudaSetDevice(nlp->device);
     if (nlp->stream) cudaStreamSynchronize(nlp->stream);
-    for (void* p : s->owned) cudaFree(p);
+    for (void* p : s->owned) fl_dev_free(p);
     s->owned.clear();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -414,7 +415,8 @@ fl_ipm* fl_ipm_create_ex(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l
         if (const char* e = std::getenv("FL_IPM_PART_MAX")) s->part_max_laps = std::atoi(e);
     }
     // vector kernels: one block per lap; wide blocks when the batch alone cannot fill the machine
-    if (B <= 64) s->vec_block = IPM_BLOCK_MAX;
+    if (S == 1) s->vec_block = 32;                // one-node problems (steady-state NLPs): a warp per problem, its reductions need no barrier tree
+    else if (B <= 64) s->vec_block = IPM_BLOCK_MAX;
     else if (B <= 512) s->vec_block = 256;
     s->vec_smem = (size_t)IPM_NCPEMAX * s->vec_block * sizeof(double);
     // long laps, few of them: a cluster of blocks per lap (each block strides over 1 / vec_cluster of the lap's vectors)
@@ -635,6 +637,15 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->ms_total = ms;
+    if (profiling() && s->warp_kkt)
+    {
+        std::vector<fl_ipm_lap> laps(B);
+        cudaMemcpy(laps.data(), I.lap, (size_t)B * sizeof(fl_ipm_lap), cudaMemcpyDeviceToHost);
+        long long sf = 0, so = 0, sh = 0, nf = 0;
+        for (const fl_ipm_lap& l : laps) { sf += l.stages_fail; so += l.stages_ok; sh += l.fail_shift; nf += l.n_fail; }
+        std::fprintf(stderr, "ipm profile: warp-per-lap factorisation walked %lld stages in successful attempts and %lld in %lld failing ones (%.0f stages each of %d); "
+                             "consecutive failures of a lap were %.1f stages apart on average\n", so, sf, nf, nf ? (double)sf / nf : 0.0, s->K.S, nf ? (double)sh / nf : 0.0);
+    }
     if (profiling()) std::fprintf(stderr, "ipm profile: total %.1f ms, factor %.1f ms (%ld launches), solve %.1f ms (%ld), callbacks %.1f ms (%ld + %ld)\n", s->ms_total,
                                   s->ms_factor, s->n_factor_launches, s->ms_solve, s->n_solve_launches, s->ms_eval, s->n_eval_full, s->n_eval_fg);
     FLI_CUDA(cudaGetLastError());

@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init(const fl_ipm_dev I)
         L.mu = I.o.mu_init; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
         L.theta_max = -1.0; L.theta_min = -1.0; L.status = IPM_RUNNING; L.ls = LS_IDLE; L.iter = 0; L.acc_count = 0; L.n_filter = 0;
         L.n_backtrack = 0; L.n_soc = 0; L.n_reg = 0; L.n_fact = 0; L.switching = 0; L.n_restart = 0; L.n_small = 0; L.dw_prev = 0.0;
+        L.fail_stage = -1; L.stages_fail = 0; L.stages_ok = 0; L.fail_shift = 0; L.n_fail = 0;
         I.dw[lap] = 0.0; I.dc[lap] = L.dc; I.act_run[lap] = 1; I.act_factor[lap] = 1; I.act_soc[lap] = 0;
     }
 }
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(IPM_BLOCK_MAX) k_ipm_init_warm(const fl_ipm_de
         L.mu = mu0; L.tau = fmax(I.o.tau_min, 1.0 - L.mu); L.dw = 0.0; L.dw_last = 0.0; L.dc = I.o.delta_c_bar * pow(L.mu, I.o.kappa_c);
         L.theta_max = -1.0; L.theta_min = -1.0; L.status = IPM_RUNNING; L.ls = LS_IDLE; L.iter = 0; L.acc_count = 0; L.n_filter = 0;
         L.n_backtrack = 0; L.n_soc = 0; L.n_reg = 0; L.n_fact = 0; L.switching = 0; L.n_restart = 0; L.n_small = 0; L.dw_prev = 0.0;
+        L.fail_stage = -1; L.stages_fail = 0; L.stages_ok = 0; L.fail_shift = 0; L.n_fail = 0;
         I.dw[lap] = 0.0; I.dc[lap] = L.dc; I.act_run[lap] = 1; I.act_factor[lap] = 1; I.act_soc[lap] = 0;
     }
 }

@@ -24,5 +24,9 @@ struct fl_ipm_lap            // state of one lap's iteration
     double f, cviol, dual_inf, compl_inf, err0, theta_soc_old, alpha_soc;
     double dw_prev;          // regularisation the previous iteration's factorisation ended with
     int status, ls, iter, acc_count, n_filter, n_backtrack, n_soc, n_reg, n_fact, switching, n_restart, n_small, pad_;
+    // diagnosis of the inertia-correcting factorisation (warp-per-lap schedule): stage at which the last failing attempt stopped, stages
+    // walked by failing / successful attempts, and how far (cyclically) consecutive failures were apart
+    int fail_stage, pad2_;
+    long long stages_fail, stages_ok, fail_shift, n_fail;
     double filter[2 * IPM_FILTER_MAX];
 };

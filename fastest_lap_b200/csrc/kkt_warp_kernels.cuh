@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
     {
         int n_neg = 0, n_zero = 0;
         bool ok = true;
+        int j_fail = -1;
         bool have_P = false;             // the previous stage left a Schur term in sm.aq
         for (int k = lane; k < 16 * 16; k += 32) sm.d0[k] = 0.0;
         if (cyc)
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
             {
                 // every pivot block carries exactly NEQ negative pivots when the reduced Hessian is positive definite
                 ok = (n_neg - neg_before == NEQ && n_zero == zero_before);
-                if (!ok) break;
+                if (!ok) { j_fail = j; break; }
             }
             if (lane < NB)
             {
@@ -647,6 +648,16 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
         // Algorithm IC (Waechter & Biegler, section 3.1); every lane takes the same decision from the same data, lane 0 records it
         const fl_ipm_options& o = K.o;
         int fl;
+        if (lane == 0)
+        {
+            if (ok) Lp->stages_ok += S;
+            else
+            {
+                Lp->stages_fail += S - j_fail;
+                if (Lp->n_fail > 0) { int d = j_fail - Lp->fail_stage; if (d < 0) d = -d; if (d > S - d) d = S - d; Lp->fail_shift += d; }
+                Lp->fail_stage = j_fail; Lp->n_fail += 1;
+            }
+        }
         if (ok)
         {
             if (lane == 0)

@@ -247,6 +247,12 @@ __device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, co
             }
         }
     }
+    if (P.n_elements == 1)
+    {
+        // one-element problems (steady-state NLPs): the element's term is the objective, no reduction
+        if (threadIdx.x == 0) P.f[prob] = fe;
+        return;
+    }
     // objective: fixed-order tree inside the block; the last block to finish sums the block partials, again in a fixed
     // order (thread t takes partials t, t + BS, ...; then the same tree) -- the result does not depend on block timing
     __shared__ double red[BS];
@@ -512,7 +518,11 @@ struct variant_ops
         // launched with programmatic stream serialisation: the grid may be scheduled before the values pass ahead of it in
         // the stream has drained (its blocks wait at griddepcontrol.wait), which hides the launch and ramp-up latency
         cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(FL_DBLOCK, 1, 1); cfg.dynamicSmemBytes = sm; cfg.stream = s;
+        // one-node problems (steady-state NLPs): one warp per block instead of eight -- a block of 256 threads at 255 registers fills
+        // an SM on its own, and a batch of 2016 problems x 8 partitions then runs in 110 waves of blocks with ONE active thread each
+        // (208 us per launch in the G-G sweep, profiles/r2_gg_launches.md); the assembly slice needs the full block and is launched on its own
+        const bool tiny = !FL_STAGE && P.n_points <= 32 && !with_assemble;
+        cfg.blockDim = dim3(tiny ? 32 : FL_DBLOCK, 1, 1); cfg.dynamicSmemBytes = sm; cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -121,6 +121,10 @@ int fl_nlp_structure(const fl_nlp* nlp, int* jac_row, int* jac_col, int* hess_ro
  * checkpointed intermediates (sin/cos/atan/tanh/exp/reciprocal/sqrt) the derivative pass loads */
 void fl_nlp_workspace_slots(const fl_nlp* nlp, int* n_values, int* n_checkpoints);
 
+/* Device memory of destroyed handles is kept in a per-device cache of blocks (exact-size reuse by the next handles; at most FL_CACHE_BYTES,
+ * default 8 GB, blocks above a quarter of that are returned at once; released and retried when an allocation fails).  This empties it. */
+void fl_release_cached_memory(void);
+
 /* Output channels of the vehicle model along the lap -- what the reference evaluates with get_outputs_map() after a solve
  * (src/main/c/fastestlapc.cpp:1643-1690: tyre slips, forces, dissipation, omega, contact-point velocities: src/core/tire/tire.h:170-196;
  * chassis accelerations, resultant force, aerodynamic forces: src/core/chassis/chassis.h:282-308, chassis.hpp:228-244) -- at x [batch][n]
