@@ -690,8 +690,11 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
 // ---------------------------------------------------------------------------------------------------------------------
 // Solves K z = (r1, r2) for every active lap with the factors of k_kkt_factor_w; dx [n], dy [m] in the NLP's own orders.
 // One warp per lap, lane r = row r of the stage; the next stage's D^-1 row is loaded while the current stage is reduced.
+#ifndef FL_KWS_MINB
+#define FL_KWS_MINB 1
+#endif
 template <int NV, int NEQ>
-__global__ void __launch_bounds__(32) k_kkt_solve_w(const fl_kkt_dev K, const double* __restrict__ r1, const double* __restrict__ r2,
+__global__ void __launch_bounds__(32, FL_KWS_MINB) k_kkt_solve_w(const fl_kkt_dev K, const double* __restrict__ r1, const double* __restrict__ r2,
                                                      double* __restrict__ dx, double* __restrict__ dy)
 {
     using St = kw_stage<NV, NEQ>;
