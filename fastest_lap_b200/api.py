@@ -16,7 +16,7 @@ the reference makes of it is a parameter sweep with vehicle_set_parameter.  Open
 (:1546-1557); <write_xml> / <xml_file_name> write the reference's solution file (optimal_laptime.hpp xml()).
 <control_variables> with chassis.brake-bias optimal_control_type="constant" | "hypermesh" (+ <hypermesh>), or ONE entry of
 <integral_constraints> (engine-energy, tire-*-energy) on flat closed F1 laps: carried node-wise, see problem.py.  More than one
-of them, other controls on a hypermesh, boost-time and sensitivities raise an exception that names what was asked.
+of them, other controls on a hypermesh and boost-time raise an exception that names what was asked.
 """
 import xml.etree.ElementTree as ET
 import numpy as np
@@ -161,9 +161,12 @@ def vehicle_save_as_xml(vehicle_name, xml_file_name):
 
 
 def vehicle_declare_new_constant_parameter(vehicle_name, parameter_path, parameter_alias, parameter_value):
-    """The reference registers `parameter_path` under an alias for its sensitivity analysis and sets its value; the
-    sensitivities are not computed on this path, the value is set."""
-    _get(vehicle_name, Vehicle).set_parameter(parameter_path, float(parameter_value))
+    """The reference registers `parameter_path` under an alias and sets its value (fastestlapc.cpp:899-939); the aliases name the
+    derivatives `<compute_sensitivity>` of optimal_laptime stores."""
+    try:
+        _get(vehicle_name, Vehicle).declare_parameter(parameter_path, parameter_alias.strip(), float(parameter_value))
+    except KeyError as e:
+        raise FastestLapError("[ERROR] vehicle_declare_new_constant_parameter -> %s" % e.args[0])
 
 
 def vehicle_declare_new_variable_parameter(vehicle_name, parameter_path, parameter_alias, parameter_values, mesh_parameter_indexes, mesh_points):
@@ -232,8 +235,7 @@ def vehicle_type_get_names(vehicle_type_name):
 def _options(options):
     root = ET.fromstring(options) if options and options.strip() else ET.Element("options")
     node = root.find("compute_sensitivity")
-    if node is not None and (node.text or "").strip().lower() in ("true", "1"):
-        raise FastestLapError("[ERROR] optimal_laptime -> option <compute_sensitivity> is not supported by the B200 path yet")
+    sensitivity = node is not None and (node.text or "").strip().lower() in ("true", "1")
     # <integral_constraints><name><lower_bound/><upper_bound/></name></integral_constraints>: fastestlapc.cpp:1298-1306
     integral = []
     node = root.find("integral_constraints")
@@ -294,7 +296,7 @@ def _options(options):
         if root.find("xml_file_name") is None:
             raise FastestLapError("[ERROR] optimal_laptime -> <write_xml> needs <xml_file_name>")
         xml_file = (root.find("xml_file_name").text or "").strip()
-    return dict(variables=variables, integral=integral, hypermesh=hypermesh, q_start=q_start, u_start=u_start, xml_file=xml_file, var_bounds=var_bounds, warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
+    return dict(sensitivity=sensitivity, variables=variables, integral=integral, hypermesh=hypermesh, q_start=q_start, u_start=u_start, xml_file=xml_file, var_bounds=var_bounds, warm_start=flag("warm_start"), save_warm_start=flag("save_warm_start"), sigma=get("sigma", 0.5), speed=speed, prefix=prefix, dissipation=diss, print_level=int(get("print_level", _print_level)), closed=closed)
 
 
 def _kart_start_node(vehicle, speed, form):
@@ -417,9 +419,17 @@ def optimal_laptime(vehicle, track, s, options=""):
                 XL[:, col] = lo
             if hi is not None:
                 XU[:, col] = hi
+    declared = list(getattr(veh, "declared", []))
+    if o["sensitivity"]:
+        # (the reference runs its sensitivity analysis on closed or open direct-form problems; here: closed laps without lap-coupling
+        # quantities, parameters declared as constants)
+        if not closed or p.aug or veh.has_variable_parameters():
+            raise FastestLapError("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for closed laps with constant parameters, "
+                                  "without hypermesh controls or integral constraints")
     nlp = CollocationNLP(p)
     solver = LapSolver(nlp, bounds=bounds)
     out = solver.solve(x0, verbose=o["print_level"] >= 5, warm=warm)
+    sigma = solver.sigma() if o["sensitivity"] and out["status"][0] >= 1 else None
     solver.close()
     if out["status"][0] < 1 and closed and warm is None:
         # The solver has no restoration phase: a closed lap that does not converge from the requested starting speed is tried
@@ -437,6 +447,7 @@ def optimal_laptime(vehicle, track, s, options=""):
                 x_try = np.tile(_kart_start_node(veh, factor * o["speed"] * KMH, form), p.n_points)
             solver = LapSolver(nlp, opts, bounds=bounds)
             out = solver.solve(x_try, verbose=o["print_level"] >= 5)
+            sigma = solver.sigma() if o["sensitivity"] and out["status"][0] >= 1 else None
             solver.close()
             if out["status"][0] >= 1:
                 break
@@ -494,6 +505,36 @@ def optimal_laptime(vehicle, track, s, options=""):
         unknown = [v for v in o["variables"] if v not in names and v not in channels]
         if unknown:
             raise FastestLapError("[ERROR] optimal_laptime -> requested output variable \"%s\" is not offered by the B200 path" % unknown[0])
+    if o["sensitivity"] and declared:
+        # derivatives with respect to the declared parameters (fastestlapc.cpp:1585-1615, 1687-1706: "derivatives/<variable>/<alias>";
+        # the reference fills chassis.velocity.x and time and leaves the other requested vectors at zero -- here every state and
+        # optimised control gets its derivative)
+        from .ipm import lap_sensitivities, dlaptime_dp
+        perturbed = []
+        for alias, key in declared:
+            col = veh.paths.index(key)
+            step = 1.0e-6 * max(abs(veh.params[col]), 1.0e-3)
+            pm = []
+            for sign in (1.0, -1.0):
+                v2 = veh.copy()
+                v2.params[col] += sign * step
+                pm.append(LapProblem.from_vehicle_track(v2, trk, s, form=form, closed=closed, dissipation=o["dissipation"], sigma=o["sigma"]))
+            perturbed.append((pm[0], pm[1], 2.0 * step))
+        dxs, _ = lap_sensitivities(p, out["x"][0], out["y"][0], sigma, perturbed)
+        h_el = np.diff(np.append(s, trk.track_length))
+        for (alias, _), dx in zip(declared, dxs):
+            dT, d = dlaptime_dp(p, out["x"][0], dx)
+            DX = dx.reshape(-1, p.nv)
+            put("derivatives/laptime/" + alias, dT)
+            k = 0
+            for nm in inputs:
+                if nm == "time":
+                    # the trapezoid rule over d/dp of dt/ds (optimal_laptime.hpp:700-716)
+                    put("derivatives/time/" + alias, np.concatenate([[0.0], np.cumsum(h_el[:-1] * ((1.0 - o["sigma"]) * d[:-1] + o["sigma"] * d[1:]))]))
+                else:
+                    put("derivatives/%s/%s" % (nm, alias), DX[:, k].copy()); k += 1
+            for c, nm in enumerate(controls):
+                put("derivatives/%s/%s" % (nm, alias), DX[:, k + full_mesh.index(c)].copy() if c in full_mesh else np.zeros(p.n_points))
     if o["xml_file"]:
         _write_solution_xml(o["xml_file"], veh.model, p, form, closed, s, time, X, out, laptime, controls, full_mesh, xyz, yaw, n_col, a_col)
     return pre, names

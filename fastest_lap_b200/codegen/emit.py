@@ -58,7 +58,7 @@ class ParamTable:
 class Emitter:
     """Emits one function body: `inputs` maps symbol name -> C expression; outputs are (expr id, "statement with one %s") pairs."""
 
-    def __init__(self, graph, ptable, inputs, dfmt="D[%d]", cut=None, lazy_inputs=None, segment=0, order="dfs"):
+    def __init__(self, graph, ptable, inputs, dfmt="D[%d]", cut=None, lazy_inputs=None, segment=0, order="dfs", ring=None):
         # cut: node id -> C expression that LOADS the node's value (a checkpoint written by an earlier pass) instead of
         # recomputing it; the load is emitted lazily, right before the first use
         # lazy_inputs: symbol name -> (local name, C expression that loads it), emitted at first use instead of up front
@@ -70,6 +70,10 @@ class Emitter:
         # other); "level" = by latency-weighted depth (independent chains, e.g. the four tyres, interleaved statement by
         # statement, so that a lone warp has several instructions in flight)
         self.order = order
+        # ring: (loads per group, groups in flight, statements a value is read ahead of its first use) -- the per-node loads
+        # (checkpoints, variables, multipliers, track constants) travel through a small per-thread ring in shared memory filled
+        # by cp.async several groups ahead of their use, see _ring()
+        self.ring = ring
 
     def body(self, outputs, indent="    "):
         g, pt = self.g, self.pt
@@ -193,7 +197,58 @@ class Emitter:
                 lines.append(indent + (fmt % ref(e)))
         if self.segment > 0:
             lines = self._pipeline(lines, is_load, indent)
+        if self.ring:
+            lines = self._ring(lines, indent)
         return "\n".join(lines)
+
+    def _ring(self, lines, indent):
+        """Asynchronous loads through shared memory.  Every per-node load `const double v = io.c(k);` (also x, t, lin, lout, uprev,
+        unext) becomes a pair: `io.rput(slot, io.pc(k))` -- an 8-byte cp.async from global to the thread's ring slot, issued KG groups
+        of G loads before the value is needed -- and `const double v = io.rget(slot);`, a shared-memory read placed `ahead` statements
+        before the first use.  The global-memory latency (an L2 round trip per checkpoint, profiles/README.md) is then covered by
+        the arithmetic in between without holding a register per load in flight."""
+        import re
+        G, KG, ahead = self.ring
+        pat = re.compile(r"\s*const double (\w+) = io\.(c|x|t|lin|lout|uprev|unext)\((\d+)\);$")
+        loads = []          # (line index, variable, pointer expression)
+        for idx, ln in enumerate(lines):
+            m = pat.match(ln)
+            if m:
+                loads.append((idx, m.group(1), "io.p%s(%s)" % (m.group(2), m.group(3))))
+        if not loads:
+            return lines
+        L = len(loads)
+        NG = (L + G - 1) // G
+        nslot = (KG + 1) * G
+        slot = lambda i: i % nslot
+
+        def issue(j):
+            out = ["%sio.rput(%d, %s);" % (indent, slot(i), loads[i][2]) for i in range(j * G, min(L, (j + 1) * G))]
+            return out + [indent + "io.rcommit();"]
+
+        # where each read goes: `ahead` statements before the original load, never before an earlier read
+        pos, last = [], 0
+        for idx, _, _ in loads:
+            last = max(last, idx - ahead)
+            pos.append(last)
+        at = {}
+        for i, q in enumerate(pos):
+            at.setdefault(q, []).append(i)
+        skip = {idx for idx, _, _ in loads}
+        out = []
+        for j in range(min(KG, NG)):
+            out += issue(j)
+        for idx, ln in enumerate(lines):
+            for i in at.get(idx, ()):
+                j = i // G
+                if i % G == 0:
+                    out.append("%sFL_RING_WAIT(%d);" % (indent, min(KG - 1, NG - 1 - j)))
+                out.append("%sconst double %s = io.rget(%d);" % (indent, loads[i][1], slot(i)))
+                if (i % G == G - 1 or i == L - 1) and j + KG < NG:
+                    out += issue(j + KG)
+            if idx not in skip:
+                out.append(ln)
+        return out
 
     def _pipeline(self, lines, is_load, indent):
         """Segments of `self.segment` arithmetic statements; segment k's loads move to the start of segment k-1, and every

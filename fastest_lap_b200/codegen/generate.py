@@ -37,6 +37,10 @@ SEGMENT = int(os.environ.get("FL_SEGMENT", 0))
 VALUES_ORDER = os.environ.get("FL_VALUES_ORDER", "level")
 DERIV_ORDER = os.environ.get("FL_DERIV_ORDER", "dfs")
 
+# "G,KG,A": the per-node loads of the derivative partitions go through a shared-memory ring filled by cp.async (emit.py _ring):
+# groups of G loads, KG groups in flight, values read A statements ahead of their first use; empty = plain loads
+RING = tuple(int(v) for v in os.environ.get("FL_RING", "").split(",")) if os.environ.get("FL_RING") else None
+
 # > 0: tape nodes that this many (or more) derivative partitions share are checkpointed by the values pass (see shared_tape)
 SHARE = int(os.environ.get("FL_SHARE", 0))
 
@@ -197,13 +201,13 @@ def generate(name, variant):
     def fn(fname, outputs, pres, use_cut=True, cut=None, order="dfs"):
         cut = cut_heavy if cut is None else cut
         lazy = {}
-        if use_cut and SEGMENT > 0:
+        if use_cut and (SEGMENT > 0 or RING):
             # derivative partitions: every input is loaded at first use and software-prefetched one segment ahead
             for l in sum(pres, []):
                 m = re.match(r"const double (\w+) = (io\.\w+\(\d*\));", l)
                 lazy[m.group(1)] = (m.group(1), m.group(2))
             pres = []
-        em = Emitter(g, pt, inputs, dfmt="io.d(%d)", order=order, cut=cut if use_cut else None, lazy_inputs=lazy, segment=SEGMENT if use_cut else 0)
+        em = Emitter(g, pt, inputs, dfmt="io.d(%d)", order=order, cut=cut if use_cut else None, lazy_inputs=lazy, segment=SEGMENT if use_cut else 0, ring=RING if use_cut else None)
         body = em.body(outputs, indent="        ")
         head = "\n".join("        " + l for l in sum(pres, []))
         return ("    template <class IO> static __device__ __forceinline__ void %s(IO& io)\n    {\n%s\n%s\n    }\n" % (fname, head, body))
@@ -281,6 +285,7 @@ def generate(name, variant):
     L.append("    static constexpr int NAUG = %d, AUG_POS = %d, P_AUG = %d;   // augmented states (the last NAUG trapezoid rows); node variable a (q follows); first aug_* parameter" %
              (n_aug, p.aug_pos[0] if n_aug else -1, raw_names.index("aug_bb") if n_aug else -1))
     L.append("    static constexpr int NP_VALUES = %d, NP_JAC = %d, NP_HESS = %d, NP_ALL = %d;   // code partitions of each pass" % (NPARTS["values"], NPARTS["jac"], NPARTS["hess"], NPARTS["all"]))
+    L.append("    static constexpr int RING_SLOTS = %d;   // shared-memory ring slots per thread of the derivative partitions (0: plain loads)" % ((RING[1] + 1) * RING[0] if RING else 0))
     L.append("    static constexpr int NCKV = %d, HAS_TAPE = %d, NP_TAPE = %d;   // checkpoints of the values pass; the tape pass writes all NCK" % (n_heavy, int(SHARE > 0), n_tape))
     for mode in ("values", "tape", "jac", "hess", "all"):
         L.append("    // %s partition operation counts: %s (sum %d)" % (mode, part_sizes[mode], sum(part_sizes[mode])))

@@ -201,6 +201,7 @@ struct Vehicle
     double wind[2] = { 0.0, 0.0 };
     std::map<int, VarParam> variable;          // parameter slot -> values along the arclength
     string track;                              // vehicle_change_track (only recorded: the track is an argument of optimal_laptime)
+    std::vector<std::pair<string, int>> declared;      // (alias, parameter slot): vehicle_declare_new_constant_parameter -- what <compute_sensitivity> differentiates by
 
     int slot(const string& path) const
     {
@@ -477,6 +478,7 @@ struct LapOptions
     // on a hypermesh (fastestlapc.cpp:1276-1283) or one restricted integral quantity (:1298-1306)
     std::vector<string> variables;             // <output_variables><variables>: names asked for (fastestlapc.cpp:1215-1233)
     bool closed = true, warm_start = false, save_warm_start = false;
+    bool sensitivity = false;                  // <compute_sensitivity> (fastestlapc.cpp:1254, 1525)
     vec q_start, u_start;                      // open simulations: <initial_condition><q from_table/><u from_table/> (fastestlapc.cpp:1237-1249)
     int aug_kind = FL_AUG_NONE;
     vec hypermesh;
@@ -491,7 +493,7 @@ static LapOptions lap_options(const string& text, int model)
     if (model == FL_MODEL_F1_3DOF) { o.diss[0] = 50.0; o.diss[1] = 20.0 * 8.0e-4; } else { o.diss[0] = 1.0e-2; o.diss[1] = 200.0 * 200.0 * 1.0e-10; }
     if (trim(text).empty()) return o;
     const auto root = parse_xml(text);
-    if (truthy(root->child("compute_sensitivity"))) throw error("[ERROR] optimal_laptime -> option <compute_sensitivity> is not supported by the B200 path");
+    o.sensitivity = truthy(root->child("compute_sensitivity"));
     int n_coupling = 0;
     if (const Xml* ic = root->child("integral_constraints"))
         for (auto& q : ic->kids)
@@ -569,6 +571,8 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     if (o.save_warm_start && (!o.closed || o.aug_kind != FL_AUG_NONE))
         throw error("[ERROR] optimal_laptime -> <save_warm_start> of open simulations / with hypermesh controls or integral constraints is not supported");
     if (!o.closed && o.aug_kind != FL_AUG_NONE) throw error("[ERROR] optimal_laptime -> hypermesh controls and integral constraints need a closed simulation");
+    if (o.sensitivity && (!o.closed || o.aug_kind != FL_AUG_NONE || !veh.variable.empty()))
+        throw error("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for closed laps with constant parameters, without hypermesh controls or integral constraints");
     const vec s = o.warm_start ? ws.s : s_in;
     const int np = (int)s.size();
     if (np < 2) throw error("[ERROR] optimal_laptime -> provide at least two values of arclength");
@@ -630,7 +634,8 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     fl_nlp_sizes(nlp, &n, &m, nullptr, nullptr);
     const int nvn = o.closed ? np : np - 1;          // nodes that carry variables
     const int NV = n / nvn;
-    vec X(n), Ylam(m), Zl(n), Zu(n);
+    vec X(n), Ylam(m), Zl(n), Zu(n), sigx, sigs;
+    double dc_last = 0.0;
     std::vector<int> status(1, 0), iters(1, 0);
     double obj = 0.0;
     string msg;
@@ -661,6 +666,12 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         if (o.warm_start) ok = fl_ipm_solve_warm(ipm, ws.x.data(), ws.lam.data(), ws.zl.data(), ws.zu.data(), 1.0e-3, 1.0e-4, o.print_level >= 5 ? 1 : 0);
         else ok = fl_ipm_solve(ipm, x0.data(), o.print_level >= 5 ? 1 : 0);
         if (!ok || !fl_ipm_results(ipm, X.data(), Ylam.data(), Zl.data(), Zu.data(), &obj, status.data(), iters.data(), nullptr)) msg = fl_error();
+        if (msg.empty() && status[0] >= 1 && o.sensitivity && !veh.declared.empty())
+        {
+            // barrier terms of the solution, with the solver's own bounds and slacks: the KKT matrix the sensitivities are solved with
+            sigx.resize(n); sigs.resize((size_t)(o.closed ? np : np - 1) * 6);
+            if (!fl_ipm_sigma(ipm, sigx.data(), sigs.data(), &dc_last)) msg = fl_error();
+        }
         fl_ipm_destroy(ipm);
         if (!msg.empty() || o.warm_start || !o.closed) break;          // (the retries are for closed laps from the steady-state start)
     }
@@ -677,6 +688,48 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
             if (!fl_eval_outputs(nlp, X.data(), out.data())) msg = fl_error();
             else for (int k : wanted) channels[fl_nlp_output_name(nlp, k)] = vec(out.begin() + (size_t)k * np, out.begin() + (size_t)(k + 1) * np);
         }
+    }
+    // Parameter sensitivities (Optimal_laptime with check_optimality, optimal_laptime.hpp:564-588): dx/dp = -K^-1 d/dp (grad f + J^T lambda, g)
+    // at fixed (x, lambda), K = the KKT matrix of the solution factorised by the device kernels; the right-hand side is a central
+    // difference of the GPU callbacks over the parameter (relative step 1e-6: the callbacks are closed-form in the parameters).
+    std::vector<vec> dx_dp;
+    if (msg.empty() && status[0] >= 1 && !sigx.empty())
+    {
+        int nnzj = 0, nnzh = 0;
+        fl_nlp_sizes(nlp, nullptr, nullptr, &nnzj, &nnzh);
+        std::vector<int> jr(nnzj), jc(nnzj), hr(nnzh), hc(nnzh);
+        fl_ipm* ipm = fl_ipm_create(nlp, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (!ipm || !fl_nlp_structure(nlp, jr.data(), jc.data(), hr.data(), hc.data())) msg = fl_error();
+        for (size_t q = 0; msg.empty() && q < veh.declared.size(); ++q)
+        {
+            const int slot = veh.declared[q].second;
+            const double step = 1.0e-6 * std::max(std::fabs(v0.params[slot]), 1.0e-3);
+            vec gl[2], gv[2];
+            for (int side = 0; side < 2 && msg.empty(); ++side)
+            {
+                vec pp = v0.params;
+                pp[slot] += side == 0 ? step : -step;
+                vec cd = ctrl_default;
+                if (f1) cd[3] = pp[18];
+                fl_problem_desc d2 = d;
+                d2.vehicle_params = pp.data(); d2.ctrl_default = cd.data();
+                fl_nlp* h2 = fl_nlp_create(&d2);
+                if (!h2) { msg = fl_error(); break; }
+                vec g(m), grad(n), jac(nnzj);
+                if (!fl_eval_all(h2, X.data(), Ylam.data(), 1.0, nullptr, g.data(), grad.data(), jac.data(), nullptr)) msg = fl_error();
+                fl_nlp_destroy(h2);
+                for (int k = 0; k < nnzj; ++k) grad[jc[k]] += jac[k] * Ylam[jr[k]];
+                gl[side] = grad; gv[side] = g;
+            }
+            if (!msg.empty()) break;
+            vec r1(n), r2(m), dx(n), dy(m);
+            for (int i = 0; i < n; ++i) r1[i] = -(gl[0][i] - gl[1][i]) / (2.0 * step);
+            for (int i = 0; i < m; ++i) r2[i] = -(gv[0][i] - gv[1][i]) / (2.0 * step);
+            const double dw0 = 0.0;
+            if (!fl_kkt_factor_solve(ipm, X.data(), Ylam.data(), sigx.data(), sigs.data(), &dw0, &dc_last, r1.data(), r2.data(), 3, 0, dx.data(), dy.data(), nullptr, nullptr)) msg = fl_error();
+            dx_dp.push_back(dx);
+        }
+        if (ipm) fl_ipm_destroy(ipm);
     }
     fl_nlp_destroy(nlp);
     if (!msg.empty()) throw error("[ERROR] optimal_laptime -> " + msg);
@@ -767,6 +820,49 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         scalars[pre + "integral_quantities." + o.integral_name] = aug_values[0];
     }
     overwrite(pre + "optimization_data.number_of_iterations"); scalars[pre + "optimization_data.number_of_iterations"] = (double)iters[0];
+    // derivatives with respect to the declared parameters: "<prefix>derivatives/<variable>/<alias>" (fastestlapc.cpp:1585-1615, 1687-1706; the
+    // reference fills chassis.velocity.x and time and leaves other requested vectors at zero -- here every input and optimised control
+    // gets its derivative); the lap time's by the trapezoid rule over d/dp of dt/ds (optimal_laptime.hpp:664-724)
+    for (size_t q = 0; q < dx_dp.size(); ++q)
+    {
+        const string& alias = veh.declared[q].first;
+        const vec& dx = dx_dp[q];
+        vec d2(np), dtime(np, 0.0);
+        for (int i = 0; i < np; ++i)
+        {
+            const double* x = X.data() + (size_t)i * NVo;
+            const double* dxi = dx.data() + (size_t)i * NVo;
+            const double mu = nodes[(size_t)i * 6 + 1], ph = nodes[(size_t)i * 6 + 2];
+            const double kz = -std::sin(ph) * nodes[(size_t)i * 6 + 4] + std::cos(mu) * std::cos(ph) * nodes[(size_t)i * 6 + 3];
+            const double ca = std::cos(x[a_col]), sa = std::sin(x[a_col]), un = x[iu] * ca - x[iv] * sa, r = 1.0 - kz * x[n_col];
+            d2[i] = -kz * dxi[n_col] / un - ca * r / (un * un) * dxi[iu] + sa * r / (un * un) * dxi[iv] + r * (x[iv] * ca + x[iu] * sa) / (un * un) * dxi[a_col];
+        }
+        double dlap = 0.0;
+        for (int i = 0; i < np; ++i)
+        {
+            const int j = (i + 1) % np;
+            const double h = (i + 1 < np) ? s[i + 1] - s[i] : trk.length - s[np - 1];
+            dlap += h * ((1.0 - o.sigma) * d2[i] + o.sigma * d2[j]);
+            if (i + 1 < np) dtime[i + 1] = dlap;
+        }
+        overwrite(pre + "derivatives/laptime/" + alias); scalars[pre + "derivatives/laptime/" + alias] = dlap;
+        int kk = 0;
+        for (int i = 0; i < n_in; ++i)
+        {
+            if (string(in_names[i]) == "time") { out_vec("derivatives/time/" + alias, dtime); continue; }
+            vec col(np);
+            for (int qn = 0; qn < np; ++qn) col[qn] = dx[(size_t)qn * NVo + kk];
+            out_vec(string("derivatives/") + in_names[i] + "/" + alias, col);
+            ++kk;
+        }
+        for (int c = 0; c < n_ctrl; ++c)
+        {
+            vec col(np, 0.0);
+            for (int fm = 0; fm < 2; ++fm)
+                if (full_mesh[fm] == c) for (int qn = 0; qn < np; ++qn) col[qn] = dx[(size_t)qn * NVo + kk + fm];
+            out_vec(string("derivatives/") + ct_names[c] + "/" + alias, col);
+        }
+    }
 }
 
 // Steady_state::gg_diagram (steady_state.hpp:696-880) at one speed, in the reference's order of solves; accelerations in m/s2
@@ -1140,10 +1236,18 @@ void track_download_data(double* data, const char* name, const int n, const char
 
 void vehicle_set_parameter(const char* name, const char* parameter, const double value) { FLC_TRY flc::vehicle(name).set(parameter, value); FLC_CATCH() }
 
-void vehicle_declare_new_constant_parameter(const char* name, const char* path, const char*, const double value)
+void vehicle_declare_new_constant_parameter(const char* name, const char* path, const char* alias, const double value)
 {
-    // (the alias names the parameter in the reference's sensitivity analysis, which is not computed here; the value is set)
-    FLC_TRY flc::vehicle(name).set(path, value); FLC_CATCH()
+    // the value is set, and the alias names the derivatives <compute_sensitivity> of optimal_laptime stores (fastestlapc.cpp:899-939)
+    FLC_TRY
+        flc::Vehicle& v = flc::vehicle(name);
+        v.set(path, value);
+        const int slot = v.slot(path);
+        if (slot < 0) throw flc::error(std::string("Parameter \"") + path + "\" cannot be differentiated");
+        const std::string a = flc::trim(alias ? alias : "");
+        for (auto& d : v.declared) if (d.first == a) throw flc::error("Parameter alias \"" + a + "\" already declared");
+        v.declared.emplace_back(a, slot);
+    FLC_CATCH()
 }
 
 void vehicle_declare_new_variable_parameter(const char* name, const char* path, const char*, const int n_parameters, const double* values,

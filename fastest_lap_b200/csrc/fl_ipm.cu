@@ -682,6 +682,51 @@ int fl_ipm_results(fl_ipm* s, double* x, double* y, double* zl, double* zu, doub
     return 1;
 }
 
+// Barrier terms of the iterates the solver holds (after a solve: of the returned points): sigx [batch][n] = zl / (x - xl) + zu / (xu - x),
+// sigs [batch][n_elements * NINEQ] = vl / (s - sl) + vu / (su - s) with the solver's own (relaxed) bounds, slacks and slack multipliers,
+// and the constraint regularisation dc [batch] of the last iteration.  With them fl_kkt_factor_solve solves systems with the KKT matrix
+// of the solution -- parameter sensitivities (optimal_laptime.hpp:564-588).  Any output may be NULL.
+int fl_ipm_sigma(fl_ipm* s, double* sigx, double* sigs, double* dc)
+{
+    FLI_ALIVE(s);
+    FLI_CUDA(cudaSetDevice(s->nlp->device));
+    FLI_CUDA(cudaStreamSynchronize(s->nlp->stream));
+    const fl_ipm_dev& I = s->I;
+    const size_t B = s->B, n = I.n, ni = I.ni;
+    auto down = [&](const double* d, size_t count, std::vector<double>& h) { h.resize(count); return cudaMemcpy(h.data(), d, count * sizeof(double), cudaMemcpyDeviceToHost); };
+    if (sigx)
+    {
+        std::vector<double> x, zl, zu, xl, xu;
+        FLI_CUDA(down(I.x, B * n, x)); FLI_CUDA(down(I.zl, B * n, zl)); FLI_CUDA(down(I.zu, B * n, zu));
+        FLI_CUDA(down(I.xl, (I.bn ? B : 1) * n, xl)); FLI_CUDA(down(I.xu, (I.bn ? B : 1) * n, xu));
+        for (size_t b = 0; b < B; ++b)
+            for (size_t i = 0; i < n; ++i)
+            {
+                const size_t k = b * n + i, kb = b * I.bn + i;
+                sigx[k] = zl[k] / (x[k] - xl[kb]) + zu[k] / (xu[kb] - x[k]);
+            }
+    }
+    if (sigs)
+    {
+        std::vector<double> sv, vl, vu, sl, su;
+        FLI_CUDA(down(I.s, B * ni, sv)); FLI_CUDA(down(I.vl, B * ni, vl)); FLI_CUDA(down(I.vu, B * ni, vu));
+        FLI_CUDA(down(I.sl, (I.bi ? B : 1) * ni, sl)); FLI_CUDA(down(I.su, (I.bi ? B : 1) * ni, su));
+        for (size_t b = 0; b < B; ++b)
+            for (size_t i = 0; i < ni; ++i)
+            {
+                const size_t k = b * ni + i, kb = b * I.bi + i;
+                sigs[k] = vl[k] / (sv[k] - sl[kb]) + vu[k] / (su[kb] - sv[k]);
+            }
+    }
+    if (dc)
+    {
+        std::vector<fl_ipm_lap> laps(B);
+        FLI_CUDA(cudaMemcpy(laps.data(), I.lap, B * sizeof(fl_ipm_lap), cudaMemcpyDeviceToHost));
+        for (size_t b = 0; b < B; ++b) dc[b] = laps[b].dc;
+    }
+    return 1;
+}
+
 // Partitioned (parallel-in-the-stages) factorisation: policy 0 = automatic (when at most `max_laps` laps are active), 1 = always,
 // -1 = never.  Returns the number of separators (0: not available for this problem).
 int fl_ipm_set_partitioned(fl_ipm* s, int policy, int max_laps)

@@ -318,6 +318,20 @@ struct DerivIO
     __device__ __forceinline__ double obj() const { return obj_; }
     __device__ __forceinline__ double uprev(int c) const { return xp[G::ctrl_pos(c)]; }
     __device__ __forceinline__ double unext(int c) const { return xq[G::ctrl_pos(c)]; }
+    // codegen FL_RING: per-node loads as 8-byte cp.async copies into a ring of shared-memory slots (one 256-byte row per slot and
+    // warp), issued groups ahead of their use and read back with ld.shared: the L2 round trip of a checkpoint load overlaps the
+    // arithmetic in between without a register per load in flight
+    unsigned ring_;                                                                    // shared-space address of this thread's slot 0
+    __device__ __forceinline__ const double* pc(int k) const { return Cn + k * 32; }
+    __device__ __forceinline__ const double* px(int k) const { return xn + k; }
+    __device__ __forceinline__ const double* pt(int k) const { return tcn + k * 32; }
+    __device__ __forceinline__ const double* plin(int r) const { return lin_ + r; }
+    __device__ __forceinline__ const double* plout(int r) const { return lout_ + r; }
+    __device__ __forceinline__ const double* puprev(int c) const { return xp + G::ctrl_pos(c); }
+    __device__ __forceinline__ const double* punext(int c) const { return xq + G::ctrl_pos(c); }
+    __device__ __forceinline__ void rput(int slot, const double* p) const { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(ring_ + slot * 256), "l"(p)); }
+    __device__ __forceinline__ void rcommit() const { asm volatile("cp.async.commit_group;"); }
+    __device__ __forceinline__ double rget(int slot) const { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ring_ + slot * 256)); return v; }
     __device__ __forceinline__ void val(int, double) const {}
     // codegen FL_SEGMENT > 0 separates code segments with fence(); measured on B200 (profiles/README.md) the fenced,
     // software-prefetched schedule is slower than ptxas' own (the spills are the reverse sweep's tape, not hoisted loads)
@@ -328,6 +342,8 @@ struct DerivIO
     __device__ __forceinline__ void h(int k, double v) const { h_[k * sH] = v; }
     __device__ __forceinline__ void cpl(int k, double v) const { if (hasC) c_[k * sC] = v; }
 };
+
+#define FL_RING_WAIT(N) asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory")
 
 enum { FL_DERIV_JAC = 1, FL_DERIV_HESS = 2, FL_DERIV_ALL = 3 };
 
@@ -347,6 +363,8 @@ template <class G> struct deriv_parts<G, FL_DERIV_ALL>  { static constexpr int N
 // 1-D TMA path, completion on an mbarrier); the straight-line code then reads its checkpoints with LDS at immediate
 // offsets instead of ~70 dependent global loads per partition (the long-scoreboard stalls of profiles/prof_r1g).
 template <class G> constexpr size_t fl_stage_bytes() { return FL_STAGE ? (size_t)(FL_DBLOCK / 32) * (G::NCK * 256 + 8) : 0; }
+// ring of the asynchronous loads (codegen FL_RING): RING_SLOTS rows of 256 bytes per warp
+template <class G> constexpr size_t fl_ring_bytes(int threads) { return (size_t)(threads / 32) * G::RING_SLOTS * 256; }
 
 template <class G, int WHAT, bool ASSEMBLE, int CD>
 __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
@@ -416,6 +434,12 @@ __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __gri
     io.lin_ = lam + (size_t)e_in * G::NCPE;
     io.lout_ = has_out ? lam + (size_t)e_out * G::NCPE : P.zeros;
     io.obj_ = P.obj_factor;
+    if constexpr (G::RING_SLOTS > 0)
+    {
+        static_assert(!FL_STAGE, "the staged checkpoints and the load ring both use the dynamic shared memory");
+        extern __shared__ __align__(128) unsigned char fl_ring_smem[];
+        io.ring_ = (unsigned)__cvta_generic_to_shared(fl_ring_smem) + (threadIdx.x >> 5) * (G::RING_SLOTS * 256) + (threadIdx.x & 31) * 8;
+    }
 #if FL_STAGE
     io.Cn = sC + lane;
 #else
@@ -503,7 +527,7 @@ struct variant_ops
     {
         // n_elements <= n_var_nodes + 1: one more block column covers the assembly slice of an open problem
         const unsigned nb = (P.n_points + FL_DBLOCK - 1) / FL_DBLOCK;
-        const size_t sm = fl_stage_bytes<G>();
+        const size_t sm = fl_stage_bytes<G>() + fl_ring_bytes<G>(FL_DBLOCK);
         static unsigned long long attr_set = 0;          // per device (and per instantiation of this function)
         int dev = 0;
         cudaGetDevice(&dev);
@@ -522,7 +546,7 @@ struct variant_ops
         // an SM on its own, and a batch of 2016 problems x 8 partitions then runs in 110 waves of blocks with ONE active thread each
         // (208 us per launch in the G-G sweep, profiles/r2_gg_launches.md); the assembly slice needs the full block and is launched on its own
         const bool tiny = !FL_STAGE && P.n_points <= 32 && !with_assemble;
-        cfg.blockDim = dim3(tiny ? 32 : FL_DBLOCK, 1, 1); cfg.dynamicSmemBytes = sm; cfg.stream = s;
+        cfg.blockDim = dim3(tiny ? 32 : FL_DBLOCK, 1, 1); cfg.dynamicSmemBytes = tiny ? fl_ring_bytes<G>(32) : sm; cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -42,6 +42,7 @@ def _bind(lib):
     lib.fl_ipm_set_partitioned.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.fl_ipm_set_warp_kkt.argtypes = [C.c_void_p, C.c_int]
     lib.fl_ipm_solve_warm.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int]
+    lib.fl_ipm_sigma.argtypes = [C.c_void_p, _dp, _dp, _dp]
     lib._ipm_bound = True
 
 
@@ -128,6 +129,15 @@ class LapSolver:
         return dict(x=x, y=y, zl=zl, zu=zu, obj=obj, status=status, iters=iters, error=err[:, 0], constr_viol=err[:, 1], dual_inf=err[:, 2], mu=err[:, 3],
                     device_ms=ms.value, stats=dict(zip(("solver_launches", "factor_launches", "solve_launches", "full_rounds", "fg_rounds", "outer_rounds"), list(stats))))
 
+    def sigma(self):
+        """Barrier terms of the points the solver holds (after solve(): the returned ones): sigx [batch][n], sigs [batch][n_ineq],
+        dc [batch] -- what kkt_factor_solve needs to solve with the KKT matrix of the solution (lap_sensitivities)."""
+        nlp, B = self.nlp, self.nlp.batch
+        sigx, sigs, dc = np.empty((B, nlp.n)), np.empty((B, nlp.problem.n_elements * 6)), np.empty(B)
+        if not self._lib.fl_ipm_sigma(self._h, _ptr(sigx), _ptr(sigs), _ptr(dc)):
+            raise RuntimeError("fl_ipm_sigma: " + self._lib.fl_last_error().decode())
+        return sigx, sigs, dc
+
     def kkt_factor_solve(self, x, lam, sigx, sigs, dw, dc, r1, r2, refine_steps=0, ls_mode=False):
         """One factorisation + solve of the augmented system for every lap (building block / test entry)."""
         nlp, B = self.nlp, self.nlp.batch
@@ -168,6 +178,64 @@ def lap_time(problem, x, obj):
             left = np.full(len(h), rate[0]); left[-1] = rate[-1]
             pen += 0.5 * problem.dissipation[c] * np.sum((left * left + np.roll(rate, -1) ** 2) * h)
     return float(obj) - pen
+
+
+def lap_sensitivities(problem, x, lam, sigma, perturbed, device=0):
+    """Derivatives of a converged lap with respect to vehicle parameters -- the reference's sensitivity analysis
+    (Optimal_laptime with check_optimality, optimal_laptime.hpp:564-588: lion's Sensitivity_analysis solves the linearised
+    optimality conditions for dx/dp).  Here: the KKT matrix of the solution, [W + Sigma_x, J^T; J, -D] with the barrier terms of the
+    final iterate (`sigma` = LapSolver.sigma() taken before the solver was closed), is factorised once per parameter by the device
+    kernels (kkt_factor_solve) and solved for  -d/dp [grad f + J^T lambda; g]  at fixed (x, lambda); that right-hand side is a central
+    difference of the GPU callbacks over `perturbed` = [(problem with p + h, problem with p - h, 2 h), ...] -- the callbacks are
+    closed-form in the parameters, a relative step of 1e-6 leaves a relative error of about 1e-9, three digits below the 1e-6 the
+    reference's own test asks of the result (f1_sensitivity_analysis.cpp:24-26, against re-solved laps).
+    Returns (dx_dp [P][n], dlambda_dp [P][m])."""
+    x, lam = np.ascontiguousarray(x, dtype=np.float64).ravel(), np.ascontiguousarray(lam, dtype=np.float64).ravel()
+    sigx, sigs, dc = sigma
+
+    def grad_lagrangian(q):
+        nlp = CollocationNLP(q, device=device)
+        try:
+            jr, jc, _, _ = nlp.structure()
+            o = nlp.eval_all(x, lam, 1.0, want=("g", "grad", "jac"))
+            gl = o["grad"][0] + np.bincount(jc, weights=o["jac"][0] * lam[jr], minlength=nlp.n)
+            return gl, o["g"][0].copy()
+        finally:
+            nlp.close()
+
+    nlp = CollocationNLP(problem, device=device)
+    solver = LapSolver(nlp)
+    dxs, dys = [], []
+    try:
+        for plus, minus, two_h in perturbed:
+            (g1, c1), (g0, c0) = grad_lagrangian(plus), grad_lagrangian(minus)
+            r1, r2 = -(g1 - g0) / two_h, -(c1 - c0) / two_h
+            dx, dy, neg, zero = solver.kkt_factor_solve(x, lam, sigx[0], sigs[0], 0.0, dc[0], r1, r2, refine_steps=3)
+            dxs.append(dx[0].copy()); dys.append(dy[0].copy())
+    finally:
+        solver.close(); nlp.close()
+    return np.array(dxs), np.array(dys)
+
+
+def dlaptime_dp(problem, x, dx):
+    """Derivative of the lap time from dx/dp, as the reference integrates it (optimal_laptime.hpp:664-724): the trapezoid rule over
+    d/dp of dt/ds = (1 - kz n) / (u cos(alpha) - v sin(alpha)), which depends on the parameters through the states only.
+    Closed laps, flat or 3-D tracks (kz = the z component of the road-frame curvature)."""
+    from .problem import N_INPUTS
+    if not problem.closed:
+        raise NotImplementedError("dlaptime_dp: closed laps")
+    X, DX = np.asarray(x).reshape(-1, problem.nv), np.asarray(dx).reshape(-1, problem.nv)
+    iu, iv = (4, 5) if problem.model == 0 else (1, 2)
+    i_n, i_a = N_INPUTS[problem.model] - 3, N_INPUTS[problem.model] - 2          # the last two inputs once the time is removed
+    nd = problem.track_nodes
+    kz = -np.sin(nd[:, 2]) * nd[:, 4] + np.cos(nd[:, 1]) * np.cos(nd[:, 2]) * nd[:, 3]
+    u, v, n, a = X[:, iu], X[:, iv], X[:, i_n], X[:, i_a]
+    un, r = u * np.cos(a) - v * np.sin(a), 1.0 - kz * n
+    d = (-kz * DX[:, i_n] / un - np.cos(a) * r / un ** 2 * DX[:, iu] + np.sin(a) * r / un ** 2 * DX[:, iv]
+         + r * (v * np.cos(a) + u * np.sin(a)) / un ** 2 * DX[:, i_a])
+    h = np.diff(np.append(problem.s, problem.track_length))
+    sg = problem.sigma
+    return float(np.sum(h * ((1.0 - sg) * d + sg * np.roll(d, -1)))), d
 
 
 def solve_lap(problem, x_start, options=None, device=0, bounds=None, coarse_nodes=500, sequence_from=3000, verbose=False):

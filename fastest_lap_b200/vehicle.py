@@ -75,7 +75,22 @@ class Vehicle:
         v = Vehicle(self.model, self.params.copy(), self.name)
         v.wind = list(self.wind)
         v.variable = {k: tuple(np.array(a) for a in val) for k, val in getattr(self, "variable", {}).items()}
+        v.declared = list(getattr(self, "declared", []))
         return v
+
+    def declare_parameter(self, path, alias, value):
+        """A constant parameter registered under an alias (vehicle_declare_new_constant_parameter, fastestlapc.cpp:899-939; the
+        reference's Model_parameters list): its value is set, and optimal_laptime's sensitivity analysis differentiates with
+        respect to it."""
+        key = path[len("vehicle/"):] if path.startswith("vehicle/") else path
+        self.set_parameter(path, value)
+        if key not in self.paths:
+            raise KeyError('Parameter "%s" cannot be differentiated' % path)
+        if not hasattr(self, "declared"):
+            self.declared = []
+        if any(a == alias for a, _ in self.declared):
+            raise KeyError('Parameter alias "%s" already declared' % alias)
+        self.declared.append((alias, key))
 
     def declare_variable_parameter(self, path, values, mesh_indexes, mesh_points):
         """A parameter that varies with the arclength (vehicle_declare_new_variable_parameter, fastestlapc.cpp:941-981;

@@ -219,6 +219,11 @@ int fl_ipm_solve_warm(fl_ipm* ipm, const double* x0, const double* lambda0, cons
 /* any output may be NULL: x [batch][n], y [batch][m], zl, zu [batch][n], obj [batch], status [batch], iters [batch],
  * errors [batch][4] = (scaled NLP error, constraint violation, dual infeasibility, barrier parameter) */
 int fl_ipm_results(fl_ipm* ipm, double* x, double* y, double* zl, double* zu, double* obj, int* status, int* iters, double* errors);
+/* Barrier terms at the points the solver holds (after a solve: the returned ones), with its own relaxed bounds, slacks and slack
+ * multipliers: sigx [batch][n], sigs [batch][n_elements * 6], dc [batch] (constraint regularisation of the last iteration); any may be
+ * NULL.  Together with fl_kkt_factor_solve: linear systems with the KKT matrix of the solution, i.e. the parameter sensitivities
+ * dx/dp = -K^-1 d(grad L, c)/dp of the reference's Sensitivity_analysis (optimal_laptime.hpp:564-588). */
+int fl_ipm_sigma(fl_ipm* ipm, double* sigx, double* sigs, double* dc);
 /* [0] solver kernel launches, [1] factorisation launches, [2] solve launches, [3] full callback rounds, [4] f/g-only rounds, [5] outer rounds */
 void fl_ipm_stats(const fl_ipm* ipm, long stats[6], double* device_ms);
 /* The factorisation has two schedules: one block per lap walking the whole chain (throughput: many laps), or the chain cut

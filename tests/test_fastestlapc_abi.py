@@ -284,3 +284,51 @@ def test_warm_start_and_open_section_through_the_c_api(lib, files):
     assert 0.9 * (tl[99] - tl[0]) <= to[-1] - to[0] <= tl[99] - tl[0] + 1e-6
     assert np.max(np.abs(uo[:20] - vec("cold/chassis.velocity.x")[:20])) <= 0.5
     lib.delete_variable(b"*")
+
+
+@pytest.mark.gpu
+def test_sensitivities_through_the_c_api(lib, files):
+    """<compute_sensitivity> (fastestlapc.cpp:1254, 1525): parameters declared with vehicle_declare_new_constant_parameter get
+    "<prefix>derivatives/laptime/<alias>" and "<prefix>derivatives/<variable>/<alias>" (:1585-1615, 1687-1706).  Checked as the
+    reference checks its own analysis (f1_sensitivity_analysis.cpp:20-26): against the difference of two laps re-solved with the
+    parameter moved, lap time to 1e-6, states to 1e-5."""
+    lib.delete_variable(b"*")
+    lib.create_vehicle_from_xml(b("car"), b(files["f1"]))
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/inertia/Ixx"), c.c_double(0.0))
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/inertia/Iyy"), c.c_double(0.0))
+    lib.vehicle_declare_new_constant_parameter(b("car"), b("vehicle/chassis/mass"), b("mass"), c.c_double(660.0))
+    lib.vehicle_declare_new_constant_parameter(b("car"), b("vehicle/chassis/aerodynamics/cd"), b("cd"), c.c_double(0.9))
+    assert err(lib) == ""
+    lib.vehicle_declare_new_constant_parameter(b("car"), b("vehicle/chassis/mass"), b("mass"), c.c_double(660.0))
+    assert "already declared" in err(lib)
+    lib.create_track_from_xml(b("catalunya"), b(files["catalunya"]))
+    s = np.linspace(0.0, lib.track_download_length(b("catalunya")), 501)[:-1]
+    c_s = (c.c_double * len(s))(*s)
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><compute_sensitivity>true</compute_sensitivity><output_variables><prefix>run/</prefix></output_variables></options>"))
+    assert err(lib) == ""
+    dT = {a: lib.download_scalar(b("run/derivatives/laptime/" + a)) for a in ("mass", "cd")}
+    print("d laptime / d mass %.8f s/kg, / d cd %.8f s" % (dT["mass"], dT["cd"]))
+    assert dT["mass"] > 0.0 and dT["cd"] > 0.0
+
+    def vector(name):
+        v = (c.c_double * 500)()
+        lib.download_vector(v, c.c_int(500), b(name))
+        return np.array(v)
+    du = vector("run/derivatives/chassis.velocity.x/mass")
+    t0, u0 = lib.download_scalar(b("run/laptime")), vector("run/chassis.velocity.x")
+    # the same lap with the mass moved by +-0.05 kg
+    laps = {}
+    for sign in (1.0, -1.0):
+        lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/mass"), c.c_double(660.0 + sign * 0.05))
+        lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><output_variables><prefix>moved/</prefix></output_variables></options>"))
+        assert err(lib) == ""
+        laps[sign] = (lib.download_scalar(b("moved/laptime")), vector("moved/chassis.velocity.x"))
+    fd_T = (laps[1.0][0] - laps[-1.0][0]) / 0.1
+    fd_u = (laps[1.0][1] - laps[-1.0][1]) / 0.1
+    print("re-solved laps: %.8f s/kg; max |du/dm - difference| %.2e of %.2e" % (fd_T, np.max(np.abs(du - fd_u)), np.max(np.abs(du))))
+    assert abs(dT["mass"] - fd_T) <= 1.0e-6
+    assert np.max(np.abs(du - fd_u)) <= 1.0e-5
+    assert abs(t0 - 0.5 * (laps[1.0][0] + laps[-1.0][0])) <= 1.0e-6
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><compute_sensitivity>true</compute_sensitivity><closed_simulation>false</closed_simulation></options>"))
+    assert err(lib) != ""
+    lib.delete_variable(b"*")
