@@ -20,17 +20,25 @@ def _model_of(params):
     return MODEL_F1 if np.shape(params)[-1] == 58 else MODEL_KART
 
 
-def _options(tol=1.0e-8):
+import os
+
+# Iterations given to the FIRST attempt at the 2 B maximum / minimum NLPs of a sweep.  A batch advances in lock step and costs its
+# slowest problem's iterations whatever its size (tools/gg_profile.py: 70 iterations for 4032 NLPs whose median is below 20); the
+# few problems that need more are handed to the continuation from their predecessor, which the reference applies to every point.
+FIRST_PASS_ITER = int(os.environ.get("FL_GG_FIRST_ITER", 30))
+
+
+def _options(tol=1.0e-8, max_iter=300):
     o = default_options()
     o.tol, o.constr_viol_tol, o.acceptable_tol = tol, tol, 1.0e-6        # steady_state.hpp:84-88
-    o.max_iter = 300          # an NLP of 8-13 variables that has not converged by then is retried by continuation instead
+    o.max_iter = max_iter     # an NLP of 8-13 variables that has not converged by then is retried by continuation instead
     return o
 
 
-def solve_batch(params, spec, x0, device=0, bounds=None):
+def solve_batch(params, spec, x0, device=0, bounds=None, max_iter=300):
     """Solves one batch of steady-state NLPs; returns the LapSolver result dict."""
     nlp = SteadyStateNLP(_model_of(params), params, spec, device=device)
-    solver = LapSolver(nlp, options=_options(), bounds=bounds)
+    solver = LapSolver(nlp, options=_options(max_iter=max_iter), bounds=bounds)
     out = solver.solve(x0)
     solver.close(); nlp.close()
     return out
@@ -115,10 +123,22 @@ def speed_envelope(params, speeds, device=0):
     out0 = solve_batch(params, np.stack([speeds, z, z, z, z, z, z], axis=1), np.tile(X0_F1 if f1 else X0, (S, 1)), device)
     x_0g = out0["x"].copy()
     x_0g[:, ia] = 0.0; x_0g[:, iy] = 0.0
-    out_lat = solve_batch(params, np.stack([speeds, z, z, one, one, z, -one], axis=1), x_0g, device)
     bnd_acc, bnd_brk = _base_bounds(params, False, device), _base_bounds(params, True, device)
-    lon_max = solve_batch(params, np.stack([speeds, z, z, one, z, -one, z], axis=1), x_0g, device, bounds=bnd_acc if f1 else None)
-    lon_min = solve_batch(params, np.stack([speeds, z, z, one, z, one, z], axis=1), x_0g, device, bounds=bnd_brk if f1 else None)
+    spec_lat = np.stack([speeds, z, z, one, one, z, -one], axis=1)
+    spec_max = np.stack([speeds, z, z, one, z, -one, z], axis=1)
+    spec_min = np.stack([speeds, z, z, one, z, one, z], axis=1)
+    if f1:
+        # (the F1's braking NLP has its own variable bounds, limebeer2014f1.h:62-80)
+        out_lat = solve_batch(params, spec_lat, x_0g, device)
+        lon_max = solve_batch(params, spec_max, x_0g, device, bounds=bnd_acc)
+        lon_min = solve_batch(params, spec_min, x_0g, device, bounds=bnd_brk)
+    else:
+        # the three NLPs of a speed start from the same point and share the bounds: ONE batch of 3 S problems (a batch costs its
+        # slowest problem's iterations whatever its size, profiles/r2_gg_launches.md)
+        p3 = params if np.ndim(params) == 1 else np.tile(np.asarray(params), (3, 1))
+        o3 = solve_batch(p3, np.concatenate([spec_lat, spec_max, spec_min]), np.tile(x_0g, (3, 1)), device)
+        part = lambda a, b: {key: (val[a * S:b * S] if isinstance(val, np.ndarray) and len(val) == 3 * S else val) for key, val in o3.items()}
+        out_lat, lon_max, lon_min = part(0, 1), part(1, 2), part(2, 3)
     return dict(x_0g=x_0g, zero_g=out0["x"].copy(), zero_g_solved=out0["status"] >= 1, x_lat=out_lat["x"].copy(), ay_max=out_lat["x"][:, iy].copy(),
                 ax_lat=out_lat["x"][:, ia].copy(), ay_max_solved=out_lat["status"] >= 1, ay_max_iters=out_lat["iters"].copy(),
                 ax_lon_max=lon_max["x"][:, ia].copy(), ax_lon_min=lon_min["x"][:, ia].copy(),
@@ -160,27 +180,40 @@ def longitudinal_limits(params, env, k, ay, prev, device=0):
     b_max = lap_bounds(env["bounds_accelerate"], env["ax_lat"] - 0.5 / unit, env["ax_lon_max"] + 0.1 / unit)
     b_min = lap_bounds(env["bounds_brake"], env["ax_lon_min"] - 0.1 / unit, env["ax_lat"] + 0.1 / unit)
     res = dict(feasible_solved=okf)
-    for name, sign, bnd in (("ax_max", -1.0, b_max), ("ax_min", 1.0, b_min)):
-        spec = np.stack([v_b, zb, ay, ob, zb, sign * ob, zb], axis=1)
-        start = x0.copy()
-        start[:, ia] = np.clip(start[:, ia], bnd[0][:, ia] + 1e-6, bnd[1][:, ia] - 1e-6)
-        out = solve_batch(p_b, spec, start, device, bounds=bnd)
-        x, status, iters = out["x"].copy(), out["status"].copy(), out["iters"].copy()
-        # (5) second attempt from the predecessor's solution (the reference does it for the minimum, steady_state.hpp:801-809; the
-        # same continuation serves the maximum here), swept along the fans until nothing changes
-        for _ in range(B):
-            todo = np.array([b for b in np.where(status < 1)[0] if prev[b] >= 0 and status[prev[b]] >= 1], dtype=int)
-            if todo.size == 0:
-                break
-            st2 = x[prev[todo]].copy()
-            st2[:, iy] = ay[todo]
-            st2[:, ia] = np.clip(st2[:, ia], bnd[0][todo, ia] + 1e-6, bnd[1][todo, ia] - 1e-6)
-            o2 = solve_batch(p_b if np.ndim(p_b) == 1 else p_b[todo], spec[todo], st2, device, bounds=tuple(a[todo] for a in bnd))
-            good = o2["status"] >= 1
-            x[todo[good]] = o2["x"][good]; status[todo[good]] = o2["status"][good]; iters[todo[good]] += o2["iters"][good]
-            if not good.any():
-                break
-        res[name], res[name + "_solved"], res[name + "_iters"], res[name + "_x"] = x[:, ia].copy(), status >= 1, iters, x
+    # the maximum and the minimum of every point are independent NLPs from the same start: ONE batch of 2 B problems with one set of
+    # bounds per problem (first half: accelerating, second half: braking)
+    two = lambda a: np.concatenate([a, a])
+    bnd = tuple(np.concatenate([a, b]) for a, b in zip(b_max, b_min))
+    spec = np.concatenate([np.stack([v_b, zb, ay, ob, zb, sg * ob, zb], axis=1) for sg in (-1.0, 1.0)])
+    p2 = p_b if np.ndim(p_b) == 1 else two(p_b)
+    ay2, prev2 = two(ay), np.concatenate([prev, np.where(prev >= 0, prev + B, -1)])
+    start = two(x0)
+    start[:, ia] = np.clip(start[:, ia], bnd[0][:, ia] + 1e-6, bnd[1][:, ia] - 1e-6)
+    out = solve_batch(p2, spec, start, device, bounds=bnd, max_iter=FIRST_PASS_ITER)
+    x, status, iters = out["x"].copy(), out["status"].copy(), out["iters"].copy()
+    res["first_pass_iters"] = out["iters"].copy()
+    # (5) second attempt from the predecessor's solution (the reference does it for the minimum, steady_state.hpp:801-809; the
+    # same continuation serves the maximum here), swept along the fans until nothing changes
+    for _ in range(B):
+        todo = np.array([b for b in np.where(status < 1)[0] if prev2[b] >= 0 and status[prev2[b]] >= 1], dtype=int)
+        if todo.size == 0:
+            break
+        st2 = x[prev2[todo]].copy()
+        st2[:, iy] = ay2[todo]
+        st2[:, ia] = np.clip(st2[:, ia], bnd[0][todo, ia] + 1e-6, bnd[1][todo, ia] - 1e-6)
+        o2 = solve_batch(p2 if np.ndim(p2) == 1 else p2[todo], spec[todo], st2, device, bounds=tuple(a[todo] for a in bnd))
+        good = o2["status"] >= 1
+        x[todo[good]] = o2["x"][good]; status[todo[good]] = o2["status"][good]; iters[todo[good]] += o2["iters"][good]
+        if not good.any():
+            break
+    if FIRST_PASS_ITER < 300 and (status < 1).any():
+        # what neither the shortened first attempt nor the continuation solved gets the full iteration count from its own start
+        todo = np.where(status < 1)[0]
+        o2 = solve_batch(p2 if np.ndim(p2) == 1 else p2[todo], spec[todo], start[todo], device, bounds=tuple(a[todo] for a in bnd))
+        good = o2["status"] >= 1
+        x[todo[good]] = o2["x"][good]; status[todo[good]] = o2["status"][good]; iters[todo[good]] += o2["iters"][good]
+    for name, half in (("ax_max", slice(0, B)), ("ax_min", slice(B, 2 * B))):
+        res[name], res[name + "_solved"], res[name + "_iters"], res[name + "_x"] = x[half, ia].copy(), status[half] >= 1, iters[half], x[half]
     return res
 
 
