@@ -31,6 +31,7 @@ FIRST_PASS_ITER = int(os.environ.get("FL_GG_FIRST_ITER", 30))
 def _options(tol=1.0e-8, max_iter=300):
     o = default_options()
     o.tol, o.constr_viol_tol, o.acceptable_tol = tol, tol, 1.0e-6        # steady_state.hpp:84-88
+    o.refine_steps = int(os.environ.get("FL_GG_REFINE", 1))
     o.max_iter = max_iter     # an NLP of 8-13 variables that has not converged by then is retried by continuation instead
     return o
 
