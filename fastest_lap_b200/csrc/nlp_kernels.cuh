@@ -81,6 +81,12 @@ constexpr int FL_BLOCK = FL_VBLOCK_N;        // values pass: nodes per block (x 
 #ifndef FL_PDL
 #define FL_PDL 1
 #endif
+// FL_L1BYPASS: the derivative kernel's streaming traffic (checkpoints, variables, multipliers, track constants in; gradient, Jacobian and
+// Hessian slots out) goes past the L1 (ld.global.cg / st.global.cg), which is then left to the spill frames of the block's warps --
+// the loads the warps actually wait for (profiles/prof_r2q_*)
+#ifndef FL_L1BYPASS
+#define FL_L1BYPASS 0
+#endif
 constexpr int FL_DBLOCK = FL_DBLOCK_N;
 constexpr int FL_ABLOCK = FL_DBLOCK;
 
@@ -309,15 +315,22 @@ struct DerivIO
     double* gradn; double* ja_; double* jb_; double* h_; double* c_;
     size_t sA, sB, sH, sC;
     bool hasB, hasC;
-    __device__ __forceinline__ double x(int k) const { return xn[k]; }
-    __device__ __forceinline__ double t(int k) const { return __ldg(tcn + k * 32); }
+#if FL_L1BYPASS
+    static __device__ __forceinline__ double ld(const double* p) { return __ldcg(p); }
+    static __device__ __forceinline__ void st(double* p, double v) { __stcg(p, v); }
+#else
+    static __device__ __forceinline__ double ld(const double* p) { return *p; }
+    static __device__ __forceinline__ void st(double* p, double v) { *p = v; }
+#endif
+    __device__ __forceinline__ double x(int k) const { return ld(xn + k); }
+    __device__ __forceinline__ double t(int k) const { return FL_L1BYPASS ? ld(tcn + k * 32) : __ldg(tcn + k * 32); }
     __device__ __forceinline__ double d(int k) const { if constexpr (CD == FL_D_CONST) return Dk->d[k]; else return __ldg(Dp + k); }
-    __device__ __forceinline__ double c(int k) const { return Cn[k * 32]; }          // global workspace, or the warp's staged copy in shared memory
-    __device__ __forceinline__ double lin(int r) const { return lin_[r]; }
-    __device__ __forceinline__ double lout(int r) const { return lout_[r]; }
+    __device__ __forceinline__ double c(int k) const { return ld(Cn + k * 32); }          // global workspace, or the warp's staged copy in shared memory
+    __device__ __forceinline__ double lin(int r) const { return ld(lin_ + r); }
+    __device__ __forceinline__ double lout(int r) const { return ld(lout_ + r); }
     __device__ __forceinline__ double obj() const { return obj_; }
-    __device__ __forceinline__ double uprev(int c) const { return xp[G::ctrl_pos(c)]; }
-    __device__ __forceinline__ double unext(int c) const { return xq[G::ctrl_pos(c)]; }
+    __device__ __forceinline__ double uprev(int c) const { return ld(xp + G::ctrl_pos(c)); }
+    __device__ __forceinline__ double unext(int c) const { return ld(xq + G::ctrl_pos(c)); }
     // codegen FL_RING: per-node loads as 8-byte cp.async copies into a ring of shared-memory slots (one 256-byte row per slot and
     // warp), issued groups ahead of their use and read back with ld.shared: the L2 round trip of a checkpoint load overlaps the
     // arithmetic in between without a register per load in flight
@@ -336,11 +349,11 @@ struct DerivIO
     // codegen FL_SEGMENT > 0 separates code segments with fence(); measured on B200 (profiles/README.md) the fenced,
     // software-prefetched schedule is slower than ptxas' own (the spills are the reverse sweep's tape, not hoisted loads)
     __device__ __forceinline__ void fence(double) const {}
-    __device__ __forceinline__ void grad(int k, double v) const { gradn[k] = v; }
-    __device__ __forceinline__ void ja(int k, double v) const { ja_[k * sA] = v; }
-    __device__ __forceinline__ void jb(int k, double v) const { if (hasB) jb_[k * sB] = v; }
-    __device__ __forceinline__ void h(int k, double v) const { h_[k * sH] = v; }
-    __device__ __forceinline__ void cpl(int k, double v) const { if (hasC) c_[k * sC] = v; }
+    __device__ __forceinline__ void grad(int k, double v) const { st(gradn + k, v); }
+    __device__ __forceinline__ void ja(int k, double v) const { st(ja_ + k * sA, v); }
+    __device__ __forceinline__ void jb(int k, double v) const { if (hasB) st(jb_ + k * sB, v); }
+    __device__ __forceinline__ void h(int k, double v) const { st(h_ + k * sH, v); }
+    __device__ __forceinline__ void cpl(int k, double v) const { if (hasC) st(c_ + k * sC, v); }
 };
 
 #define FL_RING_WAIT(N) asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory")
