@@ -281,6 +281,7 @@ def generate(name, variant):
     L.append("    static constexpr int NVAL = %d, NTC = %d, NTRACK = %d, NRAW = %d, ND = %d, NCK = %d;" % (len(p.values), len(tnames), len(p.track_names), len(raw_names), pt.size, len(ck)))
     L.append("    static constexpr int NJA = %d, NJB = %d, NH = %d, NCPL = %d;" % (len(ja), len(jb), len(hs), len(p.coupling)))
     L.append("    static constexpr int IS_DERIVATIVE = %d, IS_3D = %d;" % (int(variant.form == "derivative"), int(variant.elevation)))
+    L.append("    static constexpr int IS_STEADY = %d;   // one-node problems (steady-state NLPs): the kernels map a thread to a PROBLEM of the batch" % int(variant.form == "steady"))
     n_aug = getattr(p, "n_aug", 0)
     L.append("    static constexpr int NAUG = %d, AUG_POS = %d, P_AUG = %d;   // augmented states (the last NAUG trapezoid rows); node variable a (q follows); first aug_* parameter" %
              (n_aug, p.aug_pos[0] if n_aug else -1, raw_names.index("aug_bb") if n_aug else -1))

@@ -671,6 +671,8 @@ int fl_eval_device_masked(fl_nlp* h, int what, double obj_factor, const int* d_a
     // the values pass also writes the checkpoints every derivative pass loads: it always runs (x may have been rewritten
     // on the device since the last call)
     const int dw = ((what & FL_EVAL_JAC) ? FL_DERIV_JAC : 0) | ((what & FL_EVAL_HESS) ? FL_DERIV_HESS : 0);
+    // one-node problems: the values launch writes g and f of its problems as well (nlp_kernels.cuh, k_node_values)
+    P.steady_assemble = (h->v->IS_STEADY && h->v->NP_VALUES == 1 && (what & FL_EVAL_FG) && !(what & FL_EVAL_NO_VALUES)) ? 1 : 0;
     if (!(what & FL_EVAL_NO_VALUES))
     {
         h->v->launch_values(P, h->D0.data(), h->shared_d, dw == FL_DERIV_ALL, h->stream);
@@ -678,7 +680,7 @@ int fl_eval_device_masked(fl_nlp* h, int what, double obj_factor, const int* d_a
     }
     // a full round (f, g, grad f, Jacobian, Hessian) assembles the rows inside the derivative launch
     const int fold = (what & FL_EVAL_FG) && dw == FL_DERIV_ALL && P.n_points > 32;          // (one-node problems: see derivs_cd)
-    if ((what & FL_EVAL_FG) && !fold)
+    if ((what & FL_EVAL_FG) && !fold && !P.steady_assemble)
     {
         h->v->launch_assemble(P, h->stream);
         h->launches += 1;

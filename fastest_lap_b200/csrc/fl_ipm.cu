@@ -629,8 +629,7 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
             s->launches += 1;
             { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, FL_EVAL_FG, 1.0, I.act_factor)) return 0; }
             s->n_eval_fg += 1;
-            if (!zero_counters(s)) return 0;
-            vec_launch(s, k_ipm_line_search, I);
+            vec_launch(s, k_ipm_line_search, I);          // (its counters were zeroed by k_ipm_mask_trials)
             s->launches += 1;
             if (!read_counters(s, cnt)) return 0;
         }

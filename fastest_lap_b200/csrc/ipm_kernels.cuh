@@ -801,10 +801,12 @@ __global__ void k_ipm_inertia_part(const fl_ipm_dev I, const fl_kkt_part Q, cons
     atomicAdd(I.counters + 1, 1);
 }
 
-// mask of the laps whose trial point is waiting to be evaluated
+// mask of the laps whose trial point is waiting to be evaluated; also zeroes the counters the line-search kernel that follows the
+// evaluation adds to (one launch less per trial round than a memset of its own)
 __global__ void k_ipm_mask_trials(const fl_ipm_dev I, int batch)
 {
     const int lap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lap < 8) I.counters[lap] = 0;
     if (lap >= batch) return;
     const fl_ipm_lap& L = I.lap[lap];
     I.act_factor[lap] = (L.status == IPM_RUNNING && (L.ls == LS_TRIAL || L.ls == LS_SOC_TRIAL)) ? 1 : 0;

@@ -56,6 +56,7 @@ struct fl_dev
     double* jac;                 // [batch][nnz_jac]
     double* hess;                // [batch][nnz_hess]
     const int* active;           // [batch] or null: laps with active == 0 are skipped (device-resident solvers)
+    int steady_assemble;         // one-node problems: the values pass also writes the rows g and the objective f of its problem
 };
 
 // offset of slot 0 of `node` inside a chunked [chunk][nslot][32] array
@@ -117,6 +118,8 @@ struct ValuesIO
     __device__ __forceinline__ void fence(double) const {}
 };
 
+template <class G> __device__ __forceinline__ double assemble_element(const fl_dev& P, const int e, const int prob);
+
 // TAPE: the values pass of a full round (Jacobian and Hessian): it also writes the shared part of the primal / adjoint
 // tape, which depends on the multipliers (codegen/generate.py shared_tape), for the derivative partitions to load.
 template <class G, int CD, bool TAPE>
@@ -125,10 +128,12 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant_
     // programmatic dependent launch: the derivative grid that follows may be scheduled while this one runs; it waits
     // (griddepcontrol.wait) for this grid's completion before it reads the values and checkpoints
     asm volatile("griddepcontrol.launch_dependents;");
-    const int node = blockIdx.x * FL_BLOCK + threadIdx.x;
+    // one-node problems (steady-state NLPs, G::IS_STEADY): a thread is a PROBLEM of the batch -- 32 problems per warp instead of one
+    // warp (and block) per problem with a single active lane
+    const int node = G::IS_STEADY ? 0 : blockIdx.x * FL_BLOCK + threadIdx.x;
     const int part = blockIdx.y;
-    const int prob = blockIdx.z;
-    if (node >= P.n_points) return;
+    const int prob = G::IS_STEADY ? blockIdx.x * FL_BLOCK + threadIdx.x : blockIdx.z;
+    if (G::IS_STEADY ? prob >= P.batch : node >= P.n_points) return;
     if (P.active && !P.active[prob]) return;
     ValuesIO<G, CD> io;
     io.xn = P.x + ((size_t)prob * P.n_points + node) * G::NV;
@@ -153,6 +158,12 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_values(const __grid_constant_
     }
     else
         G::values_part(part, io);
+    if constexpr (G::IS_STEADY != 0)
+    {
+        // a thread is a problem and its single element reads this node's values only: the rows and the objective in the same launch
+        // (a line-search trial of a G-G batch is then one launch, not two; the thread reads back what it has just written itself)
+        if (P.steady_assemble && part == 0) P.f[prob] = assemble_element<G>(P, 0, prob);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -189,14 +200,13 @@ __global__ void __launch_bounds__(FL_BLOCK) k_node_outputs(const __grid_constant
 // Element assembly.  V offsets: Q [0,NTD) QD [NTD,2NTD) ALG EXT DTDS CDOT.
 // Runs as its own kernel (eval_f / eval_g alone) or as one extra blockIdx.y slice of the derivative kernel (a full
 // callback round: one launch less, and the rows are written while the derivative partitions compute).
-template <class G, int BS>
-__device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, const int nbx, const int prob)
+// rows of element e of problem prob; returns the element's term of the objective
+template <class G>
+__device__ __forceinline__ double assemble_element(const fl_dev& P, const int e, const int prob)
 {
     constexpr int oQ = 0, oQD = G::NTD, oALG = 2 * G::NTD, oEXT = oALG + G::NALG, oDT = oEXT + G::NEXT, oCD = oDT + 1;
-    const int e = bx * BS + threadIdx.x;
     const int np = P.n_points;
     double fe = 0.0;
-    if (e < P.n_elements)
     {
         const int i = e;
         const int j = (e + 1 == np) ? 0 : e + 1;
@@ -253,6 +263,14 @@ __device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, co
             }
         }
     }
+    return fe;
+}
+
+template <class G, int BS>
+__device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, const int nbx, const int prob)
+{
+    const int e = bx * BS + threadIdx.x;
+    const double fe = e < P.n_elements ? assemble_element<G>(P, e, prob) : 0.0;
     if (P.n_elements == 1)
     {
         // one-element problems (steady-state NLPs): the element's term is the objective, no reduction
@@ -301,6 +319,14 @@ __device__ __forceinline__ void assemble_block(const fl_dev& P, const int bx, co
 template <class G>
 __global__ void __launch_bounds__(FL_ABLOCK) k_assemble(const __grid_constant__ fl_dev P)
 {
+    if constexpr (G::IS_STEADY != 0)
+    {
+        // one-element problems: a thread is a problem, its element's term is the objective (no reduction)
+        const int prob = blockIdx.x * FL_ABLOCK + threadIdx.x;
+        if (prob >= P.batch || (P.active && !P.active[prob])) return;
+        P.f[prob] = assemble_element<G>(P, 0, prob);
+        return;
+    }
     if (P.active && !P.active[blockIdx.y]) return;
     assemble_block<G, FL_ABLOCK>(P, blockIdx.x, gridDim.x, blockIdx.y);
 }
@@ -383,10 +409,12 @@ template <class G, int WHAT, bool ASSEMBLE, int CD>
 __global__ void __launch_bounds__(FL_DBLOCK, FL_DMINB) k_node_derivs(const __grid_constant__ fl_dev P, const __grid_constant__ DVec<G> Dk)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the values pass this launch may overlap with has completed
-    const int node = blockIdx.x * FL_DBLOCK + threadIdx.x;   // warps are aligned with the 32-node chunks of the workspace
+    // (one-node problems, G::IS_STEADY: a thread is a problem of the batch, blocks of FL_SBLOCK threads)
+    const int node = G::IS_STEADY ? 0 : blockIdx.x * FL_DBLOCK + threadIdx.x;   // warps are aligned with the 32-node chunks of the workspace
     const int vn = node - P.node0;                           // variable-node index
     const int part = blockIdx.y;
-    const int prob = blockIdx.z;
+    const int prob = G::IS_STEADY ? blockIdx.x * blockDim.x + threadIdx.x : blockIdx.z;
+    if (G::IS_STEADY && prob >= P.batch) return;
     if (P.active && !P.active[prob]) return;
     if (ASSEMBLE && part == deriv_parts<G, WHAT>::N)         // the slice that assembles g and f (block-uniform branch)
     {
@@ -478,6 +506,7 @@ struct fl_variant
 {
     const char* name;
     int NV, NCPE, NTD, NALG, NEXT, NCR, NFM, NVAL, NCK, NTC, NTRACK, NRAW, ND, NJA, NJB, NH, NCPL, IS_DERIVATIVE, IS_3D;
+    int IS_STEADY, NP_VALUES;
     int NAUG, AUG_POS, P_AUG;      // augmented state (codegen/nlpnode.py): count, node variable of `a`, first aug_* parameter slot
     int NOUT; const char* const* OUT_NAMES;                     // named output channels
     void (*launch_outputs)(const fl_dev&, const double* D0, int shared_d, double* O, cudaStream_t);
@@ -506,7 +535,8 @@ struct variant_ops
     {
         DVec<G> Dk;
         memcpy(Dk.d, D0, sizeof(Dk.d));
-        const dim3 grid((P.n_points + FL_BLOCK - 1) / FL_BLOCK, tape ? G::NP_TAPE : G::NP_VALUES, P.batch);
+        const dim3 grid(G::IS_STEADY ? (P.batch + FL_BLOCK - 1) / FL_BLOCK : (P.n_points + FL_BLOCK - 1) / FL_BLOCK, tape ? G::NP_TAPE : G::NP_VALUES,
+                        G::IS_STEADY ? 1 : P.batch);
         if constexpr (G::HAS_TAPE != 0)          // (the tape kernels exist only in builds generated with FL_SHARE > 0)
         {
             if (tape)
@@ -533,7 +563,11 @@ struct variant_ops
             else k_node_outputs<G, FL_D_LAP><<<grid, FL_BLOCK, 0, s>>>(P, Dk, O);
         }
     }
-    static void assemble(const fl_dev& P, cudaStream_t s) { k_assemble<G><<<dim3((P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK, P.batch, 1), FL_ABLOCK, 0, s>>>(P); }
+    static void assemble(const fl_dev& P, cudaStream_t s)
+    {
+        if constexpr (G::IS_STEADY != 0) k_assemble<G><<<dim3((P.batch + FL_ABLOCK - 1) / FL_ABLOCK, 1, 1), FL_ABLOCK, 0, s>>>(P);
+        else k_assemble<G><<<dim3((P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK, P.batch, 1), FL_ABLOCK, 0, s>>>(P);
+    }
     static int assemble_blocks(const fl_dev& P) { return (P.n_elements + FL_ABLOCK - 1) / FL_ABLOCK; }
     template <int CD>
     static void derivs_cd(const fl_dev& P, const DVec<G>& Dk, int what, int with_assemble, cudaStream_t s)
@@ -559,11 +593,21 @@ struct variant_ops
         // an SM on its own, and a batch of 2016 problems x 8 partitions then runs in 110 waves of blocks with ONE active thread each
         // (208 us per launch in the G-G sweep, profiles/r2_gg_launches.md); the assembly slice needs the full block and is launched on its own
         const bool tiny = !FL_STAGE && P.n_points <= 32 && !with_assemble;
-        cfg.blockDim = dim3(tiny ? 32 : FL_DBLOCK, 1, 1); cfg.dynamicSmemBytes = tiny ? fl_ring_bytes<G>(32) : sm; cfg.stream = s;
+        constexpr int FL_SBLOCK = 64;               // one-node problems: problems per block (a thread each)
+        cfg.blockDim = dim3(G::IS_STEADY ? FL_SBLOCK : (tiny ? 32 : FL_DBLOCK), 1, 1); cfg.dynamicSmemBytes = G::IS_STEADY ? fl_ring_bytes<G>(FL_SBLOCK) : (tiny ? fl_ring_bytes<G>(32) : sm); cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = (FL_PDL && P.batch <= 64) ? 1 : 0;          // measured: 44.4 -> 42.2 us per 8000-node round; no gain once the batch fills the GPU
+        if constexpr (G::IS_STEADY != 0)
+        {
+            const unsigned nbs = (P.batch + FL_SBLOCK - 1) / FL_SBLOCK;
+            if (with_assemble || P.n_points != 1) return;          // (fl_eval_device never folds the assembly into one-node launches)
+            if (what == FL_DERIV_JAC) { cfg.gridDim = dim3(nbs, G::NP_JAC, 1); cudaLaunchKernelEx(&cfg, k_node_derivs<G, FL_DERIV_JAC, false, CD>, P, Dk); }
+            else if (what == FL_DERIV_HESS) { cfg.gridDim = dim3(nbs, G::NP_HESS, 1); cudaLaunchKernelEx(&cfg, k_node_derivs<G, FL_DERIV_HESS, false, CD>, P, Dk); }
+            else { cfg.gridDim = dim3(nbs, G::NP_ALL, 1); cudaLaunchKernelEx(&cfg, k_node_derivs<G, FL_DERIV_ALL, false, CD>, P, Dk); }
+            return;
+        }
         if (what == FL_DERIV_JAC) { cfg.gridDim = dim3(nb, G::NP_JAC, P.batch); cudaLaunchKernelEx(&cfg, k_node_derivs<G, FL_DERIV_JAC, false, CD>, P, Dk); }
         else if (what == FL_DERIV_HESS) { cfg.gridDim = dim3(nb, G::NP_HESS, P.batch); cudaLaunchKernelEx(&cfg, k_node_derivs<G, FL_DERIV_HESS, false, CD>, P, Dk); }
         else if (!with_assemble) { cfg.gridDim = dim3(nb, G::NP_ALL, P.batch); cudaLaunchKernelEx(&cfg, k_node_derivs<G, FL_DERIV_ALL, false, CD>, P, Dk); }
@@ -585,7 +629,7 @@ struct variant_ops
         v.HAS_TAPE = G::HAS_TAPE;
         v.NVAL = G::NVAL; v.NCK = G::NCK; v.NTC = G::NTC; v.NTRACK = G::NTRACK; v.NRAW = G::NRAW; v.ND = G::ND;
         v.NJA = G::NJA; v.NJB = G::NJB; v.NH = G::NH; v.NCPL = G::NCPL; v.IS_DERIVATIVE = G::IS_DERIVATIVE; v.IS_3D = G::IS_3D;
-        v.NAUG = G::NAUG; v.AUG_POS = G::AUG_POS; v.P_AUG = G::P_AUG;
+        v.NAUG = G::NAUG; v.AUG_POS = G::AUG_POS; v.P_AUG = G::P_AUG; v.IS_STEADY = G::IS_STEADY; v.NP_VALUES = G::NP_VALUES;
         v.NOUT = G::NOUT; v.OUT_NAMES = G::OUT_NAMES; v.launch_outputs = &outputs;
         v.OPS_VALUES = G::OPS_VALUES; v.OPS_JAC = G::OPS_JAC; v.OPS_HESS = G::OPS_HESS; v.OPS_ALL = G::OPS_ALL;
         v.CTRL_POS = G::CTRL_POS; v.DCTRL_POS = G::DCTRL_POS;

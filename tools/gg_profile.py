@@ -7,12 +7,12 @@ speeds = np.linspace(50.0, 120.0, 32) / 3.6
 G.gg_diagram(params, speeds[:1], n_lat=8)
 log = []
 orig = G.solve_batch
-def timed(params, spec, x0, device=0, bounds=None):
+def timed(params, spec, x0, device=0, bounds=None, max_iter=300):
     from fastest_lap_b200.nlp import SteadyStateNLP
     from fastest_lap_b200.ipm import LapSolver
     t0 = time.perf_counter()
     nlp = SteadyStateNLP(G._model_of(params), params, spec, device=device)
-    solver = LapSolver(nlp, options=G._options(), bounds=bounds)
+    solver = LapSolver(nlp, options=G._options(max_iter=max_iter), bounds=bounds)
     t1 = time.perf_counter()
     out = solver.solve(x0)
     t2 = time.perf_counter()
