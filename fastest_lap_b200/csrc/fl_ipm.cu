@@ -56,6 +56,9 @@ struct fl_ipm
     int vec_block = IPM_BLOCK;                   // threads per lap of the vector kernels (IPM_BLOCK_MAX for small batches)
     size_t vec_smem = (size_t)IPM_NCPEMAX * IPM_BLOCK * sizeof(double);
     int vec_cluster = 1;                         // blocks per lap of the vector kernels (a thread-block cluster when > 1: long laps, few of them)
+    int* d_list[2] = { nullptr, nullptr };       // running laps of this round / of the round before (compact launches of the vector kernels)
+    int n_list = 0;                              // blocks of a compact launch (0: one block per lap of the batch)
+    int vec_block_created = IPM_BLOCK;           // the choice made for the whole batch; vec_block follows the number of laps still running
     int part_policy = 0;                         // 0 auto (few active laps), 1 always, -1 never
     int part_max_laps = 512;
     bool part_round = false;                     // the current factorisation is a partitioned one
@@ -125,7 +128,7 @@ template <class... KArgs, class... Args>
 static void vec_launch(fl_ipm* s, void (*kernel)(KArgs...), Args... args)
 {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(s->B * s->vec_cluster), 1, 1);
+    cfg.gridDim = dim3((unsigned)((s->I.lap_list ? s->n_list : s->B) * s->vec_cluster), 1, 1);
     cfg.blockDim = dim3((unsigned)s->vec_block, 1, 1);
     cfg.dynamicSmemBytes = s->vec_smem;
     cfg.stream = s->nlp->stream;
@@ -375,6 +378,8 @@ fl_ipm* fl_ipm_create_ex(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l
     s->d_neg = dalloc<int>(B, own); s->d_zero = dalloc<int>(B, own);
     I.n_neg = s->d_neg; I.n_zero = s->d_zero;
     I.lap = dalloc<fl_ipm_lap>(B, own);
+    s->d_list[0] = dalloc<int>(B, own); s->d_list[1] = dalloc<int>(B, own);
+    I.lap_list = nullptr; I.lap_list_out = nullptr;
     fl_kkt_dev& K = s->K;
     K.S = S; K.n_el = n_el; K.node0 = P.node0; K.closed = P.closed; K.nB = P.nB; K.nC = P.nC; K.n_points = P.n_points;
     K.NJA = v->NJA; K.NJB = v->NJB; K.NH = v->NH; K.NCPL = v->NCPL; K.NCPE = NCPE; K.NINEQ = NINEQ; K.n = n; K.m = m;
@@ -419,6 +424,7 @@ fl_ipm* fl_ipm_create_ex(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l
     else if (B <= 64) s->vec_block = IPM_BLOCK_MAX;
     else if (B <= 512) s->vec_block = 256;
     s->vec_smem = (size_t)IPM_NCPEMAX * s->vec_block * sizeof(double);
+    s->vec_block_created = s->vec_block;
     // long laps, few of them: a cluster of blocks per lap (each block strides over 1 / vec_cluster of the lap's vectors)
     if (const char* e = std::getenv("FL_IPM_CLUSTER")) s->vec_cluster = std::max(1, std::min(8, std::atoi(e)));
     else
@@ -467,6 +473,7 @@ int fl_kkt_factor_solve(fl_ipm* s, const double* x, const double* lambda, const 
     const fl_ipm_dev& I = s->I;
     const size_t B = s->B;
     cudaStream_t st = nlp->stream;
+    s->I.lap_list = nullptr; s->I.lap_list_out = nullptr; s->n_list = 0;          // one block per lap of the batch
     FLI_CUDA(cudaMemcpyAsync(nlp->d_xuser, x, B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
     FLI_CUDA(cudaMemcpyAsync(nlp->d_lambda, lambda, B * I.m * sizeof(double), cudaMemcpyHostToDevice, st));
     if (!fl_eval_device(nlp, FL_EVAL_FG | FL_EVAL_JAC | FL_EVAL_HESS, 1.0)) return 0;
@@ -534,6 +541,9 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
     // counters of THIS solve (fl_ipm_stats)
     s->launches = 0; s->n_factor_launches = 0; s->n_solve_launches = 0; s->n_eval_full = 0; s->n_eval_fg = 0; s->n_rounds = 0; s->n_part_factor = 0;
     s->ms_factor = s->ms_solve = s->ms_eval = 0.0;
+    s->vec_block = s->vec_block_created;
+    s->vec_smem = (size_t)IPM_NCPEMAX * s->vec_block * sizeof(double);
+    s->I.lap_list = nullptr; s->I.lap_list_out = nullptr; s->n_list = 0;
     cudaEventRecord(s->ev0, st);
     FLI_CUDA(cudaMemcpyAsync(nlp->d_xuser, x0, (size_t)B * I.n * sizeof(double), cudaMemcpyHostToDevice, st));
     if (y0)
@@ -574,10 +584,17 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
         { phase_timer pt(s, &s->ms_eval); if (!fl_eval_device_masked(nlp, ALL, 1.0, round == 0 ? nullptr : I.act_run)) return 0; }
         s->n_eval_full += 1;
         if (!zero_counters(s)) return 0;
+        // (k_ipm_state runs over the laps listed in the round before -- a superset of those still running -- and the list of this
+        // round is written into the other buffer)
         vec_launch(s, k_ipm_state, I);
+        s->I.lap_list_out = s->d_list[round & 1];
         k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B);
         s->launches += 2;
         if (!read_counters(s, cnt)) return 0;
+        // compact launches once at most a quarter of the batch is still running
+        static const bool no_compact = std::getenv("FL_IPM_NO_COMPACT") != nullptr;
+        if (!no_compact && B >= 64 && cnt[0] > 0 && cnt[0] <= B / 4) { s->I.lap_list = s->d_list[round & 1]; s->n_list = cnt[0]; }
+        else { s->I.lap_list = nullptr; s->n_list = 0; }
         if (verbose)
         {
             fl_ipm_lap l0;
@@ -589,6 +606,16 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
             std::fprintf(trace, "%ld,%d,%d,%.3f,%.3f,%.3f,%.3f\n", round, cnt[0], (int)(s->P > 0 && (s->part_policy > 0 || (s->part_policy == 0 && cnt[0] <= s->part_max_laps))),
                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), s->ms_factor, s->ms_solve, s->ms_eval);
         if (cnt[0] == 0) break;
+        // The vector kernels give one block to a lap.  Its width follows the laps still RUNNING: the stragglers of a large batch get the
+        // wide blocks a small batch is created with (a 128-thread block walks a 500-node lap's vectors in 0.23 ms per line-search trial,
+        // 0.7 - 1.2 ms per state / residual kernel, whatever the number of laps -- profiles/r2_solve1024_launches.md -- which is what a
+        // round costs once few laps are left)
+        if (I.S > 1 && !std::getenv("FL_IPM_FIXED_BLOCK"))
+        {
+            const int want = cnt[0] <= 64 ? IPM_BLOCK_MAX : (cnt[0] <= 512 ? 256 : IPM_BLOCK);
+            s->vec_block = std::max(s->vec_block_created, want);
+            s->vec_smem = (size_t)IPM_NCPEMAX * s->vec_block * sizeof(double);
+        }
         // factorisation.  Many active laps: one block per lap walks the whole chain, the inertia correction (Algorithm IC)
         // runs inside the kernel.  Few active laps: the chain is cut into segments factorised by their own blocks, and IC
         // runs between the attempts.

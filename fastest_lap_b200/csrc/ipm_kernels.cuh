@@ -55,6 +55,10 @@ struct fl_ipm_dev
     int* counters;                                 // [8]: 0 running laps, 1 pending factorisations, 2 laps in line search, 3 pending SOC solves
     const int* n_neg; const int* n_zero;
     fl_ipm_lap* lap;
+    // compact launches: when few laps of a large batch are still running the vector kernels get one block per RUNNING lap, block b
+    // serving lap lap_list[b] (written by k_ipm_count_running; null: block b serves lap b)
+    const int* lap_list;
+    int* lap_list_out;
 };
 
 // ---- the lap's thread group: one block, or the blocks of one cluster ---------------------------------------------------
@@ -220,7 +224,8 @@ __device__ void ipm_H_mul_add(const fl_ipm_dev& I, const double* hes, const doub
 }
 
 #define IPM_LAP_PROLOGUE \
-    const int lap = blockIdx.x / ipm_nranks(); \
+    const int slot_ = blockIdx.x / ipm_nranks(); \
+    const int lap = I.lap_list ? I.lap_list[slot_] : slot_; \
     const int t0 = ipm_rank() * blockDim.x + threadIdx.x, tstride = ipm_nranks() * blockDim.x;   /* this thread's share of the lap's vectors */ \
     fl_ipm_lap& L = I.lap[lap]; \
     const size_t on = (size_t)lap * I.n, om = (size_t)lap * I.m, oi = (size_t)lap * I.ni; \
@@ -812,8 +817,15 @@ __global__ void k_ipm_mask_trials(const fl_ipm_dev I, int batch)
     I.act_factor[lap] = (L.status == IPM_RUNNING && (L.ls == LS_TRIAL || L.ls == LS_SOC_TRIAL)) ? 1 : 0;
 }
 
+// counts the running laps and lists them (in no particular order: every lap's computation is its own)
 __global__ void k_ipm_count_running(const fl_ipm_dev I, int batch)
 {
     const int lap = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lap < batch && I.lap[lap].status == IPM_RUNNING) atomicAdd(I.counters + 0, 1);
+    if (lap >= batch) return;
+    if (I.lap[lap].status == IPM_RUNNING)
+    {
+        const int k = atomicAdd(I.counters + 0, 1);
+        if (I.lap_list_out) I.lap_list_out[k] = lap;
+    }
+    else { I.act_refine[lap] = 0; I.act_soc[lap] = 0; }      // (compact launches have no block for a finished lap that could clear its masks)
 }
