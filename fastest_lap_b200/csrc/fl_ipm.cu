@@ -75,13 +75,15 @@ namespace {
 // or one block of four warps per lap (kkt_kernels.cuh), which also serves the reduced system of the partitioned mode.
 template <int NV, int NEQ> void launch_factor(fl_ipm* s, const fl_kkt_dev& K)
 {
-    if (s->warp_kkt && !K.sep) k_kkt_factor_w<NV, NEQ><<<s->B, 32, sizeof(kw_smem<NV, NEQ>), s->nlp->stream>>>(K);
-    else k_kkt_factor<NV, NEQ><<<s->B, KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K);
+    const int nb = K.lap_list ? s->n_list : s->B;          // blocks: one per lap of the batch, or one per running lap (compact launch)
+    if (s->warp_kkt && !K.sep) k_kkt_factor_w<NV, NEQ><<<nb, 32, sizeof(kw_smem<NV, NEQ>), s->nlp->stream>>>(K);
+    else k_kkt_factor<NV, NEQ><<<nb, KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K);
 }
 template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, const double* r1, const double* r2, double* dx, double* dy)
 {
-    if (s->warp_kkt && !K.sep) k_kkt_solve_w<NV, NEQ><<<s->B, 32, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
-    else k_kkt_solve<NV, NEQ><<<s->B, KT, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
+    const int nb = K.lap_list ? s->n_list : s->B;
+    if (s->warp_kkt && !K.sep) k_kkt_solve_w<NV, NEQ><<<nb, 32, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
+    else k_kkt_solve<NV, NEQ><<<nb, KT, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
 }
 
 #define FLI_DISPATCH(fn, ...) \
@@ -98,15 +100,15 @@ template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, con
 
 template <int NV, int NEQ> void launch_factor_seg(fl_ipm* s, const fl_kkt_dev& K)
 {
-    k_kkt_factor_seg<NV, NEQ><<<dim3(s->P, s->B), KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K, s->Q);
+    k_kkt_factor_seg<NV, NEQ><<<dim3(s->P, K.lap_list ? s->n_list : s->B), KT, sizeof(kkt_smem<NV, NEQ>), s->nlp->stream>>>(K, s->Q);
 }
 template <int NV, int NEQ> void launch_solve_seg_fwd(fl_ipm* s, const fl_kkt_dev& K, const double* r1, const double* r2)
 {
-    k_kkt_solve_seg_fwd<NV, NEQ><<<dim3(s->P, s->B), KT, 0, s->nlp->stream>>>(K, s->Q, r1, r2);
+    k_kkt_solve_seg_fwd<NV, NEQ><<<dim3(s->P, K.lap_list ? s->n_list : s->B), KT, 0, s->nlp->stream>>>(K, s->Q, r1, r2);
 }
 template <int NV, int NEQ> void launch_solve_seg_bwd(fl_ipm* s, const fl_kkt_dev& K, const double* r2, double* dx, double* dy)
 {
-    k_kkt_solve_seg_bwd<NV, NEQ><<<dim3(s->P, s->B), KT, 0, s->nlp->stream>>>(K, s->Q, s->rywork, r2, dx, dy);
+    k_kkt_solve_seg_bwd<NV, NEQ><<<dim3(s->P, K.lap_list ? s->n_list : s->B), KT, 0, s->nlp->stream>>>(K, s->Q, s->rywork, r2, dx, dy);
 }
 
 // the warp-per-lap factorisation keeps ~20 KB of shared memory per lap: ask for the largest shared-memory carve-out, so that
@@ -155,7 +157,7 @@ int kkt_factor(fl_ipm* s, const int* active, int ls_mode, bool with_ic)
 {
     phase_timer pt(s, &s->ms_factor);
     fl_kkt_dev K = s->K;
-    K.active = active; K.ls_mode = ls_mode; K.laps = with_ic ? s->I.lap : nullptr; K.o = s->I.o;
+    K.active = active; K.ls_mode = ls_mode; K.laps = with_ic ? s->I.lap : nullptr; K.o = s->I.o; K.lap_list = s->I.lap_list;
     FLI_DISPATCH(launch_factor, K);
     s->launches += 1; s->n_factor_launches += 1;
     FLI_CUDA(cudaGetLastError());
@@ -176,7 +178,7 @@ int kkt_factor_part(fl_ipm* s, const int* active, int ls_mode)
 {
     phase_timer pt(s, &s->ms_factor);
     fl_kkt_dev K = s->K;
-    K.active = active; K.ls_mode = ls_mode; K.laps = nullptr; K.o = s->I.o;
+    K.active = active; K.ls_mode = ls_mode; K.laps = nullptr; K.o = s->I.o; K.lap_list = s->I.lap_list;
     FLI_DISPATCH(launch_factor_seg, K);
     const fl_kkt_dev R = reduced_system(s, K);
     FLI_DISPATCH(launch_factor, R);
@@ -189,7 +191,7 @@ int kkt_solve(fl_ipm* s, const int* active, int ls_mode, const double* r1, const
 {
     phase_timer pt(s, &s->ms_solve);
     fl_kkt_dev K = s->K;
-    K.active = active; K.ls_mode = ls_mode; K.laps = nullptr;
+    K.active = active; K.ls_mode = ls_mode; K.laps = nullptr; K.lap_list = s->I.lap_list;
     if (s->part_round)
     {
         FLI_DISPATCH(launch_solve_seg_fwd, K, r1, r2);

@@ -54,6 +54,7 @@ struct fl_kkt_dev
     const double* dw;         // [batch]
     const double* dc;         // [batch]
     const int* active;        // [batch] or null: laps with active == 0 are skipped
+    const int* lap_list;      // null, or a compact launch: block b serves lap lap_list[b] (the laps still running, fl_ipm.cu)
     double* Dinv;             // [batch][S][NB*NB]  inverse pivot blocks (column-major, ld NB)
     double* F;                // [batch][S][NB*NB]  closed laps: fill blocks K[0, j] (rows: stage 0, columns: stage j)
     double* Aq;               // [batch][S][NINEQ*(NV+1)]  inequality rows of the stage's element w.r.t. its right node, and 1/D
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(KT, FL_KMINB) k_kkt_factor(const fl_kkt_dev K)
     constexpr int NB = St::NB, CB = St::CB, CV = St::CV;
     extern __shared__ __align__(16) unsigned char kkt_raw[];
     kkt_smem<NV, NEQ>& sm = *reinterpret_cast<kkt_smem<NV, NEQ>*>(kkt_raw);
-    const int lap = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int lap = K.lap_list ? K.lap_list[blockIdx.x] : blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
     fl_ipm_lap* Lp = K.laps ? K.laps + lap : nullptr;
     if (Lp && Lp->status != IPM_RUNNING) return;
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(KT) k_kkt_solve(const fl_kkt_dev K, const doub
     using St = kkt_stage<NV, NEQ>;
     constexpr int NB = St::NB, CB = St::CB, CV = St::CV;
     __shared__ double vb[KLD], vy[KLD], z0[KLD], part[3][KW][KLD];
-    const int lap = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int lap = K.lap_list ? K.lap_list[blockIdx.x] : blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
     if (K.laps && K.laps[lap].status != IPM_RUNNING) return;
     const int S = K.sep ? K.P : K.S;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(KT) k_kkt_factor_seg(const fl_kkt_dev K, const
     constexpr int NB = St::NB, CB = St::CB, CV = St::CV;
     extern __shared__ __align__(16) unsigned char kkt_raw[];
     kkt_smem<NV, NEQ>& sm = *reinterpret_cast<kkt_smem<NV, NEQ>*>(kkt_raw);
-    const int k = blockIdx.x, lap = blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int k = blockIdx.x, lap = K.lap_list ? K.lap_list[blockIdx.y] : blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
     int a, hi, bstage, kb;
     bool has_b;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(KT) k_kkt_solve_seg_fwd(const fl_kkt_dev K, co
     using St = kkt_stage<NV, NEQ>;
     constexpr int NB = St::NB, CB = St::CB;
     __shared__ double vb[KLD], vy[KLD], part[3][KW][KLD];
-    const int k = blockIdx.x, lap = blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int k = blockIdx.x, lap = K.lap_list ? K.lap_list[blockIdx.y] : blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
     int a, hi, bstage, kb;
     bool has_b;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(KT) k_kkt_solve_seg_bwd(const fl_kkt_dev K, co
     using St = kkt_stage<NV, NEQ>;
     constexpr int NB = St::NB, CB = St::CB;
     __shared__ double vb[KLD], vy[KLD], zb[KLD], part[2][KW][KLD];
-    const int k = blockIdx.x, lap = blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int k = blockIdx.x, lap = K.lap_list ? K.lap_list[blockIdx.y] : blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (K.active && !K.active[lap]) return;
     int a, hi, bstage, kb;
     bool has_b;

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
     double* const XL = sm.W + Sm::OXL;
     double* const Lc = sm.W + Sm::OLC;
     double* const Ft = sm.W + Sm::OFT;
-    const int lap = blockIdx.x, lane = threadIdx.x;
+    const int lap = K.lap_list ? K.lap_list[blockIdx.x] : blockIdx.x, lane = threadIdx.x;
     if (K.active && !K.active[lap]) return;
     fl_ipm_lap* Lp = K.laps ? K.laps + lap : nullptr;
     if (Lp && Lp->status != IPM_RUNNING) return;
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(32, FL_KWS_MINB) k_kkt_solve_w(const fl_kkt_de
     constexpr int NB = St::NB, LDV = St::LDV, FT = St::FT, NVP = St::NVP;
     constexpr int NBP = (NB + 1) / 2;
     __shared__ __align__(16) double vb[32], vy[32], z0[32], z0c[16];
-    const int lap = blockIdx.x, lane = threadIdx.x;
+    const int lap = K.lap_list ? K.lap_list[blockIdx.x] : blockIdx.x, lane = threadIdx.x;
     if (K.active && !K.active[lap]) return;
     if (K.laps && K.laps[lap].status != IPM_RUNNING) return;
     const int S = K.S;
