@@ -419,6 +419,10 @@ fl_ipm* fl_ipm_create_ex(fl_nlp* nlp, const fl_ipm_opts* opts, const double* x_l
         s->d_redneg = dalloc<int>(B, own); s->d_redzero = dalloc<int>(B, own);
         if (!K.F) K.F = dalloc<double>((size_t)B * S * NB2, own);          // open laps: the segments' fill blocks
         if (!s->rywork || !s->rDinv || !K.F) { fl_set_error("out of device memory for the partitioned factorisation"); fl_ipm_destroy(s); return nullptr; }
+        // automatic schedule: parallel in the stages while at most this many laps are running.  Measured on the 4096-lap sweep of 500-node
+        // laps (first pass, s): 512 laps 12.99, 1024 12.71, 1536 12.58, 2048 12.81, 2560 13.10 -- the warp-per-lap schedule needs its second
+        // wave from 1629 laps on and pays the slowest lap's inertia-correction attempts below that; scaled with the stages of a lap
+        s->part_max_laps = std::max(256, std::min(2048, 768000 / std::max(1, S)));
         if (const char* e = std::getenv("FL_IPM_PART_MAX")) s->part_max_laps = std::atoi(e);
     }
     // vector kernels: one block per lap; wide blocks when the batch alone cannot fill the machine
