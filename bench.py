@@ -283,6 +283,9 @@ def gg_leg(args, torch, dist, world, rank, local):
     # untimed warm-up: the same sweep once.  The timed sweep then finds the steady-state kernels loaded and the device blocks of its
     # dozen handles in the library's cache (cudaMalloc / cudaFree of a first sweep varied from 30 ms to 1.2 s on fresh boxes against
     # 0.11 s of solves, profiles/README.md)
+    # (the library's cache of freed device blocks is full of the lap sweeps' blocks at this point and would refuse the sweep's own)
+    from fastest_lap_b200.nlp import load_library
+    load_library().fl_release_cached_memory()
     gg.gg_diagram(params, speeds[lo:hi], n_lat=args.gg_lat, device=local)
     if dist is not None:
         dist.barrier()

@@ -176,16 +176,14 @@ void fl_dev_free(void* p)
     if (it == c.live.end()) { cudaFree(p); return; }
     const auto key = it->second;
     c.live.erase(it);
-    if (key.second > c.limit / 4)
+    // (a full cache refuses further blocks: a caller that moves on to a different workload -- bench.py between its legs -- empties
+    // it with fl_release_cached_memory, otherwise every handle of the new workload goes through cudaMalloc / cudaFree again)
+    if (key.second > c.limit / 4 || c.cached + key.second > c.limit)
     {
         int cur = 0; cudaGetDevice(&cur);
         cudaSetDevice(key.first); cudaFree(p); cudaSetDevice(cur);
         return;
     }
-    // a full cache is emptied rather than closed: the blocks it holds belong to an earlier workload (a 4096-lap sweep leaves 8 GB
-    // behind), and a cache that refused every block of the current one would send each of its handles through cudaMalloc / cudaFree
-    // again (the G-G sweep after the lap sweeps of bench.py: 0.07 s -> 0.31 s)
-    if (c.cached + key.second > c.limit) c.release_all();
     c.free_blocks.insert({ key, p }); c.cached += key.second;
 }
 
