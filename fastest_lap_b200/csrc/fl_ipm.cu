@@ -598,7 +598,7 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
         s->launches += 2;
         if (!read_counters(s, cnt)) return 0;
         // compact launches once at most a quarter of the batch is still running
-        static const bool no_compact = std::getenv("FL_IPM_NO_COMPACT") != nullptr;
+        const bool no_compact = std::getenv("FL_IPM_NO_COMPACT") != nullptr;          // (comparison runs: tests/test_gpu_ipm.py)
         if (!no_compact && B >= 64 && cnt[0] > 0 && cnt[0] <= B / 4) { s->I.lap_list = s->d_list[round & 1]; s->n_list = cnt[0]; }
         else { s->I.lap_list = nullptr; s->n_list = 0; }
         if (verbose)

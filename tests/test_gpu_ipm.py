@@ -440,6 +440,38 @@ def test_cluster_vector_kernels_give_the_same_iterates(monkeypatch):
     assert abs(res["1"][1] - res["2"][1]) <= 10 and abs(res["1"][1] - res["4"][1]) <= 10, res
 
 
+def test_compact_launches_give_the_same_laps(monkeypatch):
+    """Once at most a quarter of a batch is still running the kernels of the iteration are launched over the list of running laps,
+    with wider blocks for the vector kernels (fl_ipm.cu).  A batch of 96 F1 oval laps with different vehicles -- the laps finish between
+    iteration 30 and 60, so most of the solve runs compact -- gives the same laps with and without (FL_IPM_NO_COMPACT,
+    FL_IPM_FIXED_BLOCK): same statuses, objectives to rounding (the block width changes the grouping of the reductions)."""
+    from fastest_lap_b200 import workloads
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver
+    from fastest_lap_b200.vehicle import MODEL_F1
+    p, ex = load_golden("f1_ovaltrack_closed")
+    params = workloads.sweep_parameters(MODEL_F1, 96)
+    keep = [k for k in range(p.params.size) if k not in (0, 6, 7, 30)]
+    params[:, keep] = p.params[keep]          # the golden's vehicle with mass, cd, cl and power drawn per lap
+    params[0] = p.params
+    res = {}
+    for mode in ("compact", "plain"):
+        if mode == "plain":
+            monkeypatch.setenv("FL_IPM_NO_COMPACT", "1"); monkeypatch.setenv("FL_IPM_FIXED_BLOCK", "1")
+        nlp = CollocationNLP(p, vehicle_params=params)
+        solver = LapSolver(nlp)
+        out = solver.solve(ex["x"] * 1.0)
+        res[mode] = (out["status"].copy(), out["iters"].copy(), out["obj"].copy())
+        solver.close(); nlp.close()
+    # (started from the golden vehicle's lap, a lap or two of the 96 end in a failed line search -- in both modes)
+    assert (res["compact"][0] == res["plain"][0]).all(), (res["compact"][0], res["plain"][0])
+    ok = res["plain"][0] >= 1
+    assert ok.sum() >= 90 and ok[0]
+    assert res["compact"][1][ok].max() > res["compact"][1][ok].min()              # the laps do finish at different iterations
+    assert np.max(np.abs(res["compact"][2][ok] - res["plain"][2][ok]) / res["plain"][2][ok]) <= 1e-8
+    assert np.max(np.abs(res["compact"][1][ok] - res["plain"][1][ok])) <= 10
+
+
 @pytest.mark.parametrize("case,laps", [("f1_ovaltrack_closed", 5), ("f1_catalunya_chicane", 3), ("kart_ovaltrack_derivative", 3)])
 def test_warp_per_lap_factorisation_inside_the_iteration(case, laps):
     """The two mappings of the unpartitioned factorisation (one block of four warps per lap; one warp per lap with the stage
