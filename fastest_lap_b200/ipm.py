@@ -281,32 +281,29 @@ def sweep_bounds(problem, params):
     lap's OWN vehicle (limebeer2014f1.h:232-262): when those differ between the laps of the batch the solver gets one set of bounds
     per lap; when they do not (the usual case: lambda_max(0) dominates and does not depend on the mass), None = one set for the batch."""
     from .nlp import problem_bounds
-    from .problem import LapProblem
-    s2 = problem.s[:2]
-    def one_element(row):
-        # a two-node open section of the same problem: its single element's rows carry the parameter-dependent bounds
-        q = LapProblem(problem.model, problem.form, False, s2, problem.track_length, problem.track_nodes[:2], problem.wl[:2], problem.wr[:2], row,
-                       problem.dissipation, problem.sigma, problem.elevation, np.zeros(len(problem.q0)), np.zeros(len(problem.u0)), np.zeros(2),
-                       None, problem.kart_direct_torque)
-        _, _, gl, gu = problem_bounds(q)
-        return np.concatenate([gl, gu])
-    rows, inverse = np.unique(params, axis=0, return_inverse=True)          # (4096 distinct vehicles: 0.2 s)
-    inverse = np.asarray(inverse).ravel()
-    per_row = np.stack([one_element(r) for r in rows])
     ncpe = problem.ncpe
-    track_rows = np.zeros(2 * ncpe, dtype=bool)
-    if problem.model == 0:
-        n_eq = ncpe - 6 - (0 if problem.form == 0 else 2)
-        track_rows[[n_eq + 4, n_eq + 5, ncpe + n_eq + 4, ncpe + n_eq + 5]] = True        # track limits: per node, not per vehicle
-    if np.all(np.abs(per_row[:, ~track_rows] - per_row[0, ~track_rows]) <= 1e-15):
+    if problem.model != 0:
+        return None                                   # lot2016kart.h:194-198: the kart's slip rows are bounded by constants
+    # the F1's four slip rows (csrc/fl_capi.cu fl_problem_bounds, limebeer2014f1.h:232-262): the parameters they read are the mass and,
+    # per axle, the two reference loads and the two maximum slip angles of the tyre
+    params = np.asarray(params, dtype=np.float64)
+    deg, g0 = np.pi / 180.0, 9.81
+    m = params[:, 0]
+    eu = np.empty((params.shape[0], 4))
+    for t in range(4):
+        o = 32 if t < 2 else 45
+        l1, l2, fz1, fz2 = params[:, o + 9] * deg, params[:, o + 10] * deg, params[:, o + 1], params[:, o + 2]
+        a = (0.0 - fz1) * (l2 - l1) / (fz2 - fz1) + l1
+        b = (m * g0 - fz1) * (l2 - l1) / (fz2 - fz1) + l1
+        eu[:, t] = np.maximum(a, b)
+    if np.all(np.abs(eu - eu[0]) <= 1e-15):
         return None
+    n_eq = ncpe - 6 - (0 if problem.form == 0 else 2)
     xl, xu, gl, gu = problem_bounds(problem)
     B = params.shape[0]
     GL, GU = np.tile(gl, (B, 1)).reshape(B, problem.n_elements, ncpe), np.tile(gu, (B, 1)).reshape(B, problem.n_elements, ncpe)
-    for b in range(B):
-        r = per_row[inverse[b]]
-        for k in np.where(~track_rows[:ncpe])[0]:
-            GL[b, :, k], GU[b, :, k] = r[k], r[ncpe + k]
+    for t in range(4):
+        GL[:, :, n_eq + t], GU[:, :, n_eq + t] = -eu[:, t, None], eu[:, t, None]
     return np.tile(xl, (B, 1)), np.tile(xu, (B, 1)), GL.reshape(B, -1), GU.reshape(B, -1)
 
 
