@@ -594,12 +594,14 @@ static int ipm_solve_impl(fl_ipm* s, const double* x0, const double* y0, const d
         // round is written into the other buffer)
         vec_launch(s, k_ipm_state, I);
         s->I.lap_list_out = s->d_list[round & 1];
-        k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B);
+        const bool no_compact = std::getenv("FL_IPM_NO_COMPACT") != nullptr;          // (comparison runs: tests/test_gpu_ipm.py)
+        const bool listed = !no_compact && B >= 64 && I.S > 1;
+        if (listed) { k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B, 0); k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B, 1); s->launches += 1; }
+        else k_ipm_count_running<<<blocks_b, 128, 0, st>>>(I, B, -1);
         s->launches += 2;
         if (!read_counters(s, cnt)) return 0;
-        // compact launches once at most a quarter of the batch is still running
-        const bool no_compact = std::getenv("FL_IPM_NO_COMPACT") != nullptr;          // (comparison runs: tests/test_gpu_ipm.py)
-        if (!no_compact && B >= 64 && cnt[0] > 0 && cnt[0] <= B / 4) { s->I.lap_list = s->d_list[round & 1]; s->n_list = cnt[0]; }
+        // batches of laps: every kernel of the round is launched over the list of running laps, the costly ones first
+        if (listed && cnt[0] > 0) { s->I.lap_list = s->d_list[round & 1]; s->n_list = cnt[0]; }
         else { s->I.lap_list = nullptr; s->n_list = 0; }
         if (verbose)
         {

@@ -817,15 +817,23 @@ __global__ void k_ipm_mask_trials(const fl_ipm_dev I, int batch)
     I.act_factor[lap] = (L.status == IPM_RUNNING && (L.ls == LS_TRIAL || L.ls == LS_SOC_TRIAL)) ? 1 : 0;
 }
 
-// counts the running laps and lists them (in no particular order: every lap's computation is its own)
-__global__ void k_ipm_count_running(const fl_ipm_dev I, int batch)
+// Counts the running laps and lists them.  Two launches fill the list: pass 0 appends the laps whose last factorisation needed a
+// regularisation (their first attempt at dw = 0 fails again more often than not: they stay longest in the inertia-correcting
+// factorisation kernel), pass 1 the others -- blocks are dispatched in index order, so the long laps start first and the kernel does not
+// end on them (longest processing time first).  Within a pass the order is whatever the atomics give: every lap's computation is its own.
+__global__ void k_ipm_count_running(const fl_ipm_dev I, int batch, int pass)
 {
     const int lap = blockIdx.x * blockDim.x + threadIdx.x;
     if (lap >= batch) return;
-    if (I.lap[lap].status == IPM_RUNNING)
+    const fl_ipm_lap& L = I.lap[lap];
+    if (L.status == IPM_RUNNING)
     {
-        const int k = atomicAdd(I.counters + 0, 1);
-        if (I.lap_list_out) I.lap_list_out[k] = lap;
+        const bool costly = L.dw_prev > 0.0;
+        if (pass < 0 || costly == (pass == 0))
+        {
+            const int k = atomicAdd(I.counters + 0, 1);
+            if (I.lap_list_out) I.lap_list_out[k] = lap;
+        }
     }
-    else { I.act_refine[lap] = 0; I.act_soc[lap] = 0; }      // (compact launches have no block for a finished lap that could clear its masks)
+    else if (pass <= 0) { I.act_refine[lap] = 0; I.act_soc[lap] = 0; }      // (compact launches have no block for a finished lap that could clear its masks)
 }
