@@ -421,10 +421,9 @@ def optimal_laptime(vehicle, track, s, options=""):
                 XU[:, col] = hi
     declared = list(getattr(veh, "declared", []))
     if o["sensitivity"]:
-        # (the reference runs its sensitivity analysis on closed or open direct-form problems; here: closed laps without lap-coupling
-        # quantities, parameters declared as constants)
-        if not closed or p.aug or veh.has_variable_parameters():
-            raise FastestLapError("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for closed laps with constant parameters, "
+        # (closed laps and open sections; not together with lap-coupling quantities or parameters that vary along the lap)
+        if p.aug or veh.has_variable_parameters():
+            raise FastestLapError("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for constant parameters, "
                                   "without hypermesh controls or integral constraints")
     nlp = CollocationNLP(p)
     solver = LapSolver(nlp, bounds=bounds)
@@ -518,13 +517,16 @@ def optimal_laptime(vehicle, track, s, options=""):
             for sign in (1.0, -1.0):
                 v2 = veh.copy()
                 v2.params[col] += sign * step
-                pm.append(LapProblem.from_vehicle_track(v2, trk, s, form=form, closed=closed, dissipation=o["dissipation"], sigma=o["sigma"]))
+                pm.append(LapProblem.from_vehicle_track(v2, trk, s, form=form, closed=closed, dissipation=o["dissipation"], sigma=o["sigma"],
+                                                        q0=o["q_start"], u0=o["u_start"]))
             perturbed.append((pm[0], pm[1], 2.0 * step))
         dxs, _ = lap_sensitivities(p, out["x"][0], out["y"][0], sigma, perturbed)
-        h_el = np.diff(np.append(s, trk.track_length))
+        h_el = np.diff(np.append(s, trk.track_length)) if closed else np.append(np.diff(s), 0.0)
         for (alias, _), dx in zip(declared, dxs):
             dT, d = dlaptime_dp(p, out["x"][0], dx)
             DX = dx.reshape(-1, p.nv)
+            if not closed:
+                DX = np.vstack([np.zeros(p.nv), DX])          # the given first node does not move (optimal_laptime.hpp:651-659)
             put("derivatives/laptime/" + alias, dT)
             k = 0
             for nm in inputs:

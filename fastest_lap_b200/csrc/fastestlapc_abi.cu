@@ -571,8 +571,8 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     if (o.save_warm_start && (!o.closed || o.aug_kind != FL_AUG_NONE))
         throw error("[ERROR] optimal_laptime -> <save_warm_start> of open simulations / with hypermesh controls or integral constraints is not supported");
     if (!o.closed && o.aug_kind != FL_AUG_NONE) throw error("[ERROR] optimal_laptime -> hypermesh controls and integral constraints need a closed simulation");
-    if (o.sensitivity && (!o.closed || o.aug_kind != FL_AUG_NONE || !veh.variable.empty()))
-        throw error("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for closed laps with constant parameters, without hypermesh controls or integral constraints");
+    if (o.sensitivity && (o.aug_kind != FL_AUG_NONE || !veh.variable.empty()))
+        throw error("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for constant parameters, without hypermesh controls or integral constraints");
     const vec s = o.warm_start ? ws.s : s_in;
     const int np = (int)s.size();
     if (np < 2) throw error("[ERROR] optimal_laptime -> provide at least two values of arclength");
@@ -826,7 +826,8 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     for (size_t q = 0; q < dx_dp.size(); ++q)
     {
         const string& alias = veh.declared[q].first;
-        const vec& dx = dx_dp[q];
+        vec dx = dx_dp[q];
+        if (!o.closed) dx.insert(dx.begin(), (size_t)NVo, 0.0);          // the given first node does not move (optimal_laptime.hpp:651-659)
         vec d2(np), dtime(np, 0.0);
         for (int i = 0; i < np; ++i)
         {
@@ -838,7 +839,7 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
             d2[i] = -kz * dxi[n_col] / un - ca * r / (un * un) * dxi[iu] + sa * r / (un * un) * dxi[iv] + r * (x[iv] * ca + x[iu] * sa) / (un * un) * dxi[a_col];
         }
         double dlap = 0.0;
-        for (int i = 0; i < np; ++i)
+        for (int i = 0; i < (o.closed ? np : np - 1); ++i)
         {
             const int j = (i + 1) % np;
             const double h = (i + 1 < np) ? s[i + 1] - s[i] : trk.length - s[np - 1];

@@ -220,22 +220,26 @@ def lap_sensitivities(problem, x, lam, sigma, perturbed, device=0):
 def dlaptime_dp(problem, x, dx):
     """Derivative of the lap time from dx/dp, as the reference integrates it (optimal_laptime.hpp:664-724): the trapezoid rule over
     d/dp of dt/ds = (1 - kz n) / (u cos(alpha) - v sin(alpha)), which depends on the parameters through the states only.
-    Closed laps, flat or 3-D tracks (kz = the z component of the road-frame curvature)."""
+    Flat or 3-D tracks (kz = the z component of the road-frame curvature).  Closed laps: the closing element included; open sections:
+    the first node is given, its derivative is zero (:651-659) and the lap time is the time of the last node.
+    Returns (d laptime / dp, d/dp of dt/ds at every node of the mesh)."""
     from .problem import N_INPUTS
-    if not problem.closed:
-        raise NotImplementedError("dlaptime_dp: closed laps")
     X, DX = np.asarray(x).reshape(-1, problem.nv), np.asarray(dx).reshape(-1, problem.nv)
     iu, iv = (4, 5) if problem.model == 0 else (1, 2)
     i_n, i_a = N_INPUTS[problem.model] - 3, N_INPUTS[problem.model] - 2          # the last two inputs once the time is removed
-    nd = problem.track_nodes
+    nd = problem.track_nodes if problem.closed else problem.track_nodes[1:]
     kz = -np.sin(nd[:, 2]) * nd[:, 4] + np.cos(nd[:, 1]) * np.cos(nd[:, 2]) * nd[:, 3]
     u, v, n, a = X[:, iu], X[:, iv], X[:, i_n], X[:, i_a]
     un, r = u * np.cos(a) - v * np.sin(a), 1.0 - kz * n
     d = (-kz * DX[:, i_n] / un - np.cos(a) * r / un ** 2 * DX[:, iu] + np.sin(a) * r / un ** 2 * DX[:, iv]
          + r * (v * np.cos(a) + u * np.sin(a)) / un ** 2 * DX[:, i_a])
-    h = np.diff(np.append(problem.s, problem.track_length))
     sg = problem.sigma
-    return float(np.sum(h * ((1.0 - sg) * d + sg * np.roll(d, -1)))), d
+    if problem.closed:
+        h = np.diff(np.append(problem.s, problem.track_length))
+        return float(np.sum(h * ((1.0 - sg) * d + sg * np.roll(d, -1)))), d
+    d = np.concatenate([[0.0], d])
+    h = np.diff(problem.s)
+    return float(np.sum(h * ((1.0 - sg) * d[:-1] + sg * d[1:]))), d
 
 
 def solve_lap(problem, x_start, options=None, device=0, bounds=None, coarse_nodes=500, sequence_from=3000, verbose=False):

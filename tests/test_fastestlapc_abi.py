@@ -283,6 +283,21 @@ def test_warm_start_and_open_section_through_the_c_api(lib, files):
     assert uo[0] == q[4] and to[0] == tl[0] and lib.download_scalar(b("open/laptime")) == to[-1]
     assert 0.9 * (tl[99] - tl[0]) <= to[-1] - to[0] <= tl[99] - tl[0] + 1e-6
     assert np.max(np.abs(uo[:20] - vec("cold/chassis.velocity.x")[:20])) <= 0.5
+    # sensitivities of the open section (the reference's Catalunya_chicane case is an open section, f1_sensitivity_analysis.cpp:214-291):
+    # the given first node does not move, the derivative of the time of the last node against the section re-solved with the mass moved
+    lib.vehicle_declare_new_constant_parameter(b("car"), b("vehicle/chassis/mass"), b("mass"), c.c_double(680.0))
+    open_opts = "<closed_simulation>false</closed_simulation><initial_condition><q from_table=\"q_start\"/><u from_table=\"u_start\"/></initial_condition>"
+    assert run(open_opts + "<compute_sensitivity>true</compute_sensitivity><output_variables><prefix>os/</prefix></output_variables>", s[:100]) == ""
+    dT = lib.download_scalar(b("os/derivatives/laptime/mass"))
+    du, dt = vec("os/derivatives/chassis.velocity.x/mass", 100), vec("os/derivatives/time/mass", 100)
+    assert du[0] == 0.0 and dt[0] == 0.0 and abs(dt[-1] - dT) <= 1e-15 and dT > 0.0
+    times = {}
+    for sign in (1.0, -1.0):
+        lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/mass"), c.c_double(680.0 + sign * 0.05))
+        assert run(open_opts + "<output_variables><prefix>om/</prefix></output_variables>", s[:100]) == ""
+        times[sign] = lib.download_scalar(b("om/laptime"))
+    print("open section: d time / d mass %.8f s/kg, re-solved %.8f" % (dT, (times[1.0] - times[-1.0]) / 0.1))
+    assert abs(dT - (times[1.0] - times[-1.0]) / 0.1) <= 1.0e-6
     lib.delete_variable(b"*")
 
 
@@ -329,6 +344,8 @@ def test_sensitivities_through_the_c_api(lib, files):
     assert abs(dT["mass"] - fd_T) <= 1.0e-6
     assert np.max(np.abs(du - fd_u)) <= 1.0e-5
     assert abs(t0 - 0.5 * (laps[1.0][0] + laps[-1.0][0])) <= 1.0e-6
-    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><compute_sensitivity>true</compute_sensitivity><closed_simulation>false</closed_simulation></options>"))
-    assert err(lib) != ""
+    lib.vehicle_declare_new_variable_parameter(b("car"), b("vehicle/chassis/aerodynamics/cl"), b("cl0;cl1"), c.c_int(2), (c.c_double * 2)(3.0, 3.1), c.c_int(2),
+                                               (c.c_int * 2)(0, 1), (c.c_double * 2)(0.0, 3000.0))
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><compute_sensitivity>true</compute_sensitivity></options>"))
+    assert "constant parameters" in err(lib)
     lib.delete_variable(b"*")

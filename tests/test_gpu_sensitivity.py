@@ -80,3 +80,48 @@ def test_sensitivities_through_the_api(tmp_path):
     assert du.shape == s.shape and dt.shape == s.shape
     assert dt[0] == 0.0 and np.all(np.diff(dt) > -1e-9)      # a heavier car loses time all around the lap
     fl.delete_variable("*")
+
+
+def test_mass_sensitivity_of_an_open_section():
+    """The reference's Catalunya_chicane case (f1_sensitivity_analysis.cpp:214-291): the open section of the adapted Catalunya mesh
+    (wheel inertias 1.00 / 1.55), mass as the parameter; dx/dp and d(time of the last node)/dp against laps re-solved with the mass
+    moved by +-0.01 kg (the reference moves it by 0.01 kg and asks 1e-6)."""
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, lap_sensitivities, dlaptime_dp
+    from fastest_lap_b200.vehicle import F1_PARAM_PATHS
+    from fastest_lap_b200.api import trajectory
+    p, ex = load_golden("f1_catalunya_chicane")
+    assert not p.closed
+    col = F1_PARAM_PATHS.index("chassis/mass")
+
+    def last_node_time(q, x):
+        # time of the last node: trapezoid rule of dt/ds from the given first node (optimal_laptime.hpp:598-631)
+        first = np.concatenate([np.delete(q.q0, 11), [q.u0[0], q.u0[2]]])
+        X = np.vstack([first, x.reshape(-1, q.nv)])
+        t, lap, _, _ = trajectory(q.track_nodes, np.zeros((q.n_points, 3)), q.s, q.track_length, False, X[:, 4], X[:, 5], X[:, 11], X[:, 12])
+        return lap
+
+    def solve(q, x0):
+        nlp = CollocationNLP(q)
+        solver = LapSolver(nlp)
+        out = solver.solve(x0)
+        assert out["status"][0] == 1
+        sig = solver.sigma()
+        solver.close(); nlp.close()
+        return out, sig
+
+    base, sigma = solve(p, ex["x"])
+    x, lam = base["x"][0], base["y"][0]
+    h = 1.0e-6 * p.params[col]
+    dx, _ = lap_sensitivities(p, x, lam, sigma, [(_moved(p, col, h), _moved(p, col, -h), 2.0 * h)])
+    dT, d = dlaptime_dp(p, x, dx[0])
+    assert d[0] == 0.0 and d.shape == (p.n_points,)
+    dm = 0.01
+    xp, _ = solve(_moved(p, col, dm), x)
+    xm, _ = solve(_moved(p, col, -dm), x)
+    fd_x = (xp["x"][0] - xm["x"][0]) / (2.0 * dm)
+    fd_T = (last_node_time(_moved(p, col, dm), xp["x"][0]) - last_node_time(_moved(p, col, -dm), xm["x"][0])) / (2.0 * dm)
+    print("open section: d time / d mass %.9f s/kg (linear solve) %.9f (re-solved); max |dx/dp - difference| %.2e of %.2e" % (
+        dT, fd_T, np.max(np.abs(dx[0] - fd_x)), np.max(np.abs(dx[0]))))
+    assert abs(dT - fd_T) <= 1.0e-6
+    assert np.max(np.abs(dx[0] - fd_x)) <= 1.0e-5
