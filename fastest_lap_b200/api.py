@@ -174,7 +174,7 @@ def vehicle_declare_new_variable_parameter(vehicle_name, parameter_path, paramet
     by Model_parameter::operator()(s), model_parameter.h:51-77): optimal_laptime evaluates it at every mesh node and the kernels
     read one parameter vector per node.  (The aliases name the parameter in the reference's sensitivity analysis, not computed here.)"""
     try:
-        _get(vehicle_name, Vehicle).declare_variable_parameter(parameter_path, parameter_values, mesh_parameter_indexes, mesh_points)
+        _get(vehicle_name, Vehicle).declare_variable_parameter(parameter_path, parameter_values, mesh_parameter_indexes, mesh_points, aliases=parameter_alias)
     except (KeyError, ValueError) as e:
         raise FastestLapError("[ERROR] vehicle_declare_new_variable_parameter -> %s" % e)
 
@@ -421,10 +421,13 @@ def optimal_laptime(vehicle, track, s, options=""):
                 XU[:, col] = hi
     declared = list(getattr(veh, "declared", []))
     if o["sensitivity"]:
-        # (closed laps and open sections; not together with lap-coupling quantities or parameters that vary along the lap)
-        if p.aug or veh.has_variable_parameters():
-            raise FastestLapError("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for constant parameters, "
-                                  "without hypermesh controls or integral constraints")
+        # (closed laps and open sections; not together with lap-coupling quantities)
+        if p.aug:
+            raise FastestLapError("[ERROR] optimal_laptime -> <compute_sensitivity> is not offered together with hypermesh controls or integral constraints")
+    # the values of the parameters that vary along the lap are parameters of the analysis too, one alias each (fastestlapc.cpp:962-981)
+    declared = [(a, key, None) for a, key in declared]
+    for key, names in getattr(veh, "variable_aliases", {}).items():
+        declared += [(a, key, k) for k, a in enumerate(names)]
     nlp = CollocationNLP(p)
     solver = LapSolver(nlp, bounds=bounds)
     out = solver.solve(x0, verbose=o["print_level"] >= 5, warm=warm)
@@ -510,19 +513,26 @@ def optimal_laptime(vehicle, track, s, options=""):
         # optimised control gets its derivative)
         from .ipm import lap_sensitivities, dlaptime_dp
         perturbed = []
-        for alias, key in declared:
+        for alias, key, k_value in declared:
             col = veh.paths.index(key)
-            step = 1.0e-6 * max(abs(veh.params[col]), 1.0e-3)
+            base_value = veh.params[col] if k_value is None else veh.variable[key][0][k_value]
+            step = 1.0e-6 * max(abs(base_value), 1.0e-3)
             pm = []
             for sign in (1.0, -1.0):
                 v2 = veh.copy()
-                v2.params[col] += sign * step
+                if k_value is None:
+                    v2.params[col] += sign * step
+                else:
+                    vals, idx_m, pts_m = v2.variable[key]
+                    vals = vals.copy(); vals[k_value] += sign * step
+                    v2.variable[key] = (vals, idx_m, pts_m)
+                    v2.params[col] = vals[0]
                 pm.append(LapProblem.from_vehicle_track(v2, trk, s, form=form, closed=closed, dissipation=o["dissipation"], sigma=o["sigma"],
                                                         q0=o["q_start"], u0=o["u_start"]))
             perturbed.append((pm[0], pm[1], 2.0 * step))
         dxs, _ = lap_sensitivities(p, out["x"][0], out["y"][0], sigma, perturbed)
         h_el = np.diff(np.append(s, trk.track_length)) if closed else np.append(np.diff(s), 0.0)
-        for (alias, _), dx in zip(declared, dxs):
+        for (alias, _, _), dx in zip(declared, dxs):
             dT, d = dlaptime_dp(p, out["x"][0], dx)
             DX = dx.reshape(-1, p.nv)
             if not closed:

@@ -192,7 +192,7 @@ static const char* KART_CONTROLS[] = { "front-axle.steering-angle", "rear-axle.t
 static const char* OUTPUTS[] = { "laptime", "x", "y", "psi" };
 static const char* KEY_NAME = "road.arclength";
 
-struct VarParam { vec values; std::vector<int> idx; vec pts; };
+struct VarParam { vec values; std::vector<int> idx; vec pts; std::vector<string> aliases; };      // aliases: one per value, or none
 
 struct Vehicle
 {
@@ -571,8 +571,13 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     if (o.save_warm_start && (!o.closed || o.aug_kind != FL_AUG_NONE))
         throw error("[ERROR] optimal_laptime -> <save_warm_start> of open simulations / with hypermesh controls or integral constraints is not supported");
     if (!o.closed && o.aug_kind != FL_AUG_NONE) throw error("[ERROR] optimal_laptime -> hypermesh controls and integral constraints need a closed simulation");
-    if (o.sensitivity && (o.aug_kind != FL_AUG_NONE || !veh.variable.empty()))
-        throw error("[ERROR] optimal_laptime -> <compute_sensitivity> is offered for constant parameters, without hypermesh controls or integral constraints");
+    if (o.sensitivity && o.aug_kind != FL_AUG_NONE)
+        throw error("[ERROR] optimal_laptime -> <compute_sensitivity> is not offered together with hypermesh controls or integral constraints");
+    // what the analysis differentiates by: the declared constants, and every value of the parameters that vary along the lap (one alias each)
+    struct SensPar { string alias; int slot; int value; };          // value < 0: a constant
+    std::vector<SensPar> sens;
+    for (auto& dpar : veh.declared) sens.push_back({ dpar.first, dpar.second, -1 });
+    for (auto& kv : veh.variable) for (size_t k = 0; k < kv.second.aliases.size(); ++k) sens.push_back({ kv.second.aliases[k], kv.first, (int)k });
     const vec s = o.warm_start ? ws.s : s_in;
     const int np = (int)s.size();
     if (np < 2) throw error("[ERROR] optimal_laptime -> provide at least two values of arclength");
@@ -666,7 +671,7 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         if (o.warm_start) ok = fl_ipm_solve_warm(ipm, ws.x.data(), ws.lam.data(), ws.zl.data(), ws.zu.data(), 1.0e-3, 1.0e-4, o.print_level >= 5 ? 1 : 0);
         else ok = fl_ipm_solve(ipm, x0.data(), o.print_level >= 5 ? 1 : 0);
         if (!ok || !fl_ipm_results(ipm, X.data(), Ylam.data(), Zl.data(), Zu.data(), &obj, status.data(), iters.data(), nullptr)) msg = fl_error();
-        if (msg.empty() && status[0] >= 1 && o.sensitivity && !veh.declared.empty())
+        if (msg.empty() && status[0] >= 1 && o.sensitivity && !sens.empty())
         {
             // barrier terms of the solution, with the solver's own bounds and slacks: the KKT matrix the sensitivities are solved with
             sigx.resize(n); sigs.resize((size_t)(o.closed ? np : np - 1) * 6);
@@ -700,19 +705,26 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
         std::vector<int> jr(nnzj), jc(nnzj), hr(nnzh), hc(nnzh);
         fl_ipm* ipm = fl_ipm_create(nlp, nullptr, nullptr, nullptr, nullptr, nullptr);
         if (!ipm || !fl_nlp_structure(nlp, jr.data(), jc.data(), hr.data(), hc.data())) msg = fl_error();
-        for (size_t q = 0; msg.empty() && q < veh.declared.size(); ++q)
+        for (size_t q = 0; msg.empty() && q < sens.size(); ++q)
         {
-            const int slot = veh.declared[q].second;
-            const double step = 1.0e-6 * std::max(std::fabs(v0.params[slot]), 1.0e-3);
+            const int slot = sens[q].slot;
+            const double base_value = sens[q].value < 0 ? v0.params[slot] : veh.variable.at(slot).values[sens[q].value];
+            const double step = 1.0e-6 * std::max(std::fabs(base_value), 1.0e-3);
             vec gl[2], gv[2];
             for (int side = 0; side < 2 && msg.empty(); ++side)
             {
-                vec pp = v0.params;
-                pp[slot] += side == 0 ? step : -step;
+                Vehicle v2 = veh;
+                if (sens[q].value < 0) v2.params[slot] += side == 0 ? step : -step;
+                else v2.variable[slot].values[sens[q].value] += side == 0 ? step : -step;
+                vec np2;
+                if (!v2.variable.empty())
+                    for (int i = 0; i < np; ++i) { const vec pi = v2.params_at(s[i]); np2.insert(np2.end(), pi.begin(), pi.end()); }
+                vec pp = v2.variable.empty() ? v2.params : v2.params_at(s[0]);
                 vec cd = ctrl_default;
                 if (f1) cd[3] = pp[18];
                 fl_problem_desc d2 = d;
                 d2.vehicle_params = pp.data(); d2.ctrl_default = cd.data();
+                d2.node_params = np2.empty() ? nullptr : np2.data();
                 fl_nlp* h2 = fl_nlp_create(&d2);
                 if (!h2) { msg = fl_error(); break; }
                 vec g(m), grad(n), jac(nnzj);
@@ -825,7 +837,7 @@ static void do_optimal_laptime(const string& vname, const string& tname, const v
     // gets its derivative); the lap time's by the trapezoid rule over d/dp of dt/ds (optimal_laptime.hpp:664-724)
     for (size_t q = 0; q < dx_dp.size(); ++q)
     {
-        const string& alias = veh.declared[q].first;
+        const string& alias = sens[q].alias;
         vec dx = dx_dp[q];
         if (!o.closed) dx.insert(dx.begin(), (size_t)NVo, 0.0);          // the given first node does not move (optimal_laptime.hpp:651-659)
         vec d2(np), dtime(np, 0.0);
@@ -1251,7 +1263,7 @@ void vehicle_declare_new_constant_parameter(const char* name, const char* path, 
     FLC_CATCH()
 }
 
-void vehicle_declare_new_variable_parameter(const char* name, const char* path, const char*, const int n_parameters, const double* values,
+void vehicle_declare_new_variable_parameter(const char* name, const char* path, const char* aliases, const int n_parameters, const double* values,
                                             const int mesh_size, const int* mesh_indexes, const double* mesh_points)
 {
     FLC_TRY
@@ -1265,6 +1277,19 @@ void vehicle_declare_new_variable_parameter(const char* name, const char* path, 
     p.pts.assign(mesh_points, mesh_points + mesh_size);
     for (int i : p.idx) if (i < 0 || i >= n_parameters) throw flc::error("mesh indexes must address the parameter values");
     if (!std::is_sorted(p.pts.begin(), p.pts.end())) throw flc::error("mesh points must be sorted");
+    // "a; b; c": one alias per value (fastestlapc.cpp:962-969), the names of the derivatives of <compute_sensitivity>
+    if (aliases && *aliases)
+    {
+        std::string rest = aliases;
+        for (;;)
+        {
+            const size_t semi = rest.find(';');
+            p.aliases.push_back(flc::trim(rest.substr(0, semi)));
+            if (semi == std::string::npos) break;
+            rest = rest.substr(semi + 1);
+        }
+        if ((int)p.aliases.size() != n_parameters) throw flc::error("vehicle_declare_new_variable_parameter -> one alias per parameter value");
+    }
     v.variable[k] = p;
     v.params[k] = p.values.front();
     FLC_CATCH()

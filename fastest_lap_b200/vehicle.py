@@ -76,6 +76,7 @@ class Vehicle:
         v.wind = list(self.wind)
         v.variable = {k: tuple(np.array(a) for a in val) for k, val in getattr(self, "variable", {}).items()}
         v.declared = list(getattr(self, "declared", []))
+        v.variable_aliases = {k: list(a) for k, a in getattr(self, "variable_aliases", {}).items()}
         return v
 
     def declare_parameter(self, path, alias, value):
@@ -92,7 +93,7 @@ class Vehicle:
             raise KeyError('Parameter alias "%s" already declared' % alias)
         self.declared.append((alias, key))
 
-    def declare_variable_parameter(self, path, values, mesh_indexes, mesh_points):
+    def declare_variable_parameter(self, path, values, mesh_indexes, mesh_points, aliases=None):
         """A parameter that varies with the arclength (vehicle_declare_new_variable_parameter, fastestlapc.cpp:941-981;
         Model_parameter, src/core/foundation/model_parameter.h:18-77): `values` and a mesh of (arclength, index into values)
         pairs, blended piecewise linearly between consecutive mesh points."""
@@ -108,6 +109,14 @@ class Vehicle:
             self.variable = {}
         self.variable[key] = (values, idx, pts)
         self.params[self.paths.index(key)] = values[0]
+        # one alias per value ("a; b; c" in the reference, fastestlapc.cpp:962-969): the names of the derivatives of the sensitivity analysis
+        if not hasattr(self, "variable_aliases"):
+            self.variable_aliases = {}
+        if aliases is not None:
+            names = [a.strip() for a in aliases.split(";")] if isinstance(aliases, str) else [str(a).strip() for a in aliases]
+            if len(names) != len(values):
+                raise ValueError("one alias per parameter value (got %d for %d values)" % (len(names), len(values)))
+            self.variable_aliases[key] = names
 
     def has_variable_parameters(self):
         return bool(getattr(self, "variable", {}))

@@ -346,6 +346,14 @@ def test_sensitivities_through_the_c_api(lib, files):
     assert abs(t0 - 0.5 * (laps[1.0][0] + laps[-1.0][0])) <= 1.0e-6
     lib.vehicle_declare_new_variable_parameter(b("car"), b("vehicle/chassis/aerodynamics/cl"), b("cl0;cl1"), c.c_int(2), (c.c_double * 2)(3.0, 3.1), c.c_int(2),
                                                (c.c_int * 2)(0, 1), (c.c_double * 2)(0.0, 3000.0))
-    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><compute_sensitivity>true</compute_sensitivity></options>"))
-    assert "constant parameters" in err(lib)
+    # the values of a parameter that varies along the lap are parameters of the analysis too, one alias each (fastestlapc.cpp:962-981)
+    lib.vehicle_set_parameter(b("car"), b("vehicle/chassis/mass"), c.c_double(660.0))
+    lib.optimal_laptime(b("car"), b("catalunya"), c.c_int(len(s)), c_s, b("<options><compute_sensitivity>true</compute_sensitivity><output_variables><prefix>var/</prefix></output_variables></options>"))
+    assert err(lib) == ""
+    dcl = [lib.download_scalar(b("var/derivatives/laptime/cl%d" % k)) for k in range(2)]
+    print("d laptime / d cl0 %.6f, / d cl1 %.6f s" % tuple(dcl))
+    assert err(lib) == "" and dcl[0] < 0.0 and dcl[1] < 0.0          # more downforce, shorter lap
+    lib.vehicle_declare_new_variable_parameter(b("car"), b("vehicle/chassis/aerodynamics/cl"), b("only_one"), c.c_int(2), (c.c_double * 2)(3.0, 3.1), c.c_int(2),
+                                               (c.c_int * 2)(0, 1), (c.c_double * 2)(0.0, 3000.0))
+    assert "one alias per parameter value" in err(lib)
     lib.delete_variable(b"*")

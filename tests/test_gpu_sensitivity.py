@@ -125,3 +125,38 @@ def test_mass_sensitivity_of_an_open_section():
         dT, fd_T, np.max(np.abs(dx[0] - fd_x)), np.max(np.abs(dx[0]))))
     assert abs(dT - fd_T) <= 1.0e-6
     assert np.max(np.abs(dx[0] - fd_x)) <= 1.0e-5
+
+
+def test_sensitivity_to_the_values_of_a_parameter_that_varies_along_the_lap(tmp_path):
+    """A mass declared as a piecewise-linear function of the arclength (vehicle_declare_new_variable_parameter, aliases "m0;m1"): the
+    lap time's derivative with respect to each of its two values, against laps re-solved with that value moved."""
+    from fastest_lap_b200 import api as fl, workloads
+    from fastest_lap_b200.track import track_from_npz
+    from tests.test_gpu_api import _write_xml_fixtures
+    paths = _write_xml_fixtures(tmp_path)
+    fl.delete_variable("*")
+    fl.create_vehicle_from_xml("car", paths["f1"])
+    fl._table["catalunya"] = track_from_npz(os.path.join(os.path.dirname(workloads.__file__), "data", "catalunya.npz"), "catalunya")
+    L = fl.track_download_length("catalunya")
+    s = np.linspace(0.0, L, 501)[:-1]
+
+    def declare(m0, m1):
+        fl.vehicle_declare_new_variable_parameter("car", "vehicle/chassis/mass", "m0; m1", [m0, m1], [0, 1], [0.0, 0.9 * L])
+    declare(660.0, 670.0)
+    fl.optimal_laptime("car", "catalunya", s, "<options><compute_sensitivity>true</compute_sensitivity><output_variables><prefix>run/</prefix></output_variables></options>")
+    d0, d1 = fl.download_scalar("run/derivatives/laptime/m0"), fl.download_scalar("run/derivatives/laptime/m1")
+    fd = []
+    for k in range(2):
+        t = []
+        for sign in (1.0, -1.0):
+            m = [660.0, 670.0]; m[k] += sign * 0.05
+            declare(*m)
+            fl.optimal_laptime("car", "catalunya", s, "<options><output_variables><prefix>moved/</prefix></output_variables></options>")
+            t.append(fl.download_scalar("moved/laptime"))
+        fd.append((t[0] - t[1]) / 0.1)
+    print("d laptime / d m0 %.8f (re-solved %.8f), / d m1 %.8f (re-solved %.8f) s/kg" % (d0, fd[0], d1, fd[1]))
+    assert d0 > 0.0 and d1 > 0.0
+    assert abs(d0 - fd[0]) <= 1e-6 and abs(d1 - fd[1]) <= 1e-6
+    # the two values share the lap: together they weigh what a constant mass does (0.0395 s/kg on this lap)
+    assert abs(d0 + d1 - 0.0395) <= 2e-3
+    fl.delete_variable("*")
