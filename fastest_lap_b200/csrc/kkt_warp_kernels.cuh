@@ -717,6 +717,12 @@ __global__ void __launch_bounds__(32, FL_KW_MINB) k_kkt_factor_w(const fl_kkt_de
 #ifndef FL_KWS_MINB
 #define FL_KWS_MINB 1
 #endif
+// stages ahead of which the solve kernel asks the L2 for a stage's factor blocks (0: off).  The kernel streams 4.3 KB per stage and lap
+// and waits for it (9.8 long-scoreboard stall cycles per issue, profiles/prof_r2w_kkt_solve_w): the register prefetch one stage ahead then
+// finds its lines in L2 instead of DRAM.
+#ifndef FL_KWS_PREFETCH
+#define FL_KWS_PREFETCH 3
+#endif
 template <int NV, int NEQ>
 __global__ void __launch_bounds__(32, FL_KWS_MINB) k_kkt_solve_w(const fl_kkt_dev K, const double* __restrict__ r1, const double* __restrict__ r2,
                                                      double* __restrict__ dx, double* __restrict__ dy)
@@ -770,6 +776,16 @@ __global__ void __launch_bounds__(32, FL_KWS_MINB) k_kkt_solve_w(const fl_kkt_de
         return a0 + a1;
     };
 
+    auto prefetch_stage = [&](int j) {
+        if (j < 0 || j >= S) return;
+        auto lines = [&](const double* base, int bytes) {
+            const char* p0 = reinterpret_cast<const char*>(base);
+            for (int o = lane * 128; o < bytes + 127; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(p0 + (o < bytes ? o : bytes - 1)));
+        };
+        lines(gD + (size_t)j * NB * NB, NB * NB * 8);
+        lines(gL + (size_t)j * NB * NV, (NEQ + 1) * LDV * 8);
+        if (cyc && j >= 2) lines(gF + (size_t)j * NB * NB, NV * FT * 8);
+    };
     // ---- forward: y_j = Dinv_j b_j,  b_{j-1} -= L_j^T y_j,  b_0 -= F_j y_j
     double carry = 0.0;            // lanes < NV
     double b0c = 0.0;              // lanes < NF: compact rows of the update of stage 0
@@ -779,6 +795,9 @@ __global__ void __launch_bounds__(32, FL_KWS_MINB) k_kkt_solve_w(const fl_kkt_de
     for (int j = S - 1; j >= 1; --j)
     {
         const bool chain = j >= 2 || !cyc;
+#if FL_KWS_PREFETCH > 0
+        prefetch_stage(j - 1 - FL_KWS_PREFETCH);
+#endif
         vb[lane] = (lane < NB) ? rhs(j) + carry : 0.0;
         // operands of this stage's updates, and the next stage's D^-1 row, in flight while the product is reduced
         double lcol[NEQ + 1];
@@ -869,6 +888,9 @@ __global__ void __launch_bounds__(32, FL_KWS_MINB) k_kkt_solve_w(const fl_kkt_de
     for (int j = 1; j < S; ++j)
     {
         const bool chain = j >= 2 || !cyc;
+#if FL_KWS_PREFETCH > 0
+        prefetch_stage(j + 1 + FL_KWS_PREFETCH);
+#endif
         // t = L_j z_{j-1} + F_j^T z_0
         double t = 0.0;
         if (chain)
