@@ -82,7 +82,27 @@ template <int NV, int NEQ> void launch_factor(fl_ipm* s, const fl_kkt_dev& K)
 template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, const double* r1, const double* r2, double* dx, double* dy)
 {
     const int nb = K.lap_list ? s->n_list : s->B;
-    if (s->warp_kkt && !K.sep) k_kkt_solve_w<NV, NEQ><<<nb, 32, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
+    if (s->warp_kkt && !K.sep)
+    {
+        // the ring version (factor blocks through shared memory by bulk asynchronous copies) where the stage's blocks are multiples of
+        // 16 bytes; FL_KWS_RING=0 keeps the register-prefetch kernel (comparison runs)
+        static const bool ring = !(std::getenv("FL_KWS_RING") && std::atoi(std::getenv("FL_KWS_RING")) == 0);
+        if constexpr (kws_ring<NV, NEQ>::ok)
+        {
+            if (ring)
+            {
+                static unsigned long long attr_set = 0;          // per device
+                if (!((attr_set >> s->nlp->device) & 1ull))
+                {
+                    cudaFuncSetAttribute(k_kkt_solve_w2<NV, NEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kws_ring<NV, NEQ>::bytes);
+                    attr_set |= 1ull << s->nlp->device;
+                }
+                k_kkt_solve_w2<NV, NEQ><<<nb, 32, kws_ring<NV, NEQ>::bytes, s->nlp->stream>>>(K, r1, r2, dx, dy);
+                return;
+            }
+        }
+        k_kkt_solve_w<NV, NEQ><<<nb, 32, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
+    }
     else k_kkt_solve<NV, NEQ><<<nb, KT, 0, s->nlp->stream>>>(K, r1, r2, dx, dy);
 }
 

@@ -947,3 +947,264 @@ __global__ void __launch_bounds__(32, FL_KWS_MINB) k_kkt_solve_w(const fl_kkt_de
         __syncwarp();
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same solve with the factor blocks of a stage (D^-1, compact coupling rows, compact fill) brought into a ring of shared-memory
+// slots by bulk asynchronous copies (cp.async.bulk, the 1-D TMA path; completion on one mbarrier per slot), FL_KWS_SLOTS - 1 stages
+// ahead of their use, instead of the register prefetch of ONE stage: the kernel waits for its own streaming loads (9.8 long-scoreboard
+// stall cycles per issue, profiles/prof_r2w_kkt_solve_w), so what counts is the bytes in flight per SM.  For stage sizes whose blocks
+// are multiples of 16 bytes (NB even); the arithmetic and its order are those of k_kkt_solve_w.
+// slots of the ring.  Measured on a 4096-lap, 40-iteration solve (solve phase; k_kkt_solve_w with its register prefetch: 937 ms):
+// 2 slots (20 KB per lap, 11 laps per SM) 643 ms, 3 slots (7 per SM) 707-717 ms, 4 slots (5 per SM) 883 ms
+#ifndef FL_KWS_SLOTS
+#define FL_KWS_SLOTS 2
+#endif
+template <int NV, int NEQ> struct kws_ring
+{
+    static constexpr int NB = NV + NEQ, LDV = kw_stage<NV, NEQ>::LDV, FT = kw_stage<NV, NEQ>::FT;
+    static constexpr int DB = NB * NB, LB = (NEQ + 1) * LDV, FB = NV * FT, SLOT = DB + LB + FB;      // doubles
+    static constexpr bool ok = (DB % 2 == 0) && (LB % 2 == 0) && (FB % 2 == 0) && ((NB * NV) % 2 == 0);
+    static constexpr size_t bytes = (size_t)FL_KWS_SLOTS * SLOT * 8 + FL_KWS_SLOTS * 8 + (32 + 32 + 32 + 16) * 8;
+};
+
+template <int NV, int NEQ>
+__global__ void __launch_bounds__(32) k_kkt_solve_w2(const fl_kkt_dev K, const double* __restrict__ r1, const double* __restrict__ r2,
+                                                     double* __restrict__ dx, double* __restrict__ dy)
+{
+    using St = kw_stage<NV, NEQ>;
+    using R = kws_ring<NV, NEQ>;
+    constexpr int NB = St::NB, LDV = St::LDV, FT = St::FT, NVP = St::NVP, NS = FL_KWS_SLOTS;
+    constexpr int NBP = (NB + 1) / 2;
+    extern __shared__ __align__(128) unsigned char kws_raw[];
+    double* const ring = reinterpret_cast<double*>(kws_raw);
+    double* const vb = ring + (size_t)NS * R::SLOT;          // (16-byte aligned: read as double2)
+    double* const vy = vb + 32;
+    double* const z0 = vy + 32;
+    double* const z0c = z0 + 32;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(z0c + 16);
+    const int lap = K.lap_list ? K.lap_list[blockIdx.x] : blockIdx.x, lane = threadIdx.x;
+    if (K.active && !K.active[lap]) return;
+    if (K.laps && K.laps[lap].status != IPM_RUNNING) return;
+    const int S = K.S;
+    const bool cyc = K.closed && S > 2;
+    const int ncpl = K.ls_mode ? 0 : K.NCPL;
+    const int NF = NEQ + ncpl;
+    const double* gD = K.Dinv + (size_t)lap * S * NB * NB;
+    const double* gF = K.F ? K.F + (size_t)lap * S * NB * NB : nullptr;
+    const double* gL = K.Lst + (size_t)lap * S * NB * NV;
+    const double* gA = K.Aq + (size_t)lap * S * (K.NINEQ * (NV + 1));
+    double* yw = K.ywork + (size_t)lap * S * NB;
+    r1 += (size_t)lap * K.n; r2 += (size_t)lap * K.m; dx += (size_t)lap * K.n; dy += (size_t)lap * K.m;
+    const int AQ = K.NINEQ * (NV + 1);
+    const bool haveF = cyc && gF != nullptr;
+
+    // ---- the ring ------------------------------------------------------------------------------------------------------
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);
+    if (lane == 0)
+    {
+        for (int k = 0; k < NS; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8 * k));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phase = 0u;                                   // bit k: parity the next wait on slot k expects
+    auto issue = [&](int j, int slot) {                    // (lane 0) stage j's blocks -> slot
+        if (lane != 0) return;
+        const unsigned bar = bar0 + 8 * slot;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (size_t)slot * R::SLOT);
+        const unsigned bytes = (unsigned)((R::DB + R::LB + (haveF ? R::FB : 0)) * 8);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the slot's last readers (generic proxy) come first
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(gD + (size_t)j * NB * NB), "r"((unsigned)(R::DB * 8)), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst + R::DB * 8), "l"(gL + (size_t)j * NB * NV), "r"((unsigned)(R::LB * 8)), "r"(bar) : "memory");
+        if (haveF)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst + (R::DB + R::LB) * 8), "l"(gF + (size_t)j * NB * NB), "r"((unsigned)(R::FB * 8)), "r"(bar) : "memory");
+    };
+    auto wait = [&](int slot) {
+        const unsigned bar = bar0 + 8 * slot, par = (phase >> slot) & 1u;
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(par) : "memory");
+        phase ^= 1u << slot;
+    };
+
+    // condensed right-hand side of stage j (before the updates from later stages); lanes < NB
+    auto rhs = [&](int j) -> double {
+        const int e = St::e_in(K, j);
+        double b = 0.0;
+        if (lane < NV)
+        {
+            b = r1[(size_t)j * NV + lane];
+            for (int q = 0; q < K.NINEQ; ++q)
+                b += gA[(size_t)j * AQ + q * NV + lane] * gA[(size_t)j * AQ + K.NINEQ * NV + q] * r2[(size_t)e * K.NCPE + K.t.ineq_rows[q]];
+        }
+        else if (lane < NB) b = r2[(size_t)e * K.NCPE + K.t.eq_rows[lane - NV]];
+        return b;
+    };
+    // y = D^-1 v: row `lane` of D^-1 from the slot (or from global memory: stage 0), v in shared memory (broadcast reads); the same two
+    // accumulation chains as k_kkt_solve_w
+    auto matvec = [&](const double* D, const double* v) -> double {
+        double a0 = 0.0, a1 = 0.0;
+        if (lane < NB)
+        {
+#pragma unroll
+            for (int i = 0; i < NBP; ++i)
+            {
+                const double2 vv = reinterpret_cast<const double2*>(v)[i];
+                a0 = fma(D[lane + NB * (2 * i)], vv.x, a0);
+                if (2 * i + 1 < NB) a1 = fma(D[lane + NB * (2 * i + 1)], vv.y, a1);
+            }
+        }
+        return a0 + a1;
+    };
+
+    // ---- forward: y_j = Dinv_j b_j,  b_{j-1} -= L_j^T y_j,  b_0 -= F_j y_j
+    double carry = 0.0;            // lanes < NV
+    double b0c = 0.0;              // lanes < NF: compact rows of the update of stage 0
+    double b0f = 0.0;              // lanes < NB: full update of stage 0 (stage 1 of closed laps)
+    for (int i = 0; i < NS && S - 1 - i >= 1; ++i) issue(S - 1 - i, i);
+    for (int j = S - 1; j >= 1; --j)
+    {
+        const int slot = (S - 1 - j) % NS;
+        const double* sD = ring + (size_t)slot * R::SLOT;
+        const double* sL = sD + R::DB;
+        const double* sF = sL + R::LB;
+        const bool chain = j >= 2 || !cyc;
+        vb[lane] = (lane < NB) ? rhs(j) + carry : 0.0;
+        wait(slot);
+        __syncwarp();
+        const double y = matvec(sD, vb);
+        __syncwarp();
+        vy[lane] = y;
+        if (lane < NB) yw[(size_t)j * NB + lane] = y;
+        __syncwarp();
+        if (chain)
+        {
+            double s = 0.0;
+            if (lane < NV)
+            {
+#pragma unroll
+                for (int q = 0; q < NEQ; ++q) s = fma(sL[q * LDV + lane], vy[NV + q], s);
+                if (ncpl > 0 && lane >= NV - 2) s = fma(sL[NEQ * LDV + (lane - (NV - 2))], y, s);      // control coupling (cp, cp): own entry of y
+            }
+            carry = (lane < NV) ? -s : 0.0;
+        }
+        else carry = 0.0;
+        if (cyc)
+        {
+            if (j >= 2)
+            {
+                double s = 0.0;
+                if (lane < 16)
+                {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) s = fma(sF[k * FT + lane], vy[k], s);
+                }
+                b0c -= s;
+            }
+            else
+            {
+                double s = 0.0;
+                if (lane < NB)
+                    for (int k = 0; k < NB; ++k) s = fma(gF[(size_t)NB * NB + lane + NB * k], vy[k], s);
+                b0f -= s;
+            }
+        }
+        __syncwarp();
+        if (j - NS >= 1) issue(j - NS, slot);
+    }
+    {
+        // stage 0: the compact rows of the fill updates go to their rows
+        vb[lane] = 0.0;
+        __syncwarp();
+        if (cyc && lane < NF) vb[St::frow(lane)] = b0c;
+        __syncwarp();
+        const double b = (lane < NB) ? rhs(0) + carry + b0f + vb[lane] : 0.0;
+        __syncwarp();
+        vb[lane] = b;
+        __syncwarp();
+        const double z = matvec(gD, vb);
+        __syncwarp();
+        z0[lane] = z; vy[lane] = z;
+        if (lane < NB) yw[lane] = z;
+        __syncwarp();
+        if (lane < 16) z0c[lane] = (lane < NF) ? z0[St::frow(lane)] : 0.0;
+        __syncwarp();
+    }
+    // ---- backward: z_j = y_j - Dinv_j (L_j z_{j-1} + F_j^T z_0); vy holds z_{j-1}
+    auto scatter = [&](int j, double z) {
+        // dx, equality multipliers, then the condensed inequality multipliers dy_q = (a_q . dx_j - r2_q) / D_q (vy holds z_j)
+        const int e = St::e_in(K, j);
+        if (lane < NV) dx[(size_t)j * NV + lane] = z;
+        else if (lane < NB) dy[(size_t)e * K.NCPE + K.t.eq_rows[lane - NV]] = z;
+        if (lane < K.NINEQ)
+        {
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) a = fma(gA[(size_t)j * AQ + lane * NV + c], vy[c], a);
+            const int row = e * K.NCPE + K.t.ineq_rows[lane];
+            dy[row] = (a - r2[row]) * gA[(size_t)j * AQ + K.NINEQ * NV + lane];
+        }
+    };
+    scatter(0, vy[lane]);
+    for (int i = 0; i < NS && 1 + i < S; ++i) issue(1 + i, i);
+    for (int j = 1; j < S; ++j)
+    {
+        const int slot = (j - 1) % NS;
+        const double* sD = ring + (size_t)slot * R::SLOT;
+        const double* sL = sD + R::DB;
+        const double* sF = sL + R::LB;
+        const bool chain = j >= 2 || !cyc;
+        const double yj = (lane < NB) ? yw[(size_t)j * NB + lane] : 0.0;
+        wait(slot);
+        // t = L_j z_{j-1} + F_j^T z_0
+        double t = 0.0;
+        if (chain)
+        {
+            if (lane >= NV && lane < NB)
+            {
+                const double* lr = sL + (lane - NV) * LDV;
+#pragma unroll
+                for (int i = 0; i < NVP; ++i)
+                {
+                    const double2 lv = reinterpret_cast<const double2*>(lr)[i];
+                    t = fma(lv.x, vy[2 * i], t);
+                    if (2 * i + 1 < NV) t = fma(lv.y, vy[2 * i + 1], t);
+                }
+            }
+            else if (ncpl > 0 && lane >= NV - 2 && lane < NV)
+                t = sL[NEQ * LDV + (lane - (NV - 2))] * vy[lane];
+        }
+        if (cyc)
+        {
+            if (j >= 2)
+            {
+                if (lane < NV)
+                {
+                    const double* fr = sF + lane * FT;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                    {
+                        const double2 fv = reinterpret_cast<const double2*>(fr)[i];
+                        t = fma(fv.x, z0c[2 * i], t);
+                        t = fma(fv.y, z0c[2 * i + 1], t);
+                    }
+                }
+            }
+            else if (lane < NB)
+                for (int k = 0; k < NB; ++k) t = fma(gF[(size_t)NB * NB + k + NB * lane], z0[k], t);
+        }
+        __syncwarp();
+        vb[lane] = t;
+        __syncwarp();
+        const double z = yj - matvec(sD, vb);
+        __syncwarp();
+        vy[lane] = z;
+        __syncwarp();
+        scatter(j, z);
+        __syncwarp();
+        if (j + NS < S) issue(j + NS, slot);
+    }
+}
