@@ -95,6 +95,8 @@ template <int NV, int NEQ> void launch_solve(fl_ipm* s, const fl_kkt_dev& K, con
                 if (!((attr_set >> s->nlp->device) & 1ull))
                 {
                     cudaFuncSetAttribute(k_kkt_solve_w2<NV, NEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kws_ring<NV, NEQ>::bytes);
+                    // (the largest shared-memory carve-out, so that the ring, not the default L1 / shared split, decides the laps per SM)
+                    cudaFuncSetAttribute(k_kkt_solve_w2<NV, NEQ>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
                     attr_set |= 1ull << s->nlp->device;
                 }
                 k_kkt_solve_w2<NV, NEQ><<<nb, 32, kws_ring<NV, NEQ>::bytes, s->nlp->stream>>>(K, r1, r2, dx, dy);
