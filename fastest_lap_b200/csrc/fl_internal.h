@@ -12,7 +12,7 @@ void fl_set_error(const std::string& msg);
 // Device memory of the handles goes through a small per-device cache of freed blocks (exact size match): a G-G diagram creates and
 // destroys a dozen handles of the same few sizes, and cudaMalloc / cudaFree are synchronising calls whose cost on a shared box varied
 // from 1 ms to half a second per handle (profiles/README.md).  Blocks return to the driver when the cache holds more than
-// FL_CACHE_BYTES (default 8 GB) or when an allocation fails (cache released, allocation retried).  fl_release_cached_memory() empties it.
+// FL_CACHE_BYTES (default 64 GB) or when an allocation fails (cache released, allocation retried).  fl_release_cached_memory() empties it.
 cudaError_t fl_dev_malloc(void** p, size_t bytes);
 void fl_dev_free(void* p);
 extern "C" void fl_release_cached_memory(void);

@@ -122,7 +122,7 @@ int fl_nlp_structure(const fl_nlp* nlp, int* jac_row, int* jac_col, int* hess_ro
 void fl_nlp_workspace_slots(const fl_nlp* nlp, int* n_values, int* n_checkpoints);
 
 /* Device memory of destroyed handles is kept in a per-device cache of blocks (exact-size reuse by the next handles; at most FL_CACHE_BYTES,
- * default 8 GB, blocks above a quarter of that are returned at once; released and retried when an allocation fails).  This empties it. */
+ * default 64 GB, blocks above half of that are returned at once; released and retried when an allocation fails).  This empties it. */
 void fl_release_cached_memory(void);
 
 /* Output channels of the vehicle model along the lap -- what the reference evaluates with get_outputs_map() after a solve
